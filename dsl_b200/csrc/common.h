@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error text, CUDA error checks,
+// and TMA tensor-map encoding through the driver entry point (so libdslb.so has no link-time dependency on
+// libcuda.so and loads on a GPU-less build box).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dslb.h"
+
+namespace dslb {
+
+void set_error(const char* fmt, ...);
+
+#define DSLB_CHECK_ARG(cond, ...)  \
+  do {                             \
+    if (!(cond)) {                 \
+      dslb::set_error(__VA_ARGS__); \
+      return DSLB_EINVAL;          \
+    }                              \
+  } while (0)
+
+#define DSLB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      dslb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+      return DSLB_ECUDA;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+int num_sms();
+
+// bf16 tiled tensor map (rank 2..4), 128B swizzle. dims/strides innermost first; strides in bytes for dims 1..
+int encode_tiled_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box);
+// bf16 im2col tensor map on an NHWC tensor [N][H][W][C]: 64 channels x `pixels` output pixels per load.
+int encode_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
+                       int pad, int pixels);
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace dslb

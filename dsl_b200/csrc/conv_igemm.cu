@@ -1,0 +1,484 @@
+// Implicit-GEMM convolution for sm_100a: NHWC bf16 activations, fp32 accumulation in TMEM.
+//
+//   GEMM view     M = N*Ho*Wo output pixels (tiles of 128 consecutive pixels), N = Cout (tiles of <=256),
+//                 K = R*S*Cin walked as (tap, 64-channel chunk).
+//   A operand     im2col-mode TMA: one cp.async.bulk.tensor.4d...im2col per (tap, chunk) lands a 128-pixel x
+//                 64-channel K-major tile (128B swizzle) in shared memory; the conv halo / stride / image
+//                 wrap-around is done by the TMA unit (OOB -> 0), there is no materialised im2col.
+//   B operand     tiled TMA on the packed weights [tap][Cout_pad][Cin].
+//   MMA           tcgen05.mma.cta_group::1.kind::f16, M=128, N=bn, K=16, issued by one elected thread;
+//                 accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+//                 the MMAs of tile i+1.
+//   Warp roles    warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+//                 (tcgen05.ld 32x32b -> scale/shift/residual/ReLU/mask/GroupNorm statistics -> global).
+//   Scheduling    persistent: grid = min(#tiles, #SMs), static round-robin over the tile list of up to
+//                 DSLB_MAX_SEGS independent convs (e.g. 5 FPN levels x 2 FCOSHead towers in one launch).
+#include <new>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dslb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
+constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KiB
+constexpr int BAR_BYTES = 256;
+constexpr int CONV_SMEM = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + BAR_BYTES;
+constexpr int TMEM_COLS = 512;
+
+struct alignas(128) ConvSegDev {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  void* y;
+  const void* residual;
+  const void* relu_mask;
+  const float* scale;
+  const float* shift;
+  double* stats;
+  int npix, HoWo, Wo;
+  int m_tiles, n_tiles, tile_begin;
+  int cin_chunks, taps, S, stride, pad;
+  int cout, bn, ldc;
+  int out_fp32, relu_nch, cpg, groups;
+  int scatter2, Hs, Ws;
+};
+
+struct alignas(128) ConvParamsDev {
+  ConvSegDev seg[DSLB_MAX_SEGS];
+  int nseg;
+  int total_tiles;
+};
+
+__device__ __forceinline__ int find_seg(const ConvParamsDev* P, int tile) {
+  int si = 0;
+  const int nseg = P->nseg;
+  while (si + 1 < nseg && tile >= P->seg[si + 1].tile_begin) ++si;
+  return si;
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev* __restrict__ P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES_MAX));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = P->total_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+        const int tl = tile - sg.tile_begin;
+        const int nt = tl / sg.m_tiles;
+        const int mt = tl - nt * sg.m_tiles;
+        const int pix0 = mt * BM;
+        const int n_img = pix0 / sg.HoWo;
+        const int rem = pix0 - n_img * sg.HoWo;
+        const int p = rem / sg.Wo;
+        const int q = rem - p * sg.Wo;
+        const int cw = q * sg.stride - sg.pad;
+        const int ch = p * sg.stride - sg.pad;
+        const uint32_t tx = A_BYTES + sg.bn * (BK * 2);
+        for (int tap = 0; tap < sg.taps; ++tap) {
+          const int r = tap / sg.S;
+          const int s = tap - r * sg.S;
+          for (int kc = 0; kc < sg.cin_chunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], tx);
+            tma_load_im2col_4d(&sg.tmA, &full[stage], sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
+                               (uint16_t)r);
+            tma_load_3d(&sg.tmB, &full[stage], sB + stage * B_BYTES_MAX, kc * BK, nt * sg.bn, tap);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+        const int kiters = sg.taps * sg.cin_chunks;
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t idesc = make_idesc_bf16(BM, sg.bn, 0, 0);
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * B_BYTES_MAX);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_sdesc(a_base + k * 32, 16, 1024);
+            const uint64_t bd = make_sdesc(b_base + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (ki | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp & 3;  // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+      const int tl = tile - sg.tile_begin;
+      const int nt = tl / sg.m_tiles;
+      const int mt = tl - nt * sg.m_tiles;
+      const int pix = mt * BM + ew * 32 + lane;
+      const bool valid = pix < sg.npix;
+      const int n_img = pix / sg.HoWo;
+      long long opix = pix;
+      if (sg.scatter2) {
+        const int rem = pix - n_img * sg.HoWo;
+        const int p = rem / sg.Wo;
+        const int q = rem - p * sg.Wo;
+        opix = ((long long)n_img * sg.Hs + 2 * p) * sg.Ws + 2 * q;
+      }
+      const long long row = opix * sg.ldc;
+      const int acc = it & 1;
+      const float* __restrict__ scale = sg.scale;
+      const float* __restrict__ shift = sg.shift;
+      const __nv_bfloat16* __restrict__ resid = reinterpret_cast<const __nv_bfloat16*>(sg.residual);
+      const __nv_bfloat16* __restrict__ rmask = reinterpret_cast<const __nv_bfloat16*>(sg.relu_mask);
+      // warp-uniform image index => GroupNorm partial sums can be shuffled down to one atomic per group
+      const int n0 = __shfl_sync(0xffffffffu, n_img, 0);
+      const bool uniform = __all_sync(0xffffffffu, (!valid) || (n_img == n0));
+
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256;
+
+      for (int c0 = 0; c0 < sg.bn; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld16(taddr + c0, rr);
+        tmem_ld_wait();
+        const int cb = nt * sg.bn + c0;  // first global output channel of this chunk
+        const bool fullchunk = (cb + 16 <= sg.cout);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = min(cb + j, sg.cout - 1);
+          float x = __uint_as_float(rr[j]);
+          if (scale) x *= __ldg(scale + c);
+          if (shift) x += __ldg(shift + c);
+          v[j] = x;
+        }
+        if (valid && resid) {
+          if (fullchunk) {
+            const uint4* rp = reinterpret_cast<const uint4*>(resid + row + cb);
+            const uint4 r0 = rp[0], r1 = rp[1];
+            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += bf16_lo(w[j]);
+              v[2 * j + 1] += bf16_hi(w[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cb + j < sg.cout) v[j] += __bfloat162float(resid[row + cb + j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
+        if (valid && rmask) {
+          if (fullchunk) {
+            const uint4* mp = reinterpret_cast<const uint4*>(rmask + row + cb);
+            const uint4 m0 = mp[0], m1 = mp[1];
+            const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (!(bf16_lo(w[j]) > 0.f)) v[2 * j] = 0.f;
+              if (!(bf16_hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
+            }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (cb + j < sg.cout && !(__bfloat162float(rmask[row + cb + j]) > 0.f)) v[j] = 0.f;
+          }
+        }
+        if (sg.stats) {
+          const int cpg = sg.cpg;  // 1,2,4,8 or 16 (divides the 16-channel chunk)
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (valid && cb + j < sg.cout) {
+              s1 += v[j];
+              s2 += v[j] * v[j];
+            }
+            if (((j + 1) & (cpg - 1)) == 0) {  // group boundary (warp-uniform)
+              const int cfirst = cb + j + 1 - cpg;
+              if (cfirst < sg.cout) {
+                const int grp = cfirst / cpg;
+                if (uniform) {
+#pragma unroll
+                  for (int o = 16; o > 0; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                  }
+                  if (lane == 0 && n0 * sg.HoWo < sg.npix) {
+                    double* dst = sg.stats + ((long long)n0 * sg.groups + grp) * 2;
+                    atomicAdd(dst, (double)s1);
+                    atomicAdd(dst + 1, (double)s2);
+                  }
+                } else if (valid) {
+                  double* dst = sg.stats + ((long long)n_img * sg.groups + grp) * 2;
+                  atomicAdd(dst, (double)s1);
+                  atomicAdd(dst + 1, (double)s2);
+                }
+              }
+              s1 = 0.f;
+              s2 = 0.f;
+            }
+          }
+        }
+        if (valid) {
+          if (sg.out_fp32) {
+            float* yp = reinterpret_cast<float*>(sg.y) + row + cb;
+            if (fullchunk) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(yp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cb + j < sg.cout) yp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(sg.y) + row + cb;
+            if (fullchunk) {
+              uint4 o0, o1;
+              o0.x = pack_bf16(v[0], v[1]);
+              o0.y = pack_bf16(v[2], v[3]);
+              o0.z = pack_bf16(v[4], v[5]);
+              o0.w = pack_bf16(v[6], v[7]);
+              o1.x = pack_bf16(v[8], v[9]);
+              o1.y = pack_bf16(v[10], v[11]);
+              o1.z = pack_bf16(v[12], v[13]);
+              o1.w = pack_bf16(v[14], v[15]);
+              reinterpret_cast<uint4*>(yp)[0] = o0;
+              reinterpret_cast<uint4*>(yp)[1] = o1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cb + j < sg.cout) yp[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace dslb
+
+// ============================================================================================ host side
+using namespace dslb;
+
+struct dslb_conv_plan {
+  ConvParamsDev* dev = nullptr;
+  int total_tiles = 0;
+  double flops = 0.0;
+};
+
+static int pick_bn(int cout_pad) {
+  // largest tile width <= 256 that divides cout_pad (cout_pad is a multiple of 16)
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (cout_pad % bn == 0) return bn;
+  return 16;
+}
+
+extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb_conv_plan_t** out) {
+  DSLB_CHECK_ARG(segs && out, "dslb_conv_plan_create: null argument");
+  DSLB_CHECK_ARG(nseg >= 1 && nseg <= DSLB_MAX_SEGS, "dslb_conv_plan_create: nseg %d not in [1,%d]", nseg,
+                 DSLB_MAX_SEGS);
+  ConvParamsDev* h = new (std::nothrow) ConvParamsDev();
+  if (!h) {
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
+  memset(h, 0, sizeof(*h));
+  int tiles = 0;
+  double flops = 0.0;
+  for (int i = 0; i < nseg; ++i) {
+    const dslb_conv_seg_t& s = segs[i];
+    ConvSegDev& d = h->seg[i];
+    int rc = DSLB_OK;
+#define SEG_CHECK(cond, ...)       \
+  if (!(cond)) {                   \
+    set_error(__VA_ARGS__);        \
+    delete h;                      \
+    return DSLB_EINVAL;            \
+  }
+    SEG_CHECK(s.x && s.w && s.y, "conv seg %d: null x/w/y", i);
+    SEG_CHECK(s.N > 0 && s.H > 0 && s.W > 0, "conv seg %d: bad N/H/W", i);
+    SEG_CHECK(s.Cin > 0 && s.Cin % 64 == 0, "conv seg %d: Cin=%d must be a multiple of 64", i, s.Cin);
+    SEG_CHECK(s.Cout > 0 && s.cout_pad >= s.Cout && s.cout_pad % 16 == 0,
+              "conv seg %d: cout_pad=%d must be a multiple of 16 and >= Cout=%d", i, s.cout_pad, s.Cout);
+    SEG_CHECK(s.R >= 1 && s.S >= 1 && s.R <= 7 && s.S <= 7 && s.stride >= 1 && s.stride <= 2 && s.pad >= 0,
+              "conv seg %d: unsupported filter %dx%d stride %d pad %d", i, s.R, s.S, s.stride, s.pad);
+    SEG_CHECK(s.ldc >= s.Cout && s.ldc % (s.out_fp32 ? 4 : 8) == 0, "conv seg %d: ldc=%d misaligned", i, s.ldc);
+    SEG_CHECK(((uintptr_t)s.x % 16) == 0 && ((uintptr_t)s.w % 16) == 0 && ((uintptr_t)s.y % 16) == 0,
+              "conv seg %d: x/w/y must be 16-byte aligned", i);
+    const int Ho = (s.H + 2 * s.pad - s.R) / s.stride + 1;
+    const int Wo = (s.W + 2 * s.pad - s.S) / s.stride + 1;
+    SEG_CHECK(Ho > 0 && Wo > 0, "conv seg %d: empty output", i);
+    if (s.gn_stats) {
+      SEG_CHECK(s.gn_cpg == 1 || s.gn_cpg == 2 || s.gn_cpg == 4 || s.gn_cpg == 8 || s.gn_cpg == 16,
+                "conv seg %d: gn_cpg=%d must be 1,2,4,8,16", i, s.gn_cpg);
+      SEG_CHECK(s.Cout % s.gn_cpg == 0, "conv seg %d: Cout %% gn_cpg != 0", i);
+    }
+    if (s.scatter2) SEG_CHECK(s.Hs >= 2 * Ho - 1 && s.Ws >= 2 * Wo - 1, "conv seg %d: scatter map too small", i);
+#undef SEG_CHECK
+    d.y = s.y;
+    d.residual = s.residual;
+    d.relu_mask = s.relu_mask;
+    d.scale = s.scale;
+    d.shift = s.shift;
+    d.stats = s.gn_stats;
+    d.npix = s.N * Ho * Wo;
+    d.HoWo = Ho * Wo;
+    d.Wo = Wo;
+    d.bn = pick_bn(s.cout_pad);
+    d.m_tiles = cdiv(d.npix, BM);
+    d.n_tiles = s.cout_pad / d.bn;
+    d.tile_begin = tiles;
+    tiles += d.m_tiles * d.n_tiles;
+    d.cin_chunks = s.Cin / 64;
+    d.taps = s.R * s.S;
+    d.S = s.S;
+    d.stride = s.stride;
+    d.pad = s.pad;
+    d.cout = s.Cout;
+    d.ldc = s.ldc;
+    d.out_fp32 = s.out_fp32;
+    d.relu_nch = s.relu_nch;
+    d.cpg = s.gn_stats ? s.gn_cpg : 16;
+    d.groups = s.gn_stats ? s.Cout / s.gn_cpg : 1;
+    d.scatter2 = s.scatter2;
+    d.Hs = s.Hs;
+    d.Ws = s.Ws;
+    rc = encode_im2col_bf16(&d.tmA, s.x, s.N, s.H, s.W, s.Cin, s.R, s.S, s.stride, s.pad, BM);
+    if (rc != DSLB_OK) {
+      delete h;
+      return rc;
+    }
+    const uint64_t wd[3] = {(uint64_t)s.Cin, (uint64_t)s.cout_pad, (uint64_t)(s.R * s.S)};
+    const uint64_t ws[2] = {(uint64_t)s.Cin * 2, (uint64_t)s.cout_pad * s.Cin * 2};
+    const uint32_t wb[3] = {64, (uint32_t)d.bn, 1};
+    rc = encode_tiled_bf16(&d.tmB, s.w, 3, wd, ws, wb);
+    if (rc != DSLB_OK) {
+      delete h;
+      return rc;
+    }
+    flops += 2.0 * (double)d.npix * s.Cout * s.Cin * s.R * s.S;
+  }
+  h->nseg = nseg;
+  h->total_tiles = tiles;
+
+  dslb_conv_plan* plan = new (std::nothrow) dslb_conv_plan();
+  if (!plan) {
+    delete h;
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
+  cudaError_t e = cudaMalloc(&plan->dev, sizeof(ConvParamsDev));
+  if (e == cudaSuccess) e = cudaMemcpy(plan->dev, h, sizeof(ConvParamsDev), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) {
+    set_error("dslb_conv_plan_create: %s", cudaGetErrorString(e));
+    if (plan->dev) cudaFree(plan->dev);
+    delete plan;
+    return DSLB_ECUDA;
+  }
+  plan->total_tiles = tiles;
+  plan->flops = flops;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSLB_CHECK_CUDA(
+        cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    attr_set = true;
+  }
+  *out = plan;
+  return DSLB_OK;
+}
+
+extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
+  DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
+  const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
+  conv_igemm_kernel<<<grid, 256, CONV_SMEM, (cudaStream_t)stream>>>(plan->dev);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" void dslb_conv_plan_destroy(dslb_conv_plan_t* plan) {
+  if (!plan) return;
+  if (plan->dev) cudaFree(plan->dev);
+  delete plan;
+}
+
+extern "C" double dslb_conv_plan_flops(const dslb_conv_plan_t* plan) { return plan ? plan->flops : 0.0; }
