@@ -26,12 +26,15 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KiB
 constexpr int BAR_BYTES = 256;
-constexpr int CONV_SMEM = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + BAR_BYTES;
+constexpr int STAT_BYTES = 4 * 32 * 2 * 4;  // GroupNorm partial sums [4 warps][32 halves][2] fp32
+constexpr int OUT_BYTES = 2 * BM * 128;  // output staging: two 128B-swizzled [128 px][64 ch] bf16 slabs
+constexpr int CONV_SMEM = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + OUT_BYTES + BAR_BYTES + STAT_BYTES;
 constexpr int TMEM_COLS = 512;
 
 struct alignas(128) ConvSegDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmY;  // output store map (staged epilogue only)
   void* y;
   const void* residual;
   const void* relu_mask;
@@ -44,6 +47,7 @@ struct alignas(128) ConvSegDev {
   int cout, bn, ldc;
   int out_fp32, relu_nch, cpg, groups;
   int scatter2, Hs, Ws;
+  int staged;  // 1: bf16 output goes through the smem staging tile + TMA store
 };
 
 struct alignas(128) ConvParamsDev {
@@ -66,16 +70,70 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel
+__device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32_t (&rr)[16], float (&v)[16],
+                                              int cb, bool fullchunk, bool valid, long long row) {
+  const float* __restrict__ scale = sg.scale;
+  const float* __restrict__ shift = sg.shift;
+  const __nv_bfloat16* __restrict__ resid = reinterpret_cast<const __nv_bfloat16*>(sg.residual);
+  const __nv_bfloat16* __restrict__ rmask = reinterpret_cast<const __nv_bfloat16*>(sg.relu_mask);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = min(cb + j, sg.cout - 1);
+    float x = __uint_as_float(rr[j]);
+    if (scale) x *= __ldg(scale + c);
+    if (shift) x += __ldg(shift + c);
+    v[j] = x;
+  }
+  if (valid && resid) {
+    if (fullchunk) {
+      const uint4* rp = reinterpret_cast<const uint4*>(resid + row + cb);
+      const uint4 r0 = rp[0], r1 = rp[1];
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] += bf16_lo(w[j]);
+        v[2 * j + 1] += bf16_hi(w[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (cb + j < sg.cout) v[j] += __bfloat162float(resid[row + cb + j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
+  if (valid && rmask) {
+    if (fullchunk) {
+      const uint4* mp = reinterpret_cast<const uint4*>(rmask + row + cb);
+      const uint4 m0 = mp[0], m1 = mp[1];
+      const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(bf16_lo(w[j]) > 0.f)) v[2 * j] = 0.f;
+        if (!(bf16_hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (cb + j < sg.cout && !(__bfloat162float(rmask[row + cb + j]) > 0.f)) v[j] = 0.f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev* __restrict__ P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES_MAX));
+  uint8_t* sOut = smem + STAGES * (A_BYTES + B_BYTES_MAX);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + OUT_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sStat = reinterpret_cast<float*>(sOut + OUT_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,14 +229,16 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp & 3;  // TMEM lane quadrant this warp may read
+    const int ew = warp & 3;         // TMEM lane quadrant this warp may read
+    const int et = ew * 32 + lane;   // 0..127: row of the tile owned by this thread
     int it = 0;
+    bool store_pending = false;      // (thread et==0) a TMA store may still be reading the staging buffer
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const ConvSegDev& sg = P->seg[find_seg(P, tile)];
       const int tl = tile - sg.tile_begin;
       const int nt = tl / sg.m_tiles;
       const int mt = tl - nt * sg.m_tiles;
-      const int pix = mt * BM + ew * 32 + lane;
+      const int pix = mt * BM + et;
       const bool valid = pix < sg.npix;
       const int n_img = pix / sg.HoWo;
       long long opix = pix;
@@ -190,140 +250,159 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
       }
       const long long row = opix * sg.ldc;
       const int acc = it & 1;
-      const float* __restrict__ scale = sg.scale;
-      const float* __restrict__ shift = sg.shift;
-      const __nv_bfloat16* __restrict__ resid = reinterpret_cast<const __nv_bfloat16*>(sg.residual);
-      const __nv_bfloat16* __restrict__ rmask = reinterpret_cast<const __nv_bfloat16*>(sg.relu_mask);
-      // warp-uniform image index => GroupNorm partial sums can be shuffled down to one atomic per group
-      const int n0 = __shfl_sync(0xffffffffu, n_img, 0);
-      const bool uniform = __all_sync(0xffffffffu, (!valid) || (n_img == n0));
+      const int bn = sg.bn;
+      const bool staged = sg.staged != 0;
+      // all valid pixels of this tile in one image => GroupNorm partial sums reduce per tile
+      const int pix_first = mt * BM;
+      const int pix_last = min(pix_first + BM, sg.npix) - 1;
+      const int n_tile = pix_first / sg.HoWo;
+      const bool tile_uniform = (pix_last / sg.HoWo) == n_tile;
 
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256;
 
-      for (int c0 = 0; c0 < sg.bn; c0 += 16) {
-        uint32_t rr[16];
-        tmem_ld16(taddr + c0, rr);
-        tmem_ld_wait();
-        const int cb = nt * sg.bn + c0;  // first global output channel of this chunk
-        const bool fullchunk = (cb + 16 <= sg.cout);
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = min(cb + j, sg.cout - 1);
-          float x = __uint_as_float(rr[j]);
-          if (scale) x *= __ldg(scale + c);
-          if (shift) x += __ldg(shift + c);
-          v[j] = x;
-        }
-        if (valid && resid) {
-          if (fullchunk) {
-            const uint4* rp = reinterpret_cast<const uint4*>(resid + row + cb);
-            const uint4 r0 = rp[0], r1 = rp[1];
-            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] += bf16_lo(w[j]);
-              v[2 * j + 1] += bf16_hi(w[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cb + j < sg.cout) v[j] += __bfloat162float(resid[row + cb + j]);
+      for (int r0 = 0; r0 < bn; r0 += 128) {  // rounds of <=128 channels (= the staging buffer)
+        const int rend = min(r0 + 128, bn);
+        if (staged) {
+          if (et == 0 && store_pending) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            store_pending = false;
           }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer is free
         }
+        for (int c0 = r0; c0 < rend; c0 += 16) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + c0, rr);
+          tmem_ld_wait();
+          const int cb = nt * bn + c0;  // first global output channel of this chunk
+          const bool fullchunk = (cb + 16 <= sg.cout);
+          float v[16];
+          epilogue_math(sg, rr, v, cb, fullchunk, valid, row);
+          if (sg.stats) {
+            // GroupNorm partial sums of the two 8-channel halves of this chunk, reduced over the warp's 32 pixels
+            // with a 6-shuffle butterfly; lanes 0/8/16/24 end up with (s1,h0) (s2,h0) (s1,h1) (s2,h1).
+            float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+            if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
-        if (valid && rmask) {
-          if (fullchunk) {
-            const uint4* mp = reinterpret_cast<const uint4*>(rmask + row + cb);
-            const uint4 m0 = mp[0], m1 = mp[1];
-            const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (!(bf16_lo(w[j]) > 0.f)) v[2 * j] = 0.f;
-              if (!(bf16_hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
-            }
-          } else {
-            for (int j = 0; j < 16; ++j)
-              if (cb + j < sg.cout && !(__bfloat162float(rmask[row + cb + j]) > 0.f)) v[j] = 0.f;
-          }
-        }
-        if (sg.stats) {
-          const int cpg = sg.cpg;  // 1,2,4,8 or 16 (divides the 16-channel chunk)
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (valid && cb + j < sg.cout) {
-              s1 += v[j];
-              s2 += v[j] * v[j];
-            }
-            if (((j + 1) & (cpg - 1)) == 0) {  // group boundary (warp-uniform)
-              const int cfirst = cb + j + 1 - cpg;
-              if (cfirst < sg.cout) {
-                const int grp = cfirst / cpg;
-                if (uniform) {
-#pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                  }
-                  if (lane == 0 && n0 * sg.HoWo < sg.npix) {
-                    double* dst = sg.stats + ((long long)n0 * sg.groups + grp) * 2;
-                    atomicAdd(dst, (double)s1);
-                    atomicAdd(dst + 1, (double)s2);
-                  }
-                } else if (valid) {
-                  double* dst = sg.stats + ((long long)n_img * sg.groups + grp) * 2;
-                  atomicAdd(dst, (double)s1);
-                  atomicAdd(dst + 1, (double)s2);
+              for (int j = 0; j < 8; ++j) {
+                if (cb + j < sg.cout) {
+                  a += v[j];
+                  c += v[j] * v[j];
+                }
+                if (cb + 8 + j < sg.cout) {
+                  b += v[8 + j];
+                  d += v[8 + j] * v[8 + j];
                 }
               }
-              s1 = 0.f;
-              s2 = 0.f;
+            }
+            if (tile_uniform) {
+              const bool hi16 = (lane & 16) != 0;
+              float x = (hi16 ? b : a) + __shfl_xor_sync(0xffffffffu, hi16 ? a : b, 16);
+              float y = (hi16 ? d : c) + __shfl_xor_sync(0xffffffffu, hi16 ? c : d, 16);
+              const bool hi8 = (lane & 8) != 0;
+              float z = (hi8 ? y : x) + __shfl_xor_sync(0xffffffffu, hi8 ? x : y, 8);
+              z += __shfl_xor_sync(0xffffffffu, z, 4);
+              z += __shfl_xor_sync(0xffffffffu, z, 2);
+              z += __shfl_xor_sync(0xffffffffu, z, 1);
+              if ((lane & 7) == 0) sStat[(ew * 32 + (c0 >> 3) + (lane >> 4)) * 2 + ((lane >> 3) & 1)] = z;
+            } else if (valid) {  // rare: the tile straddles two images
+              const int cpg = sg.cpg;
+              if (cb < sg.cout) {
+                double* dst = sg.stats + ((long long)n_img * sg.groups + cb / cpg) * DSLB_GN_STAT_STRIDE;
+                atomicAdd(dst, (double)a);
+                atomicAdd(dst + 1, (double)c);
+              }
+              if (cb + 8 < sg.cout) {
+                double* dst = sg.stats + ((long long)n_img * sg.groups + (cb + 8) / cpg) * DSLB_GN_STAT_STRIDE;
+                atomicAdd(dst, (double)b);
+                atomicAdd(dst + 1, (double)d);
+              }
+            }
+          }
+          if (staged) {
+            // 128B-swizzled [128 rows][64 ch] slabs, the layout the TMA store expects
+            const int cl = c0 - r0;
+            uint8_t* slab = sOut + (cl >> 6) * (BM * 128) + et * 128;
+            const int ch = (cl & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
+            uint4 o0, o1;
+            o0.x = pack_bf16(v[0], v[1]);
+            o0.y = pack_bf16(v[2], v[3]);
+            o0.z = pack_bf16(v[4], v[5]);
+            o0.w = pack_bf16(v[6], v[7]);
+            o1.x = pack_bf16(v[8], v[9]);
+            o1.y = pack_bf16(v[10], v[11]);
+            o1.z = pack_bf16(v[12], v[13]);
+            o1.w = pack_bf16(v[14], v[15]);
+            *reinterpret_cast<uint4*>(slab + ((ch ^ (et & 7)) << 4)) = o0;
+            *reinterpret_cast<uint4*>(slab + (((ch + 1) ^ (et & 7)) << 4)) = o1;
+          } else if (valid) {
+            if (sg.out_fp32) {
+              float* yp = reinterpret_cast<float*>(sg.y) + row + cb;
+              if (fullchunk) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  reinterpret_cast<float4*>(yp)[j] =
+                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (cb + j < sg.cout) yp[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(sg.y) + row + cb;
+              if (fullchunk) {
+                uint4 o0, o1;
+                o0.x = pack_bf16(v[0], v[1]);
+                o0.y = pack_bf16(v[2], v[3]);
+                o0.z = pack_bf16(v[4], v[5]);
+                o0.w = pack_bf16(v[6], v[7]);
+                o1.x = pack_bf16(v[8], v[9]);
+                o1.y = pack_bf16(v[10], v[11]);
+                o1.z = pack_bf16(v[12], v[13]);
+                o1.w = pack_bf16(v[14], v[15]);
+                reinterpret_cast<uint4*>(yp)[0] = o0;
+                reinterpret_cast<uint4*>(yp)[1] = o1;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (cb + j < sg.cout) yp[j] = __float2bfloat16_rn(v[j]);
+              }
             }
           }
         }
-        if (valid) {
-          if (sg.out_fp32) {
-            float* yp = reinterpret_cast<float*>(sg.y) + row + cb;
-            if (fullchunk) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<float4*>(yp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cb + j < sg.cout) yp[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(sg.y) + row + cb;
-            if (fullchunk) {
-              uint4 o0, o1;
-              o0.x = pack_bf16(v[0], v[1]);
-              o0.y = pack_bf16(v[2], v[3]);
-              o0.z = pack_bf16(v[4], v[5]);
-              o0.w = pack_bf16(v[6], v[7]);
-              o1.x = pack_bf16(v[8], v[9]);
-              o1.y = pack_bf16(v[10], v[11]);
-              o1.z = pack_bf16(v[12], v[13]);
-              o1.w = pack_bf16(v[14], v[15]);
-              reinterpret_cast<uint4*>(yp)[0] = o0;
-              reinterpret_cast<uint4*>(yp)[1] = o1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cb + j < sg.cout) yp[j] = __float2bfloat16_rn(v[j]);
-            }
+        if (rend == bn) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (staged) {
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (et == 0) {
+            const int nslab = (rend - r0 + 63) >> 6;
+            for (int sl = 0; sl < nslab; ++sl)
+              tma_store_2d(&sg.tmY, sOut + sl * (BM * 128), nt * bn + r0 + sl * 64, pix_first);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (sg.stats && tile_uniform) {
+        // all four warps have passed the last round's bar.sync 2 => sStat is complete for this tile
+        if (et < 64) {
+          const int hidx = et >> 1, k = et & 1;  // 8-channel half index inside the tile, (sum | sumsq)
+          const int cfirst = nt * bn + hidx * 8;
+          if (hidx * 8 < bn && cfirst < sg.cout) {
+            const float tot = sStat[(0 * 32 + hidx) * 2 + k] + sStat[(1 * 32 + hidx) * 2 + k] +
+                              sStat[(2 * 32 + hidx) * 2 + k] + sStat[(3 * 32 + hidx) * 2 + k];
+            double* dst = sg.stats + ((long long)n_tile * sg.groups + cfirst / sg.cpg) * DSLB_GN_STAT_STRIDE;
+            atomicAdd(dst + k, (double)tot);
+          }
+        }
+      }
     }
+    if (et == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -388,8 +467,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     const int Wo = (s.W + 2 * s.pad - s.S) / s.stride + 1;
     SEG_CHECK(Ho > 0 && Wo > 0, "conv seg %d: empty output", i);
     if (s.gn_stats) {
-      SEG_CHECK(s.gn_cpg == 1 || s.gn_cpg == 2 || s.gn_cpg == 4 || s.gn_cpg == 8 || s.gn_cpg == 16,
-                "conv seg %d: gn_cpg=%d must be 1,2,4,8,16", i, s.gn_cpg);
+      SEG_CHECK(s.gn_cpg == 8 || s.gn_cpg == 16, "conv seg %d: gn_cpg=%d must be 8 or 16", i, s.gn_cpg);
       SEG_CHECK(s.Cout % s.gn_cpg == 0, "conv seg %d: Cout %% gn_cpg != 0", i);
     }
     if (s.scatter2) SEG_CHECK(s.Hs >= 2 * Ho - 1 && s.Ws >= 2 * Wo - 1, "conv seg %d: scatter map too small", i);
@@ -434,6 +512,22 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     if (rc != DSLB_OK) {
       delete h;
       return rc;
+    }
+    d.staged = (!s.out_fp32 && !s.scatter2) ? 1 : 0;
+    if (d.staged) {
+      const uint64_t yd[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};
+      const uint64_t ys[1] = {(uint64_t)s.ldc * 2};
+      const uint32_t yb[2] = {64, (uint32_t)BM};
+      rc = encode_tiled_bf16(&d.tmY, s.y, 2, yd, ys, yb);
+      if (rc != DSLB_OK) {
+        delete h;
+        return rc;
+      }
+    }
+    if (s.gn_stats && !d.staged) {
+      set_error("conv seg %d: gn_stats needs a bf16, non-scattered output", i);
+      delete h;
+      return DSLB_EINVAL;
     }
     flops += 2.0 * (double)d.npix * s.Cout * s.Cin * s.R * s.S;
   }

@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, voi
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// tiled 2-D store smem -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // im2col 4-D load on an NHWC tensor: coords (c, w, h, n) of the base pixel (input space, i.e. already
 // multiplied by the conv stride and shifted by -pad), offsets (w_off, h_off) = filter tap * dilation.
 __device__ __forceinline__ void tma_load_im2col_4d(const void* desc, uint64_t* bar, void* dst, int c, int w,

@@ -28,6 +28,9 @@ extern "C" {
 #define DSLB_ENOMEM (-3)
 
 #define DSLB_MAX_SEGS 10
+/* GroupNorm statistics records: one (sum, sumsq) pair of doubles per (image, group), each record padded to its own
+ * 256-byte block so that concurrent L2 atomics from different tiles do not serialise on one cache line. */
+#define DSLB_GN_STAT_STRIDE 32
 
 const char* dslb_last_error(void);
 int dslb_version(void);
@@ -42,7 +45,7 @@ int dslb_version(void);
  * Epilogue, per output element (n,p,q,c), in this order:
  *     v = acc * scale[c] + shift[c];  v += residual;  if (c < relu_nch) v = max(v,0);
  *     if (relu_mask) v = relu_mask > 0 ? v : 0;
- *     gn_stats[n][c / gn_cpg] += (v, v*v)   (fp64 atomics; GroupNorm statistics of the conv output)
+ *     gn_stats[n][c / gn_cpg][0..1] += (v, v*v)   (fp64 atomics on the bf16-rounded output: GroupNorm statistics)
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct dslb_conv_seg {
   const void* x;         /* bf16 NHWC [N][H][W][Cin], Cin % 64 == 0                                   */
@@ -52,7 +55,7 @@ typedef struct dslb_conv_seg {
   const void* relu_mask; /* bf16, same indexing as y, or NULL                                         */
   const float* scale;    /* [Cout] or NULL (=1)                                                       */
   const float* shift;    /* [Cout] or NULL (=0)                                                       */
-  double* gn_stats;      /* [N][Cout/gn_cpg][2] (sum, sumsq), pre-zeroed by the caller, or NULL       */
+  double* gn_stats;      /* [N][Cout/gn_cpg][DSLB_GN_STAT_STRIDE] ([0]=sum,[1]=sumsq), pre-zeroed, or NULL */
   int32_t N, H, W, Cin;
   int32_t Cout;          /* real output channels                                                      */
   int32_t cout_pad;      /* rows per tap in w; multiple of 16; tiles of <=256                         */
@@ -60,7 +63,7 @@ typedef struct dslb_conv_seg {
   int32_t ldc;           /* elements between consecutive output pixels in y/residual/relu_mask        */
   int32_t out_fp32;      /* 0: y is bf16, 1: y is fp32                                                */
   int32_t relu_nch;      /* ReLU on channels c < relu_nch (0 = none)                                  */
-  int32_t gn_cpg;        /* channels per GroupNorm group (only with gn_stats)                         */
+  int32_t gn_cpg;        /* channels per GroupNorm group, 8 or 16 (only with gn_stats)                */
   int32_t scatter2;      /* 1: write output pixel (p,q) at (2p,2q) of an [N][Hs][Ws] map (dgrad of a  */
   int32_t Hs, Ws;        /*    stride-2 1x1 conv); y must then be pre-zeroed or accumulated           */
 } dslb_conv_seg_t;

@@ -1,0 +1,264 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCE in place
+(oracle/ref_loader.py) on the deterministic inputs of tests/golden/inputs.py. Run in the build container only
+(`python -m oracle.gen_golden`); the GPU box never sees /root/reference, it reads the committed .npz files.
+
+Files written (all small; inputs are regenerated from seeds, only reference OUTPUTS are stored):
+  head_fwd.npz   FCOSHead.forward train+eval on a 64-channel, 2-conv, GN(8) head (weights from seed)
+  loss_*.npz     FCOSHead.loss: labels / bbox_targets (bit-exact contract), losses, input-gradient samples
+  backbone.npz   ResNet-50 (caffe, frozen BN) + FPN forward on a 1x3x64x96 input (weights from seed)
+  decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
+  misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from tests.golden import inputs as GI  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+HEAD_CFG = dict(
+    num_classes=80, in_channels=256, stacked_convs=4, feat_channels=256, strides=[8, 16, 32, 64, 128],
+    norm_on_bbox=True, centerness_on_reg=True, dcn_on_last_conv=False, center_sampling=True, conv_bias=True,
+    loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+    loss_bbox=dict(type="GIoULoss", loss_weight=1.0),
+    loss_centerness=dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0))  # configs/fcos_semi/*.py:22-46
+
+
+def small_head(R, **over):
+    cfg = dict(HEAD_CFG, in_channels=64, feat_channels=64, stacked_convs=2,
+               norm_cfg=dict(type="GN", num_groups=8, requires_grad=True))
+    cfg.update(over)
+    return R.FCOSHead(**cfg)
+
+
+class _Cfg(dict):
+    __getattr__ = dict.get
+
+
+def gen_head_fwd(R):
+    torch.manual_seed(0)
+    head = small_head(R)
+    GI.fill_state_dict_(head.state_dict(), seed=11)
+    rng = np.random.RandomState(12)
+    H, W, B = 128, 160, 2
+    feats = [GI.make_tensor(rng, B, 64, h, w) for (h, w) in GI.level_sizes(H, W)]
+    out = {}
+    for mode in ("train", "eval"):
+        head.train(mode == "train")
+        with torch.no_grad():
+            cls, box, ctr = head(feats)
+        for i in range(5):
+            out[f"{mode}_cls{i}"] = cls[i].numpy()
+            out[f"{mode}_box{i}"] = box[i].numpy()
+            out[f"{mode}_ctr{i}"] = ctr[i].numpy()
+    np.savez_compressed(os.path.join(OUT, "head_fwd.npz"), **out)
+
+
+LOSS_CASES = {
+    # name: (seed, B, H, W, head kwargs, gt kwargs)
+    "base_b2": (21, 2, 256, 320, dict(), dict(with_ignore=False)),
+    "dsl_b2": (22, 2, 256, 320, dict(loss_weight=3.0), dict(with_ignore=True)),
+    "dsl_b3_si": (23, 3, 256, 320, dict(loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000), dict(with_ignore=True)),
+    "empty_gt": (24, 2, 256, 320, dict(loss_weight=3.0), dict(with_ignore=True, empty_first=True)),
+    "tie_break": (25, 2, 256, 320, dict(), dict(with_ignore=False, duplicate_boxes=True)),
+    "many_gt": (26, 2, 384, 512, dict(loss_weight=3.0), dict(with_ignore=True, max_gt=40, max_ignore=8)),
+    "ragged_hw": (27, 4, 200 // 8 * 8, 264, dict(loss_weight=3.0), dict(with_ignore=True)),
+}
+
+
+def gen_loss(R):
+    for name, (seed, B, H, W, hk, gk) in LOSS_CASES.items():
+        head = small_head(R, **hk)
+        head.train()
+        cls, box, ctr = GI.make_head_outputs(seed, B, H, W, train=True)
+        for t in cls + box + ctr:
+            t.requires_grad_(True)
+        gts, labels, ignores = GI.make_gt(seed + 1000, B, H, W, **gk)
+        metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=1.0) for _ in range(B)]
+        losses = head.loss(cls, box, ctr, gts, labels, metas, gt_bboxes_ignore=ignores)
+        total = sum(losses.values())
+        total.backward()
+        # targets, straight from the reference's get_targets
+        pts = head.get_points([c.shape[-2:] for c in cls], torch.float32, "cpu")
+        lab, tgt = head.get_targets(pts, gts, labels)
+        out = {k: np.float64(v.item()) for k, v in losses.items()}
+        out["labels"] = torch.cat(lab).numpy().astype(np.int16)
+        out["bbox_targets"] = torch.cat(tgt).numpy()
+        if ignores is not None:
+            ig_lab = [torch.zeros(b.size(0), dtype=torch.int64) + 79 for b in ignores]
+            il, _ = head.get_targets(pts, ignores, ig_lab)
+            out["ig_labels"] = torch.cat(il).numpy().astype(np.int16)
+        # gradient fingerprints: full grads of bbox/ctr, strided sample + sum of the (large) cls grad
+        g_cls = torch.cat([c.grad.permute(0, 2, 3, 1).reshape(-1, 80) for c in cls])
+        out["dcls_sample"] = g_cls.reshape(-1)[::17].numpy()
+        out["dcls_abs_sum"] = np.float64(g_cls.abs().double().sum().item())
+        out["dbox"] = torch.cat([b.grad.permute(0, 2, 3, 1).reshape(-1, 4) for b in box]).numpy()
+        out["dctr"] = torch.cat([c.grad.permute(0, 2, 3, 1).reshape(-1) for c in ctr]).numpy()
+        np.savez_compressed(os.path.join(OUT, f"loss_{name}.npz"), **out)
+
+
+def gen_backbone(R):
+    torch.manual_seed(0)
+    bb = R.ResNet(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                  norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="caffe")
+    neck = R.FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1,
+                 add_extra_convs="on_output", num_outs=5, relu_before_extra_convs=True)
+    GI.fill_state_dict_(bb.state_dict(), seed=31)
+    GI.fill_state_dict_(neck.state_dict(), seed=32)
+    bb.eval()
+    neck.eval()
+    x = GI.make_tensor(np.random.RandomState(33), 1, 3, 64, 96)
+    with torch.no_grad():
+        cs = bb(x)
+        ps = neck(cs)
+    out = {f"c{i + 2}": c.numpy() for i, c in enumerate(cs)}
+    out.update({f"p{i + 3}": p.numpy() for i, p in enumerate(ps)})
+    np.savez_compressed(os.path.join(OUT, "backbone.npz"), **out)
+
+
+def gen_decode(R):
+    head = small_head(R, test_cfg=_Cfg(nms_pre=1000, min_bbox_size=0, score_thr=0.05,
+                                       nms=dict(type="nms", iou_threshold=0.6), max_per_img=100))
+    head.eval()
+    B, H, W = 2, 512, 640
+    cls, box, ctr = GI.make_head_outputs(41, B, H, W, train=False, cls_mean=-6.5)
+    metas = [dict(img_shape=(500, 630, 3), scale_factor=np.array([1.25, 1.25, 1.25, 1.25], dtype=np.float32)),
+             dict(img_shape=(512, 600, 3), scale_factor=np.array([0.8, 0.8, 0.8, 0.8], dtype=np.float32))]
+    with torch.no_grad():
+        res = head.get_bboxes(cls, box, ctr, metas, rescale=True)
+        raw = head.get_bboxes(cls, box, ctr, metas, rescale=True, with_nms=False)
+    out = {}
+    for b, (dets, labels) in enumerate(res):
+        out[f"dets{b}"] = dets.numpy()
+        out[f"labels{b}"] = labels.numpy()
+    for b, (bx, sc, cn) in enumerate(raw):
+        out[f"raw_boxes{b}"] = bx.numpy()
+        out[f"raw_scores_max{b}"] = sc.max(-1)[0].numpy()
+        out[f"raw_ctr{b}"] = cn.numpy()
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), **out)
+
+
+def _extract_method(path, cls_name, fn_name, glb):
+    import ast
+    tree = ast.parse(open(path).read())
+    for n in tree.body:
+        if isinstance(n, ast.ClassDef) and n.name == cls_name:
+            for m in n.body:
+                if isinstance(m, ast.FunctionDef) and m.name == fn_name:
+                    mod = ast.Module(body=[m], type_ignores=[])
+                    exec(compile(mod, path, "exec"), glb)
+                    return glb[fn_name]
+    raise KeyError(fn_name)
+
+
+def gen_misc(R):
+    out = {}
+    parse_det_results, adathres = ref_loader.load_hook_functions()
+    rng = np.random.RandomState(51)
+    # (1) hook gate: bbox2result-style per-class arrays -> kept boxes (score >= 0.1, int() truncation)
+    per_class = []
+    for c in range(5):
+        n = int(rng.randint(0, 6))
+        b = GI.demo_boxes(rng, n, 480, 640) + rng.rand(n, 4).astype(np.float32)
+        s = rng.rand(n, 1).astype(np.float32) * 0.5
+        per_class.append(np.concatenate([b, s], 1))
+    kept = parse_det_results(per_class, 0.1)
+    out["gate_in"] = np.concatenate([np.concatenate([p, np.full((len(p), 1), c, np.float32)], 1)
+                                     for c, p in enumerate(per_class)])
+    out["gate_bbox"] = np.array([k["bbox"] for k in kept], dtype=np.int64).reshape(-1, 4)
+    out["gate_score"] = np.array([k["score"] for k in kept], dtype=np.float64)
+    out["gate_cls"] = np.array([k["category_index"] for k in kept], dtype=np.int64)
+
+    # (2) adathres: write per-image JSONs, run the reference twice (first pass, then with history)
+    with tempfile.TemporaryDirectory() as td:
+        cats = [f"cat{i}" for i in range(6)]
+        cat2id = {c: i for i, c in enumerate(cats)}
+        id2cat = {str(i): c for i, c in enumerate(cats)}
+        files = []
+        allsc = {c: [] for c in cats}
+        for i in range(12):
+            n = int(rng.randint(0, 7))
+            tags = [cats[int(rng.randint(0, 6))] for _ in range(n)]
+            scores = [float(np.round(rng.rand() * 0.9 + 0.1, 6)) for _ in range(n)]
+            for t, s in zip(tags, scores):
+                allsc[t].append(s)
+            json.dump(dict(targetNum=n, tags=tags, scores=scores), open(os.path.join(td, f"im{i}.jpg.json"), "w"))
+            files.append(f"x/im{i}.jpg\n")
+        fn = os.path.join(td, "adathres.json")
+        adathres(0, True, fn, id2cat, cat2id, files, td, {})
+        first = json.load(open(fn))
+        adathres(0, True, fn, id2cat, cat2id, files, td, {})
+        second = json.load(open(fn))
+        out["ada_scores_json"] = np.frombuffer(json.dumps(allsc).encode(), dtype=np.uint8)
+        out["ada_first_json"] = np.frombuffer(json.dumps(first).encode(), dtype=np.uint8)
+        out["ada_second_json"] = np.frombuffer(json.dumps(second).encode(), dtype=np.uint8)
+
+        # (3) dataset filter rule: SemiCOCODataset._parse_ann_info on a synthetic per-image JSON
+        import types
+        glb = {"os": os, "json": json, "np": np}
+        parse_ann = _extract_method(os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/semicoco.py"),
+                                    "SemiCOCODataset", "_parse_ann_info", glb)
+        n = 40
+        rects = (GI.demo_boxes(rng, n, 480, 640) + np.array([-30, -30, 30, 30], np.float32)).tolist()
+        rects[3] = [10.0, 10.0, 10.5, 50.0]      # w < 1 -> dropped
+        rects[4] = [700.0, 10.0, 720.0, 50.0]    # no overlap with the image -> dropped
+        scores = [float(np.round(rng.rand() * 0.5, 4)) for _ in range(n)]
+        tags = [cats[int(rng.randint(0, 6))] for _ in range(n)]
+        json.dump(dict(targetNum=n, rects=rects, scores=scores, tags=tags),
+                  open(os.path.join(td, "a.jpg.json"), "w"))
+        thr_file = os.path.join(td, "thr.json")
+        json.dump(dict(thres={"cat0": 0.33, "cat1": 0.31, "cat2": 0.35}), open(thr_file, "w"))
+        for tag, thres in (("nofile", os.path.join(td, "missing.json")), ("file", thr_file), ("fixed", [0.1, 0.4]),
+                           ("none", None)):
+            slf = types.SimpleNamespace(ann_path=td, thres=thres, default_thres=[0.1, 0.3], thres_list_by_class={},
+                                        labelmapper=dict(cat2id=cat2id))
+            ann = parse_ann(slf, dict(filename="a.jpg", width=640, height=480), None)
+            out[f"filt_{tag}_gt"] = ann["bboxes"]
+            out[f"filt_{tag}_labels"] = ann["labels"]
+            out[f"filt_{tag}_ignore"] = ann["bboxes_ignore"]
+        out["filt_rects"] = np.array(rects, dtype=np.float64)
+        out["filt_scores"] = np.array(scores, dtype=np.float64)
+        out["filt_cls"] = np.array([cat2id[t] for t in tags], dtype=np.int64)
+
+    # (4) EMA body (semi_epoch_based_runner.py:392-406), executed on two tiny state dicts via the same expression
+    import ast
+    src = open(os.path.join(ref_loader.REF_ROOT, "mmdet/runner/hooks/semi_epoch_based_runner.py")).read()
+    assert "student_model_dict[key] * (1 - keep_rate) + value * keep_rate" in src  # the line we restate
+    s = {"w": GI.make_tensor(rng, 7, 3), "bn.running_mean": GI.make_tensor(rng, 7),
+         "bn.num_batches_tracked": torch.tensor(5)}
+    t = {"w": GI.make_tensor(rng, 7, 3), "bn.running_mean": GI.make_tensor(rng, 7),
+         "bn.num_batches_tracked": torch.tensor(9)}
+    keep_rate = 0.99
+    new = {k: s[k] * (1 - keep_rate) + v * keep_rate for k, v in t.items()}
+    for k in s:
+        out["ema_s_" + k] = s[k].numpy()
+        out["ema_t_" + k] = t[k].numpy()
+        out["ema_new_" + k] = new[k].numpy()
+    _ = ast
+    np.savez_compressed(os.path.join(OUT, "misc.npz"), **out)
+
+
+def main():
+    torch.set_num_threads(8)
+    R = ref_loader.load()
+    os.makedirs(OUT, exist_ok=True)
+    gen_head_fwd(R)
+    gen_loss(R)
+    gen_backbone(R)
+    gen_decode(R)
+    gen_misc(R)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

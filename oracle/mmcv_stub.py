@@ -1,0 +1,246 @@
+"""TEST INFRASTRUCTURE ONLY — a minimal stand-in for the un-vendored third-party dependency `mmcv-full`
+(pinned >=1.3.8,<=1.4.0 by /root/reference/mmdet/__init__.py:19-27; README says 1.3.10), just enough for the
+reference's OWN hot-path source files to execute in place (see oracle/ref_loader.py).
+
+Only thin torch.nn wrappers and no-op decorators are restated here; no detector arithmetic lives in this file.
+What each piece stands in for (mmcv 1.3.x public behaviour):
+  Registry / build_from_cfg  -- `type`-keyed class registry, `register_module(force=...)`, `build(cfg)`
+  ConvModule                 -- conv -> norm -> activation, bias='auto' means bias = (norm_cfg is None)
+  Scale                      -- learnable scalar multiply
+  build_conv_layer / build_norm_layer -- nn.Conv2d / (name, nn.BatchNorm2d|nn.GroupNorm); requires_grad flag
+  force_fp32 / auto_fp16 / jit -- identity decorators (fp16_enabled is False on this path)
+  ops.nms / ops.batched_nms  -- torchvision NMS (IoU > thr suppressed, offset 0), class-offset trick
+  ops.sigmoid_focal_loss     -- deliberately NOT provided: on CPU the reference takes its own
+                                py_sigmoid_focal_loss branch (mmdet/models/losses/focal_loss.py:162-168)
+"""
+import inspect
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+
+class Registry:
+    def __init__(self, name, build_func=None, parent=None, scope=None):
+        self._name = name
+        self._module_dict = {}
+        self.parent = parent
+        self.build_func = build_func or build_from_cfg
+        if parent is not None and build_func is None:
+            self.build_func = parent.build_func
+
+    @property
+    def module_dict(self):
+        return self._module_dict
+
+    def get(self, key):
+        if key in self._module_dict:
+            return self._module_dict[key]
+        if self.parent is not None:
+            return self.parent.get(key)
+        return None
+
+    def _register(self, cls, name=None, force=False):
+        name = name or cls.__name__
+        if not force and name in self._module_dict:
+            raise KeyError(f"{name} is already registered in {self._name}")
+        self._module_dict[name] = cls
+
+    def register_module(self, name=None, force=False, module=None):
+        if module is not None:
+            self._register(module, name, force)
+            return module
+
+        def deco(cls):
+            self._register(cls, name, force)
+            return cls
+
+        return deco
+
+    def build(self, *args, **kwargs):
+        return self.build_func(*args, **kwargs, registry=self)
+
+
+def build_from_cfg(cfg, registry, default_args=None):
+    args = dict(cfg)
+    if default_args:
+        for k, v in default_args.items():
+            args.setdefault(k, v)
+    t = args.pop("type")
+    cls = registry.get(t) if isinstance(t, str) else t
+    if cls is None:
+        raise KeyError(f"{t} is not in the {registry._name} registry")
+    return cls(**args)
+
+
+class BaseModule(nn.Module):
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self.init_cfg = init_cfg
+        self._is_init = False
+
+    def init_weights(self):
+        pass
+
+
+class Sequential(BaseModule, nn.Sequential):
+    def __init__(self, *args, init_cfg=None):
+        BaseModule.__init__(self, init_cfg)
+        nn.Sequential.__init__(self, *args)
+
+
+class ModuleList(BaseModule, nn.ModuleList):
+    def __init__(self, modules=None, init_cfg=None):
+        BaseModule.__init__(self, init_cfg)
+        nn.ModuleList.__init__(self, modules)
+
+
+class Scale(nn.Module):
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+def build_conv_layer(cfg, *args, **kwargs):
+    assert cfg is None or cfg.get("type", "Conv2d") in ("Conv2d", "Conv"), cfg
+    return nn.Conv2d(*args, **kwargs)
+
+
+def build_norm_layer(cfg, num_features, postfix=""):
+    cfg = dict(cfg)
+    t = cfg.pop("type")
+    requires_grad = cfg.pop("requires_grad", True)
+    cfg.setdefault("eps", 1e-5)
+    if t == "BN":
+        name, layer = "bn" + str(postfix), nn.BatchNorm2d(num_features, **cfg)
+    elif t == "GN":
+        name, layer = "gn" + str(postfix), nn.GroupNorm(num_channels=num_features, **cfg)
+    else:
+        raise KeyError(t)
+    for p in layer.parameters():
+        p.requires_grad = requires_grad
+    return name, layer
+
+
+def build_plugin_layer(*a, **k):
+    raise NotImplementedError("plugins are not on the DSL path")
+
+
+class ConvModule(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias="auto", conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"), inplace=True,
+                 with_spectral_norm=False, padding_mode="zeros", order=("conv", "norm", "act")):
+        super().__init__()
+        assert order == ("conv", "norm", "act")
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == "auto":
+            bias = not self.with_norm
+        self.conv = build_conv_layer(conv_cfg, in_channels, out_channels, kernel_size, stride=stride,
+                                     padding=padding, dilation=dilation, groups=groups, bias=bias)
+        if self.with_norm:
+            self.norm_name, norm = build_norm_layer(norm_cfg, out_channels)
+            self.add_module(self.norm_name, norm)
+        if self.with_activation:
+            assert act_cfg["type"] == "ReLU"
+            self.activate = nn.ReLU(inplace=inplace)
+
+    @property
+    def norm(self):
+        return getattr(self, self.norm_name) if self.with_norm else None
+
+    def forward(self, x, activate=True, norm=True):
+        x = self.conv(x)
+        if norm and self.with_norm:
+            x = self.norm(x)
+        if activate and self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+def _identity_decorator(*dargs, **dkwargs):
+    if len(dargs) == 1 and callable(dargs[0]) and not dkwargs:
+        return dargs[0]
+
+    def deco(fn):
+        return fn
+
+    return deco
+
+
+def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    from torchvision.ops import nms as tv_nms
+    cfg = dict(nms_cfg)
+    assert cfg.pop("type", "nms") == "nms"
+    thr = cfg.pop("iou_threshold")
+    if class_agnostic:
+        b = boxes
+    else:
+        max_coordinate = boxes.max()
+        offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+        b = boxes + offsets[:, None]
+    keep = tv_nms(b, scores, thr)
+    return torch.cat([boxes[keep], scores[keep, None]], -1), keep
+
+
+def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
+    from torchvision.ops import nms as tv_nms
+    is_np = not isinstance(boxes, torch.Tensor)
+    if is_np:
+        boxes, scores = torch.from_numpy(boxes), torch.from_numpy(scores)
+    if score_threshold > 0:
+        valid = scores > score_threshold
+        inds0 = valid.nonzero().squeeze(1)
+        boxes, scores = boxes[valid], scores[valid]
+    keep = tv_nms(boxes, scores, iou_threshold)
+    if max_num > 0:
+        keep = keep[:max_num]
+    dets = torch.cat([boxes[keep], scores[keep, None]], -1)
+    if score_threshold > 0:
+        keep = inds0[keep]
+    if is_np:
+        dets, keep = dets.numpy(), keep.numpy()
+    return dets, keep
+
+
+def install():
+    """Put the stub package tree into sys.modules as `mmcv` (idempotent)."""
+    if "mmcv" in sys.modules and getattr(sys.modules["mmcv"], "__dslb_stub__", False):
+        return sys.modules["mmcv"]
+    assert "mmcv" not in sys.modules, "a real mmcv is already imported"
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mmcv = mod("mmcv", __dslb_stub__=True, __version__="1.3.10", jit=_identity_decorator,
+               is_tuple_of=lambda seq, t: isinstance(seq, tuple) and all(isinstance(s, t) for s in seq))
+    MODELS = Registry("model")
+    mmcv.cnn = mod("mmcv.cnn", MODELS=MODELS, ConvModule=ConvModule, Scale=Scale,
+                   build_conv_layer=build_conv_layer, build_norm_layer=build_norm_layer,
+                   build_plugin_layer=build_plugin_layer)
+    mmcv.utils = mod("mmcv.utils", Registry=Registry, build_from_cfg=build_from_cfg)
+
+    class OptimizerHook:  # placeholder: mmdet/core/utils/dist_utils.py subclasses it at import time
+        def __init__(self, *a, **k):
+            pass
+
+    mmcv.runner = mod("mmcv.runner", BaseModule=BaseModule, Sequential=Sequential, ModuleList=ModuleList,
+                      force_fp32=_identity_decorator, auto_fp16=_identity_decorator, OptimizerHook=OptimizerHook)
+
+    def _no_cuda_focal(*a, **k):
+        raise RuntimeError("mmcv.ops.sigmoid_focal_loss is CUDA-only; the CPU oracle uses py_sigmoid_focal_loss")
+
+    mmcv.ops = mod("mmcv.ops", sigmoid_focal_loss=_no_cuda_focal, batched_nms=batched_nms, nms=nms)
+    sys.modules["mmcv.ops.nms"] = mod("mmcv.ops.nms", batched_nms=batched_nms, nms=nms)
+    mmcv.ops.nms_mod = sys.modules["mmcv.ops.nms"]
+    return mmcv
+
+
+_ = inspect  # keep import (used by downstream debugging)

@@ -1,0 +1,90 @@
+"""Deterministic synthetic inputs shared by oracle/gen_golden.py (which feeds them to the reference's own code)
+and by the tests (which feed them to the oracle restatement and to the CUDA path). Everything is drawn from
+numpy's legacy RandomState, whose streams are frozen across numpy versions, so only OUTPUTS need committing.
+
+Box recipe follows the reference's `_demo_mm_inputs` (tests/test_models/test_forward.py:369-444):
+cx, cy, bw, bh ~ U(0,1) scaled to the image and clipped.
+"""
+import numpy as np
+import torch
+
+STRIDES = (8, 16, 32, 64, 128)
+REGRESS_RANGES = ((-1, 64), (64, 128), (128, 256), (256, 512), (512, 1e8))
+
+
+def level_sizes(H, W, strides=STRIDES):
+    """FPN map sizes of a padded H x W image (conv arithmetic of ResNet + FPN P6/P7 stride-2 3x3 pad-1 convs)."""
+    sizes = []
+    h, w = H // 8, W // 8
+    for i in range(5):
+        sizes.append((h, w))
+        h, w = (h + 1) // 2, (w + 1) // 2
+    return sizes
+
+
+def demo_boxes(rng, n, H, W):
+    cx, cy, bw, bh = rng.rand(n, 4).T
+    x1 = ((cx * W) - (W * bw / 2)).clip(0, W)
+    y1 = ((cy * H) - (H * bh / 2)).clip(0, H)
+    x2 = ((cx * W) + (W * bw / 2)).clip(0, W)
+    y2 = ((cy * H) + (H * bh / 2)).clip(0, H)
+    return np.stack([x1, y1, x2, y2], 1).astype(np.float32)
+
+
+def make_gt(seed, B, H, W, max_gt=9, max_ignore=3, num_classes=80, with_ignore=True, empty_first=False,
+            duplicate_boxes=False):
+    """Per-image GT boxes/labels and ignore boxes."""
+    rng = np.random.RandomState(seed)
+    gts, labels, ignores = [], [], []
+    for b in range(B):
+        n = 0 if (empty_first and b == 0) else int(rng.randint(1, max_gt + 1))
+        boxes = demo_boxes(rng, n, H, W)
+        if duplicate_boxes and n >= 2:
+            # two GTs of identical area covering the same points: exercises the first-index tie-break
+            boxes[1] = boxes[0]
+        gts.append(torch.from_numpy(boxes.reshape(-1, 4)))
+        labels.append(torch.from_numpy(rng.randint(0, num_classes, size=n).astype(np.int64)))
+        ni = int(rng.randint(0, max_ignore + 1)) if with_ignore else 0
+        ignores.append(torch.from_numpy(demo_boxes(rng, ni, H, W).reshape(-1, 4)))
+    return gts, labels, (ignores if with_ignore else None)
+
+
+def make_head_outputs(seed, B, H, W, num_classes=80, train=True, cls_mean=-2.0):
+    """Random head outputs (NCHW lists): cls logits ~ N(-2, 1.5), bbox >= 0 (post-ReLU), centerness logits."""
+    rng = np.random.RandomState(seed)
+    cls, box, ctr = [], [], []
+    for lvl, (h, w) in enumerate(level_sizes(H, W)):
+        cls.append(torch.from_numpy((rng.randn(B, num_classes, h, w) * 1.5 + cls_mean).astype(np.float32)))
+        b = np.maximum(rng.randn(B, 4, h, w) * 2.0 + 2.0, 0).astype(np.float32)
+        if not train:
+            b = b * STRIDES[lvl]
+        box.append(torch.from_numpy(b))
+        ctr.append(torch.from_numpy(rng.randn(B, 1, h, w).astype(np.float32)))
+    return cls, box, ctr
+
+
+def make_tensor(rng, *shape, scale=1.0):
+    return torch.from_numpy((rng.randn(*shape) * scale).astype(np.float32))
+
+
+def fill_state_dict_(sd, seed, skip=()):
+    """Overwrite every tensor of a state_dict, in key order, with seeded values sized by fan-in.
+    BatchNorm running_var / weights get positive values; num_batches_tracked is left alone."""
+    rng = np.random.RandomState(seed)
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked") or k in skip:
+            continue
+        if k.endswith("running_var"):
+            v.copy_(torch.from_numpy((rng.rand(*v.shape) + 0.5).astype(np.float32)))
+        elif k.endswith("running_mean"):
+            v.copy_(make_tensor(rng, *v.shape, scale=0.1))
+        elif v.dim() == 4:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            v.copy_(make_tensor(rng, *v.shape, scale=(2.0 / fan_in) ** 0.5))
+        elif k.endswith(".weight"):  # norm weight
+            v.copy_(torch.from_numpy((rng.rand(*v.shape) + 0.5).astype(np.float32)))
+        elif k.endswith("scale"):
+            v.copy_(torch.tensor(float(rng.rand() + 0.5)))
+        else:  # biases
+            v.copy_(make_tensor(rng, *v.shape, scale=0.1))
+    return sd

@@ -1,0 +1,252 @@
+"""The oracle restatement (oracle/fcos_oracle.py) pinned against (a) golden vectors produced by executing the
+reference's own source (oracle/gen_golden.py -> tests/golden/*.npz) and (b) the known-answer tests the reference
+itself carries. CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fcos_oracle as O
+from tests.golden import inputs as GI
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_kat_giou_reference_test_box_overlap():
+    # /root/reference/tests/test_metrics/test_box_overlap.py:83-97
+    b1 = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [32, 32, 38, 42]])
+    b2 = torch.FloatTensor([[0, 0, 10, 20], [0, 10, 10, 19], [10, 10, 20, 20]])
+    g = O.giou_aligned(b1, b2, eps=1e-7).numpy().round(4)
+    assert np.allclose(g, np.array([0.5000, -0.0500, -0.8214]), rtol=0, atol=1e-7)
+
+
+def test_kat_distance2bbox_reference_test_misc():
+    # /root/reference/tests/test_utils/test_misc.py:51-64
+    point = torch.Tensor([[74., 61.], [-29., 106.], [138., 61.], [29., 170.]])
+    distance = torch.Tensor([[0., 0, 1., 1.], [1., 2., 10., 6.], [22., -29., 138., 61.], [54., -29., 170., 61.]])
+    expected = torch.Tensor([[74., 61., 75., 62.], [0., 104., 0., 112.], [100., 90., 100., 120.],
+                             [0., 120., 100., 120.]])
+    assert expected.allclose(O.distance2bbox(point, distance, max_shape=(120, 100)))
+
+
+def _small_head_sd():
+    from collections import OrderedDict
+    sd = OrderedDict()
+    for br in ("cls_convs", "reg_convs"):
+        for i in range(2):
+            sd[f"{br}.{i}.conv.weight"] = torch.zeros(64, 64, 3, 3)
+            sd[f"{br}.{i}.conv.bias"] = torch.zeros(64)
+            sd[f"{br}.{i}.gn.weight"] = torch.zeros(64)
+            sd[f"{br}.{i}.gn.bias"] = torch.zeros(64)
+    sd["conv_cls.weight"] = torch.zeros(80, 64, 3, 3)
+    sd["conv_cls.bias"] = torch.zeros(80)
+    sd["conv_reg.weight"] = torch.zeros(4, 64, 3, 3)
+    sd["conv_reg.bias"] = torch.zeros(4)
+    sd["conv_centerness.weight"] = torch.zeros(1, 64, 3, 3)
+    sd["conv_centerness.bias"] = torch.zeros(1)
+    for i in range(5):
+        sd[f"scales.{i}.scale"] = torch.tensor(1.0)
+    return sd
+
+
+def small_head_state(seed=11):
+    """Same key ORDER as the reference FCOSHead.state_dict() (checked in gen_golden by construction)."""
+    from collections import OrderedDict
+    sd = OrderedDict()
+    for i in range(2):
+        sd[f"cls_convs.{i}.conv.weight"] = torch.zeros(64, 64, 3, 3)
+        sd[f"cls_convs.{i}.conv.bias"] = torch.zeros(64)
+        sd[f"cls_convs.{i}.gn.weight"] = torch.zeros(64)
+        sd[f"cls_convs.{i}.gn.bias"] = torch.zeros(64)
+    for i in range(2):
+        sd[f"reg_convs.{i}.conv.weight"] = torch.zeros(64, 64, 3, 3)
+        sd[f"reg_convs.{i}.conv.bias"] = torch.zeros(64)
+        sd[f"reg_convs.{i}.gn.weight"] = torch.zeros(64)
+        sd[f"reg_convs.{i}.gn.bias"] = torch.zeros(64)
+    sd["conv_cls.weight"] = torch.zeros(80, 64, 3, 3)
+    sd["conv_cls.bias"] = torch.zeros(80)
+    sd["conv_reg.weight"] = torch.zeros(4, 64, 3, 3)
+    sd["conv_reg.bias"] = torch.zeros(4)
+    sd["conv_centerness.weight"] = torch.zeros(1, 64, 3, 3)
+    sd["conv_centerness.bias"] = torch.zeros(1)
+    for i in range(5):
+        sd[f"scales.{i}.scale"] = torch.tensor(1.0)
+    return GI.fill_state_dict_(sd, seed)
+
+
+def test_head_forward_matches_reference():
+    g = load("head_fwd.npz")
+    sd = small_head_state()
+    rng = np.random.RandomState(12)
+    feats = [GI.make_tensor(rng, 2, 64, h, w) for (h, w) in GI.level_sizes(128, 160)]
+    for mode in ("train", "eval"):
+        cls, box, ctr = O.fcos_head_forward(sd, feats, training=(mode == "train"), stacked_convs=2, num_groups=8)
+        for i in range(5):
+            np.testing.assert_allclose(cls[i].numpy(), g[f"{mode}_cls{i}"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(box[i].numpy(), g[f"{mode}_box{i}"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(ctr[i].numpy(), g[f"{mode}_ctr{i}"], rtol=1e-5, atol=1e-5)
+
+
+LOSS_CASES = {
+    "base_b2": (21, 2, 256, 320, dict(), dict(with_ignore=False)),
+    "dsl_b2": (22, 2, 256, 320, dict(loss_weight=3.0), dict(with_ignore=True)),
+    "dsl_b3_si": (23, 3, 256, 320, dict(loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000), dict(with_ignore=True)),
+    "empty_gt": (24, 2, 256, 320, dict(loss_weight=3.0), dict(with_ignore=True, empty_first=True)),
+    "tie_break": (25, 2, 256, 320, dict(), dict(with_ignore=False, duplicate_boxes=True)),
+    "many_gt": (26, 2, 384, 512, dict(loss_weight=3.0), dict(with_ignore=True, max_gt=40, max_ignore=8)),
+    "ragged_hw": (27, 4, 200, 264, dict(loss_weight=3.0), dict(with_ignore=True)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_CASES))
+def test_loss_and_targets_match_reference(name):
+    seed, B, H, W, hk, gk = LOSS_CASES[name]
+    g = load(f"loss_{name}.npz")
+    cls, box, ctr = GI.make_head_outputs(seed, B, H, W, train=True)
+    for t in cls + box + ctr:
+        t.requires_grad_(True)
+    gts, labels, ignores = GI.make_gt(seed + 1000, B, H, W, **gk)
+    out = O.fcos_loss(cls, box, ctr, gts, labels, ignores, return_aux=True, **hk)
+    aux = out.pop("_aux")
+    # bit-exact contract: labels and regression targets
+    assert np.array_equal(aux["labels"].numpy().astype(np.int16), g["labels"])
+    assert np.array_equal(aux["bbox_targets"].numpy(), g["bbox_targets"])
+    for k in ("loss_cls", "loss_bbox", "loss_centerness", "loss_sisoft"):
+        if k in g.files:
+            assert k in out
+            np.testing.assert_allclose(float(out[k]), float(g[k]), rtol=1e-5, atol=1e-7)
+        else:
+            assert k not in out
+    sum(out.values()).backward()
+    g_cls = torch.cat([c.grad.permute(0, 2, 3, 1).reshape(-1, 80) for c in cls])
+    np.testing.assert_allclose(g_cls.reshape(-1)[::17].numpy(), g["dcls_sample"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(g_cls.abs().double().sum().item(), float(g["dcls_abs_sum"]), rtol=1e-5)
+    dbox = torch.cat([b.grad.permute(0, 2, 3, 1).reshape(-1, 4) for b in box]).numpy()
+    dctr = torch.cat([c.grad.permute(0, 2, 3, 1).reshape(-1) for c in ctr]).numpy()
+    np.testing.assert_allclose(dbox, g["dbox"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(dctr, g["dctr"], rtol=1e-4, atol=1e-8)
+
+
+def _resnet_fpn_state(seed_bb=31, seed_neck=32):
+    """State dicts with the reference's key order for ResNet-50 (caffe) and FPN(start_level=1, 5 outs)."""
+    from collections import OrderedDict
+    bb = OrderedDict()
+
+    def bn(prefix, c):
+        bb[prefix + ".weight"] = torch.zeros(c)
+        bb[prefix + ".bias"] = torch.zeros(c)
+        bb[prefix + ".running_mean"] = torch.zeros(c)
+        bb[prefix + ".running_var"] = torch.zeros(c)
+        bb[prefix + ".num_batches_tracked"] = torch.tensor(0)
+
+    bb["conv1.weight"] = torch.zeros(64, 3, 7, 7)
+    bn("bn1", 64)
+    inpl = 64
+    for li, nb in enumerate((3, 4, 6, 3)):
+        planes = 64 * 2 ** li
+        for bi in range(nb):
+            p = f"layer{li + 1}.{bi}"
+            bb[p + ".conv1.weight"] = torch.zeros(planes, inpl, 1, 1)
+            bn(p + ".bn1", planes)
+            bb[p + ".conv2.weight"] = torch.zeros(planes, planes, 3, 3)
+            bn(p + ".bn2", planes)
+            bb[p + ".conv3.weight"] = torch.zeros(planes * 4, planes, 1, 1)
+            bn(p + ".bn3", planes * 4)
+            if bi == 0:
+                bb[p + ".downsample.0.weight"] = torch.zeros(planes * 4, inpl, 1, 1)
+                bn(p + ".downsample.1", planes * 4)
+            inpl = planes * 4
+    neck = OrderedDict()
+    for i, c in enumerate((512, 1024, 2048)):
+        neck[f"lateral_convs.{i}.conv.weight"] = torch.zeros(256, c, 1, 1)
+        neck[f"lateral_convs.{i}.conv.bias"] = torch.zeros(256)
+    for i in range(5):
+        neck[f"fpn_convs.{i}.conv.weight"] = torch.zeros(256, 256, 3, 3)
+        neck[f"fpn_convs.{i}.conv.bias"] = torch.zeros(256)
+    return GI.fill_state_dict_(bb, seed_bb), GI.fill_state_dict_(neck, seed_neck)
+
+
+def test_backbone_fpn_match_reference():
+    g = load("backbone.npz")
+    bb, neck = _resnet_fpn_state()
+    x = GI.make_tensor(np.random.RandomState(33), 1, 3, 64, 96)
+    cs = O.resnet_forward(bb, x, depth=50)
+    ps = O.fpn_forward(neck, cs)
+    for i, c in enumerate(cs):
+        np.testing.assert_allclose(c.numpy(), g[f"c{i + 2}"], rtol=1e-4, atol=1e-4)
+    for i, p in enumerate(ps):
+        np.testing.assert_allclose(p.numpy(), g[f"p{i + 3}"], rtol=1e-4, atol=1e-4)
+
+
+def test_decode_gate_nms_match_reference():
+    g = load("decode.npz")
+    B, H, W = 2, 512, 640
+    cls, box, ctr = GI.make_head_outputs(41, B, H, W, train=False, cls_mean=-6.5)
+    shapes = [(500, 630, 3), (512, 600, 3)]
+    sfs = [[1.25] * 4, [0.8] * 4]
+    cands = O.decode_candidates(cls, box, ctr, shapes, sfs, nms_pre=1000, score_thr=0.05, rescale=True)
+    for b, (boxes, scores, labels, _) in enumerate(cands):
+        dets, lab = O.multiclass_nms(boxes, scores, labels, iou_thr=0.6, max_per_img=100)
+        np.testing.assert_allclose(dets.numpy(), g[f"dets{b}"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(lab.numpy(), g[f"labels{b}"])
+
+
+def test_hook_gate_int_truncation_matches_reference():
+    g = load("misc.npz")
+    gi = g["gate_in"]
+    dets = torch.from_numpy(gi[:, :5])
+    labels = torch.from_numpy(gi[:, 5].astype(np.int64))
+    kept = O.parse_det_results(dets, labels, 0.1)
+    assert np.array_equal(np.array([k["bbox"] for k in kept], dtype=np.int64).reshape(-1, 4), g["gate_bbox"])
+    np.testing.assert_allclose(np.array([k["score"] for k in kept]), g["gate_score"], rtol=0, atol=0)
+    assert np.array_equal(np.array([k["category_index"] for k in kept], dtype=np.int64), g["gate_cls"])
+
+
+def test_adathres_matches_reference():
+    g = load("misc.npz")
+    scores = json.loads(bytes(g["ada_scores_json"]).decode())
+    first = json.loads(bytes(g["ada_first_json"]).decode())
+    second = json.loads(bytes(g["ada_second_json"]).decode())
+    thr1, w1 = O.adathres(scores, None)
+    assert set(thr1) == set(first["thres"])
+    for c in thr1:
+        assert abs(thr1[c] - first["thres"][c]) < 1e-12
+        assert abs(w1[c] - first["cat"][c]) < 1e-12
+    thr2, w2 = O.adathres(scores, first["thres"])
+    assert set(thr2) == set(second["thres"])
+    for c in thr2:
+        assert abs(thr2[c] - second["thres"][c]) < 1e-12
+        assert abs(w2[c] - second["cat"][c]) < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["nofile", "file", "fixed", "none"])
+def test_pseudo_label_filter_matches_reference(tag):
+    g = load("misc.npz")
+    rects, scores, cls = g["filt_rects"].tolist(), g["filt_scores"].tolist(), g["filt_cls"].tolist()
+    if tag == "nofile":
+        gt, gl, ig = O.filter_pseudo_labels(rects, scores, cls, 640, 480, None, (0.1, 0.3))
+    elif tag == "file":
+        gt, gl, ig = O.filter_pseudo_labels(rects, scores, cls, 640, 480, {0: 0.33, 1: 0.31, 2: 0.35}, (0.1, 0.3))
+    elif tag == "fixed":
+        gt, gl, ig = O.filter_pseudo_labels(rects, scores, cls, 640, 480, None, (0.1, 0.4))
+    else:  # thres=None: every valid box is GT (labeled dataset)
+        gt, gl, ig = O.filter_pseudo_labels(rects, scores, cls, 640, 480, None, (2.0, 2.0))
+    assert np.array_equal(gt, g[f"filt_{tag}_gt"])
+    assert np.array_equal(gl, g[f"filt_{tag}_labels"])
+    assert np.array_equal(ig, g[f"filt_{tag}_ignore"])
+
+
+def test_ema_matches_reference_expression():
+    g = load("misc.npz")
+    keys = ["w", "bn.running_mean", "bn.num_batches_tracked"]
+    s = {k: torch.from_numpy(np.asarray(g["ema_s_" + k])) for k in keys}
+    t = {k: torch.from_numpy(np.asarray(g["ema_t_" + k])) for k in keys}
+    new = O.ema_update(t, s, 0.99)
+    for k in keys:
+        np.testing.assert_allclose(new[k].numpy(), np.asarray(g["ema_new_" + k], dtype=np.float32), rtol=1e-6)
