@@ -9,8 +9,9 @@
 //   MMA           tcgen05.mma.cta_group::1.kind::f16, M=128, N=bn, K=16, issued by one elected thread;
 //                 accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 //                 the MMAs of tile i+1.
-//   Warp roles    warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
-//                 (tcgen05.ld 32x32b -> scale/shift/residual/ReLU/mask/GroupNorm statistics -> global).
+//   Warp roles    warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue (two
+//                 warpgroups, one per 64-channel slab): tcgen05.ld 32x32b -> scale/shift/residual/ReLU/mask/
+//                 GroupNorm statistics -> 128B-swizzled smem staging tile -> TMA store (bf16) or direct stores.
 //   Scheduling    persistent: grid = min(#tiles, #SMs), static round-robin over the tile list of up to
 //                 DSLB_MAX_SEGS independent convs (e.g. 5 FPN levels x 2 FCOSHead towers in one launch).
 #include <new>
@@ -70,7 +71,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel
+// scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel.
+// Fast path (all 16 channels real): vector loads, no per-element guards.
 __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32_t (&rr)[16], float (&v)[16],
                                               int cb, bool fullchunk, bool valid, long long row) {
   const float* __restrict__ scale = sg.scale;
@@ -78,15 +80,29 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
   const __nv_bfloat16* __restrict__ resid = reinterpret_cast<const __nv_bfloat16*>(sg.residual);
   const __nv_bfloat16* __restrict__ rmask = reinterpret_cast<const __nv_bfloat16*>(sg.relu_mask);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = min(cb + j, sg.cout - 1);
-    float x = __uint_as_float(rr[j]);
-    if (scale) x *= __ldg(scale + c);
-    if (shift) x += __ldg(shift + c);
-    v[j] = x;
-  }
-  if (valid && resid) {
-    if (fullchunk) {
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  if (fullchunk) {
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(scale + cb) + j);
+        v[4 * j] *= t.x;
+        v[4 * j + 1] *= t.y;
+        v[4 * j + 2] *= t.z;
+        v[4 * j + 3] *= t.w;
+      }
+    }
+    if (shift) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(shift + cb) + j);
+        v[4 * j] += t.x;
+        v[4 * j + 1] += t.y;
+        v[4 * j + 2] += t.z;
+        v[4 * j + 3] += t.w;
+      }
+    }
+    if (valid && resid) {
       const uint4* rp = reinterpret_cast<const uint4*>(resid + row + cb);
       const uint4 r0 = rp[0], r1 = rp[1];
       const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -95,17 +111,16 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
         v[2 * j] += bf16_lo(w[j]);
         v[2 * j + 1] += bf16_hi(w[j]);
       }
-    } else {
+    }
+    if (cb + 16 <= sg.relu_nch) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (cb < sg.relu_nch) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (cb + j < sg.cout) v[j] += __bfloat162float(resid[row + cb + j]);
+        if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
-  if (valid && rmask) {
-    if (fullchunk) {
+    if (valid && rmask) {
       const uint4* mp = reinterpret_cast<const uint4*>(rmask + row + cb);
       const uint4 m0 = mp[0], m1 = mp[1];
       const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
@@ -114,15 +129,21 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
         if (!(bf16_lo(w[j]) > 0.f)) v[2 * j] = 0.f;
         if (!(bf16_hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
       }
-    } else {
+    }
+  } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (cb + j < sg.cout && !(__bfloat162float(rmask[row + cb + j]) > 0.f)) v[j] = 0.f;
+    for (int j = 0; j < 16; ++j) {
+      const int c = min(cb + j, sg.cout - 1);
+      if (scale) v[j] *= __ldg(scale + c);
+      if (shift) v[j] += __ldg(shift + c);
+      if (valid && resid && cb + j < sg.cout) v[j] += __bfloat162float(resid[row + cb + j]);
+      if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
+      if (valid && rmask && cb + j < sg.cout && !(__bfloat162float(rmask[row + cb + j]) > 0.f)) v[j] = 0.f;
     }
   }
 }
 
-__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev* __restrict__ P) {
+__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev* __restrict__ P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -228,11 +249,13 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp & 3;         // TMEM lane quadrant this warp may read
-    const int et = ew * 32 + lane;   // 0..127: row of the tile owned by this thread
+    // ------------------------------------------------------------------ epilogue (2 warpgroups x 4 warps)
+    const int ew = warp & 3;          // TMEM lane quadrant this warp may read
+    const int eg = (warp - 4) >> 2;   // warpgroup: handles 64-channel slab `eg` of every 128-channel round
+    const int et = ew * 32 + lane;    // 0..127: row of the tile owned by this thread
+    const bool leader = (ew == 0 && lane == 0);  // one per warpgroup: owns that group's staging slab + TMA stores
     int it = 0;
-    bool store_pending = false;      // (thread et==0) a TMA store may still be reading the staging buffer
+    bool store_pending = false;       // (leader) a TMA store may still be reading the staging buffer
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const ConvSegDev& sg = P->seg[find_seg(P, tile)];
       const int tl = tile - sg.tile_begin;
@@ -252,6 +275,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
       const int acc = it & 1;
       const int bn = sg.bn;
       const bool staged = sg.staged != 0;
+      const bool do_stats = sg.stats != nullptr;
       // all valid pixels of this tile in one image => GroupNorm partial sums reduce per tile
       const int pix_first = mt * BM;
       const int pix_last = min(pix_first + BM, sg.npix) - 1;
@@ -265,13 +289,15 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
       for (int r0 = 0; r0 < bn; r0 += 128) {  // rounds of <=128 channels (= the staging buffer)
         const int rend = min(r0 + 128, bn);
         if (staged) {
-          if (et == 0 && store_pending) {
+          if (leader && store_pending) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             store_pending = false;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer is free
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");  // this group's staging slab is free
         }
-        for (int c0 = r0; c0 < rend; c0 += 16) {
+        const int cbeg = r0 + eg * 64;
+        const int cend = min(cbeg + 64, rend);
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(taddr + c0, rr);
           tmem_ld_wait();
@@ -279,20 +305,30 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
           const bool fullchunk = (cb + 16 <= sg.cout);
           float v[16];
           epilogue_math(sg, rr, v, cb, fullchunk, valid, row);
-          if (sg.stats) {
+          if (do_stats) {
             // GroupNorm partial sums of the two 8-channel halves of this chunk, reduced over the warp's 32 pixels
             // with a 6-shuffle butterfly; lanes 0/8/16/24 end up with (s1,h0) (s2,h0) (s1,h1) (s2,h1).
             float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
             if (valid) {
+              if (fullchunk) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (cb + j < sg.cout) {
+                for (int j = 0; j < 8; ++j) {
                   a += v[j];
-                  c += v[j] * v[j];
-                }
-                if (cb + 8 + j < sg.cout) {
+                  c = fmaf(v[j], v[j], c);
                   b += v[8 + j];
-                  d += v[8 + j] * v[8 + j];
+                  d = fmaf(v[8 + j], v[8 + j], d);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (cb + j < sg.cout) {
+                    a += v[j];
+                    c = fmaf(v[j], v[j], c);
+                  }
+                  if (cb + 8 + j < sg.cout) {
+                    b += v[8 + j];
+                    d = fmaf(v[8 + j], v[8 + j], d);
+                  }
                 }
               }
             }
@@ -378,19 +414,17 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
         }
         if (staged) {
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (et == 0) {
-            const int nslab = (rend - r0 + 63) >> 6;
-            for (int sl = 0; sl < nslab; ++sl)
-              tma_store_2d(&sg.tmY, sOut + sl * (BM * 128), nt * bn + r0 + sl * 64, pix_first);
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + eg) : "memory");
+          if (leader && cbeg < rend) {
+            tma_store_2d(&sg.tmY, sOut + eg * (BM * 128), nt * bn + cbeg, pix_first);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             store_pending = true;
           }
         }
       }
-      if (sg.stats && tile_uniform) {
-        // all four warps have passed the last round's bar.sync 2 => sStat is complete for this tile
-        if (et < 64) {
+      if (do_stats && tile_uniform) {
+        asm volatile("bar.sync 5, 256;" ::: "memory");  // both warpgroups have written their sStat entries
+        if (eg == 0 && et < 64) {
           const int hidx = et >> 1, k = et & 1;  // 8-channel half index inside the tile, (sum | sumsq)
           const int cfirst = nt * bn + hidx * 8;
           if (hidx * 8 < bn && cfirst < sg.cout) {
@@ -400,9 +434,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const ConvParamsDev*
             atomicAdd(dst + k, (double)tot);
           }
         }
+        asm volatile("bar.sync 6, 256;" ::: "memory");  // sStat may be overwritten by the next tile
       }
     }
-    if (et == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (leader && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -564,7 +599,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
 extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
   const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, 256, CONV_SMEM, (cudaStream_t)stream>>>(plan->dev);
+  conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(plan->dev);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }

@@ -95,6 +95,103 @@ int dslb_wgrad_plan_run(const dslb_wgrad_plan_t* plan, void* stream);
 void dslb_wgrad_plan_destroy(dslb_wgrad_plan_t* plan);
 double dslb_wgrad_plan_flops(const dslb_wgrad_plan_t* plan);
 
+/* ------------------------------------------------------------------------------------------------------
+ * HBM-bound glue around the convs (each replaces the torch ops named).
+ * ---------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 -> NHWC bf16 with channels zero-padded to Cpad (input of the plugin modules: the reference's tensors
+ * are NCHW fp32, mmdet/models/detectors/single_stage.py:136-141). */
+int dslb_nchw_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream);
+/* pixel-major rows of `ld` elements (bf16, or fp32 if x_is_fp32) -> NCHW fp32, first C channels. */
+int dslb_nhwc_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, int ld, int x_is_fp32, void* stream);
+/* im2col of the 7x7/2 pad-3 stem conv (resnet.py:597-610) from the NCHW fp32 image: out bf16 [N*Ho*Wo][192],
+ * k = (r*7+s)*3 + c, zero for k >= 147; the stem then runs as a 1x1 tensor-core conv with Cin = 192. */
+int dslb_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream);
+/* nn.MaxPool2d(3, 2, 1) (resnet.py:611), NHWC bf16. */
+int dslb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* FPN top-down: dst += nearest_upsample(src) (necks/fpn.py:163-172) and its backward w.r.t. src. */
+int dslb_upsample_add(void* dst, const void* src, int N, int H, int W, int h, int w, int C, void* stream);
+int dslb_upsample_add_bwd(void* dsrc, const void* ddst, int N, int H, int W, int h, int w, int C, void* stream);
+/* bf16 elementwise over n elements (n % 8 == 0): mode 0 y=relu(x); 1 y=(m>0)?x:0 (ReLU backward); 2 y=x+m. */
+int dslb_relu_family(const void* x, const void* m, void* y, long long n, int mode, void* stream);
+
+/* GroupNorm(groups) + ReLU after a conv (mmcv ConvModule, anchor_free_head.py:95-139; norm_cfg fcos_head.py:82),
+ * driven by the statistics the conv epilogue accumulated. Up to DSLB_MAX_SEGS maps per launch. */
+typedef struct dslb_gn_seg {
+  const void* x;       /* bf16 pre-norm conv output [N*HW][C]                                            */
+  void* y;             /* fwd: bf16 relu(gn(x)); bwd: bf16 gradient w.r.t. x                             */
+  const void* dz;      /* bwd only: bf16 gradient w.r.t. the post-ReLU output                            */
+  const double* stats; /* [N][groups][DSLB_GN_STAT_STRIDE]                                               */
+  const float* gamma;  /* [C]                                                                            */
+  const float* beta;   /* [C]                                                                            */
+  double* red;         /* bwd only: [N][C][2] scratch, pre-zeroed (sum dy, sum dy*xhat)                  */
+  float* dbias;        /* bwd only: [C], += gradient of the conv bias in front of the norm               */
+  int32_t N, HW;
+} dslb_gn_seg_t;
+int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream);
+/* backward: dslb_gn_bwd_blocks -> size of the block table; dslb_gn_bwd_plan fills a HOST table of 2*blocks ints the
+ * caller copies to the device once; dslb_gn_bwd runs the reduce + apply passes (C must be 256). */
+int dslb_gn_bwd_blocks(const dslb_gn_seg_t* segs, int nseg);
+int dslb_gn_bwd_plan(const dslb_gn_seg_t* segs, int nseg, int* blk_tab_host);
+int dslb_gn_bwd(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, const int* blk_tab_dev, int nblocks,
+                void* stream);
+/* dgamma[c] += sum_n red[n][c][1]; dbeta[c] += sum_n red[n][c][0] */
+int dslb_gn_bwd_params(const double* red, float* dgamma, float* dbeta, int N, int C, void* stream);
+
+/* OIHW fp32 master weights -> packed bf16 [R*S][rows_pad][cols_pad] (zero padded), optionally scaled per output
+ * channel (frozen-BN fold). transpose=1 builds the dgrad operand (180-degree rotated taps, in/out swapped). */
+int dslb_pack_weight(const float* w, void* out, int O, int I, int R, int S, int rows_pad, int cols_pad,
+                     const float* oscale, int transpose, void* stream);
+/* packed fp32 wgrad [R*S][rows][I] -> OIHW fp32 (x oscale[o]); accumulate=1 adds into g. */
+int dslb_unpack_wgrad(const float* dw, float* g, int O, int I, int R, int S, int rows, const float* oscale,
+                      int accumulate, void* stream);
+/* frozen BatchNorm2d in eval mode folded to y = x*scale + shift (resnet.py:647-656). */
+int dslb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                 float* shift, int C, void* stream);
+/* out[c] += sum_p x[p][c] over a pixel-major bf16 matrix (conv bias gradient). */
+int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense pseudo-label path: FCOSHead.loss (mmdet/models/dense_heads/fcos_head.py:170-338) =
+ * get_points (:550-560, anchor_free_head.py:287-321) + get_targets/_get_target_single (:562-705) for the
+ * (pseudo-)GT boxes and for the ignore boxes (:208-215) + ignore / unlabeled weights (:217-235, :297-307) +
+ * centerness_target (:707-726) + FocalLoss (losses/focal_loss.py:11-56) + GIoULoss (losses/iou_loss.py:85-102,
+ * 329-366; core/bbox/iou_calculators/iou2d_calculator.py:214-260; core/bbox/transforms.py:119-162) + sigmoid BCE
+ * (losses/cross_entropy_loss.py:73-112) + the scale-invariant soft loss (:312-333), forward AND backward.
+ * Flat point order everywhere = the reference's: level-major, then image, then row-major (y, x).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct dslb_fcos_level {
+  const float* cls;     /* fp32 logits, pixel-major [B*h*w][ld_cls]                                       */
+  const float* regctr;  /* fp32 [B*h*w][8]: 0-3 bbox_pred = relu(scale*conv_reg), 4 centerness logit      */
+  void* dcls_bf16;      /* out (or NULL): bf16 d loss/d logits [B*h*w][ld_dcls] (pad columns untouched)   */
+  float* dcls_f32;      /* out (or NULL): fp32 d loss/d logits [B*h*w][C]                                 */
+  void* dregctr_bf16;   /* out (or NULL): bf16 [B*h*w][ld_dreg]: 0-3 d loss/d conv_reg, 4 d/d ctr, 5-7 =0 */
+  float* dregctr_f32;   /* out (or NULL): fp32 [B*h*w][8]: 0-3 d loss/d bbox_pred, 4 d/d ctr logit        */
+  int32_t h, w, stride;
+  int32_t ld_cls, ld_dcls, ld_dreg;
+  float rr_lo, rr_hi;   /* regress range of the level                                                     */
+  float scale;          /* value of the level's Scale parameter (chain rule through relu(scale*x))        */
+  float cs_radius;      /* float(stride * center_sample_radius)                                           */
+} dslb_fcos_level_t;
+
+/* Target assignment. gt_boxes [sumG][4] fp32, gt_labels [sumG] int64, gt_off [B+1] int32 (all device); ig_* the
+ * same for the ignore boxes or NULL. Images [0,n_labeled) are labeled (weight 1), the others x loss_weight.
+ * Outputs (flat point order): labels int64 (num_classes = background), bbox_targets [P][4], weights [P] (focal
+ * weight: ignore mask x unlabeled weight), ctr_targets [P] (0 on non-positives); counts[0] += num_pos,
+ * counts[1] += sum ctr_targets (fp64, pre-zeroed). labels / bbox_targets are bit-exact with the reference. */
+int dslb_fcos_targets(const dslb_fcos_level_t* levels, int nlevels, int B, int num_classes, const float* gt_boxes,
+                      const int64_t* gt_labels, const int32_t* gt_off, const float* ig_boxes, const int32_t* ig_off,
+                      int center_sampling, int norm_on_bbox, float loss_weight, int n_labeled, int64_t* labels,
+                      float* bbox_targets, float* weights, float* ctr_targets, double* counts, void* stream);
+/* norm[0] = max(counts[0]/world_size, 1), norm[1] = max(counts[1]/world_size, 1e-6): the reduce_mean'd normalisers
+ * (fcos_head.py:266,273-274); `counts` holds the SUM over ranks (all-reduce it between the two calls). */
+int dslb_fcos_norm(const double* counts, float world_size, float* norm, void* stream);
+/* Losses + gradients. loss_sums[0..3] += loss_cls, loss_bbox, loss_centerness, loss_sisoft (fp64, pre-zeroed);
+ * dscale[l] += d loss / d scales[l].scale (or NULL). si_weight: 0 = off, else the (warm-up adjusted) soft weight. */
+int dslb_fcos_loss(const dslb_fcos_level_t* levels, int nlevels, int B, int num_classes, const int64_t* labels,
+                   const float* bbox_targets, const float* weights, const float* ctr_targets, const float* norm,
+                   float alpha, float gamma, float loss_weight, int n_labeled, float si_weight, double* loss_sums,
+                   float* dscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

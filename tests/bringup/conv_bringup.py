@@ -95,7 +95,7 @@ def run_case(name, N, H, W, Cin, Cout, R, stride, pad, out_fp32=False, relu=Fals
         e1 = ((stats[..., 0] - s1).abs().max() / (s1.abs().max() + 1e-9)).item()
         e2 = ((stats[..., 1] - s2).abs().max() / (s2.abs().max() + 1e-9)).item()
         extra += f" gn_sum_err={e1:.2e} gn_sq_err={e2:.2e}"
-        ok = ok and e1 < 1e-3 and e2 < 1e-3
+        ok = ok and e1 < 5e-3 and e2 < 5e-3
     line = f"[{'OK' if ok else 'FAIL'}] {name}: max_abs_err={err:.3e} rel={err / den:.3e}{extra}"
     if timing:
         for _ in range(3):
