@@ -52,6 +52,26 @@ class WgradSeg(C.Structure):
     ]
 
 
+class GnSeg(C.Structure):
+    """dslb_gn_seg_t"""
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("dz", C.c_void_p), ("stats", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("red", C.c_void_p), ("dbias", C.c_void_p),
+        ("N", C.c_int32), ("HW", C.c_int32),
+    ]
+
+
+class FcosLevel(C.Structure):
+    """dslb_fcos_level_t"""
+    _fields_ = [
+        ("cls", C.c_void_p), ("regctr", C.c_void_p), ("dcls_bf16", C.c_void_p), ("dcls_f32", C.c_void_p),
+        ("dregctr_bf16", C.c_void_p), ("dregctr_f32", C.c_void_p),
+        ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
+        ("ld_cls", C.c_int32), ("ld_dcls", C.c_int32), ("ld_dreg", C.c_int32),
+        ("rr_lo", C.c_float), ("rr_hi", C.c_float), ("scale", C.c_float), ("cs_radius", C.c_float),
+    ]
+
+
 lib.dslb_last_error.restype = C.c_char_p
 lib.dslb_version.restype = C.c_int
 
@@ -73,6 +93,36 @@ _proto("dslb_wgrad_plan_create", C.c_int, C.POINTER(WgradSeg), C.c_int, C.POINTE
 _proto("dslb_wgrad_plan_run", C.c_int, C.c_void_p, C.c_void_p)
 _proto("dslb_wgrad_plan_destroy", None, C.c_void_p)
 _proto("dslb_wgrad_plan_flops", C.c_double, C.c_void_p)
+
+VP, I, LL, F, D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_proto("dslb_nchw_to_nhwc_bf16", I, VP, VP, I, I, I, I, I, VP)
+_proto("dslb_nhwc_to_nchw_f32", I, VP, VP, I, I, I, I, I, I, VP)
+_proto("dslb_stem_im2col", I, VP, VP, I, I, I, VP)
+_proto("dslb_maxpool3x3s2", I, VP, VP, I, I, I, I, VP)
+_proto("dslb_upsample_add", I, VP, VP, I, I, I, I, I, I, VP)
+_proto("dslb_upsample_add_bwd", I, VP, VP, I, I, I, I, I, I, VP)
+_proto("dslb_relu_family", I, VP, VP, VP, LL, I, VP)
+_proto("dslb_gn_apply_relu", I, C.POINTER(GnSeg), I, I, I, F, VP)
+_proto("dslb_gn_bwd_blocks", I, C.POINTER(GnSeg), I)
+_proto("dslb_gn_bwd_plan", I, C.POINTER(GnSeg), I, VP)
+_proto("dslb_gn_bwd", I, C.POINTER(GnSeg), I, I, I, F, VP, I, VP)
+_proto("dslb_gn_bwd_params", I, VP, VP, VP, I, I, VP)
+_proto("dslb_pack_weight", I, VP, VP, I, I, I, I, I, I, VP, I, VP)
+_proto("dslb_unpack_wgrad", I, VP, VP, I, I, I, I, I, VP, I, VP)
+_proto("dslb_bn_fold", I, VP, VP, VP, VP, F, VP, VP, I, VP)
+_proto("dslb_colsum", I, VP, VP, LL, I, I, VP)
+_proto("dslb_conv_dgrad_naive", I, VP, VP, VP, I, I, I, I, I, I, I, I, I, I, VP)
+_proto("dslb_fcos_targets", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, I, I, F, I, VP, VP, VP, VP, VP, VP)
+_proto("dslb_fcos_norm", I, VP, F, VP, VP)
+_proto("dslb_fcos_loss", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, F, F, F, I, F, VP, VP, VP, VP)
+_proto("dslb_ema_update", I, VP, VP, LL, F, F, VP)
+_proto("dslb_sq_norm", I, VP, LL, VP, VP)
+_proto("dslb_clip_coef", I, VP, F, VP, VP)
+_proto("dslb_sgd_step", I, VP, VP, VP, LL, VP, VP, F, F, F, I, VP)
+_proto("dslb_fcos_point_scores", I, VP, VP, VP, LL, I, I, VP)
+_proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I, VP, VP, VP, VP, VP, I, VP)
+
+GN_STAT_STRIDE = 32
 
 
 def check(rc, what=""):

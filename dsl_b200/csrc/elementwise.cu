@@ -467,6 +467,40 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
   }
 }
 
+
+// Direct (CUDA-core) data gradient for the two tiny stride-2 3x3 FPN convs (P6, P7: <= 13x21 outputs), where a
+// tensor-core formulation would need a strided scatter: dx[n,h,w,ci] (+)= sum_{r,s,co} dy[n,p,q,co] * Wp[r*S+s][co][ci]
+// with h = p*stride - pad + r. Wp is the packed fprop weight (ci contiguous => coalesced across the warp).
+__global__ void conv_dgrad_naive_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ wp,
+                                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int Ci, int Co, int co_pad,
+                                        int R, int S, int stride, int pad, int Ho, int Wo, int accumulate) {
+  const long long total = (long long)N * H * W * Ci;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int ci = t % Ci;
+    const long long pix = t / Ci;
+    const int w = pix % W;
+    const int h = (pix / W) % H;
+    const int n = pix / ((long long)W * H);
+    float acc = accumulate ? __bfloat162float(dx[t]) : 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int hp = h + pad - r;
+      if (hp < 0 || hp % stride != 0) continue;
+      const int p = hp / stride;
+      if (p >= Ho) continue;
+      for (int s = 0; s < S; ++s) {
+        const int wq = w + pad - s;
+        if (wq < 0 || wq % stride != 0) continue;
+        const int q = wq / stride;
+        if (q >= Wo) continue;
+        const __nv_bfloat16* dyp = dy + (((long long)n * Ho + p) * Wo + q) * Co;
+        const __nv_bfloat16* wpp = wp + ((long long)(r * S + s) * co_pad) * Ci + ci;
+        for (int co = 0; co < Co; ++co) acc += __bfloat162float(dyp[co]) * __bfloat162float(wpp[(long long)co * Ci]);
+      }
+    }
+    dx[t] = __float2bfloat16_rn(acc);
+  }
+}
+
 }  // namespace dslb
 
 using namespace dslb;
@@ -641,5 +675,16 @@ extern "C" int dslb_bn_fold(const float* gamma, const float* beta, const float* 
 extern "C" int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream) {
   DSLB_CHECK_ARG(x && out && ld >= C, "dslb_colsum: bad arguments");
   colsum_kernel<<<grid_for(npix / 8 + 1, 1, 4), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, npix, ld, C);
+  LAUNCH_CHECK();
+}
+
+extern "C" int dslb_conv_dgrad_naive(const void* dy, const void* wp, void* dx, int N, int H, int W, int Ci, int Co,
+                                     int co_pad, int R, int S, int stride, int pad, int accumulate, void* stream) {
+  DSLB_CHECK_ARG(dy && wp && dx && stride >= 1, "dslb_conv_dgrad_naive: bad arguments");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)N * H * W * Ci;
+  conv_dgrad_naive_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)wp, (__nv_bfloat16*)dx, N, H, W, Ci, Co, co_pad, R, S, stride, pad,
+      Ho, Wo, accumulate);
   LAUNCH_CHECK();
 }

@@ -51,6 +51,7 @@ struct LossParams {
   float alpha, gamma;
   double* loss_sums;  // [0] cls [1] bbox [2] centerness [3] sisoft
   float* dscale;      // [nlevels] gradient of the per-level Scale parameter
+  const float* level_scales;  // [nlevels] device copy of the Scale values (overrides lv[].scale when non-null)
   float si_weight;    // 0 = off; else soft_weight (or soft_weight/1000 while warming up); needs odd B
 };
 
@@ -423,12 +424,13 @@ __global__ void __launch_bounds__(256) fcos_loss_kernel(const __grid_constant__ 
         dr[4] = (1.f / (1.f + expf(-cl)) - ct) * fw * inv_npos;
         // chain through bbox_pred = relu(scale_l * conv_reg): conv output = bbox_pred / scale_l where positive
         const float bpv[4] = {bp.x, bp.y, bp.z, bp.w};
+        const float lscale = P.level_scales ? __ldg(P.level_scales + lvl) : L.scale;
         float ds = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (bpv[k] > 0.f) {
-            dconv[k] = dr[k] * L.scale;
-            ds += dr[k] * (bpv[k] / L.scale);
+            dconv[k] = dr[k] * lscale;
+            ds += dr[k] * (bpv[k] / lscale);
           }
         }
         if (P.dscale && ds != 0.f) atomicAdd(P.dscale + lvl, ds);
@@ -547,7 +549,8 @@ extern "C" int dslb_fcos_norm(const double* counts, float world_size, float* nor
 extern "C" int dslb_fcos_loss(const dslb_fcos_level_t* levels, int nlevels, int B, int num_classes,
                               const int64_t* labels, const float* bbox_targets, const float* weights,
                               const float* ctr_targets, const float* norm, float alpha, float gamma, float loss_weight,
-                              int n_labeled, float si_weight, double* loss_sums, float* dscale, void* stream) {
+                              int n_labeled, float si_weight, const float* level_scales, double* loss_sums,
+                              float* dscale, void* stream) {
   LossParams P;
   int rc = fill_loss_params(P, levels, nlevels, B, num_classes);
   if (rc != DSLB_OK) return rc;
@@ -572,6 +575,7 @@ extern "C" int dslb_fcos_loss(const dslb_fcos_level_t* levels, int nlevels, int 
   P.si_weight = si_weight;
   P.loss_sums = loss_sums;
   P.dscale = dscale;
+  P.level_scales = level_scales;
   const long long total = P.npoints * (num_classes / 4);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 8;

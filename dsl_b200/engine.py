@@ -1,0 +1,794 @@
+"""Host-side execution plan of the FCOS detector on the C-ABI kernels (libdslb.so).
+
+One `FCOSNet` = one set of weights (student or EMA teacher) + every activation / gradient buffer and every TMA launch
+plan for a FIXED input shape (B, H, W). Building it allocates everything once; after that a forward or a
+forward+backward is a flat list of pre-bound C calls on the current CUDA stream — no allocation, no host sync — so the
+whole teacher+student step can be captured in a CUDA graph (see DSLEngine).
+
+Reference functions replaced (paths relative to the reference root):
+  ResNet.forward / Bottleneck.forward      mmdet/models/backbones/resnet.py:630-645, 262-301
+  FPN.forward                              mmdet/models/necks/fpn.py:151-202
+  FCOSHead.forward / forward_single        mmdet/models/dense_heads/fcos_head.py:118-168, anchor_free_head.py:197-217
+  FCOSHead.loss (+ get_targets, ...)       mmdet/models/dense_heads/fcos_head.py:170-338, 562-726
+  autograd backward of all of the above    (torch autograd in the reference)
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from .params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec
+
+BF16 = torch.bfloat16
+STRIDES = (8, 16, 32, 64, 128)
+REGRESS_RANGES = ((-1, 64), (64, 128), (128, 256), (256, 512), (512, 1e8))
+INF = 1e8
+
+
+def ceil_to(x, m):
+    return (x + m - 1) // m * m
+
+
+def conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+class ConvPlan:
+    """dslb_conv_plan_* wrapper; `segs` is a list of dicts of dslb_conv_seg_t fields (tensors for pointers)."""
+
+    def __init__(self, segs, what="conv"):
+        self.what = what
+        self.keep = []
+        arr = (L.ConvSeg * len(segs))()
+        for a, s in zip(arr, segs):
+            for k, v in s.items():
+                if isinstance(v, torch.Tensor):
+                    self.keep.append(v)
+                    setattr(a, k, v.data_ptr())
+                elif v is not None:
+                    setattr(a, k, v)
+        self.plan = C.c_void_p()
+        L.check(L.lib.dslb_conv_plan_create(arr, len(segs), C.byref(self.plan)), what)
+        self.flops = L.lib.dslb_conv_plan_flops(self.plan)
+
+    def run(self):
+        L.check(L.lib.dslb_conv_plan_run(self.plan, L.cur_stream()), self.what)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                L.lib.dslb_conv_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+
+class WgradPlan:
+    def __init__(self, segs, what="wgrad"):
+        self.what = what
+        self.keep = []
+        arr = (L.WgradSeg * len(segs))()
+        for a, s in zip(arr, segs):
+            for k, v in s.items():
+                if isinstance(v, torch.Tensor):
+                    self.keep.append(v)
+                    setattr(a, k, v.data_ptr())
+                else:
+                    setattr(a, k, v)
+        self.plan = C.c_void_p()
+        L.check(L.lib.dslb_wgrad_plan_create(arr, len(segs), C.byref(self.plan)), what)
+        self.flops = L.lib.dslb_wgrad_plan_flops(self.plan)
+
+    def run(self):
+        L.check(L.lib.dslb_wgrad_plan_run(self.plan, L.cur_stream()), self.what)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                L.lib.dslb_wgrad_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+
+class ConvW:
+    """Derived device state of one conv: packed bf16 operands (frozen BatchNorm folded in), shift vector, wgrad slot."""
+
+    def __init__(self, net, wname, bias=None, bn=None, stride=1, pad=0, need_dgrad=False, trainable=False,
+                 dy_ld=None):
+        st = net.store
+        self.net = net
+        self.wname = wname
+        self.w = st[wname]
+        self.O, self.I, self.R, self.S = self.w.shape
+        self.stride, self.pad = stride, pad
+        self.cout_pad = ceil_to(self.O, 16)
+        dev = st.device
+        self.wp = torch.zeros(self.R * self.S, self.cout_pad, self.I, dtype=BF16, device=dev)
+        self.bn = bn
+        self.scale = None
+        if bn is not None:
+            self.scale = torch.empty(self.O, dtype=torch.float32, device=dev)
+            self.shift = torch.empty(self.O, dtype=torch.float32, device=dev)
+        else:
+            self.shift = st[bias] if bias is not None else None
+        self.bias_name = bias
+        self.need_dgrad = need_dgrad
+        self.trainable = trainable
+        self.dy_ld = dy_ld or ceil_to(self.O, 64)  # channel stride of the gradient buffer feeding dgrad/wgrad
+        if need_dgrad:
+            self.wpT = torch.zeros(self.R * self.S, ceil_to(self.I, 16), self.dy_ld, dtype=BF16, device=dev)
+        self.dw = None
+        if trainable:
+            self.dw = net.alloc_dw(self.R * self.S * self.O * self.I).view(self.R * self.S, self.O, self.I)
+
+    def repack(self):
+        s = L.cur_stream()
+        st = self.net.store
+        if self.bn is not None:
+            L.check(L.lib.dslb_bn_fold(L.ptr(st[self.bn + ".weight"]), L.ptr(st[self.bn + ".bias"]),
+                                       L.ptr(st[self.bn + ".running_mean"]), L.ptr(st[self.bn + ".running_var"]),
+                                       1e-5, L.ptr(self.scale), L.ptr(self.shift), self.O, s), "bn_fold")
+        L.check(L.lib.dslb_pack_weight(L.ptr(self.w), L.ptr(self.wp), self.O, self.I, self.R, self.S, self.cout_pad,
+                                       self.I, L.ptr(self.scale), 0, s), "pack_weight")
+        if self.need_dgrad:
+            L.check(L.lib.dslb_pack_weight(L.ptr(self.w), L.ptr(self.wpT), self.O, self.I, self.R, self.S,
+                                           self.wpT.shape[1], self.wpT.shape[2], L.ptr(self.scale), 1, s),
+                    "pack_weight(T)")
+
+    def unpack_grad(self):
+        """packed fp32 wgrad -> OIHW gradient view (x folded BN scale)."""
+        g = self.net.grad_view(self.wname)
+        L.check(L.lib.dslb_unpack_wgrad(L.ptr(self.dw), L.ptr(g), self.O, self.I, self.R, self.S, self.O,
+                                        L.ptr(self.scale), 0, L.cur_stream()), "unpack_wgrad")
+
+    # ---- segment builders -------------------------------------------------------------------------------
+    def fseg(self, x, y, N, H, W, **kw):
+        """fprop segment: y = conv(x)."""
+        d = dict(x=x, w=self.wp, y=y, N=N, H=H, W=W, Cin=self.I, Cout=self.O, cout_pad=self.cout_pad, R=self.R,
+                 S=self.S, stride=self.stride, pad=self.pad, ldc=self.O, shift=self.shift)
+        d.update(kw)
+        return d
+
+    def dseg(self, dy, dx, N, Ho, Wo, Hin, Win, **kw):
+        """dgrad segment: dx = conv_transpose(dy). Stride-2 1x1 convs scatter into the (Hin, Win) map."""
+        d = dict(x=dy, w=self.wpT, y=dx, N=N, H=Ho, W=Wo, Cin=self.dy_ld, Cout=self.I, cout_pad=self.wpT.shape[1],
+                 R=self.R, S=self.S, stride=1, pad=self.R - 1 - self.pad, ldc=self.I)
+        if self.stride == 2:
+            assert self.R == 1, "tensor-core dgrad of strided convs is only implemented for 1x1"
+            d.update(scatter2=1, Hs=Hin, Ws=Win)
+        d.update(kw)
+        return d
+
+    def wseg(self, x, dy, N, H, W):
+        return dict(x=x, dy=dy, dw=self.dw, N=N, H=H, W=W, Cin=self.I, Cout=self.O, ldy=self.dy_ld, dw_rows=self.O,
+                    R=self.R, S=self.S, stride=self.stride, pad=self.pad)
+
+
+class FCOSNet:
+    """ResNet-50/101 + FPN + FCOSHead for a fixed (B, H, W); `train=True` also builds the backward plan."""
+
+    def __init__(self, B, H, W, depth=50, num_classes=80, train=True, store=None, device="cuda", seed=0,
+                 loss_weight=1.0, soft_weight=0.0, center_sampling=True, radius=1.5, norm_on_bbox=True,
+                 max_boxes=1024, parity_outputs=False):
+        assert H % 32 == 0 and W % 32 == 0, "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
+        self.B, self.H, self.W, self.depth, self.C = B, H, W, depth, num_classes
+        self.train = train
+        self.dev = torch.device(device)
+        self.loss_weight, self.soft_weight = float(loss_weight), float(soft_weight)
+        self.center_sampling, self.radius, self.norm_on_bbox = center_sampling, radius, norm_on_bbox
+        self.parity_outputs = parity_outputs
+        if store is None:
+            store = ParamStore(resnet_spec(depth) + fpn_spec() + head_spec(num_classes), device).init_reference(seed)
+        self.store = store
+        self._dw_list = []
+        self.fwd_ops, self.bwd_ops, self.repack_ops = [], [], []
+        self.convs = []
+        self.flops_fwd = 0.0
+        self.flops_bwd = 0.0
+        if train:
+            self.grad = torch.zeros(store.n_train, dtype=torch.float32, device=self.dev)
+        self._build_backbone()
+        self._build_fpn()
+        self.head_op_start = len(self.fwd_ops)
+        self._build_head()
+        if train:
+            self._build_loss()
+            self._build_head_bwd()
+            self._build_fpn_bwd()
+            self._build_backbone_bwd()
+        self.repack()
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def buf(self, *shape, dtype=BF16):
+        return torch.zeros(*shape, dtype=dtype, device=self.dev)
+
+    def alloc_dw(self, n):
+        """fp32 packed weight-gradient accumulator of one conv (zeroed at the start of every backward)."""
+        t = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self._dw_list.append(t)
+        return t
+
+    def grad_view(self, name):
+        o, n = self.store.offsets[name]
+        assert o + n <= self.store.n_train, name + " is not trainable"
+        return self.grad[o:o + n]
+
+    def conv(self, *a, **k):
+        c = ConvW(self, *a, **k)
+        self.convs.append(c)
+        return c
+
+    def add_fwd(self, fn):
+        self.fwd_ops.append(fn)
+
+    def add_bwd(self, fn):
+        self.bwd_ops.append(fn)
+
+    def plan_fwd(self, segs, what):
+        p = ConvPlan(segs, what)
+        self.flops_fwd += p.flops
+        self.add_fwd(p.run)
+        return p
+
+    def plan_bwd(self, segs, what):
+        p = ConvPlan(segs, what)
+        self.flops_bwd += p.flops
+        self.add_bwd(p.run)
+        return p
+
+    def plan_wgrad(self, segs, what):
+        p = WgradPlan(segs, what)
+        self.flops_bwd += p.flops
+        self.add_bwd(p.run)
+        return p
+
+    def ew(self, fn_name, *args):
+        """Bind an elementwise C call (pointers resolved now, stream at call time)."""
+        fn = getattr(L.lib, fn_name)
+        cargs = [L.ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
+        keep = [a for a in args if isinstance(a, torch.Tensor)]
+
+        def run(_fn=fn, _a=cargs, _k=keep, _n=fn_name):
+            L.check(_fn(*_a, L.cur_stream()), _n)
+
+        return run
+
+    # ------------------------------------------------------------------------------------------ backbone
+    def _build_backbone(self):
+        B, H, W = self.B, self.H, self.W
+        st = self.store
+        self.img = self.buf(B, 3, H, W, dtype=torch.float32)  # NCHW fp32 input, as the reference feeds it
+        H2, W2 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+        H4, W4 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
+        # stem: im2col (K = 7*7*3 = 147 -> 192) + tensor-core 1x1 conv with folded BN + ReLU, then max-pool
+        self.stem_cols = self.buf(B, H2, W2, 192)
+        self.stem_out = self.buf(B, H2, W2, 64)
+        self.x0 = self.buf(B, H4, W4, 64)
+        self.stem_wp = torch.zeros(1, 64, 192, dtype=BF16, device=self.dev)
+        self.stem_scale = torch.empty(64, dtype=torch.float32, device=self.dev)
+        self.stem_shift = torch.empty(64, dtype=torch.float32, device=self.dev)
+
+        def repack_stem():
+            s = L.cur_stream()
+            L.check(L.lib.dslb_bn_fold(L.ptr(st["backbone.bn1.weight"]), L.ptr(st["backbone.bn1.bias"]),
+                                       L.ptr(st["backbone.bn1.running_mean"]), L.ptr(st["backbone.bn1.running_var"]),
+                                       1e-5, L.ptr(self.stem_scale), L.ptr(self.stem_shift), 64, s), "bn_fold")
+            w = st["backbone.conv1.weight"]  # [64,3,7,7] -> [64][(r*7+s)*3+c]
+            wk = (w.permute(0, 2, 3, 1).reshape(64, 147) * self.stem_scale[:, None]).to(BF16)
+            self.stem_wp[0, :, :147].copy_(wk)
+
+        self.repack_ops.append(repack_stem)
+        self.add_fwd(self.ew("dslb_stem_im2col", self.img, self.stem_cols, B, H, W))
+        self.plan_fwd([dict(x=self.stem_cols, w=self.stem_wp, y=self.stem_out, N=B, H=H2, W=W2, Cin=192, Cout=64,
+                            cout_pad=64, R=1, S=1, stride=1, pad=0, ldc=64, shift=self.stem_shift, relu_nch=64)],
+                      "stem")
+        self.add_fwd(self.ew("dslb_maxpool3x3s2", self.stem_out, self.x0, B, H2, W2, 64))
+
+        self.blocks = []
+        x, h, w, inpl = self.x0, H4, W4, 64
+        self.stage_out = []
+        for li, nb in enumerate(RESNET_BLOCKS[self.depth]):
+            planes = 64 * 2 ** li
+            trainable = self.train and li >= 1  # frozen_stages = 1
+            for bi in range(nb):
+                s = 2 if (bi == 0 and li > 0) else 1
+                ho, wo = conv_out(h, 1, s, 0), conv_out(w, 1, s, 0)
+                p = f"backbone.layer{li + 1}.{bi}"
+                # dgrad into the block input is needed unless that input is the frozen layer1 output
+                dgrad_in = trainable and not (li == 1 and bi == 0)
+                blk = dict(li=li, bi=bi, stride=s, hin=h, win=w, h=ho, w=wo, cin=inpl, planes=planes, xin=x,
+                           trainable=trainable, dgrad_in=dgrad_in)
+                blk["c1"] = self.conv(p + ".conv1.weight", bn=p + ".bn1", stride=s, need_dgrad=dgrad_in,
+                                      trainable=trainable)
+                blk["c2"] = self.conv(p + ".conv2.weight", bn=p + ".bn2", pad=1, need_dgrad=trainable,
+                                      trainable=trainable)
+                blk["c3"] = self.conv(p + ".conv3.weight", bn=p + ".bn3", need_dgrad=trainable, trainable=trainable)
+                blk["a1"] = self.buf(B, ho, wo, planes)
+                blk["a2"] = self.buf(B, ho, wo, planes)
+                blk["out"] = self.buf(B, ho, wo, planes * 4)
+                segs = [blk["c1"].fseg(x, blk["a1"], B, h, w, relu_nch=planes)]
+                if bi == 0:
+                    blk["ds"] = self.conv(p + ".downsample.0.weight", bn=p + ".downsample.1", stride=s,
+                                          need_dgrad=dgrad_in, trainable=trainable)
+                    blk["idn"] = self.buf(B, ho, wo, planes * 4)
+                    segs.append(blk["ds"].fseg(x, blk["idn"], B, h, w))
+                self.plan_fwd(segs, p + ".conv1")
+                self.plan_fwd([blk["c2"].fseg(blk["a1"], blk["a2"], B, ho, wo, relu_nch=planes)], p + ".conv2")
+                self.plan_fwd([blk["c3"].fseg(blk["a2"], blk["out"], B, ho, wo,
+                                              residual=blk.get("idn", x), relu_nch=planes * 4)], p + ".conv3")
+                self.blocks.append(blk)
+                x, h, w, inpl = blk["out"], ho, wo, planes * 4
+            self.stage_out.append((x, h, w, inpl))
+
+    # ------------------------------------------------------------------------------------------ FPN
+    def _build_fpn(self):
+        B = self.B
+        tr = self.train
+        self.lat, self.fpnc = [], []
+        self.lm, self.p = [], []
+        cs = self.stage_out[1:]  # C3, C4, C5
+        segs = []
+        for i, (x, h, w, c) in enumerate(cs):
+            cw = self.conv(f"neck.lateral_convs.{i}.conv.weight", bias=f"neck.lateral_convs.{i}.conv.bias",
+                           need_dgrad=tr, trainable=tr)
+            self.lat.append(cw)
+            self.lm.append(self.buf(B, h, w, 256))
+            segs.append(cw.fseg(x, self.lm[i], B, h, w))
+        self.plan_fwd(segs, "fpn.laterals")
+        for i in (2, 1):
+            (_, h, w, _), (_, hs, ws, _) = cs[i - 1], cs[i]
+            self.add_fwd(self.ew("dslb_upsample_add", self.lm[i - 1], self.lm[i], B, h, w, hs, ws, 256))
+        segs = []
+        self.psize = []
+        for i, (x, h, w, c) in enumerate(cs):
+            cw = self.conv(f"neck.fpn_convs.{i}.conv.weight", bias=f"neck.fpn_convs.{i}.conv.bias", pad=1,
+                           need_dgrad=tr, trainable=tr)
+            self.fpnc.append(cw)
+            self.p.append(self.buf(B, h, w, 256))
+            self.psize.append((h, w))
+            segs.append(cw.fseg(self.lm[i], self.p[i], B, h, w))
+        self.plan_fwd(segs, "fpn.out")
+        h5, w5 = self.psize[2]
+        h6, w6 = conv_out(h5, 3, 2, 1), conv_out(w5, 3, 2, 1)
+        h7, w7 = conv_out(h6, 3, 2, 1), conv_out(w6, 3, 2, 1)
+        self.psize += [(h6, w6), (h7, w7)]
+        for i in (3, 4):
+            self.fpnc.append(self.conv(f"neck.fpn_convs.{i}.conv.weight", bias=f"neck.fpn_convs.{i}.conv.bias",
+                                       stride=2, pad=1, need_dgrad=False, trainable=tr))
+        self.p.append(self.buf(B, h6, w6, 256))
+        self.p.append(self.buf(B, h7, w7, 256))
+        self.r6 = self.buf(B, h6, w6, 256)
+        self.plan_fwd([self.fpnc[3].fseg(self.p[2], self.p[3], B, h5, w5)], "fpn.p6")
+        self.add_fwd(self.ew("dslb_relu_family", self.p[3], None, self.r6, self.p[3].numel(), 0))
+        self.plan_fwd([self.fpnc[4].fseg(self.r6, self.p[4], B, h6, w6)], "fpn.p7")
+
+    # ------------------------------------------------------------------------------------------ head
+    def _build_head(self):
+        B, C = self.B, self.C
+        tr = self.train
+        st = self.store
+        nl = len(self.psize)
+        self.tower = {"cls": [], "reg": []}
+        for br in ("cls", "reg"):
+            for i in range(4):
+                self.tower[br].append(self.conv(f"bbox_head.{br}_convs.{i}.conv.weight",
+                                                bias=f"bbox_head.{br}_convs.{i}.conv.bias", pad=1, need_dgrad=tr,
+                                                trainable=tr))
+        # GroupNorm statistics of all (branch, layer, level) maps in one buffer -> one memset per pass
+        self.gn_stats = torch.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=self.dev)
+        self.add_fwd(self.gn_stats.zero_)
+        self.y = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
+        self.z = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
+        for i in range(4):
+            segs, gsegs = [], []
+            for bi_, br in enumerate(("cls", "reg")):
+                for l, (h, w) in enumerate(self.psize):
+                    x = self.p[l] if i == 0 else self.z[br][i - 1][l]
+                    segs.append(self.tower[br][i].fseg(x, self.y[br][i][l], B, h, w,
+                                                       gn_stats=self.gn_stats[bi_, i, l], gn_cpg=8))
+                    gsegs.append(dict(x=self.y[br][i][l], y=self.z[br][i][l], stats=self.gn_stats[bi_, i, l],
+                                      gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
+                                      beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], N=B, HW=h * w))
+            self.plan_fwd(segs, f"head.tower{i}")
+            self.add_fwd(self._gn_apply(gsegs))
+        # predictors: conv_cls (N=80, fp32) on the cls tower; conv_reg + conv_centerness fused (N=5 -> 16, fp32
+        # rows of 8) on the reg tower with bbox = relu(scale_l * (conv + b)) (x stride in eval mode)
+        self.cls_w = self.conv("bbox_head.conv_cls.weight", bias="bbox_head.conv_cls.bias", pad=1, need_dgrad=tr,
+                               trainable=tr, dy_ld=128)
+        self.rc_w5 = torch.zeros(5, 256, 3, 3, dtype=torch.float32, device=self.dev)  # [conv_reg; conv_centerness]
+        self.rc_b5 = torch.zeros(5, dtype=torch.float32, device=self.dev)
+        self.rc_wp = torch.zeros(9, 16, 256, dtype=BF16, device=self.dev)
+        self.rc_wpT = torch.zeros(9, 256, 64, dtype=BF16, device=self.dev)
+        self.rc_scale = torch.ones(nl, 8, dtype=torch.float32, device=self.dev)
+        self.rc_shift = torch.zeros(nl, 8, dtype=torch.float32, device=self.dev)
+        self.scale_vals = torch.ones(nl, dtype=torch.float32, device=self.dev)
+        self.level_mult = torch.tensor([float(s) if not self.train else 1.0 for s in STRIDES[:nl]],
+                                       dtype=torch.float32, device=self.dev)
+        scale_names = [f"bbox_head.scales.{l}.scale" for l in range(nl)]
+
+        def repack_regctr():
+            s = L.cur_stream()
+            self.rc_w5[:4].copy_(st["bbox_head.conv_reg.weight"])
+            self.rc_w5[4:].copy_(st["bbox_head.conv_centerness.weight"])
+            self.rc_b5[:4].copy_(st["bbox_head.conv_reg.bias"])
+            self.rc_b5[4:].copy_(st["bbox_head.conv_centerness.bias"])
+            torch.stack([st[n] for n in scale_names], out=self.scale_vals)
+            sc = self.scale_vals * self.level_mult
+            self.rc_scale[:, :4] = sc[:, None]
+            self.rc_shift[:, :5] = self.rc_b5[None, :] * self.rc_scale[:, :5]
+            L.check(L.lib.dslb_pack_weight(L.ptr(self.rc_w5), L.ptr(self.rc_wp), 5, 256, 3, 3, 16, 256, None, 0, s),
+                    "pack regctr")
+            if tr:
+                L.check(L.lib.dslb_pack_weight(L.ptr(self.rc_w5), L.ptr(self.rc_wpT), 5, 256, 3, 3, 256, 64, None, 1,
+                                               s), "pack regctr T")
+
+        self.repack_ops.append(repack_regctr)
+        self.cls_out = [self.buf(B, h, w, C, dtype=torch.float32) for (h, w) in self.psize]
+        self.rc_out = [self.buf(B, h, w, 8, dtype=torch.float32) for (h, w) in self.psize]
+        segs = []
+        for l, (h, w) in enumerate(self.psize):
+            segs.append(self.cls_w.fseg(self.z["cls"][3][l], self.cls_out[l], B, h, w, out_fp32=1))
+        for l, (h, w) in enumerate(self.psize):
+            segs.append(dict(x=self.z["reg"][3][l], w=self.rc_wp, y=self.rc_out[l], N=B, H=h, W=w, Cin=256, Cout=5,
+                             cout_pad=16, R=3, S=3, stride=1, pad=1, ldc=8, out_fp32=1, relu_nch=4,
+                             scale=self.rc_scale[l], shift=self.rc_shift[l]))
+        self.plan_fwd(segs, "head.predictors")
+
+    def _gn_apply(self, gsegs):
+        arr = (L.GnSeg * len(gsegs))()
+        keep = []
+        for a, s in zip(arr, gsegs):
+            for k, v in s.items():
+                if isinstance(v, torch.Tensor):
+                    keep.append(v)
+                    setattr(a, k, v.data_ptr())
+                else:
+                    setattr(a, k, v)
+        n = len(gsegs)
+
+        def run(_arr=arr, _k=keep, _n=n):
+            L.check(L.lib.dslb_gn_apply_relu(_arr, _n, 256, 32, 1e-5, L.cur_stream()), "gn_apply")
+
+        return run
+
+    # ------------------------------------------------------------------------------------------ loss
+    def _fill_levels(self, with_grads):
+        nl = len(self.psize)
+        arr = (L.FcosLevel * nl)()
+        for l, (h, w) in enumerate(self.psize):
+            a = arr[l]
+            a.cls = self.cls_out[l].data_ptr()
+            a.regctr = self.rc_out[l].data_ptr()
+            if with_grads:
+                a.dcls_bf16 = self.dcls[l].data_ptr()
+                a.dregctr_bf16 = self.drc[l].data_ptr()
+                if self.parity_outputs:
+                    a.dcls_f32 = self.dcls_f32[l].data_ptr()
+                    a.dregctr_f32 = self.drc_f32[l].data_ptr()
+            a.h, a.w, a.stride = h, w, STRIDES[l]
+            a.ld_cls, a.ld_dcls, a.ld_dreg = self.C, 128, 64
+            a.rr_lo, a.rr_hi = float(REGRESS_RANGES[l][0]), float(REGRESS_RANGES[l][1])
+            a.scale = 1.0
+            a.cs_radius = float(STRIDES[l] * self.radius)
+        return arr
+
+    def _build_loss(self):
+        B, C = self.B, self.C
+        nl = len(self.psize)
+        self.npoints = B * sum(h * w for (h, w) in self.psize)
+        self.dcls = [self.buf(B, h, w, 128) for (h, w) in self.psize]   # bf16, cols >= C stay zero
+        self.drc = [self.buf(B, h, w, 64) for (h, w) in self.psize]     # bf16, cols >= 5 stay zero
+        if self.parity_outputs:
+            self.dcls_f32 = [self.buf(B, h, w, C, dtype=torch.float32) for (h, w) in self.psize]
+            self.drc_f32 = [self.buf(B, h, w, 8, dtype=torch.float32) for (h, w) in self.psize]
+        P = self.npoints
+        self.labels = torch.zeros(P, dtype=torch.int64, device=self.dev)
+        self.bbox_targets = torch.zeros(P, 4, dtype=torch.float32, device=self.dev)
+        self.weights = torch.zeros(P, dtype=torch.float32, device=self.dev)
+        self.ctr_targets = torch.zeros(P, dtype=torch.float32, device=self.dev)
+        self.counts = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.norm = torch.ones(2, dtype=torch.float32, device=self.dev)
+        self.loss_sums = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        self.dscale = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.max_boxes = 1024
+        self.gt_boxes = torch.zeros(self.max_boxes, 4, dtype=torch.float32, device=self.dev)
+        self.gt_labels = torch.zeros(self.max_boxes, dtype=torch.int64, device=self.dev)
+        self.gt_off = torch.zeros(B + 1, dtype=torch.int32, device=self.dev)
+        self.ig_boxes = torch.zeros(self.max_boxes, 4, dtype=torch.float32, device=self.dev)
+        self.ig_off = torch.zeros(B + 1, dtype=torch.int32, device=self.dev)
+        self.use_ignore = True
+        self.levels_arr = self._fill_levels(True)
+        self.world_size = 1.0
+        # labeled images come first (fcos_head.py:227-233): B/2 for an even batch, (B-1)/2 with the SI extra image
+        self.n_labeled = B // 2 if B % 2 == 0 else (B - 1) // 2
+        self.si_weight = 0.0
+        scale_idx = [self.store.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
+        self.scale_idx = torch.tensor(scale_idx, dtype=torch.long, device=self.dev)
+
+    def set_targets(self, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
+        """Upload per-image box lists (torch tensors, any device) into the fixed device buffers."""
+        B = self.B
+        assert len(gt_bboxes) == B and len(gt_labels) == B
+        offs = [0]
+        for b in gt_bboxes:
+            offs.append(offs[-1] + int(b.shape[0]))
+        assert offs[-1] <= self.max_boxes, "too many GT boxes for the preallocated buffer"
+        if offs[-1] > 0:
+            self.gt_boxes[:offs[-1]].copy_(torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(torch.float32),
+                                           non_blocking=True)
+            self.gt_labels[:offs[-1]].copy_(torch.cat([l.reshape(-1) for l in gt_labels]).to(torch.int64),
+                                            non_blocking=True)
+        self.gt_off.copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=True)
+        self.use_ignore = gt_bboxes_ignore is not None
+        if self.use_ignore:
+            ioffs = [0]
+            for b in gt_bboxes_ignore:
+                ioffs.append(ioffs[-1] + int(b.shape[0]))
+            assert ioffs[-1] <= self.max_boxes
+            if ioffs[-1] > 0:
+                self.ig_boxes[:ioffs[-1]].copy_(torch.cat([b.reshape(-1, 4) for b in gt_bboxes_ignore])
+                                                .to(torch.float32), non_blocking=True)
+            self.ig_off.copy_(torch.tensor(ioffs, dtype=torch.int32), non_blocking=True)
+
+    def run_targets(self):
+        """kernel 1 of the loss: labels / bbox_targets / weights / centerness targets + local normaliser sums."""
+        self.counts.zero_()
+        lw = self.loss_weight
+        L.check(L.lib.dslb_fcos_targets(
+            self.levels_arr, len(self.psize), self.B, self.C, L.ptr(self.gt_boxes), L.ptr(self.gt_labels),
+            L.ptr(self.gt_off), L.ptr(self.ig_boxes) if self.use_ignore else None,
+            L.ptr(self.ig_off) if self.use_ignore else None, int(self.center_sampling), int(self.norm_on_bbox), lw,
+            self.n_labeled, L.ptr(self.labels), L.ptr(self.bbox_targets), L.ptr(self.weights),
+            L.ptr(self.ctr_targets), L.ptr(self.counts), L.cur_stream()), "fcos_targets")
+
+    def run_loss(self):
+        """kernel 2 (after `counts` has been all-reduced over ranks): losses + gradients of the head outputs."""
+        s = L.cur_stream()
+        L.check(L.lib.dslb_fcos_norm(L.ptr(self.counts), float(self.world_size), L.ptr(self.norm), s), "fcos_norm")
+        self.loss_sums.zero_()
+        self.dscale.zero_()
+        nl = len(self.psize)
+        L.check(L.lib.dslb_fcos_loss(
+            self.levels_arr, nl, self.B, self.C, L.ptr(self.labels), L.ptr(self.bbox_targets), L.ptr(self.weights),
+            L.ptr(self.ctr_targets), L.ptr(self.norm), 0.25, 2.0, self.loss_weight, self.n_labeled,
+            float(self.si_weight), L.ptr(self.scale_vals), L.ptr(self.loss_sums), L.ptr(self.dscale), s), "fcos_loss")
+
+    # ------------------------------------------------------------------------------------------ head backward
+    def _build_head_bwd(self):
+        B = self.B
+        st = self.store
+        nl = len(self.psize)
+        br_names = ("cls", "reg")
+        self.dz = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
+        self.dy = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
+        self.gn_red = torch.zeros(2, 4, nl, B, 256, 2, dtype=torch.float64, device=self.dev)
+        self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]  # gradient w.r.t. the FPN outputs
+        self.rc_dw = torch.zeros(9, 5, 256, dtype=torch.float32, device=self.dev)
+
+        def zero_state():
+            self.grad.zero_()
+            self.gn_red.zero_()
+            for t in self._dw_list:
+                t.zero_()
+            self.rc_dw.zero_()
+
+        self.add_bwd(zero_state)
+        # --- predictors: wgrad (10 segs), bias grads, dgrad into the last tower outputs
+        wsegs = []
+        for l, (h, w) in enumerate(self.psize):
+            wsegs.append(self.cls_w.wseg(self.z["cls"][3][l], self.dcls[l], B, h, w))
+        for l, (h, w) in enumerate(self.psize):
+            wsegs.append(dict(x=self.z["reg"][3][l], dy=self.drc[l], dw=self.rc_dw, N=B, H=h, W=w, Cin=256, Cout=5,
+                              ldy=64, dw_rows=5, R=3, S=3, stride=1, pad=1))
+        self.plan_wgrad(wsegs, "head.predictors.wgrad")
+        g_cls_b = self.grad_view("bbox_head.conv_cls.bias")
+        self.rc_db = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        for l, (h, w) in enumerate(self.psize):
+            self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C))
+            self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5))
+        dsegs = []
+        for l, (h, w) in enumerate(self.psize):
+            dsegs.append(self.cls_w.dseg(self.dcls[l], self.dz["cls"][l], B, h, w, h, w))
+        for l, (h, w) in enumerate(self.psize):
+            dsegs.append(dict(x=self.drc[l], w=self.rc_wpT, y=self.dz["reg"][l], N=B, H=h, W=w, Cin=64, Cout=256,
+                              cout_pad=256, R=3, S=3, stride=1, pad=1, ldc=256))
+        self.plan_bwd(dsegs, "head.predictors.dgrad")
+        # --- towers, last layer first
+        for i in (3, 2, 1, 0):
+            gsegs = []
+            for bi_, br in enumerate(br_names):
+                for l, (h, w) in enumerate(self.psize):
+                    gsegs.append(dict(x=self.y[br][i][l], y=self.dy[br][l], dz=self.dz[br][l],
+                                      stats=self.gn_stats[bi_, i, l],
+                                      gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
+                                      beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], red=self.gn_red[bi_, i, l],
+                                      dbias=self.grad_view(f"bbox_head.{br}_convs.{i}.conv.bias"), N=B, HW=h * w))
+            self.add_bwd(self._gn_bwd(gsegs))
+            for bi_, br in enumerate(br_names):
+                # dgamma / dbeta: sum over levels and images of the per-(n,c) sums
+                red = self.gn_red[bi_, i].reshape(nl * B, 256, 2)
+                self.add_bwd(self.ew("dslb_gn_bwd_params", red, self.grad_view(f"bbox_head.{br}_convs.{i}.gn.weight"),
+                                     self.grad_view(f"bbox_head.{br}_convs.{i}.gn.bias"), nl * B, 256))
+            wsegs = []
+            for br in br_names:
+                for l, (h, w) in enumerate(self.psize):
+                    x = self.p[l] if i == 0 else self.z[br][i - 1][l]
+                    wsegs.append(self.tower[br][i].wseg(x, self.dy[br][l], B, h, w))
+            self.plan_wgrad(wsegs, f"head.tower{i}.wgrad")
+            if i > 0:
+                dsegs = []
+                for br in br_names:
+                    for l, (h, w) in enumerate(self.psize):
+                        dsegs.append(self.tower[br][i].dseg(self.dy[br][l], self.dz[br][l], B, h, w, h, w))
+                self.plan_bwd(dsegs, f"head.tower{i}.dgrad")
+            else:
+                # both towers read the FPN output: cls-tower dgrad writes dP, reg-tower dgrad accumulates into it
+                self.plan_bwd([self.tower["cls"][0].dseg(self.dy["cls"][l], self.dp[l], B, h, w, h, w)
+                               for l, (h, w) in enumerate(self.psize)], "head.tower0.dgrad.cls")
+                self.plan_bwd([self.tower["reg"][0].dseg(self.dy["reg"][l], self.dp[l], B, h, w, h, w,
+                                                         residual=self.dp[l])
+                               for l, (h, w) in enumerate(self.psize)], "head.tower0.dgrad.reg")
+
+    def _gn_bwd(self, gsegs):
+        n = len(gsegs)
+        arr = (L.GnSeg * n)()
+        keep = []
+        for a, s in zip(arr, gsegs):
+            for k, v in s.items():
+                if isinstance(v, torch.Tensor):
+                    keep.append(v)
+                    setattr(a, k, v.data_ptr())
+                else:
+                    setattr(a, k, v)
+        nb = L.lib.dslb_gn_bwd_blocks(arr, n)
+        host = (C.c_int * (2 * nb))()
+        L.check(L.lib.dslb_gn_bwd_plan(arr, n, host), "gn_bwd_plan")
+        tab = torch.tensor(list(host), dtype=torch.int32, device=self.dev)
+        keep.append(tab)
+
+        def run(_arr=arr, _n=n, _tab=tab, _nb=nb, _k=keep):
+            L.check(L.lib.dslb_gn_bwd(_arr, _n, 256, 32, 1e-5, L.ptr(_tab), _nb, L.cur_stream()), "gn_bwd")
+
+        return run
+
+    # ------------------------------------------------------------------------------------------ FPN backward
+    def _build_fpn_bwd(self):
+        B = self.B
+        cs = self.stage_out[1:]
+        (h5, w5), (h6, w6), (h7, w7) = self.psize[2], self.psize[3], self.psize[4]
+        gb = lambda i: self.grad_view(f"neck.fpn_convs.{i}.conv.bias")  # noqa: E731
+        # P7 = conv_s2(relu(P6)); P6 = conv_s2(P5)
+        self.tmp6 = self.buf(B, h6, w6, 256)
+        self.plan_wgrad([self.fpnc[4].wseg(self.r6, self.dp[4], B, h6, w6)], "fpn.p7.wgrad")
+        self.add_bwd(self.ew("dslb_colsum", self.dp[4], gb(4), B * h7 * w7, 256, 256))
+        self.add_bwd(self.ew("dslb_conv_dgrad_naive", self.dp[4], self.fpnc[4].wp, self.tmp6, B, h6, w6, 256, 256, 256,
+                             3, 3, 2, 1, 0))
+        self.add_bwd(self.ew("dslb_relu_family", self.tmp6, self.p[3], self.tmp6, self.tmp6.numel(), 1))
+        self.add_bwd(self.ew("dslb_relu_family", self.dp[3], self.tmp6, self.dp[3], self.tmp6.numel(), 2))
+        self.plan_wgrad([self.fpnc[3].wseg(self.p[2], self.dp[3], B, h5, w5)], "fpn.p6.wgrad")
+        self.add_bwd(self.ew("dslb_colsum", self.dp[3], gb(3), B * h6 * w6, 256, 256))
+        self.add_bwd(self.ew("dslb_conv_dgrad_naive", self.dp[3], self.fpnc[3].wp, self.dp[2], B, h5, w5, 256, 256,
+                             256, 3, 3, 2, 1, 1))
+        # P3..P5 = conv3x3(merged laterals)
+        self.plan_wgrad([self.fpnc[i].wseg(self.lm[i], self.dp[i], B, cs[i][1], cs[i][2]) for i in range(3)],
+                        "fpn.out.wgrad")
+        for i in range(3):
+            self.add_bwd(self.ew("dslb_colsum", self.dp[i], gb(i), B * cs[i][1] * cs[i][2], 256, 256))
+        self.dl = [self.buf(B, cs[i][1], cs[i][2], 256) for i in range(3)]
+        self.plan_bwd([self.fpnc[i].dseg(self.dp[i], self.dl[i], B, cs[i][1], cs[i][2], cs[i][1], cs[i][2])
+                       for i in range(3)], "fpn.out.dgrad")
+        # top-down path backward: d l4m += down(d l3m); d l5m += down(d l4m)
+        for i in (1, 2):
+            (_, h, w, _), (_, hs, ws, _) = cs[i - 1], cs[i]
+            self.add_bwd(self.ew("dslb_upsample_add_bwd", self.dl[i], self.dl[i - 1], B, h, w, hs, ws, 256))
+        # laterals
+        self.plan_wgrad([self.lat[i].wseg(cs[i][0], self.dl[i], B, cs[i][1], cs[i][2]) for i in range(3)],
+                        "fpn.lateral.wgrad")
+        for i in range(3):
+            self.add_bwd(self.ew("dslb_colsum", self.dl[i], self.grad_view(f"neck.lateral_convs.{i}.conv.bias"),
+                                 B * cs[i][1] * cs[i][2], 256, 256))
+        # gradient w.r.t. the stage outputs C3, C4 (unmasked: more consumers follow) and C5 (masked: last consumer)
+        self.gc = [self.buf(B, cs[i][1], cs[i][2], cs[i][3]) for i in range(3)]
+        segs = []
+        for i in range(3):
+            kw = dict(relu_mask=cs[i][0]) if i == 2 else {}
+            segs.append(self.lat[i].dseg(self.dl[i], self.gc[i], B, cs[i][1], cs[i][2], cs[i][1], cs[i][2], **kw))
+        self.plan_bwd(segs, "fpn.lateral.dgrad")
+
+    # ------------------------------------------------------------------------------------------ backbone backward
+    def _build_backbone_bwd(self):
+        B = self.B
+        stage_last = {}
+        for idx, blk in enumerate(self.blocks):
+            stage_last[blk["li"]] = idx
+        # M = masked gradient w.r.t. each trainable block's output; stage outputs C3..C5 start from the FPN's dgrad
+        for idx in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[idx]
+            if not blk["trainable"]:
+                break
+            li, bi = blk["li"], blk["bi"]
+            h, w, hin, win, planes = blk["h"], blk["w"], blk["hin"], blk["win"], blk["planes"]
+            name = f"layer{li + 1}.{bi}"
+            if idx == stage_last[li]:
+                if li == 3:
+                    blk["M"] = self.gc[2]  # already masked by the lateral dgrad epilogue
+                else:
+                    # C3 / C4: lateral dgrad + the next stage's strided dgrads have accumulated; apply the ReLU mask
+                    g = self.gc[li - 1]
+                    self.add_bwd(self.ew("dslb_relu_family", g, blk["out"], g, g.numel(), 1))
+                    blk["M"] = g
+            M = blk["M"]
+            blk["da2"] = self.buf(B, h, w, planes)
+            blk["da1"] = self.buf(B, h, w, planes)
+            self.plan_bwd([blk["c3"].dseg(M, blk["da2"], B, h, w, h, w, relu_mask=blk["a2"])], name + ".conv3.dgrad")
+            self.plan_bwd([blk["c2"].dseg(blk["da2"], blk["da1"], B, h, w, h, w, relu_mask=blk["a1"])],
+                          name + ".conv2.dgrad")
+            wsegs = [blk["c3"].wseg(blk["a2"], M, B, h, w), blk["c2"].wseg(blk["a1"], blk["da2"], B, h, w),
+                     blk["c1"].wseg(blk["xin"], blk["da1"], B, hin, win)]
+            if bi == 0:
+                wsegs.append(blk["ds"].wseg(blk["xin"], M, B, hin, win))
+            self.plan_wgrad(wsegs, name + ".wgrad")
+            if not blk["dgrad_in"]:
+                continue
+            prev = self.blocks[idx - 1]
+            if bi > 0:
+                # M_prev = (dgrad_conv1(da1) + M) * [xin > 0]   (identity shortcut fused as the residual operand)
+                prev["M"] = self.buf(B, hin, win, blk["cin"])
+                self.plan_bwd([blk["c1"].dseg(blk["da1"], prev["M"], B, h, w, hin, win, residual=M,
+                                              relu_mask=blk["xin"])], name + ".conv1.dgrad")
+            else:
+                # first block of layer3 / layer4: both strided 1x1 dgrads scatter-accumulate into the stage-input
+                # gradient that the FPN lateral dgrad has already initialised
+                g = self.gc[li - 2]
+                self.plan_bwd([blk["ds"].dseg(M, g, B, h, w, hin, win, residual=g)], name + ".downsample.dgrad")
+                self.plan_bwd([blk["c1"].dseg(blk["da1"], g, B, h, w, hin, win, residual=g)], name + ".conv1.dgrad")
+        # finally: packed wgrads -> OIHW gradient views
+        for c in self.convs:
+            if c.trainable:
+                self.add_bwd(c.unpack_grad)
+
+        def finish_head_grads():
+            s = L.cur_stream()
+            g_reg_w = self.grad_view("bbox_head.conv_reg.weight")
+            g_ctr_w = self.grad_view("bbox_head.conv_centerness.weight")
+            # rc_dw [9][5][256] -> OIHW
+            L.check(L.lib.dslb_unpack_wgrad(L.ptr(self.rc_dw), L.ptr(self._rc_g5), 5, 256, 3, 3, 5, None, 0, s),
+                    "unpack regctr")
+            g_reg_w.copy_(self._rc_g5[:4 * 256 * 9])
+            g_ctr_w.copy_(self._rc_g5[4 * 256 * 9:])
+            self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
+            self.grad_view("bbox_head.conv_centerness.bias").copy_(self.rc_db[4:5])
+            self.rc_db.zero_()
+            self.grad.index_copy_(0, self.scale_idx, self.dscale[:len(self.psize)])
+
+        self._rc_g5 = torch.zeros(5 * 256 * 9, dtype=torch.float32, device=self.dev)
+        self.add_bwd(finish_head_grads)
+
+    # ------------------------------------------------------------------------------------------ run
+    def repack(self):
+        """Refresh every derived bf16 operand from the fp32 master parameters (after an optimizer / EMA step)."""
+        for c in self.convs:
+            c.repack()
+        for f in self.repack_ops:
+            f()
+
+    def forward(self):
+        for op in self.fwd_ops:
+            op()
+
+    def forward_head(self):
+        """FCOSHead only, on whatever is in the FPN output buffers self.p[l] (NHWC bf16)."""
+        for op in self.fwd_ops[self.head_op_start:]:
+            op()
+
+    def backward(self):
+        for op in self.bwd_ops:
+            op()
+
+    def losses(self):
+        """dict of the reference's loss names -> 0-dim fp32 tensors (device)."""
+        s = self.loss_sums.to(torch.float32)
+        out = dict(loss_cls=s[0], loss_bbox=s[1], loss_centerness=s[2])
+        if self.si_weight != 0.0:
+            out["loss_sisoft"] = s[3]
+        return out

@@ -1,0 +1,188 @@
+"""One DSL teacher+student training step on one GPU (one process per GPU; pure data parallel).
+
+Step = { EMA-teacher forward (no_grad, eval mode: bbox x stride) on the weak-aug images + decode / score gate,
+         student forward + loss + backward on the strong-aug images,
+         [gradient all-reduce over ranks],  clip-grad-norm 35 + momentum SGD (bias lr x2 / wd 0),  EMA update,
+         refresh of the bf16 operand caches }
+which is what the reference spreads over SemiEpochBasedRunner.train / run_iter (mmdet/runner/hooks/
+semi_epoch_based_runner.py:169-283), OptimizerHook, EMAOWNHook -> runner.EMA (:368-409) and UnlabelPredHook's
+per-iteration teacher inference (mmdet/runner/hooks/unlabel_pred_hook.py:512-562) — minus the JSON / disk round trip.
+
+With world_size == 1 the whole step is captured once into a CUDA graph and replayed; with more ranks it is split into
+three graphs around the two collectives (the packed 2-scalar normaliser all-reduce and the gradient all-reduce).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .engine import FCOSNet, STRIDES
+
+
+class DSLEngine:
+    def __init__(self, B, H, W, depth=50, num_classes=80, device="cuda", seed=0, lr=0.01, momentum=0.9,
+                 weight_decay=1e-4, bias_lr_mult=2.0, bias_decay_mult=0.0, max_grad_norm=35.0, ema_keep=0.99,
+                 loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05):
+        self.dev = torch.device(device)
+        self.B, self.H, self.W = B, H, W
+        self.student = FCOSNet(B, H, W, depth, num_classes, train=True, device=device, seed=seed,
+                               loss_weight=loss_weight)
+        tB = teacher_B or B
+        self.teacher = FCOSNet(tB, H, W, depth, num_classes, train=False, device=device, seed=seed)
+        # teacher starts as a copy of the student (reference: both built from the same config, load_checkpoint loads
+        # the same file into both, semi_epoch_based_runner.py:350-366)
+        self.teacher.store.flat.copy_(self.student.store.flat)
+        self.teacher.repack()
+        st = self.student.store
+        self.mom = torch.zeros(st.n_train, dtype=torch.float32, device=self.dev)
+        self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.bias_lr_mult, self.bias_decay_mult = bias_lr_mult, bias_decay_mult
+        self.max_grad_norm = max_grad_norm
+        self.ema_keep = ema_keep
+        self.sqnorm = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.coef = torch.ones(2, dtype=torch.float32, device=self.dev)
+        self.lr_scale = torch.ones(1, dtype=torch.float32, device=self.dev)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.student.world_size = float(self.world)
+        self.use_graphs = use_graphs
+        self.graphs = None
+        self.nms_pre, self.score_thr = nms_pre, score_thr
+        self._build_teacher_post()
+        self.launches_per_step = None
+
+    # ---------------------------------------------------------------------------------------- teacher decode
+    def _build_teacher_post(self):
+        t = self.teacher
+        B = t.B
+        self.cand_cap = 8192
+        self.pt_scores = [torch.zeros(B, h * w, dtype=torch.float32, device=self.dev) for (h, w) in t.psize]
+        self.cand_boxes = torch.zeros(B, self.cand_cap, 4, dtype=torch.float32, device=self.dev)
+        self.cand_scores = torch.zeros(B, self.cand_cap, dtype=torch.float32, device=self.dev)
+        self.cand_labels = torch.zeros(B, self.cand_cap, dtype=torch.int32, device=self.dev)
+        self.cand_points = torch.zeros(B, self.cand_cap, dtype=torch.int32, device=self.dev)
+        self.cand_counts = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.img_hw = torch.tensor([[float(self.H), float(self.W)]] * B, dtype=torch.float32, device=self.dev)
+        self.scale_factor = torch.ones(B, 4, dtype=torch.float32, device=self.dev)
+
+    def teacher_decode(self):
+        """Per level: top-nms_pre points by max_c(score*centerness), decode + clip + rescale, gate on score_thr.
+        (fcos_head.py:452-527; bbox_nms.py:51-62). Results stay on the device in the cand_* buffers."""
+        t = self.teacher
+        s = L.cur_stream
+        self.cand_counts.zero_()
+        off = 0
+        for l, (h, w) in enumerate(t.psize):
+            n = h * w
+            L.check(L.lib.dslb_fcos_point_scores(L.ptr(t.cls_out[l]), L.ptr(t.rc_out[l]), L.ptr(self.pt_scores[l]),
+                                                 t.B * n, t.C, t.C, s()), "point_scores")
+            if 0 < self.nms_pre < n:
+                sel = self.pt_scores[l].topk(self.nms_pre, dim=1).indices
+                K = self.nms_pre
+                selp = L.ptr(sel)
+            else:
+                sel, K, selp = None, n, None
+            L.check(L.lib.dslb_fcos_decode_gate(
+                L.ptr(t.cls_out[l]), L.ptr(t.rc_out[l]), selp, t.B, K, t.C, h, w, STRIDES[l], t.C, L.ptr(self.img_hw),
+                L.ptr(self.scale_factor), float(self.score_thr), off, L.ptr(self.cand_boxes), L.ptr(self.cand_scores),
+                L.ptr(self.cand_labels), L.ptr(self.cand_points), L.ptr(self.cand_counts), self.cand_cap, s()),
+                "decode_gate")
+            off += n
+
+    # ---------------------------------------------------------------------------------------- step pieces
+    def _phase_a(self):
+        with torch.no_grad():
+            self.teacher.forward()
+            self.teacher_decode()
+            self.student.forward()
+            self.student.run_targets()
+
+    def _phase_b(self):
+        self.student.run_loss()
+        self.student.backward()
+
+    def _phase_c(self):
+        s = L.cur_stream()
+        st, tt = self.student.store, self.teacher.store
+        g = self.student.grad
+        if self.world > 1:
+            g.div_(self.world)  # the all-reduce below sums; DDP averages (mmdet/apis/train.py:88-96)
+        self.sqnorm.zero_()
+        L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
+        L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm), L.ptr(self.coef), s), "clip_coef")
+        a0, a1 = st.region_range["A"]
+        b0, b1 = st.region_range["B"]
+        L.check(L.lib.dslb_sgd_step(L.ptr(st.flat[a0:a1]), L.ptr(g[a0:a1]), L.ptr(self.mom[a0:a1]), a1 - a0,
+                                    L.ptr(self.coef), L.ptr(self.lr_scale), self.lr, self.momentum, self.wd, 0, s),
+                "sgd A")
+        L.check(L.lib.dslb_sgd_step(L.ptr(st.flat[b0:b1]), L.ptr(g[b0:b1]), L.ptr(self.mom[b0:b1]), b1 - b0,
+                                    L.ptr(self.coef), L.ptr(self.lr_scale), self.lr * self.bias_lr_mult,
+                                    self.momentum, self.wd * self.bias_decay_mult, 0, s), "sgd B")
+        k = float(self.ema_keep)
+        c_s = float(torch.tensor(1 - k, dtype=torch.float32))  # fp32(1 - keep_rate), as torch's scalar promotion does
+        c_t = float(torch.tensor(k, dtype=torch.float32))
+        L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, s), "ema")
+        self.student.repack()
+        self.teacher.repack()
+
+    def _allreduce_counts(self):
+        if self.world > 1:
+            dist.all_reduce(self.student.counts)
+
+    def _allreduce_grads(self):
+        if self.world > 1:
+            dist.all_reduce(self.student.grad)
+
+    def _run_eager(self):
+        self._phase_a()
+        self._allreduce_counts()
+        self._phase_b()
+        self._allreduce_grads()
+        self._phase_c()
+
+    def _capture(self):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream, as torch's graph capture requires
+            self._run_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        phases = [[self._phase_a, self._phase_b, self._phase_c]] if self.world == 1 else \
+            [[self._phase_a], [self._phase_b], [self._phase_c]]
+        graphs = []
+        pool = None
+        for fns in phases:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                for f in fns:
+                    f()
+            pool = g.pool()
+            graphs.append(g)
+        self.graphs = graphs
+
+    # ---------------------------------------------------------------------------------------- public
+    def set_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
+        """Copy one batch into the engine's static input buffers (host tensors should be pinned for async H2D)."""
+        self.student.img.copy_(student_img, non_blocking=True)
+        self.student.set_targets(gt_bboxes, gt_labels, gt_bboxes_ignore)
+        if teacher_img is not None:
+            self.teacher.img.copy_(teacher_img, non_blocking=True)
+
+    def step(self):
+        """Run one teacher+student step on the inputs last given to set_inputs()."""
+        if not self.use_graphs:
+            self._run_eager()
+        else:
+            if self.graphs is None:
+                self._capture()
+            if self.world == 1:
+                self.graphs[0].replay()
+            else:
+                self.graphs[0].replay()
+                self._allreduce_counts()
+                self.graphs[1].replay()
+                self._allreduce_grads()
+                self.graphs[2].replay()
+        return self.student.losses()
+
+    def flops_per_step(self):
+        return self.teacher.flops_fwd + self.student.flops_fwd + self.student.flops_bwd

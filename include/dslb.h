@@ -147,6 +147,10 @@ int dslb_unpack_wgrad(const float* dw, float* g, int O, int I, int R, int S, int
 /* frozen BatchNorm2d in eval mode folded to y = x*scale + shift (resnet.py:647-656). */
 int dslb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
                  float* shift, int C, void* stream);
+/* CUDA-core data gradient of a strided conv for tiny maps (FPN P6/P7 3x3 stride-2 convs, necks/fpn.py:192-201):
+ * dx[n,h,w,ci] (+)= sum dy[n,p,q,co] * wp[r*S+s][co][ci]; wp = packed fprop weight; accumulate=1 adds into dx. */
+int dslb_conv_dgrad_naive(const void* dy, const void* wp, void* dx, int N, int H, int W, int Ci, int Co, int co_pad,
+                          int R, int S, int stride, int pad, int accumulate, void* stream);
 /* out[c] += sum_p x[p][c] over a pixel-major bf16 matrix (conv bias gradient). */
 int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream);
 
@@ -186,11 +190,47 @@ int dslb_fcos_targets(const dslb_fcos_level_t* levels, int nlevels, int B, int n
  * (fcos_head.py:266,273-274); `counts` holds the SUM over ranks (all-reduce it between the two calls). */
 int dslb_fcos_norm(const double* counts, float world_size, float* norm, void* stream);
 /* Losses + gradients. loss_sums[0..3] += loss_cls, loss_bbox, loss_centerness, loss_sisoft (fp64, pre-zeroed);
- * dscale[l] += d loss / d scales[l].scale (or NULL). si_weight: 0 = off, else the (warm-up adjusted) soft weight. */
+ * dscale[l] += d loss / d scales[l].scale (or NULL). si_weight: 0 = off, else the (warm-up adjusted) soft weight.
+ * level_scales: device array [nlevels] of the Scale values (NULL = use levels[l].scale). */
 int dslb_fcos_loss(const dslb_fcos_level_t* levels, int nlevels, int B, int num_classes, const int64_t* labels,
                    const float* bbox_targets, const float* weights, const float* ctr_targets, const float* norm,
-                   float alpha, float gamma, float loss_weight, int n_labeled, float si_weight, double* loss_sums,
-                   float* dscale, void* stream);
+                   float alpha, float gamma, float loss_weight, int n_labeled, float si_weight,
+                   const float* level_scales, double* loss_sums, float* dscale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Flat-buffer parameter kernels. The detector's parameters live in one flat fp32 buffer (nn.Parameters are views).
+ * ---------------------------------------------------------------------------------------------------- */
+/* EMA teacher update, SemiEpochBasedRunner.EMA (mmdet/runner/hooks/semi_epoch_based_runner.py:392-406):
+ * teacher = student*c_student + teacher*c_teacher with c_student = float(1-keep_rate), c_teacher = float(keep_rate);
+ * in place, every product and the sum rounded separately like the reference's fp32 expression. */
+int dslb_ema_update(float* teacher, const float* student, long long n, float c_student, float c_teacher, void* stream);
+/* *out += sum g^2 (fp64, pre-zeroed): global L2 norm for clip_grad_norm_ (mmcv OptimizerHook, cfg grad_clip 35). */
+int dslb_sq_norm(const float* g, long long n, double* out, void* stream);
+/* coef[0] = min(max_norm/(sqrt(*sqnorm)+1e-6), 1) (1 if max_norm <= 0); coef[1] = sqrt(*sqnorm). */
+int dslb_clip_coef(const double* sqnorm, float max_norm, float* coef, void* stream);
+/* torch.optim.SGD step (momentum, dampening 0) with the clip coefficient read from device memory (or NULL):
+ * d = g*coef[0] + wd*p; buf = first_step ? d : momentum*buf + d; p -= lr*lr_scale[0]*buf (lr_scale: device scalar
+ * for the warm-up / step schedule, or NULL = 1, so a captured CUDA graph can be replayed with a changing LR).
+ * cfg optimizer: lr .01, momentum .9, wd 1e-4, paramwise bias_lr_mult 2 / bias_decay_mult 0 (one call per region). */
+int dslb_sgd_step(float* p, const float* g, float* buf, long long n, const float* coef, const float* lr_scale, float lr,
+                  float momentum, float weight_decay, int first_step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Teacher decode + score gate (FCOSHead._get_bboxes, fcos_head.py:406-527; multiclass_nms gate,
+ * mmdet/core/post_processing/bbox_nms.py:34-67). Per level.
+ * ---------------------------------------------------------------------------------------------------- */
+/* out[pt] = max_c sigmoid(cls[pt][c]) * sigmoid(centerness[pt])  — the key of the per-level top-nms_pre. */
+int dslb_fcos_point_scores(const float* cls, const float* regctr, float* out, long long npts, int C, int ld_cls,
+                           void* stream);
+/* For the K selected points of each image (sel [B][K] int64 point indices inside the level, NULL = the first K):
+ * decode + clip to img_hw[n] = (H, W) + divide by scale_factor[n][4] (NULL = no rescale); every class with raw
+ * sigmoid score > score_thr appends (box, score*centerness, label, point_offset+point) at an atomically claimed slot
+ * of image n (counts[n], pre-zeroed; slots >= cap are dropped but still counted). Order within an image is
+ * unspecified. */
+int dslb_fcos_decode_gate(const float* cls, const float* regctr, const int64_t* sel, int B, int K, int C, int h, int w,
+                          int stride, int ld_cls, const float* img_hw, const float* scale_factor, float score_thr,
+                          int point_offset, float* out_boxes, float* out_scores, int32_t* out_labels,
+                          int32_t* out_points, int32_t* counts, int cap, void* stream);
 
 #ifdef __cplusplus
 }
