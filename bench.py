@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of one DSL teacher+student step (FCOS-R50-FPN, synthetic COCO-shaped 1333x800 -> padded
+800x1344, bs 4 per GPU), the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = EMA-teacher forward (no_grad, eval) on B weak images + decode/score gate, student forward + FCOSHead
+loss + backward on B strong images, [grad all-reduce], clip-grad-norm + momentum SGD, EMA update, operand repack.
+Rank 0 prints ONE JSON line. `value` is timed with the inputs already resident in HBM; `e2e` is the same step driven
+through the public API (DSLEngine.set_inputs + step) from PINNED HOST buffers with the losses read back every step.
+`roofline` is for the dominant kernel family (the tcgen05 implicit-GEMM conv), timed live with CUDA events on the
+launching stream in an instrumented eager pass over the same workload. `cpu_baseline` is the oracle port of the
+reference's CPU arithmetic (oracle/cpu_step.py) on a bounded sample, on this box's host cores.
+`--impl reference` times that CPU port alone (the reference's own Python needs mmcv, which is neither on the GPU box
+nor installable offline) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (teacher+student step) FCOS-R50 1333x800"
+UNIT = "img/s"
+B_PER_GPU, H, W = 4, 800, 1344
+WORKLOAD = "configs[1]: FCOS-R50-FPN DSL teacher-student, synthetic COCO 1333x800 (padded 800x1344), bs=4/GPU, bf16"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU (default: the benchmark config)")
+    ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-hw", default="800x1344", help="HxW of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                       reasons=sorted(reasons))
+        return out
+
+
+def cpu_baseline(sample_hw, depth, steps=1, warmup=0):
+    """The reference's CPU arithmetic for the step (oracle port), bounded sample: B=1 teacher+student image pair."""
+    import torch
+    from oracle import cpu_step
+    h, w = (int(v) for v in sample_hw.split("x"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    r = cpu_step.time_cpu_steps(1, h, w, steps=steps, warmup=warmup, depth=depth, threads=cores)
+    return dict(value=round(r["images_per_sec"], 4), unit=UNIT, cores=r["cores"], kind="port",
+                sample=f"{steps} step(s) of B=1 teacher+student pair at {h}x{w}, R{depth}, fp32 torch CPU "
+                       f"({r['seconds_per_step']:.2f} s/step), warmup {warmup}")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=steps, warmup=warm)
+    line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=round(1000.0 / cb["value"], 1), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="fp32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, note="CPU port of the reference arithmetic on a bounded sample "
+                                                    "(B=1 pair per step); host cores only, no GPU"),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, wall_s=round(time.time() - t0, 1))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    from dsl_b200 import _lib as L
+    from dsl_b200.trainer import DSLEngine
+    from tests.golden import inputs as GI
+
+    B = args.batch
+    eng = DSLEngine(B, H, W, depth=args.depth, seed=0, use_graphs=True)
+    rng = np.random.RandomState(100 + rank)
+    # synthetic COCO-shaped batch in PINNED host memory (mean-subtracted pixels, caffe normalisation: std 1)
+    img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
+    img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
+    gts, labels, ignores = GI.make_gt(200 + rank, B, H, W, max_gt=20, max_ignore=5, with_ignore=True)
+    gts = [g.pin_memory() for g in gts]
+    labels = [l.pin_memory() for l in labels]
+    ignores = [i.pin_memory() for i in ignores]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---------------------------------------------------------------- device-resident throughput (`value`)
+    eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+    for _ in range(max(args.warmup, 3)):
+        eng.step()
+    L.reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(eng.step, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step / 1e3)
+
+    # ---------------------------------------------------------------- end to end from pinned host buffers (`e2e`)
+    host_out = torch.zeros(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+        losses = eng.step()
+        host_out[:3].copy_(torch.stack([losses["loss_cls"], losses["loss_bbox"], losses["loss_centerness"]]),
+                           non_blocking=False)  # D2H read of the step's result: synchronises every step
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    h2d = img_s.numel() * 4 + img_t.numel() * 4 + sum(g.numel() * 4 for g in gts) + \
+        sum(l.numel() * 8 for l in labels) + sum(i.numel() * 4 for i in ignores) + 2 * (B + 1) * 4
+    e2e = dict(value=round(B * world / (ms_e2e / 1e3), 2), unit=UNIT, h2d_bytes_per_step=int(h2d),
+               d2h_bytes_per_step=12, ms_per_step=round(ms_e2e, 3))
+    loss_vals = [float(v) for v in host_out[:3]]
+    assert all(np.isfinite(loss_vals)), f"non-finite losses {loss_vals}"
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (conv igemm)
+    pk = peaks()
+    prof = eng.profile_kernels(steps=3)
+    launches = prof["launches_per_step"]
+    if rank == 0 and os.environ.get("DSLB_PLAN_TABLE"):
+        with open(os.environ["DSLB_PLAN_TABLE"], "w") as f:
+            for r in prof["plans"]:
+                f.write(json.dumps(r) + "\n")
+    ck = prof["conv_igemm"]
+    achieved = ck["flops"] / (ck["ms"] * 1e-3) / 1e12 if ck["ms"] > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="conv_igemm_kernel (fprop + dgrad implicit GEMM, tcgen05)",
+                    achieved=round(achieved, 1), peak=pk["tf_sust"], unit="TFLOP/s",
+                    frac=round(achieved / pk["tf_sust"], 4), traffic=None, peak_source=pk["src"] + " sustained",
+                    launches_per_step=ck["n"], avg_launch_us=round(1e3 * ck["ms"] / max(ck["n"], 1), 2),
+                    flops_per_step=ck["flops"], share_of_step=round(ck["ms"] / prof["step_ms"], 4),
+                    wgrad=dict(achieved=round(prof["conv_wgrad"]["flops"] / max(prof["conv_wgrad"]["ms"], 1e-9) / 1e9,
+                                              1), unit="TFLOP/s", launches_per_step=prof["conv_wgrad"]["n"],
+                               share_of_step=round(prof["conv_wgrad"]["ms"] / prof["step_ms"], 4)),
+                    head_tower=prof.get("head_tower"),
+                    whole_step_tflops=round(eng.flops_per_step() / (ms_per_step * 1e-3) / 1e12, 1))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=1, warmup=0)
+
+    line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, teacher_batch=B,
+                            parallelism=f"dp{world}", l2="working set (activations) >> 126 MB L2; no flush needed",
+                            step="teacher fwd+decode gate, student fwd+loss+bwd, grad allreduce, clip+SGD, EMA, repack",
+                            cuda_graph=True),
+                e2e=e2e, gpu_launches=int(launches * args.steps), gpu_launches_per_step=int(launches),
+                roofline=roofline, cpu_baseline=cb, clocks=clocks,
+                losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

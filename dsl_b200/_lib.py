@@ -57,7 +57,28 @@ class GnSeg(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("dz", C.c_void_p), ("stats", C.c_void_p),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("red", C.c_void_p), ("dbias", C.c_void_p),
+        ("mr", C.c_void_p),
         ("N", C.c_int32), ("HW", C.c_int32),
+    ]
+
+
+class PackDesc(C.Structure):
+    """dslb_pack_desc_t"""
+    _fields_ = [
+        ("w", C.c_void_p), ("out", C.c_void_p), ("bn_gamma", C.c_void_p), ("bn_beta", C.c_void_p),
+        ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
+        ("O", C.c_int32), ("I", C.c_int32), ("R", C.c_int32), ("S", C.c_int32),
+        ("rows_pad", C.c_int32), ("cols_pad", C.c_int32), ("row_off", C.c_int32), ("col_off", C.c_int32),
+        ("mode", C.c_int32), ("fill_padding", C.c_int32), ("bn_eps", C.c_float),
+    ]
+
+
+class UnpackDesc(C.Structure):
+    """dslb_unpack_desc_t"""
+    _fields_ = [
+        ("dw", C.c_void_p), ("g", C.c_void_p), ("bn_gamma", C.c_void_p), ("bn_var", C.c_void_p),
+        ("O", C.c_int32), ("I", C.c_int32), ("R", C.c_int32), ("S", C.c_int32),
+        ("rows", C.c_int32), ("row_off", C.c_int32), ("bn_eps", C.c_float),
     ]
 
 
@@ -110,6 +131,12 @@ _proto("dslb_gn_bwd_params", I, VP, VP, VP, I, I, VP)
 _proto("dslb_pack_weight", I, VP, VP, I, I, I, I, I, I, VP, I, VP)
 _proto("dslb_unpack_wgrad", I, VP, VP, I, I, I, I, I, VP, I, VP)
 _proto("dslb_bn_fold", I, VP, VP, VP, VP, F, VP, VP, I, VP)
+_proto("dslb_pack_plan_create", I, C.POINTER(PackDesc), I, C.POINTER(C.c_void_p))
+_proto("dslb_unpack_plan_create", I, C.POINTER(UnpackDesc), I, C.POINTER(C.c_void_p))
+_proto("dslb_table_plan_run", I, VP, VP)
+_proto("dslb_table_plan_destroy", None, VP)
+_proto("dslb_fcos_regctr_affine", I, VP, I, VP, VP, VP, VP, VP, VP, I, VP)
+_proto("dslb_zero_upsample2", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_colsum", I, VP, VP, LL, I, I, VP)
 _proto("dslb_conv_dgrad_naive", I, VP, VP, VP, I, I, I, I, I, I, I, I, I, I, VP)
 _proto("dslb_fcos_targets", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, I, I, F, I, VP, VP, VP, VP, VP, VP)
@@ -125,7 +152,17 @@ _proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I
 GN_STAT_STRIDE = 32
 
 
+launch_count = 0  # C-ABI calls issued so far (each one launches at least one kernel of libdslb.so)
+
+
+def reset_launch_count():
+    global launch_count
+    launch_count = 0
+
+
 def check(rc, what=""):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = lib.dslb_last_error()
         raise DslbError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,332 @@
+// Multi-tensor ("one launch for the whole network") parameter kernels: refresh of the derived bf16 conv operands
+// from the fp32 master weights with the frozen BatchNorm folded in, and the reverse map from the packed fp32 weight
+// gradients to the OIHW gradient views. A plan owns a device copy of its descriptor table; running it is ONE launch.
+#include <new>
+
+#include "common.h"
+
+#include <cuda_bf16.h>
+
+namespace dslb {
+
+struct PackDescDev {
+  const float* w;
+  __nv_bfloat16* out;
+  const float* bn_gamma;
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  float* scale_out;
+  float* shift_out;
+  int O, I, R, S;
+  int rows_pad, cols_pad, row_off, col_off;
+  int rows, cols8;  // iteration space: rows x (cols8 * 8) per tap
+  int real_cols, fill;
+  int mode;
+  float eps;
+  long long work_begin;  // prefix sum of taps * rows * cols8
+};
+
+// One thread = 8 consecutive packed columns (one 16-byte store).
+//   mode 0 (fprop)  out[tap][row_off + o][col_off + i] = w[o][i][r][s] * sc[o]
+//   mode 1 (dgrad)  out[tap][row_off + i][col_off + o] = w[o][i][R-1-r][S-1-s] * sc[o]
+//   mode 2 (im2col) out[0][row_off + o][(r*S+s)*I + i] = w[o][i][r][s] * sc[o]      (stem: K = R*S*I in one row)
+__global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (D[mid].work_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const PackDescDev& d = D[lo];
+    const long long tl = t - d.work_begin;
+    const int c8 = tl % d.cols8;
+    const int row = (tl / d.cols8) % d.rows;
+    const int tap = tl / ((long long)d.cols8 * d.rows);
+    const int RS = d.R * d.S;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (d.mode == 0) {
+      if (row < d.O) {
+        float sc = 1.f;
+        if (d.bn_gamma) {
+          sc = d.bn_gamma[row] / sqrtf(d.bn_var[row] + d.eps);
+          if (tap == 0 && c8 == 0) {
+            d.scale_out[row] = sc;
+            d.shift_out[row] = d.bn_beta[row] - d.bn_mean[row] * sc;
+          }
+        }
+        const float* src = d.w + ((long long)row * d.I) * RS + tap;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = c8 * 8 + e;
+          if (i < d.I) v[e] = src[(long long)i * RS] * sc;
+        }
+      }
+    } else if (d.mode == 1) {
+      if (row < d.I) {
+        const int rtap = RS - 1 - tap;  // 180-degree rotation
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int o = c8 * 8 + e;
+          if (o < d.O) {
+            const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
+            v[e] = d.w[((long long)o * d.I + row) * RS + rtap] * sc;
+          }
+        }
+      }
+    } else {
+      if (row < d.O) {
+        float sc = 1.f;
+        if (d.bn_gamma) {
+          sc = d.bn_gamma[row] / sqrtf(d.bn_var[row] + d.eps);
+          if (c8 == 0) {
+            d.scale_out[row] = sc;
+            d.shift_out[row] = d.bn_beta[row] - d.bn_mean[row] * sc;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = c8 * 8 + e;
+          if (k < RS * d.I) {
+            const int tp = k / d.I, i = k - tp * d.I;
+            v[e] = d.w[((long long)row * d.I + i) * RS + tp] * sc;
+          }
+        }
+      }
+    }
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    __nv_bfloat16* dst = d.out + ((long long)tap * d.rows_pad + d.row_off + row) * d.cols_pad + d.col_off + c8 * 8;
+    const int lim = d.real_cols - c8 * 8;
+    if ((d.col_off & 7) == 0 && (d.fill || lim >= 8)) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
+    } else {  // partial / unaligned sub-block (conv_reg + conv_centerness share one packed operand): real columns only
+      const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(h);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e < lim) dst[e] = hv[e];
+    }
+  }
+}
+
+struct UnpackDescDev {
+  const float* dw;
+  float* g;
+  const float* bn_gamma;
+  const float* bn_var;
+  int O, I, R, S;
+  int rows, row_off;
+  float eps;
+  long long work_begin;  // prefix of O*I*R*S
+};
+
+// g[o][i][r][s] = dw[r*S+s][row_off + o][i] * sc[o]
+__global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n, long long total) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (D[mid].work_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const UnpackDescDev& d = D[lo];
+    const long long tl = t - d.work_begin;
+    const int RS = d.R * d.S;
+    const int tap = tl % RS;
+    const int i = (tl / RS) % d.I;
+    const int o = tl / ((long long)RS * d.I);
+    const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
+    d.g[tl] = d.dw[((long long)tap * d.rows + d.row_off + o) * d.I + i] * sc;
+  }
+}
+
+// y[n][2p][2q][:] = x[n][p][q][:], every other pixel of the [N][H][W][C] map = 0 (C % 8 == 0).
+__global__ void zero_upsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int h,
+                                      int w, int H, int W, int cv) {
+  const long long total = (long long)N * H * W * cv;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = t % cv;
+    const long long pix = t / cv;
+    const int X = pix % W;
+    const int Y = (pix / W) % H;
+    const int n = pix / ((long long)W * H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(X & 1) && !(Y & 1) && (Y >> 1) < h && (X >> 1) < w)
+      v = reinterpret_cast<const uint4*>(x)[(((long long)n * h + (Y >> 1)) * w + (X >> 1)) * cv + c8];
+    reinterpret_cast<uint4*>(y)[t] = v;
+  }
+}
+
+__global__ void regctr_affine_kernel(const float* __restrict__ scales, int stride, const float* __restrict__ reg_bias,
+                                     const float* __restrict__ ctr_bias, const float* __restrict__ level_mult,
+                                     float* __restrict__ rc_scale, float* __restrict__ rc_shift,
+                                     float* __restrict__ scale_vals, int nl) {
+  const int t = threadIdx.x;
+  if (t >= nl * 8) return;
+  const int l = t >> 3, j = t & 7;
+  const float sv = scales[(long long)l * stride];
+  const float sc = j < 4 ? sv * level_mult[l] : 1.f;
+  const float b = j < 4 ? reg_bias[j] : (j == 4 ? ctr_bias[0] : 0.f);
+  rc_scale[t] = sc;
+  rc_shift[t] = b * sc;
+  if (j == 0) scale_vals[l] = sv;
+}
+
+}  // namespace dslb
+
+using namespace dslb;
+
+struct dslb_table_plan {
+  void* dev = nullptr;
+  int n = 0;
+  long long total = 0;
+  int kind = 0;  // 0 pack, 1 unpack
+};
+
+extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_table_plan_t** out) {
+  DSLB_CHECK_ARG(descs && out && n >= 1, "dslb_pack_plan_create: bad arguments");
+  PackDescDev* h = new (std::nothrow) PackDescDev[n];
+  if (!h) {
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
+  long long w = 0;
+  for (int k = 0; k < n; ++k) {
+    const dslb_pack_desc_t& s = descs[k];
+    PackDescDev& d = h[k];
+    const bool ok = s.w && s.out && s.O > 0 && s.I > 0 && s.R > 0 && s.S > 0 && s.mode >= 0 && s.mode <= 2 &&
+                    s.cols_pad % 8 == 0 && (!s.bn_gamma || (s.bn_beta && s.bn_mean && s.bn_var)) &&
+                    (s.mode == 1 || !s.bn_gamma || (s.scale_out && s.shift_out));
+    if (!ok) {
+      delete[] h;
+      set_error("dslb_pack_plan_create: descriptor %d is invalid", k);
+      return DSLB_EINVAL;
+    }
+    d.w = s.w;
+    d.out = (__nv_bfloat16*)s.out;
+    d.bn_gamma = s.bn_gamma;
+    d.bn_beta = s.bn_beta;
+    d.bn_mean = s.bn_mean;
+    d.bn_var = s.bn_var;
+    d.scale_out = s.scale_out;
+    d.shift_out = s.shift_out;
+    d.O = s.O; d.I = s.I; d.R = s.R; d.S = s.S;
+    d.rows_pad = s.rows_pad; d.cols_pad = s.cols_pad; d.row_off = s.row_off; d.col_off = s.col_off;
+    d.mode = s.mode;
+    d.eps = s.bn_eps;
+    const int real_rows = (s.mode == 1) ? s.I : s.O;
+    const int real_cols = (s.mode == 1) ? s.O : (s.mode == 2 ? s.R * s.S * s.I : s.I);
+    // full = rewrite the zero padding too; otherwise only the real sub-block (shared, offset outputs)
+    d.rows = s.fill_padding ? s.rows_pad : real_rows;
+    d.cols8 = s.fill_padding ? s.cols_pad / 8 : (real_cols + 7) / 8;
+    d.real_cols = real_cols;
+    d.fill = s.fill_padding ? 1 : 0;
+    if (d.row_off + d.rows > s.rows_pad || d.col_off + (s.fill_padding ? s.cols_pad : real_cols) > s.cols_pad) {
+      delete[] h;
+      set_error("dslb_pack_plan_create: descriptor %d does not fit its packed block", k);
+      return DSLB_EINVAL;
+    }
+    d.work_begin = w;
+    const int taps = (s.mode == 2) ? 1 : s.R * s.S;
+    w += (long long)taps * d.rows * d.cols8;
+  }
+  dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
+  cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(PackDescDev) * n) : cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) e = cudaMemcpy(p->dev, h, sizeof(PackDescDev) * n, cudaMemcpyHostToDevice);
+  delete[] h;
+  if (e != cudaSuccess) {
+    set_error("dslb_pack_plan_create: %s", cudaGetErrorString(e));
+    if (p && p->dev) cudaFree(p->dev);
+    delete p;
+    return DSLB_ECUDA;
+  }
+  p->n = n;
+  p->total = w;
+  p->kind = 0;
+  *out = p;
+  return DSLB_OK;
+}
+
+extern "C" int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs, int n, dslb_table_plan_t** out) {
+  DSLB_CHECK_ARG(descs && out && n >= 1, "dslb_unpack_plan_create: bad arguments");
+  UnpackDescDev* h = new (std::nothrow) UnpackDescDev[n];
+  if (!h) {
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
+  long long w = 0;
+  for (int k = 0; k < n; ++k) {
+    const dslb_unpack_desc_t& s = descs[k];
+    UnpackDescDev& d = h[k];
+    if (!(s.dw && s.g && s.O > 0 && s.I > 0 && s.R > 0 && s.S > 0 && s.rows >= s.row_off + s.O &&
+          (!s.bn_gamma || s.bn_var))) {
+      delete[] h;
+      set_error("dslb_unpack_plan_create: descriptor %d is invalid", k);
+      return DSLB_EINVAL;
+    }
+    d.dw = s.dw; d.g = s.g; d.bn_gamma = s.bn_gamma; d.bn_var = s.bn_var;
+    d.O = s.O; d.I = s.I; d.R = s.R; d.S = s.S; d.rows = s.rows; d.row_off = s.row_off; d.eps = s.bn_eps;
+    d.work_begin = w;
+    w += (long long)s.O * s.I * s.R * s.S;
+  }
+  dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
+  cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(UnpackDescDev) * n) : cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) e = cudaMemcpy(p->dev, h, sizeof(UnpackDescDev) * n, cudaMemcpyHostToDevice);
+  delete[] h;
+  if (e != cudaSuccess) {
+    set_error("dslb_unpack_plan_create: %s", cudaGetErrorString(e));
+    if (p && p->dev) cudaFree(p->dev);
+    delete p;
+    return DSLB_ECUDA;
+  }
+  p->n = n;
+  p->total = w;
+  p->kind = 1;
+  *out = p;
+  return DSLB_OK;
+}
+
+extern "C" int dslb_table_plan_run(const dslb_table_plan_t* p, void* stream) {
+  DSLB_CHECK_ARG(p && p->dev, "dslb_table_plan_run: null plan");
+  long long blocks = (p->total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (p->kind == 0)
+    pack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const PackDescDev*)p->dev, p->n, p->total);
+  else
+    unpack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const UnpackDescDev*)p->dev, p->n, p->total);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" void dslb_table_plan_destroy(dslb_table_plan_t* p) {
+  if (!p) return;
+  if (p->dev) cudaFree(p->dev);
+  delete p;
+}
+
+extern "C" int dslb_zero_upsample2(const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream) {
+  DSLB_CHECK_ARG(x && y && C % 8 == 0 && H >= 2 * h - 1 && W >= 2 * w - 1, "dslb_zero_upsample2: bad arguments");
+  const long long total = (long long)N * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  zero_upsample2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, h, w,
+                                                                        H, W, C / 8);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" int dslb_fcos_regctr_affine(const float* scales, int scale_stride, const float* reg_bias, const float* ctr_bias,
+                                       const float* level_mult, float* rc_scale, float* rc_shift, float* scale_vals,
+                                       int nlevels, void* stream) {
+  DSLB_CHECK_ARG(scales && reg_bias && ctr_bias && level_mult && rc_scale && rc_shift && scale_vals && nlevels >= 1 &&
+                     nlevels <= 16,
+                 "dslb_fcos_regctr_affine: bad arguments");
+  regctr_affine_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(scales, scale_stride, reg_bias, ctr_bias, level_mult, rc_scale,
+                                                            rc_shift, scale_vals, nlevels);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}

@@ -85,29 +85,48 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 // ------------------------------------------------------------------------------------------------ stem
 // im2col of the 7x7/2 pad-3 stem conv straight from the NCHW fp32 image: out[pix][k], k = (r*7+s)*3 + c for
 // k < 147, zero up to 192 (3 x 64-channel chunks for the tensor-core 1x1 conv that follows).
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W,
-                                   int Ho, int Wo) {
-  const long long total = (long long)N * Ho * Wo * 24;  // 24 chunks of 8 k-values per pixel
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int j = t % 24;
-    const long long pix = t / 24;
-    const int q = pix % Wo;
-    const int p = (pix / Wo) % Ho;
-    const int n = pix / ((long long)Wo * Ho);
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = j * 8 + e;
-      float v = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int r = tap / 7, s = tap - r * 7;
-        const int h = p * 2 - 3 + r, w = q * 2 - 3 + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(img + (((long long)n * 3 + c) * H + h) * W + w);
-      }
-      f[e] = v;
+// Block = one output row segment of STEM_QS pixels of one image: the 7 input rows x 3 channels x (2*QS+5) columns it
+// reads are staged in shared memory with coalesced fp32 loads, then each thread assembles 16-byte chunks of the
+// K-major rows (the whole block writes one contiguous QS*384-byte span).
+constexpr int STEM_QS = 64;
+constexpr int STEM_SW = 2 * STEM_QS + 5;
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                                          int N, int H, int W, int Ho, int Wo) {
+  __shared__ float patch[21 * STEM_SW];  // [(r*3 + c)][column]
+  __shared__ short koff[192];            // k -> offset inside `patch` of tap (r, s), channel c; -1 for the zero padding
+  const int qsegs = (Wo + STEM_QS - 1) / STEM_QS;
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x;
+    const int tap = k / 3, c = k - tap * 3, r = tap / 7, sx = tap - r * 7;
+    koff[k] = k < 147 ? (short)((r * 3 + c) * STEM_SW + sx) : (short)-1;
+  }
+  const long long nblk = (long long)N * Ho * qsegs;
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const int qs = b % qsegs;
+    const int p = (b / qsegs) % Ho;
+    const int n = b / ((long long)qsegs * Ho);
+    const int q0 = qs * STEM_QS;
+    const int w0 = q0 * 2 - 3, h0 = p * 2 - 3;
+    __syncthreads();  // previous iteration's readers are done (and koff is visible on the first one)
+    for (int i = threadIdx.x; i < 21 * STEM_SW; i += 256) {
+      const int rc = i / STEM_SW, col = i - rc * STEM_SW;
+      const int r = rc / 3, c = rc - r * 3;
+      const int h = h0 + r, w = w0 + col;
+      patch[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(img + (((long long)n * 3 + c) * H + h) * W + w) : 0.f;
     }
-    reinterpret_cast<uint4*>(out)[t] = pack8(f);
+    __syncthreads();
+    const int npx = min(STEM_QS, Wo - q0);
+    uint4* dst = reinterpret_cast<uint4*>(out + (((long long)n * Ho + p) * Wo + q0) * 192);
+    for (int i = threadIdx.x; i < npx * 24; i += 256) {
+      const int ql = i / 24, j = i - ql * 24;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int o = koff[j * 8 + e];
+        f[e] = o >= 0 ? patch[o + 2 * ql] : 0.f;
+      }
+      dst[i] = pack8(f);
+    }
   }
 }
 
@@ -218,6 +237,7 @@ struct GnSeg {
   const float* beta;
   double* red;              // bwd: [N][C][2] (sum dy, sum dy*xhat), fp64
   float* dbias;             // bwd: [C] += sum dx
+  float4* mr;               // [N][G] (mean, rstd, k1, k2) in fp32: .xy written by the forward apply, .zw by the backward
   int HW, npix;             // pixels per image, N*HW
   long long work_begin;     // prefix of (npix * C/8) work items
 };
@@ -234,24 +254,39 @@ __device__ __forceinline__ int gn_find(const GnParams& P, long long t) {
   return si;
 }
 
+// (sum, sumsq) in fp64 -> (mean, rstd) in fp32, once per (map, image, group): keeps the slow fp64 pipe out of the
+// per-element kernels.
+__global__ void gn_finalize_kernel(const __grid_constant__ GnParams P, int maxN) {
+  const int G = P.C / P.cpg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nseg * maxN * G) return;
+  const int g = t % G;
+  const int n = (t / G) % maxN;
+  const GnSeg& s = P.seg[t / (G * maxN)];
+  if (n >= s.npix / s.HW) return;
+  const double* st = s.stats + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE;
+  const double m = (double)P.cpg * s.HW;
+  const double mean = st[0] / m;
+  double var = st[1] / m - mean * mean;
+  if (var < 0) var = 0;
+  float4* o = s.mr + n * G + g;
+  o->x = (float)mean;
+  o->y = (float)(1.0 / sqrt(var + (double)P.eps));
+}
+
 // y = relu((x - mean) * rstd * gamma + beta)   (mmcv ConvModule order conv -> GN -> ReLU, eps 1e-5)
 __global__ void gn_apply_relu_kernel(const __grid_constant__ GnParams P) {
   const int cv = P.C / 8;
+  const int G = P.C / P.cpg;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += (long long)gridDim.x * blockDim.x) {
     const GnSeg& s = P.seg[gn_find(P, t)];
     const long long tl = t - s.work_begin;
     const int c8 = tl % cv;
     const long long pix = tl / cv;
     const int n = pix / s.HW;
-    const int G = P.C / P.cpg;
     const int g = (c8 * 8) / P.cpg;
-    const double* st = s.stats + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE;
-    const double m = (double)P.cpg * s.HW;
-    const double mean = st[0] / m;
-    double var = st[1] / m - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)P.eps));
-    const float fmean = (float)mean;
+    const float4 mr = __ldg(s.mr + n * G + g);
+    const float rstd = mr.y, fmean = mr.x;
     float a[8];
     unpack8(*reinterpret_cast<const uint4*>(s.x + pix * P.C + c8 * 8), a);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(s.gamma + c8 * 8));
@@ -279,13 +314,8 @@ __global__ void gn_bwd_reduce_kernel(const __grid_constant__ GnParams P, const i
   const int c8 = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int G = P.C / P.cpg;
   const int g = (c8 * 8) / P.cpg;
-  const double* st = s.stats + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE;
-  const double m = (double)P.cpg * s.HW;
-  const double mean = st[0] / m;
-  double var = st[1] / m - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)P.eps));
-  const float fmean = (float)mean;
+  const float4 mr = __ldg(s.mr + n * G + g);
+  const float rstd = mr.y, fmean = mr.x;
   float ga[8], be[8], A[8], B[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -324,6 +354,27 @@ __global__ void gn_bwd_reduce_kernel(const __grid_constant__ GnParams P, const i
   atomicAdd(dst + 1, (double)b);
 }
 
+// Between the two passes: k1 = S1/m, k2 = S2/m with S1 = sum_{c in g} gamma_c A_c, S2 likewise with B (fp64 -> fp32).
+__global__ void gn_bwd_finalize_kernel(const __grid_constant__ GnParams P, int maxN) {
+  const int G = P.C / P.cpg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nseg * maxN * G) return;
+  const int g = t % G;
+  const int n = (t / G) % maxN;
+  const GnSeg& s = P.seg[t / (G * maxN)];
+  if (n >= s.npix / s.HW) return;
+  const double m = (double)P.cpg * s.HW;
+  double S1 = 0, S2 = 0;
+  for (int c = g * P.cpg; c < (g + 1) * P.cpg; ++c) {
+    const double gm = (double)__ldg(s.gamma + c);
+    S1 += gm * s.red[((long long)n * P.C + c) * 2];
+    S2 += gm * s.red[((long long)n * P.C + c) * 2 + 1];
+  }
+  float4* o = s.mr + n * G + g;
+  o->z = (float)(S1 / m);
+  o->w = (float)(S2 / m);
+}
+
 // Backward pass 2: dx = rstd * (gamma*dy - S1/m - xhat*S2/m), S1 = sum_{c in g} gamma_c A_c, S2 likewise with B;
 // also accumulates dbias[c] += sum dx (the conv bias in front of the GroupNorm).
 __global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const int* __restrict__ blk_seg,
@@ -336,20 +387,8 @@ __global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const in
   const int c8 = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int G = P.C / P.cpg;
   const int g = (c8 * 8) / P.cpg;
-  const double* st = s.stats + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE;
-  const double m = (double)P.cpg * s.HW;
-  const double mean = st[0] / m;
-  double var = st[1] / m - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)P.eps));
-  const float fmean = (float)mean;
-  double S1 = 0, S2 = 0;
-  for (int c = g * P.cpg; c < (g + 1) * P.cpg; ++c) {
-    const double gm = (double)__ldg(s.gamma + c);
-    S1 += gm * s.red[((long long)n * P.C + c) * 2];
-    S2 += gm * s.red[((long long)n * P.C + c) * 2 + 1];
-  }
-  const float k1 = (float)(S1 / m), k2 = (float)(S2 / m);
+  const float4 mr = __ldg(s.mr + n * G + g);
+  const float rstd = mr.y, fmean = mr.x, k1 = mr.z, k2 = mr.w;
   float ga[8], be[8], D[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -533,8 +572,8 @@ extern "C" int dslb_nhwc_to_nchw_f32(const void* x, float* y, int N, int C, int 
 extern "C" int dslb_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream) {
   DSLB_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "dslb_stem_im2col: bad arguments");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const long long total = (long long)N * Ho * Wo * 24;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, N, H, W, Ho, Wo);
+  const long long nblk = (long long)N * Ho * ((Wo + STEM_QS - 1) / STEM_QS);
+  stem_im2col_kernel<<<grid_for(nblk, 1, 16), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, N, H, W, Ho, Wo);
   LAUNCH_CHECK();
 }
 
@@ -590,6 +629,8 @@ static int fill_gn_params(GnParams& P, const dslb_gn_seg_t* segs, int nseg, int 
     d.beta = segs[i].beta;
     d.red = segs[i].red;
     d.dbias = segs[i].dbias;
+    d.mr = reinterpret_cast<float4*>(segs[i].mr);
+    DSLB_CHECK_ARG(d.x && d.y && d.stats && d.gamma && d.beta && d.mr, "gn: seg %d has a null pointer", i);
     d.HW = segs[i].HW;
     d.npix = segs[i].N * segs[i].HW;
     d.work_begin = w;
@@ -603,6 +644,11 @@ extern "C" int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, in
   GnParams P;
   int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
   if (rc != DSLB_OK) return rc;
+  int maxN = 1;
+  for (int i = 0; i < nseg; ++i) maxN = segs[i].N > maxN ? segs[i].N : maxN;
+  const int nfin = nseg * maxN * groups;
+  gn_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
+  DSLB_CHECK_CUDA(cudaGetLastError());
   gn_apply_relu_kernel<<<grid_for(P.total, 256), 256, 0, (cudaStream_t)stream>>>(P);
   LAUNCH_CHECK();
 }
@@ -636,6 +682,11 @@ extern "C" int dslb_gn_bwd(const dslb_gn_seg_t* segs, int nseg, int C, int group
   int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
   if (rc != DSLB_OK) return rc;
   gn_bwd_reduce_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  int maxN = 1;
+  for (int i = 0; i < nseg; ++i) maxN = segs[i].N > maxN ? segs[i].N : maxN;
+  const int nfin = nseg * maxN * groups;
+  gn_bwd_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
   DSLB_CHECK_CUDA(cudaGetLastError());
   gn_bwd_apply_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
   LAUNCH_CHECK();

@@ -90,6 +90,36 @@ class WgradPlan:
             pass
 
 
+class TablePlan:
+    """dslb_pack_plan_* / dslb_unpack_plan_* wrapper: one launch over a table of per-conv descriptors."""
+
+    def __init__(self, descs, kind, what):
+        self.what = what
+        self.keep = []
+        cls = L.PackDesc if kind == "pack" else L.UnpackDesc
+        arr = (cls * len(descs))()
+        for a, d in zip(arr, descs):
+            for k, v in d.items():
+                if isinstance(v, torch.Tensor):
+                    self.keep.append(v)
+                    setattr(a, k, v.data_ptr())
+                elif v is not None:
+                    setattr(a, k, v)
+        self.plan = C.c_void_p()
+        fn = L.lib.dslb_pack_plan_create if kind == "pack" else L.lib.dslb_unpack_plan_create
+        L.check(fn(arr, len(descs), C.byref(self.plan)), what)
+
+    def run(self):
+        L.check(L.lib.dslb_table_plan_run(self.plan, L.cur_stream()), self.what)
+
+    def __del__(self):
+        try:
+            if self.plan:
+                L.lib.dslb_table_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+
 class ConvW:
     """Derived device state of one conv: packed bf16 operands (frozen BatchNorm folded in), shift vector, wgrad slot."""
 
@@ -117,29 +147,33 @@ class ConvW:
         self.dy_ld = dy_ld or ceil_to(self.O, 64)  # channel stride of the gradient buffer feeding dgrad/wgrad
         if need_dgrad:
             self.wpT = torch.zeros(self.R * self.S, ceil_to(self.I, 16), self.dy_ld, dtype=BF16, device=dev)
-        self.dw = None
+        self.dw = None  # fp32 packed wgrad [taps][O][I]: a view into the net's zero arena (FCOSNet._alloc_arena)
         if trainable:
-            self.dw = net.alloc_dw(self.R * self.S * self.O * self.I).view(self.R * self.S, self.O, self.I)
+            net.want_arena(self, "dw", self.R * self.S * self.O * self.I, (self.R * self.S, self.O, self.I))
 
-    def repack(self):
-        s = L.cur_stream()
+    def pack_descs(self):
+        """dslb_pack_desc_t fields of the fprop (and dgrad) operands of this conv."""
         st = self.net.store
+        bn = {}
         if self.bn is not None:
-            L.check(L.lib.dslb_bn_fold(L.ptr(st[self.bn + ".weight"]), L.ptr(st[self.bn + ".bias"]),
-                                       L.ptr(st[self.bn + ".running_mean"]), L.ptr(st[self.bn + ".running_var"]),
-                                       1e-5, L.ptr(self.scale), L.ptr(self.shift), self.O, s), "bn_fold")
-        L.check(L.lib.dslb_pack_weight(L.ptr(self.w), L.ptr(self.wp), self.O, self.I, self.R, self.S, self.cout_pad,
-                                       self.I, L.ptr(self.scale), 0, s), "pack_weight")
+            bn = dict(bn_gamma=st[self.bn + ".weight"], bn_beta=st[self.bn + ".bias"],
+                      bn_mean=st[self.bn + ".running_mean"], bn_var=st[self.bn + ".running_var"], bn_eps=1e-5,
+                      scale_out=self.scale, shift_out=self.shift)
+        out = [dict(w=self.w, out=self.wp, O=self.O, I=self.I, R=self.R, S=self.S, rows_pad=self.cout_pad,
+                    cols_pad=self.I, mode=0, fill_padding=1, **bn)]
         if self.need_dgrad:
-            L.check(L.lib.dslb_pack_weight(L.ptr(self.w), L.ptr(self.wpT), self.O, self.I, self.R, self.S,
-                                           self.wpT.shape[1], self.wpT.shape[2], L.ptr(self.scale), 1, s),
-                    "pack_weight(T)")
+            out.append(dict(w=self.w, out=self.wpT, O=self.O, I=self.I, R=self.R, S=self.S,
+                            rows_pad=self.wpT.shape[1], cols_pad=self.wpT.shape[2], mode=1, fill_padding=1, **bn))
+        return out
 
-    def unpack_grad(self):
+    def unpack_desc(self):
         """packed fp32 wgrad -> OIHW gradient view (x folded BN scale)."""
-        g = self.net.grad_view(self.wname)
-        L.check(L.lib.dslb_unpack_wgrad(L.ptr(self.dw), L.ptr(g), self.O, self.I, self.R, self.S, self.O,
-                                        L.ptr(self.scale), 0, L.cur_stream()), "unpack_wgrad")
+        st = self.net.store
+        d = dict(dw=self.dw, g=self.net.grad_view(self.wname), O=self.O, I=self.I, R=self.R, S=self.S, rows=self.O,
+                 row_off=0)
+        if self.bn is not None:
+            d.update(bn_gamma=st[self.bn + ".weight"], bn_var=st[self.bn + ".running_var"], bn_eps=1e-5)
+        return d
 
     # ---- segment builders -------------------------------------------------------------------------------
     def fseg(self, x, y, N, H, W, **kw):
@@ -154,8 +188,15 @@ class ConvW:
         d = dict(x=dy, w=self.wpT, y=dx, N=N, H=Ho, W=Wo, Cin=self.dy_ld, Cout=self.I, cout_pad=self.wpT.shape[1],
                  R=self.R, S=self.S, stride=1, pad=self.R - 1 - self.pad, ldc=self.I)
         if self.stride == 2:
-            assert self.R == 1, "tensor-core dgrad of strided convs is only implemented for 1x1"
+            assert self.R == 1, "strided 3x3 convs go through dseg_upsampled"
             d.update(scatter2=1, Hs=Hin, Ws=Win)
+        d.update(kw)
+        return d
+
+    def dseg_upsampled(self, dy_up, dx, N, Hin, Win, **kw):
+        """dgrad of a stride-2 conv as a stride-1 dgrad over the zero-upsampled dY ([N][Hin][Win][dy_ld])."""
+        d = dict(x=dy_up, w=self.wpT, y=dx, N=N, H=Hin, W=Win, Cin=self.dy_ld, Cout=self.I,
+                 cout_pad=self.wpT.shape[1], R=self.R, S=self.S, stride=1, pad=self.R - 1 - self.pad, ldc=self.I)
         d.update(kw)
         return d
 
@@ -180,8 +221,9 @@ class FCOSNet:
         if store is None:
             store = ParamStore(resnet_spec(depth) + fpn_spec() + head_spec(num_classes), device).init_reference(seed)
         self.store = store
-        self._dw_list = []
+        self._arena_wants = []
         self.fwd_ops, self.bwd_ops, self.repack_ops = [], [], []
+        self.extra_pack_descs = []
         self.convs = []
         self.flops_fwd = 0.0
         self.flops_bwd = 0.0
@@ -193,20 +235,35 @@ class FCOSNet:
         self._build_head()
         if train:
             self._build_loss()
+            self._alloc_arena()
             self._build_head_bwd()
             self._build_fpn_bwd()
             self._build_backbone_bwd()
-        self.repack()
+        self._build_pack_plans()
+        self.repack(everything=True)
 
     # ------------------------------------------------------------------------------------------ helpers
     def buf(self, *shape, dtype=BF16):
         return torch.zeros(*shape, dtype=dtype, device=self.dev)
 
-    def alloc_dw(self, n):
-        """fp32 packed weight-gradient accumulator of one conv (zeroed at the start of every backward)."""
-        t = torch.zeros(n, dtype=torch.float32, device=self.dev)
-        self._dw_list.append(t)
-        return t
+    def want_arena(self, obj, attr, n, shape, dtype=torch.float32):
+        """Reserve `n` elements of the zero arena (one memset at the start of every backward clears all of it);
+        `obj.attr` becomes a view of `shape` once _alloc_arena() has run."""
+        self._arena_wants.append((obj, attr, n, shape, dtype))
+
+    def _alloc_arena(self):
+        off = 0
+        plan = []
+        for obj, attr, n, shape, dtype in self._arena_wants:
+            nf = n * (2 if dtype == torch.float64 else 1)
+            plan.append((obj, attr, off, nf, shape, dtype))
+            off += ceil_to(nf, 64)
+        self.arena = torch.zeros(max(off, 64), dtype=torch.float32, device=self.dev)
+        for obj, attr, o, nf, shape, dtype in plan:
+            v = self.arena[o:o + nf]
+            if dtype == torch.float64:
+                v = v.view(torch.float64)
+            setattr(obj, attr, v.view(shape))
 
     def grad_view(self, name):
         o, n = self.store.offsets[name]
@@ -268,16 +325,11 @@ class FCOSNet:
         self.stem_scale = torch.empty(64, dtype=torch.float32, device=self.dev)
         self.stem_shift = torch.empty(64, dtype=torch.float32, device=self.dev)
 
-        def repack_stem():
-            s = L.cur_stream()
-            L.check(L.lib.dslb_bn_fold(L.ptr(st["backbone.bn1.weight"]), L.ptr(st["backbone.bn1.bias"]),
-                                       L.ptr(st["backbone.bn1.running_mean"]), L.ptr(st["backbone.bn1.running_var"]),
-                                       1e-5, L.ptr(self.stem_scale), L.ptr(self.stem_shift), 64, s), "bn_fold")
-            w = st["backbone.conv1.weight"]  # [64,3,7,7] -> [64][(r*7+s)*3+c]
-            wk = (w.permute(0, 2, 3, 1).reshape(64, 147) * self.stem_scale[:, None]).to(BF16)
-            self.stem_wp[0, :, :147].copy_(wk)
-
-        self.repack_ops.append(repack_stem)
+        self.extra_pack_descs.append((False, dict(
+            w=st["backbone.conv1.weight"], out=self.stem_wp, bn_gamma=st["backbone.bn1.weight"],
+            bn_beta=st["backbone.bn1.bias"], bn_mean=st["backbone.bn1.running_mean"],
+            bn_var=st["backbone.bn1.running_var"], bn_eps=1e-5, scale_out=self.stem_scale, shift_out=self.stem_shift,
+            O=64, I=3, R=7, S=7, rows_pad=64, cols_pad=192, mode=2, fill_padding=1)))
         self.add_fwd(self.ew("dslb_stem_im2col", self.img, self.stem_cols, B, H, W))
         self.plan_fwd([dict(x=self.stem_cols, w=self.stem_wp, y=self.stem_out, N=B, H=H2, W=W2, Cin=192, Cout=64,
                             cout_pad=64, R=1, S=1, stride=1, pad=0, ldc=64, shift=self.stem_shift, relu_nch=64)],
@@ -354,7 +406,7 @@ class FCOSNet:
         self.psize += [(h6, w6), (h7, w7)]
         for i in (3, 4):
             self.fpnc.append(self.conv(f"neck.fpn_convs.{i}.conv.weight", bias=f"neck.fpn_convs.{i}.conv.bias",
-                                       stride=2, pad=1, need_dgrad=False, trainable=tr))
+                                       stride=2, pad=1, need_dgrad=tr, trainable=tr))
         self.p.append(self.buf(B, h6, w6, 256))
         self.p.append(self.buf(B, h7, w7, 256))
         self.r6 = self.buf(B, h6, w6, 256)
@@ -376,6 +428,7 @@ class FCOSNet:
                                                 trainable=tr))
         # GroupNorm statistics of all (branch, layer, level) maps in one buffer -> one memset per pass
         self.gn_stats = torch.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=self.dev)
+        self.gn_mr = torch.zeros(2, 4, nl, B, 32, 4, dtype=torch.float32, device=self.dev)
         self.add_fwd(self.gn_stats.zero_)
         self.y = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
         self.z = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
@@ -388,39 +441,38 @@ class FCOSNet:
                                                        gn_stats=self.gn_stats[bi_, i, l], gn_cpg=8))
                     gsegs.append(dict(x=self.y[br][i][l], y=self.z[br][i][l], stats=self.gn_stats[bi_, i, l],
                                       gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
-                                      beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], N=B, HW=h * w))
+                                      beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], mr=self.gn_mr[bi_, i, l], N=B,
+                                      HW=h * w))
             self.plan_fwd(segs, f"head.tower{i}")
             self.add_fwd(self._gn_apply(gsegs))
         # predictors: conv_cls (N=80, fp32) on the cls tower; conv_reg + conv_centerness fused (N=5 -> 16, fp32
         # rows of 8) on the reg tower with bbox = relu(scale_l * (conv + b)) (x stride in eval mode)
         self.cls_w = self.conv("bbox_head.conv_cls.weight", bias="bbox_head.conv_cls.bias", pad=1, need_dgrad=tr,
                                trainable=tr, dy_ld=128)
-        self.rc_w5 = torch.zeros(5, 256, 3, 3, dtype=torch.float32, device=self.dev)  # [conv_reg; conv_centerness]
-        self.rc_b5 = torch.zeros(5, dtype=torch.float32, device=self.dev)
-        self.rc_wp = torch.zeros(9, 16, 256, dtype=BF16, device=self.dev)
+        self.rc_wp = torch.zeros(9, 16, 256, dtype=BF16, device=self.dev)   # rows 0-3 conv_reg, 4 conv_centerness
         self.rc_wpT = torch.zeros(9, 256, 64, dtype=BF16, device=self.dev)
         self.rc_scale = torch.ones(nl, 8, dtype=torch.float32, device=self.dev)
         self.rc_shift = torch.zeros(nl, 8, dtype=torch.float32, device=self.dev)
         self.scale_vals = torch.ones(nl, dtype=torch.float32, device=self.dev)
         self.level_mult = torch.tensor([float(s) if not self.train else 1.0 for s in STRIDES[:nl]],
                                        dtype=torch.float32, device=self.dev)
-        scale_names = [f"bbox_head.scales.{l}.scale" for l in range(nl)]
+        offs = [st.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
+        self.scale_stride = offs[1] - offs[0]
+        assert all(offs[l] == offs[0] + l * self.scale_stride for l in range(nl))
+        for wname, row in (("bbox_head.conv_reg.weight", 0), ("bbox_head.conv_centerness.weight", 4)):
+            w = st[wname]
+            self.extra_pack_descs.append((tr, dict(w=w, out=self.rc_wp, O=w.shape[0], I=256, R=3, S=3, rows_pad=16,
+                                                   cols_pad=256, row_off=row, mode=0, fill_padding=0)))
+            if tr:
+                self.extra_pack_descs.append((tr, dict(w=w, out=self.rc_wpT, O=w.shape[0], I=256, R=3, S=3,
+                                                       rows_pad=256, cols_pad=64, col_off=row, mode=1,
+                                                       fill_padding=0)))
 
         def repack_regctr():
-            s = L.cur_stream()
-            self.rc_w5[:4].copy_(st["bbox_head.conv_reg.weight"])
-            self.rc_w5[4:].copy_(st["bbox_head.conv_centerness.weight"])
-            self.rc_b5[:4].copy_(st["bbox_head.conv_reg.bias"])
-            self.rc_b5[4:].copy_(st["bbox_head.conv_centerness.bias"])
-            torch.stack([st[n] for n in scale_names], out=self.scale_vals)
-            sc = self.scale_vals * self.level_mult
-            self.rc_scale[:, :4] = sc[:, None]
-            self.rc_shift[:, :5] = self.rc_b5[None, :] * self.rc_scale[:, :5]
-            L.check(L.lib.dslb_pack_weight(L.ptr(self.rc_w5), L.ptr(self.rc_wp), 5, 256, 3, 3, 16, 256, None, 0, s),
-                    "pack regctr")
-            if tr:
-                L.check(L.lib.dslb_pack_weight(L.ptr(self.rc_w5), L.ptr(self.rc_wpT), 5, 256, 3, 3, 256, 64, None, 1,
-                                               s), "pack regctr T")
+            L.check(L.lib.dslb_fcos_regctr_affine(
+                L.ptr(st["bbox_head.scales.0.scale"]), self.scale_stride, L.ptr(st["bbox_head.conv_reg.bias"]),
+                L.ptr(st["bbox_head.conv_centerness.bias"]), L.ptr(self.level_mult), L.ptr(self.rc_scale),
+                L.ptr(self.rc_shift), L.ptr(self.scale_vals), nl, L.cur_stream()), "regctr_affine")
 
         self.repack_ops.append(repack_regctr)
         self.cls_out = [self.buf(B, h, w, C, dtype=torch.float32) for (h, w) in self.psize]
@@ -488,8 +540,9 @@ class FCOSNet:
         self.ctr_targets = torch.zeros(P, dtype=torch.float32, device=self.dev)
         self.counts = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self.norm = torch.ones(2, dtype=torch.float32, device=self.dev)
-        self.loss_sums = torch.zeros(4, dtype=torch.float64, device=self.dev)
-        self.dscale = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.loss_acc = torch.zeros(16, dtype=torch.float32, device=self.dev)  # one memset for both accumulators
+        self.loss_sums = self.loss_acc[:8].view(torch.float64)
+        self.dscale = self.loss_acc[8:16]
         self.max_boxes = 1024
         self.gt_boxes = torch.zeros(self.max_boxes, 4, dtype=torch.float32, device=self.dev)
         self.gt_labels = torch.zeros(self.max_boxes, dtype=torch.int64, device=self.dev)
@@ -502,6 +555,9 @@ class FCOSNet:
         # labeled images come first (fcos_head.py:227-233): B/2 for an even batch, (B-1)/2 with the SI extra image
         self.n_labeled = B // 2 if B % 2 == 0 else (B - 1) // 2
         self.si_weight = 0.0
+        self.want_arena(self, "gn_red", 2 * 4 * nl * B * 256 * 2, (2, 4, nl, B, 256, 2), torch.float64)
+        self.want_arena(self, "rc_dw", 9 * 5 * 256, (9, 5, 256))
+        self.want_arena(self, "rc_db", 8, (8,))
         scale_idx = [self.store.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
         self.scale_idx = torch.tensor(scale_idx, dtype=torch.long, device=self.dev)
 
@@ -545,8 +601,7 @@ class FCOSNet:
         """kernel 2 (after `counts` has been all-reduced over ranks): losses + gradients of the head outputs."""
         s = L.cur_stream()
         L.check(L.lib.dslb_fcos_norm(L.ptr(self.counts), float(self.world_size), L.ptr(self.norm), s), "fcos_norm")
-        self.loss_sums.zero_()
-        self.dscale.zero_()
+        self.loss_acc.zero_()
         nl = len(self.psize)
         L.check(L.lib.dslb_fcos_loss(
             self.levels_arr, nl, self.B, self.C, L.ptr(self.labels), L.ptr(self.bbox_targets), L.ptr(self.weights),
@@ -561,16 +616,11 @@ class FCOSNet:
         br_names = ("cls", "reg")
         self.dz = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
         self.dy = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
-        self.gn_red = torch.zeros(2, 4, nl, B, 256, 2, dtype=torch.float64, device=self.dev)
         self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]  # gradient w.r.t. the FPN outputs
-        self.rc_dw = torch.zeros(9, 5, 256, dtype=torch.float32, device=self.dev)
 
         def zero_state():
             self.grad.zero_()
-            self.gn_red.zero_()
-            for t in self._dw_list:
-                t.zero_()
-            self.rc_dw.zero_()
+            self.arena.zero_()  # every packed wgrad accumulator, the GroupNorm backward sums, rc_dw / rc_db
 
         self.add_bwd(zero_state)
         # --- predictors: wgrad (10 segs), bias grads, dgrad into the last tower outputs
@@ -582,7 +632,6 @@ class FCOSNet:
                               ldy=64, dw_rows=5, R=3, S=3, stride=1, pad=1))
         self.plan_wgrad(wsegs, "head.predictors.wgrad")
         g_cls_b = self.grad_view("bbox_head.conv_cls.bias")
-        self.rc_db = torch.zeros(8, dtype=torch.float32, device=self.dev)
         for l, (h, w) in enumerate(self.psize):
             self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C))
             self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5))
@@ -602,6 +651,7 @@ class FCOSNet:
                                       stats=self.gn_stats[bi_, i, l],
                                       gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
                                       beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], red=self.gn_red[bi_, i, l],
+                                      mr=self.gn_mr[bi_, i, l],
                                       dbias=self.grad_view(f"bbox_head.{br}_convs.{i}.conv.bias"), N=B, HW=h * w))
             self.add_bwd(self._gn_bwd(gsegs))
             for bi_, br in enumerate(br_names):
@@ -661,14 +711,18 @@ class FCOSNet:
         self.tmp6 = self.buf(B, h6, w6, 256)
         self.plan_wgrad([self.fpnc[4].wseg(self.r6, self.dp[4], B, h6, w6)], "fpn.p7.wgrad")
         self.add_bwd(self.ew("dslb_colsum", self.dp[4], gb(4), B * h7 * w7, 256, 256))
-        self.add_bwd(self.ew("dslb_conv_dgrad_naive", self.dp[4], self.fpnc[4].wp, self.tmp6, B, h6, w6, 256, 256, 256,
-                             3, 3, 2, 1, 0))
-        self.add_bwd(self.ew("dslb_relu_family", self.tmp6, self.p[3], self.tmp6, self.tmp6.numel(), 1))
+        # dgrad of the two stride-2 3x3 convs: zero-upsample dY, then a stride-1 tensor-core dgrad
+        self.up7 = self.buf(B, h6, w6, 256)
+        self.up6 = self.buf(B, h5, w5, 256)
+        self.add_bwd(self.ew("dslb_zero_upsample2", self.dp[4], self.up7, B, h7, w7, h6, w6, 256))
+        self.plan_bwd([self.fpnc[4].dseg_upsampled(self.up7, self.tmp6, B, h6, w6, relu_mask=self.p[3])],
+                      "fpn.p7.dgrad")
         self.add_bwd(self.ew("dslb_relu_family", self.dp[3], self.tmp6, self.dp[3], self.tmp6.numel(), 2))
         self.plan_wgrad([self.fpnc[3].wseg(self.p[2], self.dp[3], B, h5, w5)], "fpn.p6.wgrad")
         self.add_bwd(self.ew("dslb_colsum", self.dp[3], gb(3), B * h6 * w6, 256, 256))
-        self.add_bwd(self.ew("dslb_conv_dgrad_naive", self.dp[3], self.fpnc[3].wp, self.dp[2], B, h5, w5, 256, 256,
-                             256, 3, 3, 2, 1, 1))
+        self.add_bwd(self.ew("dslb_zero_upsample2", self.dp[3], self.up6, B, h6, w6, h5, w5, 256))
+        self.plan_bwd([self.fpnc[3].dseg_upsampled(self.up6, self.dp[2], B, h5, w5, residual=self.dp[2])],
+                      "fpn.p6.dgrad")
         # P3..P5 = conv3x3(merged laterals)
         self.plan_wgrad([self.fpnc[i].wseg(self.lm[i], self.dp[i], B, cs[i][1], cs[i][2]) for i in range(3)],
                         "fpn.out.wgrad")
@@ -742,33 +796,45 @@ class FCOSNet:
                 g = self.gc[li - 2]
                 self.plan_bwd([blk["ds"].dseg(M, g, B, h, w, hin, win, residual=g)], name + ".downsample.dgrad")
                 self.plan_bwd([blk["c1"].dseg(blk["da1"], g, B, h, w, hin, win, residual=g)], name + ".conv1.dgrad")
-        # finally: packed wgrads -> OIHW gradient views
-        for c in self.convs:
-            if c.trainable:
-                self.add_bwd(c.unpack_grad)
+        # finally: every packed wgrad -> its OIHW gradient view, in ONE launch
+        descs = [c.unpack_desc() for c in self.convs if c.trainable]
+        descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_reg.weight"), O=4, I=256, R=3, S=3, rows=5,
+                          row_off=0))
+        descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_centerness.weight"), O=1, I=256, R=3, S=3,
+                          rows=5, row_off=4))
+        self.unpack_plan = TablePlan(descs, "unpack", "unpack_wgrads")
+        self.add_bwd(self.unpack_plan.run)
 
         def finish_head_grads():
-            s = L.cur_stream()
-            g_reg_w = self.grad_view("bbox_head.conv_reg.weight")
-            g_ctr_w = self.grad_view("bbox_head.conv_centerness.weight")
-            # rc_dw [9][5][256] -> OIHW
-            L.check(L.lib.dslb_unpack_wgrad(L.ptr(self.rc_dw), L.ptr(self._rc_g5), 5, 256, 3, 3, 5, None, 0, s),
-                    "unpack regctr")
-            g_reg_w.copy_(self._rc_g5[:4 * 256 * 9])
-            g_ctr_w.copy_(self._rc_g5[4 * 256 * 9:])
             self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
             self.grad_view("bbox_head.conv_centerness.bias").copy_(self.rc_db[4:5])
-            self.rc_db.zero_()
             self.grad.index_copy_(0, self.scale_idx, self.dscale[:len(self.psize)])
 
-        self._rc_g5 = torch.zeros(5 * 256 * 9, dtype=torch.float32, device=self.dev)
         self.add_bwd(finish_head_grads)
 
     # ------------------------------------------------------------------------------------------ run
-    def repack(self):
-        """Refresh every derived bf16 operand from the fp32 master parameters (after an optimizer / EMA step)."""
+    def _build_pack_plans(self):
+        """Two multi-tensor launches: `pack_all` refreshes every derived operand, `pack_train` only those whose master
+        weights an optimizer step can change (the student never needs more after construction)."""
+        all_d, train_d = [], []
         for c in self.convs:
-            c.repack()
+            ds = c.pack_descs()
+            all_d += ds
+            if c.trainable:
+                train_d += ds
+        for tr, d in self.extra_pack_descs:
+            all_d.append(d)
+            if tr:
+                train_d.append(d)
+        self.pack_all = TablePlan(all_d, "pack", "pack_all")
+        self.pack_train = TablePlan(train_d, "pack", "pack_train") if train_d else None
+
+    def repack(self, everything=True):
+        """Refresh the derived bf16 operands from the fp32 master parameters (after an optimizer / EMA step)."""
+        if everything or self.pack_train is None:
+            self.pack_all.run()
+        else:
+            self.pack_train.run()
         for f in self.repack_ops:
             f()
 

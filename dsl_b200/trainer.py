@@ -120,8 +120,8 @@ class DSLEngine:
         c_s = float(torch.tensor(1 - k, dtype=torch.float32))  # fp32(1 - keep_rate), as torch's scalar promotion does
         c_t = float(torch.tensor(k, dtype=torch.float32))
         L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, s), "ema")
-        self.student.repack()
-        self.teacher.repack()
+        self.student.repack(everything=False)  # frozen stem / layer1 / BatchNorm operands never change
+        self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
 
     def _allreduce_counts(self):
         if self.world > 1:
@@ -183,6 +183,73 @@ class DSLEngine:
                 self._allreduce_grads()
                 self.graphs[2].replay()
         return self.student.losses()
+
+    def profile_kernels(self, steps=3):
+        """Instrumented EAGER pass over the same workload: CUDA events (on the launching stream) around every
+        implicit-GEMM conv / wgrad launch. Returns summed device ms and algorithmic FLOPs per step for the two
+        tensor-core kernel families, the FCOSHead tower share, the eager step time and the C-ABI launch count."""
+        from .engine import ConvPlan, WgradPlan
+        nets = (self.teacher, self.student)
+        recs = []
+
+        def wrap(op):
+            plan = getattr(op, "__self__", None)
+            if not isinstance(plan, (ConvPlan, WgradPlan)):
+                return op
+
+            def timed(_op=op, _plan=plan):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _op()
+                e1.record()
+                recs.append((_plan, e0, e1))
+
+            return timed
+
+        saved = [(n, n.fwd_ops, n.bwd_ops) for n in nets]
+        for n in nets:
+            n.fwd_ops = [wrap(o) for o in n.fwd_ops]
+            n.bwd_ops = [wrap(o) for o in n.bwd_ops]
+        try:
+            self._run_eager()  # warm
+            torch.cuda.synchronize()
+            recs.clear()
+            L.reset_launch_count()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(steps):
+                self._run_eager()
+            t1.record()
+            torch.cuda.synchronize()
+        finally:
+            for n, f, b in saved:
+                n.fwd_ops, n.bwd_ops = f, b
+        out = dict(step_ms=t0.elapsed_time(t1) / steps, launches_per_step=L.launch_count / steps)
+        fam = dict(conv_igemm=dict(ms=0.0, flops=0.0, n=0), conv_wgrad=dict(ms=0.0, flops=0.0, n=0))
+        tower = dict(ms=0.0, flops=0.0)
+        per_plan = {}
+        for idx, (plan, e0, e1) in enumerate(recs):
+            k = "conv_wgrad" if isinstance(plan, WgradPlan) else "conv_igemm"
+            ms = e0.elapsed_time(e1)
+            key = (idx % (len(recs) // steps), plan.what, k)
+            a = per_plan.setdefault(key, [0.0, plan.flops])
+            a[0] += ms / steps
+            fam[k]["ms"] += ms / steps
+            fam[k]["flops"] += plan.flops / steps
+            fam[k]["n"] += 1.0 / steps
+            if k == "conv_igemm" and plan.what.startswith("head.tower") and "grad" not in plan.what:
+                tower["ms"] += ms / steps
+                tower["flops"] += plan.flops / steps
+        out["plans"] = [dict(i=i, what=w, kind=k, us=round(1e3 * v[0], 2), gflop=round(v[1] / 1e9, 2),
+                             tflops=round(v[1] / max(v[0], 1e-9) / 1e9, 1)) for (i, w, k), v in sorted(per_plan.items())]
+        for k in fam:
+            fam[k]["n"] = int(round(fam[k]["n"]))
+        out.update(fam)
+        if tower["ms"] > 0:
+            out["head_tower"] = dict(tflops=round(tower["flops"] / (tower["ms"] * 1e-3) / 1e12, 1),
+                                     ms_per_step=round(tower["ms"], 3), flops_per_step=tower["flops"],
+                                     note="8 tower convs x 5 levels, teacher + student forward launches")
+        return out
 
     def flops_per_step(self):
         return self.teacher.flops_fwd + self.student.flops_fwd + self.student.flops_bwd

@@ -125,6 +125,8 @@ typedef struct dslb_gn_seg {
   const float* beta;   /* [C]                                                                            */
   double* red;         /* bwd only: [N][C][2] scratch, pre-zeroed (sum dy, sum dy*xhat)                  */
   float* dbias;        /* bwd only: [C], += gradient of the conv bias in front of the norm               */
+  float* mr;           /* [N][groups][4] fp32 scratch: (mean, rstd) written by the forward apply and re-used by
+                          the backward, which adds its two per-group reduction constants                       */
   int32_t N, HW;
 } dslb_gn_seg_t;
 int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream);
@@ -147,6 +149,49 @@ int dslb_unpack_wgrad(const float* dw, float* g, int O, int I, int R, int S, int
 /* frozen BatchNorm2d in eval mode folded to y = x*scale + shift (resnet.py:647-656). */
 int dslb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
                  float* shift, int C, void* stream);
+/* ---- multi-tensor versions: ONE launch for every conv of a network (the derived-operand refresh after an optimizer /
+ * EMA step, and packed-wgrad -> OIHW gradient views at the end of the backward). A plan copies its descriptor table
+ * to the device once; pointers must stay valid for the plan's lifetime. */
+typedef struct dslb_pack_desc {
+  const float* w;          /* OIHW fp32 master weight                                                          */
+  void* out;               /* packed bf16 block [taps][rows_pad][cols_pad] (mode 2: [1][rows_pad][cols_pad])    */
+  const float* bn_gamma;   /* frozen BatchNorm to fold in (all four, [O]) or NULL                               */
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  float* scale_out;        /* [O] folded BN scale / shift for the conv epilogue (written by modes 0 and 2)      */
+  float* shift_out;
+  int32_t O, I, R, S;
+  int32_t rows_pad, cols_pad;
+  int32_t row_off, col_off; /* where the real block starts inside the packed block (shared operands)            */
+  int32_t mode;            /* 0 fprop [tap][o][i]; 1 dgrad [tap][i][o], taps rotated 180 deg; 2 stem [o][(r*S+s)*I+i] */
+  int32_t fill_padding;    /* 1: rewrite the zero padding too; 0: touch only the real sub-block                 */
+  float bn_eps;
+} dslb_pack_desc_t;
+typedef struct dslb_unpack_desc {
+  const float* dw;         /* packed fp32 wgrad [R*S][rows][I]                                                  */
+  float* g;                /* OIHW fp32 gradient, overwritten: g[o][i][r][s] = dw[r*S+s][row_off+o][i] * bn scale */
+  const float* bn_gamma;   /* folded BN (chain rule through w*scale) or NULL                                     */
+  const float* bn_var;
+  int32_t O, I, R, S;
+  int32_t rows, row_off;
+  float bn_eps;
+} dslb_unpack_desc_t;
+typedef struct dslb_table_plan dslb_table_plan_t;
+int dslb_pack_plan_create(const dslb_pack_desc_t* descs_host, int n, dslb_table_plan_t** out);
+int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs_host, int n, dslb_table_plan_t** out);
+int dslb_table_plan_run(const dslb_table_plan_t* plan, void* stream);
+void dslb_table_plan_destroy(dslb_table_plan_t* plan);
+/* Epilogue constants of the fused conv_reg + conv_centerness predictor (fcos_head.py:157-166): for level l,
+ * rc_scale[l][0..3] = scales[l] * level_mult[l] (level_mult = stride in eval mode, 1 in training), rc_scale[l][4..7] = 1,
+ * rc_shift[l][j] = bias5[j] * rc_scale[l][j] with bias5 = (conv_reg.bias[0..3], conv_centerness.bias); scale_vals[l] =
+ * scales[l]. `scales` points at scales.0.scale; consecutive levels are scale_stride floats apart. */
+int dslb_fcos_regctr_affine(const float* scales, int scale_stride, const float* reg_bias, const float* ctr_bias,
+                            const float* level_mult, float* rc_scale, float* rc_shift, float* scale_vals, int nlevels,
+                            void* stream);
+/* y[n][2p][2q][:] = x[n][p][q][:], every other pixel of the [N][H][W][C] bf16 map zero: turns the data gradient of a
+ * stride-2 conv into a stride-1 tensor-core dgrad over the zero-upsampled dY (FPN P6/P7 convs, necks/fpn.py:192-201). */
+int dslb_zero_upsample2(const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream);
 /* CUDA-core data gradient of a strided conv for tiny maps (FPN P6/P7 3x3 stride-2 convs, necks/fpn.py:192-201):
  * dx[n,h,w,ci] (+)= sum dy[n,p,q,co] * wp[r*S+s][co][ci]; wp = packed fprop weight; accumulate=1 adds into dx. */
 int dslb_conv_dgrad_naive(const void* dy, const void* wp, void* dx, int N, int H, int W, int Ci, int Co, int co_pad,
