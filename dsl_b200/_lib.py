@@ -9,7 +9,7 @@ import os
 import torch  # noqa: F401  (loads libcudart.so.12 before libdslb.so so both share one runtime)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdslb.so")
+LIB_PATH = os.environ.get("DSLB_LIB") or os.path.join(_HERE, "libdslb.so")  # DSLB_LIB: A/B builds of the kernels
 
 MAX_SEGS = 10
 
@@ -148,6 +148,11 @@ _proto("dslb_clip_coef", I, VP, F, VP, VP)
 _proto("dslb_sgd_step", I, VP, VP, VP, LL, VP, VP, F, F, F, I, VP)
 _proto("dslb_fcos_point_scores", I, VP, VP, VP, LL, I, I, VP)
 _proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I, VP, VP, VP, VP, VP, I, VP)
+
+lib.dslb_nms_workspace_bytes.restype = C.c_size_t
+lib.dslb_nms_workspace_bytes.argtypes = [I, I]
+_proto("dslb_multiclass_nms", I, VP, VP, VP, VP, VP, I, I, I, F, I, VP, C.c_size_t, VP, VP, VP, VP)
+_proto("dslb_pseudo_labels", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP)
 
 GN_STAT_STRIDE = 32
 

@@ -24,10 +24,11 @@ struct PackDescDev {
   int real_cols, fill;
   int mode;
   float eps;
-  long long work_begin;  // prefix sum of taps * rows * cols8
+  long long work_begin;  // prefix sum of rows * cols8
 };
 
-// One thread = 8 consecutive packed columns (one 16-byte store).
+// One thread = 8 consecutive packed columns of one packed row, ALL filter taps (so the R*S strided fp32 reads of one
+// thread fall into the same few cache lines, and every tap plane gets one 16-byte store).
 //   mode 0 (fprop)  out[tap][row_off + o][col_off + i] = w[o][i][r][s] * sc[o]
 //   mode 1 (dgrad)  out[tap][row_off + i][col_off + o] = w[o][i][R-1-r][S-1-s] * sc[o]
 //   mode 2 (im2col) out[0][row_off + o][(r*S+s)*I + i] = w[o][i][r][s] * sc[o]      (stem: K = R*S*I in one row)
@@ -41,73 +42,78 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
     const PackDescDev& d = D[lo];
     const long long tl = t - d.work_begin;
     const int c8 = tl % d.cols8;
-    const int row = (tl / d.cols8) % d.rows;
-    const int tap = tl / ((long long)d.cols8 * d.rows);
+    const int row = tl / d.cols8;
     const int RS = d.R * d.S;
-    float v[8];
+    const int lim = d.real_cols - c8 * 8;
+    const bool vec = (d.col_off & 7) == 0 && (d.fill || lim >= 8);
+    float sc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (d.mode == 0) {
-      if (row < d.O) {
-        float sc = 1.f;
-        if (d.bn_gamma) {
-          sc = d.bn_gamma[row] / sqrtf(d.bn_var[row] + d.eps);
-          if (tap == 0 && c8 == 0) {
-            d.scale_out[row] = sc;
-            d.shift_out[row] = d.bn_beta[row] - d.bn_mean[row] * sc;
-          }
-        }
-        const float* src = d.w + ((long long)row * d.I) * RS + tap;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = c8 * 8 + e;
-          if (i < d.I) v[e] = src[(long long)i * RS] * sc;
-        }
-      }
-    } else if (d.mode == 1) {
-      if (row < d.I) {
-        const int rtap = RS - 1 - tap;  // 180-degree rotation
+    for (int e = 0; e < 8; ++e) sc[e] = 1.f;
+    bool row_real;
+    if (d.mode == 1) {
+      row_real = row < d.I;
+      if (d.bn_gamma) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int o = c8 * 8 + e;
-          if (o < d.O) {
-            const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
-            v[e] = d.w[((long long)o * d.I + row) * RS + rtap] * sc;
-          }
+          if (o < d.O) sc[e] = d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps);
         }
       }
     } else {
-      if (row < d.O) {
-        float sc = 1.f;
-        if (d.bn_gamma) {
-          sc = d.bn_gamma[row] / sqrtf(d.bn_var[row] + d.eps);
-          if (c8 == 0) {
-            d.scale_out[row] = sc;
-            d.shift_out[row] = d.bn_beta[row] - d.bn_mean[row] * sc;
-          }
-        }
+      row_real = row < d.O;
+      if (row_real && d.bn_gamma) {
+        const float s0 = d.bn_gamma[row] / sqrtf(d.bn_var[row] + d.eps);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = c8 * 8 + e;
-          if (k < RS * d.I) {
-            const int tp = k / d.I, i = k - tp * d.I;
-            v[e] = d.w[((long long)row * d.I + i) * RS + tp] * sc;
-          }
+        for (int e = 0; e < 8; ++e) sc[e] = s0;
+        if (c8 == 0) {
+          d.scale_out[row] = s0;
+          d.shift_out[row] = d.bn_beta[row] - d.bn_mean[row] * s0;
         }
       }
     }
-    __nv_bfloat162 h[4];
+    const int ntap = d.mode == 2 ? 1 : RS;
+    for (int tap = 0; tap < ntap; ++tap) {
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    __nv_bfloat16* dst = d.out + ((long long)tap * d.rows_pad + d.row_off + row) * d.cols_pad + d.col_off + c8 * 8;
-    const int lim = d.real_cols - c8 * 8;
-    if ((d.col_off & 7) == 0 && (d.fill || lim >= 8)) {
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
-    } else {  // partial / unaligned sub-block (conv_reg + conv_centerness share one packed operand): real columns only
-      const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(h);
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (row_real) {
+        if (d.mode == 0) {
+          const float* src = d.w + ((long long)row * d.I) * RS + tap;
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (e < lim) dst[e] = hv[e];
+          for (int e = 0; e < 8; ++e) {
+            const int i = c8 * 8 + e;
+            if (i < d.I) v[e] = src[(long long)i * RS] * sc[e];
+          }
+        } else if (d.mode == 1) {
+          const int rtap = RS - 1 - tap;  // 180-degree rotation
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int o = c8 * 8 + e;
+            if (o < d.O) v[e] = d.w[((long long)o * d.I + row) * RS + rtap] * sc[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = c8 * 8 + e;
+            if (k < RS * d.I) {
+              const int tp = k / d.I, i = k - tp * d.I;
+              v[e] = d.w[((long long)row * d.I + i) * RS + tp] * sc[e];
+            }
+          }
+        }
+      }
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      __nv_bfloat16* dst = d.out + ((long long)tap * d.rows_pad + d.row_off + row) * d.cols_pad + d.col_off + c8 * 8;
+      if (vec) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
+      } else {  // partial / unaligned sub-block (conv_reg + conv_centerness share one packed operand): real columns only
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(h);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < lim) dst[e] = hv[e];
+      }
     }
   }
 }
@@ -120,10 +126,11 @@ struct UnpackDescDev {
   int O, I, R, S;
   int rows, row_off;
   float eps;
-  long long work_begin;  // prefix of O*I*R*S
+  long long work_begin;  // prefix of O*I
 };
 
-// g[o][i][r][s] = dw[r*S+s][row_off + o][i] * sc[o]
+// g[o][i][r][s] = dw[r*S+s][row_off + o][i] * sc[o]. One thread = one (o, i) pair, all taps: the reads of a warp are
+// contiguous inside every tap plane and its R*S-float writes tile a contiguous span of g.
 __global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n, long long total) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = n - 1;
@@ -134,11 +141,12 @@ __global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n
     const UnpackDescDev& d = D[lo];
     const long long tl = t - d.work_begin;
     const int RS = d.R * d.S;
-    const int tap = tl % RS;
-    const int i = (tl / RS) % d.I;
-    const int o = tl / ((long long)RS * d.I);
+    const int i = tl % d.I;
+    const int o = tl / d.I;
     const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
-    d.g[tl] = d.dw[((long long)tap * d.rows + d.row_off + o) * d.I + i] * sc;
+    const float* src = d.dw + ((long long)(d.row_off + o)) * d.I + i;
+    float* dst = d.g + tl * RS;
+    for (int tap = 0; tap < RS; ++tap) dst[tap] = src[(long long)tap * d.rows * d.I] * sc;
   }
 }
 
@@ -229,8 +237,7 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
       return DSLB_EINVAL;
     }
     d.work_begin = w;
-    const int taps = (s.mode == 2) ? 1 : s.R * s.S;
-    w += (long long)taps * d.rows * d.cols8;
+    w += (long long)d.rows * d.cols8;
   }
   dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
   cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(PackDescDev) * n) : cudaErrorMemoryAllocation;
@@ -269,7 +276,7 @@ extern "C" int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs, int n, d
     d.dw = s.dw; d.g = s.g; d.bn_gamma = s.bn_gamma; d.bn_var = s.bn_var;
     d.O = s.O; d.I = s.I; d.R = s.R; d.S = s.S; d.rows = s.rows; d.row_off = s.row_off; d.eps = s.bn_eps;
     d.work_begin = w;
-    w += (long long)s.O * s.I * s.R * s.S;
+    w += (long long)s.O * s.I;
   }
   dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
   cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(UnpackDescDev) * n) : cudaErrorMemoryAllocation;

@@ -210,8 +210,15 @@ class FCOSNet:
 
     def __init__(self, B, H, W, depth=50, num_classes=80, train=True, store=None, device="cuda", seed=0,
                  loss_weight=1.0, soft_weight=0.0, center_sampling=True, radius=1.5, norm_on_bbox=True,
-                 max_boxes=1024, parity_outputs=False):
-        assert H % 32 == 0 and W % 32 == 0, "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
+                 max_boxes=1024, parity_outputs=False, parts="all", level_sizes=None, strides=STRIDES,
+                 regress_ranges=REGRESS_RANGES):
+        """parts="all": backbone + FPN + head on a (B, 3, H, W) image. parts="head": FCOSHead only, on caller-filled
+        FPN maps self.p[l] of `level_sizes` (the standalone HEADS-registry module); backward then ends at self.dp."""
+        assert parts in ("all", "head")
+        assert parts == "head" or (H % 32 == 0 and W % 32 == 0), \
+            "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
+        self.parts = parts
+        self.strides, self.regress_ranges = tuple(strides), tuple(regress_ranges)
         self.B, self.H, self.W, self.depth, self.C = B, H, W, depth, num_classes
         self.train = train
         self.dev = torch.device(device)
@@ -219,7 +226,9 @@ class FCOSNet:
         self.center_sampling, self.radius, self.norm_on_bbox = center_sampling, radius, norm_on_bbox
         self.parity_outputs = parity_outputs
         if store is None:
-            store = ParamStore(resnet_spec(depth) + fpn_spec() + head_spec(num_classes), device).init_reference(seed)
+            spec = head_spec(num_classes) if parts == "head" else \
+                resnet_spec(depth) + fpn_spec() + head_spec(num_classes)
+            store = ParamStore(spec, device).init_reference(seed)
         self.store = store
         self._arena_wants = []
         self.fwd_ops, self.bwd_ops, self.repack_ops = [], [], []
@@ -229,16 +238,22 @@ class FCOSNet:
         self.flops_bwd = 0.0
         if train:
             self.grad = torch.zeros(store.n_train, dtype=torch.float32, device=self.dev)
-        self._build_backbone()
-        self._build_fpn()
+        if parts == "all":
+            self._build_backbone()
+            self._build_fpn()
+        else:
+            self.psize = [tuple(hw) for hw in level_sizes]
+            self.p = [self.buf(B, h, w, 256) for (h, w) in self.psize]
         self.head_op_start = len(self.fwd_ops)
         self._build_head()
         if train:
             self._build_loss()
             self._alloc_arena()
             self._build_head_bwd()
-            self._build_fpn_bwd()
-            self._build_backbone_bwd()
+            if parts == "all":
+                self._build_fpn_bwd()
+                self._build_backbone_bwd()
+            self._build_finish_bwd()
         self._build_pack_plans()
         self.repack(everything=True)
 
@@ -454,7 +469,7 @@ class FCOSNet:
         self.rc_scale = torch.ones(nl, 8, dtype=torch.float32, device=self.dev)
         self.rc_shift = torch.zeros(nl, 8, dtype=torch.float32, device=self.dev)
         self.scale_vals = torch.ones(nl, dtype=torch.float32, device=self.dev)
-        self.level_mult = torch.tensor([float(s) if not self.train else 1.0 for s in STRIDES[:nl]],
+        self.level_mult = torch.tensor([float(s) if not self.train else 1.0 for s in self.strides[:nl]],
                                        dtype=torch.float32, device=self.dev)
         offs = [st.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
         self.scale_stride = offs[1] - offs[0]
@@ -517,11 +532,11 @@ class FCOSNet:
                 if self.parity_outputs:
                     a.dcls_f32 = self.dcls_f32[l].data_ptr()
                     a.dregctr_f32 = self.drc_f32[l].data_ptr()
-            a.h, a.w, a.stride = h, w, STRIDES[l]
+            a.h, a.w, a.stride = h, w, self.strides[l]
             a.ld_cls, a.ld_dcls, a.ld_dreg = self.C, 128, 64
-            a.rr_lo, a.rr_hi = float(REGRESS_RANGES[l][0]), float(REGRESS_RANGES[l][1])
+            a.rr_lo, a.rr_hi = float(self.regress_ranges[l][0]), float(self.regress_ranges[l][1])
             a.scale = 1.0
-            a.cs_radius = float(STRIDES[l] * self.radius)
+            a.cs_radius = float(self.strides[l] * self.radius)
         return arr
 
     def _build_loss(self):
@@ -796,6 +811,7 @@ class FCOSNet:
                 g = self.gc[li - 2]
                 self.plan_bwd([blk["ds"].dseg(M, g, B, h, w, hin, win, residual=g)], name + ".downsample.dgrad")
                 self.plan_bwd([blk["c1"].dseg(blk["da1"], g, B, h, w, hin, win, residual=g)], name + ".conv1.dgrad")
+    def _build_finish_bwd(self):
         # finally: every packed wgrad -> its OIHW gradient view, in ONE launch
         descs = [c.unpack_desc() for c in self.convs if c.trainable]
         descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_reg.weight"), O=4, I=256, R=3, S=3, rows=5,

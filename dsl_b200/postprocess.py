@@ -1,0 +1,103 @@
+"""Teacher-side post-processing on the device, through the C ABI (libdslb.so): per-level top-nms_pre + decode + score
+gate (FCOSHead._get_bboxes, mmdet/models/dense_heads/fcos_head.py:406-527; multiclass_nms gate,
+mmdet/core/post_processing/bbox_nms.py:34-67), class-aware NMS (bbox_nms.py:78-94) and the pseudo-label rule chain of
+UnlabelPredHook + SemiCOCODataset (mmdet/runner/hooks/unlabel_pred_hook.py:20-38,142-165; mmdet/datasets/
+semicoco.py:220-269). The reference does the last two on the host and through JSON files; here nothing leaves HBM.
+"""
+import torch
+
+from . import _lib as L
+
+
+class TeacherPost:
+    """Buffers + launches for B images whose head outputs are pixel-major fp32 level tensors:
+    cls_out[l] [B, h, w, C] and rc_out[l] [B, h, w, 8] (0-3 distances already x stride, 4 centerness logit)."""
+
+    def __init__(self, B, level_sizes, strides, num_classes, device, nms_pre=1000, score_thr=0.05, iou_thr=0.6,
+                 max_per_img=100, cand_cap=8192, max_boxes=1024):
+        self.B, self.psize, self.strides, self.C = B, list(level_sizes), tuple(strides), num_classes
+        self.dev = torch.device(device)
+        self.nms_pre, self.score_thr, self.iou_thr, self.max_per_img = nms_pre, score_thr, iou_thr, max_per_img
+        assert max_per_img <= 128
+        self.cand_cap = cand_cap
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype, device=self.dev)  # noqa: E731
+        self.pt_scores = [z(B, h * w) for (h, w) in self.psize]
+        self.cand_boxes = z(B, cand_cap, 4)
+        self.cand_scores = z(B, cand_cap)
+        self.cand_labels = z(B, cand_cap, dtype=i32)
+        self.cand_points = z(B, cand_cap, dtype=i32)
+        self.cand_counts = z(B, dtype=i32)
+        self.img_hw = z(B, 2)          # img_shape (H, W): clip range of the decoded boxes
+        self.scale_factor = torch.ones(B, 4, dtype=f32, device=self.dev)
+        self.ws_bytes = L.lib.dslb_nms_workspace_bytes(B, cand_cap)
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.dets = z(B, max_per_img, 5)
+        self.det_labels = z(B, max_per_img, dtype=i32)
+        self.det_count = z(B, dtype=i32)
+        # pseudo-label rule parameters (cfg data.unlabel_pred.infer_score_thre / eval_config.iou; semicoco default_thres)
+        self.thr_class = torch.full((num_classes,), 0.3, dtype=torch.float64, device=self.dev)
+        self.img_wh = z(B, 2)          # (width, height) of the ORIGINAL image the rescaled boxes live in
+        self.max_boxes = max_boxes
+        self.rescale = True
+
+    def set_meta(self, img_shapes, scale_factors=None, ori_shapes=None):
+        """img_shapes: [(H, W, ...)] per image (img_metas['img_shape']); scale_factors: [4 floats] per image or None."""
+        hw = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32)
+        self.img_hw.copy_(hw, non_blocking=True)
+        self.rescale = scale_factors is not None
+        if self.rescale:
+            self.scale_factor.copy_(torch.tensor([[float(v) for v in sf] for sf in scale_factors], dtype=torch.float32),
+                                    non_blocking=True)
+        if ori_shapes is None:
+            ori_shapes = img_shapes
+        self.img_wh.copy_(torch.tensor([[float(s[1]), float(s[0])] for s in ori_shapes], dtype=torch.float32),
+                          non_blocking=True)
+
+    def set_class_thresholds(self, thr):
+        """Per-class ignore thresholds (adathres.json "thres" of the reference), python floats / fp64."""
+        self.thr_class.copy_(torch.as_tensor(thr, dtype=torch.float64), non_blocking=True)
+
+    def decode(self, cls_out, rc_out):
+        """Per level: top-nms_pre points by max_c(score * centerness), decode + clip + rescale, score gate."""
+        s = L.cur_stream
+        self.cand_counts.zero_()
+        off = 0
+        for l, (h, w) in enumerate(self.psize):
+            n = h * w
+            L.check(L.lib.dslb_fcos_point_scores(L.ptr(cls_out[l]), L.ptr(rc_out[l]), L.ptr(self.pt_scores[l]),
+                                                 self.B * n, self.C, self.C, s()), "point_scores")
+            if 0 < self.nms_pre < n:
+                sel = self.pt_scores[l].topk(self.nms_pre, dim=1).indices
+                K, selp = self.nms_pre, L.ptr(sel)
+            else:
+                sel, K, selp = None, n, None
+            L.check(L.lib.dslb_fcos_decode_gate(
+                L.ptr(cls_out[l]), L.ptr(rc_out[l]), selp, self.B, K, self.C, h, w, self.strides[l], self.C,
+                L.ptr(self.img_hw), L.ptr(self.scale_factor) if self.rescale else None, float(self.score_thr), off,
+                L.ptr(self.cand_boxes), L.ptr(self.cand_scores), L.ptr(self.cand_labels), L.ptr(self.cand_points),
+                L.ptr(self.cand_counts), self.cand_cap, s()), "decode_gate")
+            off += n
+
+    def nms(self):
+        """multiclass_nms: survivors in self.dets / det_labels / det_count (score-descending, <= max_per_img)."""
+        L.check(L.lib.dslb_multiclass_nms(
+            L.ptr(self.cand_boxes), L.ptr(self.cand_scores), L.ptr(self.cand_labels), L.ptr(self.cand_points),
+            L.ptr(self.cand_counts), self.B, self.cand_cap, self.C, float(self.iou_thr), self.max_per_img,
+            L.ptr(self.ws), self.ws_bytes, L.ptr(self.dets), L.ptr(self.det_labels), L.ptr(self.det_count),
+            L.cur_stream()), "multiclass_nms")
+
+    def pseudo_labels(self, gt_boxes, gt_labels, gt_off, ig_boxes, ig_off, infer_score_thr=0.1, hook_iou=0.6,
+                      ignore_lo=0.1):
+        """Detections -> packed (pseudo GT, ignore) box lists written straight into a student's target buffers."""
+        L.check(L.lib.dslb_pseudo_labels(
+            L.ptr(self.dets), L.ptr(self.det_labels), L.ptr(self.det_count), L.ptr(self.thr_class), L.ptr(self.img_wh),
+            self.B, self.max_per_img, self.C, float(infer_score_thr), float(hook_iou), float(ignore_lo),
+            int(gt_boxes.shape[0]), L.ptr(gt_boxes), L.ptr(gt_labels), L.ptr(gt_off), L.ptr(ig_boxes), L.ptr(ig_off),
+            L.cur_stream()), "pseudo_labels")
+
+    def results(self):
+        """Host copy: [(dets (n,5) fp32, labels (n,) int64)] per image — what FCOSHead.get_bboxes returns."""
+        cnt = self.det_count.cpu().tolist()
+        dets, labels = self.dets.cpu(), self.det_labels.cpu()
+        return [(dets[b, :cnt[b]].clone(), labels[b, :cnt[b]].to(torch.int64)) for b in range(self.B)]

@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .engine import FCOSNet, STRIDES
+from .postprocess import TeacherPost
 
 
 class DSLEngine:
@@ -52,40 +53,25 @@ class DSLEngine:
     # ---------------------------------------------------------------------------------------- teacher decode
     def _build_teacher_post(self):
         t = self.teacher
-        B = t.B
-        self.cand_cap = 8192
-        self.pt_scores = [torch.zeros(B, h * w, dtype=torch.float32, device=self.dev) for (h, w) in t.psize]
-        self.cand_boxes = torch.zeros(B, self.cand_cap, 4, dtype=torch.float32, device=self.dev)
-        self.cand_scores = torch.zeros(B, self.cand_cap, dtype=torch.float32, device=self.dev)
-        self.cand_labels = torch.zeros(B, self.cand_cap, dtype=torch.int32, device=self.dev)
-        self.cand_points = torch.zeros(B, self.cand_cap, dtype=torch.int32, device=self.dev)
-        self.cand_counts = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        self.img_hw = torch.tensor([[float(self.H), float(self.W)]] * B, dtype=torch.float32, device=self.dev)
-        self.scale_factor = torch.ones(B, 4, dtype=torch.float32, device=self.dev)
+        self.post = TeacherPost(t.B, t.psize, STRIDES, t.C, self.dev, nms_pre=self.nms_pre, score_thr=self.score_thr)
+        self.post.set_meta([(self.H, self.W, 3)] * t.B, [[1.0] * 4] * t.B)
+        self.cand_counts = self.post.cand_counts
+        # detections -> pseudo GT / ignore boxes of the NEXT student batch (reference: JSON files read back by the
+        # dataloader `preload` iterations later); kept in separate buffers unless feed_pseudo_labels is set
+        mb = self.student.max_boxes
+        self.pl_gt_boxes = torch.zeros(mb, 4, dtype=torch.float32, device=self.dev)
+        self.pl_gt_labels = torch.zeros(mb, dtype=torch.int64, device=self.dev)
+        self.pl_gt_off = torch.zeros(t.B + 1, dtype=torch.int32, device=self.dev)
+        self.pl_ig_boxes = torch.zeros(mb, 4, dtype=torch.float32, device=self.dev)
+        self.pl_ig_off = torch.zeros(t.B + 1, dtype=torch.int32, device=self.dev)
 
     def teacher_decode(self):
-        """Per level: top-nms_pre points by max_c(score*centerness), decode + clip + rescale, gate on score_thr.
-        (fcos_head.py:452-527; bbox_nms.py:51-62). Results stay on the device in the cand_* buffers."""
+        """Teacher head outputs -> gated candidates -> NMS -> pseudo GT / ignore boxes, all on the device
+        (fcos_head.py:406-548; bbox_nms.py:34-94; unlabel_pred_hook.py:20-38,142-165; semicoco.py:220-269)."""
         t = self.teacher
-        s = L.cur_stream
-        self.cand_counts.zero_()
-        off = 0
-        for l, (h, w) in enumerate(t.psize):
-            n = h * w
-            L.check(L.lib.dslb_fcos_point_scores(L.ptr(t.cls_out[l]), L.ptr(t.rc_out[l]), L.ptr(self.pt_scores[l]),
-                                                 t.B * n, t.C, t.C, s()), "point_scores")
-            if 0 < self.nms_pre < n:
-                sel = self.pt_scores[l].topk(self.nms_pre, dim=1).indices
-                K = self.nms_pre
-                selp = L.ptr(sel)
-            else:
-                sel, K, selp = None, n, None
-            L.check(L.lib.dslb_fcos_decode_gate(
-                L.ptr(t.cls_out[l]), L.ptr(t.rc_out[l]), selp, t.B, K, t.C, h, w, STRIDES[l], t.C, L.ptr(self.img_hw),
-                L.ptr(self.scale_factor), float(self.score_thr), off, L.ptr(self.cand_boxes), L.ptr(self.cand_scores),
-                L.ptr(self.cand_labels), L.ptr(self.cand_points), L.ptr(self.cand_counts), self.cand_cap, s()),
-                "decode_gate")
-            off += n
+        self.post.decode(t.cls_out, t.rc_out)
+        self.post.nms()
+        self.post.pseudo_labels(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, self.pl_ig_boxes, self.pl_ig_off)
 
     # ---------------------------------------------------------------------------------------- step pieces
     def _phase_a(self):

@@ -277,6 +277,31 @@ int dslb_fcos_decode_gate(const float* cls, const float* regctr, const int64_t* 
                           int point_offset, float* out_boxes, float* out_scores, int32_t* out_labels,
                           int32_t* out_points, int32_t* counts, int cap, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Teacher post-processing on the device (the reference does this on the host: D2H, numpy, JSON files).
+ * ---------------------------------------------------------------------------------------------------- */
+/* multiclass_nms -> mmcv batched_nms (mmdet/core/post_processing/bbox_nms.py:78-94): class-aware greedy NMS with the
+ * class-offset trick (boxes + label * (max_coordinate + 1), fp32), IoU > iou_thr suppresses, survivors in descending
+ * score order, first max_det kept. Inputs are the gated candidates of dslb_fcos_decode_gate ([B][cap] slots, counts[n]
+ * valid, any order; cap a power of two <= 8192). Ties in score are broken by ascending (point * num_classes + label).
+ * dets [B][max_det][5] = (x1, y1, x2, y2, score); det_labels [B][max_det]; det_count [B]. */
+size_t dslb_nms_workspace_bytes(int B, int cap);
+int dslb_multiclass_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* points,
+                        const int32_t* counts, int B, int cap, int num_classes, float iou_thr, int max_det,
+                        void* workspace, size_t ws_bytes, float* dets, int32_t* det_labels, int32_t* det_count,
+                        void* stream);
+/* Detections -> pseudo ground truth for the student, i.e. the rule chain the reference spreads over
+ * UnlabelPredHook (mmdet/runner/hooks/unlabel_pred_hook.py:20-38 parse_det_results: score >= infer_score_thr, int()
+ * truncation, round(score, 6); :142-165 per-class nms(iou, score_threshold=0.1) over classes 0..C-2 — the last class is
+ * skipped by the reference's range(0, len(id2cat)-1)) and SemiCOCODataset._parse_ann_info (mmdet/datasets/
+ * semicoco.py:220-269: boxes without overlap with the image or thinner than 1 px dropped; ignore_lo <= score <
+ * thr_class[c] -> ignore region, every other box -> GT). Output order = the reference's (class ascending, score
+ * descending). Writes the packed box lists + offsets that dslb_fcos_targets consumes. max_det <= 128. */
+int dslb_pseudo_labels(const float* dets, const int32_t* det_labels, const int32_t* det_count, const double* thr_class,
+                       const float* img_wh, int B, int max_det, int num_classes, double infer_score_thr, float nms_iou,
+                       double ignore_lo, int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
+                       float* ig_boxes, int32_t* ig_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

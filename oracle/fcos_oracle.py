@@ -433,6 +433,47 @@ def filter_pseudo_labels(rects, scores, cls_ids, img_w, img_h, thres_by_class=No
     return gt, np.array(gl, dtype=np.int64), ig
 
 
+def hook_pseudo_labels(dets, labels, num_classes, img_w, img_h, thr_by_class, infer_score_thr=0.1, iou=0.6,
+                       default_thres=(0.1, 0.3)):
+    """Detections of one image (multiclass_nms order: score descending) -> (gt_bboxes, gt_labels, gt_bboxes_ignore):
+    runner/hooks/unlabel_pred_hook.py:20-38 (gate score >= thr, int() truncation, round(score, 6)), :55 (stable sort by
+    score, descending), :142-165 (per class in range(0, num_classes - 1) — the last class is dropped —
+    nms(iou, score_threshold=0.1) on the truncated fp32 boxes) and datasets/semicoco.py:220-269 (filter_pseudo_labels).
+    thr_by_class: sequence of per-class thresholds (fp64)."""
+    dets = np.asarray(dets, dtype=np.float32).reshape(-1, 5)
+    labels = np.asarray(labels).reshape(-1)
+    items = []
+    for c in range(num_classes):  # bbox2result groups by class, keeping the detection order inside a class
+        for d in dets[labels == c]:
+            if float(d[4]) < infer_score_thr:
+                continue
+            items.append(([int(d[0]), int(d[1]), int(d[2]), int(d[3])], round(float(d[4]), 6), c))
+    items.sort(key=lambda t: t[1], reverse=True)  # stable
+    rects, scores, cls = [], [], []
+    if items:
+        b = np.array([t[0] for t in items], dtype=np.float32)
+        s = np.array([t[1] for t in items], dtype=np.float32)
+        c = np.array([t[2] for t in items], dtype=np.float32)
+        for i in range(0, num_classes - 1):
+            sel = c == i
+            if not sel.any():
+                continue
+            bi, si = b[sel], s[sel]
+            v = si > np.float32(0.1)
+            bi, si = bi[v], si[v]
+            if len(si) == 0:
+                continue
+            order = np.argsort(-si, kind="stable")
+            bi, si = bi[order], si[order]
+            keep = nms_greedy(bi, si, iou)
+            for k in keep:
+                rects.append(bi[k].tolist())
+                scores.append(float(si[k]))
+                cls.append(i)
+    thr = {i: float(t) for i, t in enumerate(thr_by_class)}
+    return filter_pseudo_labels(rects, scores, cls, img_w, img_h, thr, default_thres)
+
+
 def adathres(scores_by_class, prev_thres=None, ranges=(0.3, 0.35), gamma1=0.05, gamma2=0.6, base=0.3):
     """runner/hooks/unlabel_pred_hook.py:295-367. scores_by_class: {class: [scores of all pseudo boxes]}.
     A box is counted if score >= 0.3 (first pass) or >= last epoch's thr_c (class absent from history => counted).

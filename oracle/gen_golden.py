@@ -246,6 +246,62 @@ def gen_misc(R):
     np.savez_compressed(os.path.join(OUT, "misc.npz"), **out)
 
 
+def gen_hook_chain(R):
+    """Detections (multiclass_nms output order) -> bbox2result -> UnlabelPredHook.save_results2file (JSON on disk) ->
+    SemiCOCODataset._parse_ann_info: the reference's whole pseudo-label rule chain, executed from its own source."""
+    import types
+    save_results2file = ref_loader.load_hook_chain()
+    C = 6
+    cats = [f"cat{i}" for i in range(C)]
+    cat2id = {c: i for i, c in enumerate(cats)}
+    id2cat = {str(i): c for i, c in enumerate(cats)}
+    glb = {"os": os, "json": json, "np": np}
+    parse_ann = _extract_method(os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/semicoco.py"),
+                                "SemiCOCODataset", "_parse_ann_info", glb)
+    out = {}
+    rng = np.random.RandomState(77)
+    Wi, Hi = 640, 480
+    ncase = 6
+    for k in range(ncase):
+        n = int(rng.randint(0, 60)) if k else 100
+        boxes = GI.demo_boxes(rng, n, Hi, Wi) + rng.rand(n, 4).astype(np.float32)
+        if n > 10:  # near-duplicates of the same class (second NMS must fire), a thin box, an outside box
+            boxes[5] = boxes[4] + np.array([0.3, 0.2, 0.4, 0.1], np.float32)
+            boxes[7] = np.array([10.2, 10.7, 10.9, 80.3], np.float32)
+            boxes[8] = np.array([700.5, 10.0, 720.0, 50.0], np.float32)
+        scores = np.sort(rng.rand(n).astype(np.float32) * 0.6)[::-1].copy()
+        labels = rng.randint(0, C, size=n).astype(np.int64)
+        if n > 10:
+            labels[5] = labels[4]
+            scores[9] = scores[8]  # tie
+        dets = torch.from_numpy(np.concatenate([boxes, scores[:, None]], 1))
+        result = R.bbox2result(dets, torch.from_numpy(labels), C)
+        with tempfile.TemporaryDirectory() as td:
+            root = os.path.join(td, "images")
+            anno = os.path.join(td, "anno")
+            save = os.path.join(td, "save")
+            os.makedirs(os.path.join(root, "sub"))
+            os.makedirs(os.path.join(anno, "sub"))
+            json.dump(dict(imageName="sub/a.jpg", targetNum=0, rects=[], tags=[], masks=[], scores=[]),
+                      open(os.path.join(anno, "sub", "a.jpg.json"), "w"))
+            save_results2file(result, os.path.join(root, "sub", "a.jpg"), Hi, Wi, "json", "ckpt", 0.1, id2cat, cat2id,
+                              root, save, "Det", anno_root_path=anno, iou=0.6, fuse=False, first_ignore=False)
+            thr_file = os.path.join(td, "thr.json")
+            thr = {"cat0": 0.33, "cat1": 0.31, "cat2": 0.35, "cat3": 0.3}
+            json.dump(dict(thres=thr), open(thr_file, "w"))
+            slf = types.SimpleNamespace(ann_path=os.path.join(save, "sub"), thres=thr_file, default_thres=[0.1, 0.3],
+                                        thres_list_by_class={}, labelmapper=dict(cat2id=cat2id))
+            ann = parse_ann(slf, dict(filename="a.jpg", width=Wi, height=Hi), None)
+        out[f"c{k}_dets"] = dets.numpy()
+        out[f"c{k}_labels"] = labels
+        out[f"c{k}_gt"] = ann["bboxes"]
+        out[f"c{k}_gt_labels"] = ann["labels"]
+        out[f"c{k}_ignore"] = ann["bboxes_ignore"]
+    out["thr"] = np.array([0.33, 0.31, 0.35, 0.3, 0.3, 0.3], dtype=np.float64)  # missing classes -> default 0.3
+    out["meta"] = np.array([ncase, C, Wi, Hi], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "hook_chain.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     R = ref_loader.load()
@@ -255,6 +311,7 @@ def main():
     gen_backbone(R)
     gen_decode(R)
     gen_misc(R)
+    gen_hook_chain(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

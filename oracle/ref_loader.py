@@ -122,3 +122,20 @@ def load_hook_functions():
     glb = {"os": os, "json": __import__("json"), "math": __import__("math")}
     exec(compile(mod, path, "exec"), glb)
     return glb["parse_det_results"], glb["adathres"]
+
+
+def load_hook_chain():
+    """save_results2file (+ gen_save_json_dict / parse_det_results / create_dir) from
+    mmdet/runner/hooks/unlabel_pred_hook.py:20-175 compiled from the reference source file, with mmcv.ops.nms answered
+    by the stub's restatement (torchvision nms: same IoU > thr rule, offset 0). Used only to generate golden vectors."""
+    import ast
+    import numpy as np
+    from oracle import mmcv_stub
+    path = os.path.join(REF_ROOT, "mmdet/runner/hooks/unlabel_pred_hook.py")
+    tree = ast.parse(open(path).read())
+    names = ("parse_det_results", "gen_save_json_dict", "create_dir", "save_results2file")
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    mod = ast.Module(body=keep, type_ignores=[])
+    glb = {"os": os, "json": __import__("json"), "np": np, "nms": mmcv_stub.nms}
+    exec(compile(mod, path, "exec"), glb)
+    return glb["save_results2file"]

@@ -422,3 +422,93 @@ def test_ema_and_sgd_kernels():
     assert abs(coef[1].item() - total.item()) / total.item() < 1e-5
     assert _rel(pd.cpu(), p_ref) < 1e-6 and _rel(bd.cpu(), b_ref) < 1e-6
     _ = C
+
+
+def test_decode_nms_matches_reference_golden():
+    """Teacher decode + score gate + class-aware NMS on the device vs the reference's FCOSHead.get_bboxes
+    (golden decode.npz, produced by the reference's own code): same survivors in the same order, labels exact."""
+    from dsl_b200.postprocess import TeacherPost
+    g = np.load(os.path.join(G, "decode.npz"))
+    B, H, W = 2, 512, 640
+    cls, box, ctr = GI.make_head_outputs(41, B, H, W, train=False, cls_mean=-6.5)
+    sizes = GI.level_sizes(H, W)
+    post = TeacherPost(B, sizes, GI.STRIDES, 80, "cuda", nms_pre=1000, score_thr=0.05, iou_thr=0.6, max_per_img=100)
+    post.set_meta([(500, 630, 3), (512, 600, 3)], [[1.25] * 4, [0.8] * 4])
+    cls_out, rc_out = [], []
+    for l, (h, w) in enumerate(sizes):
+        cls_out.append(cls[l].permute(0, 2, 3, 1).contiguous().cuda())
+        rc = torch.zeros(B, h, w, 8, device="cuda")
+        rc[..., :4] = box[l].permute(0, 2, 3, 1).cuda()
+        rc[..., 4] = ctr[l][:, 0].cuda()
+        rc_out.append(rc)
+    post.decode(cls_out, rc_out)
+    post.nms()
+    torch.cuda.synchronize()
+    assert int(post.cand_counts.max()) <= post.cand_cap
+    for b, (dets, labels) in enumerate(post.results()):
+        ref = g[f"dets{b}"]
+        print(f"image {b}: {int(post.cand_counts[b])} candidates -> {len(dets)} detections (reference {len(ref)})")
+        assert dets.shape == ref.shape
+        np.testing.assert_allclose(dets.numpy(), ref, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(labels.numpy(), g[f"labels{b}"])
+
+
+def test_multiclass_nms_dense_random_vs_oracle():
+    """NMS kernel alone on a crowded random candidate set (thousands of boxes, heavy overlap, shuffled slots)."""
+    from dsl_b200.postprocess import TeacherPost
+    from oracle import fcos_oracle as O
+    B, C = 3, 80
+    post = TeacherPost(B, [(8, 8)], (8,), C, "cuda", max_per_img=100)
+    rng = np.random.RandomState(3)
+    refs = []
+    for b in range(B):
+        n = [5000, 777, 0][b]
+        ctrs = rng.rand(n, 2) * 300
+        wh = rng.rand(n, 2) * 80 + 5
+        boxes = np.concatenate([ctrs - wh / 2, ctrs + wh / 2], 1).clip(0, None).astype(np.float32)
+        scores = rng.rand(n).astype(np.float32)
+        labels = rng.randint(0, 4, size=n).astype(np.int32)
+        points = rng.permutation(max(n, 1))[:n].astype(np.int32)
+        post.cand_boxes[b, :n] = torch.from_numpy(boxes).cuda()
+        post.cand_scores[b, :n] = torch.from_numpy(scores).cuda()
+        post.cand_labels[b, :n] = torch.from_numpy(labels).cuda()
+        post.cand_points[b, :n] = torch.from_numpy(points).cuda()
+        post.cand_counts[b] = n
+        refs.append(O.multiclass_nms(torch.from_numpy(boxes), torch.from_numpy(scores),
+                                     torch.from_numpy(labels.astype(np.int64)), 0.6, 100))
+    post.nms()
+    torch.cuda.synchronize()
+    for b, (dets, labels) in enumerate(post.results()):
+        rd, rl = refs[b]
+        assert dets.shape == tuple(rd.shape), (b, dets.shape, rd.shape)
+        assert torch.equal(dets, rd.float()) and torch.equal(labels, rl)
+
+
+def test_pseudo_label_chain_matches_reference_golden():
+    """Detections -> pseudo GT / ignore boxes on the device vs the reference's UnlabelPredHook.save_results2file +
+    SemiCOCODataset._parse_ann_info executed on the same detections (golden hook_chain.npz): bit-exact, same order."""
+    from dsl_b200.postprocess import TeacherPost
+    g = np.load(os.path.join(G, "hook_chain.npz"))
+    ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+    post = TeacherPost(ncase, [(8, 8)], (8,), C, "cuda", max_per_img=100)
+    post.set_meta([(Hi, Wi, 3)] * ncase, None)
+    post.set_class_thresholds(g["thr"])
+    for k in range(ncase):
+        d = torch.from_numpy(g[f"c{k}_dets"]).float()
+        post.dets[k, :len(d)] = d.cuda()
+        post.det_labels[k, :len(d)] = torch.from_numpy(g[f"c{k}_labels"]).int().cuda()
+        post.det_count[k] = len(d)
+    mb = 1024
+    gt_b = torch.zeros(mb, 4, device="cuda")
+    gt_l = torch.zeros(mb, dtype=torch.int64, device="cuda")
+    gt_o = torch.zeros(ncase + 1, dtype=torch.int32, device="cuda")
+    ig_b = torch.zeros(mb, 4, device="cuda")
+    ig_o = torch.zeros(ncase + 1, dtype=torch.int32, device="cuda")
+    post.pseudo_labels(gt_b, gt_l, gt_o, ig_b, ig_o, infer_score_thr=0.1, hook_iou=0.6)
+    torch.cuda.synchronize()
+    go, io = gt_o.cpu().tolist(), ig_o.cpu().tolist()
+    for k in range(ncase):
+        assert np.array_equal(gt_b[go[k]:go[k + 1]].cpu().numpy(), g[f"c{k}_gt"].reshape(-1, 4)), k
+        assert np.array_equal(gt_l[go[k]:go[k + 1]].cpu().numpy(), g[f"c{k}_gt_labels"]), k
+        assert np.array_equal(ig_b[io[k]:io[k + 1]].cpu().numpy(), g[f"c{k}_ignore"].reshape(-1, 4)), k
+    assert go[-1] > 20 and io[-1] > 5

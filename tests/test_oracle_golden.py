@@ -250,3 +250,16 @@ def test_ema_matches_reference_expression():
     new = O.ema_update(t, s, 0.99)
     for k in keys:
         np.testing.assert_allclose(new[k].numpy(), np.asarray(g["ema_new_" + k], dtype=np.float32), rtol=1e-6)
+
+
+def test_hook_pseudo_label_chain_matches_reference():
+    """Detections -> pseudo GT / ignore boxes: the oracle restatement against the reference's own
+    save_results2file + SemiCOCODataset._parse_ann_info run on the same detections (golden: hook_chain.npz)."""
+    g = load("hook_chain.npz")
+    ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+    for k in range(ncase):
+        gt, gl, ig = O.hook_pseudo_labels(g[f"c{k}_dets"], g[f"c{k}_labels"], C, Wi, Hi, g["thr"])
+        assert np.array_equal(gt, g[f"c{k}_gt"].reshape(-1, 4)), k
+        assert np.array_equal(gl, g[f"c{k}_gt_labels"]), k
+        assert np.array_equal(ig, g[f"c{k}_ignore"].reshape(-1, 4)), k
+    assert sum(len(g[f"c{k}_gt"]) for k in range(ncase)) > 20 and sum(len(g[f"c{k}_ignore"]) for k in range(ncase)) > 5
