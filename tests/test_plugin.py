@@ -1,0 +1,237 @@
+"""The drop-in boundary (dsl_b200/plugin.py): config schema, registry keys, state_dict names — on CPU; and the
+reference-style unit tests of the modules through the CUDA path — on the GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden import inputs as GI
+
+# the model dict of configs/fcos_semi/r50_caffe_mslonger_tricks_0.Xdata.py:2-62 (baseline) with the DSL head keys of
+# configs/fcos_semi/RLA_r50_..._singlestage.py:35-37 added
+MODEL_CFG = dict(
+    type="FCOS",
+    backbone=dict(type="ResNet", depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                  norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="caffe",
+                  init_cfg=dict(type="Pretrained", checkpoint="open-mmlab://detectron2/resnet50_caffe")),
+    neck=dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1,
+              add_extra_convs="on_output", num_outs=5, relu_before_extra_convs=True),
+    bbox_head=dict(type="FCOSHead", num_classes=80, in_channels=256, stacked_convs=4, feat_channels=256,
+                   strides=[8, 16, 32, 64, 128], norm_on_bbox=True, centerness_on_reg=True, dcn_on_last_conv=False,
+                   center_sampling=True, conv_bias=True, loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000,
+                   loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                   loss_bbox=dict(type="GIoULoss", loss_weight=1.0),
+                   loss_centerness=dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0)),
+    train_cfg=dict(assigner=dict(type="MaxIoUAssigner", pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0,
+                                 ignore_iof_thr=-1), allowed_border=-1, pos_weight=-1, debug=False),
+    test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5),
+                  max_per_img=100))
+
+
+def _build(cfg=MODEL_CFG):
+    from dsl_b200 import plugin
+    c = {k: v for k, v in cfg.items() if k != "type"}
+    return plugin.FCOS(**c)
+
+
+def test_plugin_builds_from_reference_config_schema():
+    m = _build()
+    sd = m.state_dict()
+    n_all = sum(p.numel() for p in m.parameters())
+    n_train = sum(p.numel() for p in m.parameters() if p.requires_grad)
+    # ResNet-50 23 508 032 + FPN 3 868 672 + head 4 920 666
+    assert n_all == 23508032 + 3868672 + 4920666
+    assert n_train == n_all - sum(p.numel() for n, p in m.named_parameters() if not p.requires_grad)
+    for k in ("backbone.conv1.weight", "backbone.layer4.2.bn3.running_var", "backbone.layer1.0.downsample.1.weight",
+              "neck.lateral_convs.0.conv.bias", "neck.fpn_convs.4.conv.weight", "bbox_head.cls_convs.3.gn.weight",
+              "bbox_head.conv_centerness.bias", "bbox_head.scales.4.scale",
+              "backbone.bn1.num_batches_tracked"):
+        assert k in sd, k
+    assert sd["backbone.layer2.0.conv2.weight"].shape == (128, 128, 3, 3)   # OIHW fp32, as the reference stores it
+    assert not dict(m.named_parameters())["backbone.layer1.0.conv1.weight"].requires_grad   # frozen_stages=1
+    assert not dict(m.named_parameters())["backbone.layer3.0.bn1.weight"].requires_grad     # frozen BatchNorm
+    assert dict(m.named_parameters())["backbone.layer2.0.conv1.weight"].requires_grad
+    # parameters are views of ONE flat buffer: an optimizer-style in-place update shows up in the store
+    p = dict(m.named_parameters())["bbox_head.conv_cls.bias"]
+    with torch.no_grad():
+        p.add_(1.0)
+    assert torch.equal(m.store["bbox_head.conv_cls.bias"], p.detach())
+
+
+def test_plugin_rejects_unsupported_options_loudly():
+    from dsl_b200 import plugin
+    bad = dict(MODEL_CFG, bbox_head=dict(MODEL_CFG["bbox_head"], dcn_on_last_conv=True))
+    with pytest.raises(NotImplementedError):
+        _build(bad)
+    bad = dict(MODEL_CFG, backbone=dict(MODEL_CFG["backbone"], style="pytorch"))
+    with pytest.raises(NotImplementedError):
+        _build(bad)
+    with pytest.raises(TypeError):
+        plugin.FCOSHead(80, 256, centerness_on_reg=True, no_such_kwarg=1)
+    m = _build()
+    with pytest.raises(RuntimeError, match="no CPU"):   # no silent CPU fallback
+        m.forward_train(torch.zeros(2, 3, 64, 64), [{}, {}], [torch.zeros(0, 4)] * 2, [torch.zeros(0).long()] * 2,
+                        [torch.zeros(0, 4)] * 2)
+
+
+def test_plugin_registers_under_reference_registry_keys():
+    """With the reference's own registry loaded (source tree + mmcv stub; build container only), importing the plugin
+    answers the keys the fcos_semi configs name, and build_detector(cfg.model) returns the B200 classes with the
+    reference's state_dict names."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    R = ref_loader.load()
+    ref_model = R.builder.build_detector(dict(MODEL_CFG, backbone=dict(MODEL_CFG["backbone"], init_cfg=None)))
+    ref_keys = {k: tuple(v.shape) for k, v in ref_model.state_dict().items()}
+    from dsl_b200 import plugin
+    keys = plugin.register(force=True)
+    try:
+        assert "DETECTORS.FCOS" in keys and "HEADS.FCOSHead" in keys
+        m = R.builder.build_detector(dict(MODEL_CFG))
+        assert isinstance(m, plugin.FCOS)
+        ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert ours == ref_keys
+        # checkpoints travel both ways
+        m.load_state_dict(ref_model.state_dict())
+        assert torch.equal(m.store["bbox_head.conv_reg.weight"], ref_model.state_dict()["bbox_head.conv_reg.weight"])
+        ref_model.load_state_dict(m.state_dict())
+    finally:   # put the reference's own classes back for the other tests
+        R.builder.DETECTORS.register_module(name="FCOS", force=True, module=R.FCOS)
+        R.builder.HEADS.register_module(name="FCOSHead", force=True, module=R.FCOSHead)
+
+
+def test_scale_invariant_input_matches_oracle():
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    rng = np.random.RandomState(0)
+    img = GI.make_tensor(rng, 2, 3, 64, 96)
+    gts, lbs, igs = GI.make_gt(3, 2, 64, 96, with_ignore=True)
+    metas = [dict(img_shape=(64, 96, 3), pad_shape=(64, 96, 3), scale_factor=np.ones(4, np.float32))] * 2
+    a = plugin.scale_invariant_input(img, gts, lbs, igs, metas)
+    b = O.scale_invariant_input(img, gts, igs)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1][-1], b[1]) and torch.equal(a[3][-1], b[2])
+    assert len(a[1]) == len(a[2]) == len(a[3]) == len(a[4]) == 3 and torch.equal(a[2][-1], lbs[-1])
+    assert a[4][-1]["img_shape"][:2] == (32, 48)
+
+
+# ------------------------------------------------------------------------------------------------------- GPU
+def _data(B, H, W, seed, dev="cuda"):
+    rng = np.random.RandomState(seed)
+    img = GI.make_tensor(rng, B, 3, H, W, scale=50.0).to(dev)
+    gts, labels, ignores = GI.make_gt(seed + 1, B, H, W, with_ignore=True)
+    metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=np.ones(4, np.float32), filename=f"{i}.jpg")
+             for i in range(B)]
+    return dict(img=img, img_metas=metas, gt_bboxes=[g.to(dev) for g in gts], gt_labels=[l.to(dev) for l in labels],
+                gt_bboxes_ignore=[i.to(dev) for i in ignores])
+
+
+@pytest.mark.gpu
+def test_plugin_train_step_backward_and_sgd():
+    """detector.train_step -> loss.backward() -> torch.optim.SGD.step(), as tools/train.py drives it: losses match the
+    fp32 oracle on the same weights (bf16 forward: 2e-2), parameter gradients arrive on the nn.Parameters, and an
+    optimizer step on them changes what the kernels compute (parameters are views of the flat store)."""
+    from oracle import fcos_oracle as O
+    from tests.test_gpu_parity import _oracle_state
+    m = _build().cuda()
+    m.train()
+    data = _data(2, 256, 320, 11)
+    out = m.train_step(data, None)
+    assert set(out) == {"loss", "log_vars", "num_samples"} and out["num_samples"] == 2
+    assert set(out["log_vars"]) == {"loss_cls", "loss_bbox", "loss_centerness", "loss"}
+    net = next(iter(m._nets.values()))
+    bb, neck, head = _oracle_state(net)
+    with torch.no_grad():
+        ps = O.fpn_forward(neck, O.resnet_forward(bb, data["img"].cpu(), 50))
+        cls, box, ctr = O.fcos_head_forward(head, ps, training=True)
+        ref = O.fcos_loss(cls, box, ctr, [g.cpu() for g in data["gt_bboxes"]], [l.cpu() for l in data["gt_labels"]],
+                          [i.cpu() for i in data["gt_bboxes_ignore"]], loss_weight=3.0)
+    for k, v in ref.items():
+        got = out["log_vars"][k]
+        print(k, got, float(v))
+        assert abs(got - float(v)) <= 2e-2 * abs(float(v)) + 1e-4
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.01, momentum=0.9)
+    opt.zero_grad()
+    out["loss"].backward()
+    named = dict(m.named_parameters())
+    g = named["bbox_head.conv_cls.weight"].grad
+    assert g is not None and g.shape == (80, 256, 3, 3) and float(g.abs().sum()) > 0
+    assert named["backbone.layer1.0.conv1.weight"].grad is None
+    o, n = m.store.offsets["bbox_head.conv_cls.weight"]
+    assert torch.equal(g.flatten(), net.grad[o:o + n])
+    before = m.store["bbox_head.conv_cls.weight"].clone()
+    opt.step()
+    assert not torch.equal(before, m.store["bbox_head.conv_cls.weight"])
+    out2 = m.train_step(data, None)
+    assert out2["log_vars"]["loss"] != out["log_vars"]["loss"]
+
+
+@pytest.mark.gpu
+def test_plugin_head_reference_unit_test_properties():
+    """The reference's own FCOSHead unit test (tests/test_models/test_dense_heads/test_fcos_head.py:7-63), restated for
+    256 input channels: empty GT => cls loss > 0 and box loss == 0; one GT => both > 0. Plus get_targets bit-exact
+    against the oracle and forward against the oracle on the same weights."""
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    s = 256
+    img_metas = [dict(img_shape=(s, s, 3), scale_factor=1, pad_shape=(s, s, 3))]
+    head = plugin.FCOSHead(num_classes=16, in_channels=256, strides=(4, 8, 16, 32, 64), centerness_on_reg=True,
+                           loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                           loss_bbox=dict(type="GIoULoss", loss_weight=1.0)).cuda()
+    head.train()
+    g = torch.Generator().manual_seed(0)
+    feat = [torch.rand(1, 256, s // f, s // f, generator=g).cuda() for f in (4, 8, 16, 32, 64)]
+    cls_scores, bbox_preds, centerness = head.forward(feat)
+    assert [tuple(c.shape) for c in cls_scores] == [(1, 16, s // f, s // f) for f in (4, 8, 16, 32, 64)]
+    # forward vs the oracle on the same weights
+    sd = {k: v.detach().cpu() for k, v in head.state_dict().items()}
+    with torch.no_grad():
+        rc, rb, rt = O.fcos_head_forward(sd, [f.cpu().bfloat16().float() for f in feat], strides=(4, 8, 16, 32, 64),
+                                         training=True)
+    for l in range(5):
+        e = (cls_scores[l].cpu() - rc[l]).abs().max().item() / rc[l].abs().max().item()
+        assert e < 1e-2, (l, e)
+    empty = head.loss(cls_scores, bbox_preds, centerness, [torch.empty((0, 4)).cuda()], [torch.LongTensor([]).cuda()],
+                      img_metas, None)
+    assert empty["loss_cls"].item() > 0 and empty["loss_bbox"].item() == 0
+    gt_b = [torch.Tensor([[23.6667, 23.8757, 238.6326, 151.8874]]).cuda()]
+    gt_l = [torch.LongTensor([2]).cuda()]
+    one = head.loss(cls_scores, bbox_preds, centerness, gt_b, gt_l, img_metas, None)
+    assert one["loss_cls"].item() > 0 and one["loss_bbox"].item() > 0 and one["loss_centerness"].item() > 0
+    # get_targets: bit-exact with the reference algorithm
+    sizes = [tuple(c.shape[-2:]) for c in cls_scores]
+    pts = head.get_points(sizes)
+    labels, targets = head.get_targets(pts, gt_b, gt_l)
+    rl, rt_ = O.get_targets(O.get_points(sizes, (4, 8, 16, 32, 64)), [b.cpu() for b in gt_b], [l.cpu() for l in gt_l],
+                            (4, 8, 16, 32, 64), ((-1, 64), (64, 128), (128, 256), (256, 512), (512, 1e8)), 16,
+                            center_sampling=False, norm_on_bbox=False)
+    for l in range(5):
+        assert torch.equal(labels[l].cpu(), rl[l]) and torch.equal(targets[l].cpu(), rt_[l])
+
+
+@pytest.mark.gpu
+def test_plugin_simple_test_and_ema_hook():
+    """simple_test returns the reference's bbox2result structure; EMAOWNHook drives the fused EMA kernel bit-exactly."""
+    import types
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    student, teacher = _build().cuda(), _build().cuda()
+    with torch.no_grad():
+        student.store.flat.add_(torch.randn_like(student.store.flat) * 1e-3)
+        teacher.store["bbox_head.conv_cls.bias"].fill_(-1.0)   # confident teacher: plenty of candidates
+    teacher._dirty()
+    teacher.eval()
+    data = _data(2, 256, 320, 5)
+    res = teacher.simple_test(data["img"], data["img_metas"], rescale=True)
+    assert len(res) == 2 and len(res[0]) == 80 and all(r.shape[1] == 5 for r in res[0])
+    assert sum(len(r) for r in res[0]) == 100    # max_per_img
+    t0 = {k: v.detach().cpu().clone() for k, v in teacher.state_dict().items() if v.dtype.is_floating_point}
+    s0 = {k: v.detach().cpu().clone() for k, v in student.state_dict().items() if v.dtype.is_floating_point}
+    hook = plugin.EMAOWNHook(interval=1, mode="iteration", ratio=0.99, start_point=0)
+    runner = types.SimpleNamespace(model=student, ema_model=teacher, iter=4, epoch=0, ema_flag=False)
+    hook.after_train_iter(runner)
+    ref = O.ema_update(t0, s0, 0.99)
+    for k in ("backbone.layer2.0.conv1.weight", "bbox_head.conv_cls.bias", "backbone.bn1.running_var"):
+        assert torch.equal(teacher.state_dict()[k].cpu(), ref[k]), k
+    assert runner.ema_flag
