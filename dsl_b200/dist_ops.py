@@ -1,0 +1,45 @@
+"""The three collectives of the data-parallel step, one process per GPU over torch.distributed:
+  1. grad mean all-reduce          (reference: DDP bucket all-reduce, mmdet/apis/train.py:88-102)
+  2. ONE packed 2-scalar all-reduce for num_pos and sum(centerness targets)
+                                   (reference: two reduce_mean calls, fcos_head.py:266,274; dist_utils.py:63-69)
+  3. packed log-var all-reduce     (reference: one all-reduce + .item() per key, detectors/base.py:201-206)
+Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(t):
+    """In place: t <- mean over ranks (what DDP leaves in .grad)."""
+    w = world_size()
+    if w > 1:
+        t.div_(w)
+        dist.all_reduce(t)
+    return t
+
+
+def allreduce_sum_(t):
+    if world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+def normalisers_from_counts(counts_sum, w):
+    """(num_pos, sum ctr-targets) summed over ranks -> the reference's normalisers: max(reduce_mean(num_pos), 1.0) and
+    max(reduce_mean(sum_ctr), 1e-6) (fcos_head.py:266,273-274). Host restatement of dslb_fcos_norm for the tests."""
+    c = counts_sum.to(torch.float64) / float(w)
+    return torch.stack([torch.clamp(c[0], min=1.0), torch.clamp(c[1], min=1e-6)]).to(torch.float32)
+
+
+def reduce_log_vars(log_vars):
+    """OrderedDict of 0-dim tensors -> OrderedDict of python floats, world-averaged with ONE all-reduce."""
+    keys = list(log_vars.keys())
+    vals = torch.stack([log_vars[k].detach().to(torch.float32) for k in keys])
+    w = world_size()
+    if w > 1:
+        vals = vals.clone()
+        dist.all_reduce(vals.div_(w))
+    return type(log_vars)(zip(keys, vals.tolist()))

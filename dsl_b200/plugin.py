@@ -329,15 +329,11 @@ class FCOS(_StoreModule):
 
     def _parse_losses(self, losses):
         """base.py:175-208, with the per-key all-reduces packed into one."""
+        from .dist_ops import reduce_log_vars
         log_vars = OrderedDict((k, v.mean()) for k, v in losses.items())
         loss = sum(v for k, v in log_vars.items() if "loss" in k)
         log_vars["loss"] = loss
-        vals = torch.stack([v.detach() for v in log_vars.values()])
-        if dist.is_available() and dist.is_initialized():
-            vals = vals.clone()
-            dist.all_reduce(vals.div_(dist.get_world_size()))
-        vals = vals.tolist()
-        return loss, OrderedDict(zip(log_vars.keys(), vals))
+        return loss, reduce_log_vars(log_vars)
 
     def train_step(self, data, optimizer):
         losses = self(**data)

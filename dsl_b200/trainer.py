@@ -15,6 +15,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import dist_ops
 from .engine import FCOSNet, STRIDES
 from .postprocess import TeacherPost
 
@@ -89,8 +90,6 @@ class DSLEngine:
         s = L.cur_stream()
         st, tt = self.student.store, self.teacher.store
         g = self.student.grad
-        if self.world > 1:
-            g.div_(self.world)  # the all-reduce below sums; DDP averages (mmdet/apis/train.py:88-96)
         self.sqnorm.zero_()
         L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
         L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm), L.ptr(self.coef), s), "clip_coef")
@@ -110,12 +109,10 @@ class DSLEngine:
         self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
 
     def _allreduce_counts(self):
-        if self.world > 1:
-            dist.all_reduce(self.student.counts)
+        dist_ops.allreduce_sum_(self.student.counts)   # packed (num_pos, sum ctr-targets): one collective
 
     def _allreduce_grads(self):
-        if self.world > 1:
-            dist.all_reduce(self.student.grad)
+        dist_ops.allreduce_mean_(self.student.grad)    # DDP semantics: mean over ranks (mmdet/apis/train.py:88-96)
 
     def _run_eager(self):
         self._phase_a()

@@ -1,0 +1,85 @@
+"""N > 1 host logic on CPU: two gloo ranks exercise the three collectives of the data-parallel step (dist_ops.py) and
+check them against what the reference's per-rank code computes (DDP mean of grads; reduce_mean of the two loss
+normalisers, mmdet/core/utils/dist_utils.py:63-69; per-key log-var averaging, mmdet/models/detectors/base.py:201-206)."""
+import os
+import socket
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dsl_b200 import dist_ops
+    from oracle import fcos_oracle as O
+    from tests.golden import inputs as GI
+    try:
+        assert dist_ops.world_size() == world
+        # 1. gradient mean (per-rank seed = seed + rank, as bench.py feeds the ranks)
+        g = torch.Generator().manual_seed(100 + rank)
+        grad = torch.randn(1000, generator=g)
+        mine = grad.clone()
+        dist_ops.allreduce_mean_(grad)
+        gathered = [torch.zeros(1000) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        assert torch.allclose(grad, torch.stack(gathered).mean(0), atol=1e-7)
+        # 2. packed normalisers: each rank runs the reference's target assignment on ITS images (oracle), the packed
+        #    sum over ranks must give the same normalisers as the reference's two reduce_mean calls
+        B, H, W = 2, 128, 160
+        gts, labels, _ = GI.make_gt(7 + rank, B, H, W, with_ignore=False)
+        sizes = GI.level_sizes(H, W)
+        pts = O.get_points(sizes, GI.STRIDES)
+        lab, tgt = O.get_targets(pts, gts, labels, GI.STRIDES, GI.REGRESS_RANGES, 80, center_sampling=True,
+                                 norm_on_bbox=True)
+        lab, tgt = torch.cat(lab), torch.cat(tgt)
+        pos = (lab >= 0) & (lab < 80)
+        num_pos = float(pos.sum())
+        sum_ctr = float(O.centerness_target(tgt[pos]).sum()) if num_pos > 0 else 0.0
+        counts = torch.tensor([num_pos, sum_ctr], dtype=torch.float64)
+        dist_ops.allreduce_sum_(counts)
+        norm = dist_ops.normalisers_from_counts(counts, world)
+        # reference: reduce_mean(tensor) = all_reduce(tensor / world) (dist_utils.py:63-69), then max(., 1.0) / max(., 1e-6)
+        a = torch.tensor(num_pos, dtype=torch.float32).div_(world)
+        b = torch.tensor(sum_ctr, dtype=torch.float32).div_(world)
+        dist.all_reduce(a)
+        dist.all_reduce(b)
+        assert abs(float(norm[0]) - max(float(a), 1.0)) <= 1e-6 * max(float(a), 1.0)
+        assert abs(float(norm[1]) - max(float(b), 1e-6)) <= 1e-6 * max(float(b), 1e-6)
+        # 3. log vars: one packed all-reduce == the reference's per-key all-reduce
+        lv = OrderedDict(loss_cls=torch.tensor(1.0 + rank), loss_bbox=torch.tensor(0.5 * (rank + 1)),
+                         loss=torch.tensor(3.0 - rank))
+        red = dist_ops.reduce_log_vars(lv)
+        for k, v in lv.items():
+            t = v.clone()
+            dist.all_reduce(t.div_(world))
+            assert abs(red[k] - t.item()) < 1e-7
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_collectives_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
