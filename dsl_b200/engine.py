@@ -232,6 +232,7 @@ class FCOSNet:
         self.store = store
         self._arena_wants = []
         self.fwd_ops, self.bwd_ops, self.repack_ops = [], [], []
+        self.bwd_meta = []
         self.extra_pack_descs = []
         self.convs = []
         self.flops_fwd = 0.0
@@ -293,8 +294,12 @@ class FCOSNet:
     def add_fwd(self, fn):
         self.fwd_ops.append(fn)
 
-    def add_bwd(self, fn):
+    def add_bwd(self, fn, side=False, tag=None, wait=None):
+        """Append a backward op. side=True: independent of the dgrad critical path (weight gradients) — may run on a
+        second stream; `tag` names its completion event, `wait` names a side op the main stream must have finished
+        before this op runs (buffer re-use), "__all__" = every side op issued so far."""
         self.bwd_ops.append(fn)
+        self.bwd_meta.append((side, tag, wait))
 
     def plan_fwd(self, segs, what):
         p = ConvPlan(segs, what)
@@ -311,7 +316,7 @@ class FCOSNet:
     def plan_wgrad(self, segs, what):
         p = WgradPlan(segs, what)
         self.flops_bwd += p.flops
-        self.add_bwd(p.run)
+        self.add_bwd(p.run, side=True, tag=what)
         return p
 
     def ew(self, fn_name, *args):
@@ -630,7 +635,9 @@ class FCOSNet:
         nl = len(self.psize)
         br_names = ("cls", "reg")
         self.dz = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
-        self.dy = {br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names}
+        # two sets, alternating between tower layers: the (side-stream) wgrad of layer i may still be reading its dY
+        # while the GroupNorm backward of layer i-1 writes the other set
+        self.dy2 = [{br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names} for _ in range(2)]
         self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]  # gradient w.r.t. the FPN outputs
 
         def zero_state():
@@ -659,6 +666,7 @@ class FCOSNet:
         self.plan_bwd(dsegs, "head.predictors.dgrad")
         # --- towers, last layer first
         for i in (3, 2, 1, 0):
+            self.dy = self.dy2[i & 1]
             gsegs = []
             for bi_, br in enumerate(br_names):
                 for l, (h, w) in enumerate(self.psize):
@@ -668,7 +676,7 @@ class FCOSNet:
                                       beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], red=self.gn_red[bi_, i, l],
                                       mr=self.gn_mr[bi_, i, l],
                                       dbias=self.grad_view(f"bbox_head.{br}_convs.{i}.conv.bias"), N=B, HW=h * w))
-            self.add_bwd(self._gn_bwd(gsegs))
+            self.add_bwd(self._gn_bwd(gsegs), wait=f"head.tower{i + 2}.wgrad" if i + 2 <= 3 else None)
             for bi_, br in enumerate(br_names):
                 # dgamma / dbeta: sum over levels and images of the per-(n,c) sums
                 red = self.gn_red[bi_, i].reshape(nl * B, 256, 2)
@@ -819,7 +827,7 @@ class FCOSNet:
         descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_centerness.weight"), O=1, I=256, R=3, S=3,
                           rows=5, row_off=4))
         self.unpack_plan = TablePlan(descs, "unpack", "unpack_wgrads")
-        self.add_bwd(self.unpack_plan.run)
+        self.add_bwd(self.unpack_plan.run, wait="__all__")
 
         def finish_head_grads():
             self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
@@ -863,9 +871,33 @@ class FCOSNet:
         for op in self.fwd_ops[self.head_op_start:]:
             op()
 
-    def backward(self):
-        for op in self.bwd_ops:
-            op()
+    def backward(self, side_stream=None):
+        """Run the backward plan. With `side_stream` the weight-gradient launches (off the dgrad critical path) go to
+        that stream, ordered by events, so they fill the SMs the small deep-layer dgrad grids leave idle."""
+        if side_stream is None:
+            for op in self.bwd_ops:
+                op()
+            return
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_bwd_events"):
+            self._bwd_events = [(torch.cuda.Event(), torch.cuda.Event()) if m[0] else None for m in self.bwd_meta]
+        done = {}
+        last = None
+        for op, (side, tag, wait), evs in zip(self.bwd_ops, self.bwd_meta, self._bwd_events):
+            if wait is not None:
+                ev = last if wait == "__all__" else done.get(wait)
+                if ev is not None:
+                    main.wait_event(ev)
+            if side:
+                ev_main, ev_side = evs
+                ev_main.record(main)
+                side_stream.wait_event(ev_main)
+                with torch.cuda.stream(side_stream):
+                    op()
+                    ev_side.record(side_stream)
+                done[tag] = last = ev_side
+            else:
+                op()
 
     def losses(self):
         """dict of the reference's loss names -> 0-dim fp32 tensors (device)."""

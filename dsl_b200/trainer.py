@@ -23,7 +23,7 @@ from .postprocess import TeacherPost
 class DSLEngine:
     def __init__(self, B, H, W, depth=50, num_classes=80, device="cuda", seed=0, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, bias_lr_mult=2.0, bias_decay_mult=0.0, max_grad_norm=35.0, ema_keep=0.99,
-                 loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05):
+                 loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05, two_streams=True):
         self.dev = torch.device(device)
         self.B, self.H, self.W = B, H, W
         self.student = FCOSNet(B, H, W, depth, num_classes, train=True, device=device, seed=seed,
@@ -50,6 +50,18 @@ class DSLEngine:
         self.nms_pre, self.score_thr = nms_pre, score_thr
         self._build_teacher_post()
         self.launches_per_step = None
+        self.two_streams = two_streams
+        self.s2 = torch.cuda.Stream()   # teacher branch
+        self.s3 = torch.cuda.Stream()   # weight gradients of the student backward
+        self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
+        # double-buffered input staging for prefetch_inputs(): H2D of batch i+1 on a copy stream under step i
+        self.copy_stream = torch.cuda.Stream()
+        self._stage = None
+        self._stage_ev, self._consumed_ev = torch.cuda.Event(), torch.cuda.Event()
+        self._consumed_ev.record()
+        self._stage_pending = False
+        self._h_gt_off = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self._h_ig_off = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
 
     # ---------------------------------------------------------------------------------------- teacher decode
     def _build_teacher_post(self):
@@ -75,18 +87,45 @@ class DSLEngine:
         self.post.pseudo_labels(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, self.pl_ig_boxes, self.pl_ig_off)
 
     # ---------------------------------------------------------------------------------------- step pieces
-    def _phase_a(self):
+    def _teacher_branch(self):
         with torch.no_grad():
             self.teacher.forward()
             self.teacher_decode()
+
+    def _fork_teacher(self):
+        """Teacher forward + post-processing on a second stream: nothing in this step's student pass consumes it (the
+        reference's pseudo labels reach the student `preload` iterations later), so it only has to be done before the
+        EMA overwrites the teacher weights. Tail waves and the small latency-bound post-processing kernels then overlap
+        with the student's launches."""
+        if not self.two_streams:
+            self._teacher_branch()
+            return
+        main = torch.cuda.current_stream()
+        self._fork_ev.record(main)
+        self.s2.wait_event(self._fork_ev)
+        with torch.cuda.stream(self.s2):
+            self._teacher_branch()
+            self._join_ev.record(self.s2)
+
+    def _join_teacher(self):
+        if self.two_streams:
+            torch.cuda.current_stream().wait_event(self._join_ev)
+
+    def _phase_a(self):
+        self._fork_teacher()
+        with torch.no_grad():
             self.student.forward()
             self.student.run_targets()
+        if self.world > 1:
+            self._join_teacher()   # each captured graph must re-join its forked stream
 
     def _phase_b(self):
         self.student.run_loss()
-        self.student.backward()
+        self.student.backward(self.s3 if self.two_streams else None)
 
     def _phase_c(self):
+        if self.world == 1:
+            self._join_teacher()
         s = L.cur_stream()
         st, tt = self.student.store, self.teacher.store
         g = self.student.grad
@@ -150,8 +189,72 @@ class DSLEngine:
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
 
+    def prefetch_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
+        """Asynchronous set_inputs(): the pinned host batch is copied H2D on a separate copy stream into staging
+        buffers (so it overlaps the step that is still running); the next step() moves it into the plan's static input
+        buffers with device-side copies before launching. Call it right after step() for the NEXT batch."""
+        st = self.student
+        if self._stage is None:
+            self._stage = dict(img_s=torch.empty_like(st.img), img_t=torch.empty_like(self.teacher.img),
+                               gt_boxes=torch.empty_like(st.gt_boxes), gt_labels=torch.empty_like(st.gt_labels),
+                               gt_off=torch.empty_like(st.gt_off), ig_boxes=torch.empty_like(st.ig_boxes),
+                               ig_off=torch.empty_like(st.ig_off))
+        sg = self._stage
+        offs, ioffs = [0], [0]
+        for b in gt_bboxes:
+            offs.append(offs[-1] + int(b.shape[0]))
+        assert offs[-1] <= st.max_boxes, "too many GT boxes for the preallocated buffer"
+        use_ignore = gt_bboxes_ignore is not None
+        if use_ignore:
+            for b in gt_bboxes_ignore:
+                ioffs.append(ioffs[-1] + int(b.shape[0]))
+            assert ioffs[-1] <= st.max_boxes
+        cs = self.copy_stream
+        cs.wait_event(self._consumed_ev)   # the previous step has moved the staging buffers into its inputs
+        with torch.cuda.stream(cs):
+            sg["img_s"].copy_(student_img, non_blocking=True)
+            if teacher_img is not None:
+                sg["img_t"].copy_(teacher_img, non_blocking=True)
+            o = 0
+            for b, l in zip(gt_bboxes, gt_labels):
+                n = int(b.shape[0])
+                if n:
+                    sg["gt_boxes"][o:o + n].copy_(b, non_blocking=True)
+                    sg["gt_labels"][o:o + n].copy_(l, non_blocking=True)
+                o += n
+            self._h_gt_off.copy_(torch.tensor(offs, dtype=torch.int32))
+            sg["gt_off"].copy_(self._h_gt_off, non_blocking=True)
+            if use_ignore:
+                o = 0
+                for b in gt_bboxes_ignore:
+                    n = int(b.shape[0])
+                    if n:
+                        sg["ig_boxes"][o:o + n].copy_(b, non_blocking=True)
+                    o += n
+                self._h_ig_off.copy_(torch.tensor(ioffs, dtype=torch.int32))
+                sg["ig_off"].copy_(self._h_ig_off, non_blocking=True)
+            self._stage_ev.record(cs)
+        self._stage_pending = True
+        self._stage_teacher = teacher_img is not None
+        assert use_ignore == st.use_ignore or self.graphs is None, "ignore boxes on/off is fixed once the graph exists"
+        st.use_ignore = use_ignore
+
+    def _consume_stage(self):
+        if not self._stage_pending:
+            return
+        st, sg = self.student, self._stage
+        torch.cuda.current_stream().wait_event(self._stage_ev)
+        st.img.copy_(sg["img_s"], non_blocking=True)
+        if self._stage_teacher:
+            self.teacher.img.copy_(sg["img_t"], non_blocking=True)
+        for k in ("gt_boxes", "gt_labels", "gt_off", "ig_boxes", "ig_off"):
+            getattr(st, k).copy_(sg[k], non_blocking=True)
+        self._consumed_ev.record()
+        self._stage_pending = False
+
     def step(self):
-        """Run one teacher+student step on the inputs last given to set_inputs()."""
+        """Run one teacher+student step on the inputs last given to set_inputs() / prefetch_inputs()."""
+        self._consume_stage()
         if not self.use_graphs:
             self._run_eager()
         else:
@@ -190,6 +293,7 @@ class DSLEngine:
             return timed
 
         saved = [(n, n.fwd_ops, n.bwd_ops) for n in nets]
+        two, self.two_streams = self.two_streams, False   # serialise the teacher branch: per-kernel times must not overlap
         for n in nets:
             n.fwd_ops = [wrap(o) for o in n.fwd_ops]
             n.bwd_ops = [wrap(o) for o in n.bwd_ops]
@@ -207,6 +311,7 @@ class DSLEngine:
         finally:
             for n, f, b in saved:
                 n.fwd_ops, n.bwd_ops = f, b
+            self.two_streams = two
         out = dict(step_ms=t0.elapsed_time(t1) / steps, launches_per_step=L.launch_count / steps)
         fam = dict(conv_igemm=dict(ms=0.0, flops=0.0, n=0), conv_wgrad=dict(ms=0.0, flops=0.0, n=0))
         tower = dict(ms=0.0, flops=0.0)
