@@ -36,6 +36,7 @@ struct alignas(128) ConvSegDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmY;  // output store map (staged epilogue only)
+  CUtensorMap tmAux;  // residual (aux_kind 1) or ReLU mask (aux_kind 2) tile load map, same geometry as tmY
   void* y;
   const void* residual;
   const void* relu_mask;
@@ -49,12 +50,15 @@ struct alignas(128) ConvSegDev {
   int out_fp32, relu_nch, cpg, groups;
   int scatter2, Hs, Ws;
   int staged;  // 1: bf16 output goes through the smem staging tile + TMA store
+  int aux_kind;  // 0: none; 1: residual, 2: ReLU mask arrive by TMA in the staging slab and are consumed in place
 };
 
 struct alignas(128) ConvParamsDev {
   ConvSegDev seg[DSLB_MAX_SEGS];
   int nseg;
   int total_tiles;
+  int nstages;  // operand pipeline depth: 4, or 3 when the staging slabs are double-buffered
+  int nbuf;     // staging slabs per epilogue warpgroup: 1, or 2 with TMA-prefetched residual / mask tiles
 };
 
 __device__ __forceinline__ int find_seg(const ConvParamsDev* P, int tile) {
@@ -73,8 +77,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel.
 // Fast path (all 16 channels real): vector loads, no per-element guards.
+// aux_kind 1 / 2: the residual / mask values of this chunk were brought in by TMA and are passed in (a0, a1).
 __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32_t (&rr)[16], float (&v)[16],
-                                              int cb, bool fullchunk, bool valid, long long row) {
+                                              int cb, bool fullchunk, bool valid, long long row, int aux_kind,
+                                              const uint4& a0, const uint4& a1) {
   const float* __restrict__ scale = sg.scale;
   const float* __restrict__ shift = sg.shift;
   const __nv_bfloat16* __restrict__ resid = reinterpret_cast<const __nv_bfloat16*>(sg.residual);
@@ -102,7 +108,14 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
         v[4 * j + 3] += t.w;
       }
     }
-    if (valid && resid) {
+    if (aux_kind == 1) {
+      const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] += bf16_lo(w[j]);
+        v[2 * j + 1] += bf16_hi(w[j]);
+      }
+    } else if (valid && resid) {
       const uint4* rp = reinterpret_cast<const uint4*>(resid + row + cb);
       const uint4 r0 = rp[0], r1 = rp[1];
       const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -120,7 +133,14 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
       for (int j = 0; j < 16; ++j)
         if (cb + j < sg.relu_nch) v[j] = fmaxf(v[j], 0.f);
     }
-    if (valid && rmask) {
+    if (aux_kind == 2) {
+      const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(bf16_lo(w[j]) > 0.f)) v[2 * j] = 0.f;
+        if (!(bf16_hi(w[j]) > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    } else if (valid && rmask) {
       const uint4* mp = reinterpret_cast<const uint4*>(rmask + row + cb);
       const uint4 m0 = mp[0], m1 = mp[1];
       const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
@@ -143,18 +163,27 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
   }
 }
 
-__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev* __restrict__ P) {
+// The whole parameter block (tile table + TMA descriptors, <= 8 KiB) travels as a __grid_constant__ kernel parameter:
+// it lives in the constant bank, so the per-tile / per-chunk reads of segment fields are constant-cache hits instead
+// of dependent global loads that every "memory"-clobbering barrier asm would force again.
+__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvParamsDev PP) {
+  const ConvParamsDev* P = &PP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Two layouts share the same budget: 4 stages + one staging slab per epilogue warpgroup (compute-bound plans), or
+  // 3 stages + two slabs per warpgroup (plans whose residual / mask tiles are prefetched by TMA into the idle slab).
+  const int nst = P->nstages, nbuf = P->nbuf;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* sOut = smem + STAGES * (A_BYTES + B_BYTES_MAX);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + OUT_BYTES);
+  uint8_t* sB = smem + nst * A_BYTES;
+  uint8_t* sOut = smem + nst * (A_BYTES + B_BYTES_MAX);
+  uint8_t* sBar = sOut + nbuf * OUT_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBar);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sStat = reinterpret_cast<float*>(sOut + OUT_BYTES + BAR_BYTES);
+  uint64_t* auxfull = tempty + 2;  // [warpgroup][slab buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 4);
+  float* sStat = reinterpret_cast<float*>(sBar + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,6 +197,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&auxfull[i], 1);
     fence_mbar_init();
   } else if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
             tma_load_im2col_4d(&sg.tmA, &full[stage], sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
                                (uint16_t)r);
             tma_load_3d(&sg.tmB, &full[stage], sB + stage * B_BYTES_MAX, kc * BK, nt * sg.bn, tap);
-            if (++stage == STAGES) {
+            if (++stage == nst) {
               stage = 0;
               phase ^= 1;
             }
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
             umma_bf16(d_tmem, ad, bd, idesc, (ki | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -256,6 +286,23 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
     const bool leader = (ew == 0 && lane == 0);  // one per warpgroup: owns that group's staging slab + TMA stores
     int it = 0;
     bool store_pending = false;       // (leader) a TMA store may still be reading the staging buffer
+    int sbuf = 0;                     // staging slab of the current round (toggles every round when nbuf == 2)
+    uint32_t aux_par0 = 0, aux_par1 = 0;
+    // (leader) TMA-load the residual / mask tile of work item (tile_n, round r0_n) into slab `buf` of this group
+    auto aux_issue = [&](int tile_n, int r0_n, int buf) {
+      if (tile_n >= total) return;
+      const ConvSegDev& s2 = P->seg[find_seg(P, tile_n)];
+      if (!s2.aux_kind) return;
+      const int cbeg2 = r0_n + eg * 64;
+      if (cbeg2 >= min(r0_n + 128, s2.bn)) return;
+      const int tl2 = tile_n - s2.tile_begin;
+      const int nt2 = tl2 / s2.m_tiles;
+      const int mt2 = tl2 - nt2 * s2.m_tiles;
+      uint64_t* bar = &auxfull[eg * 2 + buf];
+      mbar_expect_tx(bar, BM * 128);
+      tma_load_2d(&s2.tmAux, bar, sOut + (eg * nbuf + buf) * (BM * 128), nt2 * s2.bn + cbeg2, mt2 * BM);
+    };
+    if (leader && nbuf == 2) aux_issue(blockIdx.x, 0, 0);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const ConvSegDev& sg = P->seg[find_seg(P, tile)];
       const int tl = tile - sg.tile_begin;
@@ -288,23 +335,47 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
 
       for (int r0 = 0; r0 < bn; r0 += 128) {  // rounds of <=128 channels (= the staging buffer)
         const int rend = min(r0 + 128, bn);
-        if (staged) {
+        const int cbeg = r0 + eg * 64;
+        const int cend = min(cbeg + 64, rend);
+        const int aux_here = (nbuf == 2 && cbeg < rend) ? sg.aux_kind : 0;
+        uint8_t* const slab_base = sOut + (eg * nbuf + sbuf) * (BM * 128);
+        if (nbuf == 2) {
+          // Double-buffered slabs: the slab of this round was released a whole round ago (its store was drained
+          // before the previous round's hand-over barrier). The leader drains the previous store and immediately
+          // queues the NEXT work item's residual / mask tile into the other slab, one full round ahead of its use.
+          if (leader) {
+            if (store_pending) {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              store_pending = false;
+            }
+            if (r0 + 128 < bn) aux_issue(tile, r0 + 128, sbuf ^ 1);
+            else aux_issue(tile + gridDim.x, 0, sbuf ^ 1);
+          }
+          if (aux_here) {
+            mbar_wait(&auxfull[eg * 2 + sbuf], sbuf ? aux_par1 : aux_par0);
+            if (sbuf) aux_par1 ^= 1; else aux_par0 ^= 1;
+          }
+        } else if (staged) {
           if (leader && store_pending) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             store_pending = false;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");  // this group's staging slab is free
         }
-        const int cbeg = r0 + eg * 64;
-        const int cend = min(cbeg + 64, rend);
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(taddr + c0, rr);
+          uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0;
+          if (aux_here) {  // this thread's 32 bytes of the TMA-loaded tile (same swizzled slots it will overwrite)
+            const int chx = ((c0 - r0) & 63) >> 3;
+            a0 = *reinterpret_cast<const uint4*>(slab_base + et * 128 + ((chx ^ (et & 7)) << 4));
+            a1 = *reinterpret_cast<const uint4*>(slab_base + et * 128 + (((chx + 1) ^ (et & 7)) << 4));
+          }
           tmem_ld_wait();
           const int cb = nt * bn + c0;  // first global output channel of this chunk
           const bool fullchunk = (cb + 16 <= sg.cout);
           float v[16];
-          epilogue_math(sg, rr, v, cb, fullchunk, valid, row);
+          epilogue_math(sg, rr, v, cb, fullchunk, valid, row, aux_here, a0, a1);
           if (do_stats) {
             // GroupNorm partial sums of the two 8-channel halves of this chunk, reduced over the warp's 32 pixels
             // with a 6-shuffle butterfly; lanes 0/8/16/24 end up with (s1,h0) (s2,h0) (s1,h1) (s2,h1).
@@ -359,7 +430,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
           if (staged) {
             // 128B-swizzled [128 rows][64 ch] slabs, the layout the TMA store expects
             const int cl = c0 - r0;
-            uint8_t* slab = sOut + (cl >> 6) * (BM * 128) + et * 128;
+            uint8_t* slab = slab_base + et * 128;
             const int ch = (cl & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
             uint4 o0, o1;
             o0.x = pack_bf16(v[0], v[1]);
@@ -416,11 +487,12 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           asm volatile("bar.sync %0, 128;" ::"r"(3 + eg) : "memory");
           if (leader && cbeg < rend) {
-            tma_store_2d(&sg.tmY, sOut + eg * (BM * 128), nt * bn + cbeg, pix_first);
+            tma_store_2d(&sg.tmY, slab_base, nt * bn + cbeg, pix_first);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             store_pending = true;
           }
         }
+        if (nbuf == 2) sbuf ^= 1;
       }
       if (do_stats && tile_uniform) {
         asm volatile("bar.sync 5, 256;" ::: "memory");  // both warpgroups have written their sStat entries
@@ -454,7 +526,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const ConvParamsDev*
 using namespace dslb;
 
 struct dslb_conv_plan {
-  ConvParamsDev* dev = nullptr;
+  ConvParamsDev* dev = nullptr;  // HOST copy, passed by value at launch
   int total_tiles = 0;
   double flops = 0.0;
 };
@@ -478,6 +550,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   memset(h, 0, sizeof(*h));
   int tiles = 0;
   double flops = 0.0;
+  bool any_aux = false;
   for (int i = 0; i < nseg; ++i) {
     const dslb_conv_seg_t& s = segs[i];
     ConvSegDev& d = h->seg[i];
@@ -559,6 +632,20 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
         return rc;
       }
     }
+    d.aux_kind = 0;
+    if (d.staged && s.Cout % 64 == 0 && s.ldc % 8 == 0 && (s.residual || s.relu_mask)) {
+      const void* aux = s.residual ? s.residual : s.relu_mask;
+      d.aux_kind = s.residual ? 1 : 2;
+      const uint64_t ad[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};
+      const uint64_t as[1] = {(uint64_t)s.ldc * 2};
+      const uint32_t ab[2] = {64, (uint32_t)BM};
+      rc = encode_tiled_bf16(&d.tmAux, aux, 2, ad, as, ab);
+      if (rc != DSLB_OK) {
+        delete h;
+        return rc;
+      }
+      any_aux = true;
+    }
     if (s.gn_stats && !d.staged) {
       set_error("conv seg %d: gn_stats needs a bf16, non-scattered output", i);
       delete h;
@@ -568,6 +655,11 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   }
   h->nseg = nseg;
   h->total_tiles = tiles;
+  // residual / mask tiles by TMA need the second staging slab, paid for with one operand stage
+  h->nstages = any_aux ? 3 : STAGES;
+  h->nbuf = any_aux ? 2 : 1;
+  if (!any_aux)
+    for (int i = 0; i < nseg; ++i) h->seg[i].aux_kind = 0;
 
   dslb_conv_plan* plan = new (std::nothrow) dslb_conv_plan();
   if (!plan) {
@@ -575,15 +667,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     set_error("out of host memory");
     return DSLB_ENOMEM;
   }
-  cudaError_t e = cudaMalloc(&plan->dev, sizeof(ConvParamsDev));
-  if (e == cudaSuccess) e = cudaMemcpy(plan->dev, h, sizeof(ConvParamsDev), cudaMemcpyHostToDevice);
-  delete h;
-  if (e != cudaSuccess) {
-    set_error("dslb_conv_plan_create: %s", cudaGetErrorString(e));
-    if (plan->dev) cudaFree(plan->dev);
-    delete plan;
-    return DSLB_ECUDA;
-  }
+  plan->dev = h;
   plan->total_tiles = tiles;
   plan->flops = flops;
   static bool attr_set = false;
@@ -599,14 +683,14 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
 extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
   const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(plan->dev);
+  conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }
 
 extern "C" void dslb_conv_plan_destroy(dslb_conv_plan_t* plan) {
   if (!plan) return;
-  if (plan->dev) cudaFree(plan->dev);
+  delete plan->dev;
   delete plan;
 }
 
