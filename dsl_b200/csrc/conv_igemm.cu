@@ -335,11 +335,25 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
 
       for (int r0 = 0; r0 < bn; r0 += 128) {  // rounds of <=128 channels (= the staging buffer)
         const int rend = min(r0 + 128, bn);
-        const int cbeg = r0 + eg * 64;
-        const int cend = min(cbeg + 64, rend);
-        const int aux_here = (nbuf == 2 && cbeg < rend) ? sg.aux_kind : 0;
-        uint8_t* const slab_base = sOut + (eg * nbuf + sbuf) * (BM * 128);
-        if (nbuf == 2) {
+        // A round of <= 64 channels (N <= 64 layers: stem, layer1 conv1 / conv2) would leave warpgroup 1 idle: both
+        // groups then split the chunks of warpgroup 0's slab and hand it over with 256-thread barriers.
+        const bool shared = staged && (rend - r0 <= 64);
+        int cbeg = r0 + eg * 64;
+        int cend = min(cbeg + 64, rend);
+        if (shared) {
+          const int half = (((rend - r0 + 15) >> 4) + 1) >> 1;
+          cbeg = eg ? r0 + half * 16 : r0;
+          cend = eg ? rend : min(r0 + half * 16, rend);
+        }
+        const int aux_here = (nbuf == 2 && !shared && cbeg < rend) ? sg.aux_kind : 0;
+        uint8_t* const slab_base = sOut + ((shared ? 0 : eg) * nbuf + sbuf) * (BM * 128);
+        if (shared) {
+          if (leader && eg == 0 && store_pending) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            store_pending = false;
+          }
+          asm volatile("bar.sync 7, 256;" ::: "memory");  // warpgroup 0's slab is free
+        } else if (nbuf == 2) {
           // Double-buffered slabs: the slab of this round was released a whole round ago (its store was drained
           // before the previous round's hand-over barrier). The leader drains the previous store and immediately
           // queues the NEXT work item's residual / mask tile into the other slab, one full round ahead of its use.
@@ -483,7 +497,15 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (staged) {
+        if (shared) {
+          fence_proxy_async();
+          asm volatile("bar.sync 8, 256;" ::: "memory");
+          if (leader && eg == 0) {
+            tma_store_2d(&sg.tmY, slab_base, nt * bn + r0, pix_first);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
+          }
+        } else if (staged) {
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           asm volatile("bar.sync %0, 128;" ::"r"(3 + eg) : "memory");
           if (leader && cbeg < rend) {
@@ -633,7 +655,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
       }
     }
     d.aux_kind = 0;
-    if (d.staged && s.Cout % 64 == 0 && s.ldc % 8 == 0 && (s.residual || s.relu_mask)) {
+    if (d.staged && s.Cout % 64 == 0 && d.bn > 64 && s.ldc % 8 == 0 && (s.residual || s.relu_mask)) {
       const void* aux = s.residual ? s.residual : s.relu_mask;
       d.aux_kind = s.residual ? 1 : 2;
       const uint64_t ad[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};

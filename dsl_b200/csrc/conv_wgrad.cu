@@ -69,7 +69,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const WgParamsDev* __restrict__ P) {
+// parameter block by value in the constant bank (see conv_igemm.cu)
+__global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgParamsDev PP) {
+  const WgParamsDev* P = &PP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const WgParamsDev* _
 using namespace dslb;
 
 struct dslb_wgrad_plan {
-  WgParamsDev* dev = nullptr;
+  WgParamsDev* dev = nullptr;  // HOST copy, passed by value at launch
   int total_jobs = 0;
   double flops = 0.0;
 };
@@ -313,15 +315,7 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
     set_error("out of host memory");
     return DSLB_ENOMEM;
   }
-  cudaError_t e = cudaMalloc(&plan->dev, sizeof(WgParamsDev));
-  if (e == cudaSuccess) e = cudaMemcpy(plan->dev, h, sizeof(WgParamsDev), cudaMemcpyHostToDevice);
-  delete h;
-  if (e != cudaSuccess) {
-    set_error("dslb_wgrad_plan_create: %s", cudaGetErrorString(e));
-    if (plan->dev) cudaFree(plan->dev);
-    delete plan;
-    return DSLB_ECUDA;
-  }
+  plan->dev = h;
   plan->total_jobs = jobs;
   plan->flops = flops;
   static bool attr_set = false;
@@ -336,14 +330,14 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
 extern "C" int dslb_wgrad_plan_run(const dslb_wgrad_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_wgrad_plan_run: null plan");
   const int grid = plan->total_jobs < num_sms() ? plan->total_jobs : num_sms();
-  conv_wgrad_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(plan->dev);
+  conv_wgrad_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(*plan->dev);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }
 
 extern "C" void dslb_wgrad_plan_destroy(dslb_wgrad_plan_t* plan) {
   if (!plan) return;
-  if (plan->dev) cudaFree(plan->dev);
+  delete plan->dev;
   delete plan;
 }
 
