@@ -119,6 +119,7 @@ VP, I, LL, F, D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _proto("dslb_nchw_to_nhwc_bf16", I, VP, VP, I, I, I, I, I, VP)
 _proto("dslb_nhwc_to_nchw_f32", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_stem_im2col", I, VP, VP, I, I, I, VP)
+_proto("dslb_stem_conv", I, VP, VP, VP, VP, VP, VP, F, VP, VP, I, I, I, VP)
 _proto("dslb_maxpool3x3s2", I, VP, VP, I, I, I, I, VP)
 _proto("dslb_upsample_add", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_upsample_add_bwd", I, VP, VP, I, I, I, I, I, I, VP)

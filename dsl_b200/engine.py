@@ -337,23 +337,14 @@ class FCOSNet:
         self.img = self.buf(B, 3, H, W, dtype=torch.float32)  # NCHW fp32 input, as the reference feeds it
         H2, W2 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
         H4, W4 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
-        # stem: im2col (K = 7*7*3 = 147 -> 192) + tensor-core 1x1 conv with folded BN + ReLU, then max-pool
-        self.stem_cols = self.buf(B, H2, W2, 192)
+        # stem: one fused kernel (im2col tile assembled in shared memory -> tcgen05 MMA -> folded BN + ReLU), max-pool
         self.stem_out = self.buf(B, H2, W2, 64)
         self.x0 = self.buf(B, H4, W4, 64)
-        self.stem_wp = torch.zeros(1, 64, 192, dtype=BF16, device=self.dev)
-        self.stem_scale = torch.empty(64, dtype=torch.float32, device=self.dev)
-        self.stem_shift = torch.empty(64, dtype=torch.float32, device=self.dev)
-
-        self.extra_pack_descs.append((False, dict(
-            w=st["backbone.conv1.weight"], out=self.stem_wp, bn_gamma=st["backbone.bn1.weight"],
-            bn_beta=st["backbone.bn1.bias"], bn_mean=st["backbone.bn1.running_mean"],
-            bn_var=st["backbone.bn1.running_var"], bn_eps=1e-5, scale_out=self.stem_scale, shift_out=self.stem_shift,
-            O=64, I=3, R=7, S=7, rows_pad=64, cols_pad=192, mode=2, fill_padding=1)))
-        self.add_fwd(self.ew("dslb_stem_im2col", self.img, self.stem_cols, B, H, W))
-        self.plan_fwd([dict(x=self.stem_cols, w=self.stem_wp, y=self.stem_out, N=B, H=H2, W=W2, Cin=192, Cout=64,
-                            cout_pad=64, R=1, S=1, stride=1, pad=0, ldc=64, shift=self.stem_shift, relu_nch=64)],
-                      "stem")
+        self.img4 = self.buf(B, H, W, 4)   # NHWC bf16 copy of the image, channels padded 3 -> 4 (stem workspace)
+        self.add_fwd(self.ew("dslb_stem_conv", self.img, st["backbone.conv1.weight"], st["backbone.bn1.weight"],
+                             st["backbone.bn1.bias"], st["backbone.bn1.running_mean"], st["backbone.bn1.running_var"],
+                             1e-5, self.img4, self.stem_out, B, H, W))
+        self.flops_fwd += 2.0 * B * H2 * W2 * 64 * 147
         self.add_fwd(self.ew("dslb_maxpool3x3s2", self.stem_out, self.x0, B, H2, W2, 64))
 
         self.blocks = []

@@ -106,6 +106,12 @@ int dslb_nhwc_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, i
 /* im2col of the 7x7/2 pad-3 stem conv (resnet.py:597-610) from the NCHW fp32 image: out bf16 [N*Ho*Wo][192],
  * k = (r*7+s)*3 + c, zero for k >= 147; the stem then runs as a 1x1 tensor-core conv with Cin = 192. */
 int dslb_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream);
+/* The whole stem in one kernel: 7x7/2 pad-3 conv (3 -> 64) + frozen BatchNorm + ReLU (resnet.py:597-610,630-637) from
+ * the NCHW fp32 image to NHWC bf16 [N][Ho][Wo][64]. The im2col tile is assembled in shared memory and fed to
+ * tcgen05.mma; w is the fp32 OIHW master weight [64][3][7][7], bn_* the frozen BatchNorm tensors [64]. */
+size_t dslb_stem_workspace_bytes(int N, int H, int W); /* NHWC4 bf16 copy of the image: N*H*W*8 bytes, 16-byte aligned */
+int dslb_stem_conv(const float* img, const float* w, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                   const float* bn_var, float eps, void* workspace, void* out, int N, int H, int W, void* stream);
 /* nn.MaxPool2d(3, 2, 1) (resnet.py:611), NHWC bf16. */
 int dslb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
 /* FPN top-down: dst += nearest_upsample(src) (necks/fpn.py:163-172) and its backward w.r.t. src. */

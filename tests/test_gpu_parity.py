@@ -512,3 +512,53 @@ def test_pseudo_label_chain_matches_reference_golden():
         assert np.array_equal(gt_l[go[k]:go[k + 1]].cpu().numpy(), g[f"c{k}_gt_labels"]), k
         assert np.array_equal(ig_b[io[k]:io[k + 1]].cpu().numpy(), g[f"c{k}_ignore"].reshape(-1, 4)), k
     assert go[-1] > 20 and io[-1] > 5
+
+
+@pytest.mark.parametrize("depth,B,H,W", [(101, 1, 192, 256), (50, 3, 160, 288), (50, 1, 320, 224)])
+def test_other_configs_forward_loss_backward(depth, B, H, W):
+    """BASELINE.json configs[3] (R101) and configs[4] (variable shapes, odd batch = scale-invariant extra image) as
+    parity cases: forward vs the fp32 oracle, targets bit-exact, losses <= 1e-3 on the same head outputs, backward runs
+    and yields finite, non-zero gradients for every trainable tensor."""
+    from dsl_b200.engine import FCOSNet
+    from oracle import fcos_oracle as O
+    si = B % 2 == 1 and B >= 3   # scale-invariant extra image: odd batch of labeled + unlabeled + half-res copy
+    net = FCOSNet(B, H, W, depth=depth, train=True, seed=7, loss_weight=3.0, soft_weight=1.0 if si else 0.0)
+    rng = np.random.RandomState(depth + H)
+    img = GI.make_tensor(rng, B, 3, H, W, scale=50.0)
+    gts, labels, ignores = GI.make_gt(depth + W, B, H, W, with_ignore=True)
+    net.img.copy_(img)
+    if si:
+        net.si_weight = 1.0 / 1000.0   # warm-up branch of the SI-soft loss (fcos_head.py:325-327)
+    net.forward()
+    _run_loss(net, gts, labels, ignores)
+    net.backward()
+    torch.cuda.synchronize()
+    bb, neck, head = _oracle_state(net)
+    with torch.no_grad():
+        cs = O.resnet_forward(bb, img, depth)
+        ps = O.fpn_forward(neck, cs)
+    assert len(net.blocks) == sum({50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}[depth])
+    for l in range(5):
+        e = _rel(_nchw(net.p[l], 256), ps[l])
+        assert e < 4e-2, (l, e)
+    cls = [_nchw(net.cls_out[l], 80) for l in range(5)]
+    box = [_nchw(net.rc_out[l], 4) for l in range(5)]
+    ctr = [_nchw(net.rc_out[l][..., 4:5], 1) for l in range(5)]
+    kw = dict(loss_weight=3.0, return_aux=True)
+    if si:
+        kw.update(soft_weight=1.0, soft_warm_up=5000)
+    out = O.fcos_loss(cls, box, ctr, gts, labels, ignores, **kw)
+    aux = out.pop("_aux")
+    assert torch.equal(net.labels.cpu(), aux["labels"]) and torch.equal(net.bbox_targets.cpu(), aux["bbox_targets"])
+    got = net.losses()
+    assert set(got) == set(out)
+    for k, v in out.items():
+        r = abs(got[k].item() - float(v)) / (abs(float(v)) + 1e-12)
+        print(depth, (B, H, W), k, got[k].item(), float(v), f"rel {r:.2e}")
+        assert r < 1e-3
+    g = net.grad
+    assert torch.isfinite(g).all()
+    for p in net.store.spec:
+        if p.region in ("A", "B") and p.kind in ("conv", "gn_w", "gn_b", "bias"):
+            o, n = net.store.offsets[p.name]
+            assert float(g[o:o + n].abs().sum()) > 0, p.name
