@@ -573,6 +573,43 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   int tiles = 0;
   double flops = 0.0;
   bool any_aux = false;
+  // Tile width: the widest tile (<= 256) is the most MMA-efficient, but the deep layers have so few 128-pixel row
+  // tiles (layer4: 33) that 256-wide tiles leave most SMs idle. Estimate waves x per-tile cycles for caps 256 / 128 /
+  // 64 (k-iteration of a 256-wide tile ~ 542 clk, ~3000 clk of per-tile fill + epilogue) and take the cheapest.
+  int bn_cap = 256;
+  {
+    const int sms = num_sms();
+    double best = 0.0;
+    for (int cap = 256; cap >= 64; cap >>= 1) {
+      long long ntile = 0;
+      double work = 0.0;
+      bool ok = true;
+      for (int i = 0; i < nseg && ok; ++i) {
+        const dslb_conv_seg_t& s = segs[i];
+        if (s.stride < 1 || s.R < 1 || s.S < 1 || s.cout_pad < 16) { ok = false; break; }
+        const int Ho = (s.H + 2 * s.pad - s.R) / s.stride + 1, Wo = (s.W + 2 * s.pad - s.S) / s.stride + 1;
+        if (Ho <= 0 || Wo <= 0) { ok = false; break; }
+        int bn = pick_bn(s.cout_pad);
+        if (bn > cap && s.cout_pad % cap == 0) bn = cap;
+        // residual / mask tiles by TMA need > 64 channels; GroupNorm statistics were tuned for full-width tiles
+        if (cap < 128 && (s.residual || s.relu_mask)) bn = pick_bn(s.cout_pad) > 128 && s.cout_pad % 128 == 0 ? 128 : pick_bn(s.cout_pad);
+        if (s.gn_stats) bn = pick_bn(s.cout_pad);
+        const long long t = (long long)cdiv(s.N * Ho * Wo, BM) * (s.cout_pad / bn);
+        const double kit = (double)s.R * s.S * (s.Cin / 64);
+        ntile += t;
+        work += (double)t * (kit * 542.0 * bn / 256.0 + 3000.0);
+      }
+      if (!ok || ntile == 0) break;
+      const double waves = (double)((ntile + sms - 1) / sms);
+      const double cost = waves * (work / (double)ntile);
+      if (cap == 256 || cost < 0.9 * best) {
+        if (cap == 256 || cost < best) {
+          best = cost;
+          bn_cap = cap;
+        }
+      }
+    }
+  }
   for (int i = 0; i < nseg; ++i) {
     const dslb_conv_seg_t& s = segs[i];
     ConvSegDev& d = h->seg[i];
@@ -612,6 +649,11 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     d.HoWo = Ho * Wo;
     d.Wo = Wo;
     d.bn = pick_bn(s.cout_pad);
+    if (!s.gn_stats) {
+      if (d.bn > bn_cap && s.cout_pad % bn_cap == 0) d.bn = bn_cap;
+      if (bn_cap < 128 && (s.residual || s.relu_mask))
+        d.bn = pick_bn(s.cout_pad) > 128 && s.cout_pad % 128 == 0 ? 128 : pick_bn(s.cout_pad);
+    }
     d.m_tiles = cdiv(d.npix, BM);
     d.n_tiles = s.cout_pad / d.bn;
     d.tile_begin = tiles;
