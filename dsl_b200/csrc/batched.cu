@@ -40,9 +40,9 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
       if (D[mid].work_begin <= t) lo = mid; else hi = mid - 1;
     }
     const PackDescDev& d = D[lo];
-    const long long tl = t - d.work_begin;
-    const int c8 = tl % d.cols8;
-    const int row = tl / d.cols8;
+    const unsigned tl = (unsigned)(t - d.work_begin);   // per-descriptor work fits 32 bits (checked at plan creation)
+    const int c8 = (int)(tl % (unsigned)d.cols8);
+    const int row = (int)(tl / (unsigned)d.cols8);
     const int RS = d.R * d.S;
     const int lim = d.real_cols - c8 * 8;
     const bool vec = (d.col_off & 7) == 0 && (d.fill || lim >= 8);
@@ -139,13 +139,13 @@ __global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n
       if (D[mid].work_begin <= t) lo = mid; else hi = mid - 1;
     }
     const UnpackDescDev& d = D[lo];
-    const long long tl = t - d.work_begin;
+    const unsigned tl = (unsigned)(t - d.work_begin);
     const int RS = d.R * d.S;
-    const int i = tl % d.I;
-    const int o = tl / d.I;
+    const int i = (int)(tl % (unsigned)d.I);
+    const int o = (int)(tl / (unsigned)d.I);
     const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
     const float* src = d.dw + ((long long)(d.row_off + o)) * d.I + i;
-    float* dst = d.g + tl * RS;
+    float* dst = d.g + (long long)tl * RS;
     for (int tap = 0; tap < RS; ++tap) dst[tap] = src[(long long)tap * d.rows * d.I] * sc;
   }
 }

@@ -301,6 +301,37 @@ __global__ void gn_apply_relu_kernel(const __grid_constant__ GnParams P) {
   }
 }
 
+// Same, driven by the block table of the backward (block = GN_PIXB pixels of ONE image of ONE map; thread = one
+// 8-channel group x one of 8 pixel lanes): per-thread constants (mean, rstd, gamma, beta) are loaded once and the loop
+// body is two 16-byte accesses and 16 FMAs — no per-element search or integer division.
+__global__ void __launch_bounds__(256) gn_apply_relu_tab_kernel(const __grid_constant__ GnParams P,
+                                                                const int* __restrict__ blk_seg,
+                                                                const int* __restrict__ blk_pix0) {
+  const GnSeg& s = P.seg[blk_seg[blockIdx.x]];
+  const int pix0 = blk_pix0[blockIdx.x];
+  const int n = pix0 / s.HW;
+  const int pend = min(pix0 + 256, (n + 1) * s.HW);
+  const int c8 = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int G = P.C / P.cpg;
+  const float4 mr = __ldg(s.mr + n * G + (c8 * 8) / P.cpg);
+  float a_[8], b_[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float ga = __ldg(s.gamma + c8 * 8 + e) * mr.y;
+    a_[e] = ga;
+    b_[e] = __ldg(s.beta + c8 * 8 + e) - mr.x * ga;
+  }
+  const uint4* x = reinterpret_cast<const uint4*>(s.x) + c8;
+  uint4* y = reinterpret_cast<uint4*>(s.y) + c8;
+  for (int p = pix0 + pl; p < pend; p += 8) {
+    float v[8];
+    unpack8(x[(long long)p * 32], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], a_[e], b_[e]), 0.f);
+    y[(long long)p * 32] = pack8(v);
+  }
+}
+
 // Backward pass 1: per (image, channel) sums of dy and dy*xhat, dy = dz * [relu input > 0].
 // Block = 256 threads = 32 channel-octets x 8 pixel lanes (C == 256), PIXB pixels of one image per block.
 constexpr int GN_PIXB = 256;
@@ -638,6 +669,21 @@ static int fill_gn_params(GnParams& P, const dslb_gn_seg_t* segs, int nseg, int 
   }
   P.total = w;
   return DSLB_OK;
+}
+
+extern "C" int dslb_gn_apply_relu_tab(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps,
+                                      const int* blk_tab_dev, int nblocks, void* stream) {
+  DSLB_CHECK_ARG(C == 256 && blk_tab_dev && nblocks > 0, "dslb_gn_apply_relu_tab: C must be 256 and a block table given");
+  GnParams P;
+  int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
+  if (rc != DSLB_OK) return rc;
+  int maxN = 1;
+  for (int i = 0; i < nseg; ++i) maxN = segs[i].N > maxN ? segs[i].N : maxN;
+  const int nfin = nseg * maxN * groups;
+  gn_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  gn_apply_relu_tab_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
+  LAUNCH_CHECK();
 }
 
 extern "C" int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream) {

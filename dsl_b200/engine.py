@@ -508,9 +508,14 @@ class FCOSNet:
                 else:
                     setattr(a, k, v)
         n = len(gsegs)
+        nb = L.lib.dslb_gn_bwd_blocks(arr, n)
+        host = (C.c_int * (2 * nb))()
+        L.check(L.lib.dslb_gn_bwd_plan(arr, n, host), "gn_plan")
+        tab = torch.tensor(list(host), dtype=torch.int32, device=self.dev)
+        keep.append(tab)
 
-        def run(_arr=arr, _k=keep, _n=n):
-            L.check(L.lib.dslb_gn_apply_relu(_arr, _n, 256, 32, 1e-5, L.cur_stream()), "gn_apply")
+        def run(_arr=arr, _k=keep, _n=n, _tab=tab, _nb=nb):
+            L.check(L.lib.dslb_gn_apply_relu_tab(_arr, _n, 256, 32, 1e-5, L.ptr(_tab), _nb, L.cur_stream()), "gn_apply")
 
         return run
 

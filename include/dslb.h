@@ -136,6 +136,9 @@ typedef struct dslb_gn_seg {
   int32_t N, HW;
 } dslb_gn_seg_t;
 int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream);
+/* same result, faster: driven by the block table of dslb_gn_bwd_plan (C must be 256) */
+int dslb_gn_apply_relu_tab(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, const int* blk_tab_dev,
+                           int nblocks, void* stream);
 /* backward: dslb_gn_bwd_blocks -> size of the block table; dslb_gn_bwd_plan fills a HOST table of 2*blocks ints the
  * caller copies to the device once; dslb_gn_bwd runs the reduce + apply passes (C must be 256). */
 int dslb_gn_bwd_blocks(const dslb_gn_seg_t* segs, int nseg);
