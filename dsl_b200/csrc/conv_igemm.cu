@@ -59,6 +59,8 @@ struct alignas(128) ConvParamsDev {
   int total_tiles;
   int nstages;  // operand pipeline depth: 4, or 3 when the staging slabs are double-buffered
   int nbuf;     // staging slabs per epilogue warpgroup: 1, or 2 with TMA-prefetched residual / mask tiles
+  int any_aux;  // some segment brings its residual / mask tiles in by TMA (nbuf == 2); with nbuf == 2 and no aux the
+                // second slab double-buffers the TMA stores instead
 };
 
 __device__ __forceinline__ int find_seg(const ConvParamsDev* P, int tile) {
@@ -73,6 +75,34 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// two fp32 -> packed bf16x2 (lo = a, hi = b), round to nearest even; the .relu form clamps negatives to +0, which is
+// exactly relu-then-round
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// 0xffff in each half where the bf16 half of m is > 0, else 0
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t m) {
+  uint32_t r;
+  const uint32_t z = 0u;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(z));
+  return r;
 }
 
 // scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel.
@@ -287,6 +317,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     int it = 0;
     bool store_pending = false;       // (leader) a TMA store may still be reading the staging buffer
     int sbuf = 0;                     // staging slab of the current round (toggles every round when nbuf == 2)
+    const bool dbl_store = (nbuf == 2 && !P->any_aux);
     uint32_t aux_par0 = 0, aux_par1 = 0;
     // (leader) TMA-load the residual / mask tile of work item (tile_n, round r0_n) into slab `buf` of this group
     auto aux_issue = [&](int tile_n, int r0_n, int buf) {
@@ -349,10 +380,18 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         uint8_t* const slab_base = sOut + ((shared ? 0 : eg) * nbuf + sbuf) * (BM * 128);
         if (shared) {
           if (leader && eg == 0 && store_pending) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            store_pending = false;
+            if (dbl_store) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              store_pending = false;
+            }
           }
           asm volatile("bar.sync 7, 256;" ::: "memory");  // warpgroup 0's slab is free
+        } else if (dbl_store) {
+          // Two slabs, no TMA-loaded operands: the store issued a round ago (other slab) may still be in flight; only
+          // the one before it, which read THIS round's slab, has to be drained.
+          if (leader && store_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         } else if (nbuf == 2) {
           // Double-buffered slabs: the slab of this round was released a whole round ago (its store was drained
           // before the previous round's hand-over barrier). The leader drains the previous store and immediately
@@ -376,6 +415,72 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");  // this group's staging slab is free
         }
+        // Lean path for the common tile: bf16 output through the staging slab, every 16-channel chunk inside Cout,
+        // no per-channel scale, no GroupNorm statistics, ReLU on all or none of the tile's channels, residual / mask
+        // (if any) already in the slab. Shared memory is addressed through 32-bit shared-space ld / st, ReLU rides on
+        // the bf16x2 conversion and the mask is applied to the packed result, so a chunk costs ~50-80 instructions.
+        const int relu_nch = sg.relu_nch;
+        const int tile_c0 = nt * bn;
+        const bool fast = staged && !do_stats && sg.scale == nullptr && tile_c0 + bn <= sg.cout &&
+                          (relu_nch >= tile_c0 + bn || relu_nch <= tile_c0) &&
+                          (sg.residual == nullptr || aux_here == 1) && (sg.relu_mask == nullptr || aux_here == 2);
+        if (fast) {
+          const float* __restrict__ shp = sg.shift ? sg.shift + tile_c0 : nullptr;
+          const bool relu_all = relu_nch >= tile_c0 + bn;
+          const uint32_t slab_row = smem_u32(slab_base) + et * 128;
+          const uint32_t sw = et & 7;
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            uint32_t rr[16];
+            tmem_ld16(taddr + c0, rr);
+            const uint32_t chx = ((c0 - r0) & 63) >> 3;
+            const uint32_t ad0 = slab_row + ((chx ^ sw) << 4), ad1 = slab_row + (((chx + 1) ^ sw) << 4);
+            uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0;
+            if (aux_here) {
+              a0 = lds128(ad0);
+              a1 = lds128(ad1);
+            }
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            if (shp) {
+              const float4* sp = reinterpret_cast<const float4*>(shp + c0);
+              s0 = __ldg(sp);
+              s1 = __ldg(sp + 1);
+              s2 = __ldg(sp + 2);
+              s3 = __ldg(sp + 3);
+            }
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+            if (shp) {
+              v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+              v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+              v[8] += s2.x; v[9] += s2.y; v[10] += s2.z; v[11] += s2.w;
+              v[12] += s3.x; v[13] += s3.y; v[14] += s3.z; v[15] += s3.w;
+            }
+            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (aux_here == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[2 * j] += bf16_lo(aw[j]);
+                v[2 * j + 1] += bf16_hi(aw[j]);
+              }
+            }
+            uint32_t o[8];
+            if (relu_all) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = cvt_relu_bf16x2(v[2 * j], v[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = cvt_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+            if (aux_here == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] &= gt0_mask_bf16x2(aw[j]);
+            }
+            sts128(ad0, o[0], o[1], o[2], o[3]);
+            sts128(ad1, o[4], o[5], o[6], o[7]);
+          }
+        } else
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(taddr + c0, rr);
@@ -720,8 +825,16 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   h->nseg = nseg;
   h->total_tiles = tiles;
   // residual / mask tiles by TMA need the second staging slab, paid for with one operand stage
-  h->nstages = any_aux ? 3 : STAGES;
-  h->nbuf = any_aux ? 2 : 1;
+  // plans without TMA-loaded operands whose tiles are short (few k-iterations, narrow tiles: store / epilogue bound)
+  // use the same 3-stage + 2-slab layout to double-buffer their TMA stores
+  bool short_tiles = true;
+  for (int i = 0; i < nseg; ++i) {
+    const ConvSegDev& d = h->seg[i];
+    if (!d.staged || (long long)d.taps * d.cin_chunks * d.bn >= 16 * 256) short_tiles = false;
+  }
+  h->any_aux = any_aux ? 1 : 0;
+  h->nstages = (any_aux || short_tiles) ? 3 : STAGES;
+  h->nbuf = (any_aux || short_tiles) ? 2 : 1;
   if (!any_aux)
     for (int i = 0; i < nseg; ++i) h->seg[i].aux_kind = 0;
 

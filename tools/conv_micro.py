@@ -41,7 +41,7 @@ def run(name, N, H, W, Ci, Co, R, stride, pad, res, mask, affine, relu, iters=20
         seg = dict(x=x, w=w, y=y, N=N, H=H, W=W, Cin=Ci, Cout=Co, cout_pad=Co, R=R, S=R, stride=stride, pad=pad, ldc=Co,
                    relu_nch=Co if relu else 0)
         if affine:
-            seg.update(scale=scale, shift=shift)
+            seg.update(shift=shift)  # BN scale is folded into the packed weights, as in the engine
         if res:
             seg["residual"] = torch.randn(N, Ho, Wo, Co, device=dev).to(BF)
         if mask:
