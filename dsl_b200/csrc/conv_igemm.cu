@@ -23,7 +23,8 @@ namespace dslb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;       // operand stages of the widest (256-column) tiles
+constexpr int MAX_STAGES = 8;   // narrower B tiles leave room for a deeper ring
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KiB
 constexpr int BAR_BYTES = 256;
@@ -31,12 +32,17 @@ constexpr int STAT_BYTES = 4 * 32 * 2 * 4;  // GroupNorm partial sums [4 warps][
 constexpr int OUT_BYTES = 2 * BM * 128;  // output staging: two 128B-swizzled [128 px][64 ch] bf16 slabs
 constexpr int CONV_SMEM = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + OUT_BYTES + BAR_BYTES + STAT_BYTES;
 constexpr int TMEM_COLS = 512;
+constexpr int IDENT_BYTES = 64 * 128;
+static_assert(1024 + 3 * (A_BYTES + B_BYTES_MAX) + 2 * OUT_BYTES + IDENT_BYTES + BAR_BYTES + STAT_BYTES <= CONV_SMEM,
+              "3-stage layout (double slabs + identity tile) must fit the 4-stage budget");
+static_assert(CONV_SMEM <= 232448, "more than 227 KiB of shared memory");
 
 struct alignas(128) ConvSegDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmY;  // output store map (staged epilogue only)
   CUtensorMap tmAux;  // residual (aux_kind 1) or ReLU mask (aux_kind 2) tile load map, same geometry as tmY
+  CUtensorMap tmRes;  // residual tiles [128 px][64 ch] for the identity-MMA path (res_mma)
   void* y;
   const void* residual;
   const void* relu_mask;
@@ -51,14 +57,19 @@ struct alignas(128) ConvSegDev {
   int scatter2, Hs, Ws;
   int staged;  // 1: bf16 output goes through the smem staging tile + TMA store
   int aux_kind;  // 0: none; 1: residual, 2: ReLU mask arrive by TMA in the staging slab and are consumed in place
+  int res_mma;   // 1: the residual is added on the tensor core: after the K loop its [128 px][64 ch] tiles travel
+                 // through the operand ring as A tiles and are multiplied by a shared-memory 64x64 identity into
+                 // the matching 64 accumulator columns, so the epilogue never sees it (`residual` is null then)
 };
 
 struct alignas(128) ConvParamsDev {
   ConvSegDev seg[DSLB_MAX_SEGS];
   int nseg;
   int total_tiles;
-  int nstages;  // operand pipeline depth: 4, or 3 when the staging slabs are double-buffered
+  int nstages;  // operand pipeline depth: as many (A tile + widest B tile of the plan) stages as fit, <= MAX_STAGES
+  int b_stride; // bytes between the B tiles of consecutive stages (= widest tile of the plan x 128 B)
   int nbuf;     // staging slabs per epilogue warpgroup: 1, or 2 with TMA-prefetched residual / mask tiles
+  int has_ident;  // some segment uses res_mma: 8 KiB identity tile after the staging slabs (3-stage layout only)
   int any_aux;  // some segment brings its residual / mask tiles in by TMA (nbuf == 2); with nbuf == 2 and no aux the
                 // second slab double-buffers the TMA stores instead
 };
@@ -103,6 +114,98 @@ __device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t m) {
   const uint32_t z = 0u;
   asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(z));
   return r;
+}
+
+// One 16-channel chunk of the lean epilogue: fp32 accumulators (already loaded from TMEM) -> + shift -> + residual
+// (AUX 1) -> bf16x2 (ReLU fused into the conversion) -> & mask (AUX 2) -> the thread's two 16-byte slots of the
+// 128B-swizzled staging row. `aux` = this thread's 32 bytes of the TMA-loaded residual / mask tile.
+template <bool SHIFT, int AUX, bool RELU>
+__device__ __forceinline__ void fast_chunk_math(const uint32_t (&rr)[16], const float4 (&sh)[4], const uint4 (&aux)[2],
+                                                uint32_t ad0, uint32_t ad1) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  if (SHIFT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j] += sh[j].x;
+      v[4 * j + 1] += sh[j].y;
+      v[4 * j + 2] += sh[j].z;
+      v[4 * j + 3] += sh[j].w;
+    }
+  }
+  const uint32_t aw[8] = {aux[0].x, aux[0].y, aux[0].z, aux[0].w, aux[1].x, aux[1].y, aux[1].z, aux[1].w};
+  if (AUX == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[2 * j] += bf16_lo(aw[j]);
+      v[2 * j + 1] += bf16_hi(aw[j]);
+    }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = RELU ? cvt_relu_bf16x2(v[2 * j], v[2 * j + 1]) : cvt_bf16x2(v[2 * j], v[2 * j + 1]);
+  if (AUX == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] &= gt0_mask_bf16x2(aw[j]);
+  }
+  sts128(ad0, o[0], o[1], o[2], o[3]);
+  sts128(ad1, o[4], o[5], o[6], o[7]);
+}
+
+// Lean epilogue over the channel range [cbeg, cend) of one round (r0 = first channel of the round's 128-channel
+// window), two 16-channel chunks per iteration so both TMEM loads, the shift loads and the slab loads are in flight
+// before the single tcgen05.wait.
+template <bool SHIFT, int AUX, bool RELU>
+__device__ __forceinline__ void fast_chunks(uint32_t taddr, int cbeg, int cend, int r0, uint32_t slab_row, uint32_t sw,
+                                            const float* __restrict__ shp) {
+  int c0 = cbeg;
+  for (; c0 + 32 <= cend; c0 += 32) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16(taddr + c0, ra);
+    tmem_ld16(taddr + c0 + 16, rb);
+    const uint32_t chx = ((c0 - r0) & 63) >> 3;  // 16-byte slot of the chunk's first 8 channels in the 128-byte row
+    const uint32_t ad0 = slab_row + ((chx ^ sw) << 4), ad1 = slab_row + (((chx + 1) ^ sw) << 4);
+    const uint32_t ad2 = slab_row + (((chx + 2) ^ sw) << 4), ad3 = slab_row + (((chx + 3) ^ sw) << 4);
+    uint4 xa[2], xb[2];
+    if (AUX) {
+      xa[0] = lds128(ad0);
+      xa[1] = lds128(ad1);
+      xb[0] = lds128(ad2);
+      xb[1] = lds128(ad3);
+    }
+    float4 sa[4], sb[4];
+    if (SHIFT) {
+      const float4* sp = reinterpret_cast<const float4*>(shp + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sa[j] = __ldg(sp + j);
+        sb[j] = __ldg(sp + 4 + j);
+      }
+    }
+    tmem_ld_wait();
+    fast_chunk_math<SHIFT, AUX, RELU>(ra, sa, xa, ad0, ad1);
+    fast_chunk_math<SHIFT, AUX, RELU>(rb, sb, xb, ad2, ad3);
+  }
+  for (; c0 < cend; c0 += 16) {
+    uint32_t ra[16];
+    tmem_ld16(taddr + c0, ra);
+    const uint32_t chx = ((c0 - r0) & 63) >> 3;
+    const uint32_t ad0 = slab_row + ((chx ^ sw) << 4), ad1 = slab_row + (((chx + 1) ^ sw) << 4);
+    uint4 xa[2];
+    if (AUX) {
+      xa[0] = lds128(ad0);
+      xa[1] = lds128(ad1);
+    }
+    float4 sa[4];
+    if (SHIFT) {
+      const float4* sp = reinterpret_cast<const float4*>(shp + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sa[j] = __ldg(sp + j);
+    }
+    tmem_ld_wait();
+    fast_chunk_math<SHIFT, AUX, RELU>(ra, sa, xa, ad0, ad1);
+  }
 }
 
 // scale/shift -> residual -> ReLU(c < relu_nch) -> mask, on one 16-channel chunk of one output pixel.
@@ -205,11 +308,13 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   const int nst = P->nstages, nbuf = P->nbuf;
   uint8_t* sA = smem;
   uint8_t* sB = smem + nst * A_BYTES;
-  uint8_t* sOut = smem + nst * (A_BYTES + B_BYTES_MAX);
-  uint8_t* sBar = sOut + nbuf * OUT_BYTES;
+  const int b_stride = P->b_stride;
+  uint8_t* sOut = smem + nst * (A_BYTES + b_stride);
+  uint8_t* sIdent = sOut + nbuf * OUT_BYTES;  // [64][64] bf16 identity, K-major, 128B swizzle (res_mma plans)
+  uint8_t* sBar = sIdent + (P->has_ident ? IDENT_BYTES : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBar);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tfull = empty + MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* auxfull = tempty + 2;  // [warpgroup][slab buffer]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 4);
@@ -219,7 +324,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -232,6 +337,23 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   } else if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
+  }
+  if (P->has_ident) {
+    // row n holds 1.0 at k == n: 16-byte slot (n >> 3) ^ (n & 7) of the 128-byte row, element n & 7 inside it
+    for (int i = threadIdx.x; i < IDENT_BYTES / 16; i += blockDim.x) {
+      const int n = i >> 3, slot = i & 7;
+      uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      if (slot == ((n >> 3) ^ (n & 7))) {
+        const uint32_t one = 0x3f80u << ((n & 1) * 16);
+        const int w = (n & 7) >> 1;
+        if (w == 0) z.x = one;
+        else if (w == 1) z.y = one;
+        else if (w == 2) z.z = one;
+        else z.w = one;
+      }
+      reinterpret_cast<uint4*>(sIdent)[i] = z;
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -265,7 +387,18 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
             mbar_expect_tx(&full[stage], tx);
             tma_load_im2col_4d(&sg.tmA, &full[stage], sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
                                (uint16_t)r);
-            tma_load_3d(&sg.tmB, &full[stage], sB + stage * B_BYTES_MAX, kc * BK, nt * sg.bn, tap);
+            tma_load_3d(&sg.tmB, &full[stage], sB + stage * b_stride, kc * BK, nt * sg.bn, tap);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        if (sg.res_mma) {
+          for (int j = 0; j < sg.bn / 64; ++j) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], A_BYTES);
+            tma_load_2d(&sg.tmRes, &full[stage], sA + stage * A_BYTES, nt * sg.bn + 64 * j, pix0);
             if (++stage == nst) {
               stage = 0;
               phase ^= 1;
@@ -292,7 +425,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_base = smem_u32(sB + stage * B_BYTES_MAX);
+          const uint32_t b_base = smem_u32(sB + stage * b_stride);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = make_sdesc(a_base + k * 32, 16, 1024);
@@ -303,6 +436,24 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           if (++stage == nst) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if (sg.res_mma) {
+          const uint32_t idesc64 = make_idesc_bf16(BM, 64, 0, 0);
+          const uint32_t i_base = smem_u32(sIdent);
+          for (int j = 0; j < sg.bn / 64; ++j) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem + 64 * j, make_sdesc(a_base + k * 32, 16, 1024), make_sdesc(i_base + k * 32, 16, 1024),
+                        idesc64, 1);
+            umma_commit(&empty[stage]);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         umma_commit(&tfull[acc]);
@@ -429,57 +580,23 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           const bool relu_all = relu_nch >= tile_c0 + bn;
           const uint32_t slab_row = smem_u32(slab_base) + et * 128;
           const uint32_t sw = et & 7;
-          for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            uint32_t rr[16];
-            tmem_ld16(taddr + c0, rr);
-            const uint32_t chx = ((c0 - r0) & 63) >> 3;
-            const uint32_t ad0 = slab_row + ((chx ^ sw) << 4), ad1 = slab_row + (((chx + 1) ^ sw) << 4);
-            uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0;
-            if (aux_here) {
-              a0 = lds128(ad0);
-              a1 = lds128(ad1);
-            }
-            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
-            if (shp) {
-              const float4* sp = reinterpret_cast<const float4*>(shp + c0);
-              s0 = __ldg(sp);
-              s1 = __ldg(sp + 1);
-              s2 = __ldg(sp + 2);
-              s3 = __ldg(sp + 3);
-            }
-            tmem_ld_wait();
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-            if (shp) {
-              v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
-              v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-              v[8] += s2.x; v[9] += s2.y; v[10] += s2.z; v[11] += s2.w;
-              v[12] += s3.x; v[13] += s3.y; v[14] += s3.z; v[15] += s3.w;
-            }
-            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            if (aux_here == 1) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[2 * j] += bf16_lo(aw[j]);
-                v[2 * j + 1] += bf16_hi(aw[j]);
-              }
-            }
-            uint32_t o[8];
-            if (relu_all) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = cvt_relu_bf16x2(v[2 * j], v[2 * j + 1]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = cvt_bf16x2(v[2 * j], v[2 * j + 1]);
-            }
-            if (aux_here == 2) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] &= gt0_mask_bf16x2(aw[j]);
-            }
-            sts128(ad0, o[0], o[1], o[2], o[3]);
-            sts128(ad1, o[4], o[5], o[6], o[7]);
+#define DSLB_FAST(S_, A_, R_) fast_chunks<S_, A_, R_>(taddr, cbeg, cend, r0, slab_row, sw, shp)
+          const int variant = (shp ? 6 : 0) + aux_here * 2 + (relu_all ? 1 : 0);
+          switch (variant) {
+            case 0: DSLB_FAST(false, 0, false); break;
+            case 1: DSLB_FAST(false, 0, true); break;
+            case 2: DSLB_FAST(false, 1, false); break;
+            case 3: DSLB_FAST(false, 1, true); break;
+            case 4: DSLB_FAST(false, 2, false); break;
+            case 5: DSLB_FAST(false, 2, true); break;
+            case 6: DSLB_FAST(true, 0, false); break;
+            case 7: DSLB_FAST(true, 0, true); break;
+            case 8: DSLB_FAST(true, 1, false); break;
+            case 9: DSLB_FAST(true, 1, true); break;
+            case 10: DSLB_FAST(true, 2, false); break;
+            default: DSLB_FAST(true, 2, true); break;
           }
+#undef DSLB_FAST
         } else
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t rr[16];
@@ -677,7 +794,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   memset(h, 0, sizeof(*h));
   int tiles = 0;
   double flops = 0.0;
-  bool any_aux = false;
+  bool any_aux = false, any_ident = false;
   // Tile width: the widest tile (<= 256) is the most MMA-efficient, but the deep layers have so few 128-pixel row
   // tiles (layer4: 33) that 256-wide tiles leave most SMs idle. Estimate waves x per-tile cycles for caps 256 / 128 /
   // 64 (k-iteration of a 256-wide tile ~ 542 clk, ~3000 clk of per-tile fill + epilogue) and take the cheapest.
@@ -801,10 +918,24 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
         return rc;
       }
     }
+    d.res_mma = 0;
+    if (s.residual && !s.scatter2 && !s.scale && s.Cout % 64 == 0 && d.bn % 64 == 0 && s.ldc % 8 == 0) {
+      const uint64_t rd[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};
+      const uint64_t rs[1] = {(uint64_t)s.ldc * 2};
+      const uint32_t rb[2] = {64, (uint32_t)BM};
+      rc = encode_tiled_bf16(&d.tmRes, s.residual, 2, rd, rs, rb);
+      if (rc != DSLB_OK) {
+        delete h;
+        return rc;
+      }
+      d.res_mma = 1;
+      d.residual = nullptr;
+      any_ident = true;
+    }
     d.aux_kind = 0;
-    if (d.staged && s.Cout % 64 == 0 && d.bn > 64 && s.ldc % 8 == 0 && (s.residual || s.relu_mask)) {
-      const void* aux = s.residual ? s.residual : s.relu_mask;
-      d.aux_kind = s.residual ? 1 : 2;
+    if (d.staged && s.Cout % 64 == 0 && d.bn > 64 && s.ldc % 8 == 0 && (d.residual || s.relu_mask)) {
+      const void* aux = d.residual ? d.residual : s.relu_mask;
+      d.aux_kind = d.residual ? 1 : 2;
       const uint64_t ad[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};
       const uint64_t as[1] = {(uint64_t)s.ldc * 2};
       const uint32_t ab[2] = {64, (uint32_t)BM};
@@ -833,8 +964,16 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     if (!d.staged || (long long)d.taps * d.cin_chunks * d.bn >= 16 * 256) short_tiles = false;
   }
   h->any_aux = any_aux ? 1 : 0;
-  h->nstages = (any_aux || short_tiles) ? 3 : STAGES;
-  h->nbuf = (any_aux || short_tiles) ? 2 : 1;
+  h->has_ident = any_ident ? 1 : 0;
+  h->nbuf = (any_aux || any_ident || short_tiles) ? 2 : 1;
+  {
+    int bn_max = 16;
+    for (int i = 0; i < nseg; ++i) bn_max = h->seg[i].bn > bn_max ? h->seg[i].bn : bn_max;
+    h->b_stride = ((bn_max * BK * 2 + 1023) / 1024) * 1024;  // tiles stay 1024-byte aligned (128B swizzle atoms)
+    const int budget = CONV_SMEM - 1024 - h->nbuf * OUT_BYTES - (any_ident ? IDENT_BYTES : 0) - BAR_BYTES - STAT_BYTES;
+    int nst = budget / (A_BYTES + h->b_stride);
+    h->nstages = nst > MAX_STAGES ? MAX_STAGES : nst;
+  }
   if (!any_aux)
     for (int i = 0; i < nseg; ++i) h->seg[i].aux_kind = 0;
 

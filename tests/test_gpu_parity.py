@@ -312,6 +312,10 @@ def test_backward_matches_oracle_autograd(small_net):
         floor = (emu[name] - r).norm().item() / den
         bar = 3e-2 if name.startswith(("bbox_head.conv_cls", "bbox_head.conv_reg", "bbox_head.conv_centerness")) \
             else 1.5 * floor + 2e-2
+        if r.numel() == 1:
+            # a one-element gradient (bbox_head.scales.l.scale) is a single draw of the bf16 rounding noise: there is
+            # no averaging over elements, so two equally valid bf16 evaluations differ by a few floors
+            bar = 4.0 * floor + 2e-2
         checked += 1
         if err > bar:
             bad.append((name, err, floor))
