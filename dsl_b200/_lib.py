@@ -121,6 +121,7 @@ _proto("dslb_nhwc_to_nchw_f32", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_stem_im2col", I, VP, VP, I, I, I, VP)
 _proto("dslb_stem_conv", I, VP, VP, VP, VP, VP, VP, F, VP, VP, I, I, I, VP)
 _proto("dslb_maxpool3x3s2", I, VP, VP, I, I, I, I, VP)
+_proto("dslb_si_half_image", I, VP, VP, I, I, I, VP)
 _proto("dslb_upsample_add", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_upsample_add_bwd", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_relu_family", I, VP, VP, VP, LL, I, VP)
@@ -155,6 +156,8 @@ lib.dslb_nms_workspace_bytes.restype = C.c_size_t
 lib.dslb_nms_workspace_bytes.argtypes = [I, I]
 _proto("dslb_multiclass_nms", I, VP, VP, VP, VP, VP, I, I, I, F, I, VP, C.c_size_t, VP, VP, VP, VP)
 _proto("dslb_pseudo_labels", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP)
+_proto("dslb_pseudo_labels_stats", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP, VP, VP, VP)
+_proto("dslb_adathres_finalize", I, VP, VP, I, D, D, D, D, D, D, VP, VP, VP, VP)
 
 GN_STAT_STRIDE = 32
 

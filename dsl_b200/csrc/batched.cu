@@ -118,6 +118,94 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
   }
 }
 
+// Tiled variant for the regular convs (O, I multiples of 32, no padding / offsets, <= 9 taps): one block = 32 output
+// channels x 32 input channels x all taps. The OIHW rows are read fully coalesced into shared memory (scaled by the
+// folded BatchNorm), then written tap plane by tap plane as 64-byte runs: [tap][o][i] (mode 0) or, transposed and
+// rotated by 180 degrees, [RS-1-tap][i][o] (mode 1). `work_begin` counts tiles here.
+constexpr int PT = 32;
+constexpr int PT_MAX_TAPS = 9;
+__global__ void __launch_bounds__(256) pack_tiled_kernel(const PackDescDev* __restrict__ D, int n, int total_tiles) {
+  __shared__ float st[PT][PT * PT_MAX_TAPS + 1];
+  __shared__ float ssc[PT];
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (D[mid].work_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    const PackDescDev& d = D[lo];
+    const int tl = tile - (int)d.work_begin;
+    const int itiles = d.I / PT;
+    const int ot = tl / itiles, it = tl - ot * itiles;
+    const int o0 = ot * PT, i0 = it * PT;
+    const int RS = d.R * d.S;
+    const int rowlen = PT * RS;
+    if (tid < PT) {
+      float sc = 1.f;
+      if (d.bn_gamma) {
+        const int o = o0 + tid;
+        sc = d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps);
+        if (d.mode == 0 && it == 0) {
+          d.scale_out[o] = sc;
+          d.shift_out[o] = d.bn_beta[o] - d.bn_mean[o] * sc;
+        }
+      }
+      ssc[tid] = sc;
+    }
+    __syncthreads();
+    {
+      // warp wv reads rows wv, wv+8, ...: the (up to) 9 x 128-byte pieces of a row are independent loads issued back to
+      // back, so every thread keeps ~9 requests in flight (the plain strided loop was latency bound)
+      const int wv = tid >> 5, lane = tid & 31;
+#pragma unroll
+      for (int rr = 0; rr < PT / 8; ++rr) {
+        const int oo = wv + 8 * rr;
+        const float* __restrict__ src = d.w + ((long long)(o0 + oo) * d.I + i0) * RS + lane;
+        float v[PT_MAX_TAPS];
+#pragma unroll
+        for (int j = 0; j < PT_MAX_TAPS; ++j)
+          if (j < RS) v[j] = __ldg(src + 32 * j);
+        const float sc = ssc[oo];
+#pragma unroll
+        for (int j = 0; j < PT_MAX_TAPS; ++j)
+          if (j < RS) st[oo][lane + 32 * j] = v[j] * sc;
+      }
+    }
+    (void)rowlen;
+    __syncthreads();
+    // 16-byte stores: one thread = 8 consecutive packed columns of one (tap, row)
+    const int octs = RS * PT * (PT / 8);
+    if (d.mode == 0) {
+      for (int idx = tid; idx < octs; idx += 256) {
+        const int i8 = idx & 3, oo = (idx >> 2) & 31, tap = idx >> 7;
+        const float* sp = &st[oo][(8 * i8) * RS + tap];
+        uint4 o;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(sp[0], sp[RS]); o.x = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[2 * RS], sp[3 * RS]); o.y = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[4 * RS], sp[5 * RS]); o.z = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[6 * RS], sp[7 * RS]); o.w = *reinterpret_cast<uint32_t*>(&h);
+        *reinterpret_cast<uint4*>(d.out + ((long long)tap * d.rows_pad + o0 + oo) * d.cols_pad + i0 + 8 * i8) = o;
+      }
+    } else {
+      constexpr int PITCH = PT * PT_MAX_TAPS + 1;
+      for (int idx = tid; idx < octs; idx += 256) {
+        const int o8 = idx & 3, ii = (idx >> 2) & 31, tap = idx >> 7;
+        const float* sp = &st[8 * o8][ii * RS + tap];
+        uint4 o;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(sp[0], sp[PITCH]); o.x = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[2 * PITCH], sp[3 * PITCH]); o.y = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[4 * PITCH], sp[5 * PITCH]); o.z = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(sp[6 * PITCH], sp[7 * PITCH]); o.w = *reinterpret_cast<uint32_t*>(&h);
+        *reinterpret_cast<uint4*>(d.out + ((long long)(RS - 1 - tap) * d.rows_pad + i0 + ii) * d.cols_pad + o0 + 8 * o8) = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct UnpackDescDev {
   const float* dw;
   float* g;
@@ -126,7 +214,8 @@ struct UnpackDescDev {
   int O, I, R, S;
   int rows, row_off;
   float eps;
-  long long work_begin;  // prefix of O*I
+  int vec4;              // 1x1 conv with I % 4 == 0 and 16-byte aligned buffers: work items are float4s
+  long long work_begin;  // prefix of O*I (O*I/4 for vec4 descriptors)
 };
 
 // g[o][i][r][s] = dw[r*S+s][row_off + o][i] * sc[o]. One thread = one (o, i) pair, all taps: the reads of a warp are
@@ -139,14 +228,62 @@ __global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n
       if (D[mid].work_begin <= t) lo = mid; else hi = mid - 1;
     }
     const UnpackDescDev& d = D[lo];
-    const unsigned tl = (unsigned)(t - d.work_begin);
     const int RS = d.R * d.S;
+    if (d.vec4) {  // 1x1 conv, I % 4 == 0: work item = 4 consecutive input channels (a plain scaled float4 copy)
+      const unsigned tl4 = (unsigned)(t - d.work_begin);
+      const unsigned i4n = (unsigned)d.I >> 2;
+      const int o = (int)(tl4 / i4n);
+      const int i = (int)(tl4 - (unsigned)o * i4n) << 2;
+      const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
+      float4 v = __ldg(reinterpret_cast<const float4*>(d.dw + ((long long)(d.row_off + o)) * d.I + i));
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      *reinterpret_cast<float4*>(d.g + (long long)o * d.I + i) = v;
+      continue;
+    }
+    const unsigned tl = (unsigned)(t - d.work_begin);
     const int i = (int)(tl % (unsigned)d.I);
     const int o = (int)(tl / (unsigned)d.I);
     const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
     const float* src = d.dw + ((long long)(d.row_off + o)) * d.I + i;
     float* dst = d.g + (long long)tl * RS;
     for (int tap = 0; tap < RS; ++tap) dst[tap] = src[(long long)tap * d.rows * d.I] * sc;
+  }
+}
+
+// Coalesced variant: one work item = one output channel x 256 consecutive input channels. The 256 x RS values are
+// gathered tap plane by tap plane (contiguous reads) into shared memory and leave as one contiguous run of g.
+// `work_begin` counts (o, i-chunk) items here; serves every descriptor with 1 < RS <= 9.
+__global__ void __launch_bounds__(256) unpack_tiled_kernel(const UnpackDescDev* __restrict__ D, int n, long long total) {
+  __shared__ float st[256 * 9];
+  const int tid = threadIdx.x;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (D[mid].work_begin <= item) lo = mid; else hi = mid - 1;
+    }
+    const UnpackDescDev& d = D[lo];
+    const int tl = (int)(item - d.work_begin);
+    const int chunks = (d.I + 255) >> 8;
+    const int o = tl / chunks, i0 = (tl - o * chunks) << 8;
+    const int ni = min(256, d.I - i0);
+    const int RS = d.R * d.S;
+    const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
+    if (tid < ni) {
+      const float* __restrict__ src = d.dw + ((long long)(d.row_off + o)) * d.I + i0 + tid;
+      const long long plane = (long long)d.rows * d.I;
+      float v[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        if (tap < RS) v[tap] = __ldg(src + tap * plane);   // independent loads, all in flight together
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        if (tap < RS) st[tid * RS + tap] = v[tap] * sc;
+    }
+    __syncthreads();
+    float* dst = d.g + ((long long)o * d.I + i0) * RS;
+    for (int idx = tid; idx < ni * RS; idx += 256) dst[idx] = st[idx];
+    __syncthreads();
   }
 }
 
@@ -191,6 +328,9 @@ struct dslb_table_plan {
   int n = 0;
   long long total = 0;
   int kind = 0;  // 0 pack, 1 unpack
+  void* dev_tiled = nullptr;  // pack only: descriptors served by pack_tiled_kernel
+  int n_tiled = 0;
+  int tiles = 0;
 };
 
 extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_table_plan_t** out) {
@@ -200,15 +340,25 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
     set_error("out of host memory");
     return DSLB_ENOMEM;
   }
+  PackDescDev* ht = new (std::nothrow) PackDescDev[n];
+  if (!ht) {
+    delete[] h;
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
   long long w = 0;
+  int nslow = 0, ntiled = 0;
+  long long tiles = 0;
   for (int k = 0; k < n; ++k) {
     const dslb_pack_desc_t& s = descs[k];
-    PackDescDev& d = h[k];
+    PackDescDev d0;
+    PackDescDev& d = d0;
     const bool ok = s.w && s.out && s.O > 0 && s.I > 0 && s.R > 0 && s.S > 0 && s.mode >= 0 && s.mode <= 2 &&
                     s.cols_pad % 8 == 0 && (!s.bn_gamma || (s.bn_beta && s.bn_mean && s.bn_var)) &&
                     (s.mode == 1 || !s.bn_gamma || (s.scale_out && s.shift_out));
     if (!ok) {
       delete[] h;
+      delete[] ht;
       set_error("dslb_pack_plan_create: descriptor %d is invalid", k);
       return DSLB_EINVAL;
     }
@@ -233,25 +383,44 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
     d.fill = s.fill_padding ? 1 : 0;
     if (d.row_off + d.rows > s.rows_pad || d.col_off + (s.fill_padding ? s.cols_pad : real_cols) > s.cols_pad) {
       delete[] h;
+      delete[] ht;
       set_error("dslb_pack_plan_create: descriptor %d does not fit its packed block", k);
       return DSLB_EINVAL;
     }
-    d.work_begin = w;
-    w += (long long)d.rows * d.cols8;
+    // regular convs without padding go to the tiled (coalesced) kernel
+    const bool tiled = s.mode <= 1 && s.O % PT == 0 && s.I % PT == 0 && s.R * s.S <= PT_MAX_TAPS && s.row_off == 0 &&
+                       s.col_off == 0 && s.rows_pad == real_rows && s.cols_pad == real_cols && s.cols_pad % 8 == 0 &&
+                       ((uintptr_t)s.out % 16) == 0;
+    if (tiled) {
+      d.work_begin = tiles;
+      tiles += (long long)(s.O / PT) * (s.I / PT);
+      ht[ntiled++] = d;
+    } else {
+      d.work_begin = w;
+      w += (long long)d.rows * d.cols8;
+      h[nslow++] = d;
+    }
   }
   dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
-  cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(PackDescDev) * n) : cudaErrorMemoryAllocation;
-  if (e == cudaSuccess) e = cudaMemcpy(p->dev, h, sizeof(PackDescDev) * n, cudaMemcpyHostToDevice);
+  cudaError_t e = p ? cudaSuccess : cudaErrorMemoryAllocation;
+  if (e == cudaSuccess && nslow) e = cudaMalloc(&p->dev, sizeof(PackDescDev) * nslow);
+  if (e == cudaSuccess && nslow) e = cudaMemcpy(p->dev, h, sizeof(PackDescDev) * nslow, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ntiled) e = cudaMalloc(&p->dev_tiled, sizeof(PackDescDev) * ntiled);
+  if (e == cudaSuccess && ntiled) e = cudaMemcpy(p->dev_tiled, ht, sizeof(PackDescDev) * ntiled, cudaMemcpyHostToDevice);
   delete[] h;
-  if (e != cudaSuccess) {
-    set_error("dslb_pack_plan_create: %s", cudaGetErrorString(e));
+  delete[] ht;
+  if (e != cudaSuccess || tiles > 0x7fffffffLL) {
+    set_error("dslb_pack_plan_create: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many tiles");
     if (p && p->dev) cudaFree(p->dev);
+    if (p && p->dev_tiled) cudaFree(p->dev_tiled);
     delete p;
     return DSLB_ECUDA;
   }
-  p->n = n;
+  p->n = nslow;
   p->total = w;
   p->kind = 0;
+  p->n_tiled = ntiled;
+  p->tiles = (int)tiles;
   *out = p;
   return DSLB_OK;
 }
@@ -263,47 +432,84 @@ extern "C" int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs, int n, d
     set_error("out of host memory");
     return DSLB_ENOMEM;
   }
-  long long w = 0;
+  UnpackDescDev* ht = new (std::nothrow) UnpackDescDev[n];
+  if (!ht) {
+    delete[] h;
+    set_error("out of host memory");
+    return DSLB_ENOMEM;
+  }
+  long long w = 0, items = 0;
+  int nslow = 0, ntiled = 0;
   for (int k = 0; k < n; ++k) {
     const dslb_unpack_desc_t& s = descs[k];
-    UnpackDescDev& d = h[k];
+    UnpackDescDev d0;
+    UnpackDescDev& d = d0;
     if (!(s.dw && s.g && s.O > 0 && s.I > 0 && s.R > 0 && s.S > 0 && s.rows >= s.row_off + s.O &&
           (!s.bn_gamma || s.bn_var))) {
       delete[] h;
+      delete[] ht;
       set_error("dslb_unpack_plan_create: descriptor %d is invalid", k);
       return DSLB_EINVAL;
     }
     d.dw = s.dw; d.g = s.g; d.bn_gamma = s.bn_gamma; d.bn_var = s.bn_var;
     d.O = s.O; d.I = s.I; d.R = s.R; d.S = s.S; d.rows = s.rows; d.row_off = s.row_off; d.eps = s.bn_eps;
-    d.work_begin = w;
-    w += (long long)s.O * s.I;
+    d.vec4 = 0;
+    if (s.R * s.S > 1 && s.R * s.S <= 9) {
+      d.work_begin = items;
+      items += (long long)s.O * ((s.I + 255) / 256);
+      ht[ntiled++] = d;
+    } else {
+      d.vec4 = (s.R * s.S == 1 && s.I % 4 == 0 && ((uintptr_t)s.dw % 16) == 0 && ((uintptr_t)s.g % 16) == 0 &&
+                ((long long)s.row_off * s.I) % 4 == 0) ? 1 : 0;
+      d.work_begin = w;
+      w += d.vec4 ? (long long)s.O * s.I / 4 : (long long)s.O * s.I;
+      h[nslow++] = d;
+    }
   }
   dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
-  cudaError_t e = p ? cudaMalloc(&p->dev, sizeof(UnpackDescDev) * n) : cudaErrorMemoryAllocation;
-  if (e == cudaSuccess) e = cudaMemcpy(p->dev, h, sizeof(UnpackDescDev) * n, cudaMemcpyHostToDevice);
+  cudaError_t e = p ? cudaSuccess : cudaErrorMemoryAllocation;
+  if (e == cudaSuccess && nslow) e = cudaMalloc(&p->dev, sizeof(UnpackDescDev) * nslow);
+  if (e == cudaSuccess && nslow) e = cudaMemcpy(p->dev, h, sizeof(UnpackDescDev) * nslow, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ntiled) e = cudaMalloc(&p->dev_tiled, sizeof(UnpackDescDev) * ntiled);
+  if (e == cudaSuccess && ntiled) e = cudaMemcpy(p->dev_tiled, ht, sizeof(UnpackDescDev) * ntiled, cudaMemcpyHostToDevice);
   delete[] h;
-  if (e != cudaSuccess) {
-    set_error("dslb_unpack_plan_create: %s", cudaGetErrorString(e));
+  delete[] ht;
+  if (e != cudaSuccess || items > 0x7fffffffLL) {
+    set_error("dslb_unpack_plan_create: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many work items");
     if (p && p->dev) cudaFree(p->dev);
+    if (p && p->dev_tiled) cudaFree(p->dev_tiled);
     delete p;
     return DSLB_ECUDA;
   }
-  p->n = n;
+  p->n = nslow;
   p->total = w;
   p->kind = 1;
+  p->n_tiled = ntiled;
+  p->tiles = (int)items;
   *out = p;
   return DSLB_OK;
 }
 
 extern "C" int dslb_table_plan_run(const dslb_table_plan_t* p, void* stream) {
-  DSLB_CHECK_ARG(p && p->dev, "dslb_table_plan_run: null plan");
+  DSLB_CHECK_ARG(p && (p->dev || p->dev_tiled), "dslb_table_plan_run: null plan");
   long long blocks = (p->total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (p->kind == 0)
-    pack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const PackDescDev*)p->dev, p->n, p->total);
-  else
-    unpack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const UnpackDescDev*)p->dev, p->n, p->total);
+  if (p->kind == 0) {
+    if (p->n_tiled) {
+      const int tb = p->tiles < num_sms() * 6 ? p->tiles : num_sms() * 6;
+      pack_tiled_kernel<<<tb, 256, 0, (cudaStream_t)stream>>>((const PackDescDev*)p->dev_tiled, p->n_tiled, p->tiles);
+    }
+    if (p->n)
+      pack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const PackDescDev*)p->dev, p->n, p->total);
+  } else {
+    if (p->n_tiled) {
+      const int tb = p->tiles < num_sms() * 8 ? p->tiles : num_sms() * 8;
+      unpack_tiled_kernel<<<tb, 256, 0, (cudaStream_t)stream>>>((const UnpackDescDev*)p->dev_tiled, p->n_tiled, p->tiles);
+    }
+    if (p->n)
+      unpack_batched_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const UnpackDescDev*)p->dev, p->n, p->total);
+  }
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }
@@ -311,6 +517,7 @@ extern "C" int dslb_table_plan_run(const dslb_table_plan_t* p, void* stream) {
 extern "C" void dslb_table_plan_destroy(dslb_table_plan_t* p) {
   if (!p) return;
   if (p->dev) cudaFree(p->dev);
+  if (p->dev_tiled) cudaFree(p->dev_tiled);
   delete p;
 }
 

@@ -608,6 +608,46 @@ extern "C" int dslb_stem_im2col(const float* img, void* out, int N, int H, int W
   LAUNCH_CHECK();
 }
 
+namespace dslb {
+// Scale-invariant extra input (SemiEpochBasedRunner.train, mmdet/runner/hooks/semi_epoch_based_runner.py:186-204):
+// out[c] = zeros(H, W) with the bilinear (align_corners=False) resize of img[c] to (H/2, W/2) in its top-left corner.
+// Index arithmetic follows torch's upsample_bilinear2d: src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out.
+__global__ void si_half_image_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W, int oh,
+                                     int ow) {
+  const long long total = (long long)C * H * W;
+  const float sh = (float)H / (float)oh, sw = (float)W / (float)ow;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % W);
+    const int y = (int)((t / W) % H);
+    const int c = (int)(t / ((long long)W * H));
+    float v = 0.f;
+    if (y < oh && x < ow) {
+      float fy = sh * ((float)y + 0.5f) - 0.5f;
+      float fx = sw * ((float)x + 0.5f) - 0.5f;
+      fy = fy < 0.f ? 0.f : fy;
+      fx = fx < 0.f ? 0.f : fx;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int yp = y0 < H - 1 ? 1 : 0, xp = x0 < W - 1 ? 1 : 0;
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      const float* p = img + ((long long)c * H + y0) * W + x0;
+      v = hy * (hx * p[0] + lx * p[xp]) + ly * (hx * p[(long long)yp * W] + lx * p[(long long)yp * W + xp]);
+    }
+    out[t] = v;
+  }
+}
+}  // namespace dslb
+
+extern "C" int dslb_si_half_image(const float* img, float* out, int C, int H, int W, void* stream) {
+  DSLB_CHECK_ARG(img && out && C > 0 && H >= 2 && W >= 2, "dslb_si_half_image: bad arguments");
+  const long long total = (long long)C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)dslb::num_sms() * 16) blocks = (long long)dslb::num_sms() * 16;
+  dslb::si_half_image_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, out, C, H, W, H / 2, W / 2);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
 extern "C" int dslb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   DSLB_CHECK_ARG(x && y && C % 8 == 0, "dslb_maxpool3x3s2: C must be a multiple of 8");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;

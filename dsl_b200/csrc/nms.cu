@@ -169,6 +169,11 @@ struct PseudoParams {
   int B, max_det, C, max_boxes;
   float nms_iou;
   double infer_score_thr, ignore_lo;
+  // adaptive-threshold statistics (unlabel_pred_hook.py:295-343), optional: per-class count / score sum of the boxes
+  // the hook would have written to its JSON file and adathres() would have counted
+  long long* stat_cnt;      // [C] or null
+  double* stat_cum;         // [C]
+  const double* stat_prev;  // [C] last epoch's thresholds (-inf = class absent from the history) or null = first pass
 };
 
 __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant__ PseudoParams P) {
@@ -245,6 +250,16 @@ __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant
         const int i = rank_of[r];
         if (!alive[i]) continue;
         const float4 bb = sbox[i];
+        if (P.stat_cnt) {
+          // adathres() reads the hook's JSON, i.e. every box alive here (before the dataset's geometry filter): counted
+          // when score >= 0.3 (no history file yet) or >= last epoch's threshold of its class
+          const double sj = (double)(float)sscore[i];
+          const double gate = P.stat_prev ? P.stat_prev[slabel[i]] : 0.3;
+          if (sj >= gate) {
+            P.stat_cnt[slabel[i]] += 1;
+            P.stat_cum[slabel[i]] += sj;
+          }
+        }
         const float iw = fmaxf(0.f, fminf(bb.z, W) - fmaxf(bb.x, 0.f));
         const float ih = fmaxf(0.f, fminf(bb.w, H) - fmaxf(bb.y, 0.f));
         if (iw * ih == 0.f) continue;
@@ -268,6 +283,39 @@ __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant
       P.ig_off[n_img + 1] = ig_base;
     }
     __syncthreads();
+  }
+}
+
+// adathres() tail (unlabel_pred_hook.py:344-361), fp64 like the reference's Python floats: over the classes that were
+// counted at all, mean = sum(count) / #classes; weight_c = (mean / cum_c)^gamma2;
+// thr_c = clip((cum_c / mean)^gamma1 * base, lo, hi). Classes never counted keep `absent_thr` / weight 0 and get
+// prev_out = -inf ("not in history": always counted next epoch).
+__global__ void adathres_finalize_kernel(const long long* __restrict__ cnt, const double* __restrict__ cum, int C,
+                                         double gamma1, double gamma2, double base, double lo, double hi,
+                                         double absent_thr, double* __restrict__ thr_out,
+                                         double* __restrict__ weight_out, double* __restrict__ prev_out) {
+  __shared__ double s_mean;
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    int present = 0;
+    for (int c = 0; c < C; ++c) {
+      tot += cnt[c];
+      present += cnt[c] > 0 ? 1 : 0;
+    }
+    s_mean = present ? (double)tot / (double)present : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (cnt[c] > 0) {
+      const double t = pow(cum[c] / s_mean, gamma1) * base;
+      thr_out[c] = fmax(fmin(t, hi), lo);
+      weight_out[c] = pow(s_mean / cum[c], gamma2);
+      if (prev_out) prev_out[c] = thr_out[c];
+    } else {
+      thr_out[c] = absent_thr;
+      weight_out[c] = 0.0;
+      if (prev_out) prev_out[c] = -INFINITY;
+    }
   }
 }
 
@@ -309,20 +357,44 @@ extern "C" int dslb_multiclass_nms(const float* boxes, const float* scores, cons
   return DSLB_OK;
 }
 
-extern "C" int dslb_pseudo_labels(const float* dets, const int32_t* det_labels, const int32_t* det_count,
-                                  const double* thr_class, const float* img_wh, int B, int max_det, int num_classes,
-                                  double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
-                                  int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, void* stream) {
+extern "C" int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                                        const double* thr_class, const float* img_wh, int B, int max_det,
+                                        int num_classes, double infer_score_thr, float nms_iou, double ignore_lo,
+                                        int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
+                                        float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt, double* stat_cum,
+                                        const double* stat_prev, void* stream) {
   DSLB_CHECK_ARG(dets && det_labels && det_count && thr_class && img_wh && gt_boxes && gt_labels && gt_off && ig_boxes &&
                      ig_off,
                  "dslb_pseudo_labels: null argument");
   DSLB_CHECK_ARG(B >= 1 && max_det >= 1 && max_det <= 128, "dslb_pseudo_labels: max_det must be in [1, 128]");
+  DSLB_CHECK_ARG((stat_cnt == nullptr) == (stat_cum == nullptr), "dslb_pseudo_labels: stat_cnt and stat_cum go together");
   PseudoParams P;
   P.dets = dets; P.det_labels = det_labels; P.det_count = det_count; P.thr_class = thr_class; P.img_wh = img_wh;
   P.gt_boxes = gt_boxes; P.gt_labels = (long long*)gt_labels; P.gt_off = gt_off; P.ig_boxes = ig_boxes; P.ig_off = ig_off;
   P.B = B; P.max_det = max_det; P.C = num_classes; P.max_boxes = max_boxes;
   P.infer_score_thr = infer_score_thr; P.nms_iou = nms_iou; P.ignore_lo = ignore_lo;
+  P.stat_cnt = (long long*)stat_cnt; P.stat_cum = stat_cum; P.stat_prev = stat_prev;
   pseudo_label_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(P);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" int dslb_pseudo_labels(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                                  const double* thr_class, const float* img_wh, int B, int max_det, int num_classes,
+                                  double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
+                                  int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, void* stream) {
+  return dslb_pseudo_labels_stats(dets, det_labels, det_count, thr_class, img_wh, B, max_det, num_classes,
+                                  infer_score_thr, nms_iou, ignore_lo, max_boxes, gt_boxes, gt_labels, gt_off, ig_boxes,
+                                  ig_off, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int dslb_adathres_finalize(const int64_t* stat_cnt, const double* stat_cum, int num_classes, double gamma1,
+                                      double gamma2, double base, double lo, double hi, double absent_thr,
+                                      double* thr_out, double* weight_out, double* prev_out, void* stream) {
+  DSLB_CHECK_ARG(stat_cnt && stat_cum && thr_out && weight_out && num_classes >= 1, "dslb_adathres_finalize: bad arguments");
+  adathres_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const long long*)stat_cnt, stat_cum, num_classes, gamma1,
+                                                               gamma2, base, lo, hi, absent_thr, thr_out, weight_out,
+                                                               prev_out);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }

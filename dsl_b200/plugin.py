@@ -609,11 +609,14 @@ def scale_invariant_input(img, gt_bboxes, gt_labels, gt_bboxes_ignore, img_metas
     """SemiEpochBasedRunner.train SI block (semi_epoch_based_runner.py:186-204): append a bilinear half-resolution copy
     of the LAST image (zero padded to the batch H x W), with its boxes, ignore boxes and meta sizes halved.
     Returns (img, gt_bboxes, gt_labels, gt_bboxes_ignore, img_metas) of the batch of B + 1."""
-    import torch.nn.functional as F
+    from . import _lib as L
+    _need_cuda(img, "scale_invariant_input(img)")
     h, w = img.shape[-2:]
-    half = F.interpolate(img[-1:].clone(), (int(h / 2), int(w / 2)), mode="bilinear")
-    tmp = torch.zeros_like(img[-1:])
-    tmp[:, :, :int(h / 2), :int(w / 2)] = half
+    src = img[-1].contiguous().float()
+    tmp = torch.empty_like(src)
+    L.check(L.lib.dslb_si_half_image(L.ptr(src), L.ptr(tmp), int(src.shape[0]), int(h), int(w), L.cur_stream()),
+            "si_half_image")
+    tmp = tmp.to(img.dtype)[None]
     meta = dict(img_metas[-1])
     for k in ("img_shape", "pad_shape"):
         if k in meta:

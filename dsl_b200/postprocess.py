@@ -40,6 +40,12 @@ class TeacherPost:
         self.img_wh = z(B, 2)          # (width, height) of the ORIGINAL image the rescaled boxes live in
         self.max_boxes = max_boxes
         self.rescale = True
+        # adaptive-threshold statistics of the running epoch (unlabel_pred_hook.py:295-343), accumulated on the device
+        self.stat_cnt = z(num_classes, dtype=torch.int64)
+        self.stat_cum = z(num_classes, dtype=torch.float64)
+        self.stat_prev = z(num_classes, dtype=torch.float64)   # last epoch's thresholds (-inf: class not in the history)
+        self.have_prev = False
+        self.class_weight = z(num_classes, dtype=torch.float64)
 
     def set_meta(self, img_shapes, scale_factors=None, ori_shapes=None):
         """img_shapes: [(H, W, ...)] per image (img_metas['img_shape']); scale_factors: [4 floats] per image or None."""
@@ -88,13 +94,38 @@ class TeacherPost:
             L.cur_stream()), "multiclass_nms")
 
     def pseudo_labels(self, gt_boxes, gt_labels, gt_off, ig_boxes, ig_off, infer_score_thr=0.1, hook_iou=0.6,
-                      ignore_lo=0.1):
-        """Detections -> packed (pseudo GT, ignore) box lists written straight into a student's target buffers."""
-        L.check(L.lib.dslb_pseudo_labels(
+                      ignore_lo=0.1, accumulate_stats=False):
+        """Detections -> packed (pseudo GT, ignore) box lists written straight into a student's target buffers.
+        accumulate_stats: also add this batch to the epoch's adathres statistics (per-class count / score sum of the
+        boxes the reference's hook would have written to JSON and adathres() would have counted)."""
+        L.check(L.lib.dslb_pseudo_labels_stats(
             L.ptr(self.dets), L.ptr(self.det_labels), L.ptr(self.det_count), L.ptr(self.thr_class), L.ptr(self.img_wh),
             self.B, self.max_per_img, self.C, float(infer_score_thr), float(hook_iou), float(ignore_lo),
             int(gt_boxes.shape[0]), L.ptr(gt_boxes), L.ptr(gt_labels), L.ptr(gt_off), L.ptr(ig_boxes), L.ptr(ig_off),
-            L.cur_stream()), "pseudo_labels")
+            L.ptr(self.stat_cnt) if accumulate_stats else None, L.ptr(self.stat_cum) if accumulate_stats else None,
+            L.ptr(self.stat_prev) if (accumulate_stats and self.have_prev) else None, L.cur_stream()), "pseudo_labels")
+
+    def adathres_reset(self, forget_history=False):
+        self.stat_cnt.zero_()
+        self.stat_cum.zero_()
+        if forget_history:
+            self.have_prev = False
+
+    def adathres_update(self, gamma1=0.05, gamma2=0.6, base=0.3, ranges=(0.3, 0.35), default_thres=0.3):
+        """End of an epoch: adathres() of the reference (unlabel_pred_hook.py:295-367) on the device. Statistics are
+        summed over ranks first (the reference's rank 0 reads every rank's JSON files). Installs the new per-class
+        thresholds for the pseudo-label rule, keeps them as next epoch's counting gate, clears the accumulators."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.stat_cnt)
+            dist.all_reduce(self.stat_cum)
+        L.check(L.lib.dslb_adathres_finalize(
+            L.ptr(self.stat_cnt), L.ptr(self.stat_cum), self.C, float(gamma1), float(gamma2), float(base),
+            float(ranges[0]), float(ranges[1]), float(default_thres), L.ptr(self.thr_class), L.ptr(self.class_weight),
+            L.ptr(self.stat_prev), L.cur_stream()), "adathres_finalize")
+        self.have_prev = True
+        self.adathres_reset()
+        return self.thr_class, self.class_weight
 
     def results(self):
         """Host copy: [(dets (n,5) fp32, labels (n,) int64)] per image — what FCOSHead.get_bboxes returns."""

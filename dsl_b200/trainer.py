@@ -48,6 +48,7 @@ class DSLEngine:
         self.use_graphs = use_graphs
         self.graphs = None
         self.nms_pre, self.score_thr = nms_pre, score_thr
+        self.adathres_stats = True   # accumulate the adaptive-threshold statistics in every teacher pass
         self._build_teacher_post()
         self.launches_per_step = None
         self.two_streams = two_streams
@@ -84,7 +85,13 @@ class DSLEngine:
         t = self.teacher
         self.post.decode(t.cls_out, t.rc_out)
         self.post.nms()
-        self.post.pseudo_labels(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, self.pl_ig_boxes, self.pl_ig_off)
+        self.post.pseudo_labels(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, self.pl_ig_boxes, self.pl_ig_off,
+                                accumulate_stats=self.adathres_stats)
+
+    def end_epoch(self, **adathres_kw):
+        """Per-epoch adaptive thresholds (UnlabelPredHook.before_train_epoch -> adathres, unlabel_pred_hook.py:447-449):
+        turn the statistics the teacher branch accumulated on the device into next epoch's per-class thresholds."""
+        return self.post.adathres_update(**adathres_kw)
 
     # ---------------------------------------------------------------------------------------- step pieces
     def _teacher_branch(self):

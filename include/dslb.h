@@ -114,6 +114,9 @@ int dslb_stem_conv(const float* img, const float* w, const float* bn_gamma, cons
                    const float* bn_var, float eps, void* workspace, void* out, int N, int H, int W, void* stream);
 /* nn.MaxPool2d(3, 2, 1) (resnet.py:611), NHWC bf16. */
 int dslb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* Scale-invariant extra input of the DSL runner (mmdet/runner/hooks/semi_epoch_based_runner.py:186-204): out (C,H,W)
+ * fp32 = zeros with F.interpolate(img, (int(H/2), int(W/2)), mode="bilinear") of img (C,H,W) in the top-left corner. */
+int dslb_si_half_image(const float* img, float* out, int C, int H, int W, void* stream);
 /* FPN top-down: dst += nearest_upsample(src) (necks/fpn.py:163-172) and its backward w.r.t. src. */
 int dslb_upsample_add(void* dst, const void* src, int N, int H, int W, int h, int w, int C, void* stream);
 int dslb_upsample_add_bwd(void* dsrc, const void* ddst, int N, int H, int W, int h, int w, int C, void* stream);
@@ -310,6 +313,24 @@ int dslb_pseudo_labels(const float* dets, const int32_t* det_labels, const int32
                        const float* img_wh, int B, int max_det, int num_classes, double infer_score_thr, float nms_iou,
                        double ignore_lo, int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
                        float* ig_boxes, int32_t* ig_off, void* stream);
+/* Same, plus the on-device statistics of the adaptive-threshold rule (adathres(), mmdet/runner/hooks/
+ * unlabel_pred_hook.py:295-343): every box the hook would have written to its per-image JSON (i.e. alive after the
+ * per-class NMS, BEFORE the dataset's geometry filter) with score >= 0.3 (stat_prev NULL: no history file yet) or
+ * >= stat_prev[class] (last epoch's threshold; -inf = class absent from the history) adds 1 to stat_cnt[class] and its
+ * score to stat_cum[class]. The caller zeroes the two [num_classes] accumulators at the start of an epoch and, with
+ * several ranks, sums them over ranks before dslb_adathres_finalize (the reference's rank 0 reads every file). */
+int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                             const double* thr_class, const float* img_wh, int B, int max_det, int num_classes,
+                             double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
+                             int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt,
+                             double* stat_cum, const double* stat_prev, void* stream);
+/* adathres() tail (unlabel_pred_hook.py:344-361) in fp64: mean = sum(cnt) / #{c: cnt_c > 0};
+ * thr_out[c] = clip((cum_c / mean)^gamma1 * base, lo, hi); weight_out[c] = (mean / cum_c)^gamma2 (the reference writes
+ * the weights but never reads them). Classes never counted: thr_out = absent_thr (SemiCOCODataset's default),
+ * weight_out = 0, prev_out = -inf. prev_out (nullable) is next epoch's stat_prev. */
+int dslb_adathres_finalize(const int64_t* stat_cnt, const double* stat_cum, int num_classes, double gamma1, double gamma2,
+                           double base, double lo, double hi, double absent_thr, double* thr_out, double* weight_out,
+                           double* prev_out, void* stream);
 
 #ifdef __cplusplus
 }

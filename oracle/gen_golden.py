@@ -302,16 +302,78 @@ def gen_hook_chain(R):
     np.savez_compressed(os.path.join(OUT, "hook_chain.npz"), **out)
 
 
+def gen_adathres_chain(R):
+    """Detections -> UnlabelPredHook.save_results2file (one JSON per image) -> adathres() twice (first pass without a
+    history file, second pass gated by the first pass's thresholds): the reference's per-epoch adaptive-threshold
+    statistics on the very files its own hook wrote, for the on-device accumulation (dslb_pseudo_labels_stats +
+    dslb_adathres_finalize)."""
+    save_results2file = ref_loader.load_hook_chain()
+    _, adathres = ref_loader.load_hook_functions()
+    C = 6
+    cats = [f"cat{i}" for i in range(C)]
+    cat2id = {c: i for i, c in enumerate(cats)}
+    id2cat = {str(i): c for i, c in enumerate(cats)}
+    out = {}
+    rng = np.random.RandomState(91)
+    Wi, Hi = 640, 480
+    ncase = 8
+    with tempfile.TemporaryDirectory() as td:
+        root = os.path.join(td, "images")
+        anno = os.path.join(td, "anno")
+        save = os.path.join(td, "save")
+        os.makedirs(os.path.join(root, "sub"))
+        os.makedirs(os.path.join(anno, "sub"))
+        files = []
+        for k in range(ncase):
+            n = int(rng.randint(5, 80))
+            boxes = GI.demo_boxes(rng, n, Hi, Wi) + rng.rand(n, 4).astype(np.float32)
+            boxes[3] = boxes[2] + np.array([0.3, 0.2, 0.4, 0.1], np.float32)   # duplicate: the hook's NMS must fire
+            scores = np.sort(rng.rand(n).astype(np.float32) * 0.9)[::-1].copy()
+            # skewed class frequencies: thresholds of frequent classes leave the lower clip (cum_c > mean count)
+            labels = rng.choice(C, size=n, p=[0.45, 0.25, 0.12, 0.08, 0.05, 0.05]).astype(np.int64)
+            labels[3] = labels[2]
+            dets = torch.from_numpy(np.concatenate([boxes, scores[:, None]], 1))
+            result = R.bbox2result(dets, torch.from_numpy(labels), C)
+            name = f"im{k}.jpg"
+            json.dump(dict(imageName="sub/" + name, targetNum=0, rects=[], tags=[], masks=[], scores=[]),
+                      open(os.path.join(anno, "sub", name + ".json"), "w"))
+            save_results2file(result, os.path.join(root, "sub", name), Hi, Wi, "json", "ckpt", 0.1, id2cat, cat2id,
+                              root, save, "Det", anno_root_path=anno, iou=0.6, fuse=False, first_ignore=False)
+            files.append("sub/" + name + "\n")
+            out[f"c{k}_dets"] = dets.numpy()
+            out[f"c{k}_labels"] = labels
+        fn = os.path.join(td, "adathres.json")
+        for tag in ("first", "second"):
+            adathres(0, True, fn, id2cat, cat2id, files, os.path.join(save, "sub"), {})
+            res = json.load(open(fn))
+            thr = np.full(C, np.nan)
+            wgt = np.full(C, np.nan)
+            for c, v in res["thres"].items():
+                thr[cat2id[c]] = v
+            for c, v in res["id"].items():
+                wgt[int(c)] = v
+            out[f"{tag}_thr"] = thr
+            out[f"{tag}_weight"] = wgt
+    out["meta"] = np.array([ncase, C, Wi, Hi], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "adathres_chain.npz"), **out)
+
+
 def main():
+    import sys
     torch.set_num_threads(8)
     R = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:   # regenerate only the named files, e.g. `python -m oracle.gen_golden adathres_chain`
+        for name in sys.argv[1:]:
+            globals()["gen_" + name](R)
+        return
     gen_head_fwd(R)
     gen_loss(R)
     gen_backbone(R)
     gen_decode(R)
     gen_misc(R)
     gen_hook_chain(R)
+    gen_adathres_chain(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -518,6 +518,40 @@ def test_pseudo_label_chain_matches_reference_golden():
     assert go[-1] > 20 and io[-1] > 5
 
 
+def test_adathres_statistics_match_reference_golden():
+    """Per-epoch adaptive thresholds: the teacher post-processing accumulates per-class count / score sum on the device
+    while it builds the pseudo labels; the finalize kernel turns them into thresholds + class weights. Golden
+    adathres_chain.npz = the reference's adathres() run on the JSON files its own hook wrote for the same detections,
+    first without a history file, then gated by the first pass's thresholds (unlabel_pred_hook.py:295-367)."""
+    from dsl_b200.postprocess import TeacherPost
+    g = np.load(os.path.join(G, "adathres_chain.npz"))
+    ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+    post = TeacherPost(ncase, [(8, 8)], (8,), C, "cuda", max_per_img=100)
+    post.set_meta([(Hi, Wi, 3)] * ncase, None)
+    for k in range(ncase):
+        d = torch.from_numpy(g[f"c{k}_dets"]).float()
+        post.dets[k, :len(d)] = d.cuda()
+        post.det_labels[k, :len(d)] = torch.from_numpy(g[f"c{k}_labels"]).int().cuda()
+        post.det_count[k] = len(d)
+    mb = 1024
+    bufs = (torch.zeros(mb, 4, device="cuda"), torch.zeros(mb, dtype=torch.int64, device="cuda"),
+            torch.zeros(ncase + 1, dtype=torch.int32, device="cuda"), torch.zeros(mb, 4, device="cuda"),
+            torch.zeros(ncase + 1, dtype=torch.int32, device="cuda"))
+    for tag in ("first", "second"):
+        post.pseudo_labels(*bufs, infer_score_thr=0.1, hook_iou=0.6, accumulate_stats=True)
+        thr, wgt = post.adathres_update(gamma1=0.05, gamma2=0.6, base=0.3, ranges=(0.3, 0.35), default_thres=0.3)
+        thr, wgt = thr.cpu().numpy(), wgt.cpu().numpy()
+        ref_t, ref_w = g[f"{tag}_thr"], g[f"{tag}_weight"]
+        present = ~np.isnan(ref_t)
+        assert present.sum() >= 4
+        # fp64 throughout; only the summation order (and the last ulp of pow) may differ from CPython's
+        assert np.allclose(thr[present], ref_t[present], rtol=1e-12, atol=0), (tag, thr, ref_t)
+        assert np.allclose(wgt[present], ref_w[present], rtol=1e-12, atol=0), (tag, wgt, ref_w)
+        assert np.all(thr[~present] == 0.3) and np.all(wgt[~present] == 0.0)
+        assert int(post.stat_cnt.sum()) == 0   # accumulators cleared for the next epoch
+    assert not np.array_equal(g["first_thr"], g["second_thr"])   # the history gate really changed the statistics
+
+
 @pytest.mark.parametrize("depth,B,H,W", [(101, 1, 192, 256), (50, 3, 160, 288), (50, 1, 320, 224)])
 def test_other_configs_forward_loss_backward(depth, B, H, W):
     """BASELINE.json configs[3] (R101) and configs[4] (variable shapes, odd batch = scale-invariant extra image) as
