@@ -648,6 +648,11 @@ def register(force=True):
         done.append("HOOKS.EMAOWNHook")
     except Exception:
         pass
+    try:   # LOSSES.{FocalLoss, GIoULoss, CrossEntropyLoss} and RUNNERS.SemiEpochBasedRunner (need libdslb.so)
+        from . import losses, runner
+        done += losses.register(force) + runner.register(force)
+    except Exception:
+        pass
     return done
 
 

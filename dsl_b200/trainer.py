@@ -23,17 +23,29 @@ from .postprocess import TeacherPost
 class DSLEngine:
     def __init__(self, B, H, W, depth=50, num_classes=80, device="cuda", seed=0, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, bias_lr_mult=2.0, bias_decay_mult=0.0, max_grad_norm=35.0, ema_keep=0.99,
-                 loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05, two_streams=True):
+                 loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05, two_streams=True,
+                 student_store=None, teacher_store=None, scale_invariant=False, soft_weight=0.0, soft_warm_up=0,
+                 head_kwargs=None):
+        """student_store / teacher_store: existing ParamStores (e.g. of two plugin.FCOS modules) to train in place.
+        scale_invariant: the student batch gets the reference's extra half-resolution copy of its last image
+        (semi_epoch_based_runner.py:186-204) -> B + 1 images, and the SI soft loss (fcos_head.py:312-333) with
+        soft_weight (soft_weight / 1000 for the first soft_warm_up + 1 steps)."""
         self.dev = torch.device(device)
         self.B, self.H, self.W = B, H, W
-        self.student = FCOSNet(B, H, W, depth, num_classes, train=True, device=device, seed=seed,
-                               loss_weight=loss_weight)
+        self.scale_invariant = bool(scale_invariant)
+        self.soft_weight, self.soft_warm_up, self.cur_iter = float(soft_weight), int(soft_warm_up), 0
+        sB = B + 1 if self.scale_invariant else B
+        hk = dict(head_kwargs or {})
+        self.student = FCOSNet(sB, H, W, depth, num_classes, train=True, device=device, seed=seed,
+                               loss_weight=loss_weight, soft_weight=soft_weight, store=student_store, **hk)
         tB = teacher_B or B
-        self.teacher = FCOSNet(tB, H, W, depth, num_classes, train=False, device=device, seed=seed)
-        # teacher starts as a copy of the student (reference: both built from the same config, load_checkpoint loads
-        # the same file into both, semi_epoch_based_runner.py:350-366)
-        self.teacher.store.flat.copy_(self.student.store.flat)
-        self.teacher.repack()
+        self.teacher = FCOSNet(tB, H, W, depth, num_classes, train=False, device=device, seed=seed,
+                               store=teacher_store, **hk)
+        if teacher_store is None:
+            # teacher starts as a copy of the student (reference: both built from the same config, load_checkpoint
+            # loads the same file into both, semi_epoch_based_runner.py:350-366)
+            self.teacher.store.flat.copy_(self.student.store.flat)
+            self.teacher.repack()
         st = self.student.store
         self.mom = torch.zeros(st.n_train, dtype=torch.float32, device=self.dev)
         self.lr, self.momentum, self.wd = lr, momentum, weight_decay
@@ -191,7 +203,27 @@ class DSLEngine:
     # ---------------------------------------------------------------------------------------- public
     def set_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
         """Copy one batch into the engine's static input buffers (host tensors should be pinned for async H2D)."""
-        self.student.img.copy_(student_img, non_blocking=True)
+        if self.scale_invariant:
+            # reference: SemiEpochBasedRunner.train builds the extra image on the host (:186-204); here the batch of B
+            # lands in the first B slots and the half-resolution copy of the last one is written by a kernel
+            B = self.B
+            self.student.img[:B].copy_(student_img, non_blocking=True)
+            L.check(L.lib.dslb_si_half_image(L.ptr(self.student.img[B - 1]), L.ptr(self.student.img[B]), 3, self.H,
+                                             self.W, L.cur_stream()), "si_half_image")
+            gt_bboxes = list(gt_bboxes) + [gt_bboxes[-1] / 2]
+            gt_labels = list(gt_labels) + [gt_labels[-1]]
+            if gt_bboxes_ignore is not None:
+                gt_bboxes_ignore = list(gt_bboxes_ignore) + [gt_bboxes_ignore[-1] / 2]
+            # soft-loss warm-up (fcos_head.py:325-327): weight / 1000 while soft_warm_up >= cur_iter
+            if self.soft_weight != 0.0:
+                sw = self.soft_weight / 1000.0 if self.soft_warm_up >= self.cur_iter else self.soft_weight
+                if sw != self.student.si_weight:
+                    self.student.si_weight = sw
+                    self.graphs = None      # the weight is a launch constant of the captured loss kernel
+                if self.soft_warm_up >= self.cur_iter:
+                    self.cur_iter += 1
+        else:
+            self.student.img.copy_(student_img, non_blocking=True)
         self.student.set_targets(gt_bboxes, gt_labels, gt_bboxes_ignore)
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
@@ -201,6 +233,7 @@ class DSLEngine:
         buffers (so it overlaps the step that is still running); the next step() moves it into the plan's static input
         buffers with device-side copies before launching. Call it right after step() for the NEXT batch."""
         st = self.student
+        assert not self.scale_invariant, "prefetch_inputs does not build the scale-invariant extra image: use set_inputs"
         if self._stage is None:
             self._stage = dict(img_s=torch.empty_like(st.img), img_t=torch.empty_like(self.teacher.img),
                                gt_boxes=torch.empty_like(st.gt_boxes), gt_labels=torch.empty_like(st.gt_labels),

@@ -332,6 +332,23 @@ int dslb_adathres_finalize(const int64_t* stat_cnt, const double* stat_cum, int 
                            double base, double lo, double hi, double absent_thr, double* thr_out, double* weight_out,
                            double* prev_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Standalone LOSSES-registry kernels (the training step uses the fused dslb_fcos_loss; these answer configs that build
+ * the loss modules by themselves). One pass each: loss_elem (nullable) = weighted element-wise loss, *loss_sum
+ * (nullable, fp64, ACCUMULATED: zero it first) += its sum, d* (nullable) = gradient of the weighted element-wise loss
+ * w.r.t. the prediction. Reduction / avg_factor / loss_weight (mmdet/models/losses/utils.py:27-54) are scalars for
+ * the caller.
+ *   dslb_sigmoid_focal_loss  losses/focal_loss.py:11-56,59-102; labels int64 in [0, C], C = background; weight [N]
+ *   dslb_giou_loss           losses/iou_loss.py:85-102 + iou2d_calculator.py:214-260 (aligned GIoU, eps); weight [n]
+ *   dslb_bce_with_logits     losses/cross_entropy_loss.py:73-112 (use_sigmoid=True, no class_weight); weight [n]
+ * ---------------------------------------------------------------------------------------------------- */
+int dslb_sigmoid_focal_loss(const float* logits, const int64_t* labels, const float* weight, long long N, int C,
+                            float alpha, float gamma, float* loss_elem, double* loss_sum, float* dlogits, void* stream);
+int dslb_giou_loss(const float* pred, const float* target, const float* weight, long long n, float eps, float* loss_elem,
+                   double* loss_sum, float* dpred, void* stream);
+int dslb_bce_with_logits(const float* x, const float* target, const float* weight, long long n, float* loss_elem,
+                         double* loss_sum, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,6 +358,46 @@ def gen_adathres_chain(R):
     np.savez_compressed(os.path.join(OUT, "adathres_chain.npz"), **out)
 
 
+def gen_loss_modules(R):
+    """The reference's own LOSSES modules (FocalLoss -> py_sigmoid_focal_loss on CPU, GIoULoss,
+    CrossEntropyLoss(use_sigmoid=True)) on random inputs: value + gradient w.r.t. the prediction for every
+    reduction / avg_factor / weight combination the modules accept."""
+    out = {}
+    rng = np.random.RandomState(123)
+    N, C, n = 257, 11, 131
+    logits = torch.from_numpy((rng.randn(N, C) * 2).astype(np.float32))
+    labels = torch.from_numpy(rng.randint(0, C + 1, size=N).astype(np.int64))   # C = background
+    wN = torch.from_numpy((rng.rand(N) * (rng.rand(N) > 0.2)).astype(np.float32))
+    b1 = torch.from_numpy(GI.demo_boxes(rng, n, 300, 400) + rng.rand(n, 4).astype(np.float32))
+    b2 = torch.from_numpy(GI.demo_boxes(rng, n, 300, 400) + rng.rand(n, 4).astype(np.float32))
+    b2[:7] = b1[:7]                                    # identical boxes (tie gradients)
+    b2[7:12] = b1[7:12] + 500.0                        # disjoint boxes
+    wn = torch.from_numpy(rng.rand(n).astype(np.float32))
+    ctr = torch.from_numpy((rng.randn(n) * 2).astype(np.float32))
+    ctr_t = torch.from_numpy(rng.rand(n).astype(np.float32))
+    out.update(logits=logits.numpy(), labels=labels.numpy(), wN=wN.numpy(), b1=b1.numpy(), b2=b2.numpy(), wn=wn.numpy(),
+               ctr=ctr.numpy(), ctr_t=ctr_t.numpy())
+    cases = [("mean_w_avg", dict(weight=True, avg_factor=37.5, reduction_override=None)),
+             ("mean_now", dict(weight=False, avg_factor=None, reduction_override=None)),
+             ("sum_w", dict(weight=True, avg_factor=None, reduction_override="sum")),
+             ("none_w", dict(weight=True, avg_factor=None, reduction_override="none"))]
+    mods = [("focal", R.FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0), logits, labels, wN),
+            ("giou", R.GIoULoss(loss_weight=1.0), b1, b2, wn),
+            ("bce", R.CrossEntropyLoss(use_sigmoid=True, loss_weight=1.0), ctr, ctr_t, wn),
+            ("focal_lw", R.FocalLoss(use_sigmoid=True, gamma=1.5, alpha=0.4, loss_weight=2.5), logits, labels, wN)]
+    for mname, mod, pred, tgt, w in mods:
+        for cname, kw in cases:
+            x = pred.clone().requires_grad_(True)
+            val = mod(x, tgt, weight=w if kw["weight"] else None, avg_factor=kw["avg_factor"],
+                      reduction_override=kw["reduction_override"])
+            g = torch.from_numpy(rng.rand(*val.shape).astype(np.float32)) if val.dim() else torch.tensor(1.7)
+            (val * g).sum().backward()
+            out[f"{mname}_{cname}_val"] = val.detach().numpy()
+            out[f"{mname}_{cname}_gout"] = g.numpy()
+            out[f"{mname}_{cname}_grad"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "loss_modules.npz"), **out)
+
+
 def main():
     import sys
     torch.set_num_threads(8)
@@ -374,6 +414,7 @@ def main():
     gen_misc(R)
     gen_hook_chain(R)
     gen_adathres_chain(R)
+    gen_loss_modules(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

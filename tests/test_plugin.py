@@ -243,3 +243,55 @@ def test_plugin_simple_test_and_ema_hook():
     for k in ("backbone.layer2.0.conv1.weight", "bbox_head.conv_cls.bias", "backbone.bn1.running_var"):
         assert torch.equal(teacher.state_dict()[k].cpu(), ref[k]), k
     assert runner.ema_flag
+
+
+@pytest.mark.gpu
+def test_semi_epoch_based_runner_drives_the_fused_step(tmp_path):
+    """RUNNERS['SemiEpochBasedRunner'] mirror: reference constructor / counters / hook stages / checkpoint names over the
+    fused engine, with the scale-invariant extra input and the SI soft loss switched on as in the shipped DSL config."""
+    import logging
+    from dsl_b200 import plugin
+    from dsl_b200.runner import SemiEpochBasedRunner
+    cfg = {k: v for k, v in MODEL_CFG.items() if k != "type"}
+    cfg["bbox_head"] = dict(cfg["bbox_head"], loss_weight=3.0, soft_weight=1.0, soft_warm_up=1)
+    model, ema = plugin.FCOS(**cfg).cuda(), plugin.FCOS(**cfg).cuda()
+    ema.load_state_dict(model.state_dict())
+    opt = torch.optim.SGD([p for _, p in model._trainable], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    with pytest.raises(TypeError):
+        SemiEpochBasedRunner(model, optimizer=opt, logger="not a logger", max_epochs=1)
+    runner = SemiEpochBasedRunner(model, optimizer=opt, work_dir=str(tmp_path), logger=logging.getLogger("t"),
+                                  meta=dict(seed=0), max_epochs=2, ema_model=ema, scale_invariant=True)
+    runner.register_hook(plugin.EMAOWNHook(interval=1, mode="iteration", ratio=0.99, start_point=0))
+    stages = []
+
+    class Probe:
+        def before_train_epoch(self, r): stages.append(("be", r.epoch))
+        def after_train_iter(self, r): stages.append(("ai", r.iter, r.inner_iter))
+        def after_train_epoch(self, r): stages.append(("ae", r.epoch))
+
+    runner.register_hook(Probe())
+    B, H, W = 2, 128, 160
+    loader = []
+    for i in range(2):
+        loader.append(_data(B, H, W, 10 + i))
+    t0 = ema.store.flat.clone()
+    s0 = model.store.flat.clone()
+    runner.run([loader], [("train", 1)])
+    torch.cuda.synchronize()
+    assert (runner.epoch, runner.iter, runner.max_iters) == (2, 4, 4)
+    assert stages == [("be", 0), ("ai", 0, 0), ("ai", 1, 1), ("ae", 0), ("be", 1), ("ai", 2, 0), ("ai", 3, 1), ("ae", 1)]
+    lv = runner.outputs["log_vars"]
+    assert set(lv) == {"loss_cls", "loss_bbox", "loss_centerness", "loss_sisoft", "loss"} and np.isfinite(lv["loss"])
+    assert runner.outputs["num_samples"] == B
+    assert runner.engine.student.B == B + 1            # the scale-invariant extra image was appended on the device
+    assert not torch.equal(model.store.flat, s0)       # SGD moved the student (plugin parameters are the same memory)
+    assert not torch.equal(ema.store.flat, t0)         # ... and the EMA moved the teacher
+    # frozen stem: student unchanged there, so the teacher's copy is unchanged too (0.01 s + 0.99 t with s == t)
+    o, n = model.store.offsets["backbone.conv1.weight"]
+    assert torch.allclose(ema.store.flat[o:o + n], t0[o:o + n], rtol=1e-6, atol=0)
+    path = runner.save_checkpoint(str(tmp_path))
+    assert os.path.basename(path) == "epoch_3.pth" and os.path.exists(path + "_ema")
+    ck = torch.load(path, weights_only=False)
+    assert ck["meta"]["epoch"] == 3 and ck["meta"]["iter"] == 4 and ck["meta"]["seed"] == 0
+    assert "bbox_head.conv_cls.weight" in ck["state_dict"] and "backbone.layer4.2.bn3.running_var" in ck["state_dict"]
+    assert int(runner.engine.post.stat_cnt.sum()) == 0 and runner.engine.post.have_prev   # adathres ran at epoch end
