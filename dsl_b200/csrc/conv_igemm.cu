@@ -15,6 +15,7 @@
 //   Scheduling    persistent: grid = min(#tiles, #SMs), static round-robin over the tile list of up to
 //                 DSLB_MAX_SEGS independent convs (e.g. 5 FPN levels x 2 FCOSHead towers in one launch).
 #include <new>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -156,11 +157,11 @@ __device__ __forceinline__ void fast_chunk_math(const uint32_t (&rr)[16], const 
 // Lean epilogue over the channel range [cbeg, cend) of one round (r0 = first channel of the round's 128-channel
 // window), two 16-channel chunks per iteration so both TMEM loads, the shift loads and the slab loads are in flight
 // before the single tcgen05.wait.
-template <bool SHIFT, int AUX, bool RELU>
+template <bool SHIFT, int AUX, bool RELU, bool PAIR>
 __device__ __forceinline__ void fast_chunks(uint32_t taddr, int cbeg, int cend, int r0, uint32_t slab_row, uint32_t sw,
                                             const float* __restrict__ shp) {
   int c0 = cbeg;
-  for (; c0 + 32 <= cend; c0 += 32) {
+  for (; PAIR && c0 + 32 <= cend; c0 += 32) {
     uint32_t ra[16], rb[16];
     tmem_ld16(taddr + c0, ra);
     tmem_ld16(taddr + c0 + 16, rb);
@@ -296,46 +297,76 @@ __device__ __forceinline__ void epilogue_math(const ConvSegDev& sg, const uint32
   }
 }
 
-// The whole parameter block (tile table + TMA descriptors, <= 8 KiB) travels as a __grid_constant__ kernel parameter:
-// it lives in the constant bank, so the per-tile / per-chunk reads of segment fields are constant-cache hits instead
-// of dependent global loads that every "memory"-clobbering barrier asm would force again.
-__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvParamsDev PP) {
-  const ConvParamsDev* P = &PP;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // Two layouts share the same budget: 4 stages + one staging slab per epilogue warpgroup (compute-bound plans), or
-  // 3 stages + two slabs per warpgroup (plans whose residual / mask tiles are prefetched by TMA into the idle slab).
-  const int nst = P->nstages, nbuf = P->nbuf;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + nst * A_BYTES;
-  const int b_stride = P->b_stride;
-  uint8_t* sOut = smem + nst * (A_BYTES + b_stride);
-  uint8_t* sIdent = sOut + nbuf * OUT_BYTES;  // [64][64] bf16 identity, K-major, 128B swizzle (res_mma plans)
-  uint8_t* sBar = sIdent + (P->has_ident ? IDENT_BYTES : 0);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sBar);
-  uint64_t* empty = full + MAX_STAGES;
-  uint64_t* tfull = empty + MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* auxfull = tempty + 2;  // [warpgroup][slab buffer]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 4);
-  float* sStat = reinterpret_cast<float*>(sBar + BAR_BYTES);
+template <bool PAIR>
+__device__ __forceinline__ void fast_dispatch(int variant, uint32_t taddr, int cbeg, int cend, int r0, uint32_t slab_row,
+                                              uint32_t sw, const float* __restrict__ shp) {
+#define DSLB_FAST(S_, A_, R_) fast_chunks<S_, A_, R_, PAIR>(taddr, cbeg, cend, r0, slab_row, sw, shp)
+  switch (variant) {  // (shift ? 6 : 0) + aux_kind * 2 + relu
+    case 0: DSLB_FAST(false, 0, false); break;
+    case 1: DSLB_FAST(false, 0, true); break;
+    case 2: DSLB_FAST(false, 1, false); break;
+    case 3: DSLB_FAST(false, 1, true); break;
+    case 4: DSLB_FAST(false, 2, false); break;
+    case 5: DSLB_FAST(false, 2, true); break;
+    case 6: DSLB_FAST(true, 0, false); break;
+    case 7: DSLB_FAST(true, 0, true); break;
+    case 8: DSLB_FAST(true, 1, false); break;
+    case 9: DSLB_FAST(true, 1, true); break;
+    case 10: DSLB_FAST(true, 2, false); break;
+    default: DSLB_FAST(true, 2, true); break;
+  }
+#undef DSLB_FAST
+}
 
+// Shared-memory carve-up + pipeline barriers, common to both kernels below.
+struct ConvSmem {
+  uint8_t *sA, *sB, *sOut, *sIdent;
+  uint64_t *full, *empty, *tfull, *tempty, *auxfull;
+  uint32_t* tmem_slot;
+  float* sStat;
+  int nst, b_stride;
+};
+
+__device__ __forceinline__ ConvSmem conv_carve(const ConvParamsDev* P, uint8_t* smem_raw) {
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Layouts sharing one budget: as many (A + widest B) stages as fit next to one staging slab per epilogue warpgroup
+  // (compute-bound plans) or next to four slabs (double-buffered slabs of the 2-group kernel / one slab for each of the
+  // 4 groups of the fast kernel) plus, for res_mma plans, the identity tile.
+  ConvSmem S;
+  S.nst = P->nstages;
+  S.b_stride = P->b_stride;
+  S.sA = smem;
+  S.sB = smem + S.nst * A_BYTES;
+  S.sOut = smem + S.nst * (A_BYTES + S.b_stride);
+  S.sIdent = S.sOut + P->nbuf * OUT_BYTES;  // [64][64] bf16 identity, K-major, 128B swizzle (res_mma plans)
+  uint8_t* sBar = S.sIdent + (P->has_ident ? IDENT_BYTES : 0);
+  S.full = reinterpret_cast<uint64_t*>(sBar);
+  S.empty = S.full + MAX_STAGES;
+  S.tfull = S.empty + MAX_STAGES;
+  S.tempty = S.tfull + 2;
+  S.auxfull = S.tempty + 2;  // [warpgroup][slab buffer] (2-group kernel) / [warpgroup] (fast kernel)
+  S.tmem_slot = reinterpret_cast<uint32_t*>(S.auxfull + 4);
+  S.sStat = reinterpret_cast<float*>(sBar + BAR_BYTES);
+  return S;
+}
+
+// barrier init, TMEM allocation, identity tile; returns the TMEM base address. Ends with a CTA-wide barrier.
+__device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const ConvSmem& S, int epi_warps) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&S.full[i], 1);
+      mbar_init(&S.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&S.tfull[i], 1);
+      mbar_init(&S.tempty[i], epi_warps);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&auxfull[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&S.auxfull[i], 1);
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_alloc(S.tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   if (P->has_ident) {
@@ -351,114 +382,138 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         else if (w == 2) z.z = one;
         else z.w = one;
       }
-      reinterpret_cast<uint4*>(sIdent)[i] = z;
+      reinterpret_cast<uint4*>(S.sIdent)[i] = z;
     }
     fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  return *S.tmem_slot;
+}
+
+// ------------------------------------------------------------------ TMA producer (one elected thread of warp 0)
+__device__ __forceinline__ void conv_producer(const ConvParamsDev* P, const ConvSmem& S) {
+  const int total = P->total_tiles, nst = S.nst;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+    const int tl = tile - sg.tile_begin;
+    const int nt = tl / sg.m_tiles;
+    const int mt = tl - nt * sg.m_tiles;
+    const int pix0 = mt * BM;
+    const int n_img = pix0 / sg.HoWo;
+    const int rem = pix0 - n_img * sg.HoWo;
+    const int p = rem / sg.Wo;
+    const int q = rem - p * sg.Wo;
+    const int cw = q * sg.stride - sg.pad;
+    const int ch = p * sg.stride - sg.pad;
+    const uint32_t tx = A_BYTES + sg.bn * (BK * 2);
+    for (int tap = 0; tap < sg.taps; ++tap) {
+      const int r = tap / sg.S;
+      const int s = tap - r * sg.S;
+      for (int kc = 0; kc < sg.cin_chunks; ++kc) {
+        mbar_wait(&S.empty[stage], phase ^ 1);
+        mbar_expect_tx(&S.full[stage], tx);
+        tma_load_im2col_4d(&sg.tmA, &S.full[stage], S.sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
+                           (uint16_t)r);
+        tma_load_3d(&sg.tmB, &S.full[stage], S.sB + stage * S.b_stride, kc * BK, nt * sg.bn, tap);
+        if (++stage == nst) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    if (sg.res_mma) {
+      for (int j = 0; j < sg.bn / 64; ++j) {
+        mbar_wait(&S.empty[stage], phase ^ 1);
+        mbar_expect_tx(&S.full[stage], A_BYTES);
+        tma_load_2d(&sg.tmRes, &S.full[stage], S.sA + stage * A_BYTES, nt * sg.bn + 64 * j, pix0);
+        if (++stage == nst) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ MMA issuer (one elected thread of warp 1)
+__device__ __forceinline__ void conv_mma(const ConvParamsDev* P, const ConvSmem& S, uint32_t tmem_base) {
+  const int total = P->total_tiles, nst = S.nst;
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+    const int kiters = sg.taps * sg.cin_chunks;
+    const int acc = it & 1;
+    mbar_wait(&S.tempty[acc], ((it >> 1) & 1) ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * 256;
+    const uint32_t idesc = make_idesc_bf16(BM, sg.bn, 0, 0);
+    for (int ki = 0; ki < kiters; ++ki) {
+      mbar_wait(&S.full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(S.sA + stage * A_BYTES);
+      const uint32_t b_base = smem_u32(S.sB + stage * S.b_stride);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) {
+        const uint64_t ad = make_sdesc(a_base + k * 32, 16, 1024);
+        const uint64_t bd = make_sdesc(b_base + k * 32, 16, 1024);
+        umma_bf16(d_tmem, ad, bd, idesc, (ki | k) != 0);
+      }
+      umma_commit(&S.empty[stage]);
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (sg.res_mma) {
+      const uint32_t idesc64 = make_idesc_bf16(BM, 64, 0, 0);
+      const uint32_t i_base = smem_u32(S.sIdent);
+      for (int j = 0; j < sg.bn / 64; ++j) {
+        mbar_wait(&S.full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(S.sA + stage * A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(d_tmem + 64 * j, make_sdesc(a_base + k * 32, 16, 1024), make_sdesc(i_base + k * 32, 16, 1024),
+                    idesc64, 1);
+        umma_commit(&S.empty[stage]);
+        if (++stage == nst) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    umma_commit(&S.tfull[acc]);
+  }
+}
+
+// The whole parameter block (tile table + TMA descriptors, <= 10 KiB) travels as a __grid_constant__ kernel parameter:
+// it lives in the constant bank, so the per-tile / per-chunk reads of segment fields are constant-cache hits instead
+// of dependent global loads that every "memory"-clobbering barrier asm would force again.
+__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvParamsDev PP) {
+  const ConvParamsDev* P = &PP;
+  extern __shared__ uint8_t smem_raw[];
+  const ConvSmem S = conv_carve(P, smem_raw);
+  const int nbuf = P->nbuf;
+  uint8_t* const sOut = S.sOut;
+  uint64_t* const tfull = S.tfull;
+  uint64_t* const tempty = S.tempty;
+  uint64_t* const auxfull = S.auxfull;
+  float* const sStat = S.sStat;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = conv_prologue(P, S, 8);
   const int total = P->total_tiles;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const ConvSegDev& sg = P->seg[find_seg(P, tile)];
-        const int tl = tile - sg.tile_begin;
-        const int nt = tl / sg.m_tiles;
-        const int mt = tl - nt * sg.m_tiles;
-        const int pix0 = mt * BM;
-        const int n_img = pix0 / sg.HoWo;
-        const int rem = pix0 - n_img * sg.HoWo;
-        const int p = rem / sg.Wo;
-        const int q = rem - p * sg.Wo;
-        const int cw = q * sg.stride - sg.pad;
-        const int ch = p * sg.stride - sg.pad;
-        const uint32_t tx = A_BYTES + sg.bn * (BK * 2);
-        for (int tap = 0; tap < sg.taps; ++tap) {
-          const int r = tap / sg.S;
-          const int s = tap - r * sg.S;
-          for (int kc = 0; kc < sg.cin_chunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], tx);
-            tma_load_im2col_4d(&sg.tmA, &full[stage], sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
-                               (uint16_t)r);
-            tma_load_3d(&sg.tmB, &full[stage], sB + stage * b_stride, kc * BK, nt * sg.bn, tap);
-            if (++stage == nst) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-        if (sg.res_mma) {
-          for (int j = 0; j < sg.bn / 64; ++j) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], A_BYTES);
-            tma_load_2d(&sg.tmRes, &full[stage], sA + stage * A_BYTES, nt * sg.bn + 64 * j, pix0);
-            if (++stage == nst) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
+    if (elect_one()) conv_producer(P, S);
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const ConvSegDev& sg = P->seg[find_seg(P, tile)];
-        const int kiters = sg.taps * sg.cin_chunks;
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        const uint32_t idesc = make_idesc_bf16(BM, sg.bn, 0, 0);
-        for (int ki = 0; ki < kiters; ++ki) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_base = smem_u32(sB + stage * b_stride);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = make_sdesc(a_base + k * 32, 16, 1024);
-            const uint64_t bd = make_sdesc(b_base + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (ki | k) != 0);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == nst) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        if (sg.res_mma) {
-          const uint32_t idesc64 = make_idesc_bf16(BM, 64, 0, 0);
-          const uint32_t i_base = smem_u32(sIdent);
-          for (int j = 0; j < sg.bn / 64; ++j) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem + 64 * j, make_sdesc(a_base + k * 32, 16, 1024), make_sdesc(i_base + k * 32, 16, 1024),
-                        idesc64, 1);
-            umma_commit(&empty[stage]);
-            if (++stage == nst) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-        umma_commit(&tfull[acc]);
-      }
-    }
+    if (elect_one()) conv_mma(P, S, tmem_base);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (2 warpgroups x 4 warps)
     const int ew = warp & 3;          // TMEM lane quadrant this warp may read
@@ -580,23 +635,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
           const bool relu_all = relu_nch >= tile_c0 + bn;
           const uint32_t slab_row = smem_u32(slab_base) + et * 128;
           const uint32_t sw = et & 7;
-#define DSLB_FAST(S_, A_, R_) fast_chunks<S_, A_, R_>(taddr, cbeg, cend, r0, slab_row, sw, shp)
-          const int variant = (shp ? 6 : 0) + aux_here * 2 + (relu_all ? 1 : 0);
-          switch (variant) {
-            case 0: DSLB_FAST(false, 0, false); break;
-            case 1: DSLB_FAST(false, 0, true); break;
-            case 2: DSLB_FAST(false, 1, false); break;
-            case 3: DSLB_FAST(false, 1, true); break;
-            case 4: DSLB_FAST(false, 2, false); break;
-            case 5: DSLB_FAST(false, 2, true); break;
-            case 6: DSLB_FAST(true, 0, false); break;
-            case 7: DSLB_FAST(true, 0, true); break;
-            case 8: DSLB_FAST(true, 1, false); break;
-            case 9: DSLB_FAST(true, 1, true); break;
-            case 10: DSLB_FAST(true, 2, false); break;
-            default: DSLB_FAST(true, 2, true); break;
-          }
-#undef DSLB_FAST
+          fast_dispatch<true>((shp ? 6 : 0) + aux_here * 2 + (relu_all ? 1 : 0), taddr, cbeg, cend, r0, slab_row, sw, shp);
         } else
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t rr[16];
@@ -764,6 +803,98 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   }
 }
 
+// Fast kernel for plans whose every tile takes the lean epilogue (bf16 staged output, full chunks, no scale / GroupNorm
+// statistics, residual on the tensor core, mask by TMA) and whose tiles are short and wide (<= 16 k-iterations, up to 256
+// columns): SIXTEEN epilogue warps = four warpgroups, each owning one 64-channel slab of the tile and one staging slab.
+// The 8-warp epilogue of the general kernel is issue / latency bound on such tiles (2 warps per scheduler); with 4 per
+// scheduler the per-tile epilogue time halves and the store / mask-load latency of one group hides behind the others.
+__global__ void __launch_bounds__(640, 1) conv_igemm_fast4_kernel(const __grid_constant__ ConvParamsDev PP) {
+  const ConvParamsDev* P = &PP;
+  extern __shared__ uint8_t smem_raw[];
+  const ConvSmem S = conv_carve(P, smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = conv_prologue(P, S, 16);
+  const int total = P->total_tiles;
+
+  if (warp == 0) {
+    if (elect_one()) conv_producer(P, S);
+  } else if (warp == 1) {
+    if (elect_one()) conv_mma(P, S, tmem_base);
+  } else if (warp >= 4) {
+    const int ew = warp & 3;          // TMEM lane quadrant
+    const int eg = (warp - 4) >> 2;   // warpgroup 0..3: channels [64 eg, 64 eg + 64) of the tile
+    const int et = ew * 32 + lane;
+    const bool leader = (ew == 0 && lane == 0);
+    uint8_t* const slab = S.sOut + eg * (BM * 128);
+    const uint32_t slab_row = smem_u32(slab) + et * 128;
+    const uint32_t sw = et & 7;
+    uint64_t* const auxbar = &S.auxfull[eg];
+    uint32_t aux_par = 0;
+    // (leader) queue the mask tile of work item `tile_n` into this group's slab; the slab must be free
+    auto aux_issue = [&](int tile_n) {
+      if (tile_n >= total) return;
+      const ConvSegDev& s2 = P->seg[find_seg(P, tile_n)];
+      if (!s2.aux_kind || eg * 64 >= s2.bn) return;
+      const int tl2 = tile_n - s2.tile_begin;
+      const int nt2 = tl2 / s2.m_tiles;
+      const int mt2 = tl2 - nt2 * s2.m_tiles;
+      mbar_expect_tx(auxbar, BM * 128);
+      tma_load_2d(&s2.tmAux, auxbar, slab, nt2 * s2.bn + eg * 64, mt2 * BM);
+    };
+    if (leader) aux_issue(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+      const int tl = tile - sg.tile_begin;
+      const int nt = tl / sg.m_tiles;
+      const int mt = tl - nt * sg.m_tiles;
+      const int acc = it & 1;
+      const int bn = sg.bn;
+      const int cbeg = eg * 64, cend = min(cbeg + 64, bn);
+      const bool active = cbeg < bn;
+      const int aux_here = active ? sg.aux_kind : 0;
+      // slab hand-over: the leader drained the previous store before it queued the mask tile / reached this barrier
+      if (aux_here) {
+        mbar_wait(auxbar, aux_par);
+        aux_par ^= 1;
+      } else {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+      }
+      mbar_wait(&S.tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (active) {
+        const int tile_c0 = nt * bn;
+        const float* __restrict__ shp = sg.shift ? sg.shift + tile_c0 : nullptr;
+        const bool relu_all = sg.relu_nch >= tile_c0 + bn;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256;
+        fast_dispatch<false>((shp ? 6 : 0) + aux_here * 2 + (relu_all ? 1 : 0), taddr, cbeg, cend, 0, slab_row, sw, shp);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tempty[acc]);
+      if (active) fence_proxy_async();
+      asm volatile("bar.sync %0, 128;" ::"r"(5 + eg) : "memory");
+      if (leader) {
+        if (active) {
+          tma_store_2d(&sg.tmY, slab, nt * bn + cbeg, mt * BM);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        aux_issue(tile + gridDim.x);
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace dslb
 
 // ============================================================================================ host side
@@ -773,6 +904,7 @@ struct dslb_conv_plan {
   ConvParamsDev* dev = nullptr;  // HOST copy, passed by value at launch
   int total_tiles = 0;
   double flops = 0.0;
+  int fast4 = 0;  // launch conv_igemm_fast4_kernel (16 epilogue warps)
 };
 
 static int pick_bn(int cout_pad) {
@@ -963,9 +1095,23 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     const ConvSegDev& d = h->seg[i];
     if (!d.staged || (long long)d.taps * d.cin_chunks * d.bn >= 16 * 256) short_tiles = false;
   }
+  // every tile lean-epilogue eligible, <= 16 k-iterations, and wide enough to occupy at least 3 of the 4 groups?
+  bool fast4 = getenv("DSLB_NO_FAST4") == nullptr;
+  int bn_widest = 0;
+  for (int i = 0; i < nseg && fast4; ++i) {
+    const ConvSegDev& d = h->seg[i];
+    const dslb_conv_seg_t& s = segs[i];
+    const bool relu_ok = d.relu_nch <= 0 || d.relu_nch >= d.cout;
+    const bool mask_ok = s.relu_mask == nullptr || d.aux_kind == 2;
+    if (!d.staged || d.stats || d.scale || d.residual || s.cout_pad != s.Cout || d.cout % d.bn != 0 || !relu_ok ||
+        !mask_ok || d.taps * d.cin_chunks > 16 || d.bn > 256)
+      fast4 = false;
+    bn_widest = d.bn > bn_widest ? d.bn : bn_widest;
+  }
+  if (bn_widest < 192) fast4 = false;
   h->any_aux = any_aux ? 1 : 0;
   h->has_ident = any_ident ? 1 : 0;
-  h->nbuf = (any_aux || any_ident || short_tiles) ? 2 : 1;
+  h->nbuf = (any_aux || any_ident || short_tiles || fast4) ? 2 : 1;
   {
     int bn_max = 16;
     for (int i = 0; i < nseg; ++i) bn_max = h->seg[i].bn > bn_max ? h->seg[i].bn : bn_max;
@@ -986,10 +1132,13 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   plan->dev = h;
   plan->total_tiles = tiles;
   plan->flops = flops;
+  plan->fast4 = fast4 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     DSLB_CHECK_CUDA(
         cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    DSLB_CHECK_CUDA(
+        cudaFuncSetAttribute(conv_igemm_fast4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     attr_set = true;
   }
   *out = plan;
@@ -999,7 +1148,10 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
 extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
   const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
-  conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
+  if (plan->fast4)
+    conv_igemm_fast4_kernel<<<grid, 640, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
+  else
+    conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }
