@@ -1,9 +1,16 @@
+#include <stdlib.h>
 #include "common.h"
 
 #include <mutex>
 #include <string.h>
 
 namespace dslb {
+
+bool pdl_enabled() {
+  static const bool on = getenv("DSLB_NO_PDL") == nullptr;
+  return on;
+}
+
 
 static thread_local char g_err[512] = "";
 

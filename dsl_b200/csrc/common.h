@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/dslb.h"
 
 namespace dslb {
@@ -41,5 +43,26 @@ int encode_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, i
                        int pad, int pixels);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// true unless DSLB_NO_PDL is set: launch the tensor-core kernels with programmatic stream serialization
+bool pdl_enabled();
+
+// Launch `kernel` so that it may begin (up to its griddepcontrol.wait) before the previous kernel of the stream has
+// finished. The kernel must call pdl_wait() before touching anything a predecessor wrote.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace dslb

@@ -354,6 +354,7 @@ __device__ __forceinline__ ConvSmem conv_carve(const ConvParamsDev* P, uint8_t* 
 __device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const ConvSmem& S, int epi_warps) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel of the stream may set itself up behind this one
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&S.full[i], 1);
@@ -386,6 +387,7 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const 
     }
     fence_proxy_async();
   }
+  pdl_wait();  // everything above overlapped the predecessor's tail; from here on its outputs are read
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1149,9 +1151,9 @@ extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
   const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
   if (plan->fast4)
-    conv_igemm_fast4_kernel<<<grid, 640, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
+    DSLB_CHECK_CUDA(launch_pdl(conv_igemm_fast4_kernel, dim3(grid), dim3(640), CONV_SMEM, (cudaStream_t)stream, *plan->dev));
   else
-    conv_igemm_kernel<<<grid, 384, CONV_SMEM, (cudaStream_t)stream>>>(*plan->dev);
+    DSLB_CHECK_CUDA(launch_pdl(conv_igemm_kernel, dim3(grid), dim3(384), CONV_SMEM, (cudaStream_t)stream, *plan->dev));
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < WG_STAGES; ++i) {
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     tmem_alloc(tmem_slot, WG_TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -330,7 +332,7 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
 extern "C" int dslb_wgrad_plan_run(const dslb_wgrad_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_wgrad_plan_run: null plan");
   const int grid = plan->total_jobs < num_sms() ? plan->total_jobs : num_sms();
-  conv_wgrad_kernel<<<grid, 256, WG_SMEM, (cudaStream_t)stream>>>(*plan->dev);
+  DSLB_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, dim3(grid), dim3(256), WG_SMEM, (cudaStream_t)stream, *plan->dev));
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }
