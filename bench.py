@@ -114,6 +114,25 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic_per_launch():
+    """DRAM bytes per launch of the conv_igemm family (both kernels) from the committed ncu launch list of
+    `tools/profile_step.py` (same workload, `--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`),
+    summarised by tools/launch_summary.py into profiles/r01d_launches_summary.txt. None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r01d_launches_summary.txt")
+    try:
+        n_tot, b_tot = 0, 0.0
+        for line in open(path):
+            if "dslb::conv_igemm" in line:
+                f = line.split()
+                n, mb = int(f[1]), float(f[3])
+                n_tot += n
+                b_tot += n * mb * 1e6
+        return dict(bytes=round(b_tot / n_tot), source="profiles/r01d_launches_summary.txt (ncu dram__bytes_read+write)") \
+            if n_tot else None
+    except OSError:
+        return None
+
+
 def cpu_baseline(sample_hw, depth, steps=1, warmup=0, batch=1):
     """The reference's CPU arithmetic for the step (oracle port) on a bounded sample of the workload."""
     import torch
@@ -242,9 +261,13 @@ def main():
                 f.write(json.dumps(r) + "\n")
     ck = prof["conv_igemm"]
     achieved = ck["flops"] / (ck["ms"] * 1e-3) / 1e12 if ck["ms"] > 0 else 0.0
-    roofline = dict(bound="tensor", kernel="conv_igemm_kernel (fprop + dgrad implicit GEMM, tcgen05)",
+    traffic = ncu_traffic_per_launch()
+    roofline = dict(bound="tensor", kernel="conv_igemm_kernel + conv_igemm_fast4_kernel (fprop + dgrad implicit GEMM, "
+                                           "tcgen05)",
                     achieved=round(achieved, 1), peak=pk["tf_sust"], unit="TFLOP/s",
-                    frac=round(achieved / pk["tf_sust"], 4), traffic=None, peak_source=pk["src"] + " sustained",
+                    frac=round(achieved / pk["tf_sust"], 4), traffic=traffic["bytes"] if traffic else None,
+                    traffic_unit="bytes/launch (DRAM read+write)", traffic_source=traffic["source"] if traffic else None,
+                    peak_source=pk["src"] + " sustained",
                     launches_per_step=ck["n"], avg_launch_us=round(1e3 * ck["ms"] / max(ck["n"], 1), 2),
                     flops_per_step=ck["flops"], share_of_step=round(ck["ms"] / prof["step_ms"], 4),
                     wgrad=dict(achieved=round(prof["conv_wgrad"]["flops"] / max(prof["conv_wgrad"]["ms"], 1e-9) / 1e9,
