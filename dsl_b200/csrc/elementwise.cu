@@ -141,23 +141,29 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     const int q = pix % Wo;
     const int p = (pix / Wo) % Ho;
     const int n = pix / ((long long)Wo * Ho);
-    float m[8];
+    // all nine taps are loaded first (independent requests in flight), padding taps read -inf; max is exact in bf16,
+    // so the reduction runs on packed bf16x2 values
+    uint4 u[9];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
     for (int r = 0; r < 3; ++r) {
       const int h = p * 2 - 1 + r;
-      if (h < 0 || h >= H) continue;
+#pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int w = q * 2 - 1 + s;
-        if (w < 0 || w >= W) continue;
-        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + c8 * 8);
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+        const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+        u[r * 3 + s] = ok ? __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + c8 * 8))
+                          : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
       }
     }
-    *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = pack8(m);
+    uint4 m = u[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+      __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&m);
+      const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = __hmax2(a[e], b[e]);
+    }
+    *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = m;
   }
 }
 

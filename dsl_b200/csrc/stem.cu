@@ -7,9 +7,11 @@
 // TMEM, double-buffered so the MMA of tile i overlaps the epilogue of tile i-1 and the gather of tile i+1).
 //   pre-pass   NCHW fp32 -> NHWC bf16 with 4 channels per pixel (8 bytes), so a patch row is a plain byte range
 //              that cp.async moves without touching registers (zero-fill outside the image = the conv padding).
-//   K layout   k' = r*32 + s*4 + c  (8 taps x 4 channels per filter row, K = 224 -> 256): the 32 values of (pixel q,
-//              filter row r) are the 64 CONTIGUOUS bytes patch[r][2q .. 2q+8), so an A row is 28 aligned sixteen-byte
-//              chunks copied verbatim; the pad tap / pad channel read real (finite) data and meet zero weights.
+//   K layout   k' = r*32 + s'*4 + c  (8 tap slots x 4 channels per filter row, K = 224 -> 256; slot s' = 0 is a pad tap,
+//              slot s' = s + 1 carries filter tap s): the patch starts one pixel early (at an EVEN image column, so two
+//              pixels move per 16-byte cp.async), and the 32 values of (pixel q, filter row r) are the 64 CONTIGUOUS
+//              bytes patch[r][2q .. 2q+8): an A row is 28 aligned sixteen-byte chunks copied verbatim; the pad tap /
+//              pad channel read real (finite) data and meet zero weights.
 //   B operand  built in shared memory by the kernel itself from the fp32 OIHW master weight x BN scale.
 #include "common.h"
 #include "ptx.cuh"
@@ -38,11 +40,12 @@ constexpr int ST_KC = 4;                   // K = 7 rows x 32 (8 taps x 4 ch) = 
 constexpr int ST_A_BYTES = ST_KC * 128 * 128;
 constexpr int ST_B_BYTES = ST_KC * 64 * 128;
 constexpr int ST_PATCH_BYTES = 7 * ST_ROWB;
-constexpr int ST_SMEM = 1024 + 2 * ST_A_BYTES + ST_B_BYTES + 2 * ST_PATCH_BYTES + 64 * 4 + 64;
+constexpr int ST_NPATCH = 3;               // patch ring: tiles i+1 and i+2 are in flight while tile i is consumed
+constexpr int ST_SMEM = 1024 + 2 * ST_A_BYTES + ST_B_BYTES + ST_NPATCH * ST_PATCH_BYTES + 64 * 4 + 64;
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t n = valid ? 8u : 0u;  // src-size 0 -> the 8 bytes are zero-filled (conv padding)
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;  // src-size 0 -> the 16 bytes (two pixels) are zero-filled (conv padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 
 // K layout k' = r*32 + s*4 + c (s = 0..7, c = 0..3; weights of s = 7 and c = 3 are zero): the 32 values of (pixel q,
@@ -56,8 +59,8 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                              // 2 buffers
   uint8_t* sB = smem + 2 * ST_A_BYTES;
-  uint8_t* sPatch = sB + ST_B_BYTES;               // 2 buffers (cp.async of tile i+1 lands while tile i is consumed)
-  float* sShift = reinterpret_cast<float*>(sPatch + 2 * ST_PATCH_BYTES);
+  uint8_t* sPatch = sB + ST_B_BYTES;               // ST_NPATCH buffers (cp.async ring)
+  float* sShift = reinterpret_cast<float*>(sPatch + ST_NPATCH * ST_PATCH_BYTES);
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(sShift + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
 
@@ -77,9 +80,9 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
   }
   for (int e = tid; e < 64 * 64 * ST_KC; e += ST_NT) {
     const int o = e / (64 * ST_KC), k = e - o * (64 * ST_KC);
-    const int r = k >> 5, s = (k & 31) >> 2, c = k & 3;
+    const int r = k >> 5, s = ((k & 31) >> 2) - 1, c = k & 3;   // tap slot 0 is the pad tap
     float v = 0.f;
-    if (r < 7 && s < 7 && c < 3) {
+    if (r < 7 && s >= 0 && c < 3) {
       const float sc = bn_gamma[o] / sqrtf(bn_var[o] + eps);
       v = w[((o * 3 + c) * 7 + r) * 7 + s] * sc;
     }
@@ -103,29 +106,31 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
 
-  // asynchronous patch load: 7 rows x 264 pixels x 8 bytes, one cp.async per pixel, zero-filled outside the image.
-  // Element e = tid + ST_NT * i of the patch <-> (row r, pixel cx): tile independent, computed once.
-  constexpr int ST_LD = (7 * ST_PW + ST_NT - 1) / ST_NT;
+  // asynchronous patch load: 7 rows x 132 pixel PAIRS x 16 bytes, one cp.async per pair, zero-filled outside the image
+  // (the patch starts at an even column and W is even, so a pair is never half inside).
+  // Element e = tid + ST_NT * i of the patch <-> (row r, pair cp): tile independent, computed once.
+  constexpr int ST_PAIRS = ST_PW / 2;
+  constexpr int ST_LD = (7 * ST_PAIRS + ST_NT - 1) / ST_NT;
   int p_r[ST_LD], p_cx[ST_LD];
 #pragma unroll
   for (int i = 0; i < ST_LD; ++i) {
     const int e = tid + i * ST_NT;
-    p_r[i] = e < 7 * ST_PW ? e / ST_PW : -1;
-    p_cx[i] = e % ST_PW;
+    p_r[i] = e < 7 * ST_PAIRS ? e / ST_PAIRS : -1;
+    p_cx[i] = 2 * (e % ST_PAIRS);
   }
   auto load_patch = [&](int tile, int pb) {
     const int qs = tile % qsegs;
     const int np = tile / qsegs;       // n * Ho + p
     const int p = np % Ho, n = np / Ho;
-    const int h0 = 2 * p - 3, w0 = 2 * (qs * 128) - 3;
+    const int h0 = 2 * p - 3, w0 = 2 * (qs * 128) - 4;
     uint8_t* dst = sPatch + pb * ST_PATCH_BYTES;
     const uint2* img_n = x4 + (long long)n * H * W;
 #pragma unroll
     for (int i = 0; i < ST_LD; ++i) {
       if (p_r[i] >= 0) {
         const int h = h0 + p_r[i], ww = w0 + p_cx[i];
-        const bool ok = h >= 0 && h < H && ww >= 0 && ww < W;
-        cp_async8(dst + p_r[i] * ST_ROWB + p_cx[i] * 8, img_n + (ok ? h * W + ww : 0), ok);
+        const bool ok = h >= 0 && h < H && ww >= 0 && ww + 1 < W;
+        cp_async16(dst + p_r[i] * ST_ROWB + p_cx[i] * 8, img_n + (ok ? h * W + ww : 0), ok);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -167,22 +172,22 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
   };
 
   int tile = blockIdx.x;
-  if (tile < ntiles) load_patch(tile, 0);
+  // every thread commits exactly one group per tile slot (possibly empty), so wait_group counts stay uniform
+  if (tile < ntiles) load_patch(tile, 0); else asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tile + (int)gridDim.x < ntiles) load_patch(tile + gridDim.x, 1); else asm volatile("cp.async.commit_group;" ::: "memory");
   int it = 0;
   int prev_tile = -1;
   for (; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    if (next < ntiles) {
-      load_patch(next, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's patch has landed (the next one may be in flight)
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int pbuf = it % ST_NPATCH;
+    const int next2 = tile + 2 * gridDim.x;
+    if (next2 < ntiles) load_patch(next2, (it + 2) % ST_NPATCH);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 2;" ::: "memory");  // this tile's patch has landed (two younger groups may be in flight)
     __syncthreads();  // ... for every thread's copies
     // ---- A tile: 128 rows x 28 sixteen-byte chunks copied from the patch (LDS.128 -> STS.128, conflict-free)
     uint8_t* a = sA + buf * ST_A_BYTES;
-    const uint8_t* pt = sPatch + buf * ST_PATCH_BYTES;
+    const uint8_t* pt = sPatch + pbuf * ST_PATCH_BYTES;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const uint4 v = *reinterpret_cast<const uint4*>(pt + j * ST_ROWB + a_src0);

@@ -295,8 +295,8 @@ class FCOSNet:
         self.fwd_ops.append(fn)
 
     def add_bwd(self, fn, side=False, tag=None, wait=None):
-        """Append a backward op. side=True: independent of the dgrad critical path (weight gradients) — may run on a
-        second stream; `tag` names its completion event, `wait` names a side op the main stream must have finished
+        """Append a backward op. side=True: independent of the dgrad critical path (weight / bias / GroupNorm-parameter
+        gradients: they only read buffers no later op of the step rewrites) — may run on a second stream; `tag` names its completion event, `wait` names a side op the main stream must have finished
         before this op runs (buffer re-use), "__all__" = every side op issued so far."""
         self.bwd_ops.append(fn)
         self.bwd_meta.append((side, tag, wait))
@@ -651,8 +651,8 @@ class FCOSNet:
         self.plan_wgrad(wsegs, "head.predictors.wgrad")
         g_cls_b = self.grad_view("bbox_head.conv_cls.bias")
         for l, (h, w) in enumerate(self.psize):
-            self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C))
-            self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5))
+            self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C), side=True, tag="colsum")
+            self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5), side=True, tag="colsum")
         dsegs = []
         for l, (h, w) in enumerate(self.psize):
             dsegs.append(self.cls_w.dseg(self.dcls[l], self.dz["cls"][l], B, h, w, h, w))
@@ -677,7 +677,8 @@ class FCOSNet:
                 # dgamma / dbeta: sum over levels and images of the per-(n,c) sums
                 red = self.gn_red[bi_, i].reshape(nl * B, 256, 2)
                 self.add_bwd(self.ew("dslb_gn_bwd_params", red, self.grad_view(f"bbox_head.{br}_convs.{i}.gn.weight"),
-                                     self.grad_view(f"bbox_head.{br}_convs.{i}.gn.bias"), nl * B, 256))
+                                     self.grad_view(f"bbox_head.{br}_convs.{i}.gn.bias"), nl * B, 256),
+                             side=True, tag="gn_params")
             wsegs = []
             for br in br_names:
                 for l, (h, w) in enumerate(self.psize):
@@ -729,7 +730,7 @@ class FCOSNet:
         # P7 = conv_s2(relu(P6)); P6 = conv_s2(P5)
         self.tmp6 = self.buf(B, h6, w6, 256)
         self.plan_wgrad([self.fpnc[4].wseg(self.r6, self.dp[4], B, h6, w6)], "fpn.p7.wgrad")
-        self.add_bwd(self.ew("dslb_colsum", self.dp[4], gb(4), B * h7 * w7, 256, 256))
+        self.add_bwd(self.ew("dslb_colsum", self.dp[4], gb(4), B * h7 * w7, 256, 256), side=True, tag="colsum")
         # dgrad of the two stride-2 3x3 convs: zero-upsample dY, then a stride-1 tensor-core dgrad
         self.up7 = self.buf(B, h6, w6, 256)
         self.up6 = self.buf(B, h5, w5, 256)
@@ -738,7 +739,7 @@ class FCOSNet:
                       "fpn.p7.dgrad")
         self.add_bwd(self.ew("dslb_relu_family", self.dp[3], self.tmp6, self.dp[3], self.tmp6.numel(), 2))
         self.plan_wgrad([self.fpnc[3].wseg(self.p[2], self.dp[3], B, h5, w5)], "fpn.p6.wgrad")
-        self.add_bwd(self.ew("dslb_colsum", self.dp[3], gb(3), B * h6 * w6, 256, 256))
+        self.add_bwd(self.ew("dslb_colsum", self.dp[3], gb(3), B * h6 * w6, 256, 256), side=True, tag="colsum")
         self.add_bwd(self.ew("dslb_zero_upsample2", self.dp[3], self.up6, B, h6, w6, h5, w5, 256))
         self.plan_bwd([self.fpnc[3].dseg_upsampled(self.up6, self.dp[2], B, h5, w5, residual=self.dp[2])],
                       "fpn.p6.dgrad")
@@ -746,7 +747,7 @@ class FCOSNet:
         self.plan_wgrad([self.fpnc[i].wseg(self.lm[i], self.dp[i], B, cs[i][1], cs[i][2]) for i in range(3)],
                         "fpn.out.wgrad")
         for i in range(3):
-            self.add_bwd(self.ew("dslb_colsum", self.dp[i], gb(i), B * cs[i][1] * cs[i][2], 256, 256))
+            self.add_bwd(self.ew("dslb_colsum", self.dp[i], gb(i), B * cs[i][1] * cs[i][2], 256, 256), side=True, tag="colsum")
         self.dl = [self.buf(B, cs[i][1], cs[i][2], 256) for i in range(3)]
         self.plan_bwd([self.fpnc[i].dseg(self.dp[i], self.dl[i], B, cs[i][1], cs[i][2], cs[i][1], cs[i][2])
                        for i in range(3)], "fpn.out.dgrad")
@@ -759,7 +760,7 @@ class FCOSNet:
                         "fpn.lateral.wgrad")
         for i in range(3):
             self.add_bwd(self.ew("dslb_colsum", self.dl[i], self.grad_view(f"neck.lateral_convs.{i}.conv.bias"),
-                                 B * cs[i][1] * cs[i][2], 256, 256))
+                                 B * cs[i][1] * cs[i][2], 256, 256), side=True, tag="colsum")
         # gradient w.r.t. the stage outputs C3, C4 (unmasked: more consumers follow) and C5 (masked: last consumer)
         self.gc = [self.buf(B, cs[i][1], cs[i][2], cs[i][3]) for i in range(3)]
         segs = []
