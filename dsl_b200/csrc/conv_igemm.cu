@@ -70,6 +70,9 @@ struct alignas(128) ConvParamsDev {
   int nstages;  // operand pipeline depth: as many (A tile + widest B tile of the plan) stages as fit, <= MAX_STAGES
   int b_stride; // bytes between the B tiles of consecutive stages (= widest tile of the plan x 128 B)
   int nbuf;     // staging slabs per epilogue warpgroup: 1, or 2 with TMA-prefetched residual / mask tiles
+  int pair;       // 1: every CTA works on PAIRS of consecutive 128-pixel tiles (same n-tile) that share the B operand:
+                  // a stage holds two A tiles + one B tile, each k-iteration issues MMAs into both TMEM accumulators
+                  // (no double buffering) -> 64 instead of 96 operand bytes per MMA clock for 256-wide tiles
   int has_ident;  // some segment uses res_mma: 8 KiB identity tile after the staging slabs (3-stage layout only)
   int any_aux;  // some segment brings its residual / mask tiles in by TMA (nbuf == 2); with nbuf == 2 and no aux the
                 // second slab double-buffers the TMA stores instead
@@ -324,7 +327,7 @@ struct ConvSmem {
   uint64_t *full, *empty, *tfull, *tempty, *auxfull;
   uint32_t* tmem_slot;
   float* sStat;
-  int nst, b_stride;
+  int nst, a_stride, b_stride;
 };
 
 __device__ __forceinline__ ConvSmem conv_carve(const ConvParamsDev* P, uint8_t* smem_raw) {
@@ -335,9 +338,10 @@ __device__ __forceinline__ ConvSmem conv_carve(const ConvParamsDev* P, uint8_t* 
   ConvSmem S;
   S.nst = P->nstages;
   S.b_stride = P->b_stride;
+  S.a_stride = P->pair ? 2 * A_BYTES : A_BYTES;
   S.sA = smem;
-  S.sB = smem + S.nst * A_BYTES;
-  S.sOut = smem + S.nst * (A_BYTES + S.b_stride);
+  S.sB = smem + S.nst * S.a_stride;
+  S.sOut = smem + S.nst * (S.a_stride + S.b_stride);
   S.sIdent = S.sOut + P->nbuf * OUT_BYTES;  // [64][64] bf16 identity, K-major, 128B swizzle (res_mma plans)
   uint8_t* sBar = S.sIdent + (P->has_ident ? IDENT_BYTES : 0);
   S.full = reinterpret_cast<uint64_t*>(sBar);
@@ -397,29 +401,35 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const 
 // ------------------------------------------------------------------ TMA producer (one elected thread of warp 0)
 __device__ __forceinline__ void conv_producer(const ConvParamsDev* P, const ConvSmem& S) {
   const int total = P->total_tiles, nst = S.nst;
+  const int nsub = P->pair ? 2 : 1;   // 128-pixel tiles per work item
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  for (int tile = blockIdx.x * nsub; tile < total; tile += gridDim.x * nsub) {
     const ConvSegDev& sg = P->seg[find_seg(P, tile)];
     const int tl = tile - sg.tile_begin;
     const int nt = tl / sg.m_tiles;
     const int mt = tl - nt * sg.m_tiles;
-    const int pix0 = mt * BM;
-    const int n_img = pix0 / sg.HoWo;
-    const int rem = pix0 - n_img * sg.HoWo;
-    const int p = rem / sg.Wo;
-    const int q = rem - p * sg.Wo;
-    const int cw = q * sg.stride - sg.pad;
-    const int ch = p * sg.stride - sg.pad;
-    const uint32_t tx = A_BYTES + sg.bn * (BK * 2);
+    int n_img[2], cw[2], ch[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pix0 = (mt + h) * BM;   // a padding tile (pix0 >= npix) reads out-of-bounds images: zero fill
+      n_img[h] = pix0 / sg.HoWo;
+      const int rem = pix0 - n_img[h] * sg.HoWo;
+      const int p = rem / sg.Wo;
+      const int q = rem - p * sg.Wo;
+      cw[h] = q * sg.stride - sg.pad;
+      ch[h] = p * sg.stride - sg.pad;
+    }
+    const uint32_t tx = nsub * A_BYTES + sg.bn * (BK * 2);
     for (int tap = 0; tap < sg.taps; ++tap) {
       const int r = tap / sg.S;
       const int s = tap - r * sg.S;
       for (int kc = 0; kc < sg.cin_chunks; ++kc) {
         mbar_wait(&S.empty[stage], phase ^ 1);
         mbar_expect_tx(&S.full[stage], tx);
-        tma_load_im2col_4d(&sg.tmA, &S.full[stage], S.sA + stage * A_BYTES, kc * BK, cw, ch, n_img, (uint16_t)s,
-                           (uint16_t)r);
+        for (int h = 0; h < nsub; ++h)
+          tma_load_im2col_4d(&sg.tmA, &S.full[stage], S.sA + stage * S.a_stride + h * A_BYTES, kc * BK, cw[h], ch[h],
+                             n_img[h], (uint16_t)s, (uint16_t)r);
         tma_load_3d(&sg.tmB, &S.full[stage], S.sB + stage * S.b_stride, kc * BK, nt * sg.bn, tap);
         if (++stage == nst) {
           stage = 0;
@@ -430,8 +440,10 @@ __device__ __forceinline__ void conv_producer(const ConvParamsDev* P, const Conv
     if (sg.res_mma) {
       for (int j = 0; j < sg.bn / 64; ++j) {
         mbar_wait(&S.empty[stage], phase ^ 1);
-        mbar_expect_tx(&S.full[stage], A_BYTES);
-        tma_load_2d(&sg.tmRes, &S.full[stage], S.sA + stage * A_BYTES, nt * sg.bn + 64 * j, pix0);
+        mbar_expect_tx(&S.full[stage], nsub * A_BYTES);
+        for (int h = 0; h < nsub; ++h)
+          tma_load_2d(&sg.tmRes, &S.full[stage], S.sA + stage * S.a_stride + h * A_BYTES, nt * sg.bn + 64 * j,
+                      (mt + h) * BM);
         if (++stage == nst) {
           stage = 0;
           phase ^= 1;
@@ -444,27 +456,34 @@ __device__ __forceinline__ void conv_producer(const ConvParamsDev* P, const Conv
 // ------------------------------------------------------------------ MMA issuer (one elected thread of warp 1)
 __device__ __forceinline__ void conv_mma(const ConvParamsDev* P, const ConvSmem& S, uint32_t tmem_base) {
   const int total = P->total_tiles, nst = S.nst;
+  const int nsub = P->pair ? 2 : 1;
   int stage = 0;
   uint32_t phase = 0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+  int it = 0;   // work items done by this CTA
+  for (int tile = blockIdx.x * nsub; tile < total; tile += gridDim.x * nsub, ++it) {
     const ConvSegDev& sg = P->seg[find_seg(P, tile)];
     const int kiters = sg.taps * sg.cin_chunks;
-    const int acc = it & 1;
-    mbar_wait(&S.tempty[acc], ((it >> 1) & 1) ^ 1);
+    // single mode: accumulators alternate per tile (the epilogue of tile i overlaps the MMAs of tile i+1);
+    // pair mode: sub-tile h owns accumulator h, both must have been drained
+    const int acc0 = nsub == 2 ? 0 : (it & 1);
+    const uint32_t par = nsub == 2 ? ((it & 1) ^ 1) : (((it >> 1) & 1) ^ 1);
+    mbar_wait(&S.tempty[acc0], par);
+    if (nsub == 2) mbar_wait(&S.tempty[1], par);
     tc_fence_after();
-    const uint32_t d_tmem = tmem_base + acc * 256;
+    const uint32_t d_tmem = tmem_base + acc0 * 256;
     const uint32_t idesc = make_idesc_bf16(BM, sg.bn, 0, 0);
     for (int ki = 0; ki < kiters; ++ki) {
       mbar_wait(&S.full[stage], phase);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(S.sA + stage * A_BYTES);
+      const uint32_t a_base = smem_u32(S.sA + stage * S.a_stride);
       const uint32_t b_base = smem_u32(S.sB + stage * S.b_stride);
+      for (int h = 0; h < nsub; ++h) {
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) {
-        const uint64_t ad = make_sdesc(a_base + k * 32, 16, 1024);
-        const uint64_t bd = make_sdesc(b_base + k * 32, 16, 1024);
-        umma_bf16(d_tmem, ad, bd, idesc, (ki | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = make_sdesc(a_base + h * A_BYTES + k * 32, 16, 1024);
+          const uint64_t bd = make_sdesc(b_base + k * 32, 16, 1024);
+          umma_bf16(d_tmem + h * 256, ad, bd, idesc, (ki | k) != 0);
+        }
       }
       umma_commit(&S.empty[stage]);
       if (++stage == nst) {
@@ -478,11 +497,13 @@ __device__ __forceinline__ void conv_mma(const ConvParamsDev* P, const ConvSmem&
       for (int j = 0; j < sg.bn / 64; ++j) {
         mbar_wait(&S.full[stage], phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(S.sA + stage * A_BYTES);
+        const uint32_t a_base = smem_u32(S.sA + stage * S.a_stride);
+        for (int h = 0; h < nsub; ++h) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(d_tmem + 64 * j, make_sdesc(a_base + k * 32, 16, 1024), make_sdesc(i_base + k * 32, 16, 1024),
-                    idesc64, 1);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem + h * 256 + 64 * j, make_sdesc(a_base + h * A_BYTES + k * 32, 16, 1024),
+                      make_sdesc(i_base + k * 32, 16, 1024), idesc64, 1);
+        }
         umma_commit(&S.empty[stage]);
         if (++stage == nst) {
           stage = 0;
@@ -490,7 +511,8 @@ __device__ __forceinline__ void conv_mma(const ConvParamsDev* P, const ConvSmem&
         }
       }
     }
-    umma_commit(&S.tfull[acc]);
+    umma_commit(&S.tfull[acc0]);
+    if (nsub == 2) umma_commit(&S.tfull[1]);
   }
 }
 
@@ -542,7 +564,12 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       tma_load_2d(&s2.tmAux, bar, sOut + (eg * nbuf + buf) * (BM * 128), nt2 * s2.bn + cbeg2, mt2 * BM);
     };
     if (leader && nbuf == 2) aux_issue(blockIdx.x, 0, 0);
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    // pair mode: a work item = two consecutive 128-pixel tiles whose accumulators sit side by side in TMEM; they are
+    // drained one after the other exactly like two tiles of the single mode (accumulator it & 1, same barrier phases)
+    const int nsub = P->pair ? 2 : 1;
+    for (int base = blockIdx.x * nsub; base < total; base += gridDim.x * nsub)
+    for (int hsub = 0; hsub < nsub; ++hsub, ++it) {
+      const int tile = base + hsub;
       const ConvSegDev& sg = P->seg[find_seg(P, tile)];
       const int tl = tile - sg.tile_begin;
       const int nt = tl / sg.m_tiles;
@@ -561,7 +588,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       const int acc = it & 1;
       const int bn = sg.bn;
       const bool staged = sg.staged != 0;
-      const bool do_stats = sg.stats != nullptr;
+      const bool do_stats = sg.stats != nullptr && mt * BM < sg.npix;   // (a pair-mode padding tile has no pixels)
       // all valid pixels of this tile in one image => GroupNorm partial sums reduce per tile
       const int pix_first = mt * BM;
       const int pix_last = min(pix_first + BM, sg.npix) - 1;
@@ -1111,6 +1138,39 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     bn_widest = d.bn > bn_widest ? d.bn : bn_widest;
   }
   if (bn_widest < 192) fast4 = false;
+  // pair mode (two 128-pixel tiles per work item sharing B): compute-heavy plans without TMA-loaded epilogue operands
+  // or identity tile (their smem goes to the 64 KiB stages), whose wave quantisation does not eat the gain
+  bool pair = !fast4 && !any_aux && !any_ident;
+  {
+    const char* e = getenv("DSLB_PAIR");
+    long long tiles1 = 0, tiles2 = 0;
+    for (int i = 0; i < nseg && pair; ++i) {
+      const ConvSegDev& d = h->seg[i];
+      if (d.taps * d.cin_chunks < 18 || d.bn < 128 || d.scatter2) pair = false;
+      tiles1 += (long long)d.m_tiles * d.n_tiles;
+      tiles2 += (long long)((d.m_tiles + 1) / 2) * d.n_tiles;
+    }
+    if (pair) {
+      const int sms = num_sms();
+      const double w1 = (double)((tiles1 + sms - 1) / sms);          // waves of 1 tile-time
+      const double w2 = (double)((tiles2 + sms - 1) / sms) * 2.0;    // waves of 2 tile-times
+      if (w2 * 0.80 > w1) pair = false;                              // assume a pair-mode tile-time is ~0.8x
+    }
+    if (e) pair = pair && e[0] == '1';
+    else pair = false;   // opt-in until validated on the GPU
+  }
+  if (pair) {   // re-number the tiles: every segment gets an even number of 128-pixel row tiles
+    int t = 0;
+    for (int i = 0; i < nseg; ++i) {
+      ConvSegDev& d = h->seg[i];
+      d.m_tiles = (d.m_tiles + 1) & ~1;
+      d.tile_begin = t;
+      t += d.m_tiles * d.n_tiles;
+    }
+    tiles = t;
+    h->total_tiles = tiles;
+  }
+  h->pair = pair ? 1 : 0;
   h->any_aux = any_aux ? 1 : 0;
   h->has_ident = any_ident ? 1 : 0;
   h->nbuf = (any_aux || any_ident || short_tiles || fast4) ? 2 : 1;
@@ -1119,7 +1179,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     for (int i = 0; i < nseg; ++i) bn_max = h->seg[i].bn > bn_max ? h->seg[i].bn : bn_max;
     h->b_stride = ((bn_max * BK * 2 + 1023) / 1024) * 1024;  // tiles stay 1024-byte aligned (128B swizzle atoms)
     const int budget = CONV_SMEM - 1024 - h->nbuf * OUT_BYTES - (any_ident ? IDENT_BYTES : 0) - BAR_BYTES - STAT_BYTES;
-    int nst = budget / (A_BYTES + h->b_stride);
+    int nst = budget / ((pair ? 2 : 1) * A_BYTES + h->b_stride);
     h->nstages = nst > MAX_STAGES ? MAX_STAGES : nst;
   }
   if (!any_aux)
@@ -1149,7 +1209,8 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
 
 extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_conv_plan_run: null plan");
-  const int grid = plan->total_tiles < num_sms() ? plan->total_tiles : num_sms();
+  const int work = plan->dev->pair ? plan->total_tiles / 2 : plan->total_tiles;
+  const int grid = work < num_sms() ? work : num_sms();
   if (plan->fast4)
     DSLB_CHECK_CUDA(launch_pdl(conv_igemm_fast4_kernel, dim3(grid), dim3(640), CONV_SMEM, (cudaStream_t)stream, *plan->dev));
   else

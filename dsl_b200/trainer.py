@@ -67,6 +67,7 @@ class DSLEngine:
         self.s2 = torch.cuda.Stream()   # teacher branch
         self.s3 = torch.cuda.Stream()   # weight gradients of the student backward
         self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
+        self._fork2_ev, self._join2_ev = torch.cuda.Event(), torch.cuda.Event()
         # double-buffered input staging for prefetch_inputs(): H2D of batch i+1 on a copy stream under step i
         self.copy_stream = torch.cuda.Stream()
         self._stage = None
@@ -162,9 +163,25 @@ class DSLEngine:
         k = float(self.ema_keep)
         c_s = float(torch.tensor(1 - k, dtype=torch.float32))  # fp32(1 - keep_rate), as torch's scalar promotion does
         c_t = float(torch.tensor(k, dtype=torch.float32))
-        L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, s), "ema")
-        self.student.repack(everything=False)  # frozen stem / layer1 / BatchNorm operands never change
-        self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
+
+        def teacher_side():
+            L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, L.cur_stream()), "ema")
+            self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
+
+        if self.two_streams:
+            # EMA + teacher operand refresh on the second stream, student operand refresh on this one: both only READ the
+            # student's new weights, and each alone is latency bound rather than bandwidth bound
+            main = torch.cuda.current_stream()
+            self._fork2_ev.record(main)
+            self.s2.wait_event(self._fork2_ev)
+            with torch.cuda.stream(self.s2):
+                teacher_side()
+                self._join2_ev.record(self.s2)
+            self.student.repack(everything=False)  # frozen stem / layer1 / BatchNorm operands never change
+            main.wait_event(self._join2_ev)
+        else:
+            teacher_side()
+            self.student.repack(everything=False)
 
     def _allreduce_counts(self):
         dist_ops.allreduce_sum_(self.student.counts)   # packed (num_pos, sum ctr-targets): one collective
@@ -181,11 +198,21 @@ class DSLEngine:
 
     def _capture(self):
         torch.cuda.synchronize()
+        # The warm-up pass torch's graph capture requires must not count as a training step: every piece of state a step
+        # mutates (weights, momentum, EMA teacher, adathres statistics) is put back afterwards, so the first replay IS
+        # the first step.
+        state = [self.student.store.flat, self.teacher.store.flat, self.mom, self.post.stat_cnt, self.post.stat_cum]
+        saved = [t.clone() for t in state]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream, as torch's graph capture requires
             self._run_eager()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for t, v in zip(state, saved):
+            t.copy_(v)
+        self.student.repack(everything=True)
+        self.teacher.repack(everything=True)
         torch.cuda.synchronize()
         phases = [[self._phase_a, self._phase_b, self._phase_c]] if self.world == 1 else \
             [[self._phase_a], [self._phase_b], [self._phase_c]]

@@ -600,3 +600,57 @@ def test_other_configs_forward_loss_backward(depth, B, H, W):
         if p.region in ("A", "B") and p.kind in ("conv", "gn_w", "gn_b", "bias"):
             o, n = net.store.offsets[p.name]
             assert float(g[o:o + n].abs().sum()) > 0, p.name
+
+
+def test_full_size_graph_step_properties():
+    """BASELINE.json configs[1] at its FULL size (B=4, 800x1344 padded, R50) through the public engine with CUDA graphs:
+    size-independent properties — per-point labels / bbox targets / weights bit-exact against the oracle's
+    get_targets at 89 600 points, losses within 1e-3 of the oracle evaluated on the CUDA head outputs, graph replay
+    deterministic in the integer outputs, teacher weights obey the EMA identity against the recorded student weights,
+    and the teacher's pseudo-label lists are well formed."""
+    from dsl_b200.trainer import DSLEngine
+    from oracle import fcos_oracle as O
+    B, H, W = 4, 800, 1344
+    eng = DSLEngine(B, H, W, depth=50, seed=0, use_graphs=True)
+    rng = np.random.RandomState(5)
+    img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
+    img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
+    gts, labels, ignores = GI.make_gt(300, B, H, W, max_gt=20, max_ignore=5, with_ignore=True)
+    eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+    t_before = eng.teacher.store.flat.clone()
+    losses = {k: float(v) for k, v in eng.step().items()}
+    torch.cuda.synchronize()
+    net = eng.student
+    assert net.npoints == B * 22400
+    # the head outputs in the buffers are those of THIS step's forward (the optimizer ran after the loss)
+    cls = [_nchw(net.cls_out[l], 80) for l in range(5)]
+    box = [_nchw(net.rc_out[l], 4) for l in range(5)]
+    ctr = [_nchw(net.rc_out[l][..., 4:5], 1) for l in range(5)]
+    ref = O.fcos_loss(cls, box, ctr, gts, labels, ignores, loss_weight=3.0, return_aux=True)
+    aux = ref.pop("_aux")
+    lab1 = net.labels.clone()
+    assert torch.equal(lab1.cpu(), aux["labels"]) and torch.equal(net.bbox_targets.cpu(), aux["bbox_targets"])
+    assert torch.equal(net.weights.cpu(), aux["weight"])
+    assert int((lab1 < 80).sum()) > 300                      # center sampling keeps ~0.6 % of the points positive
+    for k, v in ref.items():
+        assert abs(losses[k] - float(v)) <= 1e-3 * abs(float(v)) + 1e-6, (k, losses[k], float(v))
+    # EMA identity on the frozen part (student never changes there): teacher == its old value up to fp32 rounding
+    o, n = net.store.offsets["backbone.layer1.0.conv1.weight"]
+    assert torch.allclose(eng.teacher.store.flat[o:o + n], t_before[o:o + n], rtol=1e-6, atol=0)
+    # ... and on a trainable tensor: T' = 0.01 * S' + 0.99 * T, bit-exact in fp32
+    o, n = net.store.offsets["bbox_head.cls_convs.0.conv.weight"]
+    want = net.store.flat[o:o + n] * torch.tensor(1 - 0.99, dtype=torch.float32) + \
+        t_before[o:o + n] * torch.tensor(0.99, dtype=torch.float32)
+    assert torch.equal(eng.teacher.store.flat[o:o + n], want)
+    # pseudo labels of the teacher branch: offsets monotone, <= 100 detections per image, boxes inside the image
+    go = eng.pl_gt_off.cpu().tolist()
+    io = eng.pl_ig_off.cpu().tolist()
+    assert go[0] == 0 and all(0 <= b - a <= 100 for a, b in zip(go, go[1:])) and all(b >= a for a, b in zip(io, io[1:]))
+    if go[-1]:
+        bx = eng.pl_gt_boxes[:go[-1]].cpu()
+        assert (bx[:, 2] >= bx[:, 0]).all() and (bx[:, 3] >= bx[:, 1]).all() and bx.min() >= 0 and bx[:, 2].max() <= W
+    # a second replay on the same inputs: integer outputs identical (targets do not depend on the weights)
+    eng.step()
+    torch.cuda.synchronize()
+    assert torch.equal(net.labels, lab1)
+    assert all(np.isfinite(float(v)) for v in eng.student.losses().values())
