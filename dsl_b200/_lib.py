@@ -160,6 +160,10 @@ _proto("dslb_pseudo_labels_stats", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, V
 _proto("dslb_sigmoid_focal_loss", I, VP, VP, VP, LL, I, F, F, VP, VP, VP, VP)
 _proto("dslb_giou_loss", I, VP, VP, VP, LL, F, VP, VP, VP, VP)
 _proto("dslb_bce_with_logits", I, VP, VP, VP, LL, VP, VP, VP, VP)
+lib.dslb_view_boxes_workspace_bytes.restype = C.c_size_t
+lib.dslb_view_boxes_workspace_bytes.argtypes = [I]
+_proto("dslb_view_boxes", I, VP, VP, VP, VP, I, I, I, VP, C.c_size_t, VP, VP, VP, VP)
+_proto("dslb_pad_batch", I, VP, VP, VP, I, I, I, I, VP)
 _proto("dslb_adathres_finalize", I, VP, VP, I, D, D, D, D, D, D, VP, VP, VP, VP)
 
 GN_STAT_STRIDE = 32

@@ -1,0 +1,83 @@
+"""Device-side view geometry: carries packed box lists through the box part of the reference's
+Resize -> PatchShuffle -> RandomFlip pipeline steps (mmdet/datasets/pipelines/transforms.py:249-257, 2168-2248, 397-429)
+and assembles zero-padded batches, on libdslb.so. With it the EMA teacher's boxes (original-image coordinates) reach
+the student's strong view without the host data pipeline. CUDA only."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class View(C.Structure):
+    """dslb_view_t"""
+    _fields_ = [("sx", C.c_float), ("sy", C.c_float), ("img_w", C.c_int32), ("img_h", C.c_int32), ("clip", C.c_int32),
+                ("ps_mode", C.c_int32), ("ps_crop", C.c_int32), ("flip", C.c_int32)]
+
+
+PS_MODES = {None: 0, False: 0, "flip": 1, "flop": 2}
+
+
+def view_from_meta(meta, clip=True):
+    """img_metas entry of the reference's Collect (`scale_factor`, `img_shape`, `flip`, `PS`, `PS_mode`, `PS_place`,
+    configs/fcos_semi/*.py:80) -> View. ps_crop = min(int(round(extent * PS_place)), extent) as PatchShuffle computes it."""
+    h, w = int(meta["img_shape"][0]), int(meta["img_shape"][1])
+    sf = meta.get("scale_factor", (1.0, 1.0, 1.0, 1.0))
+    mode = PS_MODES[meta.get("PS_mode")] if meta.get("PS") else 0
+    crop = 0
+    if mode:
+        ext = w if mode == 1 else h
+        crop = min(int(round(ext * float(meta["PS_place"]))), ext)
+    if meta.get("flip") and meta.get("flip_direction", "horizontal") != "horizontal":
+        raise NotImplementedError("dsl_b200.geometry: only horizontal flips (the DSL configs' RandomFlip default)")
+    return View(float(sf[0]), float(sf[1]), w, h, int(bool(clip)), mode, crop, int(bool(meta.get("flip"))))
+
+
+class ViewGeometry:
+    """Buffers + launch for B images and up to `max_boxes` input boxes."""
+
+    def __init__(self, B, max_boxes=1024, device="cuda"):
+        self.B, self.max_in, self.max_out = B, max_boxes, 2 * max_boxes
+        self.dev = torch.device(device)
+        self.views = torch.zeros(B * C.sizeof(View), dtype=torch.uint8, device=self.dev)
+        self._h_views = torch.zeros(B * C.sizeof(View), dtype=torch.uint8).pin_memory()
+        self.ws_bytes = L.lib.dslb_view_boxes_workspace_bytes(max_boxes)
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.out_boxes = torch.zeros(self.max_out, 4, dtype=torch.float32, device=self.dev)
+        self.out_labels = torch.zeros(self.max_out, dtype=torch.int64, device=self.dev)
+        self.out_off = torch.zeros(B + 1, dtype=torch.int32, device=self.dev)
+
+    def set_views(self, views):
+        assert len(views) == self.B
+        arr = (View * self.B)(*views)
+        self._h_views.copy_(torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8))
+        self.views.copy_(self._h_views, non_blocking=True)
+
+    def run(self, boxes, labels, off, out_boxes=None, out_labels=None, out_off=None):
+        """boxes (n,4) fp32 / labels (n,) int64 or None / off (B+1,) int32, all on the device, packed over images."""
+        ob = self.out_boxes if out_boxes is None else out_boxes
+        ol = (self.out_labels if out_labels is None else out_labels) if labels is not None else None
+        oo = self.out_off if out_off is None else out_off
+        assert boxes.shape[0] <= self.max_in
+        L.check(L.lib.dslb_view_boxes(L.ptr(boxes), L.ptr(labels) if labels is not None else None, L.ptr(off),
+                                      L.ptr(self.views), self.B, self.max_in, int(ob.shape[0]), L.ptr(self.ws),
+                                      self.ws_bytes, L.ptr(ob), L.ptr(ol) if ol is not None else None, L.ptr(oo),
+                                      L.cur_stream()), "view_boxes")
+        return ob, ol, oo
+
+
+def pad_batch(imgs, H=None, W=None, size_divisor=32):
+    """Pad(size_divisor) + collate of the reference's loader: list of (C, h_i, w_i) fp32 CUDA tensors -> (B, C, H, W)
+    zero-padded batch (H, W = per-batch maxima rounded up to the divisor unless given)."""
+    B, Cc = len(imgs), int(imgs[0].shape[0])
+    imgs = [i.contiguous().float() for i in imgs]
+    hs, ws = [int(i.shape[1]) for i in imgs], [int(i.shape[2]) for i in imgs]
+    up = lambda v: (v + size_divisor - 1) // size_divisor * size_divisor  # noqa: E731
+    H = up(max(hs)) if H is None else H
+    W = up(max(ws)) if W is None else W
+    dev = imgs[0].device
+    ptrs = torch.tensor([i.data_ptr() for i in imgs], dtype=torch.int64, device=dev)
+    hw = torch.tensor([[h, w] for h, w in zip(hs, ws)], dtype=torch.int32, device=dev)
+    out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
+    L.check(L.lib.dslb_pad_batch(L.ptr(ptrs), L.ptr(hw), L.ptr(out), B, Cc, H, W, L.cur_stream()), "pad_batch")
+    return out

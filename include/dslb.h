@@ -333,6 +333,29 @@ int dslb_adathres_finalize(const int64_t* stat_cnt, const double* stat_cum, int 
                            double* prev_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Device-side view geometry of the data pipeline: the BOX part of Resize -> PatchShuffle -> RandomFlip (horizontal) as
+ * the reference's train pipelines chain them (configs/fcos_semi/*.py:70-92; mmdet/datasets/pipelines/
+ * transforms.py:249-257 _resize_bboxes, :2168-2248 PatchShuffle incl. the split of a box that straddles the cut,
+ * :397-429 bbox_flip), per image, in fp32 exactly like the NumPy float32 expressions. Boxes are packed over images
+ * with offsets off[B+1]; a box can become two, so outputs hold up to 2x the inputs (truncated at max_out).
+ * dslb_pad_batch: zero-padded batch assembly (Pad + collate): out[b] (C,H,W) <- imgs[b] (C,h_b,w_b) top-left.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct dslb_view {
+  float sx, sy;            /* Resize scale_factor (w_scale, h_scale)                                             */
+  int32_t img_w, img_h;    /* img_shape after the resize: clip range, PatchShuffle / flip extent                 */
+  int32_t clip;            /* Resize.bbox_clip_border                                                            */
+  int32_t ps_mode;         /* PatchShuffle: 0 off, 1 'flip' (vertical cut at column ps_crop), 2 'flop' (row)     */
+  int32_t ps_crop;         /* min(int(round(extent * PS_place)), extent); 0 or extent = no-op, as in the reference */
+  int32_t flip;            /* RandomFlip, direction 'horizontal'                                                 */
+} dslb_view_t;
+size_t dslb_view_boxes_workspace_bytes(int max_in);
+int dslb_view_boxes(const float* boxes, const int64_t* labels, const int32_t* off, const dslb_view_t* views_dev, int B,
+                    int max_in, int max_out, void* workspace, size_t ws_bytes, float* out_boxes, int64_t* out_labels,
+                    int32_t* out_off, void* stream);
+int dslb_pad_batch(const float* const* imgs_dev, const int32_t* hw_dev, float* out, int B, int C, int H, int W,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Standalone LOSSES-registry kernels (the training step uses the fused dslb_fcos_loss; these answer configs that build
  * the loss modules by themselves). One pass each: loss_elem (nullable) = weighted element-wise loss, *loss_sum
  * (nullable, fp64, ACCUMULATED: zero it first) += its sum, d* (nullable) = gradient of the weighted element-wise loss

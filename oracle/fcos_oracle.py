@@ -530,3 +530,55 @@ def scale_invariant_input(img, gt_bboxes, gt_bboxes_ignore):
 
 
 _ = math
+
+
+def view_boxes(boxes, labels, sx, sy, img_w, img_h, clip=True, ps_mode=0, ps_crop=0, flip=False):
+    """Box part of Resize._resize_bboxes -> PatchShuffle.__call__ -> RandomFlip.bbox_flip('horizontal')
+    (mmdet/datasets/pipelines/transforms.py:249-257, 2168-2248, 397-429), NumPy float32 arithmetic left to right.
+    ps_mode 0 off / 1 'flip' (vertical cut at column ps_crop) / 2 'flop' (horizontal cut at row ps_crop).
+    Returns (boxes (m,4) float32, labels (m,) int64 or None); a box straddling the cut becomes two."""
+    import numpy as np
+    f = np.float32
+    b = np.asarray(boxes, np.float32).reshape(-1, 4) * np.array([sx, sy, sx, sy], dtype=np.float32)
+    if clip:
+        b[:, 0::2] = np.clip(b[:, 0::2], 0, img_w)
+        b[:, 1::2] = np.clip(b[:, 1::2], 0, img_h)
+    lab = None if labels is None else list(np.asarray(labels).tolist())
+    w, h = f(img_w), f(img_h)
+    active = (ps_mode == 1 and ps_crop not in (0, img_w)) or (ps_mode == 2 and ps_crop not in (0, img_h))
+    if active and len(b):
+        cw = f(ps_crop) if ps_mode == 1 else w
+        chh = f(ps_crop) if ps_mode == 2 else h
+        ob, ol = [], []
+        for i in range(len(b)):
+            x1, y1, x2, y2 = (f(v) for v in b[i])
+            one = f(1)
+            if (x1 - cw + one) * (x2 - cw + one) >= 0 and (y1 - chh + one) * (y2 - chh + one) >= 0:
+                if ps_mode == 1:
+                    if x1 - cw + one < 0:
+                        x1, x2 = x1 + w - cw, x2 + w - cw
+                    if x2 - cw + one > 0:
+                        x1, x2 = x1 - cw, x2 - cw
+                else:
+                    if y1 - chh + one < 0:
+                        y1, y2 = y1 + h - chh, y2 + h - chh
+                    if y2 - chh + one > 0:
+                        y1, y2 = y1 - chh, y2 - chh
+                ob.append([x1, y1, x2, y2])
+                if lab is not None:
+                    ol.append(lab[i])
+            else:
+                if ps_mode == 1:
+                    ob += [[x1 + w - cw, y1, w - one, y2], [f(0), y1, x2 - cw, y2]]
+                else:
+                    ob += [[x1, y1 + h - chh, x2, h - one], [x1, f(0), x2, y2 - chh]]
+                if lab is not None:
+                    ol += [lab[i], lab[i]]
+        b = np.array(ob, dtype=np.float32).reshape(-1, 4)
+        lab = ol if lab is not None else None
+    if flip and len(b):
+        fb = b.copy()
+        fb[:, 0] = w - b[:, 2]
+        fb[:, 2] = w - b[:, 0]
+        b = fb
+    return b, (None if lab is None else np.asarray(lab, np.int64))

@@ -398,6 +398,81 @@ def gen_loss_modules(R):
     np.savez_compressed(os.path.join(OUT, "loss_modules.npz"), **out)
 
 
+def _load_pipeline_classes():
+    """Resize / RandomFlip / PatchShuffle (+ get_bbox_fields) compiled from the reference's own
+    mmdet/datasets/pipelines/transforms.py, without importing the module's heavy dependencies: mmcv is answered by a
+    two-function stub (imcrop with inclusive corners, as mmcv.imcrop), the registry decorator by the identity."""
+    import ast
+    import random
+    import types
+    import cv2
+    path = os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/pipelines/transforms.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name == "get_bbox_fields") or
+            (isinstance(n, ast.ClassDef) and n.name in ("Resize", "RandomFlip", "PatchShuffle"))]
+    mm = types.SimpleNamespace(
+        imcrop=lambda img, b: img[int(b[1]):int(b[3]) + 1, int(b[0]):int(b[2]) + 1].copy(),
+        is_list_of=lambda seq, t: isinstance(seq, list) and all(isinstance(x, t) for x in seq),
+        is_tuple_of=lambda seq, t: isinstance(seq, tuple) and all(isinstance(x, t) for x in seq))
+    reg = types.SimpleNamespace(register_module=lambda *a, **k: (lambda c: c))
+    glb = {"np": np, "random": random, "mmcv": mm, "cv2": cv2, "PIPELINES": reg}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), glb)
+    return glb["Resize"], glb["RandomFlip"], glb["PatchShuffle"]
+
+
+def gen_view_geometry(R):
+    """Boxes through the reference's Resize._resize_bboxes -> PatchShuffle.__call__ -> RandomFlip.bbox_flip (the order of
+    the train pipelines, configs/fcos_semi/*.py:70-92) for a set of views: flip / flop cuts with boxes on either side of,
+    straddling and touching the cut, degenerate cuts (no-op), flips, clipping, empty lists."""
+    import random
+    Resize, RandomFlip, PatchShuffle = _load_pipeline_classes()
+    out = {}
+    rng = np.random.RandomState(202)
+    views = []
+    ncase = 14
+    for k in range(ncase):
+        oh, ow = int(rng.randint(300, 700)), int(rng.randint(300, 900))
+        sx, sy = np.float32(rng.uniform(0.6, 1.9)), np.float32(rng.uniform(0.6, 1.9))
+        h, w = int(round(oh * float(sy))), int(round(ow * float(sx)))
+        n = 0 if k == 5 else int(rng.randint(1, 40))
+        boxes = GI.demo_boxes(rng, n, oh, ow).astype(np.float32) + rng.rand(n, 4).astype(np.float32) if n else \
+            np.zeros((0, 4), np.float32)
+        labels = rng.randint(0, 80, size=n).astype(np.int64)
+        ign = GI.demo_boxes(rng, int(rng.randint(0, 6)), oh, ow).astype(np.float32)
+        ps_mode = [None, "flip", "flop"][k % 3]
+        place = float(rng.uniform(0.0, 1.0)) if k not in (7, 8) else (0.0 if k == 7 else 1.0)   # degenerate cuts
+        flip = bool(k % 2)
+        clip = k != 3
+        res = dict(img=np.zeros((h, w, 3), np.uint8), img_shape=(h, w, 3), gt_bboxes=boxes.copy(), gt_labels=labels.copy(),
+                   gt_bboxes_ignore=ign.copy(), bbox_fields=["gt_bboxes_ignore", "gt_bboxes"],
+                   scale_factor=np.array([sx, sy, sx, sy], dtype=np.float32))
+        rz = Resize.__new__(Resize)
+        rz.bbox_clip_border = clip
+        rz._resize_bboxes(res)
+        crop = 0
+        if ps_mode is not None:
+            ps = PatchShuffle(ratio=1.0, ranges=[place, place], mode=[ps_mode])
+            np.random.seed(k)       # np.random.rand(1) > ratio never holds with ratio 1.0; `seed` only scales a 0 range
+            random.seed(k)
+            res = ps(res)
+            assert res["PS"] and res["PS_mode"] == ps_mode
+            ext = w if ps_mode == "flip" else h
+            crop = min(int(round(ext * res["PS_place"])), ext)
+        if flip:
+            rf = RandomFlip.__new__(RandomFlip)
+            for key in ("gt_bboxes_ignore", "gt_bboxes"):
+                if len(res[key]):
+                    res[key] = rf.bbox_flip(res[key], (h, w, 3), "horizontal")
+        out[f"c{k}_boxes"], out[f"c{k}_labels"], out[f"c{k}_ignore"] = boxes, labels, ign
+        out[f"c{k}_out_boxes"] = np.asarray(res["gt_bboxes"], np.float32).reshape(-1, 4)
+        out[f"c{k}_out_labels"] = np.asarray(res["gt_labels"], np.int64)
+        out[f"c{k}_out_ignore"] = np.asarray(res["gt_bboxes_ignore"], np.float32).reshape(-1, 4)
+        views.append([float(sx), float(sy), w, h, int(clip), {None: 0, "flip": 1, "flop": 2}[ps_mode], crop, int(flip)])
+    out["views"] = np.array(views, dtype=np.float64)
+    out["meta"] = np.array([ncase], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "view_geometry.npz"), **out)
+
+
 def main():
     import sys
     torch.set_num_threads(8)
@@ -415,6 +490,7 @@ def main():
     gen_hook_chain(R)
     gen_adathres_chain(R)
     gen_loss_modules(R)
+    gen_view_geometry(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
