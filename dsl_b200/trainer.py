@@ -255,6 +255,49 @@ class DSLEngine:
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
 
+    def set_inputs_with_pseudo_labels(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore, views, teacher_img=None):
+        """set_inputs() for the reference's labeled + unlabeled batch mix, with the unlabeled part labelled ON THE
+        DEVICE: `gt_*` cover only the first B - tB (labeled) images; the last tB images are the strong views of the
+        images the EMA teacher labelled in its previous pass (self.pl_* = pseudo GT / ignore boxes in original-image
+        coordinates), carried into each strong view by `views` (geometry.View per unlabeled image: Resize scale,
+        PatchShuffle cut, flip). Replaces the reference's JSON round trip (UnlabelPredHook.save_results2file ->
+        SemiCOCODataset -> pipelines) for the transforms geometry.py covers. No host sync."""
+        from .geometry import ViewGeometry
+        assert not self.scale_invariant, "the device-side pseudo-label feed does not build the SI extra image yet"
+        st, tB = self.student, self.teacher.B
+        BL = self.B - tB
+        assert BL >= 0 and len(gt_bboxes) == BL and len(gt_labels) == BL and len(views) == tB
+        assert gt_bboxes_ignore is not None and len(gt_bboxes_ignore) == BL
+        if getattr(self, "_geo", None) is None:
+            self._geo = ViewGeometry(tB, max_boxes=st.max_boxes, device=self.dev)
+            self._geo_off = torch.zeros(tB + 1, dtype=torch.int32, device=self.dev)
+        self._geo.set_views(views)
+        st.img.copy_(student_img, non_blocking=True)
+        if teacher_img is not None:
+            self.teacher.img.copy_(teacher_img, non_blocking=True)
+        # labeled part from the host lists
+        offs, ioffs = [0], [0]
+        for b in gt_bboxes:
+            offs.append(offs[-1] + int(b.shape[0]))
+        for b in gt_bboxes_ignore:
+            ioffs.append(ioffs[-1] + int(b.shape[0]))
+        nL, nI = offs[-1], ioffs[-1]
+        if nL:
+            st.gt_boxes[:nL].copy_(torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(torch.float32), non_blocking=True)
+            st.gt_labels[:nL].copy_(torch.cat([l.reshape(-1) for l in gt_labels]).to(torch.int64), non_blocking=True)
+        if nI:
+            st.ig_boxes[:nI].copy_(torch.cat([b.reshape(-1, 4) for b in gt_bboxes_ignore]).to(torch.float32),
+                                   non_blocking=True)
+        st.gt_off[:BL + 1].copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=True)
+        st.ig_off[:BL + 1].copy_(torch.tensor(ioffs, dtype=torch.int32), non_blocking=True)
+        st.use_ignore = True
+        # unlabeled part: teacher's pseudo GT / ignore lists -> strong views, appended behind the labeled boxes
+        self._geo.run(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, out_boxes=st.gt_boxes[nL:],
+                      out_labels=st.gt_labels[nL:], out_off=self._geo_off)
+        st.gt_off[BL + 1:].copy_(self._geo_off[1:] + nL)
+        self._geo.run(self.pl_ig_boxes, None, self.pl_ig_off, out_boxes=st.ig_boxes[nI:], out_off=self._geo_off)
+        st.ig_off[BL + 1:].copy_(self._geo_off[1:] + nI)
+
     def prefetch_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
         """Asynchronous set_inputs(): the pinned host batch is copied H2D on a separate copy stream into staging
         buffers (so it overlaps the step that is still running); the next step() moves it into the plan's static input

@@ -66,3 +66,49 @@ def test_pad_batch_matches_torch():
     for b, im in enumerate(imgs):
         ref[b, :, :im.shape[1], :im.shape[2]] = im
     assert torch.equal(out, ref)
+
+
+@pytest.mark.gpu
+def test_engine_feeds_teacher_pseudo_labels_through_the_views():
+    """DSLEngine.set_inputs_with_pseudo_labels: labeled lists from the host + the teacher's pseudo GT / ignore lists mapped
+    into the unlabeled images' strong views on the device; the student's target buffers must equal the oracle mapping,
+    and a step on them must run."""
+    from dsl_b200.geometry import View
+    from dsl_b200.trainer import DSLEngine
+    from oracle import fcos_oracle as O
+    from tests.golden import inputs as GI
+    B, tB, H, W = 4, 2, 128, 160
+    eng = DSLEngine(B, H, W, depth=50, seed=0, use_graphs=False, teacher_B=tB)
+    rng = np.random.RandomState(3)
+    # synthetic teacher output in original-image coordinates (random-init weights detect nothing)
+    pl_b = [(GI.demo_boxes(rng, 7, 200, 260) + rng.rand(7, 4)).astype(np.float32),
+            (GI.demo_boxes(rng, 4, 180, 300) + rng.rand(4, 4)).astype(np.float32)]
+    pl_l = [rng.randint(0, 80, size=7).astype(np.int64), rng.randint(0, 80, size=4).astype(np.int64)]
+    pl_i = [np.zeros((0, 4), np.float32), (GI.demo_boxes(rng, 3, 180, 300) + rng.rand(3, 4)).astype(np.float32)]
+    eng.pl_gt_boxes[:11] = torch.from_numpy(np.concatenate(pl_b)).cuda()
+    eng.pl_gt_labels[:11] = torch.from_numpy(np.concatenate(pl_l)).cuda()
+    eng.pl_gt_off.copy_(torch.tensor([0, 7, 11], dtype=torch.int32))
+    eng.pl_ig_boxes[:3] = torch.from_numpy(pl_i[1]).cuda()
+    eng.pl_ig_off.copy_(torch.tensor([0, 0, 3], dtype=torch.int32))
+    views = [View(0.6, 0.62, 156, 124, 1, 1, 70, 1), View(0.5, 0.7, 150, 126, 1, 2, 60, 0)]
+    img = GI.make_tensor(rng, B, 3, H, W, scale=50.0)
+    gts, labels, ignores = GI.make_gt(9, B - tB, H, W, with_ignore=True)
+    eng.set_inputs_with_pseudo_labels(img, gts, labels, ignores, views, teacher_img=img[:tB])
+    torch.cuda.synchronize()
+    st = eng.student
+    go, io = st.gt_off.cpu().tolist(), st.ig_off.cpu().tolist()
+    nL = sum(len(g) for g in gts)
+    assert go[:B - tB + 1] == list(np.concatenate([[0], np.cumsum([len(g) for g in gts])]))
+    for j, v in enumerate(views):
+        kw = dict(sx=np.float32(v.sx), sy=np.float32(v.sy), img_w=v.img_w, img_h=v.img_h, clip=bool(v.clip),
+                  ps_mode=v.ps_mode, ps_crop=v.ps_crop, flip=bool(v.flip))
+        wb, wl = O.view_boxes(pl_b[j], pl_l[j], **kw)
+        a, b = go[B - tB + j], go[B - tB + j + 1]
+        assert a >= nL and np.array_equal(st.gt_boxes[a:b].cpu().numpy(), wb), j
+        assert np.array_equal(st.gt_labels[a:b].cpu().numpy(), wl), j
+        wi, _ = O.view_boxes(pl_i[j], None, **kw)
+        a, b = io[B - tB + j], io[B - tB + j + 1]
+        assert np.array_equal(st.ig_boxes[a:b].cpu().numpy(), wi), j
+    losses = eng.step()
+    torch.cuda.synchronize()
+    assert all(np.isfinite(float(v)) for v in losses.values())
