@@ -21,6 +21,15 @@ def allreduce_mean_(t):
     return t
 
 
+def allreduce_mean_async_(t):
+    """Same as allreduce_mean_ but returns the in-flight work handle (None with one rank): call .wait() before using t."""
+    w = world_size()
+    if w > 1:
+        t.div_(w)
+        return dist.all_reduce(t, async_op=True)
+    return None
+
+
 def allreduce_sum_(t):
     if world_size() > 1:
         dist.all_reduce(t)

@@ -250,9 +250,12 @@ class FCOSNet:
         if train:
             self._build_loss()
             self._alloc_arena()
+            self.bwd_buckets = []   # (index one past the bucket's last backward op, flat grad range lo, hi)
+            self._unpacked = set()
             self._build_head_bwd()
             if parts == "all":
                 self._build_fpn_bwd()
+                self._emit_bucket(("neck.", "bbox_head."), head=True)   # + every bias (region B follows region A)
                 self._build_backbone_bwd()
             self._build_finish_bwd()
         self._build_pack_plans()
@@ -783,6 +786,8 @@ class FCOSNet:
             li, bi = blk["li"], blk["bi"]
             h, w, hin, win, planes = blk["h"], blk["w"], blk["hin"], blk["win"], blk["planes"]
             name = f"layer{li + 1}.{bi}"
+            if idx == stage_last[li] and li == 2:
+                self._emit_bucket(("backbone.layer4.",))   # 60 MB of gradients are final once layer4 is done
             if idx == stage_last[li]:
                 if li == 3:
                     blk["M"] = self.gc[2]  # already masked by the lateral dgrad epilogue
@@ -816,22 +821,48 @@ class FCOSNet:
                 g = self.gc[li - 2]
                 self.plan_bwd([blk["ds"].dseg(M, g, B, h, w, hin, win, residual=g)], name + ".downsample.dgrad")
                 self.plan_bwd([blk["c1"].dseg(blk["da1"], g, B, h, w, hin, win, residual=g)], name + ".conv1.dgrad")
+    def _emit_bucket(self, prefixes, head=False):
+        """Close a gradient bucket: unpack the packed weight gradients of the convs named by `prefixes` (one launch,
+        after every side-stream op issued so far) and record the flat-gradient range that is final from here on, so a
+        data-parallel trainer can start its all-reduce while the rest of the backward still runs."""
+        convs = [c for c in self.convs if c.trainable and c.wname.startswith(prefixes) and c.wname not in self._unpacked]
+        descs = [c.unpack_desc() for c in convs]
+        names = [c.wname for c in convs]
+        if head:
+            descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_reg.weight"), O=4, I=256, R=3, S=3, rows=5,
+                              row_off=0))
+            descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_centerness.weight"), O=1, I=256, R=3, S=3,
+                              rows=5, row_off=4))
+        self._unpacked.update(names)
+        plan = TablePlan(descs, "unpack", "unpack_wgrads")
+        self.unpack_plans = getattr(self, "unpack_plans", []) + [plan]
+        # on the side stream, in order behind the weight / bias gradient launches it reads: the main (dgrad) stream never
+        # stalls at a bucket boundary; backward() joins the two streams at the end of every op range
+        self.add_bwd(plan.run, side=True, tag="unpack")
+        if head:
+            def finish_head_grads():
+                self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
+                self.grad_view("bbox_head.conv_centerness.bias").copy_(self.rc_db[4:5])
+                self.grad.index_copy_(0, self.scale_idx, self.dscale[:len(self.psize)])
+
+            self.add_bwd(finish_head_grads, side=True, tag="finish_head")
+        offs = [self.store.offsets[n] for n in names]
+        lo = min(o for o, _ in offs)
+        hi = max(o + n for o, n in offs)
+        if head:
+            hi = self.store.n_train          # head / neck biases (region B) and the Scale parameters travel with it
+        self.bwd_buckets.append((len(self.bwd_ops), lo, hi))
+
     def _build_finish_bwd(self):
-        # finally: every packed wgrad -> its OIHW gradient view, in ONE launch
-        descs = [c.unpack_desc() for c in self.convs if c.trainable]
-        descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_reg.weight"), O=4, I=256, R=3, S=3, rows=5,
-                          row_off=0))
-        descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_centerness.weight"), O=1, I=256, R=3, S=3,
-                          rows=5, row_off=4))
-        self.unpack_plan = TablePlan(descs, "unpack", "unpack_wgrads")
-        self.add_bwd(self.unpack_plan.run, wait="__all__")
-
-        def finish_head_grads():
-            self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
-            self.grad_view("bbox_head.conv_centerness.bias").copy_(self.rc_db[4:5])
-            self.grad.index_copy_(0, self.scale_idx, self.dscale[:len(self.psize)])
-
-        self.add_bwd(finish_head_grads)
+        # the remaining packed wgrads -> their OIHW gradient views (standalone head: everything, in one launch)
+        if self.parts == "head":
+            self._emit_bucket(("bbox_head.",), head=True)
+            self.bwd_buckets[-1] = (len(self.bwd_ops), 0, self.store.n_train)
+            return
+        self._emit_bucket(("backbone.",))
+        # the buckets must tile the trainable range exactly: [0, layer4) | [layer4, neck) | [neck, n_train)
+        rng = sorted((lo, hi) for _, lo, hi in self.bwd_buckets)
+        assert rng[0][0] == 0 and rng[-1][1] == self.store.n_train and all(a[1] == b[0] for a, b in zip(rng, rng[1:])), rng
 
     # ------------------------------------------------------------------------------------------ run
     def _build_pack_plans(self):
@@ -868,21 +899,27 @@ class FCOSNet:
         for op in self.fwd_ops[self.head_op_start:]:
             op()
 
-    def backward(self, side_stream=None):
-        """Run the backward plan. With `side_stream` the weight-gradient launches (off the dgrad critical path) go to
-        that stream, ordered by events, so they fill the SMs the small deep-layer dgrad grids leave idle."""
+    def backward(self, side_stream=None, start=0, end=None):
+        """Run backward ops [start, end) (default: all). With `side_stream` the weight-gradient launches (off the dgrad
+        critical path) go to that stream, ordered by events, so they fill the SMs the small deep-layer dgrad grids
+        leave idle. A partial range ends with the main stream joined to the side stream (bucket boundaries of
+        `bwd_buckets`: everything in the bucket's gradient range is final when the call returns)."""
+        end = len(self.bwd_ops) if end is None else end
         if side_stream is None:
-            for op in self.bwd_ops:
+            for op in self.bwd_ops[start:end]:
                 op()
             return
         main = torch.cuda.current_stream()
         if not hasattr(self, "_bwd_events"):
             self._bwd_events = [(torch.cuda.Event(), torch.cuda.Event()) if m[0] else None for m in self.bwd_meta]
-        done = {}
-        last = None
-        for op, (side, tag, wait), evs in zip(self.bwd_ops, self.bwd_meta, self._bwd_events):
+        # every earlier range ended joined to the side stream, so no event of it needs (or, under graph capture, may) be
+        # waited on again
+        self._bwd_done, self._bwd_last = {}, None
+        done = self._bwd_done
+        for i in range(start, end):
+            op, (side, tag, wait), evs = self.bwd_ops[i], self.bwd_meta[i], self._bwd_events[i]
             if wait is not None:
-                ev = last if wait == "__all__" else done.get(wait)
+                ev = self._bwd_last if wait == "__all__" else done.get(wait)
                 if ev is not None:
                     main.wait_event(ev)
             if side:
@@ -892,9 +929,11 @@ class FCOSNet:
                 with torch.cuda.stream(side_stream):
                     op()
                     ev_side.record(side_stream)
-                done[tag] = last = ev_side
+                done[tag] = self._bwd_last = ev_side
             else:
                 op()
+        if self._bwd_last is not None:
+            main.wait_event(self._bwd_last)   # join: the range's gradients are final (and a captured graph re-joins its fork)
 
     def losses(self):
         """dict of the reference's loss names -> 0-dim fp32 tensors (device)."""

@@ -11,6 +11,8 @@ per-iteration teacher inference (mmdet/runner/hooks/unlabel_pred_hook.py:512-562
 With world_size == 1 the whole step is captured once into a CUDA graph and replayed; with more ranks it is split into
 three graphs around the two collectives (the packed 2-scalar normaliser all-reduce and the gradient all-reduce).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -61,6 +63,8 @@ class DSLEngine:
         self.graphs = None
         self.nms_pre, self.score_thr = nms_pre, score_thr
         self.adathres_stats = True   # accumulate the adaptive-threshold statistics in every teacher pass
+        # world > 1: all-reduce the gradient in buckets as the backward produces them (DSLB_NO_BUCKETS=1: one all-reduce)
+        self.bucketed = os.environ.get("DSLB_NO_BUCKETS") is None
         self._build_teacher_post()
         self.launches_per_step = None
         self.two_streams = two_streams
@@ -143,6 +147,22 @@ class DSLEngine:
         self.student.run_loss()
         self.student.backward(self.s3 if self.two_streams else None)
 
+    def _bucket_ranges(self):
+        """Backward op ranges ending at the gradient-bucket boundaries: [(op_start, op_end, grad_lo, grad_hi)]."""
+        out, start = [], 0
+        for end, lo, hi in self.student.bwd_buckets:
+            out.append((start, end, lo, hi))
+            start = end
+        out[-1] = (out[-1][0], len(self.student.bwd_ops), out[-1][2], out[-1][3])
+        return out
+
+    def _phase_b_part(self, k):
+        """Bucket k of the backward (k = 0 also evaluates the loss): when it returns, grad[lo:hi] of that bucket is final."""
+        start, end, _, _ = self._bucket_ranges()[k]
+        if k == 0:
+            self.student.run_loss()
+        self.student.backward(self.s3 if self.two_streams else None, start=start, end=end)
+
     def _phase_c(self):
         if self.world == 1:
             self._join_teacher()
@@ -189,11 +209,26 @@ class DSLEngine:
     def _allreduce_grads(self):
         dist_ops.allreduce_mean_(self.student.grad)    # DDP semantics: mean over ranks (mmdet/apis/train.py:88-96)
 
+    def _allreduce_bucket_async(self, k):
+        """Mean all-reduce of gradient bucket k, asynchronous: it overlaps the backward of the later buckets (the
+        reference's DDP does the same with its 25 MB buckets, mmdet/apis/train.py:88-102)."""
+        _, _, lo, hi = self._bucket_ranges()[k]
+        return dist_ops.allreduce_mean_async_(self.student.grad[lo:hi])
+
     def _run_eager(self):
         self._phase_a()
         self._allreduce_counts()
-        self._phase_b()
-        self._allreduce_grads()
+        if self.world > 1 and self.bucketed:
+            works = []
+            for k in range(len(self.student.bwd_buckets)):
+                self._phase_b_part(k)
+                works.append(self._allreduce_bucket_async(k))
+            for w in works:
+                if w is not None:
+                    w.wait()
+        else:
+            self._phase_b()
+            self._allreduce_grads()
         self._phase_c()
 
     def _capture(self):
@@ -214,8 +249,13 @@ class DSLEngine:
         self.student.repack(everything=True)
         self.teacher.repack(everything=True)
         torch.cuda.synchronize()
-        phases = [[self._phase_a, self._phase_b, self._phase_c]] if self.world == 1 else \
-            [[self._phase_a], [self._phase_b], [self._phase_c]]
+        if self.world == 1:
+            phases = [[self._phase_a, self._phase_b, self._phase_c]]
+        elif self.bucketed:
+            nb = len(self.student.bwd_buckets)
+            phases = [[self._phase_a]] + [[(lambda k=k: self._phase_b_part(k))] for k in range(nb)] + [[self._phase_c]]
+        else:
+            phases = [[self._phase_a], [self._phase_b], [self._phase_c]]
         graphs = []
         pool = None
         for fns in phases:
@@ -372,6 +412,17 @@ class DSLEngine:
                 self._capture()
             if self.world == 1:
                 self.graphs[0].replay()
+            elif self.bucketed:
+                self.graphs[0].replay()
+                self._allreduce_counts()
+                works = []
+                for k in range(len(self.student.bwd_buckets)):
+                    self.graphs[1 + k].replay()
+                    works.append(self._allreduce_bucket_async(k))
+                for w in works:
+                    if w is not None:
+                        w.wait()
+                self.graphs[-1].replay()
             else:
                 self.graphs[0].replay()
                 self._allreduce_counts()

@@ -34,6 +34,15 @@ def _worker(rank, world, port, q):
         gathered = [torch.zeros(1000) for _ in range(world)]
         dist.all_gather(gathered, mine)
         assert torch.allclose(grad, torch.stack(gathered).mean(0), atol=1e-7)
+        # 1b. bucketed form used by the engine at world > 1: asynchronous mean all-reduces of disjoint slices of the flat
+        #     gradient (issued as the backward finishes each bucket) == one all-reduce of the whole buffer
+        flat = torch.randn(1000, generator=torch.Generator().manual_seed(200 + rank))
+        whole = flat.clone()
+        works = [dist_ops.allreduce_mean_async_(flat[lo:hi]) for lo, hi in ((600, 1000), (250, 600), (0, 250))]
+        for wk in works:
+            wk.wait()
+        dist_ops.allreduce_mean_(whole)
+        assert torch.equal(flat, whole)
         # 2. packed normalisers: each rank runs the reference's target assignment on ITS images (oracle), the packed
         #    sum over ranks must give the same normalisers as the reference's two reduce_mean calls
         B, H, W = 2, 128, 160
