@@ -30,6 +30,11 @@ def allreduce_mean_async_(t):
     return None
 
 
+def allreduce_sum_async_(t):
+    """In-flight sum all-reduce (None with one rank): .wait() before the result is consumed."""
+    return dist.all_reduce(t, async_op=True) if world_size() > 1 else None
+
+
 def allreduce_sum_(t):
     if world_size() > 1:
         dist.all_reduce(t)

@@ -143,6 +143,18 @@ class DSLEngine:
         if self.world > 1:
             self._join_teacher()   # each captured graph must re-join its forked stream
 
+    def _phase_t(self):
+        """Target assignment alone: it needs only the GT / ignore boxes, so with several ranks it runs FIRST and the
+        packed normaliser all-reduce hides under the forward passes instead of sitting between forward and loss."""
+        with torch.no_grad():
+            self.student.run_targets()
+
+    def _phase_a_fwd(self):
+        self._fork_teacher()
+        with torch.no_grad():
+            self.student.forward()
+        self._join_teacher()
+
     def _phase_b(self):
         self.student.run_loss()
         self.student.backward(self.s3 if self.two_streams else None)
@@ -216,9 +228,12 @@ class DSLEngine:
         return dist_ops.allreduce_mean_async_(self.student.grad[lo:hi])
 
     def _run_eager(self):
-        self._phase_a()
-        self._allreduce_counts()
         if self.world > 1 and self.bucketed:
+            self._phase_t()
+            wc = dist_ops.allreduce_sum_async_(self.student.counts)
+            self._phase_a_fwd()
+            if wc is not None:
+                wc.wait()
             works = []
             for k in range(len(self.student.bwd_buckets)):
                 self._phase_b_part(k)
@@ -227,6 +242,8 @@ class DSLEngine:
                 if w is not None:
                     w.wait()
         else:
+            self._phase_a()
+            self._allreduce_counts()
             self._phase_b()
             self._allreduce_grads()
         self._phase_c()
@@ -253,7 +270,8 @@ class DSLEngine:
             phases = [[self._phase_a, self._phase_b, self._phase_c]]
         elif self.bucketed:
             nb = len(self.student.bwd_buckets)
-            phases = [[self._phase_a]] + [[(lambda k=k: self._phase_b_part(k))] for k in range(nb)] + [[self._phase_c]]
+            phases = [[self._phase_t], [self._phase_a_fwd]] + [[(lambda k=k: self._phase_b_part(k))] for k in range(nb)] + \
+                [[self._phase_c]]
         else:
             phases = [[self._phase_a], [self._phase_b], [self._phase_c]]
         graphs = []
@@ -414,10 +432,13 @@ class DSLEngine:
                 self.graphs[0].replay()
             elif self.bucketed:
                 self.graphs[0].replay()
-                self._allreduce_counts()
+                wc = dist_ops.allreduce_sum_async_(self.student.counts)
+                self.graphs[1].replay()
+                if wc is not None:
+                    wc.wait()
                 works = []
                 for k in range(len(self.student.bwd_buckets)):
-                    self.graphs[1 + k].replay()
+                    self.graphs[2 + k].replay()
                     works.append(self._allreduce_bucket_async(k))
                 for w in works:
                     if w is not None:
