@@ -213,11 +213,17 @@ class FCOSNet:
                  max_boxes=1024, parity_outputs=False, parts="all", level_sizes=None, strides=STRIDES,
                  regress_ranges=REGRESS_RANGES):
         """parts="all": backbone + FPN + head on a (B, 3, H, W) image. parts="head": FCOSHead only, on caller-filled
-        FPN maps self.p[l] of `level_sizes` (the standalone HEADS-registry module); backward then ends at self.dp."""
-        assert parts in ("all", "head")
-        assert parts == "head" or (H % 32 == 0 and W % 32 == 0), \
+        FPN maps self.p[l] of `level_sizes` (the standalone HEADS-registry module); backward then ends at self.dp.
+        parts="backbone": ResNet only (BACKBONES module): stage outputs in self.stage_out, backward seeded by the caller
+        in self.gc (gradients w.r.t. C3..C5, unmasked). parts="neck": FPN only (NECKS module) on caller-filled C3..C5
+        maps of `level_sizes` (first three entries), outputs self.p, backward seeded in self.dp, input gradients in
+        self.gc."""
+        assert parts in ("all", "head", "backbone", "neck")
+        assert parts in ("head", "neck") or (H % 32 == 0 and W % 32 == 0), \
             "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
         self.parts = parts
+        self.bb_prefix = "" if parts == "backbone" else "backbone."
+        self.neck_prefix = "" if parts == "neck" else "neck."
         self.strides, self.regress_ranges = tuple(strides), tuple(regress_ranges)
         self.B, self.H, self.W, self.depth, self.C = B, H, W, depth, num_classes
         self.train = train
@@ -226,8 +232,9 @@ class FCOSNet:
         self.center_sampling, self.radius, self.norm_on_bbox = center_sampling, radius, norm_on_bbox
         self.parity_outputs = parity_outputs
         if store is None:
-            spec = head_spec(num_classes) if parts == "head" else \
-                resnet_spec(depth) + fpn_spec() + head_spec(num_classes)
+            spec = {"head": lambda: head_spec(num_classes), "backbone": lambda: resnet_spec(depth, prefix=""),
+                    "neck": lambda: fpn_spec(prefix=""),
+                    "all": lambda: resnet_spec(depth) + fpn_spec() + head_spec(num_classes)}[parts]()
             store = ParamStore(spec, device).init_reference(seed)
         self.store = store
         self._arena_wants = []
@@ -239,23 +246,46 @@ class FCOSNet:
         self.flops_bwd = 0.0
         if train:
             self.grad = torch.zeros(store.n_train, dtype=torch.float32, device=self.dev)
-        if parts == "all":
+        if parts in ("all", "backbone"):
             self._build_backbone()
+        if parts == "neck":
+            chans = (512, 1024, 2048)
+            self.stage_out = [None] + [(self.buf(B, h, w, c), h, w, c) for (h, w), c in zip(level_sizes[:3], chans)]
+        if parts in ("all", "neck"):
             self._build_fpn()
-        else:
+        if parts == "head":
             self.psize = [tuple(hw) for hw in level_sizes]
             self.p = [self.buf(B, h, w, 256) for (h, w) in self.psize]
         self.head_op_start = len(self.fwd_ops)
-        self._build_head()
+        if parts in ("all", "head"):
+            self._build_head()
         if train:
-            self._build_loss()
-            self._alloc_arena()
             self.bwd_buckets = []   # (index one past the bucket's last backward op, flat grad range lo, hi)
             self._unpacked = set()
-            self._build_head_bwd()
-            if parts == "all":
+            if parts in ("all", "head"):
+                self._build_loss()
+                self._alloc_arena()
+                self._build_head_bwd()
+            else:
+                self._alloc_arena()
+
+                def zero_state():
+                    self.grad.zero_()
+                    self.arena.zero_()
+
+                self.add_bwd(zero_state)
+            if parts == "neck":
+                self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]   # seeds: gradients w.r.t. P3..P7
+            if parts in ("all", "neck"):
                 self._build_fpn_bwd()
+            if parts == "all":
                 self._emit_bucket(("neck.", "bbox_head."), head=True)   # + every bias (region B follows region A)
+            if parts == "backbone":
+                cs = self.stage_out[1:]
+                self.gc = [self.buf(B, h, w, c) for (_, h, w, c) in cs]          # seeds: gradients w.r.t. C3..C5
+                # the fused plan masks dC5 in the lateral dgrad epilogue; standalone, the last ReLU's mask is applied here
+                self.add_bwd(self.ew("dslb_relu_family", self.gc[2], cs[2][0], self.gc[2], self.gc[2].numel(), 1))
+            if parts in ("all", "backbone"):
                 self._build_backbone_bwd()
             self._build_finish_bwd()
         self._build_pack_plans()
@@ -344,8 +374,9 @@ class FCOSNet:
         self.stem_out = self.buf(B, H2, W2, 64)
         self.x0 = self.buf(B, H4, W4, 64)
         self.img4 = self.buf(B, H, W, 4)   # NHWC bf16 copy of the image, channels padded 3 -> 4 (stem workspace)
-        self.add_fwd(self.ew("dslb_stem_conv", self.img, st["backbone.conv1.weight"], st["backbone.bn1.weight"],
-                             st["backbone.bn1.bias"], st["backbone.bn1.running_mean"], st["backbone.bn1.running_var"],
+        self.add_fwd(self.ew("dslb_stem_conv", self.img, st[self.bb_prefix + "conv1.weight"],
+                             st[self.bb_prefix + "bn1.weight"], st[self.bb_prefix + "bn1.bias"],
+                             st[self.bb_prefix + "bn1.running_mean"], st[self.bb_prefix + "bn1.running_var"],
                              1e-5, self.img4, self.stem_out, B, H, W))
         self.flops_fwd += 2.0 * B * H2 * W2 * 64 * 147
         self.add_fwd(self.ew("dslb_maxpool3x3s2", self.stem_out, self.x0, B, H2, W2, 64))
@@ -359,7 +390,7 @@ class FCOSNet:
             for bi in range(nb):
                 s = 2 if (bi == 0 and li > 0) else 1
                 ho, wo = conv_out(h, 1, s, 0), conv_out(w, 1, s, 0)
-                p = f"backbone.layer{li + 1}.{bi}"
+                p = f"{self.bb_prefix}layer{li + 1}.{bi}"
                 # dgrad into the block input is needed unless that input is the frozen layer1 output
                 dgrad_in = trainable and not (li == 1 and bi == 0)
                 blk = dict(li=li, bi=bi, stride=s, hin=h, win=w, h=ho, w=wo, cin=inpl, planes=planes, xin=x,
@@ -395,7 +426,8 @@ class FCOSNet:
         cs = self.stage_out[1:]  # C3, C4, C5
         segs = []
         for i, (x, h, w, c) in enumerate(cs):
-            cw = self.conv(f"neck.lateral_convs.{i}.conv.weight", bias=f"neck.lateral_convs.{i}.conv.bias",
+            cw = self.conv(f"{self.neck_prefix}lateral_convs.{i}.conv.weight",
+                           bias=f"{self.neck_prefix}lateral_convs.{i}.conv.bias",
                            need_dgrad=tr, trainable=tr)
             self.lat.append(cw)
             self.lm.append(self.buf(B, h, w, 256))
@@ -407,7 +439,8 @@ class FCOSNet:
         segs = []
         self.psize = []
         for i, (x, h, w, c) in enumerate(cs):
-            cw = self.conv(f"neck.fpn_convs.{i}.conv.weight", bias=f"neck.fpn_convs.{i}.conv.bias", pad=1,
+            cw = self.conv(f"{self.neck_prefix}fpn_convs.{i}.conv.weight",
+                           bias=f"{self.neck_prefix}fpn_convs.{i}.conv.bias", pad=1,
                            need_dgrad=tr, trainable=tr)
             self.fpnc.append(cw)
             self.p.append(self.buf(B, h, w, 256))
@@ -419,7 +452,8 @@ class FCOSNet:
         h7, w7 = conv_out(h6, 3, 2, 1), conv_out(w6, 3, 2, 1)
         self.psize += [(h6, w6), (h7, w7)]
         for i in (3, 4):
-            self.fpnc.append(self.conv(f"neck.fpn_convs.{i}.conv.weight", bias=f"neck.fpn_convs.{i}.conv.bias",
+            self.fpnc.append(self.conv(f"{self.neck_prefix}fpn_convs.{i}.conv.weight",
+                                       bias=f"{self.neck_prefix}fpn_convs.{i}.conv.bias",
                                        stride=2, pad=1, need_dgrad=tr, trainable=tr))
         self.p.append(self.buf(B, h6, w6, 256))
         self.p.append(self.buf(B, h7, w7, 256))
@@ -729,7 +763,7 @@ class FCOSNet:
         B = self.B
         cs = self.stage_out[1:]
         (h5, w5), (h6, w6), (h7, w7) = self.psize[2], self.psize[3], self.psize[4]
-        gb = lambda i: self.grad_view(f"neck.fpn_convs.{i}.conv.bias")  # noqa: E731
+        gb = lambda i: self.grad_view(f"{self.neck_prefix}fpn_convs.{i}.conv.bias")  # noqa: E731
         # P7 = conv_s2(relu(P6)); P6 = conv_s2(P5)
         self.tmp6 = self.buf(B, h6, w6, 256)
         self.plan_wgrad([self.fpnc[4].wseg(self.r6, self.dp[4], B, h6, w6)], "fpn.p7.wgrad")
@@ -762,13 +796,15 @@ class FCOSNet:
         self.plan_wgrad([self.lat[i].wseg(cs[i][0], self.dl[i], B, cs[i][1], cs[i][2]) for i in range(3)],
                         "fpn.lateral.wgrad")
         for i in range(3):
-            self.add_bwd(self.ew("dslb_colsum", self.dl[i], self.grad_view(f"neck.lateral_convs.{i}.conv.bias"),
+            self.add_bwd(self.ew("dslb_colsum", self.dl[i], self.grad_view(f"{self.neck_prefix}lateral_convs.{i}.conv.bias"),
                                  B * cs[i][1] * cs[i][2], 256, 256), side=True, tag="colsum")
         # gradient w.r.t. the stage outputs C3, C4 (unmasked: more consumers follow) and C5 (masked: last consumer)
         self.gc = [self.buf(B, cs[i][1], cs[i][2], cs[i][3]) for i in range(3)]
         segs = []
         for i in range(3):
-            kw = dict(relu_mask=cs[i][0]) if i == 2 else {}
+            # (fused plan only: C5 has no other consumer, so its ReLU mask rides on this epilogue; a standalone FPN must
+            # return the plain gradient w.r.t. its input)
+            kw = dict(relu_mask=cs[i][0]) if (i == 2 and self.parts == "all") else {}
             segs.append(self.lat[i].dseg(self.dl[i], self.gc[i], B, cs[i][1], cs[i][2], cs[i][1], cs[i][2], **kw))
         self.plan_bwd(segs, "fpn.lateral.dgrad")
 
@@ -787,7 +823,7 @@ class FCOSNet:
             h, w, hin, win, planes = blk["h"], blk["w"], blk["hin"], blk["win"], blk["planes"]
             name = f"layer{li + 1}.{bi}"
             if idx == stage_last[li] and li == 2:
-                self._emit_bucket(("backbone.layer4.",))   # 60 MB of gradients are final once layer4 is done
+                self._emit_bucket((self.bb_prefix + "layer4.",))   # 60 MB of gradients are final once layer4 is done
             if idx == stage_last[li]:
                 if li == 3:
                     blk["M"] = self.gc[2]  # already masked by the lateral dgrad epilogue
@@ -859,7 +895,13 @@ class FCOSNet:
             self._emit_bucket(("bbox_head.",), head=True)
             self.bwd_buckets[-1] = (len(self.bwd_ops), 0, self.store.n_train)
             return
-        self._emit_bucket(("backbone.",))
+        if self.parts == "neck":
+            self._emit_bucket(("lateral_convs.", "fpn_convs."))
+            self.bwd_buckets[-1] = (len(self.bwd_ops), 0, self.store.n_train)
+            return
+        self._emit_bucket((self.bb_prefix,))
+        if self.parts == "backbone":
+            return
         # the buckets must tile the trainable range exactly: [0, layer4) | [layer4, neck) | [neck, n_train)
         rng = sorted((lo, hi) for _, lo, hi in self.bwd_buckets)
         assert rng[0][0] == 0 and rng[-1][1] == self.store.n_train and all(a[1] == b[0] for a, b in zip(rng, rng[1:])), rng

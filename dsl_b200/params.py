@@ -159,7 +159,7 @@ class ParamStore:
                 o, i, kh, kw = p.shape
                 if "bbox_head" in p.name:
                     t = torch.randn(p.shape, generator=g) * 0.01
-                elif "neck" in p.name:
+                elif "neck" in p.name or "lateral_convs" in p.name or "fpn_convs" in p.name:
                     bound = math.sqrt(6.0 / (i * kh * kw + o * kh * kw))
                     t = (torch.rand(p.shape, generator=g) * 2 - 1) * bound
                 else:

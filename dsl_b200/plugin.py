@@ -5,6 +5,8 @@ and lets a config pull extra modules in with `custom_imports` (tools/train.py:93
 re-registers, with force=True, the keys the fcos_semi configs name:
 
     DETECTORS['FCOS']  -> FCOS          (mmdet/models/detectors/{fcos,single_stage,base}.py)
+    BACKBONES['ResNet'], NECKS['FPN'] -> ResNet, FPN   (backbones/resnet.py, necks/fpn.py; standalone modules)
+    LOSSES[...] / RUNNERS['SemiEpochBasedRunner'] -> dsl_b200.losses / dsl_b200.runner
     HEADS['FCOSHead']  -> FCOSHead      (mmdet/models/dense_heads/{fcos_head,anchor_free_head}.py)
     HOOKS['EMAOWNHook']-> EMAOWNHook    (mmdet/runner/hooks/ema.py + SemiEpochBasedRunner.EMA,
                                          mmdet/runner/hooks/semi_epoch_based_runner.py:368-409)
@@ -344,6 +346,172 @@ class FCOS(_StoreModule):
         return self.train_step(data, optimizer)
 
 
+# ====================================================================================================== backbone / neck
+def _to_nchw(t_nhwc, B, C, h, w, dev):
+    from . import _lib as L
+    o = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+    L.check(L.lib.dslb_nhwc_to_nchw_f32(L.ptr(t_nhwc), L.ptr(o), B, C, h, w, C, 0, L.cur_stream()), "nhwc_to_nchw")
+    return o
+
+
+def _to_nhwc(t_nchw, dst, B, C, h, w):
+    from . import _lib as L
+    L.check(L.lib.dslb_nchw_to_nhwc_bf16(L.ptr(t_nchw.contiguous().float()), L.ptr(dst), B, C, h, w, C, L.cur_stream()),
+            "nchw_to_nhwc")
+
+
+class _PartFn(torch.autograd.Function):
+    """Autograd bridge of the standalone ResNet / FPN modules: forward already ran on the plan `net`; backward copies the
+    upstream gradients into the plan's seed buffers, runs its CUDA backward and hands back input + parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, owner, net, outs, seeds, in_grads, n_in, *inputs_and_params):
+        ctx.owner, ctx.net, ctx.seeds, ctx.in_grads, ctx.n_in = owner, net, seeds, in_grads, n_in
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        net, owner = ctx.net, ctx.owner
+        for g, (buf, B, C, h, w) in zip(gouts, ctx.seeds):
+            if buf is None:
+                continue
+            if g is None:
+                buf.zero_()
+            else:
+                _to_nhwc(g, buf, B, C, h, w)
+        net.backward()
+        gin = [None if e is None else _to_nchw(e[0], *e[1:], owner.store.device) for e in ctx.in_grads]
+        grads = []
+        for p, _ in owner._trainable:
+            o, n = net.store.offsets[p.name]
+            grads.append(net.grad[o:o + n].view(p.shape).clone())
+        return (None, None, None, None, None, None) + tuple(gin) + tuple(grads)
+
+
+class ResNet(_StoreModule):
+    """BACKBONES['ResNet'] (mmdet/models/backbones/resnet.py:304-656) for the configuration the fcos_semi configs use:
+    depth 50 / 101, caffe style, frozen BatchNorm (norm_eval, requires_grad=False), frozen_stages=1. NCHW fp32 in,
+    tuple of NCHW fp32 stage outputs (C2..C5 at `out_indices`) out, autograd-connected for layers 2-4."""
+
+    def __init__(self, depth, in_channels=3, num_stages=4, strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1),
+                 out_indices=(0, 1, 2, 3), style="pytorch", frozen_stages=-1, norm_cfg=None, norm_eval=True,
+                 init_cfg=None, pretrained=None, **kwargs):
+        super().__init__()
+        _check(depth in (50, 101), f"ResNet depth {depth}")
+        _check(in_channels == 3 and num_stages == 4 and tuple(strides) == (1, 2, 2, 2) and
+               tuple(dilations) == (1, 1, 1, 1), "only the standard 4-stage stride-(1,2,2,2) layout")
+        _check(style == "caffe", "ResNet style must be 'caffe' (stride on conv1)")
+        _check(frozen_stages == 1, "frozen_stages must be 1")
+        _check(norm_eval and not dict(norm_cfg or {}).get("requires_grad", True),
+               "BatchNorm must be frozen (norm_eval=True, requires_grad=False)")
+        _check(not kwargs.get("dcn") and not kwargs.get("plugins") and not kwargs.get("deep_stem") and
+               not kwargs.get("avg_down") and not kwargs.get("with_cp"), "dcn / plugins / deep_stem / avg_down / with_cp")
+        self.depth, self.out_indices = depth, tuple(out_indices)
+        self._bind_store(ParamStore(resnet_spec(depth, prefix=""), "cpu").init_reference(0))
+        self._trainable = self.trainable_parameters()
+        self._nets = OrderedDict()
+
+    def _on_store_moved(self):
+        self._nets.clear()
+
+    def init_weights(self):
+        self.store.init_reference(0)
+        self._nets.clear()
+
+    def load_state_dict(self, sd, strict=True):
+        missing = self.store.load_state_dict({k: v for k, v in sd.items() if not k.endswith("num_batches_tracked")},
+                                             strict=strict)
+        for n in self._nets.values():
+            n._stale = True
+        return missing
+
+    def _net(self, B, H, W, train):
+        from .engine import FCOSNet
+        key = (B, H, W, bool(train))
+        if key not in self._nets:
+            if len(self._nets) >= 4:
+                self._nets.popitem(last=False)
+            self._nets[key] = FCOSNet(B, H, W, depth=self.depth, train=train, store=self.store,
+                                      device=self.store.device, parts="backbone")
+        return self._nets[key]
+
+    def forward(self, x):
+        _need_cuda(x, "ResNet.forward")
+        B, _, H, W = x.shape
+        train = torch.is_grad_enabled() and self.training
+        net = self._net(B, H, W, train)
+        with torch.no_grad():
+            net.repack(everything=True)     # parameters may have been stepped by any optimizer since the last call
+            net.img.copy_(x)
+            net.forward()
+            outs = [_to_nchw(t, B, c, h, w, x.device) for (t, h, w, c) in net.stage_out]
+        if train:
+            seeds = [(None, 0, 0, 0, 0)] + [(net.gc[i], B, c, h, w) for i, (_, h, w, c) in enumerate(net.stage_out[1:])]
+            outs = _PartFn.apply(self, net, outs, seeds, [], 0, *[p for _, p in self._trainable])
+        return tuple(outs[i] for i in self.out_indices)
+
+
+class FPN(_StoreModule):
+    """NECKS['FPN'] (mmdet/models/necks/fpn.py:9-202) for the fcos_semi layout: in_channels [256, 512, 1024, 2048],
+    start_level=1, add_extra_convs='on_output', num_outs=5, relu_before_extra_convs=True. Tuple of NCHW fp32 C2..C5 in
+    (C2 is unused, as in the reference with start_level=1), tuple of five NCHW fp32 maps out, autograd-connected."""
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False,
+                 relu_before_extra_convs=False, no_norm_on_lateral=False, conv_cfg=None, norm_cfg=None, act_cfg=None,
+                 upsample_cfg=None, init_cfg=None, **kwargs):
+        super().__init__()
+        _check(list(in_channels) == [256, 512, 1024, 2048] and out_channels == 256 and start_level == 1 and num_outs == 5
+               and add_extra_convs == "on_output" and relu_before_extra_convs and end_level in (-1, 4)
+               and norm_cfg is None and act_cfg is None and conv_cfg is None,
+               "FPN config differs from configs/fcos_semi (start_level=1, on_output, 5 outs, relu_before_extra_convs)")
+        _check(dict(upsample_cfg or dict(mode="nearest")).get("mode") == "nearest", "FPN upsample mode must be nearest")
+        self.in_channels, self.out_channels, self.num_outs = list(in_channels), out_channels, num_outs
+        self._bind_store(ParamStore(fpn_spec(prefix=""), "cpu").init_reference(0))
+        self._trainable = self.trainable_parameters()
+        self._nets = OrderedDict()
+
+    def _on_store_moved(self):
+        self._nets.clear()
+
+    def init_weights(self):
+        self.store.init_reference(0)
+        self._nets.clear()
+
+    def load_state_dict(self, sd, strict=True):
+        return self.store.load_state_dict(sd, strict=strict)
+
+    def _net(self, B, sizes, train):
+        from .engine import FCOSNet
+        key = (B, tuple(sizes), bool(train))
+        if key not in self._nets:
+            if len(self._nets) >= 4:
+                self._nets.popitem(last=False)
+            self._nets[key] = FCOSNet(B, 0, 0, train=train, store=self.store, device=self.store.device, parts="neck",
+                                      level_sizes=list(sizes))
+        return self._nets[key]
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)
+        feats = list(inputs[1:])
+        _need_cuda(feats[0], "FPN.forward")
+        B = feats[0].shape[0]
+        sizes = [tuple(f.shape[-2:]) for f in feats]
+        train = torch.is_grad_enabled() and self.training
+        net = self._net(B, sizes, train)
+        with torch.no_grad():
+            net.repack(everything=True)
+            for f, (buf, h, w, c) in zip(feats, net.stage_out[1:]):
+                _to_nhwc(f, buf, B, c, h, w)
+            net.forward()
+            outs = [_to_nchw(net.p[l], B, 256, h, w, feats[0].device) for l, (h, w) in enumerate(net.psize)]
+        if train:
+            seeds = [(net.dp[l], B, 256, h, w) for l, (h, w) in enumerate(net.psize)]
+            in_grads = [None] + [(net.gc[i], B, c, h, w) for i, (_, h, w, c) in enumerate(net.stage_out[1:])]
+            outs = _PartFn.apply(self, net, outs, seeds, in_grads, len(inputs), *inputs,
+                                 *[p for _, p in self._trainable])
+        return tuple(outs)
+
+
 # ====================================================================================================== head
 class FCOSHead(_StoreModule):
     """FCOSHead (mmdet/models/dense_heads/fcos_head.py:14-726; tower layout anchor_free_head.py:89-139) as a
@@ -642,6 +810,13 @@ def register(force=True):
     DETECTORS.register_module(name="FCOS", force=force, module=FCOS)
     HEADS.register_module(name="FCOSHead", force=force, module=FCOSHead)
     done += ["DETECTORS.FCOS", "HEADS.FCOSHead"]
+    try:
+        from mmdet.models.builder import BACKBONES, NECKS
+        BACKBONES.register_module(name="ResNet", force=force, module=ResNet)
+        NECKS.register_module(name="FPN", force=force, module=FPN)
+        done += ["BACKBONES.ResNet", "NECKS.FPN"]
+    except Exception:
+        pass
     try:
         from mmcv.runner import HOOKS
         HOOKS.register_module(name="EMAOWNHook", force=force, module=EMAOWNHook)

@@ -295,3 +295,64 @@ def test_semi_epoch_based_runner_drives_the_fused_step(tmp_path):
     assert ck["meta"]["epoch"] == 3 and ck["meta"]["iter"] == 4 and ck["meta"]["seed"] == 0
     assert "bbox_head.conv_cls.weight" in ck["state_dict"] and "backbone.layer4.2.bn3.running_var" in ck["state_dict"]
     assert int(runner.engine.post.stat_cnt.sum()) == 0 and runner.engine.post.have_prev   # adathres ran at epoch end
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.gpu
+def test_standalone_resnet_and_fpn_modules_forward_backward():
+    """BACKBONES['ResNet'] / NECKS['FPN'] as modules of their own (NCHW fp32 in / out, autograd-connected), chained like
+    SingleStageDetector.extract_feat (single_stage.py:136-141): forward vs the fp32 oracle within the bf16 bar,
+    parameter / input gradients vs the oracle's autograd (direction and norm; bf16 activations through <= 16 layers)."""
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    torch.manual_seed(0)
+    bb = plugin.ResNet(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                       norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="caffe").cuda()
+    neck = plugin.FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1, add_extra_convs="on_output",
+                      num_outs=5, relu_before_extra_convs=True).cuda()
+    with pytest.raises(NotImplementedError):
+        plugin.ResNet(depth=50, style="pytorch", frozen_stages=1, norm_cfg=dict(type="BN", requires_grad=False))
+    with pytest.raises(NotImplementedError):
+        plugin.FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5)     # start_level=0 layout
+    B, H, W = 2, 128, 160
+    rng = np.random.RandomState(4)
+    x = GI.make_tensor(rng, B, 3, H, W, scale=50.0)
+    cs = bb(x.cuda())
+    ps = neck(cs)
+    assert [tuple(c.shape) for c in cs] == [(B, 256, 32, 40), (B, 512, 16, 20), (B, 1024, 8, 10), (B, 2048, 4, 5)]
+    assert [tuple(p.shape[1:]) for p in ps] == [(256, 16, 20), (256, 8, 10), (256, 4, 5), (256, 2, 3), (256, 1, 2)]
+    # oracle (fp32, CPU) on the same weights
+    sd_b = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+            for k, v in bb.state_dict().items() if "num_batches" not in k}
+    sd_n = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in neck.state_dict().items()}
+    rc = O.resnet_forward(sd_b, x, 50)
+    rp = O.fpn_forward(sd_n, rc)
+    for got, ref in zip(list(cs) + list(ps), rc + rp):
+        err = (got.detach().cpu() - ref.detach()).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        assert err < 3e-2, err
+    ws = [torch.from_numpy(rng.randn(*p.shape).astype(np.float32)) for p in ps]
+    sum((p * w.cuda()).sum() for p, w in zip(ps, ws)).backward()
+    sum((p * w).sum() for p, w in zip(rp, ws)).backward()
+    checked = 0
+    for name, p in list(neck.named_parameters()):
+        ref = sd_n[name].grad
+        assert _cos(p.grad.cpu(), ref) > 0.999 and abs(p.grad.norm().item() / ref.norm().item() - 1) < 2e-2, name
+        checked += 1
+    for name, p in bb.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None and name.startswith(("conv1", "bn", "layer1")) or ".bn" in name or "downsample.1" in name
+            continue
+        ref = sd_b[name].grad
+        c = _cos(p.grad.cpu(), ref)
+        floor = 0.99 if name.startswith("layer4") else (0.97 if name.startswith("layer3") else 0.93)
+        assert c > floor, (name, c)
+        checked += 1
+    assert checked > 50
+    # SGD on the plugin parameters moves the flat store the kernels read (same memory)
+    before = bb.store.flat.clone()
+    torch.optim.SGD([p for p in bb.parameters() if p.requires_grad], lr=0.1).step()
+    assert not torch.equal(bb.store.flat, before)
