@@ -133,6 +133,28 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.dslb_version() >= 100
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [(64, 96), (70, 101), (33, 47)])
+def test_scale_invariant_input_matches_oracle(hw):
+    """SI extra input (semi_epoch_based_runner.py:186-204): the half-resolution kernel vs F.interpolate on the CPU."""
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    H, W = hw
+    rng = np.random.RandomState(0)
+    img = GI.make_tensor(rng, 2, 3, H, W)
+    gts, lbs, igs = GI.make_gt(3, 2, H, W, with_ignore=True)
+    metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=np.ones(4, np.float32))] * 2
+    a = plugin.scale_invariant_input(img.cuda(), [g.cuda() for g in gts], lbs, [i.cuda() for i in igs], metas)
+    b = O.scale_invariant_input(img, gts, igs)
+    assert a[0].shape == b[0].shape
+    assert torch.equal(a[0][:2].cpu(), b[0][:2])
+    assert (a[0][2].cpu() - b[0][2]).abs().max().item() <= 1e-5      # fp32 bilinear weights, fma contraction may differ
+    assert torch.equal(a[0][2, :, H // 2:].cpu(), torch.zeros(3, H - H // 2, W))    # zero padding outside the copy
+    assert torch.equal(a[1][-1].cpu(), b[1]) and torch.equal(a[3][-1].cpu(), b[2])
+    assert len(a[1]) == len(a[2]) == len(a[3]) == len(a[4]) == 3 and torch.equal(a[2][-1], lbs[-1])
+    assert a[4][-1]["img_shape"][:2] == (H // 2, W // 2)
+
+
 # ------------------------------------------------------------------------------------------------------- GPU
 def _data(B, H, W, seed, dev="cuda"):
     rng = np.random.RandomState(seed)
