@@ -361,10 +361,11 @@ __global__ void gn_bwd_reduce_kernel(const __grid_constant__ GnParams P, const i
     A[e] = 0.f;
     B[e] = 0.f;
   }
-  for (int p = pix0 + pl; p < pend; p += 8) {
+#pragma unroll 4
+  for (int p = pix0 + pl; p < pend; p += 8) {   // unrolled: 8 independent 16-byte loads in flight per thread
     float x[8], d[8];
-    unpack8(*reinterpret_cast<const uint4*>(s.x + (long long)p * P.C + c8 * 8), x);
-    unpack8(*reinterpret_cast<const uint4*>(s.dz + (long long)p * P.C + c8 * 8), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s.x + (long long)p * P.C + c8 * 8)), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s.dz + (long long)p * P.C + c8 * 8)), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - fmean) * rstd;
@@ -433,10 +434,11 @@ __global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const in
     be[e] = __ldg(s.beta + c8 * 8 + e);
     D[e] = 0.f;
   }
-  for (int p = pix0 + pl; p < pend; p += 8) {
+#pragma unroll 4
+  for (int p = pix0 + pl; p < pend; p += 8) {   // unrolled: 8 independent 16-byte loads in flight per thread
     float x[8], d[8];
-    unpack8(*reinterpret_cast<const uint4*>(s.x + (long long)p * P.C + c8 * 8), x);
-    unpack8(*reinterpret_cast<const uint4*>(s.dz + (long long)p * P.C + c8 * 8), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s.x + (long long)p * P.C + c8 * 8)), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s.dz + (long long)p * P.C + c8 * 8)), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - fmean) * rstd;
