@@ -141,7 +141,7 @@ _proto("dslb_table_plan_destroy", None, VP)
 _proto("dslb_fcos_regctr_affine", I, VP, I, VP, VP, VP, VP, VP, VP, I, VP)
 _proto("dslb_zero_upsample2", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_colsum", I, VP, VP, LL, I, I, VP)
-_proto("dslb_conv_dgrad_naive", I, VP, VP, VP, I, I, I, I, I, I, I, I, I, I, VP)
+_proto("dslb_conv_dgrad_naive", I, VP, VP, VP, I, I, I, I, I, I, I, I, I, I, I, VP)
 _proto("dslb_fcos_targets", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, I, I, F, I, VP, VP, VP, VP, VP, VP)
 _proto("dslb_fcos_norm", I, VP, F, VP, VP)
 _proto("dslb_fcos_loss", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, F, F, F, I, F, VP, VP, VP, VP)

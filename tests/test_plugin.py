@@ -387,3 +387,25 @@ def test_standalone_resnet_and_fpn_modules_forward_backward():
     before = bb.store.flat.clone()
     torch.optim.SGD([p for p in bb.parameters() if p.requires_grad], lr=0.1).step()
     assert not torch.equal(bb.store.flat, before)
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every function bound in dsl_b200/_lib.py carries as many ctypes argtypes as include/dslb.h declares parameters
+    (a mismatch would corrupt the call frame silently)."""
+    import re
+    from dsl_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "dslb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(dslb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    checked = 0
+    for name, nargs in decl.items():
+        fn = getattr(L.lib, name)
+        if fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == nargs, (name, len(fn.argtypes), nargs)
+        checked += 1
+    assert checked > 45, checked
