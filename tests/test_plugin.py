@@ -409,3 +409,40 @@ def test_ctypes_prototypes_match_the_header():
         assert len(fn.argtypes) == nargs, (name, len(fn.argtypes), nargs)
         checked += 1
     assert checked > 45, checked
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the ABI structs have the size and field offsets a C compiler gives include/dslb.h."""
+    import ctypes
+    import re
+    import shutil
+    import subprocess
+    from dsl_b200 import _lib as L
+    from dsl_b200.geometry import View
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"dslb_conv_seg_t": L.ConvSeg, "dslb_wgrad_seg_t": L.WgradSeg, "dslb_gn_seg_t": L.GnSeg,
+             "dslb_pack_desc_t": L.PackDesc, "dslb_unpack_desc_t": L.UnpackDesc, "dslb_fcos_level_t": L.FcosLevel,
+             "dslb_view_t": View}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dslb.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for cname, field, val in re.findall(r"(\w+) (\w+) (\d+)", out):
+        cls = pairs[cname]
+        if field == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, field).offset == int(val), (cname, field)
+        seen += 1
+    assert seen > 80
