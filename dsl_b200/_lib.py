@@ -69,7 +69,7 @@ class PackDesc(C.Structure):
         ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
         ("O", C.c_int32), ("I", C.c_int32), ("R", C.c_int32), ("S", C.c_int32),
         ("rows_pad", C.c_int32), ("cols_pad", C.c_int32), ("row_off", C.c_int32), ("col_off", C.c_int32),
-        ("mode", C.c_int32), ("fill_padding", C.c_int32), ("bn_eps", C.c_float),
+        ("mode", C.c_int32), ("fill_padding", C.c_int32), ("bn_eps", C.c_float), ("w_ld", C.c_int32),
     ]
 
 
@@ -78,7 +78,20 @@ class UnpackDesc(C.Structure):
     _fields_ = [
         ("dw", C.c_void_p), ("g", C.c_void_p), ("bn_gamma", C.c_void_p), ("bn_var", C.c_void_p),
         ("O", C.c_int32), ("I", C.c_int32), ("R", C.c_int32), ("S", C.c_int32),
-        ("rows", C.c_int32), ("row_off", C.c_int32), ("bn_eps", C.c_float),
+        ("rows", C.c_int32), ("row_off", C.c_int32), ("bn_eps", C.c_float), ("dw_ld", C.c_int32),
+        ("g_ld", C.c_int32),
+    ]
+
+
+class BnGradDesc(C.Structure):
+    """dslb_bn_grad_desc_t"""
+    _fields_ = [
+        ("dw0", C.c_void_p), ("w0", C.c_void_p), ("dw1", C.c_void_p), ("w1", C.c_void_p),
+        ("mean", C.c_void_p), ("var", C.c_void_p), ("dbeta", C.c_void_p), ("dgamma", C.c_void_p),
+        ("O", C.c_int32), ("R", C.c_int32), ("S", C.c_int32),
+        ("I0", C.c_int32), ("dw_ld0", C.c_int32), ("w_ld0", C.c_int32), ("rows0", C.c_int32),
+        ("I1", C.c_int32), ("dw_ld1", C.c_int32), ("w_ld1", C.c_int32), ("rows1", C.c_int32),
+        ("bn_eps", C.c_float),
     ]
 
 
@@ -138,6 +151,11 @@ _proto("dslb_pack_plan_create", I, C.POINTER(PackDesc), I, C.POINTER(C.c_void_p)
 _proto("dslb_unpack_plan_create", I, C.POINTER(UnpackDesc), I, C.POINTER(C.c_void_p))
 _proto("dslb_table_plan_run", I, VP, VP)
 _proto("dslb_table_plan_destroy", None, VP)
+_proto("dslb_rla_state_fwd", I, VP, VP, VP, VP, VP, VP, F, VP, I, I, I, I, VP)
+_proto("dslb_rla_state_bwd", I, VP, VP, VP, VP, VP, VP, VP, F, VP, VP, VP, VP, I, I, I, I, VP)
+_proto("dslb_bn_grad_plan_create", I, C.POINTER(BnGradDesc), I, C.POINTER(C.c_void_p))
+_proto("dslb_bn_grad_plan_run", I, VP, VP)
+_proto("dslb_bn_grad_plan_destroy", None, VP)
 _proto("dslb_fcos_regctr_affine", I, VP, I, VP, VP, VP, VP, VP, VP, I, VP)
 _proto("dslb_zero_upsample2", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_colsum", I, VP, VP, LL, I, I, VP)

@@ -24,6 +24,7 @@ struct PackDescDev {
   int real_cols, fill;
   int mode;
   float eps;
+  int ldw;               // input channels per output-channel row of w in memory (>= I; > I for a slice of a wider tensor)
   long long work_begin;  // prefix sum of rows * cols8
 };
 
@@ -78,7 +79,7 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
       for (int e = 0; e < 8; ++e) v[e] = 0.f;
       if (row_real) {
         if (d.mode == 0) {
-          const float* src = d.w + ((long long)row * d.I) * RS + tap;
+          const float* src = d.w + ((long long)row * d.ldw) * RS + tap;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int i = c8 * 8 + e;
@@ -89,7 +90,7 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int o = c8 * 8 + e;
-            if (o < d.O) v[e] = d.w[((long long)o * d.I + row) * RS + rtap] * sc[e];
+            if (o < d.O) v[e] = d.w[((long long)o * d.ldw + row) * RS + rtap] * sc[e];
           }
         } else {
 #pragma unroll
@@ -97,7 +98,7 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
             const int k = c8 * 8 + e;
             if (k < RS * d.I) {
               const int tp = k / d.I, i = k - tp * d.I;
-              v[e] = d.w[((long long)row * d.I + i) * RS + tp] * sc[e];
+              v[e] = d.w[((long long)row * d.ldw + i) * RS + tp] * sc[e];
             }
           }
         }
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const PackDescDev* __re
 #pragma unroll
       for (int rr = 0; rr < PT / 8; ++rr) {
         const int oo = wv + 8 * rr;
-        const float* __restrict__ src = d.w + ((long long)(o0 + oo) * d.I + i0) * RS + lane;
+        const float* __restrict__ src = d.w + ((long long)(o0 + oo) * d.ldw + i0) * RS + lane;
         float v[PT_MAX_TAPS];
 #pragma unroll
         for (int j = 0; j < PT_MAX_TAPS; ++j)
@@ -214,6 +215,7 @@ struct UnpackDescDev {
   int O, I, R, S;
   int rows, row_off;
   float eps;
+  int ldd, ldg;          // columns per packed dw row (>= I), input channels per output-channel row of g (>= I)
   int vec4;              // 1x1 conv with I % 4 == 0 and 16-byte aligned buffers: work items are float4s
   long long work_begin;  // prefix of O*I (O*I/4 for vec4 descriptors)
 };
@@ -235,18 +237,18 @@ __global__ void unpack_batched_kernel(const UnpackDescDev* __restrict__ D, int n
       const int o = (int)(tl4 / i4n);
       const int i = (int)(tl4 - (unsigned)o * i4n) << 2;
       const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
-      float4 v = __ldg(reinterpret_cast<const float4*>(d.dw + ((long long)(d.row_off + o)) * d.I + i));
+      float4 v = __ldg(reinterpret_cast<const float4*>(d.dw + ((long long)(d.row_off + o)) * d.ldd + i));
       v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-      *reinterpret_cast<float4*>(d.g + (long long)o * d.I + i) = v;
+      *reinterpret_cast<float4*>(d.g + (long long)o * d.ldg + i) = v;
       continue;
     }
     const unsigned tl = (unsigned)(t - d.work_begin);
     const int i = (int)(tl % (unsigned)d.I);
     const int o = (int)(tl / (unsigned)d.I);
     const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
-    const float* src = d.dw + ((long long)(d.row_off + o)) * d.I + i;
-    float* dst = d.g + (long long)tl * RS;
-    for (int tap = 0; tap < RS; ++tap) dst[tap] = src[(long long)tap * d.rows * d.I] * sc;
+    const float* src = d.dw + ((long long)(d.row_off + o)) * d.ldd + i;
+    float* dst = d.g + ((long long)o * d.ldg + i) * RS;
+    for (int tap = 0; tap < RS; ++tap) dst[tap] = src[(long long)tap * d.rows * d.ldd] * sc;
   }
 }
 
@@ -270,8 +272,8 @@ __global__ void __launch_bounds__(256) unpack_tiled_kernel(const UnpackDescDev* 
     const int RS = d.R * d.S;
     const float sc = d.bn_gamma ? d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps) : 1.f;
     if (tid < ni) {
-      const float* __restrict__ src = d.dw + ((long long)(d.row_off + o)) * d.I + i0 + tid;
-      const long long plane = (long long)d.rows * d.I;
+      const float* __restrict__ src = d.dw + ((long long)(d.row_off + o)) * d.ldd + i0 + tid;
+      const long long plane = (long long)d.rows * d.ldd;
       float v[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap)
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(256) unpack_tiled_kernel(const UnpackDescDev* 
         if (tap < RS) st[tid * RS + tap] = v[tap] * sc;
     }
     __syncthreads();
-    float* dst = d.g + ((long long)o * d.I + i0) * RS;
+    float* dst = d.g + ((long long)o * d.ldg + i0) * RS;
     for (int idx = tid; idx < ni * RS; idx += 256) dst[idx] = st[idx];
     __syncthreads();
   }
@@ -374,6 +376,13 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
     d.rows_pad = s.rows_pad; d.cols_pad = s.cols_pad; d.row_off = s.row_off; d.col_off = s.col_off;
     d.mode = s.mode;
     d.eps = s.bn_eps;
+    d.ldw = s.w_ld > 0 ? s.w_ld : s.I;
+    if (d.ldw < s.I) {
+      delete[] h;
+      delete[] ht;
+      set_error("dslb_pack_plan_create: descriptor %d has w_ld < I", k);
+      return DSLB_EINVAL;
+    }
     const int real_rows = (s.mode == 1) ? s.I : s.O;
     const int real_cols = (s.mode == 1) ? s.O : (s.mode == 2 ? s.R * s.S * s.I : s.I);
     // full = rewrite the zero padding too; otherwise only the real sub-block (shared, offset outputs)
@@ -453,6 +462,14 @@ extern "C" int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs, int n, d
     }
     d.dw = s.dw; d.g = s.g; d.bn_gamma = s.bn_gamma; d.bn_var = s.bn_var;
     d.O = s.O; d.I = s.I; d.R = s.R; d.S = s.S; d.rows = s.rows; d.row_off = s.row_off; d.eps = s.bn_eps;
+    d.ldd = s.dw_ld > 0 ? s.dw_ld : s.I;
+    d.ldg = s.g_ld > 0 ? s.g_ld : s.I;
+    if (d.ldd < s.I || d.ldg < s.I) {
+      delete[] h;
+      delete[] ht;
+      set_error("dslb_unpack_plan_create: descriptor %d has dw_ld / g_ld < I", k);
+      return DSLB_EINVAL;
+    }
     d.vec4 = 0;
     if (s.R * s.S > 1 && s.R * s.S <= 9) {
       d.work_begin = items;
@@ -460,7 +477,7 @@ extern "C" int dslb_unpack_plan_create(const dslb_unpack_desc_t* descs, int n, d
       ht[ntiled++] = d;
     } else {
       d.vec4 = (s.R * s.S == 1 && s.I % 4 == 0 && ((uintptr_t)s.dw % 16) == 0 && ((uintptr_t)s.g % 16) == 0 &&
-                ((long long)s.row_off * s.I) % 4 == 0) ? 1 : 0;
+                ((long long)s.row_off * d.ldd) % 4 == 0 && d.ldd % 4 == 0 && d.ldg % 4 == 0) ? 1 : 0;
       d.work_begin = w;
       w += d.vec4 ? (long long)s.O * s.I / 4 : (long long)s.O * s.I;
       h[nslow++] = d;

@@ -18,7 +18,7 @@ import math
 import torch
 
 from . import _lib as L
-from .params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec
+from .params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
 
 BF16 = torch.bfloat16
 STRIDES = (8, 16, 32, 64, 128)
@@ -211,7 +211,7 @@ class FCOSNet:
     def __init__(self, B, H, W, depth=50, num_classes=80, train=True, store=None, device="cuda", seed=0,
                  loss_weight=1.0, soft_weight=0.0, center_sampling=True, radius=1.5, norm_on_bbox=True,
                  max_boxes=1024, parity_outputs=False, parts="all", level_sizes=None, strides=STRIDES,
-                 regress_ranges=REGRESS_RANGES):
+                 regress_ranges=REGRESS_RANGES, backbone="resnet"):
         """parts="all": backbone + FPN + head on a (B, 3, H, W) image. parts="head": FCOSHead only, on caller-filled
         FPN maps self.p[l] of `level_sizes` (the standalone HEADS-registry module); backward then ends at self.dp.
         parts="backbone": ResNet only (BACKBONES module): stage outputs in self.stage_out, backward seeded by the caller
@@ -219,6 +219,10 @@ class FCOSNet:
         maps of `level_sizes` (first three entries), outputs self.p, backward seeded in self.dp, input gradients in
         self.gc."""
         assert parts in ("all", "head", "backbone", "neck")
+        # backbone="rla": RLA_ResNet (resnet_rla.py:140-400, the backbone of configs/fcos_semi/RLA_*.py) with
+        # layers = RESNET_BLOCKS[depth]; see engine_rla.py
+        assert backbone in ("resnet", "rla")
+        self.backbone = backbone
         assert parts in ("head", "neck") or (H % 32 == 0 and W % 32 == 0), \
             "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
         self.parts = parts
@@ -232,9 +236,11 @@ class FCOSNet:
         self.center_sampling, self.radius, self.norm_on_bbox = center_sampling, radius, norm_on_bbox
         self.parity_outputs = parity_outputs
         if store is None:
-            spec = {"head": lambda: head_spec(num_classes), "backbone": lambda: resnet_spec(depth, prefix=""),
+            bb_spec = resnet_spec if backbone == "resnet" else \
+                (lambda depth, prefix="backbone.": rla_resnet_spec(RESNET_BLOCKS[depth], prefix=prefix))
+            spec = {"head": lambda: head_spec(num_classes), "backbone": lambda: bb_spec(depth, prefix=""),
                     "neck": lambda: fpn_spec(prefix=""),
-                    "all": lambda: resnet_spec(depth) + fpn_spec() + head_spec(num_classes)}[parts]()
+                    "all": lambda: bb_spec(depth) + fpn_spec() + head_spec(num_classes)}[parts]()
             store = ParamStore(spec, device).init_reference(seed)
         self.store = store
         self._arena_wants = []
@@ -365,6 +371,9 @@ class FCOSNet:
 
     # ------------------------------------------------------------------------------------------ backbone
     def _build_backbone(self):
+        if self.backbone == "rla":
+            from . import engine_rla
+            return engine_rla.build_backbone(self)
         B, H, W = self.B, self.H, self.W
         st = self.store
         self.img = self.buf(B, 3, H, W, dtype=torch.float32)  # NCHW fp32 input, as the reference feeds it
@@ -810,6 +819,9 @@ class FCOSNet:
 
     # ------------------------------------------------------------------------------------------ backbone backward
     def _build_backbone_bwd(self):
+        if self.backbone == "rla":
+            from . import engine_rla
+            return engine_rla.build_backbone_bwd(self)
         B = self.B
         stage_last = {}
         for idx, blk in enumerate(self.blocks):
@@ -870,6 +882,14 @@ class FCOSNet:
             descs.append(dict(dw=self.rc_dw, g=self.grad_view("bbox_head.conv_centerness.weight"), O=1, I=256, R=3, S=3,
                               rows=5, row_off=4))
         self._unpacked.update(names)
+        # trainable BatchNorms folded into those convs (RLA_ResNet): dgamma from the packed weight gradients, one launch
+        bnd = [(n, d) for n, d in getattr(self, "bn_grad_descs", []) if n.startswith(prefixes) and n not in self._unpacked]
+        if bnd:
+            from .engine_rla import BnGradPlan
+            self._unpacked.update(n for n, _ in bnd)
+            bplan = BnGradPlan([d for _, d in bnd])
+            self.bn_grad_plans = getattr(self, "bn_grad_plans", []) + [bplan]
+            self.add_bwd(bplan.run, side=True, tag="bn_grads")
         plan = TablePlan(descs, "unpack", "unpack_wgrads")
         self.unpack_plans = getattr(self, "unpack_plans", []) + [plan]
         # on the side stream, in order behind the weight / bias gradient launches it reads: the main (dgrad) stream never

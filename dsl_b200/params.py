@@ -58,6 +58,52 @@ def resnet_spec(depth=50, frozen_stages=1, prefix="backbone."):
     return out
 
 
+RLA_CHANNEL = 32  # resnet_rla.py:9,162: rla_channel, the width of the recurrent state h
+
+
+def rla_resnet_spec(layers=(3, 4, 6, 3), frozen_stages=1, prefix="backbone."):
+    """RLA_ResNet (resnet_rla.py:140-400): PyTorch-style bottlenecks (stride on conv2) whose conv1 acts on cat(x, h),
+    plus per stage a shared 1x1 `conv_outs` (4*planes -> 32), a shared 3x3 `recurrent_convs` (32 -> 32) and one
+    BatchNorm(32) per block (`stage_bns`). Names as in the reference's state_dict. Unlike ResNet(norm_cfg requires_grad=
+    False) the BatchNorm affine parameters of the non-frozen stages are TRAINABLE (only the statistics are frozen by
+    norm_eval, :389-399), except stage_bns[3][2] (:375-377). Listed stage by stage (conv_outs first, recurrent_convs
+    last) so that every stage is one contiguous range of the flat gradient (the gradient buckets of the backward)."""
+    out = []
+
+    def conv(name, o, i, k, frozen):
+        out.append(P(prefix + name + ".weight", (o, i, k, k), "F" if frozen else "A", "conv"))
+
+    def bn(name, c, frozen):
+        out.append(P(prefix + name + ".weight", (c,), "F" if frozen else "A", "bn_w"))
+        out.append(P(prefix + name + ".bias", (c,), "F" if frozen else "A", "bn_b"))
+        out.append(P(prefix + name + ".running_mean", (c,), "F", "bn_mean"))
+        out.append(P(prefix + name + ".running_var", (c,), "F", "bn_var"))
+
+    conv("conv1", 64, 3, 7, True)
+    bn("bn1", 64, True)
+    inpl = 64
+    for li, nb in enumerate(layers):
+        planes = 64 * 2 ** li
+        frozen = (li + 1) <= frozen_stages
+        conv(f"conv_outs.{li}", RLA_CHANNEL, planes * 4, 1, frozen)
+        for bi in range(nb):
+            p = f"stages.{li}.{bi}"
+            conv(p + ".conv1", planes, inpl + RLA_CHANNEL, 1, frozen)
+            bn(p + ".bn1", planes, frozen)
+            conv(p + ".conv2", planes, planes, 3, frozen)
+            bn(p + ".bn2", planes, frozen)
+            conv(p + ".conv3", planes * 4, planes, 1, frozen)
+            bn(p + ".bn3", planes * 4, frozen)
+            if bi == 0:
+                conv(p + ".downsample.0", planes * 4, inpl, 1, frozen)
+                bn(p + ".downsample.1", planes * 4, frozen)
+            inpl = planes * 4
+        for bi in range(nb):
+            bn(f"stage_bns.{li}.{bi}", RLA_CHANNEL, frozen or (li == 3 and bi == 2))
+        conv(f"recurrent_convs.{li}", RLA_CHANNEL, RLA_CHANNEL, 3, frozen)
+    return out
+
+
 def fpn_spec(in_channels=(512, 1024, 2048), out_channels=256, prefix="neck."):
     """FPN(start_level=1, add_extra_convs='on_output', num_outs=5) (necks/fpn.py:61-149)."""
     out = []

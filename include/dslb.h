@@ -179,6 +179,9 @@ typedef struct dslb_pack_desc {
   int32_t mode;            /* 0 fprop [tap][o][i]; 1 dgrad [tap][i][o], taps rotated 180 deg; 2 stem [o][(r*S+s)*I+i] */
   int32_t fill_padding;    /* 1: rewrite the zero padding too; 0: touch only the real sub-block                 */
   float bn_eps;
+  int32_t w_ld;            /* input channels per output-channel row of `w` in memory (0 = I). With w pointing at input
+                              channel i0 of a wider OIHW tensor and w_ld = its full width, an input-channel SLICE is packed
+                              (RLA_Bottleneck.conv1 acts on cat(x, h), resnet_rla.py:108-110: one operand per half)  */
 } dslb_pack_desc_t;
 typedef struct dslb_unpack_desc {
   const float* dw;         /* packed fp32 wgrad [R*S][rows][I]                                                  */
@@ -188,6 +191,8 @@ typedef struct dslb_unpack_desc {
   int32_t O, I, R, S;
   int32_t rows, row_off;
   float bn_eps;
+  int32_t dw_ld;           /* columns per packed row of dw (0 = I): > I when the conv ran on a channel-padded input   */
+  int32_t g_ld;            /* input channels per output-channel row of g in memory (0 = I): slice of a wider OIHW tensor */
 } dslb_unpack_desc_t;
 typedef struct dslb_table_plan dslb_table_plan_t;
 int dslb_pack_plan_create(const dslb_pack_desc_t* descs_host, int n, dslb_table_plan_t** out);
@@ -201,6 +206,48 @@ void dslb_table_plan_destroy(dslb_table_plan_t* plan);
 int dslb_fcos_regctr_affine(const float* scales, int scale_stride, const float* reg_bias, const float* ctr_bias,
                             const float* level_mult, float* rc_scale, float* rc_shift, float* scale_vals, int nlevels,
                             void* stream);
+/* ------------------------------------------------------------------------------------------------------
+ * RLA_ResNet (mmdet/models/backbones/resnet_rla.py; the backbone of configs/fcos_semi/RLA_*.py:3-13).
+ * The convs of RLA_Bottleneck (:71-137) and the shared conv_out / recurrent_conv (:259-260, 303-311) run through
+ * dslb_conv_plan_* / dslb_wgrad_plan_*; the recurrent state h (rla_channel = 32) is stored as bf16 NHWC with
+ * 64-channel rows (channels 32..63 zero) so it is a regular tensor-core operand.
+ * dslb_rla_state_fwd:  hb = tanh(BatchNorm_eval(pre)),  pre = h_old' + y_out  (resnet_rla.py:306-310), where
+ *   h_old' = AvgPool2d(2,2)(h_old) in the first block of a strided stage (pool = 1, :93-95,131-132; h_old is then
+ *   [N][2Ho][2Wo][64]) and h_old otherwise ([N][Ho][Wo][64]); y_out, hb: [N][Ho][Wo][64].
+ * dslb_rla_state_bwd:  autograd of the above. d_hb = gradient w.r.t. hb; writes d_pre (gradient w.r.t. pre = w.r.t.
+ *   y_out = w.r.t. an un-pooled h_old) and, with pool = 1, dh_old = the pooled gradient 0.25 * d_pre spread over each
+ *   2x2 source block; dgamma / dbeta (both or neither; [32] fp32) are ACCUMULATED into.
+ * ---------------------------------------------------------------------------------------------------- */
+int dslb_rla_state_fwd(const void* h_old, const void* y_out, const float* bn_gamma, const float* bn_beta,
+                       const float* bn_mean, const float* bn_var, float eps, void* hb, int N, int Ho, int Wo, int pool,
+                       void* stream);
+int dslb_rla_state_bwd(const void* d_hb, const void* hb, const void* h_old, const void* y_out, const float* bn_gamma,
+                       const float* bn_mean, const float* bn_var, float eps, void* d_pre, void* dh_old, float* dgamma,
+                       float* dbeta, int N, int Ho, int Wo, int pool, void* stream);
+/* Gradients of BatchNorm affine parameters that are trainable while the statistics are frozen (RLA_ResNet: norm_eval=True
+ * keeps running stats, but only frozen_stages' parameters have requires_grad=False, resnet_rla.py:361-375,389-399).
+ * The BatchNorm is folded into its conv (W' = W * gamma / sigma), so for output channel c
+ *     dgamma[c] = (<dW'[c], W[c]> - mean[c] * dbeta[c]) / sqrt(var[c] + eps),   dbeta[c] = sum_pix dy[c] (dslb_colsum)
+ * with dW' the packed fp32 weight gradient [R*S][rows][dw_ld] of the folded conv and W the OIHW master weight. A conv on
+ * a concatenated input (RLA_Bottleneck.conv1 on cat(x, h)) passes one (dW', W-slice) piece per part. One launch per plan. */
+typedef struct dslb_bn_grad_desc {
+  const float* dw0;        /* piece 0: packed wgrad, rows0 rows of dw_ld0 columns per tap                           */
+  const float* w0;         /*          master weight (pointer to the slice's first input channel)                    */
+  const float* dw1;        /* piece 1 or NULL                                                                        */
+  const float* w1;
+  const float* mean;       /* [O] running_mean                                                                       */
+  const float* var;        /* [O] running_var                                                                        */
+  const float* dbeta;      /* [O] already reduced                                                                    */
+  float* dgamma;           /* [O] overwritten                                                                        */
+  int32_t O, R, S;
+  int32_t I0, dw_ld0, w_ld0, rows0;   /* slice width; columns per dw row (0 = I0); input channels per w row (0 = I0) */
+  int32_t I1, dw_ld1, w_ld1, rows1;
+  float bn_eps;
+} dslb_bn_grad_desc_t;
+typedef struct dslb_bn_grad_plan dslb_bn_grad_plan_t;
+int dslb_bn_grad_plan_create(const dslb_bn_grad_desc_t* descs_host, int n, dslb_bn_grad_plan_t** out);
+int dslb_bn_grad_plan_run(const dslb_bn_grad_plan_t* plan, void* stream);
+void dslb_bn_grad_plan_destroy(dslb_bn_grad_plan_t* plan);
 /* y[n][2p][2q][:] = x[n][p][q][:], every other pixel of the [N][H][W][C] bf16 map zero: turns the data gradient of a
  * stride-2 conv into a stride-1 tensor-core dgrad over the zero-upsampled dY (FPN P6/P7 convs, necks/fpn.py:192-201). */
 int dslb_zero_upsample2(const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream);

@@ -57,6 +57,46 @@ def resnet_forward(sd, x, depth=50, prefix=""):
     return outs
 
 
+def rla_bottleneck_forward(sd, prefix, x, h, stride, has_downsample):
+    """RLA_Bottleneck.forward (backbones/resnet_rla.py:105-137), PyTorch style (stride on conv2, :86). `y = out` at :127
+    aliases the tensor that `out += identity` (:134) and the in-place ReLU (:135) then rewrite, so the `y` the reference
+    returns IS the block output; returns (out, h') with h' = AvgPool2d(2,2)(h) when the block is strided (:93-95,131-132)."""
+    identity = x
+    out = F.conv2d(torch.cat((x, h), dim=1), sd[prefix + ".conv1.weight"])
+    out = F.relu(_bn_eval(sd, prefix + ".bn1", out))
+    out = F.conv2d(out, sd[prefix + ".conv2.weight"], stride=stride, padding=1)
+    out = F.relu(_bn_eval(sd, prefix + ".bn2", out))
+    out = F.conv2d(out, sd[prefix + ".conv3.weight"])
+    out = _bn_eval(sd, prefix + ".bn3", out)
+    if has_downsample:
+        identity = F.conv2d(x, sd[prefix + ".downsample.0.weight"], stride=stride)
+        identity = _bn_eval(sd, prefix + ".downsample.1", identity)
+        if stride != 1:
+            h = F.avg_pool2d(h, 2, 2)
+    return F.relu(out + identity), h
+
+
+def rla_resnet_forward(sd, x, layers=(3, 4, 6, 3), prefix=""):
+    """RLA_ResNet._forward_impl (backbones/resnet_rla.py:289-327): stem, then per block the bottleneck on cat(x, h)
+    followed by the recurrent-state update h = recurrent_conv(tanh(bn(h + conv_out(y)))) (:306-311) with conv_out /
+    recurrent_conv shared inside a stage (:259-260) and one BatchNorm(32) per block (:284); returns the four stage
+    outputs x (the state is not part of the outputs, :312-313)."""
+    x = F.conv2d(x, sd[prefix + "conv1.weight"], stride=2, padding=3)
+    x = F.relu(_bn_eval(sd, prefix + "bn1", x))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    h = x.new_zeros(x.shape[0], sd[prefix + "recurrent_convs.0.weight"].shape[0], x.shape[2], x.shape[3])
+    outs = []
+    for li, nblocks in enumerate(layers):
+        for bi in range(nblocks):
+            stride = 2 if (bi == 0 and li > 0) else 1
+            x, h = rla_bottleneck_forward(sd, f"{prefix}stages.{li}.{bi}", x, h, stride, bi == 0)
+            h = h + F.conv2d(x, sd[f"{prefix}conv_outs.{li}.weight"])
+            h = torch.tanh(_bn_eval(sd, f"{prefix}stage_bns.{li}.{bi}", h))
+            h = F.conv2d(h, sd[f"{prefix}recurrent_convs.{li}.weight"], padding=1)
+        outs.append(x)
+    return outs
+
+
 def fpn_forward(sd, feats, prefix=""):
     """FPN.forward (necks/fpn.py:151-202) with start_level=1, add_extra_convs='on_output', num_outs=5,
     relu_before_extra_convs=True: laterals on C3..C5, nearest top-down, 3x3 outputs, P6 = conv s2 on P5 output,

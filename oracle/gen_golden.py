@@ -6,6 +6,7 @@ Files written (all small; inputs are regenerated from seeds, only reference OUTP
   head_fwd.npz   FCOSHead.forward train+eval on a 64-channel, 2-conv, GN(8) head (weights from seed)
   loss_*.npz     FCOSHead.loss: labels / bbox_targets (bit-exact contract), losses, input-gradient samples
   backbone.npz   ResNet-50 (caffe, frozen BN) + FPN forward on a 1x3x64x96 input (weights from seed)
+  rla_backbone.npz  RLA_ResNet (the shipped configs' backbone) forward + sampled parameter gradients, 1x3x64x96
   decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
   misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
 """
@@ -122,6 +123,38 @@ def gen_backbone(R):
     out = {f"c{i + 2}": c.numpy() for i, c in enumerate(cs)}
     out.update({f"p{i + 3}": p.numpy() for i, p in enumerate(ps)})
     np.savez_compressed(os.path.join(OUT, "backbone.npz"), **out)
+
+
+RLA_GRAD_KEYS = ("conv_outs.1.weight", "recurrent_convs.2.weight", "stage_bns.1.0.weight", "stage_bns.2.3.bias",
+                 "stages.1.0.conv1.weight", "stages.2.0.bn1.weight", "stages.2.0.downsample.1.weight",
+                 "stages.3.2.bn3.bias", "stages.3.0.conv2.weight", "stages.1.3.bn2.weight")
+
+
+def gen_rla_backbone(R):
+    """RLA_ResNet (mmdet/models/backbones/resnet_rla.py), the reference's own class, train() mode with norm_eval=True and
+    frozen_stages=1 as in configs/fcos_semi/RLA_*.py:3-13: stage outputs on a 1x3x64x96 input, which parameters are
+    trainable, and gradients of a weighted sum of the outputs for a sample of parameters. `flops=True` only moves the
+    initial state tensor to the CPU (:296-300)."""
+    RLA = ref_loader.load_rla()
+    m = RLA(layers=[3, 4, 6, 3], frozen_stages=1, norm_eval=True, style="pytorch")
+    m.flops = True
+    sd = GI.rla_state_dict(51)
+    missing = m.load_state_dict(sd, strict=False)
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys
+    m.train()
+    x = GI.make_tensor(np.random.RandomState(52), 1, 3, 64, 96)
+    cs = m(x)
+    out = {f"c{i + 2}": c.detach().numpy() for i, c in enumerate(cs)}
+    rng = np.random.RandomState(53)
+    ws = [torch.from_numpy(rng.randn(*c.shape).astype(np.float32)) for c in cs]
+    sum((c * w).sum() for c, w in zip(cs, ws)).backward()
+    params = dict(m.named_parameters())
+    out["trainable"] = np.array(sorted(n for n, p in params.items() if p.requires_grad))
+    out["no_grad"] = np.array(sorted(n for n, p in params.items() if p.requires_grad and p.grad is None))
+    for k in RLA_GRAD_KEYS:
+        g = params[k].grad.reshape(-1)
+        out["grad:" + k] = (g[::97] if g.numel() > 4096 else g).numpy()   # large tensors: every 97th element
+    np.savez_compressed(os.path.join(OUT, "rla_backbone.npz"), **out)
 
 
 def gen_decode(R):
@@ -485,6 +518,7 @@ def main():
     gen_head_fwd(R)
     gen_loss(R)
     gen_backbone(R)
+    gen_rla_backbone(R)
     gen_decode(R)
     gen_misc(R)
     gen_hook_chain(R)

@@ -231,8 +231,12 @@ def install():
         def __init__(self, *a, **k):
             pass
 
+    def _no_checkpoint(*a, **k):   # resnet_rla.py imports these; the oracle never loads a checkpoint file
+        raise RuntimeError("checkpoint loading is not part of the oracle")
+
     mmcv.runner = mod("mmcv.runner", BaseModule=BaseModule, Sequential=Sequential, ModuleList=ModuleList,
-                      force_fp32=_identity_decorator, auto_fp16=_identity_decorator, OptimizerHook=OptimizerHook)
+                      force_fp32=_identity_decorator, auto_fp16=_identity_decorator, OptimizerHook=OptimizerHook,
+                      load_checkpoint=_no_checkpoint, load_state_dict=_no_checkpoint)
 
     def _no_cuda_focal(*a, **k):
         raise RuntimeError("mmcv.ops.sigmoid_focal_loss is CUDA-only; the CPU oracle uses py_sigmoid_focal_loss")

@@ -110,6 +110,13 @@ def load():
     return ns
 
 
+def load_rla():
+    """RLA_ResNet (mmdet/models/backbones/resnet_rla.py:140-400), the backbone of the shipped DSL config
+    (configs/fcos_semi/RLA_*.py:3-13), imported from the reference tree after load()."""
+    load()
+    return importlib.import_module("mmdet.models.backbones.resnet_rla").RLA_ResNet
+
+
 def load_hook_functions():
     """parse_det_results / adathres from mmdet/runner/hooks/unlabel_pred_hook.py, executed without importing the
     module's heavy dependencies: only the two pure-Python function bodies are compiled from the source file."""

@@ -88,3 +88,47 @@ def fill_state_dict_(sd, seed, skip=()):
         else:  # biases
             v.copy_(make_tensor(rng, *v.shape, scale=0.1))
     return sd
+
+
+def rla_state_dict(seed, layers=(3, 4, 6, 3), rla_channel=32):
+    """Seeded state_dict of RLA_ResNet (reference names: mmdet/models/backbones/resnet_rla.py:205-268). Every tensor is
+    drawn from its own RandomState(crc32(name) ^ seed), so the values do not depend on key order. Gains are chosen so
+    that activations stay O(1) through 16 residual blocks and the tanh of the state update is not saturated."""
+    import zlib
+    from collections import OrderedDict
+    sd = OrderedDict()
+
+    def rs(name):
+        return np.random.RandomState((zlib.crc32(name.encode()) ^ seed) & 0x7fffffff)
+
+    def conv(name, o, i, k, gain=1.0):
+        sd[name + ".weight"] = make_tensor(rs(name), o, i, k, k, scale=gain * (2.0 / (i * k * k)) ** 0.5)
+
+    def bn(name, c, gain=1.0):
+        r = rs(name)
+        sd[name + ".weight"] = torch.from_numpy(((r.rand(c) + 0.5) * gain).astype(np.float32))
+        sd[name + ".bias"] = make_tensor(r, c, scale=0.1)
+        sd[name + ".running_mean"] = make_tensor(r, c, scale=0.1)
+        sd[name + ".running_var"] = torch.from_numpy((r.rand(c) + 0.5).astype(np.float32))
+
+    conv("conv1", 64, 3, 7)
+    bn("bn1", 64)
+    inpl = 64
+    for li, nb in enumerate(layers):
+        planes = 64 * 2 ** li
+        conv(f"conv_outs.{li}", rla_channel, planes * 4, 1, gain=0.5)
+        conv(f"recurrent_convs.{li}", rla_channel, rla_channel, 3)
+        for bi in range(nb):
+            p = f"stages.{li}.{bi}"
+            conv(p + ".conv1", planes, inpl + rla_channel, 1)
+            bn(p + ".bn1", planes)
+            conv(p + ".conv2", planes, planes, 3)
+            bn(p + ".bn2", planes)
+            conv(p + ".conv3", planes * 4, planes, 1)
+            bn(p + ".bn3", planes * 4, gain=0.3)
+            if bi == 0:
+                conv(p + ".downsample.0", planes * 4, inpl, 1, gain=0.7)
+                bn(p + ".downsample.1", planes * 4)
+            bn(f"stage_bns.{li}.{bi}", rla_channel)
+            inpl = planes * 4
+    return sd

@@ -184,6 +184,31 @@ def test_backbone_fpn_match_reference():
         np.testing.assert_allclose(p.numpy(), g[f"p{i + 3}"], rtol=1e-4, atol=1e-4)
 
 
+def test_rla_resnet_matches_reference():
+    """The restatement of RLA_ResNet (incl. the aliased `y`, the pooled state and which BatchNorm parameters train) vs
+    the reference's own class: stage outputs, the trainable set of params.rla_resnet_spec, sampled gradients."""
+    from dsl_b200.params import rla_resnet_spec
+    g = load("rla_backbone.npz")
+    sd = GI.rla_state_dict(51)
+    spec = {p.name: p for p in rla_resnet_spec(prefix="")}
+    assert sorted(n for n, p in spec.items() if p.region != "F") == list(g["trainable"])
+    assert len(g["no_grad"]) == 0
+    sd = {k: v.clone().requires_grad_(k in spec and spec[k].region != "F") for k, v in sd.items()}
+    x = GI.make_tensor(np.random.RandomState(52), 1, 3, 64, 96)
+    cs = O.rla_resnet_forward(sd, x)
+    for i, c in enumerate(cs):
+        np.testing.assert_allclose(c.detach().numpy(), g[f"c{i + 2}"], rtol=1e-4, atol=1e-4)
+    rng = np.random.RandomState(53)
+    ws = [torch.from_numpy(rng.randn(*c.shape).astype(np.float32)) for c in cs]
+    sum((c * w).sum() for c, w in zip(cs, ws)).backward()
+    keys = [k[5:] for k in g.files if k.startswith("grad:")]
+    assert len(keys) == 10
+    for k in keys:
+        got = sd[k].grad.reshape(-1)
+        got = (got[::97] if got.numel() > 4096 else got).numpy()
+        np.testing.assert_allclose(got, g["grad:" + k], rtol=2e-3, atol=2e-3 * np.abs(g["grad:" + k]).max())
+
+
 def test_decode_gate_nms_match_reference():
     g = load("decode.npz")
     B, H, W = 2, 512, 640

@@ -425,7 +425,7 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = {"dslb_conv_seg_t": L.ConvSeg, "dslb_wgrad_seg_t": L.WgradSeg, "dslb_gn_seg_t": L.GnSeg,
              "dslb_pack_desc_t": L.PackDesc, "dslb_unpack_desc_t": L.UnpackDesc, "dslb_fcos_level_t": L.FcosLevel,
-             "dslb_view_t": View}
+             "dslb_view_t": View, "dslb_bn_grad_desc_t": L.BnGradDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dslb.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
