@@ -49,6 +49,7 @@ class ConvPlan:
                 elif v is not None:
                     setattr(a, k, v)
         self.plan = C.c_void_p()
+        self._lib = L.lib   # the library that owns the plan handle
         L.check(L.lib.dslb_conv_plan_create(arr, len(segs), C.byref(self.plan)), what)
         self.flops = L.lib.dslb_conv_plan_flops(self.plan)
 
@@ -58,7 +59,7 @@ class ConvPlan:
     def __del__(self):
         try:
             if self.plan:
-                L.lib.dslb_conv_plan_destroy(self.plan)
+                self._lib.dslb_conv_plan_destroy(self.plan)
         except Exception:
             pass
 
@@ -76,6 +77,7 @@ class WgradPlan:
                 else:
                     setattr(a, k, v)
         self.plan = C.c_void_p()
+        self._lib = L.lib   # the library that owns the plan handle
         L.check(L.lib.dslb_wgrad_plan_create(arr, len(segs), C.byref(self.plan)), what)
         self.flops = L.lib.dslb_wgrad_plan_flops(self.plan)
 
@@ -85,7 +87,7 @@ class WgradPlan:
     def __del__(self):
         try:
             if self.plan:
-                L.lib.dslb_wgrad_plan_destroy(self.plan)
+                self._lib.dslb_wgrad_plan_destroy(self.plan)
         except Exception:
             pass
 
@@ -106,6 +108,7 @@ class TablePlan:
                 elif v is not None:
                     setattr(a, k, v)
         self.plan = C.c_void_p()
+        self._lib = L.lib   # the library that owns the plan handle
         fn = L.lib.dslb_pack_plan_create if kind == "pack" else L.lib.dslb_unpack_plan_create
         L.check(fn(arr, len(descs), C.byref(self.plan)), what)
 
@@ -115,7 +118,7 @@ class TablePlan:
     def __del__(self):
         try:
             if self.plan:
-                L.lib.dslb_table_plan_destroy(self.plan)
+                self._lib.dslb_table_plan_destroy(self.plan)
         except Exception:
             pass
 
@@ -885,9 +888,9 @@ class FCOSNet:
         # trainable BatchNorms folded into those convs (RLA_ResNet): dgamma from the packed weight gradients, one launch
         bnd = [(n, d) for n, d in getattr(self, "bn_grad_descs", []) if n.startswith(prefixes) and n not in self._unpacked]
         if bnd:
-            from .engine_rla import BnGradPlan
+            from .engine_rla import BnGradPlan, bn_grad_desc
             self._unpacked.update(n for n, _ in bnd)
-            bplan = BnGradPlan([d for _, d in bnd])
+            bplan = BnGradPlan([bn_grad_desc(self, n, convs) for n, convs in bnd])
             self.bn_grad_plans = getattr(self, "bn_grad_plans", []) + [bplan]
             self.add_bwd(bplan.run, side=True, tag="bn_grads")
         plan = TablePlan(descs, "unpack", "unpack_wgrads")

@@ -136,6 +136,7 @@ class BnGradPlan:
                 elif v is not None:
                     setattr(a, k, v)
         self.plan = C.c_void_p()
+        self._lib = L.lib   # the library that owns the plan handle
         L.check(L.lib.dslb_bn_grad_plan_create(arr, len(descs), C.byref(self.plan)), "bn_grad_plan")
 
     def run(self):
@@ -144,7 +145,7 @@ class BnGradPlan:
     def __del__(self):
         try:
             if self.plan:
-                L.lib.dslb_bn_grad_plan_destroy(self.plan)
+                self._lib.dslb_bn_grad_plan_destroy(self.plan)
         except Exception:
             pass
 
@@ -152,6 +153,7 @@ class BnGradPlan:
 def bn_grad_desc(net, bn, convs):
     """Descriptor of one trainable BatchNorm folded into `convs` (one ConvW, or the two halves of an RLA conv1)."""
     st = net.store
+    assert all(c.dw is not None for c in convs), "weight-gradient accumulators are not allocated yet"
     d = dict(mean=st[bn + ".running_mean"], var=st[bn + ".running_var"], dbeta=net.grad_view(bn + ".bias"),
              dgamma=net.grad_view(bn + ".weight"), O=convs[0].O, R=convs[0].R, S=convs[0].S, bn_eps=1e-5)
     for k, c in enumerate(convs):
@@ -185,7 +187,7 @@ def build_backbone(net):
 
     net.blocks = []
     net.stage_out = []
-    net.bn_grad_descs = []     # (name of the BatchNorm, descriptor) of every trainable folded BatchNorm
+    net.bn_grad_descs = []     # (name of the BatchNorm, convs) of every trainable folded BatchNorm
     layers = RESNET_BLOCKS[net.depth]
     x, h, w, inpl = net.x0, H4, W4, 64
     hstate = net.buf(B, H4, W4, HLD)       # h0 = zeros (resnet_rla.py:296-300); never written
@@ -230,11 +232,11 @@ def build_backbone(net):
             net.plan_fwd([blk["c3"].fseg(blk["a2"], blk["out"], B, ho, wo, residual=blk.get("idn", x),
                                          relu_nch=planes * 4)], p + ".conv3")
             if trainable:
-                net.bn_grad_descs += [(p + ".bn1", bn_grad_desc(net, p + ".bn1", [c1x, c1h])),
-                                      (p + ".bn2", bn_grad_desc(net, p + ".bn2", [blk["c2"]])),
-                                      (p + ".bn3", bn_grad_desc(net, p + ".bn3", [blk["c3"]]))]
+                # (BatchNorm name, convs it is folded into): descriptors are built at bucket time, once the weight-
+                # gradient accumulators exist (FCOSNet._alloc_arena)
+                net.bn_grad_descs += [(p + ".bn1", [c1x, c1h]), (p + ".bn2", [blk["c2"]]), (p + ".bn3", [blk["c3"]])]
                 if bi == 0:
-                    net.bn_grad_descs.append((p + ".downsample.1", bn_grad_desc(net, p + ".downsample.1", [blk["ds"]])))
+                    net.bn_grad_descs.append((p + ".downsample.1", [blk["ds"]]))
             if not last:
                 # RLA module update (resnet_rla.py:306-311)
                 blk["yo"] = net.buf(B, ho, wo, HLD)

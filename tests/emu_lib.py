@@ -1,0 +1,315 @@
+"""TEST INFRASTRUCTURE ONLY — a CPU stand-in for the subset of libdslb.so's C ABI (include/dslb.h) that a
+FCOSNet(parts="backbone") plan calls, so the HOST-side plan logic of dsl_b200/engine.py / engine_rla.py (which buffer
+feeds which launch, masks, residuals, gradient routing, operand packing with folded BatchNorm, buckets) can be executed
+and checked against the oracle without a GPU. Each function implements the contract written in include/dslb.h with torch
+fp32 math and bf16 rounding where the kernels round. It is never imported by the product; the CUDA kernels themselves are
+checked on the GPU (`-m gpu` tests).
+
+Usage:  with emu_lib.installed(): net = FCOSNet(..., device="cpu", parts="backbone"); net.forward(); net.backward()
+"""
+import contextlib
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, C.c_void_p):
+        return p.value or 0
+    return int(p)
+
+
+def view(p, n, dtype):
+    """Writable torch view of n elements at host address p."""
+    a = _addr(p)
+    assert a != 0
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    buf = (C.c_char * nbytes).from_address(a)
+    return torch.frombuffer(buf, dtype=dtype, count=n)
+
+
+def _rows(p, nrows, ld, dtype):
+    return view(p, nrows * ld, dtype).view(nrows, ld)
+
+
+class _Plan:
+    def __init__(self, kind, items):
+        self.kind, self.items = kind, items
+
+
+class EmuLib:
+    """Attribute access returns the emulated entry point; anything not emulated raises."""
+
+    def __init__(self):
+        self.plans = {}
+        self.next_handle = 1
+        self.calls = []
+
+    def __getattr__(self, name):
+        raise AttributeError(f"emu_lib: {name} is not emulated")
+
+    def _new(self, out_ref, plan):
+        h = self.next_handle
+        self.next_handle += 1
+        self.plans[h] = plan
+        out_ref._obj.value = h
+        return 0
+
+    def _get(self, h):
+        return self.plans[_addr(h)]
+
+    def dslb_last_error(self):
+        return b"emulated"
+
+    # ------------------------------------------------------------------------------------------ conv plans
+    def dslb_conv_plan_create(self, segs, n, out):
+        fields = [f for f, _ in type(segs[0])._fields_]
+        items = [{f: getattr(segs[i], f) for f in fields} for i in range(n)]
+        for s in items:
+            assert s["Cin"] % 64 == 0 and s["cout_pad"] % 16 == 0 and s["cout_pad"] >= s["Cout"], s
+            assert s["ldc"] >= s["Cout"]
+        return self._new(out, _Plan("conv", items))
+
+    def dslb_conv_plan_flops(self, h):
+        return 0.0
+
+    def dslb_conv_plan_destroy(self, h):
+        self.plans.pop(_addr(h), None)
+
+    def dslb_conv_plan_run(self, h, stream):
+        for s in self._get(h).items:
+            self._conv_seg(s)
+        return 0
+
+    def _conv_seg(self, s):
+        N, H, W, Cin, Cout, R, S = s["N"], s["H"], s["W"], s["Cin"], s["Cout"], s["R"], s["S"]
+        st, pad, ldc = s["stride"], s["pad"], s["ldc"]
+        x = view(s["x"], N * H * W * Cin, BF16).view(N, H, W, Cin).permute(0, 3, 1, 2).float()
+        w = view(s["w"], R * S * s["cout_pad"] * Cin, BF16).view(R, S, s["cout_pad"], Cin).permute(2, 3, 0, 1).float()
+        acc = F.conv2d(x, w[:Cout].contiguous(), stride=st, padding=pad)
+        Ho, Wo = acc.shape[2], acc.shape[3]
+        v = acc.permute(0, 2, 3, 1).reshape(-1, Cout)
+        if s["scale"]:
+            v = v * view(s["scale"], Cout, torch.float32)
+        if s["shift"]:
+            v = v + view(s["shift"], Cout, torch.float32)
+        npix = N * Ho * Wo
+        ydt = torch.float32 if s["out_fp32"] else BF16
+        if s["scatter2"]:
+            Hs, Ws = s["Hs"], s["Ws"]
+            ymap = view(s["y"], N * Hs * Ws * ldc, ydt).view(N, Hs, Ws, ldc)
+            ysel = ymap[:, 0:2 * Ho:2, 0:2 * Wo:2, :Cout]
+            if s["residual"]:
+                r = view(s["residual"], N * Hs * Ws * ldc, BF16).view(N, Hs, Ws, ldc)[:, 0:2 * Ho:2, 0:2 * Wo:2, :Cout]
+                v = v + r.reshape(-1, Cout).float()
+            assert not s["relu_mask"] and not s["relu_nch"]
+            ysel.copy_(v.view(N, Ho, Wo, Cout).to(ydt))
+            return
+        if s["residual"]:
+            v = v + _rows(s["residual"], npix, ldc, BF16)[:, :Cout].float()
+        if s["relu_nch"]:
+            k = min(s["relu_nch"], Cout)
+            v = torch.cat([v[:, :k].clamp_min(0), v[:, k:]], dim=1)
+        if s["relu_mask"]:
+            m = _rows(s["relu_mask"], npix, ldc, BF16)[:, :Cout].float()
+            v = torch.where(m > 0, v, torch.zeros_like(v))
+        assert not s["gn_stats"], "GroupNorm statistics are not emulated"
+        _rows(s["y"], npix, ldc, ydt)[:, :Cout] = v.to(ydt)
+
+    # ------------------------------------------------------------------------------------------ wgrad plans
+    def dslb_wgrad_plan_create(self, segs, n, out):
+        fields = [f for f, _ in type(segs[0])._fields_]
+        items = [{f: getattr(segs[i], f) for f in fields} for i in range(n)]
+        for s in items:
+            assert s["Cin"] % 64 == 0 and s["ldy"] % 64 == 0 and s["ldy"] >= s["Cout"] and s["dw_rows"] >= s["Cout"], s
+        return self._new(out, _Plan("wgrad", items))
+
+    def dslb_wgrad_plan_flops(self, h):
+        return 0.0
+
+    def dslb_wgrad_plan_destroy(self, h):
+        self.plans.pop(_addr(h), None)
+
+    def dslb_wgrad_plan_run(self, h, stream):
+        for s in self._get(h).items:
+            N, H, W, Cin, Cout, R, S = s["N"], s["H"], s["W"], s["Cin"], s["Cout"], s["R"], s["S"]
+            st, pad = s["stride"], s["pad"]
+            Ho, Wo = (H + 2 * pad - R) // st + 1, (W + 2 * pad - S) // st + 1
+            x = view(s["x"], N * H * W * Cin, BF16).view(N, H, W, Cin).permute(0, 3, 1, 2).float()
+            dy_full = _rows(s["dy"], N * Ho * Wo, s["ldy"], BF16).float()
+            assert float(dy_full[:, Cout:].abs().max() if s["ldy"] > Cout else 0.0) == 0.0, "dy padding must be zero"
+            dy = dy_full[:, :Cout].reshape(N, Ho, Wo, Cout).permute(0, 3, 1, 2)
+            g = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, S), dy.contiguous(), stride=st, padding=pad)
+            dw = view(s["dw"], R * S * s["dw_rows"] * Cin, torch.float32).view(R * S, s["dw_rows"], Cin)
+            dw[:, :Cout] += g.permute(2, 3, 0, 1).reshape(R * S, Cout, Cin)
+        return 0
+
+    # ------------------------------------------------------------------------------------------ pack / unpack
+    def dslb_pack_plan_create(self, descs, n, out):
+        fields = [f for f, _ in type(descs[0])._fields_]
+        return self._new(out, _Plan("pack", [{f: getattr(descs[i], f) for f in fields} for i in range(n)]))
+
+    def dslb_unpack_plan_create(self, descs, n, out):
+        fields = [f for f, _ in type(descs[0])._fields_]
+        return self._new(out, _Plan("unpack", [{f: getattr(descs[i], f) for f in fields} for i in range(n)]))
+
+    def dslb_table_plan_destroy(self, h):
+        self.plans.pop(_addr(h), None)
+
+    @staticmethod
+    def _w_slice(p, O, I, RS, ld):
+        flat = view(p, (O - 1) * ld * RS + I * RS, torch.float32)
+        return torch.as_strided(flat, (O, I, RS), (ld * RS, RS, 1))
+
+    def dslb_table_plan_run(self, h, stream):
+        plan = self._get(h)
+        for d in plan.items:
+            O, I, R, S = d["O"], d["I"], d["R"], d["S"]
+            RS = R * S
+            sc = torch.ones(O)
+            if d["bn_gamma"]:
+                sc = view(d["bn_gamma"], O, torch.float32) / torch.sqrt(view(d["bn_var"], O, torch.float32) + d["bn_eps"])
+            if plan.kind == "pack":
+                ld = d["w_ld"] or I
+                w = self._w_slice(d["w"], O, I, RS, ld) * sc.view(O, 1, 1)          # [O][I][RS]
+                rp, cp = d["rows_pad"], d["cols_pad"]
+                out = view(d["out"], RS * rp * cp, BF16).view(RS, rp, cp)
+                assert d["mode"] in (0, 1)
+                if d["mode"] == 0:
+                    blk = w.permute(2, 0, 1)                                          # [tap][o][i]
+                    if d["bn_gamma"]:
+                        view(d["scale_out"], O, torch.float32).copy_(sc)
+                        view(d["shift_out"], O, torch.float32).copy_(
+                            view(d["bn_beta"], O, torch.float32) - view(d["bn_mean"], O, torch.float32) * sc)
+                else:
+                    blk = w.permute(2, 1, 0).flip(0)                                  # [RS-1-tap][i][o]
+                r0, c0 = d["row_off"], d["col_off"]
+                if d["fill_padding"]:
+                    assert r0 == 0 and c0 == 0
+                    out.zero_()
+                out[:, r0:r0 + blk.shape[1], c0:c0 + blk.shape[2]] = blk.to(BF16)
+            else:
+                ldd, ldg = d["dw_ld"] or I, d["g_ld"] or I
+                dw = view(d["dw"], RS * d["rows"] * ldd, torch.float32).view(RS, d["rows"], ldd)
+                g = self._w_slice(d["g"], O, I, RS, ldg)
+                g.copy_((dw[:, d["row_off"]:d["row_off"] + O, :I] * sc.view(1, O, 1)).permute(1, 2, 0))
+        return 0
+
+    # ------------------------------------------------------------------------------------------ glue kernels
+    def dslb_stem_conv(self, img, w, g, b, mean, var, eps, ws, out, N, H, W, stream):
+        x = view(img, N * 3 * H * W, torch.float32).view(N, 3, H, W)
+        wt = view(w, 64 * 147, torch.float32).view(64, 3, 7, 7)
+        sc = view(g, 64, torch.float32) / torch.sqrt(view(var, 64, torch.float32) + eps)
+        sh = view(b, 64, torch.float32) - view(mean, 64, torch.float32) * sc
+        y = F.conv2d(x.to(BF16).float(), (wt * sc.view(64, 1, 1, 1)).to(BF16).float(), stride=2, padding=3)
+        y = F.relu(y + sh.view(1, 64, 1, 1))
+        Ho, Wo = y.shape[2], y.shape[3]
+        view(out, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64).copy_(y.permute(0, 2, 3, 1).to(BF16))
+        return 0
+
+    def dslb_maxpool3x3s2(self, x, y, N, H, W, Cc, stream):
+        xi = view(x, N * H * W * Cc, BF16).view(N, H, W, Cc).permute(0, 3, 1, 2).float()
+        yo = F.max_pool2d(xi, 3, 2, 1)
+        view(y, yo.numel(), BF16).view(N, yo.shape[2], yo.shape[3], Cc).copy_(yo.permute(0, 2, 3, 1).to(BF16))
+        return 0
+
+    def dslb_relu_family(self, x, m, y, n, mode, stream):
+        xv = view(x, n, BF16).float()
+        if mode == 0:
+            r = xv.clamp_min(0)
+        elif mode == 1:
+            r = torch.where(view(m, n, BF16).float() > 0, xv, torch.zeros_like(xv))
+        else:
+            r = xv + view(m, n, BF16).float()
+        view(y, n, BF16).copy_(r.to(BF16))
+        return 0
+
+    def dslb_colsum(self, x, out, npix, ld, Cc, stream):
+        view(out, Cc, torch.float32).add_(_rows(x, npix, ld, BF16)[:, :Cc].float().sum(0))
+        return 0
+
+    def dslb_zero_upsample2(self, x, y, N, h, w, H, W, Cc, stream):
+        yo = view(y, N * H * W * Cc, BF16).view(N, H, W, Cc)
+        yo.zero_()
+        yo[:, 0:2 * h:2, 0:2 * w:2] = view(x, N * h * w * Cc, BF16).view(N, h, w, Cc)
+        return 0
+
+    # ------------------------------------------------------------------------------------------ RLA
+    @staticmethod
+    def _rla_pre(h_old, y_out, N, Ho, Wo, pool):
+        y = view(y_out, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32].float()
+        if pool:
+            h = view(h_old, N * 4 * Ho * Wo * 64, BF16).view(N, 2 * Ho, 2 * Wo, 64)[..., :32].float()
+            h = h.view(N, Ho, 2, Wo, 2, 32).sum(dim=(2, 4)) * 0.25
+        else:
+            h = view(h_old, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32].float()
+        return h + y
+
+    def dslb_rla_state_fwd(self, h_old, y_out, g, b, mean, var, eps, hb, N, Ho, Wo, pool, stream):
+        f32 = lambda p: view(p, 32, torch.float32)  # noqa: E731
+        pre = self._rla_pre(h_old, y_out, N, Ho, Wo, pool)
+        sc = f32(g) / torch.sqrt(f32(var) + eps)
+        out = torch.tanh(pre * sc + (f32(b) - f32(mean) * sc))
+        view(hb, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32] = out.to(BF16)
+        return 0
+
+    def dslb_rla_state_bwd(self, d_hb, hb, h_old, y_out, g, mean, var, eps, d_pre, dh_old, dgamma, dbeta, N, Ho, Wo,
+                           pool, stream):
+        f32 = lambda p: view(p, 32, torch.float32)  # noqa: E731
+        pre = self._rla_pre(h_old, y_out, N, Ho, Wo, pool)
+        t = view(hb, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32].float()
+        dh = view(d_hb, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32].float()
+        rstd = 1.0 / torch.sqrt(f32(var) + eps)
+        gg = dh * (1 - t * t)
+        if _addr(dgamma):
+            f32(dbeta).add_(gg.sum(dim=(0, 1, 2)))
+            f32(dgamma).add_((gg * (pre - f32(mean)) * rstd).sum(dim=(0, 1, 2)))
+        o = (gg * f32(g) * rstd).to(BF16)
+        view(d_pre, N * Ho * Wo * 64, BF16).view(N, Ho, Wo, 64)[..., :32] = o
+        if pool:
+            q = (o.float() * 0.25).to(BF16)
+            up = q.view(N, Ho, 1, Wo, 1, 32).expand(N, Ho, 2, Wo, 2, 32).reshape(N, 2 * Ho, 2 * Wo, 32)
+            view(dh_old, N * 4 * Ho * Wo * 64, BF16).view(N, 2 * Ho, 2 * Wo, 64)[..., :32] = up
+        return 0
+
+    def dslb_bn_grad_plan_create(self, descs, n, out):
+        fields = [f for f, _ in type(descs[0])._fields_]
+        return self._new(out, _Plan("bn", [{f: getattr(descs[i], f) for f in fields} for i in range(n)]))
+
+    def dslb_bn_grad_plan_destroy(self, h):
+        self.plans.pop(_addr(h), None)
+
+    def dslb_bn_grad_plan_run(self, h, stream):
+        for d in self._get(h).items:
+            O, RS = d["O"], d["R"] * d["S"]
+            dot = torch.zeros(O)
+            for k in (0, 1):
+                if not d[f"dw{k}"]:
+                    continue
+                I, ldd, ldw, rows = d[f"I{k}"], d[f"dw_ld{k}"] or d[f"I{k}"], d[f"w_ld{k}"] or d[f"I{k}"], d[f"rows{k}"]
+                dw = view(d[f"dw{k}"], RS * rows * ldd, torch.float32).view(RS, rows, ldd)[:, :O, :I]
+                w = self._w_slice(d[f"w{k}"], O, I, RS, ldw)
+                dot += (dw.permute(1, 2, 0) * w).sum(dim=(1, 2))
+            mean, var = view(d["mean"], O, torch.float32), view(d["var"], O, torch.float32)
+            view(d["dgamma"], O, torch.float32).copy_(
+                (dot - mean * view(d["dbeta"], O, torch.float32)) / torch.sqrt(var + d["bn_eps"]))
+        return 0
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap dsl_b200._lib.lib (and the stream lookup) for the emulator inside the block."""
+    from dsl_b200 import _lib as L
+    real_lib, real_stream = L.lib, L.cur_stream
+    emu = EmuLib()
+    L.lib = emu
+    L.cur_stream = lambda: None
+    try:
+        yield emu
+    finally:
+        L.lib, L.cur_stream = real_lib, real_stream

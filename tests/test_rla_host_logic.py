@@ -1,0 +1,94 @@
+"""Host-side plan logic of the backbones on CPU: FCOSNet(parts="backbone") is built and run against tests/emu_lib.py (a
+torch restatement of the C-ABI contracts in include/dslb.h), and its stage outputs and parameter gradients are compared
+with the oracle. The ResNet case validates the emulator on the plan the GPU tests already cover; the RLA_ResNet case
+checks engine_rla.py's dataflow (concat-as-two-launches conv1, pooled state, in-place masked gradients, trainable
+BatchNorm affines, sliced pack / unpack, gradient buckets). Kernel numerics are the `-m gpu` tests' job."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fcos_oracle as O
+from tests import emu_lib
+from tests.golden import inputs as GI
+
+
+def _run(backbone, sd_ref, spec_fn, fwd_fn):
+    from dsl_b200.engine import FCOSNet
+    from dsl_b200.params import ParamStore
+    x = GI.make_tensor(np.random.RandomState(52), 1, 3, 64, 96)
+    with emu_lib.installed():
+        store = ParamStore(spec_fn(), "cpu")
+        store.load_state_dict(sd_ref)
+        net = FCOSNet(1, 64, 96, depth=50, train=True, store=store, device="cpu", parts="backbone", backbone=backbone)
+        net.img.copy_(x)
+        net.forward()
+        outs = [so[0].float().permute(0, 3, 1, 2) for so in net.stage_out]
+        rng = np.random.RandomState(53)
+        ws = [torch.from_numpy(rng.randn(*o.shape).astype(np.float32)).bfloat16().float() for o in outs]
+        for g, wt in zip(net.gc, ws[1:]):
+            g.copy_(wt.permute(0, 2, 3, 1).bfloat16())
+        net.backward()
+        grads = {p.name: net.grad_view(p.name).clone().view(p.shape) for p in store.spec if p.region != "F"}
+        ranges = sorted((lo, hi) for _, lo, hi in net.bwd_buckets)
+    sd = {k: v.clone().requires_grad_(k in grads) for k, v in sd_ref.items()}
+    ref = fwd_fn(sd, x)
+    sum((c * wt).sum() for c, wt in zip(ref[1:], ws[1:])).backward()
+    return outs, ref, grads, sd, ranges, store
+
+
+def _cos(a, b):
+    a, b = a.reshape(-1).double(), b.reshape(-1).double()
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+
+
+def _floor(name):
+    """bf16 rounding noise grows towards the input (more layers of backward behind the gradient): same graded floors as
+    the GPU test of the standalone ResNet module (tests/test_plugin.py)."""
+    if name.startswith(("layer4", "stages.3", "stage_bns.3", "conv_outs.3", "recurrent_convs.3")):
+        return 0.985
+    if name.startswith(("layer3", "stages.2", "stage_bns.2", "conv_outs.2", "recurrent_convs.2")):
+        return 0.97
+    return 0.93
+
+
+def _check(outs, ref, grads, sd, min_checked):
+    for got, want in zip(outs, ref):
+        err = (got - want.detach()).norm().item() / want.norm().item()
+        assert err < 2e-2, err
+    bad = []
+    for name, g in grads.items():
+        r = sd[name].grad
+        assert r is not None, name
+        c = _cos(g, r)
+        ratio = g.norm().item() / (r.norm().item() + 1e-30)
+        if c < _floor(name) or abs(ratio - 1) > 0.1:
+            bad.append((name, round(c, 4), round(ratio, 4)))
+    assert not bad, (len(bad), bad[:8])
+    assert len(grads) >= min_checked
+
+
+def test_resnet_backbone_plan_on_the_emulator():
+    from dsl_b200.params import ParamStore, resnet_spec
+    st = ParamStore(resnet_spec(50, prefix=""), "cpu").init_reference(3)   # Kaiming convs, bounded residual gains
+    rng = np.random.RandomState(7)
+    bb = {}
+    for p in st.spec:
+        v = st[p.name].clone()
+        if p.kind in ("bn_b", "bn_mean"):
+            v = torch.from_numpy((rng.randn(*p.shape) * 0.1).astype(np.float32))
+        elif p.kind == "bn_var":
+            v = torch.from_numpy((rng.rand(*p.shape) + 0.5).astype(np.float32))
+        bb[p.name] = v
+    outs, ref, grads, sd, _, _ = _run("resnet", bb, lambda: resnet_spec(50, prefix=""),
+                                      lambda s, x: O.resnet_forward(s, x, depth=50))
+    _check(outs, ref, grads, sd, 35)
+
+
+def test_rla_resnet_backbone_plan_on_the_emulator():
+    from dsl_b200.params import rla_resnet_spec
+    sd0 = GI.rla_state_dict(51)
+    outs, ref, grads, sd, ranges, store = _run("rla", sd0, lambda: rla_resnet_spec(prefix=""),
+                                               lambda s, x: O.rla_resnet_forward(s, x))
+    _check(outs, ref, grads, sd, 156)
+    # the gradient buckets tile the trainable range: [stages 2-3 | stage 4]
+    assert ranges[0][0] == 0 and ranges[-1][1] == store.n_train and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
