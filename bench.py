@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU (default: the benchmark config)")
     ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--backbone", default="resnet", choices=["resnet", "rla"],
+                    help="rla: RLA_ResNet, the backbone of the shipped DSL configs (not the BASELINE.json config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-hw", default="800x1344", help="HxW of the bounded CPU sample")
     return ap.parse_args()
@@ -188,7 +190,7 @@ def main():
     from tests.golden import inputs as GI
 
     B = args.batch
-    eng = DSLEngine(B, H, W, depth=args.depth, seed=0, use_graphs=True)
+    eng = DSLEngine(B, H, W, depth=args.depth, seed=0, use_graphs=True, backbone=args.backbone)
     rng = np.random.RandomState(100 + rank)
     # synthetic COCO-shaped batch in PINNED host memory (mean-subtracted pixels, caffe normalisation: std 1)
     img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
@@ -289,7 +291,9 @@ def main():
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, teacher_batch=B,
+                config=dict(workload=WORKLOAD if args.backbone == "resnet" else WORKLOAD.replace(
+                    "configs[1]: FCOS-R50-FPN", "variant of configs[1] with the shipped configs' RLA_ResNet backbone: FCOS-RLA_R50-FPN"),
+                            global_batch=B * world, per_gpu_batch=B, teacher_batch=B,
                             parallelism=f"dp{world}", l2="working set (activations) >> 126 MB L2; no flush needed",
                             step="teacher fwd+decode gate, student fwd+loss+bwd, grad allreduce, clip+SGD, EMA, repack",
                             cuda_graph=True),

@@ -162,6 +162,16 @@ def bn_grad_desc(net, bn, convs):
     return d
 
 
+def _real_flops(net, plan, over, bwd):
+    """The plans count 2*MACs on the channel-padded operands; take the zero-padding part (`over`) out again so that the
+    reported FLOPs stay algorithmic (32-channel state, not its 64-channel storage)."""
+    plan.flops -= over
+    if bwd:
+        net.flops_bwd -= over
+    else:
+        net.flops_fwd -= over
+
+
 def stage_prefixes(net, li):
     p = net.bb_prefix
     return (f"{p}stages.{li}.", f"{p}stage_bns.{li}.", f"{p}conv_outs.{li}.", f"{p}recurrent_convs.{li}.")
@@ -226,7 +236,7 @@ def build_backbone(net):
                                      trainable=trainable)
                 blk["idn"] = net.buf(B, ho, wo, planes * 4)
                 segs.append(blk["ds"].fseg(x, blk["idn"], B, h, w))
-            net.plan_fwd(segs, p + ".conv1.h")
+            _real_flops(net, net.plan_fwd(segs, p + ".conv1.h"), 2.0 * B * h * w * planes * (HLD - RLA_CHANNEL), False)
             net.plan_fwd([c1x.fseg(x, blk["a1"], B, h, w, residual=blk["a1"], relu_nch=planes)], p + ".conv1.x")
             net.plan_fwd([blk["c2"].fseg(blk["a1"], blk["a2"], B, h, w, relu_nch=planes)], p + ".conv2")
             net.plan_fwd([blk["c3"].fseg(blk["a2"], blk["out"], B, ho, wo, residual=blk.get("idn", x),
@@ -243,11 +253,13 @@ def build_backbone(net):
                 blk["hb"] = net.buf(B, ho, wo, HLD)
                 blk["hout"] = net.buf(B, ho, wo, HLD)
                 sb = blk["sbn"]
-                net.plan_fwd([co.fseg(blk["out"], blk["yo"], B, ho, wo)], p + ".conv_out")
+                _real_flops(net, net.plan_fwd([co.fseg(blk["out"], blk["yo"], B, ho, wo)], p + ".conv_out"),
+                            2.0 * B * ho * wo * planes * 4 * (HLD - RLA_CHANNEL), False)
                 net.add_fwd(net.ew("dslb_rla_state_fwd", hstate, blk["yo"], st[sb + ".weight"], st[sb + ".bias"],
                                    st[sb + ".running_mean"], st[sb + ".running_var"], 1e-5, blk["hb"], B, ho, wo,
                                    int(s == 2)))
-                net.plan_fwd([rc.fseg(blk["hb"], blk["hout"], B, ho, wo)], p + ".recurrent_conv")
+                _real_flops(net, net.plan_fwd([rc.fseg(blk["hb"], blk["hout"], B, ho, wo)], p + ".recurrent_conv"),
+                            2.0 * B * ho * wo * 9 * (HLD * HLD - RLA_CHANNEL * RLA_CHANNEL), False)
                 hstate = blk["hout"]
             net.blocks.append(blk)
             x, h, w, inpl = blk["out"], ho, wo, planes * 4
@@ -284,16 +296,19 @@ def build_backbone_bwd(net):
             blk["d_hb"] = net.buf(B, h, w, HLD)
             blk["d_pre"] = net.buf(B, h, w, HLD)
             blk["dh_pool"] = net.buf(B, hin, win, HLD) if s == 2 else None
-            net.plan_bwd([rc.dseg(dh_out, blk["d_hb"], B, h, w, h, w)], name + ".recurrent_conv.dgrad")
+            _real_flops(net, net.plan_bwd([rc.dseg(dh_out, blk["d_hb"], B, h, w, h, w)], name + ".recurrent_conv.dgrad"),
+                        2.0 * B * h * w * 9 * (HLD * HLD - RLA_CHANNEL * RLA_CHANNEL), True)
             sb = blk["sbn"]
             net.add_bwd(net.ew("dslb_rla_state_bwd", blk["d_hb"], blk["hb"], blk["hin_state"], blk["yo"],
                                st[sb + ".weight"], st[sb + ".running_mean"], st[sb + ".running_var"], 1e-5,
                                blk["d_pre"], blk["dh_pool"], gv(sb + ".weight"), gv(sb + ".bias"), B, h, w, int(s == 2)))
-            net.plan_wgrad([rc.wseg(blk["hb"], dh_out, B, h, w), co.wseg(blk["out"], blk["d_pre"], B, h, w)],
-                           name + ".state.wgrad")
+            _real_flops(net, net.plan_wgrad([rc.wseg(blk["hb"], dh_out, B, h, w),
+                                             co.wseg(blk["out"], blk["d_pre"], B, h, w)], name + ".state.wgrad"),
+                        2.0 * B * h * w * 9 * RLA_CHANNEL * (HLD - RLA_CHANNEL), True)
             # M = (G + conv_out^T(d_pre)) * [out > 0], in place
-            net.plan_bwd([co.dseg(blk["d_pre"], G, B, h, w, h, w, residual=G, relu_mask=blk["out"])],
-                         name + ".conv_out.dgrad")
+            _real_flops(net, net.plan_bwd([co.dseg(blk["d_pre"], G, B, h, w, h, w, residual=G, relu_mask=blk["out"])],
+                                          name + ".conv_out.dgrad"),
+                        2.0 * B * h * w * planes * 4 * (HLD - RLA_CHANNEL), True)
             M = G
         blk["M"] = M
         blk["da2"] = net.buf(B, h, w, planes)
@@ -310,7 +325,7 @@ def build_backbone_bwd(net):
                  c1x.wseg(blk["xin"], blk["da1"], B, hin, win), c1h.wseg(blk["hin_state"], blk["da1"], B, hin, win)]
         if bi == 0:
             wsegs.append(blk["ds"].wseg(blk["xin"], M, B, hin, win))
-        net.plan_wgrad(wsegs, name + ".wgrad")
+        _real_flops(net, net.plan_wgrad(wsegs, name + ".wgrad"), 2.0 * B * hin * win * planes * (HLD - RLA_CHANNEL), True)
         # dbeta of the folded BatchNorms = column sums of the gradients w.r.t. their outputs
         p = f"{net.bb_prefix}{name}"
         net.add_bwd(net.ew("dslb_colsum", blk["da1"], gv(p + ".bn1.bias"), B * hin * win, planes, planes), side=True,
@@ -329,7 +344,8 @@ def build_backbone_bwd(net):
         prev["dh_out"] = net.buf(B, hin, win, HLD)
         res = None if blk["last"] else (blk["dh_pool"] if s == 2 else blk["d_pre"])
         kw = dict(residual=res) if res is not None else {}
-        net.plan_bwd([c1h.dseg(blk["da1"], prev["dh_out"], B, hin, win, hin, win, **kw)], name + ".conv1.h.dgrad")
+        _real_flops(net, net.plan_bwd([c1h.dseg(blk["da1"], prev["dh_out"], B, hin, win, hin, win, **kw)],
+                                      name + ".conv1.h.dgrad"), 2.0 * B * hin * win * planes * (HLD - RLA_CHANNEL), True)
         if bi > 0:
             # unmasked: the previous block adds its conv_out path and applies its ReLU mask
             prev["G"] = net.buf(B, hin, win, cin)

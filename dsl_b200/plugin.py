@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .params import ParamStore, fpn_spec, head_spec, resnet_spec
+from .params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
 
 INF = 1e8
 _DEFAULT_RANGES = ((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF))
@@ -168,13 +168,18 @@ class FCOS(_StoreModule):
     def __init__(self, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None, init_cfg=None):
         super().__init__()
         bb, nk, hd = dict(backbone), dict(neck), dict(bbox_head)
-        _check(bb.get("type", "ResNet") == "ResNet", f"backbone type {bb.get('type')}")
-        _check(bb.get("depth") in (50, 101), f"ResNet depth {bb.get('depth')}")
-        _check(bb.get("style", "pytorch") == "caffe", "ResNet style must be 'caffe' (stride on conv1)")
+        _check(bb.get("type", "ResNet") in ("ResNet", "RLA_ResNet"), f"backbone type {bb.get('type')}")
+        self.backbone_kind = "rla" if bb.get("type") == "RLA_ResNet" else "resnet"
+        if self.backbone_kind == "rla":      # configs/fcos_semi/RLA_*.py:3-13
+            bb["depth"] = RLA_ResNet.check_cfg(bb)
+        else:
+            _check(bb.get("depth") in (50, 101), f"ResNet depth {bb.get('depth')}")
+            _check(bb.get("style", "pytorch") == "caffe", "ResNet style must be 'caffe' (stride on conv1)")
+            _check(bb.get("norm_eval", True) and not dict(bb.get("norm_cfg", {})).get("requires_grad", True),
+                   "BatchNorm must be frozen (norm_eval=True, requires_grad=False)")
+            _check(tuple(bb.get("out_indices", (0, 1, 2, 3))) == (0, 1, 2, 3), "out_indices")
         _check(bb.get("frozen_stages", -1) == 1, "frozen_stages must be 1")
-        _check(bb.get("norm_eval", True) and not dict(bb.get("norm_cfg", {})).get("requires_grad", True),
-               "BatchNorm must be frozen (norm_eval=True, requires_grad=False)")
-        _check(tuple(bb.get("out_indices", (0, 1, 2, 3))) == (0, 1, 2, 3), "out_indices")
+        self.pretrained = bb.get("pretrained", pretrained)
         _check(nk.get("type", "FPN") == "FPN" and list(nk.get("in_channels")) == [256, 512, 1024, 2048]
                and nk.get("out_channels") == 256 and nk.get("start_level", 0) == 1 and nk.get("num_outs") == 5
                and nk.get("add_extra_convs") == "on_output" and nk.get("relu_before_extra_convs", False),
@@ -183,7 +188,8 @@ class FCOS(_StoreModule):
         self.head_cfg = FCOSHead.parse_cfg(hd)
         self.num_classes = self.head_cfg["num_classes"]
         self.train_cfg, self.test_cfg = train_cfg, dict(test_cfg or {})
-        store = ParamStore(resnet_spec(self.depth) + fpn_spec() + head_spec(self.num_classes), "cpu").init_reference(0)
+        bb_spec = rla_resnet_spec(RESNET_BLOCKS[self.depth]) if self.backbone_kind == "rla" else resnet_spec(self.depth)
+        store = ParamStore(bb_spec + fpn_spec() + head_spec(self.num_classes), "cpu").init_reference(0)
         self._bind_store(store)
         self._trainable = self.trainable_parameters()
         self._nets = OrderedDict()   # (B, H, W, train) -> FCOSNet
@@ -231,7 +237,8 @@ class FCOS(_StoreModule):
                                       store=self.store, device=self.store.device, loss_weight=hc["loss_weight"],
                                       soft_weight=hc["soft_weight"], center_sampling=hc["center_sampling"],
                                       radius=hc["center_sample_radius"], norm_on_bbox=hc["norm_on_bbox"],
-                                      strides=hc["strides"], regress_ranges=hc["regress_ranges"])
+                                      strides=hc["strides"], regress_ranges=hc["regress_ranges"],
+                                      backbone=self.backbone_kind)
         else:
             self._nets.move_to_end(key)
         return self._nets[key]
@@ -432,7 +439,8 @@ class ResNet(_StoreModule):
             if len(self._nets) >= 4:
                 self._nets.popitem(last=False)
             self._nets[key] = FCOSNet(B, H, W, depth=self.depth, train=train, store=self.store,
-                                      device=self.store.device, parts="backbone")
+                                      device=self.store.device, parts="backbone",
+                                      backbone=getattr(self, "backbone_kind", "resnet"))
         return self._nets[key]
 
     def forward(self, x):
@@ -799,6 +807,52 @@ def scale_invariant_input(img, gt_bboxes, gt_labels, gt_bboxes_ignore, img_metas
 
 
 # ====================================================================================================== registry
+class RLA_ResNet(ResNet):
+    """BACKBONES['RLA_ResNet'] (mmdet/models/backbones/resnet_rla.py:140-400), the backbone of the shipped DSL configs
+    (configs/fcos_semi/RLA_*.py:3-13): same constructor keywords; supported = what those configs use (Bottleneck blocks,
+    layers (3,4,6,3) or (3,4,23,3), rla_channel 32, no SE / ECA, frozen_stages=1, norm_eval=True). NCHW fp32 in, the four
+    stage outputs NCHW fp32 out (:312-313), autograd-connected for stages 2-4 incl. the trainable BatchNorm affines."""
+
+    @staticmethod
+    def check_cfg(cfg):
+        """Validate an RLA_ResNet config dict / kwargs; returns the equivalent ResNet depth (block counts)."""
+        layers = tuple(cfg.get("layers", (3, 4, 6, 3)))
+        depth = {v: k for k, v in RESNET_BLOCKS.items()}.get(layers)
+        _check(depth is not None, f"RLA_ResNet layers {layers}")
+        _check(cfg.get("block") is None and cfg.get("rla_channel", 32) == 32 and not cfg.get("SE", False)
+               and cfg.get("ECA") is None, "only RLA_Bottleneck, rla_channel=32, no SE / ECA")
+        _check(cfg.get("groups", 1) == 1 and cfg.get("width_per_group", 64) == 64 and
+               not any(cfg.get("replace_stride_with_dilation") or ()), "groups / width_per_group / dilation")
+        _check(cfg.get("norm_eval", True) and cfg.get("norm_layer") is None, "norm_eval=True with nn.BatchNorm2d")
+        _check(cfg.get("style", "pytorch") == "pytorch", "RLA_ResNet is PyTorch style (stride on conv2)")
+        return depth
+
+    def __init__(self, block=None, layers=(3, 4, 6, 3), num_classes=1000, rla_channel=32, SE=False, ECA=None,
+                 frozen_stages=-1, norm_eval=True, style="pytorch", zero_init_last_bn=True, groups=1, width_per_group=64,
+                 replace_stride_with_dilation=None, norm_layer=None, pretrained=None):
+        _StoreModule.__init__(self)
+        self.depth = self.check_cfg(dict(block=block, layers=layers, rla_channel=rla_channel, SE=SE, ECA=ECA,
+                                         norm_eval=norm_eval, style=style, groups=groups,
+                                         width_per_group=width_per_group, norm_layer=norm_layer,
+                                         replace_stride_with_dilation=replace_stride_with_dilation))
+        _check(frozen_stages == 1, "frozen_stages must be 1")
+        self.backbone_kind = "rla"
+        self.out_indices = (0, 1, 2, 3)
+        self.pretrained = pretrained
+        self._bind_store(ParamStore(rla_resnet_spec(tuple(layers), prefix=""), "cpu").init_reference(0))
+        self._trainable = self.trainable_parameters()
+        self._nets = OrderedDict()
+
+    def init_weights(self):
+        """resnet_rla.py:379-388: load `pretrained` (non-strict) when it names a checkpoint file."""
+        import os
+        if isinstance(self.pretrained, str) and os.path.isfile(self.pretrained):
+            ck = torch.load(self.pretrained, map_location="cpu")
+            self.load_state_dict(ck.get("state_dict", ck), strict=False)
+        else:
+            ResNet.init_weights(self)
+
+
 def register(force=True):
     """Register under the reference's registry keys. Returns the list of keys registered ([] when mmdet / mmcv are not
     importable, e.g. on a bare GPU box: the classes are then used directly)."""
@@ -813,8 +867,9 @@ def register(force=True):
     try:
         from mmdet.models.builder import BACKBONES, NECKS
         BACKBONES.register_module(name="ResNet", force=force, module=ResNet)
+        BACKBONES.register_module(name="RLA_ResNet", force=force, module=RLA_ResNet)
         NECKS.register_module(name="FPN", force=force, module=FPN)
-        done += ["BACKBONES.ResNet", "NECKS.FPN"]
+        done += ["BACKBONES.ResNet", "BACKBONES.RLA_ResNet", "NECKS.FPN"]
     except Exception:
         pass
     try:

@@ -116,7 +116,8 @@ class SemiEpochBasedRunner:
                                 loss_weight=hc["loss_weight"], ema_keep=self.ema_keep, student_store=m.store,
                                 teacher_store=self.ema_model.store if self.ema_flag else None,
                                 scale_invariant=self.scale_invariant, soft_weight=hc["soft_weight"],
-                                soft_warm_up=hc["soft_warm_up"], head_kwargs=head_kwargs, **kw)
+                                soft_warm_up=hc["soft_warm_up"], head_kwargs=head_kwargs,
+                                backbone=getattr(m, "backbone_kind", "resnet"), **kw)
         m._dirty()
         if self.ema_flag:
             self.ema_model._dirty()

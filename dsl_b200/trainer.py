@@ -27,7 +27,7 @@ class DSLEngine:
                  weight_decay=1e-4, bias_lr_mult=2.0, bias_decay_mult=0.0, max_grad_norm=35.0, ema_keep=0.99,
                  loss_weight=3.0, teacher_B=None, use_graphs=True, nms_pre=1000, score_thr=0.05, two_streams=True,
                  student_store=None, teacher_store=None, scale_invariant=False, soft_weight=0.0, soft_warm_up=0,
-                 head_kwargs=None):
+                 head_kwargs=None, backbone="resnet"):
         """student_store / teacher_store: existing ParamStores (e.g. of two plugin.FCOS modules) to train in place.
         scale_invariant: the student batch gets the reference's extra half-resolution copy of its last image
         (semi_epoch_based_runner.py:186-204) -> B + 1 images, and the SI soft loss (fcos_head.py:312-333) with
@@ -38,6 +38,7 @@ class DSLEngine:
         self.soft_weight, self.soft_warm_up, self.cur_iter = float(soft_weight), int(soft_warm_up), 0
         sB = B + 1 if self.scale_invariant else B
         hk = dict(head_kwargs or {})
+        hk["backbone"] = backbone   # "rla": RLA_ResNet (configs/fcos_semi/RLA_*.py:3-13), see engine_rla.py
         self.student = FCOSNet(sB, H, W, depth, num_classes, train=True, device=device, seed=seed,
                                loss_weight=loss_weight, soft_weight=soft_weight, store=student_store, **hk)
         tB = teacher_B or B

@@ -113,8 +113,12 @@ def load():
 def load_rla():
     """RLA_ResNet (mmdet/models/backbones/resnet_rla.py:140-400), the backbone of the shipped DSL config
     (configs/fcos_semi/RLA_*.py:3-13), imported from the reference tree after load()."""
-    load()
-    return importlib.import_module("mmdet.models.backbones.resnet_rla").RLA_ResNet
+    ns = load()
+    name = "mmdet.models.backbones.resnet_rla"
+    if name not in sys.modules:
+        # the module registers itself without force=True: drop a plugin class that already answers to the key
+        ns.builder.BACKBONES._module_dict.pop("RLA_ResNet", None)
+    return importlib.import_module(name).RLA_ResNet
 
 
 def load_hook_functions():

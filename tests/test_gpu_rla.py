@@ -167,3 +167,61 @@ def test_rla_detector_forward_loss_backward():
     assert n_bn == 2 * (42 + 12)   # 13 trainable blocks x 3 + 3 downsample BatchNorms, 12 trainable stage_bns
     rng_ = sorted((lo, hi) for _, lo, hi in net.bwd_buckets)
     assert rng_[0][0] == 0 and rng_[-1][1] == net.store.n_train and all(a[1] == b[0] for a, b in zip(rng_, rng_[1:]))
+
+
+def test_rla_engine_graph_step_and_plugin_train_step():
+    """The fused teacher+student step (CUDA graph) with the RLA_ResNet backbone: finite losses, deterministic replay
+    from restored state, every trainable tensor (incl. BatchNorm affines) moves, frozen ones do not, EMA identity
+    bit-exact; and the same weights through the plugin's FCOS.forward_train / autograd give the same losses."""
+    from dsl_b200 import plugin
+    from dsl_b200.trainer import DSLEngine
+    from tests.test_plugin import RLA_MODEL_CFG
+    B, H, W = 2, 160, 224
+    eng = DSLEngine(B, H, W, depth=50, seed=0, use_graphs=True, backbone="rla")
+    rng = np.random.RandomState(1)
+    img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).cuda()
+    img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).cuda()
+    gts, labels, ignores = GI.make_gt(7, B, H, W, max_gt=6, max_ignore=2, with_ignore=True)
+    gts, labels, ignores = [g.cuda() for g in gts], [l.cuda() for l in labels], [i.cuda() for i in ignores]
+    eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+    st = eng.student.store
+    s0, t0, m0 = st.flat.clone(), eng.teacher.store.flat.clone(), eng.mom.clone()
+    l1 = {k: float(v) for k, v in eng.step().items()}
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for v in l1.values()), l1
+    s1, t1 = st.flat.clone(), eng.teacher.store.flat.clone()
+    assert torch.equal(t1, (0.99 * t0 + 0.01 * s1).float()) or torch.allclose(t1, 0.99 * t0 + 0.01 * s1, rtol=1e-6, atol=1e-8)
+    moved = {}
+    for p in st.spec:
+        o, n = st.offsets[p.name]
+        moved[p.name] = not torch.equal(s0[o:o + n], s1[o:o + n])
+        assert moved[p.name] == (p.region != "F"), (p.name, p.region, moved[p.name])
+    assert moved["backbone.stages.1.0.bn1.weight"] and moved["backbone.stage_bns.2.3.bias"]
+    assert not moved["backbone.stage_bns.3.2.weight"] and not moved["backbone.stages.0.2.conv3.weight"]
+    # replay from the restored state reproduces the losses (graph replays are deterministic up to fp32 atomics order)
+    st.flat.copy_(s0)
+    eng.teacher.store.flat.copy_(t0)
+    eng.mom.copy_(m0)
+    eng.student.repack()
+    eng.teacher.repack()
+    l2 = {k: float(v) for k, v in eng.step().items()}
+    for k in l1:
+        assert abs(l1[k] - l2[k]) <= 1e-4 * abs(l1[k]) + 1e-6, (k, l1[k], l2[k])
+    # the plugin detector on the same (restored) weights: same losses through FCOS.forward_train
+    st.flat.copy_(s0)
+    m = plugin.FCOS(**{k: v for k, v in RLA_MODEL_CFG.items() if k != "type"}).cuda()
+    m.load_state_dict({k: v for k, v in st.state_dict().items()})
+    m.train()
+    metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=np.ones(4, dtype=np.float32), filename=f"{i}.jpg")
+             for i in range(B)]
+    m.head_cfg["soft_weight"] = 0.0
+    losses = m.forward_train(img_s, metas, gts, labels, ignores)
+    for k in ("loss_cls", "loss_bbox", "loss_centerness"):
+        assert abs(float(losses[k]) - l1[k]) <= 2e-3 * abs(l1[k]) + 1e-5, (k, float(losses[k]), l1[k])
+    sum(losses.values()).backward()
+    named = dict(m.named_parameters())
+    for k in ("backbone.stages.1.0.bn1.weight", "backbone.stage_bns.1.2.weight", "backbone.conv_outs.2.weight",
+              "backbone.stages.3.0.conv1.weight", "backbone.recurrent_convs.3.weight"):
+        g = named[k].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, k
+    assert named["backbone.stage_bns.3.2.weight"].grad is None

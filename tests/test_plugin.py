@@ -446,3 +446,67 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
             assert getattr(cls, field).offset == int(val), (cname, field)
         seen += 1
     assert seen > 80
+
+
+# the model dict of the SHIPPED DSL config, configs/fcos_semi/RLA_r50_caffe_mslonger_tricks_0.Xdata_unlabel_dynamic_lw_
+# nofuse_iterlabel_lowfilter_singlestage.py:1-62 — RLA_ResNet backbone (:3-13)
+RLA_MODEL_CFG = dict(MODEL_CFG, backbone=dict(type="RLA_ResNet", layers=[3, 4, 6, 3], frozen_stages=1, norm_eval=True,
+                                               style="pytorch", pretrained="/nonexistent/resnet50_rla_2283.pth.tar"))
+
+
+def test_plugin_builds_the_shipped_rla_config():
+    m = _build(RLA_MODEL_CFG)
+    named = dict(m.named_parameters())
+    n_bb = sum(p.numel() for n, p in named.items() if n.startswith("backbone."))
+    assert n_bb == 23789632     # parameter count of the reference's RLA_ResNet([3, 4, 6, 3]) (tests/golden/rla_backbone.npz)
+    sd = m.state_dict()
+    for k in ("backbone.conv_outs.3.weight", "backbone.recurrent_convs.0.weight", "backbone.stage_bns.2.5.running_var",
+              "backbone.stages.1.0.downsample.1.weight", "backbone.stages.0.0.conv1.weight",
+              "backbone.stage_bns.3.2.num_batches_tracked"):
+        assert k in sd, k
+    assert sd["backbone.stages.2.1.conv1.weight"].shape == (256, 1024 + 32, 1, 1)   # conv1 acts on cat(x, h)
+    # resnet_rla.py:344-377: stem + stage 1 frozen, stage_bns[3][2] frozen, every other BatchNorm affine TRAINABLE
+    assert not named["backbone.stages.0.1.conv2.weight"].requires_grad
+    assert not named["backbone.stage_bns.0.0.weight"].requires_grad and not named["backbone.conv_outs.0.weight"].requires_grad
+    assert not named["backbone.stage_bns.3.2.weight"].requires_grad
+    assert named["backbone.stages.1.0.bn1.weight"].requires_grad and named["backbone.stage_bns.3.1.bias"].requires_grad
+    assert named["backbone.recurrent_convs.1.weight"].requires_grad
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rla_backbone.npz"))
+    assert sorted(n[len("backbone."):] for n, p in named.items() if n.startswith("backbone.") and p.requires_grad) == \
+        list(g["trainable"])
+    with pytest.raises(NotImplementedError):
+        _build(dict(RLA_MODEL_CFG, backbone=dict(RLA_MODEL_CFG["backbone"], SE=True)))
+    with pytest.raises(NotImplementedError):
+        _build(dict(RLA_MODEL_CFG, backbone=dict(RLA_MODEL_CFG["backbone"], layers=[2, 2, 2, 2])))
+
+
+def test_plugin_rla_registry_and_state_dict_names():
+    """build_backbone / build_detector of the reference's registry return the B200 classes for `RLA_ResNet`, with the
+    reference's state_dict names and shapes; checkpoints load both ways."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    R = ref_loader.load()
+    RefRLA = ref_loader.load_rla()
+    ref_bb = RefRLA(layers=[3, 4, 6, 3], frozen_stages=1, norm_eval=True, style="pytorch")
+    ref_keys = {k: tuple(v.shape) for k, v in ref_bb.state_dict().items()}
+    from dsl_b200 import plugin
+    reg = R.builder.DETECTORS
+    names = ("FCOS", "FCOSHead", "ResNet", "RLA_ResNet", "FPN", "FocalLoss", "GIoULoss", "CrossEntropyLoss")
+    originals = {n: reg.get(n) for n in names}
+    keys = plugin.register(force=True)
+    try:
+        assert "BACKBONES.RLA_ResNet" in keys
+        bb = R.builder.build_backbone(dict(RLA_MODEL_CFG["backbone"]))
+        assert isinstance(bb, plugin.RLA_ResNet)
+        assert {k: tuple(v.shape) for k, v in bb.state_dict().items()} == ref_keys
+        bb.load_state_dict(ref_bb.state_dict())
+        assert torch.equal(bb.store["stages.3.0.conv1.weight"], ref_bb.state_dict()["stages.3.0.conv1.weight"])
+        ref_bb.load_state_dict(bb.state_dict())
+        m = R.builder.build_detector(dict(RLA_MODEL_CFG))
+        assert isinstance(m, plugin.FCOS) and m.backbone_kind == "rla"
+        assert {k[len("backbone."):] for k in m.state_dict() if k.startswith("backbone.")} == set(ref_keys)
+    finally:
+        for n, cls in originals.items():
+            if cls is not None:
+                reg.register_module(name=n, force=True, module=cls)
