@@ -546,6 +546,56 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
 }
 
 
+// Vector variant (C % 8 == 0, ld % 8 == 0, 16-byte aligned rows): one thread = 8 consecutive channels (one 16-byte load
+// per pixel), T = C / 8 threads per pixel row, 256 / T rows per block iteration, 4 independent loads in flight per
+// thread; per-block shared-memory reduction, then one atomicAdd per channel and block.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                         long long npix, int ld, int T, int R) {
+  __shared__ float sm[256][9];
+  const int t = threadIdx.x % T, r = threadIdx.x / T;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (r < R) {
+    const long long step = (long long)gridDim.x * R;
+    const __nv_bfloat16* base = x + t * 8;
+    long long p = (long long)blockIdx.x * R + r;
+    for (; p + 3 * step < npix; p += 4 * step) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + k * step) * ld));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += bflo(w[e]);
+          acc[2 * e + 1] += bfhi(w[e]);
+        }
+      }
+    }
+    for (; p < npix; p += step) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + p * ld));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += bflo(w[e]);
+        acc[2 * e + 1] += bfhi(w[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  // thread (t, e-th channel) for t < T: sum over the R row lanes
+  for (int idx = threadIdx.x; idx < T * 8; idx += 256) {
+    const int tt = idx >> 3, e = idx & 7;
+    float a = 0.f;
+    for (int rr = 0; rr < R; ++rr) a += sm[rr * T + tt][e];
+    atomicAdd(out + idx, a);
+  }
+}
+
 // Direct (CUDA-core) data gradient for the two tiny stride-2 3x3 FPN convs (P6, P7: <= 13x21 outputs), where a
 // tensor-core formulation would need a strided scatter: dx[n,h,w,ci] (+)= sum_{r,s,co} dy[n,p,q,co] * Wp[r*S+s][co][ci]
 // with h = p*stride - pad + r. Wp is the packed fprop weight (ci contiguous => coalesced across the warp).
@@ -819,6 +869,13 @@ extern "C" int dslb_bn_fold(const float* gamma, const float* beta, const float* 
 
 extern "C" int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream) {
   DSLB_CHECK_ARG(x && out && ld >= C, "dslb_colsum: bad arguments");
+  if (C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ((uintptr_t)x % 16) == 0 && getenv("DSLB_COLSUM_SCALAR") == nullptr) {
+    const int T = C / 8, R = 256 / T;
+    // ~16 rows per thread at least, capped at 8 blocks per SM
+    colsum_vec_kernel<<<grid_for(npix / ((long long)R * 16) + 1, 1, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, out, npix, ld, T, R);
+    LAUNCH_CHECK();
+  }
   colsum_kernel<<<grid_for(npix / 8 + 1, 1, 4), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, npix, ld, C);
   LAUNCH_CHECK();
 }
