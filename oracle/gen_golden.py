@@ -7,6 +7,7 @@ Files written (all small; inputs are regenerated from seeds, only reference OUTP
   loss_*.npz     FCOSHead.loss: labels / bbox_targets (bit-exact contract), losses, input-gradient samples
   backbone.npz   ResNet-50 (caffe, frozen BN) + FPN forward on a 1x3x64x96 input (weights from seed)
   rla_backbone.npz  RLA_ResNet (the shipped configs' backbone) forward + sampled parameter gradients, 1x3x64x96
+  rla_detector.npz  build_detector(shipped RLA model dict).forward_train: losses + sampled parameter gradients
   decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
   misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
 """
@@ -155,6 +156,52 @@ def gen_rla_backbone(R):
         g = params[k].grad.reshape(-1)
         out["grad:" + k] = (g[::97] if g.numel() > 4096 else g).numpy()   # large tensors: every 97th element
     np.savez_compressed(os.path.join(OUT, "rla_backbone.npz"), **out)
+
+
+RLA_DET_GRAD_KEYS = GI.RLA_DET_GRAD_KEYS
+
+
+def rla_detector_cfg():
+    """Model dict of the shipped config (configs/fcos_semi/RLA_r50_caffe_mslonger_tricks_0.Xdata_unlabel_dynamic_lw_
+    nofuse_iterlabel_lowfilter_singlestage.py:1-62), `pretrained` dropped (no checkpoint offline)."""
+    return dict(
+        type="FCOS",
+        backbone=dict(type="RLA_ResNet", layers=[3, 4, 6, 3], frozen_stages=1, norm_eval=True, style="pytorch"),
+        neck=dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1,
+                  add_extra_convs="on_output", num_outs=5, relu_before_extra_convs=True),
+        bbox_head=dict(type="FCOSHead", loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000, **HEAD_CFG),
+        train_cfg=dict(assigner=dict(type="MaxIoUAssigner", pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0,
+                                     ignore_iof_thr=-1), allowed_border=-1, pos_weight=-1, debug=False),
+        test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5),
+                      max_per_img=100))
+
+
+def gen_rla_detector(R):
+    """The reference's FCOS detector built by its own build_detector from the shipped RLA config's model dict:
+    forward_train (single_stage.py:152-180 -> FCOSHead.loss) on 2x3x256x320 with GT + ignore boxes; losses and sampled
+    parameter gradients of the summed loss."""
+    ref_loader.load_rla()
+    m = R.builder.build_detector(rla_detector_cfg())
+    m.backbone.flops = True                       # initial state tensor on the CPU (resnet_rla.py:296-300)
+    sd = m.state_dict()
+    mine = GI.rla_detector_state(61, 62)
+    assert set(mine) == {k for k in sd if not k.endswith("num_batches_tracked")}
+    with torch.no_grad():
+        for k, v in mine.items():
+            sd[k].copy_(v)
+    m.train()
+    B, H, W = 2, 256, 320
+    img = GI.make_tensor(np.random.RandomState(63), B, 3, H, W)
+    gts, labels, ignores = GI.make_gt(64, B, H, W, max_gt=9, max_ignore=3, with_ignore=True)
+    metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=1.0, filename=f"{i}.jpg") for i in range(B)]
+    losses = m.forward_train(img, metas, gts, labels, gt_bboxes_ignore=ignores)
+    out = {k: np.float64(v.item()) for k, v in losses.items()}
+    sum(losses.values()).backward()
+    params = dict(m.named_parameters())
+    for k in RLA_DET_GRAD_KEYS:
+        g = params[k].grad.reshape(-1)
+        out["grad:" + k] = (g[::97] if g.numel() > 4096 else g).numpy()
+    np.savez_compressed(os.path.join(OUT, "rla_detector.npz"), **out)
 
 
 def gen_decode(R):
@@ -519,6 +566,7 @@ def main():
     gen_loss(R)
     gen_backbone(R)
     gen_rla_backbone(R)
+    gen_rla_detector(R)
     gen_decode(R)
     gen_misc(R)
     gen_hook_chain(R)

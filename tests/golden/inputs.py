@@ -132,3 +132,49 @@ def rla_state_dict(seed, layers=(3, 4, 6, 3), rla_channel=32):
             bn(f"stage_bns.{li}.{bi}", rla_channel)
             inpl = planes * 4
     return sd
+
+
+def fill_by_name_(sd, seed, skip_prefix=None):
+    """Like fill_state_dict_, but every tensor is drawn from RandomState(crc32(key) ^ seed): independent of key order, so
+    a test can rebuild the same values from names and shapes alone."""
+    import zlib
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked") or (skip_prefix and k.startswith(skip_prefix)):
+            continue
+        rng = np.random.RandomState((zlib.crc32(k.encode()) ^ seed) & 0x7fffffff)
+        if k.endswith("running_var"):
+            t = torch.from_numpy((rng.rand(*v.shape) + 0.5).astype(np.float32))
+        elif k.endswith("running_mean"):
+            t = make_tensor(rng, *v.shape, scale=0.1)
+        elif v.dim() == 4:
+            t = make_tensor(rng, *v.shape, scale=(2.0 / (v.shape[1] * v.shape[2] * v.shape[3])) ** 0.5)
+        elif k.endswith(".weight"):
+            t = torch.from_numpy((rng.rand(*v.shape) + 0.5).astype(np.float32))
+        elif k.endswith("scale"):
+            t = torch.tensor(float(rng.rand() + 0.5))
+        else:
+            t = make_tensor(rng, *v.shape, scale=0.1)
+        with torch.no_grad():
+            v.copy_(t.reshape(v.shape))
+    return sd
+
+
+def rla_detector_state(seed_bb, seed_rest, num_classes=80):
+    """Seeded state_dict (reference names) of FCOS with the RLA_ResNet backbone: rla_state_dict for the backbone,
+    fill_by_name_ for FPN + head (names / shapes from dsl_b200.params), classification prior bias -4.59 and a small
+    conv_cls gain so that the focal loss is in its working range."""
+    from collections import OrderedDict
+    from dsl_b200.params import fpn_spec, head_spec
+    sd = OrderedDict(("backbone." + k, v) for k, v in rla_state_dict(seed_bb).items())
+    rest = OrderedDict((p.name, torch.zeros(p.shape)) for p in fpn_spec() + head_spec(num_classes))
+    fill_by_name_(rest, seed_rest)
+    rest["bbox_head.conv_cls.weight"] *= 0.1
+    rest["bbox_head.conv_cls.bias"].fill_(-4.59)
+    sd.update(rest)
+    return sd
+
+
+# parameters whose gradients tests/golden/rla_detector.npz samples (oracle/gen_golden.py::gen_rla_detector)
+RLA_DET_GRAD_KEYS = ("backbone.stages.1.0.bn1.weight", "backbone.conv_outs.3.weight", "backbone.stage_bns.2.1.bias",
+                     "backbone.stages.2.2.conv1.weight", "neck.lateral_convs.0.conv.weight", "bbox_head.conv_cls.bias",
+                     "bbox_head.reg_convs.1.gn.weight", "bbox_head.scales.2.scale")

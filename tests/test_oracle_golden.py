@@ -209,6 +209,31 @@ def test_rla_resnet_matches_reference():
         np.testing.assert_allclose(got, g["grad:" + k], rtol=2e-3, atol=2e-3 * np.abs(g["grad:" + k]).max())
 
 
+def test_rla_detector_losses_and_gradients_match_reference():
+    """The whole student path of the shipped config (RLA_ResNet -> FPN -> FCOSHead -> DSL loss with ignore boxes and
+    loss_weight 3) restated by the oracle vs the reference's own build_detector(...).forward_train: losses and sampled
+    parameter gradients through backbone state path, trainable BatchNorm affines, neck and head."""
+    RLA_DET_GRAD_KEYS = GI.RLA_DET_GRAD_KEYS
+    g = load("rla_detector.npz")
+    sd = {k: v.clone().requires_grad_(k in RLA_DET_GRAD_KEYS) for k, v in GI.rla_detector_state(61, 62).items()}
+    B, H, W = 2, 256, 320
+    img = GI.make_tensor(np.random.RandomState(63), B, 3, H, W)
+    gts, labels, ignores = GI.make_gt(64, B, H, W, max_gt=9, max_ignore=3, with_ignore=True)
+    cs = O.rla_resnet_forward(sd, img, prefix="backbone.")
+    ps = O.fpn_forward(sd, cs, prefix="neck.")
+    cls, box, ctr = O.fcos_head_forward(sd, ps, training=True, prefix="bbox_head.")
+    out = O.fcos_loss(cls, box, ctr, gts, labels, ignores, loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000)
+    assert set(out) == {"loss_cls", "loss_bbox", "loss_centerness"}      # even batch: no SI-soft term
+    for k, v in out.items():
+        np.testing.assert_allclose(float(v.detach()), float(g[k]), rtol=2e-4)
+    sum(out.values()).backward()
+    for k in RLA_DET_GRAD_KEYS:
+        got = sd[k].grad.reshape(-1)
+        got = (got[::97] if got.numel() > 4096 else got).numpy()
+        want = g["grad:" + k]
+        np.testing.assert_allclose(got, want, rtol=5e-3, atol=5e-3 * np.abs(want).max(), err_msg=k)
+
+
 def test_decode_gate_nms_match_reference():
     g = load("decode.npz")
     B, H, W = 2, 512, 640
