@@ -92,3 +92,79 @@ def test_two_rank_collectives_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _rla_bucket_worker(rank, world, port, q):
+    """Data-parallel backward of the RLA_ResNet backbone plan (executed on tests/emu_lib.py): the gradient leaves in the
+    plan's buckets — each all-reduced asynchronously as soon as the ops up to its boundary have run — and must equal a
+    full backward followed by ONE all-reduce (the reference's DDP result, mmdet/apis/train.py:88-102), on both ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from dsl_b200 import dist_ops
+    from dsl_b200.engine import FCOSNet
+    from dsl_b200.params import ParamStore, rla_resnet_spec
+    from tests import emu_lib
+    from tests.golden import inputs as GI
+    try:
+        torch.set_num_threads(2)
+        B, H, W = 1, 64, 96
+        x = GI.make_tensor(np.random.RandomState(300 + rank), B, 3, H, W)      # per-rank images, shared weights
+        rng = np.random.RandomState(400 + rank)
+        with emu_lib.installed():
+            store = ParamStore(rla_resnet_spec(prefix=""), "cpu")
+            store.load_state_dict(GI.rla_state_dict(51))
+            net = FCOSNet(B, H, W, depth=50, train=True, store=store, device="cpu", parts="backbone", backbone="rla")
+            net.img.copy_(x)
+            net.forward()
+            seeds = [torch.from_numpy(rng.randn(*g.shape).astype(np.float32)).bfloat16() for g in net.gc]
+
+            def seed():
+                for g, s in zip(net.gc, seeds):
+                    g.copy_(s)
+
+            # bucketed: ops [start, end) of each bucket, then its flat-gradient range goes on the wire
+            seed()
+            start, works = 0, []
+            assert len(net.bwd_buckets) == 2
+            for end, lo, hi in net.bwd_buckets:
+                net.backward(start=start, end=end)
+                works.append(dist_ops.allreduce_mean_async_(net.grad[lo:hi]))
+                start = end
+            assert start == len(net.bwd_ops)        # nothing is left behind the last bucket
+            for wk in works:
+                wk.wait()
+            bucketed = net.grad.clone()
+            # one all-reduce after the whole backward (the gradient maps are consumed in place: seed again)
+            seed()
+            net.backward()
+            local = net.grad.clone()
+            dist_ops.allreduce_mean_(net.grad)
+            assert torch.equal(bucketed, net.grad)
+            both = [torch.zeros_like(local) for _ in range(world)]
+            dist.all_gather(both, local)
+            assert not torch.equal(both[0], both[1])                       # the ranks really saw different images
+            assert torch.allclose(net.grad, (both[0] + both[1]) / 2, rtol=1e-6, atol=1e-9)
+            o, n = store.offsets["stages.2.0.bn1.weight"]                   # trainable BatchNorm affines travel with the bucket
+            assert float(net.grad[o:o + n].abs().sum()) > 0
+            del net
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_rla_gradient_buckets_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rla_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
