@@ -208,8 +208,16 @@ class FCOS(_StoreModule):
         return True
 
     def init_weights(self):
-        """Reference init_cfg (synthetic, no checkpoint offline): see ParamStore.init_reference."""
+        """Reference init_cfg (synthetic, no checkpoint offline): see ParamStore.init_reference. A backbone `pretrained`
+        path that names an existing checkpoint file is loaded into `backbone.*` non-strictly, as
+        RLA_ResNet.init_weights does (resnet_rla.py:379-388; single_stage.py:32-36 hands `pretrained` to the backbone)."""
+        import os
         self.store.init_reference(0)
+        if isinstance(self.pretrained, str) and os.path.isfile(self.pretrained):
+            ck = torch.load(self.pretrained, map_location="cpu")
+            ck = ck.get("state_dict", ck)
+            self.store.load_state_dict({"backbone." + k: v for k, v in ck.items()
+                                        if not k.endswith("num_batches_tracked")}, strict=False)
         self._dirty()
 
     def _on_store_moved(self):

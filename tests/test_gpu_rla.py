@@ -225,3 +225,36 @@ def test_rla_engine_graph_step_and_plugin_train_step():
         g = named[k].grad
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, k
     assert named["backbone.stage_bns.3.2.weight"].grad is None
+
+
+def test_plugin_rla_resnet_module_forward_backward():
+    """BACKBONES['RLA_ResNet'] as a module of its own: NCHW fp32 in, four NCHW fp32 stage outputs, autograd-connected
+    (parameter gradients of stages 2-4 incl. BatchNorm affines) — against the oracle's autograd."""
+    from dsl_b200 import plugin
+    from oracle import fcos_oracle as O
+    bb = plugin.RLA_ResNet(layers=[3, 4, 6, 3], frozen_stages=1, norm_eval=True, style="pytorch").cuda()
+    sd0 = GI.rla_state_dict(51)
+    bb.load_state_dict(sd0)
+    bb.train()
+    x = GI.make_tensor(np.random.RandomState(52), 2, 3, 128, 192)
+    cs = bb(x.cuda())
+    assert [tuple(c.shape) for c in cs] == [(2, 256, 32, 48), (2, 512, 16, 24), (2, 1024, 8, 12), (2, 2048, 4, 6)]
+    spec = {p.name: p for p in bb.store.spec}
+    sd = {k: v.clone().requires_grad_(spec[k].region != "F") for k, v in sd0.items()}
+    ref = O.rla_resnet_forward(sd, x)
+    for got, want in zip(cs, ref):
+        assert _l2(got.detach(), want.detach()) < 2e-2
+    rng = np.random.RandomState(53)
+    ws = [torch.from_numpy(rng.randn(*c.shape).astype(np.float32)).bfloat16().float() for c in ref]
+    sum((c * w.cuda()).sum() for c, w in zip(cs[1:], ws[1:])).backward()
+    sum((c * w).sum() for c, w in zip(ref[1:], ws[1:])).backward()
+    checked = 0
+    for name, p in bb.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        c = _cos(p.grad.cpu(), sd[name].grad)
+        floor = 0.95 if name.startswith("stage_bns") else _floor(name)
+        assert c > floor, (name, c)
+        checked += 1
+    assert checked == 156

@@ -510,3 +510,17 @@ def test_plugin_rla_registry_and_state_dict_names():
         for n, cls in originals.items():
             if cls is not None:
                 reg.register_module(name=n, force=True, module=cls)
+
+
+def test_plugin_rla_pretrained_checkpoint_loads_into_the_backbone(tmp_path):
+    """`pretrained` of the shipped config names an ImageNet RLA checkpoint: init_weights loads it non-strictly into
+    backbone.* (classifier keys of the checkpoint are ignored, missing keys keep their initialisation)."""
+    ck = {k: v for k, v in GI.rla_state_dict(5).items() if not k.startswith("stage_bns.3")}
+    ck["fc.weight"] = torch.zeros(1000, 2048 + 32)          # ImageNet head of the checkpoint: not part of the detector
+    path = tmp_path / "resnet50_rla.pth.tar"
+    torch.save({"state_dict": ck}, path)
+    m = _build(dict(RLA_MODEL_CFG, backbone=dict(RLA_MODEL_CFG["backbone"], pretrained=str(path))))
+    m.init_weights()
+    assert torch.equal(m.store["backbone.stages.2.3.conv1.weight"], ck["stages.2.3.conv1.weight"])
+    assert torch.equal(m.store["backbone.conv_outs.1.weight"], ck["conv_outs.1.weight"])
+    assert float(m.store["backbone.stage_bns.3.0.running_var"].min()) == 1.0      # missing in the checkpoint: init kept
