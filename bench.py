@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--backbone", default="resnet", choices=["resnet", "rla"],
                     help="rla: RLA_ResNet, the backbone of the shipped DSL configs (not the BASELINE.json config)")
+    ap.add_argument("--mix", default="bench", choices=["bench", "literal"],
+                    help="literal: the reference's hard-coded per-GPU mix (SURVEY 8d): 2 student images + the half-resolution "
+                         "SI copy of the last one (semi_epoch_based_runner.py:186-204) + 1 teacher image "
+                         "(unlabel_pred_hook.py:517,543), SI-soft loss on; secondary measurement, not the BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-hw", default="800x1344", help="HxW of the bounded CPU sample")
     return ap.parse_args()
@@ -189,12 +193,15 @@ def main():
     from dsl_b200.trainer import DSLEngine
     from tests.golden import inputs as GI
 
-    B = args.batch
-    eng = DSLEngine(B, H, W, depth=args.depth, seed=0, use_graphs=True, backbone=args.backbone)
+    literal = args.mix == "literal"
+    B = 2 if literal else args.batch
+    tB = 1 if literal else B
+    ekw = dict(scale_invariant=True, soft_weight=1.0, soft_warm_up=5000, teacher_B=1) if literal else {}
+    eng = DSLEngine(B, H, W, depth=args.depth, seed=0, use_graphs=True, backbone=args.backbone, **ekw)
     rng = np.random.RandomState(100 + rank)
     # synthetic COCO-shaped batch in PINNED host memory (mean-subtracted pixels, caffe normalisation: std 1)
     img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
-    img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
+    img_t = torch.from_numpy((rng.rand(tB, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
     gts, labels, ignores = GI.make_gt(200 + rank, B, H, W, max_gt=20, max_ignore=5, with_ignore=True)
     gts = [g.pin_memory() for g in gts]
     labels = [l.pin_memory() for l in labels]
@@ -237,12 +244,16 @@ def main():
     def e2e_step():
         # the step consumes the batch prefetched under the previous step; the H2D of the NEXT batch (pinned host ->
         # device staging, every step) is issued on the copy stream before this step's result is read back
+        if literal:   # the SI extra image is built by set_inputs (in-stream H2D + one kernel), no prefetch path
+            eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
         losses = eng.step()
-        eng.prefetch_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+        if not literal:
+            eng.prefetch_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
         host_out[:3].copy_(torch.stack([losses["loss_cls"], losses["loss_bbox"], losses["loss_centerness"]]),
                            non_blocking=False)  # D2H read of the step's result: synchronises every step
 
-    eng.prefetch_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
+    if not literal:
+        eng.prefetch_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
     for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
@@ -291,9 +302,12 @@ def main():
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=WORKLOAD if args.backbone == "resnet" else WORKLOAD.replace(
-                    "configs[1]: FCOS-R50-FPN", "variant of configs[1] with the shipped configs' RLA_ResNet backbone: FCOS-RLA_R50-FPN"),
-                            global_batch=B * world, per_gpu_batch=B, teacher_batch=B,
+                config=dict(workload=(WORKLOAD if args.backbone == "resnet" else WORKLOAD.replace(
+                    "configs[1]: FCOS-R50-FPN", "variant of configs[1] with the shipped configs' RLA_ResNet backbone: FCOS-RLA_R50-FPN"))
+                    if not literal else WORKLOAD.replace("configs[1]:", "reference-literal mix (SURVEY 8d) of configs[1]:").replace(
+                        "bs=4/GPU", "2 student images + half-res SI copy + 1 teacher image per GPU, SI-soft loss on")
+                    + ("" if args.backbone == "resnet" else ", RLA_ResNet backbone"),
+                            global_batch=B * world, per_gpu_batch=B, teacher_batch=tB,
                             parallelism=f"dp{world}", l2="working set (activations) >> 126 MB L2; no flush needed",
                             step="teacher fwd+decode gate, student fwd+loss+bwd, grad allreduce, clip+SGD, EMA, repack",
                             cuda_graph=True),
