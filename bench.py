@@ -161,8 +161,8 @@ def run_reference(args):
     warm = 1 if args.warmup > 0 else 0
     cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=steps, warmup=warm, batch=args.batch)
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
-                ms_per_step=round(1000.0 / cb["value"], 1), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="fp32", data="synthetic", impl="reference",
+                ms_per_step=round(1000.0 * args.batch / cb["value"], 1), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="fp32", data="synthetic", impl="reference",
                 config=dict(workload=WORKLOAD, note="CPU port of the reference arithmetic, same per-GPU batch, bounded "
                                                     "number of steps; host cores only, no GPU"),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
