@@ -654,3 +654,44 @@ def test_full_size_graph_step_properties():
     torch.cuda.synchronize()
     assert torch.equal(net.labels, lab1)
     assert all(np.isfinite(float(v)) for v in eng.student.losses().values())
+
+
+def test_config0_supervised_baseline_2x800x800():
+    """BASELINE.json configs[0]: the supervised-baseline FCOS-R50-FPN config (configs/fcos_semi/r50_caffe_mslonger_
+    tricks_0.Xdata.py: loss_weight 1, no ignore boxes) on 2 synthetic 800x800 images — the reference's own CPU-runnable
+    case, here at its full size: FPN maps and head outputs vs the fp32 oracle (bf16 bar), labels / bbox targets of all
+    2 x 13 343 points bit-exact, losses <= 1e-3 on the CUDA head outputs, one backward with finite gradients."""
+    from dsl_b200.engine import FCOSNet
+    from oracle import fcos_oracle as O
+    B, H, W = 2, 800, 800
+    net = FCOSNet(B, H, W, depth=50, train=True, seed=2, loss_weight=1.0)
+    rng = np.random.RandomState(9)
+    img = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))   # caffe normalisation: mean-subtracted
+    gts, labels, _ = GI.make_gt(90, B, H, W, max_gt=9, with_ignore=False)
+    net.img.copy_(img)
+    net.forward()
+    _run_loss(net, gts, labels, None)
+    net.backward()
+    torch.cuda.synchronize()
+    assert net.npoints == B * 13343
+    bb, neck, head = _oracle_state(net)
+    with torch.no_grad():
+        ps = O.fpn_forward(neck, O.resnet_forward(bb, img, 50))
+        rc, rb, rt = O.fcos_head_forward(head, ps, training=True)
+    for l in range(5):
+        assert _rel(_nchw(net.p[l], 256), ps[l]) < 4e-2, l
+    cls = [_nchw(net.cls_out[l], 80) for l in range(5)]
+    box = [_nchw(net.rc_out[l], 4) for l in range(5)]
+    ctr = [_nchw(net.rc_out[l][..., 4:5], 1) for l in range(5)]
+    e_cls = max(_rel(a, b) for a, b in zip(cls, rc))
+    e_box = max(_rel(a, b) for a, b in zip(box, rb))
+    print(f"config0 head outputs vs fp32 oracle: cls {e_cls:.2e} box {e_box:.2e}")
+    assert e_cls < 2e-2 and e_box < 6e-2     # 60+ stacked bf16 convs: same bars as test_forward_matches_oracle
+    out = O.fcos_loss(cls, box, ctr, gts, labels, None, loss_weight=1.0, return_aux=True)
+    aux = out.pop("_aux")
+    assert torch.equal(net.labels.cpu(), aux["labels"]) and torch.equal(net.bbox_targets.cpu(), aux["bbox_targets"])
+    got = net.losses()
+    assert set(got) == set(out)
+    for k, v in out.items():
+        assert abs(got[k].item() - float(v)) <= 1e-3 * abs(float(v)) + 1e-6, (k, got[k].item(), float(v))
+    assert torch.isfinite(net.grad).all() and float(net.grad.abs().sum()) > 0
