@@ -548,7 +548,9 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
 
 // Vector variant (C % 8 == 0, ld % 8 == 0, 16-byte aligned rows): one thread = 8 consecutive channels (one 16-byte load
 // per pixel), T = C / 8 threads per pixel row, 256 / T rows per block iteration, 4 independent loads in flight per
-// thread; per-block shared-memory reduction, then one atomicAdd per channel and block.
+// thread; per-block shared-memory reduction, then one reduction per channel and block (V4: one 16-byte
+// red.global.add.v4.f32 per 4 channels — the few output lines are shared by every block, so the op count matters).
+template <bool V4>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                          long long npix, int ld, int T, int R) {
   __shared__ float sm[256][9];
@@ -587,12 +589,27 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __
 #pragma unroll
   for (int e = 0; e < 8; ++e) sm[threadIdx.x][e] = acc[e];
   __syncthreads();
-  // thread (t, e-th channel) for t < T: sum over the R row lanes
-  for (int idx = threadIdx.x; idx < T * 8; idx += 256) {
-    const int tt = idx >> 3, e = idx & 7;
-    float a = 0.f;
-    for (int rr = 0; rr < R; ++rr) a += sm[rr * T + tt][e];
-    atomicAdd(out + idx, a);
+  if (V4) {
+    // thread = 4 consecutive channels of octet tt: sum over the R row lanes, one vector reduction
+    for (int idx = threadIdx.x; idx < T * 2; idx += 256) {
+      const int tt = idx >> 1, e0 = (idx & 1) * 4;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] += sm[rr * T + tt][e0 + e];
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + tt * 8 + e0), "f"(a[0]), "f"(a[1]),
+                   "f"(a[2]), "f"(a[3])
+                   : "memory");
+    }
+  } else {
+    // thread (t, e-th channel) for t < T: sum over the R row lanes
+    for (int idx = threadIdx.x; idx < T * 8; idx += 256) {
+      const int tt = idx >> 3, e = idx & 7;
+      float a = 0.f;
+      for (int rr = 0; rr < R; ++rr) a += sm[rr * T + tt][e];
+      atomicAdd(out + idx, a);
+    }
   }
 }
 
@@ -871,9 +888,13 @@ extern "C" int dslb_colsum(const void* x, float* out, long long npix, int ld, in
   DSLB_CHECK_ARG(x && out && ld >= C, "dslb_colsum: bad arguments");
   if (C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ((uintptr_t)x % 16) == 0 && getenv("DSLB_COLSUM_SCALAR") == nullptr) {
     const int T = C / 8, R = 256 / T;
-    // ~16 rows per thread at least, capped at 8 blocks per SM
-    colsum_vec_kernel<<<grid_for(npix / ((long long)R * 16) + 1, 1, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, out, npix, ld, T, R);
+    // ~16 rows per thread at least, capped at 3 blocks per SM: every block ends with C reductions onto the same few
+    // cache lines, so fewer, longer blocks (4 x 16-byte loads in flight per thread) beat a wide grid
+    const int grid = grid_for(npix / ((long long)R * 16) + 1, 1, 3);
+    if (((uintptr_t)out % 16) == 0 && getenv("DSLB_COLSUM_NO_V4") == nullptr)
+      colsum_vec_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, npix, ld, T, R);
+    else
+      colsum_vec_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, npix, ld, T, R);
     LAUNCH_CHECK();
   }
   colsum_kernel<<<grid_for(npix / 8 + 1, 1, 4), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, npix, ld, C);
