@@ -3,9 +3,10 @@ FCOSNet(parts="backbone") plan calls, so the HOST-side plan logic of dsl_b200/en
 feeds which launch, masks, residuals, gradient routing, operand packing with folded BatchNorm, buckets) can be executed
 and checked against the oracle without a GPU. Each function implements the contract written in include/dslb.h with torch
 fp32 math and bf16 rounding where the kernels round. It is never imported by the product; the CUDA kernels themselves are
-checked on the GPU (`-m gpu` tests).
+checked on the GPU (`-m gpu` tests). The loss entry points are emulated THROUGH the oracle (autograd over its FCOSHead.loss
+restatement), so what a full-detector run on the emulator checks is the plan around them, not the loss arithmetic.
 
-Usage:  with emu_lib.installed(): net = FCOSNet(..., device="cpu", parts="backbone"); net.forward(); net.backward()
+Usage:  with emu_lib.installed(): net = FCOSNet(..., device="cpu"); net.forward(); ...; net.backward()
 """
 import contextlib
 import ctypes as C
@@ -14,6 +15,7 @@ import torch
 import torch.nn.functional as F
 
 BF16 = torch.bfloat16
+GN_STAT_STRIDE = 32   # DSLB_GN_STAT_STRIDE
 
 
 def _addr(p):
@@ -118,8 +120,15 @@ class EmuLib:
         if s["relu_mask"]:
             m = _rows(s["relu_mask"], npix, ldc, BF16)[:, :Cout].float()
             v = torch.where(m > 0, v, torch.zeros_like(v))
-        assert not s["gn_stats"], "GroupNorm statistics are not emulated"
-        _rows(s["y"], npix, ldc, ydt)[:, :Cout] = v.to(ydt)
+        vq = v.to(ydt)
+        if s["gn_stats"]:   # (sum, sumsq) per (image, group) of the bf16-rounded output, fp64
+            cpg = s["gn_cpg"]
+            G = Cout // cpg
+            st = view(s["gn_stats"], N * G * GN_STAT_STRIDE, torch.float64).view(N, G, GN_STAT_STRIDE)
+            vg = vq.double().view(N, Ho * Wo, G, cpg)
+            st[:, :, 0] += vg.sum(dim=(1, 3))
+            st[:, :, 1] += (vg * vg).sum(dim=(1, 3))
+        _rows(s["y"], npix, ldc, ydt)[:, :Cout] = vq
 
     # ------------------------------------------------------------------------------------------ wgrad plans
     def dslb_wgrad_plan_create(self, segs, n, out):
@@ -237,6 +246,206 @@ class EmuLib:
         yo = view(y, N * H * W * Cc, BF16).view(N, H, W, Cc)
         yo.zero_()
         yo[:, 0:2 * h:2, 0:2 * w:2] = view(x, N * h * w * Cc, BF16).view(N, h, w, Cc)
+        return 0
+
+    # ------------------------------------------------------------------------------------------ FPN glue
+    def dslb_upsample_add(self, dst, src, N, H, W, h, w, Cc, stream):
+        d = view(dst, N * H * W * Cc, BF16).view(N, H, W, Cc)
+        sv = view(src, N * h * w * Cc, BF16).view(N, h, w, Cc).permute(0, 3, 1, 2).float()
+        up = F.interpolate(sv, size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+        d.copy_((d.float() + up).to(BF16))
+        return 0
+
+    def dslb_upsample_add_bwd(self, dsrc, ddst, N, H, W, h, w, Cc, stream):
+        g = view(ddst, N * H * W * Cc, BF16).view(N, H, W, Cc).permute(0, 3, 1, 2).float()
+        z = torch.zeros(N, Cc, h, w, requires_grad=True)
+        F.interpolate(z, size=(H, W), mode="nearest").backward(g)
+        d = view(dsrc, N * h * w * Cc, BF16).view(N, h, w, Cc)
+        d.copy_((d.float() + z.grad.permute(0, 2, 3, 1)).to(BF16))
+        return 0
+
+    # ------------------------------------------------------------------------------------------ GroupNorm
+    def dslb_gn_bwd_blocks(self, segs, n):
+        return 1
+
+    def dslb_gn_bwd_plan(self, segs, n, host):
+        return 0
+
+    @staticmethod
+    def _gn_items(segs, n):
+        fields = [f for f, _ in type(segs[0])._fields_]
+        return [{f: getattr(segs[i], f) for f in fields} for i in range(n)]
+
+    @staticmethod
+    def _gn_norm(d, Cc, groups, eps):
+        N, HW = d["N"], d["HW"]
+        cpg = Cc // groups
+        x = view(d["x"], N * HW * Cc, BF16).view(N, HW, groups, cpg).float()
+        st = view(d["stats"], N * groups * GN_STAT_STRIDE, torch.float64).view(N, groups, GN_STAT_STRIDE)
+        cnt = float(HW * cpg)
+        mean = st[:, :, 0] / cnt
+        var = (st[:, :, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        mean, rstd = mean.float().view(N, 1, groups, 1), rstd.float().view(N, 1, groups, 1)
+        gamma = view(d["gamma"], Cc, torch.float32).view(1, 1, groups, cpg)
+        beta = view(d["beta"], Cc, torch.float32).view(1, 1, groups, cpg)
+        xhat = (x - mean) * rstd
+        return x, xhat, gamma, beta, mean, rstd, cpg
+
+    def dslb_gn_apply_relu_tab(self, segs, n, Cc, groups, eps, tab, nb, stream):
+        for d in self._gn_items(segs, n):
+            x, xhat, gamma, beta, mean, rstd, cpg = self._gn_norm(d, Cc, groups, eps)
+            y = (xhat * gamma + beta).clamp_min(0)
+            view(d["y"], y.numel(), BF16).copy_(y.reshape(-1).to(BF16))
+            if d["mr"]:
+                mr = view(d["mr"], d["N"] * groups * 4, torch.float32).view(d["N"], groups, 4)
+                mr[:, :, 0] = mean.view(d["N"], groups)
+                mr[:, :, 1] = rstd.view(d["N"], groups)
+        return 0
+
+    def dslb_gn_apply_relu(self, segs, n, Cc, groups, eps, stream):
+        return self.dslb_gn_apply_relu_tab(segs, n, Cc, groups, eps, None, 0, stream)
+
+    def dslb_gn_bwd(self, segs, n, Cc, groups, eps, tab, nb, stream):
+        for d in self._gn_items(segs, n):
+            N, HW = d["N"], d["HW"]
+            x, xhat, gamma, beta, mean, rstd, cpg = self._gn_norm(d, Cc, groups, eps)
+            dz = view(d["dz"], N * HW * Cc, BF16).view(N, HW, groups, cpg).float()
+            dy = torch.where(xhat * gamma + beta > 0, dz, torch.zeros_like(dz))
+            red = view(d["red"], N * Cc * 2, torch.float64).view(N, Cc, 2)
+            red[:, :, 0] += dy.sum(dim=1).reshape(N, Cc).double()
+            red[:, :, 1] += (dy * xhat).sum(dim=1).reshape(N, Cc).double()
+            gdy = gamma * dy
+            m1 = gdy.mean(dim=(1, 3), keepdim=True)
+            m2 = (gdy * xhat).mean(dim=(1, 3), keepdim=True)
+            dx = (rstd * (gdy - m1 - xhat * m2)).to(BF16)
+            view(d["y"], dx.numel(), BF16).copy_(dx.reshape(-1))
+            if d["dbias"]:
+                view(d["dbias"], Cc, torch.float32).add_(dx.float().sum(dim=(0, 1)).reshape(Cc))
+        return 0
+
+    def dslb_gn_bwd_params(self, red, dgamma, dbeta, N, Cc, stream):
+        r = view(red, N * Cc * 2, torch.float64).view(N, Cc, 2)
+        view(dgamma, Cc, torch.float32).add_(r[:, :, 1].sum(0).float())
+        view(dbeta, Cc, torch.float32).add_(r[:, :, 0].sum(0).float())
+        return 0
+
+    # ------------------------------------------------------------------------------------------ head / loss
+    def dslb_fcos_regctr_affine(self, scales, stride, reg_bias, ctr_bias, level_mult, rc_scale, rc_shift, scale_vals, nl,
+                                stream):
+        sc = view(scales, (nl - 1) * stride + 1, torch.float32)[::stride]
+        lm = view(level_mult, nl, torch.float32)
+        bias5 = torch.cat([view(reg_bias, 4, torch.float32), view(ctr_bias, 1, torch.float32)])
+        rs = view(rc_scale, nl * 8, torch.float32).view(nl, 8)
+        rh = view(rc_shift, nl * 8, torch.float32).view(nl, 8)
+        rs.fill_(1.0)
+        rs[:, :4] = (sc * lm).view(nl, 1)
+        rh.zero_()
+        rh[:, :5] = bias5.view(1, 5) * rs[:, :5]
+        view(scale_vals, nl, torch.float32).copy_(sc)
+        return 0
+
+    @staticmethod
+    def _levels(levels, nl):
+        fields = [f for f, _ in type(levels[0])._fields_]
+        return [{f: getattr(levels[i], f) for f in fields} for i in range(nl)]
+
+    @staticmethod
+    def _box_lists(boxes, off, B, labels=None):
+        o = view(off, B + 1, torch.int32).tolist()
+        bx = view(boxes, max(o[-1], 1) * 4, torch.float32).view(-1, 4)
+        out = [bx[o[i]:o[i + 1]].clone() for i in range(B)]
+        if labels is None:
+            return out
+        lb = view(labels, max(o[-1], 1), torch.int64)
+        return out, [lb[o[i]:o[i + 1]].clone() for i in range(B)]
+
+    def dslb_fcos_targets(self, levels, nl, B, Cn, gt_boxes, gt_labels, gt_off, ig_boxes, ig_off, center_sampling,
+                          norm_on_bbox, lw, n_labeled, labels, bbox_targets, weights, ctr_targets, counts, stream):
+        """Targets through the oracle's restatement of get_targets / the ignore and unlabeled weights (the CUDA kernel is
+        checked bit-exact against the same functions on the GPU)."""
+        from oracle import fcos_oracle as O
+        lv = self._levels(levels, nl)
+        gts, gls = self._box_lists(gt_boxes, gt_off, B, gt_labels)
+        igs = self._box_lists(ig_boxes, ig_off, B) if _addr(ig_boxes) else None
+        strides = tuple(l["stride"] for l in lv)
+        rr = tuple((l["rr_lo"], l["rr_hi"]) for l in lv)
+        radius = lv[0]["cs_radius"] / lv[0]["stride"]
+        self.loss_ctx = dict(gts=gts, gls=gls, igs=igs, strides=strides, rr=rr, radius=radius, Cn=Cn,
+                             center_sampling=bool(center_sampling), norm_on_bbox=bool(norm_on_bbox))
+        zeros = lambda c: [torch.zeros(B, c, l["h"], l["w"]) for l in lv]  # noqa: E731
+        out = O.fcos_loss(zeros(Cn), zeros(4), zeros(1), gts, gls, igs, strides=strides, regress_ranges=rr,
+                          num_classes=Cn, center_sampling=bool(center_sampling), radius=radius,
+                          norm_on_bbox=bool(norm_on_bbox), loss_weight=lw, return_aux=True)
+        aux = out["_aux"]
+        P = aux["labels"].numel()
+        view(labels, P, torch.int64).copy_(aux["labels"])
+        view(bbox_targets, P * 4, torch.float32).view(P, 4).copy_(aux["bbox_targets"])
+        view(weights, P, torch.float32).copy_(aux["weight"])
+        ct = view(ctr_targets, P, torch.float32)
+        ct.zero_()
+        ct[aux["pos_inds"]] = aux["centerness_targets"]
+        c = view(counts, 2, torch.float64)
+        c[0] += aux["num_pos_local"]
+        c[1] += aux["ctr_sum_local"]
+        return 0
+
+    def dslb_fcos_norm(self, counts, world, norm, stream):
+        c = view(counts, 2, torch.float64)
+        nv = view(norm, 2, torch.float32)
+        nv[0] = max(float(c[0]) / world, 1.0)
+        nv[1] = max(float(c[1]) / world, 1e-6)
+        return 0
+
+    def dslb_fcos_loss(self, levels, nl, B, Cn, labels, bbox_targets, weights, ctr_targets, norm, alpha, gamma, lw,
+                       n_labeled, si_weight, level_scales, loss_sums, dscale, stream):
+        """Losses and head-output gradients by autograd over the oracle's FCOSHead.loss restatement, then the chain rule
+        the header documents (d/d conv_reg through relu(scale * x), d/d scale)."""
+        from oracle import fcos_oracle as O
+        lv, ctx = self._levels(levels, nl), self.loss_ctx
+        cls, box, ctr = [], [], []
+        for l in lv:
+            n = B * l["h"] * l["w"]
+            c = _rows(l["cls"], n, l["ld_cls"], torch.float32)[:, :Cn].reshape(B, l["h"], l["w"], Cn)
+            r = _rows(l["regctr"], n, 8, torch.float32).reshape(B, l["h"], l["w"], 8)
+            cls.append(c.permute(0, 3, 1, 2).clone().requires_grad_(True))
+            box.append(r[..., :4].permute(0, 3, 1, 2).clone().requires_grad_(True))
+            ctr.append(r[..., 4:5].permute(0, 3, 1, 2).clone().requires_grad_(True))
+        nv = view(norm, 2, torch.float32)
+        out = O.fcos_loss(cls, box, ctr, ctx["gts"], ctx["gls"], ctx["igs"], strides=ctx["strides"],
+                          regress_ranges=ctx["rr"], num_classes=Cn, center_sampling=ctx["center_sampling"],
+                          radius=ctx["radius"], norm_on_bbox=ctx["norm_on_bbox"], loss_weight=lw,
+                          soft_weight=float(si_weight), soft_warm_up=-1, world_num_pos=float(nv[0]),
+                          world_ctr_sum=float(nv[1]))
+        sum(out.values()).backward()
+        ls = view(loss_sums, 4, torch.float64)
+        for i, k in enumerate(("loss_cls", "loss_bbox", "loss_centerness", "loss_sisoft")):
+            if k in out:
+                ls[i] += float(out[k].detach())
+        sc = view(level_scales, nl, torch.float32) if _addr(level_scales) else None
+        for i, l in enumerate(lv):
+            n = B * l["h"] * l["w"]
+            scale = float(sc[i]) if sc is not None else l["scale"]
+            gcls = (cls[i].grad if cls[i].grad is not None else torch.zeros_like(cls[i])).permute(0, 2, 3, 1).reshape(n, Cn)
+            gbox = (box[i].grad if box[i].grad is not None else torch.zeros_like(box[i])).permute(0, 2, 3, 1).reshape(n, 4)
+            gctr = (ctr[i].grad if ctr[i].grad is not None else torch.zeros_like(ctr[i])).permute(0, 2, 3, 1).reshape(n, 1)
+            bx = box[i].detach().permute(0, 2, 3, 1).reshape(n, 4)
+            if l["dcls_bf16"]:
+                _rows(l["dcls_bf16"], n, l["ld_dcls"], BF16)[:, :Cn] = gcls.to(BF16)
+            if l["dcls_f32"]:
+                _rows(l["dcls_f32"], n, Cn, torch.float32).copy_(gcls)
+            live = (bx > 0).float()
+            if l["dregctr_bf16"]:
+                d = _rows(l["dregctr_bf16"], n, l["ld_dreg"], BF16)
+                d[:, :4] = (gbox * scale * live).to(BF16)
+                d[:, 4:5] = gctr.to(BF16)
+                d[:, 5:8] = 0
+            if l["dregctr_f32"]:
+                d = _rows(l["dregctr_f32"], n, 8, torch.float32)
+                d[:, :4] = gbox
+                d[:, 4:5] = gctr
+            if _addr(dscale):
+                view(dscale, nl, torch.float32)[i] += float((gbox * live * bx / scale).sum())
         return 0
 
     # ------------------------------------------------------------------------------------------ RLA

@@ -1,5 +1,5 @@
-"""Host-side plan logic of the backbones on CPU: FCOSNet(parts="backbone") is built and run against tests/emu_lib.py (a
-torch restatement of the C-ABI contracts in include/dslb.h), and its stage outputs and parameter gradients are compared
+"""Host-side plan logic on CPU: FCOSNet (backbone only, and the whole detector) is built and run against tests/emu_lib.py
+(a torch restatement of the C-ABI contracts in include/dslb.h), and its outputs and parameter gradients are compared
 with the oracle. The ResNet case validates the emulator on the plan the GPU tests already cover; the RLA_ResNet case
 checks engine_rla.py's dataflow (concat-as-two-launches conv1, pooled state, in-place masked gradients, trainable
 BatchNorm affines, sliced pack / unpack, gradient buckets). Kernel numerics are the `-m gpu` tests' job."""
@@ -107,3 +107,84 @@ def test_rla_other_configs_on_the_emulator(layers, depth, B, H, W):
     # 23 blocks in stage 3: the bf16 rounding noise of the gradient maps has 4x the depth to accumulate over
     _check(outs, ref, grads, sd, 156 if depth == 50 else 156 + 17 * 10, slack=0.0 if depth == 50 else 0.08)
     assert ranges[0][0] == 0 and ranges[-1][1] == store.n_train
+
+
+def _detector_state(backbone, seed):
+    """Reference-named state of the whole detector with bounded gains (see GI.rla_detector_state)."""
+    if backbone == "rla":
+        return GI.rla_detector_state(seed, seed + 1)
+    from dsl_b200.params import ParamStore, resnet_spec
+    st = ParamStore(resnet_spec(50, prefix="backbone."), "cpu").init_reference(seed)
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for p in st.spec:
+        v = st[p.name].clone()
+        if p.kind in ("bn_b", "bn_mean"):
+            v = torch.from_numpy((rng.randn(*p.shape) * 0.1).astype(np.float32))
+        elif p.kind == "bn_var":
+            v = torch.from_numpy((rng.rand(*p.shape) + 0.5).astype(np.float32))
+        sd[p.name] = v
+    rest = GI.rla_detector_state(seed, seed + 1)
+    sd.update({k: v for k, v in rest.items() if not k.startswith("backbone.")})
+    return sd
+
+
+@pytest.mark.parametrize("backbone", ["resnet", "rla"])
+def test_full_detector_plan_on_the_emulator(backbone):
+    """The whole student plan — backbone, FPN, FCOSHead with GroupNorm, target assignment + loss, and the backward through
+    all of it with its gradient buckets — executed on the emulator: FPN maps, head outputs and the three losses against
+    the fp32 oracle on the same weights, every trainable tensor's gradient against the oracle's autograd."""
+    from dsl_b200.engine import FCOSNet
+    from dsl_b200.params import ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
+    B, H, W = 2, 128, 160
+    sd0 = _detector_state(backbone, 71)
+    spec = (rla_resnet_spec() if backbone == "rla" else resnet_spec(50)) + fpn_spec() + head_spec(80)
+    x = GI.make_tensor(np.random.RandomState(72), B, 3, H, W)
+    gts, labels, ignores = GI.make_gt(73, B, H, W, max_gt=6, max_ignore=2, with_ignore=True)
+    with emu_lib.installed():
+        store = ParamStore(spec, "cpu")
+        store.load_state_dict(sd0)
+        net = FCOSNet(B, H, W, depth=50, train=True, store=store, device="cpu", loss_weight=3.0, backbone=backbone)
+        net.img.copy_(x)
+        net.forward()
+        net.set_targets(gts, labels, ignores)
+        net.run_targets()
+        net.run_loss()
+        net.backward()
+        got_losses = {k: float(v) for k, v in net.losses().items()}
+        ps = [p.float().permute(0, 3, 1, 2).clone() for p in net.p]
+        cls = [c.permute(0, 3, 1, 2).clone() for c in net.cls_out]
+        grads = {p.name: net.grad_view(p.name).clone().view(p.shape) for p in store.spec if p.region != "F"}
+        ranges = sorted((lo, hi) for _, lo, hi in net.bwd_buckets)
+    assert ranges[0][0] == 0 and ranges[-1][1] == store.n_train and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    sd = {k: v.clone().requires_grad_(k in grads) for k, v in sd0.items()}
+    fwd = O.rla_resnet_forward if backbone == "rla" else (lambda s, xx, prefix: O.resnet_forward(s, xx, 50, prefix=prefix))
+    rp = O.fpn_forward(sd, fwd(sd, x, prefix="backbone."), prefix="neck.")
+    rc, rb, rt = O.fcos_head_forward(sd, rp, training=True, prefix="bbox_head.")
+    ref = O.fcos_loss(rc, rb, rt, gts, labels, ignores, loss_weight=3.0)
+    for a, b in zip(ps, rp):
+        assert (a - b.detach()).norm().item() / b.norm().item() < 2e-2
+    for a, b in zip(cls, rc):
+        assert (a - b.detach()).abs().max().item() < 5e-2          # logits around the -4.59 prior
+    for k, v in ref.items():
+        assert abs(got_losses[k] - float(v.detach())) <= 2e-2 * abs(float(v.detach())), (k, got_losses[k], float(v.detach()))
+    sum(ref.values()).backward()
+    bad = []
+    for name, g in grads.items():
+        r = sd[name].grad
+        assert r is not None, name
+        if g.numel() == 1:      # Scale parameters: one number each (exactly 0 on levels without positive points), a
+            # single draw of the bf16 rounding noise summed over a handful of positive points (cf. the GPU test's bar)
+            assert abs(float(g) - float(r)) <= 0.5 * abs(float(r)) + 1e-5, (name, float(g), float(r))
+            continue
+        c = _cos(g, r)
+        if name.startswith(("neck.", "bbox_head.")):
+            floor = 0.98
+        elif ".stage_bns." in name:
+            floor = 0.90
+        else:
+            floor = _floor(name[len("backbone."):]) - 0.03      # + the FPN / head backward in front of the backbone
+        if c < floor:
+            bad.append((name, round(c, 4)))
+    assert not bad, (len(bad), bad[:10])
+    assert len(grads) > 90
