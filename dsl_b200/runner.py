@@ -17,6 +17,7 @@ import logging
 import os
 import os.path as osp
 import time
+from collections import OrderedDict
 
 import torch
 
@@ -71,7 +72,13 @@ class SemiEpochBasedRunner:
         self.outputs = None
         self.log_buffer = []
         self.imagefiles = []
-        self.engine = None
+        self.engine = None                   # the engine of the current batch shape
+        # multi-scale training (BASELINE configs[4]: Resize [(1333,640),(1333,800)] + Pad(32) gives a handful of padded
+        # shapes): one engine (plan + CUDA graph) per (B, H, W), least recently used first; all of them train the SAME
+        # parameter stores and share the optimizer / adathres state (see _share_state)
+        self._engines = OrderedDict()
+        self.max_cached_shapes = 8
+        self._si_iter = 0                    # FCOSHead.cur_iter of the SI-soft warm-up, across shapes
         self.ema_keep = 0.99                 # cfg ema_config ratio (configs/fcos_semi/*.py:199)
 
     # ---- counters (mmcv BaseRunner properties) ----------------------------------------------------------------
@@ -87,9 +94,9 @@ class SemiEpochBasedRunner:
         from .plugin import EMAOWNHook
         if isinstance(hook, EMAOWNHook):
             self.ema_keep = float(hook.ratio)
-            if self.engine is not None:
-                self.engine.ema_keep = self.ema_keep
-                self.engine.graphs = None
+            for eng in self._engines.values():
+                eng.ema_keep = self.ema_keep
+                eng.graphs = None
             return
         self._hooks.append(hook)
 
@@ -98,8 +105,20 @@ class SemiEpochBasedRunner:
             getattr(h, fn_name, lambda r: None)(self)
 
     # ---- engine ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _share_state(src, dst):
+        """Everything a step carries over to the next one besides the weights must not depend on the batch shape: the
+        SGD momentum buffer, the LR-schedule scalar and the epoch's adaptive-threshold statistics / thresholds are ONE set
+        of tensors used by every shape's engine (assigned before the new engine captures its graph)."""
+        dst.mom, dst.lr_scale = src.mom, src.lr_scale
+        for name in ("stat_cnt", "stat_cum", "stat_prev", "thr_class", "class_weight", "have_prev"):
+            setattr(dst.post, name, getattr(src.post, name))
+
     def _engine_for(self, B, H, W):
-        if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
+        key = (B, H, W)
+        if key in self._engines:
+            self._engines.move_to_end(key)
+            self.engine = self._engines[key]
             return self.engine
         m, hc = self.model, self.model.head_cfg
         if m.store.device.type != "cuda":
@@ -118,6 +137,12 @@ class SemiEpochBasedRunner:
                                 scale_invariant=self.scale_invariant, soft_weight=hc["soft_weight"],
                                 soft_warm_up=hc["soft_warm_up"], head_kwargs=head_kwargs,
                                 backbone=getattr(m, "backbone_kind", "resnet"), **kw)
+        self.engine.ema_keep = self.ema_keep
+        if self._engines:
+            self._share_state(next(reversed(self._engines.values())), self.engine)
+        self._engines[key] = self.engine
+        while len(self._engines) > self.max_cached_shapes:
+            self._engines.popitem(last=False)
         m._dirty()
         if self.ema_flag:
             self.ema_model._dirty()
@@ -135,7 +160,9 @@ class SemiEpochBasedRunner:
         B, _, H, W = img.shape
         eng = self._engine_for(B, H, W)
         teacher_img = data_batch.get("teacher_img")
+        eng.cur_iter = self._si_iter
         eng.set_inputs(img, gts, labels, ign, teacher_img=_unwrap(teacher_img) if teacher_img is not None else img)
+        self._si_iter = eng.cur_iter
         losses = eng.step()
         log_vars = {k: float(v) for k, v in losses.items()}     # the reference's .item() per logged value (base.py:206)
         log_vars["loss"] = sum(v for k, v in log_vars.items() if "loss" in k)
@@ -159,6 +186,10 @@ class SemiEpochBasedRunner:
         # per-epoch adaptive thresholds (UnlabelPredHook.before_train_epoch -> adathres, unlabel_pred_hook.py:447-449)
         if self.engine is not None:
             self.engine.end_epoch()
+            for eng in self._engines.values():     # the other shapes' engines: same history flag, capture again
+                if eng is not self.engine and eng.post.have_prev != self.engine.post.have_prev:
+                    eng.post.have_prev = self.engine.post.have_prev
+                    eng.graphs = None
         self.call_hook("after_train_epoch")
         self._epoch += 1
 

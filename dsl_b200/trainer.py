@@ -109,7 +109,13 @@ class DSLEngine:
     def end_epoch(self, **adathres_kw):
         """Per-epoch adaptive thresholds (UnlabelPredHook.before_train_epoch -> adathres, unlabel_pred_hook.py:447-449):
         turn the statistics the teacher branch accumulated on the device into next epoch's per-class thresholds."""
-        return self.post.adathres_update(**adathres_kw)
+        had = self.post.have_prev
+        out = self.post.adathres_update(**adathres_kw)
+        if self.post.have_prev != had:
+            # the captured pseudo-label launch carries the "no history yet" gate (a NULL pointer for last epoch's
+            # thresholds, unlabel_pred_hook.py:315-343): capture again now that a history exists
+            self.graphs = None
+        return out
 
     # ---------------------------------------------------------------------------------------- step pieces
     def _teacher_branch(self):

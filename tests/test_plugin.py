@@ -524,3 +524,86 @@ def test_plugin_rla_pretrained_checkpoint_loads_into_the_backbone(tmp_path):
     assert torch.equal(m.store["backbone.stages.2.3.conv1.weight"], ck["stages.2.3.conv1.weight"])
     assert torch.equal(m.store["backbone.conv_outs.1.weight"], ck["conv_outs.1.weight"])
     assert float(m.store["backbone.stage_bns.3.0.running_var"].min()) == 1.0      # missing in the checkpoint: init kept
+
+
+def test_runner_keeps_one_engine_per_batch_shape_with_shared_optimizer_state(monkeypatch):
+    """Multi-scale training (BASELINE configs[4]) changes the padded batch shape between iterations: the runner keeps one
+    engine per (B, H, W) (LRU) and all of them share the momentum buffer, the LR scalar, the SI warm-up counter and the
+    adaptive-threshold state. Host logic only: the engine is replaced by a stub, nothing touches the GPU."""
+    import logging
+    from types import SimpleNamespace
+    from dsl_b200 import plugin, runner as R
+
+    class FakeEngine:
+        made = []
+
+        def __init__(self, B, H, W, **kw):
+            self.B, self.H, self.W, self.kw = B, H, W, kw
+            self.mom, self.lr_scale = torch.zeros(4), torch.ones(1)
+            self.cur_iter, self.graphs, self.lr, self.ema_keep = 0, "captured", kw["lr"], kw["ema_keep"]
+            z = lambda dt: torch.zeros(80, dtype=dt)  # noqa: E731
+            self.post = SimpleNamespace(stat_cnt=z(torch.int64), stat_cum=z(torch.float64), stat_prev=z(torch.float64),
+                                        thr_class=z(torch.float64), class_weight=z(torch.float64), have_prev=False)
+            FakeEngine.made.append(self)
+
+        def set_inputs(self, *a, **k):
+            self.cur_iter += 1
+
+        def step(self):
+            self.mom += 1
+            self.post.stat_cnt += 1
+            return dict(loss_cls=torch.tensor(1.0), loss_bbox=torch.tensor(0.5), loss_centerness=torch.tensor(0.25))
+
+        def end_epoch(self):
+            self.post.have_prev = True
+            self.graphs = None
+
+    monkeypatch.setattr(R, "DSLEngine", FakeEngine)
+    m = _build()
+    m.store.device = torch.device("cuda")          # the stub never dereferences it
+    run = R.SemiEpochBasedRunner(m, logger=logging.getLogger("t"), max_epochs=1)
+    run.register_hook(plugin.EMAOWNHook(interval=1, mode="iteration", ratio=0.999, start_point=0))
+    shapes = [(2, 128, 160), (2, 160, 128), (2, 128, 160), (2, 192, 160)]
+    loader = [dict(img=torch.zeros(B, 3, H, W), img_metas=[dict(filename=f"{i}_{b}.jpg") for b in range(B)],
+                   gt_bboxes=[torch.zeros(0, 4)] * B, gt_labels=[torch.zeros(0, dtype=torch.long)] * B,
+                   gt_bboxes_ignore=[torch.zeros(0, 4)] * B) for i, (B, H, W) in enumerate(shapes)]
+    run.train(loader)
+    e = FakeEngine.made
+    assert [(x.B, x.H, x.W) for x in e] == [(2, 128, 160), (2, 160, 128), (2, 192, 160)]      # the third batch re-used #0
+    assert e[1].mom is e[0].mom and e[2].mom is e[0].mom and float(e[0].mom[0]) == 4.0           # ONE momentum buffer
+    assert e[2].lr_scale is e[0].lr_scale and e[1].post.stat_cnt is e[0].post.stat_cnt
+    assert int(e[0].post.stat_cnt[0]) == 4 and run._si_iter == 4 and all(x.ema_keep == 0.999 for x in e)
+    assert run.engine is e[2] and all(x.post.have_prev and x.graphs is None for x in e)       # epoch end reached every shape
+    assert e[0].kw["backbone"] == "resnet" and e[0].kw["student_store"] is m.store
+    run.max_cached_shapes = 2
+    run._engine_for(2, 224, 160)
+    assert list(run._engines) == [(2, 192, 160), (2, 224, 160)] and FakeEngine.made[3].mom is e[0].mom
+
+
+@pytest.mark.gpu
+def test_runner_multi_shape_training_on_the_gpu():
+    """Two padded shapes alternating (multi-scale training): two engines, one momentum buffer, weights keep moving, losses
+    finite, the engine of the first shape is re-used (its CUDA graph replays against the shared state)."""
+    import logging
+    from dsl_b200 import plugin
+    from dsl_b200.runner import SemiEpochBasedRunner
+    cfg = {k: v for k, v in MODEL_CFG.items() if k != "type"}
+    model, ema = plugin.FCOS(**cfg).cuda(), plugin.FCOS(**cfg).cuda()
+    ema.load_state_dict(model.state_dict())
+    runner = SemiEpochBasedRunner(model, logger=logging.getLogger("t"), max_epochs=1, ema_model=ema)
+    loader = [_data(2, 128, 160, 20), _data(2, 160, 128, 21), _data(2, 128, 160, 22), _data(2, 160, 128, 23)]
+    flats = []
+
+    class Probe:
+        def after_train_iter(self, r):
+            torch.cuda.synchronize()
+            flats.append(model.store.flat.clone())
+            assert np.isfinite(r.outputs["log_vars"]["loss"])
+
+    runner.register_hook(Probe())
+    runner.run([loader], [("train", 1)])
+    assert list(runner._engines) == [(2, 128, 160), (2, 160, 128)]
+    e0, e1 = runner._engines.values()
+    assert e0.mom is e1.mom and float(e0.mom.abs().sum()) > 0
+    assert all(not torch.equal(a, b) for a, b in zip(flats, flats[1:]))      # every iteration stepped the same weights
+    assert e0.post.have_prev and e1.post.have_prev and e0.graphs is None and e1.graphs is None
