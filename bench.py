@@ -139,16 +139,16 @@ def ncu_traffic_per_launch():
         return None
 
 
-def cpu_baseline(sample_hw, depth, steps=1, warmup=0, batch=1):
+def cpu_baseline(sample_hw, depth, steps=1, warmup=0, batch=1, backbone="resnet"):
     """The reference's CPU arithmetic for the step (oracle port) on a bounded sample of the workload."""
     import torch
     from oracle import cpu_step
     h, w = (int(v) for v in sample_hw.split("x"))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    r = cpu_step.time_cpu_steps(batch, h, w, steps=steps, warmup=warmup, depth=depth, threads=cores)
+    r = cpu_step.time_cpu_steps(batch, h, w, steps=steps, warmup=warmup, depth=depth, threads=cores, backbone=backbone)
     return dict(value=round(r["images_per_sec"], 4), unit=UNIT, cores=r["cores"], kind="port",
-                sample=f"{steps} teacher+student step(s) of B={batch} at {h}x{w}, R{depth}, fp32 torch CPU "
+                sample=f"{steps} teacher+student step(s) of B={batch} at {h}x{w}, {'RLA_' if backbone == 'rla' else ''}R{depth}, fp32 torch CPU "
                        f"({r['seconds_per_step']:.2f} s/step), warmup {warmup}")
 
 
@@ -159,7 +159,7 @@ def run_reference(args):
     t0 = time.time()
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=steps, warmup=warm, batch=args.batch)
+    cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=steps, warmup=warm, batch=args.batch, backbone=args.backbone)
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=round(1000.0 * args.batch / cb["value"], 1), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="fp32", data="synthetic", impl="reference",
@@ -297,7 +297,7 @@ def main():
 
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=3, warmup=1, batch=2)
+        cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=3, warmup=1, batch=2, backbone=args.backbone)
 
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",

@@ -19,12 +19,15 @@ def _split(sd):
 
 
 class CpuStep:
-    def __init__(self, B, H, W, depth=50, seed=0, threads=None):
-        from dsl_b200.params import ParamStore, fpn_spec, head_spec, resnet_spec
+    def __init__(self, B, H, W, depth=50, seed=0, threads=None, backbone="resnet"):
+        from dsl_b200.params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
         if threads:
             torch.set_num_threads(threads)
         self.B, self.H, self.W, self.depth = B, H, W, depth
-        store = ParamStore(resnet_spec(depth) + fpn_spec() + head_spec(), "cpu").init_reference(seed)
+        self.layers = RESNET_BLOCKS[depth]
+        self.backbone = backbone     # "rla": RLA_ResNet, the shipped configs' backbone (oracle: rla_resnet_forward)
+        bb_spec = rla_resnet_spec(self.layers) if backbone == "rla" else resnet_spec(depth)
+        store = ParamStore(bb_spec + fpn_spec() + head_spec(), "cpu").init_reference(seed)
         self.spec = store.spec
         self.student = {p.name: store.views[p.name].clone() for p in store.spec}
         self.teacher = {k: v.clone() for k, v in self.student.items()}
@@ -37,11 +40,16 @@ class CpuStep:
         from tests.golden import inputs as GI
         self.gts, self.labels, self.ignores = GI.make_gt(seed + 1, B, H, W, with_ignore=True)
 
+    def _backbone(self, bb, img):
+        if self.backbone == "rla":
+            return O.rla_resnet_forward(bb, img, self.layers)
+        return O.resnet_forward(bb, img, self.depth)
+
     def step(self, lr=0.01):
         B = self.B
         with torch.no_grad():
             bb, neck, head = _split(self.teacher)
-            ps = O.fpn_forward(neck, O.resnet_forward(bb, self.img_t, self.depth))
+            ps = O.fpn_forward(neck, self._backbone(bb, self.img_t))
             cls, box, ctr = O.fcos_head_forward(head, ps, training=False)
             O.decode_candidates(cls, box, ctr, [(self.H, self.W, 3)] * B, [[1.0] * 4] * B, nms_pre=1000,
                                 score_thr=0.05, rescale=True)
@@ -49,7 +57,7 @@ class CpuStep:
         sd = dict(self.student)
         sd.update(params)
         bb, neck, head = _split(sd)
-        ps = O.fpn_forward(neck, O.resnet_forward(bb, self.img_s, self.depth))
+        ps = O.fpn_forward(neck, self._backbone(bb, self.img_s))
         cls, box, ctr = O.fcos_head_forward(head, ps, training=True)
         losses = O.fcos_loss(cls, box, ctr, self.gts, self.labels, self.ignores, loss_weight=3.0)
         sum(losses.values()).backward()
@@ -63,11 +71,11 @@ class CpuStep:
                                            0.0 if bias else 1e-4)
                 self.student[n], self.mom[n] = p, m
             self.teacher = O.ema_update(self.teacher, self.student, 0.99)
-        return {k: float(v) for k, v in losses.items()}
+        return {k: float(v.detach()) for k, v in losses.items()}
 
 
-def time_cpu_steps(B, H, W, steps=1, warmup=0, depth=50, threads=None):
-    cs = CpuStep(B, H, W, depth=depth, threads=threads)
+def time_cpu_steps(B, H, W, steps=1, warmup=0, depth=50, threads=None, backbone="resnet"):
+    cs = CpuStep(B, H, W, depth=depth, threads=threads, backbone=backbone)
     for _ in range(warmup):
         cs.step()
     t0 = time.perf_counter()
