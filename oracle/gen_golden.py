@@ -501,15 +501,19 @@ def _load_pipeline_classes():
 
 
 def gen_view_geometry(R):
+    np.savez_compressed(os.path.join(OUT, "view_geometry.npz"), **view_cases(202, 14))
+
+
+def view_cases(seed, ncase):
     """Boxes through the reference's Resize._resize_bboxes -> PatchShuffle.__call__ -> RandomFlip.bbox_flip (the order of
     the train pipelines, configs/fcos_semi/*.py:70-92) for a set of views: flip / flop cuts with boxes on either side of,
-    straddling and touching the cut, degenerate cuts (no-op), flips, clipping, empty lists."""
+    straddling and touching the cut, degenerate cuts (no-op), flips, clipping, empty lists. Returns the dict the golden
+    file stores (seed 202, 14 cases); tests/test_geometry.py also runs other seeds live where the reference is present."""
     import random
     Resize, RandomFlip, PatchShuffle = _load_pipeline_classes()
     out = {}
-    rng = np.random.RandomState(202)
+    rng = np.random.RandomState(seed)
     views = []
-    ncase = 14
     for k in range(ncase):
         oh, ow = int(rng.randint(300, 700)), int(rng.randint(300, 900))
         sx, sy = np.float32(rng.uniform(0.6, 1.9)), np.float32(rng.uniform(0.6, 1.9))
@@ -550,7 +554,7 @@ def gen_view_geometry(R):
         views.append([float(sx), float(sy), w, h, int(clip), {None: 0, "flip": 1, "flop": 2}[ps_mode], crop, int(flip)])
     out["views"] = np.array(views, dtype=np.float64)
     out["meta"] = np.array([ncase], dtype=np.int64)
-    np.savez_compressed(os.path.join(OUT, "view_geometry.npz"), **out)
+    return out
 
 
 def main():
