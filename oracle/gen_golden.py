@@ -327,8 +327,13 @@ def gen_misc(R):
 
 
 def gen_hook_chain(R):
+    np.savez_compressed(os.path.join(OUT, "hook_chain.npz"), **hook_chain_cases(R, 77, 6))
+
+
+def hook_chain_cases(R, seed, ncase):
     """Detections (multiclass_nms output order) -> bbox2result -> UnlabelPredHook.save_results2file (JSON on disk) ->
-    SemiCOCODataset._parse_ann_info: the reference's whole pseudo-label rule chain, executed from its own source."""
+    SemiCOCODataset._parse_ann_info: the reference's whole pseudo-label rule chain, executed from its own source.
+    Returns the dict the golden file stores (seed 77, 6 cases); the tests also run other seeds live."""
     import types
     save_results2file = ref_loader.load_hook_chain()
     C = 6
@@ -339,9 +344,8 @@ def gen_hook_chain(R):
     parse_ann = _extract_method(os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/semicoco.py"),
                                 "SemiCOCODataset", "_parse_ann_info", glb)
     out = {}
-    rng = np.random.RandomState(77)
+    rng = np.random.RandomState(seed)
     Wi, Hi = 640, 480
-    ncase = 6
     for k in range(ncase):
         n = int(rng.randint(0, 60)) if k else 100
         boxes = GI.demo_boxes(rng, n, Hi, Wi) + rng.rand(n, 4).astype(np.float32)
@@ -379,7 +383,7 @@ def gen_hook_chain(R):
         out[f"c{k}_ignore"] = ann["bboxes_ignore"]
     out["thr"] = np.array([0.33, 0.31, 0.35, 0.3, 0.3, 0.3], dtype=np.float64)  # missing classes -> default 0.3
     out["meta"] = np.array([ncase, C, Wi, Hi], dtype=np.int64)
-    np.savez_compressed(os.path.join(OUT, "hook_chain.npz"), **out)
+    return out
 
 
 def gen_adathres_chain(R):

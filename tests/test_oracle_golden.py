@@ -315,6 +315,27 @@ def test_hook_pseudo_label_chain_matches_reference():
     assert sum(len(g[f"c{k}_gt"]) for k in range(ncase)) > 20 and sum(len(g[f"c{k}_ignore"]) for k in range(ncase)) > 5
 
 
+def test_hook_pseudo_label_chain_vs_live_reference_other_seeds():
+    """Where the reference tree is present: the hook -> JSON -> dataset-filter chain of the reference run live on four
+    more random detection sets (24 images) against the oracle, bit-exact."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box): covered by hook_chain.npz")
+    from oracle.gen_golden import hook_chain_cases
+    R = ref_loader.load()
+    n_gt = n_ig = 0
+    for seed in range(80, 84):
+        g = hook_chain_cases(R, seed, 6)
+        ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+        for k in range(ncase):
+            gt, gl, ig = O.hook_pseudo_labels(g[f"c{k}_dets"], g[f"c{k}_labels"], C, Wi, Hi, g["thr"])
+            assert np.array_equal(gt, g[f"c{k}_gt"].reshape(-1, 4)), (seed, k)
+            assert np.array_equal(gl, g[f"c{k}_gt_labels"]), (seed, k)
+            assert np.array_equal(ig, g[f"c{k}_ignore"].reshape(-1, 4)), (seed, k)
+            n_gt, n_ig = n_gt + len(gt), n_ig + len(ig)
+    assert n_gt > 80 and n_ig > 20
+
+
 def test_oracle_vs_live_reference_randomised_loss_configs():
     """Beyond the committed fixtures: where the reference tree is present (build container), its own FCOSHead.loss /
     get_targets are executed live on a sweep of random batches — batch size 1-4 (odd: SI-soft branch), ragged map sizes,
