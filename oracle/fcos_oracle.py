@@ -473,13 +473,11 @@ def filter_pseudo_labels(rects, scores, cls_ids, img_w, img_h, thres_by_class=No
     return gt, np.array(gl, dtype=np.int64), ig
 
 
-def hook_pseudo_labels(dets, labels, num_classes, img_w, img_h, thr_by_class, infer_score_thr=0.1, iou=0.6,
-                       default_thres=(0.1, 0.3)):
-    """Detections of one image (multiclass_nms order: score descending) -> (gt_bboxes, gt_labels, gt_bboxes_ignore):
+def hook_saved_boxes(dets, labels, num_classes, infer_score_thr=0.1, iou=0.6):
+    """What UnlabelPredHook.save_results2file writes to the image's JSON file, as (rects, scores, class ids):
     runner/hooks/unlabel_pred_hook.py:20-38 (gate score >= thr, int() truncation, round(score, 6)), :55 (stable sort by
     score, descending), :142-165 (per class in range(0, num_classes - 1) — the last class is dropped —
-    nms(iou, score_threshold=0.1) on the truncated fp32 boxes) and datasets/semicoco.py:220-269 (filter_pseudo_labels).
-    thr_by_class: sequence of per-class thresholds (fp64)."""
+    nms(iou, score_threshold=0.1) on the truncated fp32 boxes). These are also the boxes adathres() counts (:315-343)."""
     dets = np.asarray(dets, dtype=np.float32).reshape(-1, 5)
     labels = np.asarray(labels).reshape(-1)
     items = []
@@ -510,6 +508,15 @@ def hook_pseudo_labels(dets, labels, num_classes, img_w, img_h, thr_by_class, in
                 rects.append(bi[k].tolist())
                 scores.append(float(si[k]))
                 cls.append(i)
+    return rects, scores, cls
+
+
+def hook_pseudo_labels(dets, labels, num_classes, img_w, img_h, thr_by_class, infer_score_thr=0.1, iou=0.6,
+                       default_thres=(0.1, 0.3)):
+    """Detections of one image (multiclass_nms order: score descending) -> (gt_bboxes, gt_labels, gt_bboxes_ignore):
+    hook_saved_boxes (the JSON the hook writes) followed by datasets/semicoco.py:220-269 (filter_pseudo_labels).
+    thr_by_class: sequence of per-class thresholds (fp64)."""
+    rects, scores, cls = hook_saved_boxes(dets, labels, num_classes, infer_score_thr, iou)
     thr = {i: float(t) for i, t in enumerate(thr_by_class)}
     return filter_pseudo_labels(rects, scores, cls, img_w, img_h, thr, default_thres)
 

@@ -315,6 +315,30 @@ def test_hook_pseudo_label_chain_matches_reference():
     assert sum(len(g[f"c{k}_gt"]) for k in range(ncase)) > 20 and sum(len(g[f"c{k}_ignore"]) for k in range(ncase)) > 5
 
 
+def test_adathres_chain_matches_reference():
+    """Per-epoch adaptive thresholds over a whole (small) epoch: the oracle's hook_saved_boxes + adathres against the
+    reference's adathres() run twice on the JSON files its own hook wrote (adathres_chain.npz): first pass without a
+    history, second pass gated by the first pass's thresholds — thresholds and class weights to 1e-12."""
+    g = load("adathres_chain.npz")
+    ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+    by_class = {}
+    for k in range(ncase):
+        rects, scores, cls = O.hook_saved_boxes(g[f"c{k}_dets"], g[f"c{k}_labels"], C)
+        for s_, c in zip(scores, cls):
+            by_class.setdefault(c, []).append(s_)
+    prev = None
+    for tag in ("first", "second"):
+        thr, wgt = O.adathres(by_class, prev)
+        ref_t, ref_w = g[f"{tag}_thr"], g[f"{tag}_weight"]
+        present = {int(c) for c in np.nonzero(~np.isnan(ref_t))[0]}
+        assert set(thr) == present and len(present) >= 4
+        for c in present:
+            np.testing.assert_allclose(thr[c], ref_t[c], rtol=1e-12)
+            np.testing.assert_allclose(wgt[c], ref_w[c], rtol=1e-12)
+        prev = thr
+    assert not np.array_equal(g["first_thr"], g["second_thr"])
+
+
 def test_hook_pseudo_label_chain_vs_live_reference_other_seeds():
     """Where the reference tree is present: the hook -> JSON -> dataset-filter chain of the reference run live on four
     more random detection sets (24 images) against the oracle, bit-exact."""
