@@ -24,6 +24,14 @@ CASES = {
     "l3_conv3_256_1024_res": (4, 50, 84, 256, 1024, 1, 1, 0, True, False, True, True),
     "l2_conv1dgrad_128_512_res_mask": (4, 100, 168, 128, 512, 1, 1, 0, True, True, False, False),
     "tower_3x3_256": (4, 100, 168, 256, 256, 3, 1, 1, False, False, False, False),
+    # RLA_ResNet state path at C2 / C3 (engine_rla.py): conv_out 4*planes -> 64-channel state rows, the h half of conv1,
+    # recurrent_conv 3x3 on the state rows, conv1's x half with the h half as the residual operand
+    "rla_c2_conv_out_256_64": (4, 200, 336, 256, 64, 1, 1, 0, False, False, False, False),
+    "rla_c2_conv1h_64_64": (4, 200, 336, 64, 64, 1, 1, 0, False, False, False, False),
+    "rla_c2_recurrent_3x3_64": (4, 200, 336, 64, 64, 3, 1, 1, False, False, False, False),
+    "rla_c2_conv1x_256_64_res": (4, 200, 336, 256, 64, 1, 1, 0, True, False, True, True),
+    "rla_c3_conv_out_512_64": (4, 100, 168, 512, 64, 1, 1, 0, False, False, False, False),
+    "rla_c3_recurrent_3x3_64": (4, 100, 168, 64, 64, 3, 1, 1, False, False, False, False),
 }
 
 
