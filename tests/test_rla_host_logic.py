@@ -188,3 +188,38 @@ def test_full_detector_plan_on_the_emulator(backbone):
             bad.append((name, round(c, 4)))
     assert not bad, (len(bad), bad[:10])
     assert len(grads) > 90
+
+
+def test_scale_invariant_odd_batch_plan_on_the_emulator():
+    """Odd batch (labeled + unlabeled + the half-resolution SI copy, fcos_head.py:227-233, 312-333) through the whole plan
+    on the emulator: n_labeled = (B - 1) // 2, the SI-soft loss with its warm-up weight, and its gradient reaching the
+    classification branch — against the oracle on the same weights."""
+    from dsl_b200.engine import FCOSNet
+    from dsl_b200.params import ParamStore, fpn_spec, head_spec, resnet_spec
+    B, H, W = 3, 96, 128
+    sd0 = _detector_state("resnet", 81)
+    x = GI.make_tensor(np.random.RandomState(82), B, 3, H, W)
+    gts, labels, ignores = GI.make_gt(83, B, H, W, max_gt=5, max_ignore=2, with_ignore=True)
+    with emu_lib.installed():
+        store = ParamStore(resnet_spec(50) + fpn_spec() + head_spec(80), "cpu")
+        store.load_state_dict(sd0)
+        net = FCOSNet(B, H, W, depth=50, train=True, store=store, device="cpu", loss_weight=3.0, soft_weight=1.0)
+        assert net.n_labeled == 1
+        net.si_weight = 1.0 / 1000.0
+        net.img.copy_(x)
+        net.forward()
+        net.set_targets(gts, labels, ignores)
+        net.run_targets()
+        net.run_loss()
+        net.backward()
+        got = {k: float(v) for k, v in net.losses().items()}
+        g_cls = net.grad_view("bbox_head.conv_cls.weight").clone().view(80, 256, 3, 3)
+    sd = {k: v.clone().requires_grad_(k == "bbox_head.conv_cls.weight") for k, v in sd0.items()}
+    rp = O.fpn_forward(sd, O.resnet_forward(sd, x, 50, prefix="backbone."), prefix="neck.")
+    rc, rb, rt = O.fcos_head_forward(sd, rp, training=True, prefix="bbox_head.")
+    ref = O.fcos_loss(rc, rb, rt, gts, labels, ignores, loss_weight=3.0, soft_weight=1.0, soft_warm_up=5000, cur_iter=0)
+    assert set(got) == set(ref) == {"loss_cls", "loss_bbox", "loss_centerness", "loss_sisoft"}
+    for k, v in ref.items():
+        assert abs(got[k] - float(v.detach())) <= 3e-2 * abs(float(v.detach())) + 1e-7, (k, got[k], float(v.detach()))
+    sum(ref.values()).backward()
+    assert _cos(g_cls, sd["bbox_head.conv_cls.weight"].grad) > 0.98
