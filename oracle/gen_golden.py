@@ -9,6 +9,7 @@ Files written (all small; inputs are regenerated from seeds, only reference OUTP
   rla_backbone.npz  RLA_ResNet (the shipped configs' backbone) forward + sampled parameter gradients, 1x3x64x96
   rla_detector.npz  build_detector(shipped RLA model dict).forward_train: losses + sampled parameter gradients
   decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
+  view_image.npz  pixel side of the view pipelines (Resize / PatchShuffle / RandomFlip / Normalize / Pad) on small images
   misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
 """
 import json
@@ -504,6 +505,130 @@ def _load_pipeline_classes():
     return glb["Resize"], glb["RandomFlip"], glb["PatchShuffle"]
 
 
+def _mmcv_image_stub():
+    """The mmcv image functions the pipeline classes call, restated from their published definitions (mmcv 1.3.x,
+    mmcv/image/geometric.py and photometric.py — mmcv itself is not installable here): thin cv2 / numpy wrappers."""
+    import types
+    import cv2
+
+    def rescale_size(old_size, scale, return_scale=False):
+        w, h = old_size
+        if isinstance(scale, (float, int)):
+            f = scale
+        else:
+            f = min(max(scale) / max(h, w), min(scale) / min(h, w))
+        new = (int(w * float(f) + 0.5), int(h * float(f) + 0.5))
+        return (new, f) if return_scale else new
+
+    def imresize(img, size, return_scale=False, interpolation="bilinear", out=None, backend=None):
+        assert interpolation == "bilinear" and backend in (None, "cv2")
+        h, w = img.shape[:2]
+        r = cv2.resize(img, size, dst=out, interpolation=cv2.INTER_LINEAR)
+        return (r, size[0] / w, size[1] / h) if return_scale else r
+
+    def imrescale(img, scale, return_scale=False, interpolation="bilinear", backend=None):
+        h, w = img.shape[:2]
+        new, f = rescale_size((w, h), scale, return_scale=True)
+        r = imresize(img, new, interpolation=interpolation, backend=backend)
+        return (r, f) if return_scale else r
+
+    def imflip(img, direction="horizontal"):
+        assert direction in ("horizontal", "vertical", "diagonal")
+        return np.flip(img, axis={"horizontal": 1, "vertical": 0, "diagonal": (0, 1)}[direction])
+
+    def imnormalize(img, mean, std, to_rgb=True):
+        img = img.copy().astype(np.float32)
+        assert img.dtype != np.uint8
+        mean = np.float64(mean.reshape(1, -1))
+        stdinv = 1 / np.float64(std.reshape(1, -1))
+        if to_rgb:
+            cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+        cv2.subtract(img, mean, img)
+        cv2.multiply(img, stdinv, img)
+        return img
+
+    def impad(img, *, shape=None, padding=None, pad_val=0, padding_mode="constant"):
+        assert shape is not None and padding is None and padding_mode == "constant"
+        return cv2.copyMakeBorder(img, 0, shape[0] - img.shape[0], 0, shape[1] - img.shape[1], cv2.BORDER_CONSTANT,
+                                  value=pad_val)
+
+    def impad_to_multiple(img, divisor, pad_val=0):
+        ph = int(np.ceil(img.shape[0] / divisor)) * divisor
+        pw = int(np.ceil(img.shape[1] / divisor)) * divisor
+        return impad(img, shape=(ph, pw), pad_val=pad_val)
+
+    return types.SimpleNamespace(
+        imcrop=lambda img, b: img[int(b[1]):int(b[3]) + 1, int(b[0]):int(b[2]) + 1].copy(),
+        is_list_of=lambda seq, t: isinstance(seq, list) and all(isinstance(x, t) for x in seq),
+        is_tuple_of=lambda seq, t: isinstance(seq, tuple) and all(isinstance(x, t) for x in seq),
+        imresize=imresize, imrescale=imrescale, imflip=imflip, imnormalize=imnormalize, impad=impad,
+        impad_to_multiple=impad_to_multiple)
+
+
+def _load_image_pipeline():
+    """Resize / PatchShuffle / RandomFlip / Normalize / Pad compiled from the reference's own transforms.py over
+    _mmcv_image_stub (registry decorator = identity)."""
+    import ast
+    import random
+    import types
+    import cv2
+    path = os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/pipelines/transforms.py")
+    tree = ast.parse(open(path).read())
+    names = ("Resize", "RandomFlip", "PatchShuffle", "Normalize", "Pad")
+    keep = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name == "get_bbox_fields") or
+            (isinstance(n, ast.ClassDef) and n.name in names)]
+    reg = types.SimpleNamespace(register_module=lambda *a, **k: (lambda c: c))
+    glb = {"np": np, "random": random, "mmcv": _mmcv_image_stub(), "cv2": cv2, "PIPELINES": reg}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), glb)
+    return {n: glb[n] for n in names}
+
+
+IMG_NORM = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)   # shipped config :66-67
+
+
+def view_image_cases(seed, ncase):
+    """uint8 BGR images through the reference's own Resize(keep_ratio) -> PatchShuffle -> RandomFlip -> Normalize ->
+    Pad(32) (the labeled / weak pipeline of the shipped config, :68-81), with the random draws pinned: the scale tuple,
+    the PatchShuffle mode / place and the flip flag are chosen per case and handed to the classes the way their own
+    random draws would set them. Returns inputs (source images, view parameters) and outputs (fp32 HWC images, metas)."""
+    import random
+    P = _load_image_pipeline()
+    rng = np.random.RandomState(seed)
+    out = {}
+    views = []
+    for k in range(ncase):
+        h, w = int(rng.randint(37, 90)), int(rng.randint(37, 120))
+        src = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        scale = [(160, 77), (133, 96), (90, 90), (200, 64)][k % 4]
+        ps_mode = [None, "flip", "flop"][k % 3]
+        place = float(rng.uniform(0.0, 1.0)) if k not in (4, 5) else (0.0 if k == 4 else 1.0)      # degenerate cuts
+        flip = bool(k % 2)
+        res = dict(img=src.copy(), img_shape=src.shape, ori_shape=src.shape, img_fields=["img"], bbox_fields=[],
+                   scale=scale, flip=flip, flip_direction="horizontal" if flip else None)
+        res = P["Resize"](img_scale=[(1333, 640), (1333, 800)], multiscale_mode="value", keep_ratio=True)(res)
+        if ps_mode is not None:
+            ps = P["PatchShuffle"](ratio=1.0, ranges=[place, place], mode=[ps_mode])
+            np.random.seed(k)
+            random.seed(k)
+            res = ps(res)
+            assert res["PS"] and res["PS_mode"] == ps_mode
+        res = P["RandomFlip"](flip_ratio=0.5)(res)
+        res = P["Normalize"](**IMG_NORM)(res)
+        res = P["Pad"](size_divisor=32)(res)
+        out[f"c{k}_src"] = src
+        out[f"c{k}_out"] = np.ascontiguousarray(res["img"], dtype=np.float32)
+        out[f"c{k}_scale_factor"] = res["scale_factor"]
+        out[f"c{k}_img_shape"] = np.array(res["img_shape"], dtype=np.int64)
+        views.append([scale[0], scale[1], {None: 0, "flip": 1, "flop": 2}[ps_mode], place, int(flip)])
+    out["views"] = np.array(views, dtype=np.float64)
+    out["meta"] = np.array([ncase], dtype=np.int64)
+    return out
+
+
+def gen_view_image(R):
+    np.savez_compressed(os.path.join(OUT, "view_image.npz"), **view_image_cases(404, 6))
+
+
 def gen_view_geometry(R):
     np.savez_compressed(os.path.join(OUT, "view_geometry.npz"), **view_cases(202, 14))
 
@@ -581,6 +706,7 @@ def main():
     gen_adathres_chain(R)
     gen_loss_modules(R)
     gen_view_geometry(R)
+    gen_view_image(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -1,0 +1,61 @@
+"""The pixel-side view oracle (oracle/image_oracle.py; SURVEY section 8(f) row 3, the next widening step) pinned on CPU:
+the uint8 bilinear resize bit-exactly against cv2.resize — the arithmetic the reference reaches through
+mmcv.imrescale(backend='cv2') — and the whole Resize -> PatchShuffle -> RandomFlip -> Normalize -> Pad chain bit-exactly
+against the reference's own pipeline classes (golden view_image.npz, plus live sweeps where the reference is present)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import image_oracle as IO
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_bilinear_u8_resize_is_bit_exact_with_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    sizes = [(rng.randint(20, 300), rng.randint(20, 300), rng.randint(20, 400), rng.randint(20, 400)) for _ in range(40)]
+    sizes += [(480, 640, 800, 1067), (427, 640, 800, 1199), (64, 64, 64, 64), (33, 57, 1, 1), (2, 2, 31, 17)]
+    for sh, sw, dh, dw in sizes:
+        img = rng.randint(0, 256, size=(sh, sw, 3)).astype(np.uint8)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(IO.imresize_bilinear_u8(img, dw, dh), ref), (sh, sw, dh, dw)
+
+
+def test_rescale_size_matches_the_coco_shapes_of_the_config():
+    # img_scale (1333, 800) / (1333, 640), keep_ratio: the usual COCO sizes
+    assert IO.rescale_size(640, 480, (1333, 800)) == (1067, 800)
+    assert IO.rescale_size(640, 427, (1333, 800)) == (1199, 800)
+    assert IO.rescale_size(500, 375, (1333, 640)) == (853, 640)
+    assert IO.rescale_size(333, 500, (1333, 800)) == (800, 1201)
+
+
+def _check_cases(g):
+    n = int(g["meta"][0])
+    seen = set()
+    for k in range(n):
+        sl, ss, mode, place, flip = g["views"][k]
+        out, meta = IO.view_image(g[f"c{k}_src"], (int(sl), int(ss)), ps_mode=int(mode), ps_place=float(place),
+                                  flip=bool(flip))
+        ref = g[f"c{k}_out"]                                      # HWC fp32, padded
+        assert out.shape == (3,) + ref.shape[:2], (k, out.shape, ref.shape)
+        assert np.array_equal(out, ref.transpose(2, 0, 1)), k     # bit-exact float32
+        assert np.array_equal(meta["scale_factor"], g[f"c{k}_scale_factor"])
+        assert tuple(g[f"c{k}_img_shape"]) == meta["img_shape"] and meta["pad_shape"][0] % 32 == 0
+        seen.add((int(mode), bool(flip)))
+    return seen
+
+
+def test_view_image_matches_reference_golden():
+    seen = _check_cases(np.load(os.path.join(G, "view_image.npz")))
+    assert {(0, False), (1, True), (2, False)} <= seen
+
+
+def test_view_image_vs_live_reference_other_seeds():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box): covered by view_image.npz")
+    from oracle.gen_golden import view_image_cases
+    for seed in range(410, 414):
+        _check_cases(view_image_cases(seed, 12))
