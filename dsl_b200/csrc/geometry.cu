@@ -5,6 +5,7 @@
 // without leaving the device. Arithmetic is fp32, left to right, no fused multiply-adds, exactly like the NumPy
 // float32 expressions of the reference.
 #include "common.h"
+#include "view_image.cuh"
 
 namespace dslb {
 
@@ -121,6 +122,54 @@ __global__ void pad_batch_kernel(const float* const* __restrict__ imgs, const in
   }
 }
 
+// Pixel side of the same pipelines (view_image.cuh): one launch turns B uint8 HWC source images into the zero-padded
+// fp32 NCHW batch the network reads. HBM-bound: 12 B written per output pixel, <= 12 source bytes gathered (adjacent
+// threads read adjacent source pixels, so the taps come from L1 / L2). A 32 x 8 thread block covers a 32 x 32 output
+// tile: a thread keeps its column tap (two double divisions) and walks four rows; a warp writes 128 contiguous bytes
+// of one channel plane.
+struct ViewImageParams {
+  float mean[3];
+  double inv_std[3];
+  int to_rgb;
+};
+
+constexpr int VI_TX = 32, VI_TY = 8, VI_ROWS = 4;
+
+__global__ void __launch_bounds__(VI_TX * VI_TY) view_images_kernel(
+    const uint8_t* const* __restrict__ srcs, const ImageViewDev* __restrict__ views, ViewImageParams prm,
+    float* __restrict__ out, int H, int W) {
+  const int b = blockIdx.z;
+  const ImageViewDev v = views[b];
+  const uint8_t* __restrict__ src = srcs[b];
+  const int x = blockIdx.x * VI_TX + threadIdx.x;
+  if (x >= W) return;
+  const size_t plane = (size_t)H * W;
+  float* ob = out + (size_t)b * 3 * plane;
+  const bool in_x = x < v.img_w;
+  LinTap tx = {0, 0, 0, 0};
+  if (in_x) {
+    int ry, rx;
+    vi_source_pos(v, 0, x, ry, rx);
+    tx = vi_linear_tap(rx, v.img_w, v.src_w, false);
+  }
+#pragma unroll
+  for (int j = 0; j < VI_ROWS; ++j) {
+    const int y = blockIdx.y * (VI_TY * VI_ROWS) + j * VI_TY + threadIdx.y;
+    if (y >= H) break;
+    float o[3] = {0.f, 0.f, 0.f};
+    if (in_x && y < v.img_h) {
+      int ry, rx;
+      vi_source_pos(v, y, x, ry, rx);
+      const LinTap ty = vi_linear_tap(ry, v.img_h, v.src_h, true);
+      vi_pixel_taps(src, v.src_w, tx, ty, prm.mean, prm.inv_std, prm.to_rgb, o);
+    }
+    const size_t at = (size_t)y * W + x;
+    ob[at] = o[0];
+    ob[plane + at] = o[1];
+    ob[2 * plane + at] = o[2];
+  }
+}
+
 }  // namespace dslb
 
 using namespace dslb;
@@ -151,6 +200,26 @@ extern "C" int dslb_pad_batch(const float* const* imgs_dev, const int32_t* hw_de
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
   pad_batch_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(imgs_dev, hw_dev, out, B, C, H, W);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" int dslb_view_images(const uint8_t* const* srcs_dev, const dslb_image_view_t* views_dev, int B,
+                                const float* mean, const float* std, int to_rgb, float* out, int H, int W, void* stream) {
+  DSLB_CHECK_ARG(srcs_dev && views_dev && mean && std && out, "dslb_view_images: null argument");
+  DSLB_CHECK_ARG(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "dslb_view_images: bad batch or output size");
+  static_assert(sizeof(dslb_image_view_t) == sizeof(ImageViewDev), "dslb_image_view_t layout");
+  ViewImageParams prm;
+  for (int c = 0; c < 3; ++c) {
+    DSLB_CHECK_ARG(std[c] != 0.f, "dslb_view_images: std must be non-zero");
+    prm.mean[c] = mean[c];
+    prm.inv_std[c] = 1.0 / (double)std[c];
+  }
+  prm.to_rgb = to_rgb ? 1 : 0;
+  const dim3 grid(cdiv(W, VI_TX), cdiv(H, VI_TY * VI_ROWS), B);
+  DSLB_CHECK_ARG(grid.y <= 65535, "dslb_view_images: output too tall");
+  view_images_kernel<<<grid, dim3(VI_TX, VI_TY), 0, (cudaStream_t)stream>>>(srcs_dev, (const ImageViewDev*)views_dev, prm,
+                                                                            out, H, W);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }

@@ -1,0 +1,134 @@
+// Per-pixel arithmetic of the PIXEL side of the reference's view pipelines: Resize(keep_ratio, cv2
+// INTER_LINEAR on uint8) -> PatchShuffle -> RandomFlip(horizontal) -> Normalize(to_rgb) -> Pad, i.e.
+// mmdet/datasets/pipelines/transforms.py:218-247 (_resize_img -> mmcv.imrescale -> cv2.resize), :2180-2199 (PatchShuffle
+// pixel moves), :374-383 (imflip), :668-683 (imnormalize), :729-741 (impad_to_multiple), evaluated backwards from one
+// OUTPUT pixel. Every operation is spelled with a fixed rounding (no fused multiply-adds, double where OpenCV uses
+// double), so the result is the same bits as the CPU pipeline's. The functions are __host__ __device__: geometry.cu
+// calls them from view_images_kernel; tests/view_image_host.cpp compiles the same header with g++ so the arithmetic is
+// pinned against the oracle on the GPU-less build box (test infrastructure: nothing in libdslb.so runs on the host).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DSLB_HD __host__ __device__ __forceinline__
+#else
+#define DSLB_HD static inline
+#endif
+
+namespace dslb {
+
+struct ImageViewDev {   // == dslb_image_view_t
+  int src_h, src_w;     // source image: uint8 HWC, 3 channels
+  int img_h, img_w;     // size after Resize (img_shape), from mmcv.rescale_size on the host
+  int ps_mode;          // PatchShuffle: 0 off, 1 'flip' (columns), 2 'flop' (rows)
+  int ps_crop;          // min(int(round(extent * PS_place)), extent); 0 or extent = no-op
+  int flip;             // RandomFlip horizontal
+  int reserved;
+};
+
+// products / sums with one rounding each, also where the compiler would otherwise contract them into an FMA
+DSLB_HD double vi_dmul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+DSLB_HD double vi_dadd(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+DSLB_HD float vi_fsub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b;
+  return r;
+#endif
+}
+
+// OpenCV's INTER_LINEAR source index and 11-bit weights of destination index d along one axis (modules/imgproc/src/
+// resize.cpp, resizeGeneric_ set-up): scale = 1 / (dn / sn) in double, f = (float)((d + 0.5) * scale - 0.5),
+// i = floor(f), weights cvRound((1 - f) * 2048), cvRound(f * 2048) (round half to even). Horizontally the weight is
+// reset where the tap leaves the image; vertically only the row indices are clamped.
+struct LinTap {
+  int i0, i1;   // clamped source indices
+  int a0, a1;   // weights, a0 + a1 == 2048 up to the two roundings
+};
+
+DSLB_HD LinTap vi_linear_tap(int d, int dn, int sn, bool vertical) {
+  const double scale = 1.0 / ((double)dn / (double)sn);
+  float f = (float)vi_dadd(vi_dmul((double)d + 0.5, scale), -0.5);
+  int i = (int)floorf(f);
+  f = vi_fsub(f, (float)i);
+  if (!vertical) {
+    if (i < 0) { f = 0.f; i = 0; }
+    if (i >= sn - 1) { f = 0.f; i = sn - 1; }
+  }
+  LinTap t;
+  t.a1 = (int)rintf(f * 2048.f);                 // exact scaling by a power of two, then round half to even
+  t.a0 = (int)rintf(vi_fsub(1.f, f) * 2048.f);
+  t.i0 = i < 0 ? 0 : (i > sn - 1 ? sn - 1 : i);
+  t.i1 = i + 1 < 0 ? 0 : (i + 1 > sn - 1 ? sn - 1 : i + 1);
+  return t;
+}
+
+// cv2.resize(INTER_LINEAR) of one uint8 sample: horizontal pass in int32 (pixel * 11-bit weight), vertical pass
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2 (VResizeLinear<uchar, int, short, FixedPtCast<..., 22>>).
+DSLB_HD int vi_bilinear_u8(int p00, int p01, int p10, int p11, const LinTap& tx, const LinTap& ty) {
+  const int s0 = p00 * tx.a0 + p01 * tx.a1;
+  const int s1 = p10 * tx.a0 + p11 * tx.a1;
+  return (((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
+}
+
+// position in the RESIZED image that output pixel (y, x) of the view shows: undo RandomFlip, then PatchShuffle
+// ('flip': shuffled[:, j] = resized[:, (j + crop) mod w]; 'flop': the same on rows).
+DSLB_HD void vi_source_pos(const ImageViewDev& v, int y, int x, int& ry, int& rx) {
+  if (v.flip) x = v.img_w - 1 - x;
+  if (v.ps_mode == 1 && v.ps_crop > 0 && v.ps_crop < v.img_w) {
+    x += v.ps_crop;
+    if (x >= v.img_w) x -= v.img_w;
+  } else if (v.ps_mode == 2 && v.ps_crop > 0 && v.ps_crop < v.img_h) {
+    y += v.ps_crop;
+    if (y >= v.img_h) y -= v.img_h;
+  }
+  ry = y;
+  rx = x;
+}
+
+// mmcv.imnormalize on one resized uint8 sample: float32 subtraction of the float32 mean, then the float32 value times
+// the DOUBLE reciprocal of the float32 std, rounded to float32 once (what cv2.subtract / cv2.multiply do with float64
+// scalar operands on a float32 image; transforms.py:665-666 stores mean / std as float32).
+DSLB_HD float vi_normalize(int pix, float mean, double inv_std) {
+  return (float)vi_dmul((double)vi_fsub((float)pix, mean), inv_std);
+}
+
+// The three channels of one output pixel from its taps. to_rgb: output channel c shows source channel 2 - c.
+DSLB_HD void vi_pixel_taps(const uint8_t* src, int src_w, const LinTap& tx, const LinTap& ty, const float* mean,
+                           const double* inv_std, int to_rgb, float* out3) {
+  const uint8_t* r0 = src + (long long)ty.i0 * src_w * 3;
+  const uint8_t* r1 = src + (long long)ty.i1 * src_w * 3;
+  for (int c = 0; c < 3; ++c) {
+    const int sc = to_rgb ? 2 - c : c;
+    const int p = vi_bilinear_u8(r0[tx.i0 * 3 + sc], r0[tx.i1 * 3 + sc], r1[tx.i0 * 3 + sc], r1[tx.i1 * 3 + sc], tx, ty);
+    out3[c] = vi_normalize(p, mean[c], inv_std[c]);
+  }
+}
+
+// Output pixel (y, x), y < img_h, x < img_w, of the view.
+DSLB_HD void vi_pixel(const uint8_t* src, const ImageViewDev& v, int y, int x, const float* mean, const double* inv_std,
+                      int to_rgb, float* out3) {
+  int ry, rx;
+  vi_source_pos(v, y, x, ry, rx);
+  const LinTap tx = vi_linear_tap(rx, v.img_w, v.src_w, false);
+  const LinTap ty = vi_linear_tap(ry, v.img_h, v.src_h, true);
+  vi_pixel_taps(src, v.src_w, tx, ty, mean, inv_std, to_rgb, out3);
+}
+
+}  // namespace dslb

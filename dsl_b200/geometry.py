@@ -1,7 +1,8 @@
 """Device-side view geometry: carries packed box lists through the box part of the reference's
-Resize -> PatchShuffle -> RandomFlip pipeline steps (mmdet/datasets/pipelines/transforms.py:249-257, 2168-2248, 397-429)
-and assembles zero-padded batches, on libdslb.so. With it the EMA teacher's boxes (original-image coordinates) reach
-the student's strong view without the host data pipeline. CUDA only."""
+Resize -> PatchShuffle -> RandomFlip pipeline steps (mmdet/datasets/pipelines/transforms.py:249-257, 2168-2248, 397-429),
+renders the pixel side of the same steps + Normalize + Pad from uint8 source images (`view_images`, bit-exact with the
+cv2 / mmcv CPU pipeline) and assembles zero-padded batches, on libdslb.so. With it the EMA teacher's boxes
+(original-image coordinates) reach the student's strong view without the host data pipeline. CUDA only."""
 import ctypes as C
 
 import torch
@@ -64,6 +65,69 @@ class ViewGeometry:
                                       self.ws_bytes, L.ptr(ob), L.ptr(ol) if ol is not None else None, L.ptr(oo),
                                       L.cur_stream()), "view_boxes")
         return ob, ol, oo
+
+
+class ImageView(C.Structure):
+    """dslb_image_view_t"""
+    _fields_ = [("src_h", C.c_int32), ("src_w", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("ps_mode", C.c_int32), ("ps_crop", C.c_int32), ("flip", C.c_int32), ("reserved", C.c_int32)]
+
+
+def rescale_size(w, h, scale):
+    """mmcv.rescale_size for an img_scale tuple (Resize keep_ratio=True, transforms.py:218-230): the largest size that
+    keeps the long edge <= max(scale) and the short edge <= min(scale), each edge rounded half up."""
+    f = min(max(scale) / max(h, w), min(scale) / min(h, w))
+    return int(w * float(f) + 0.5), int(h * float(f) + 0.5)
+
+
+def image_view(src_hw, scale, ps_mode=None, ps_place=0.0, flip=False):
+    """The draws of one pipeline pass (Resize's img_scale tuple, PatchShuffle's mode / place, RandomFlip's flag) ->
+    (ImageView, img_meta dict with the keys the reference's Collect hands on: img_shape, scale_factor, flip, PS, ...)."""
+    import numpy as np
+    h, w = int(src_hw[0]), int(src_hw[1])
+    nw, nh = rescale_size(w, h, scale)
+    mode = ps_mode if isinstance(ps_mode, int) and not isinstance(ps_mode, bool) else PS_MODES[ps_mode]
+    crop = 0
+    if mode:
+        ext = nw if mode == 1 else nh
+        crop = min(int(round(ext * float(ps_place))), ext)
+    ws, hs = nw / w, nh / h
+    meta = dict(ori_shape=(h, w, 3), img_shape=(nh, nw, 3), scale_factor=np.array([ws, hs, ws, hs], dtype=np.float32),
+                flip=bool(flip), flip_direction="horizontal" if flip else None, PS=bool(mode),
+                PS_mode={0: None, 1: "flip", 2: "flop"}[mode], PS_place=float(ps_place))
+    return ImageView(h, w, nh, nw, mode, crop, int(bool(flip)), 0), meta
+
+
+def view_images(srcs, views, mean, std, to_rgb=True, H=None, W=None, size_divisor=32, out=None):
+    """Resize -> PatchShuffle -> RandomFlip -> Normalize -> Pad -> collate of the reference's train pipelines
+    (configs/fcos_semi/*.py:70-92) for a batch: `srcs` = uint8 HWC 3-channel CUDA tensors (cv2.imread order), `views` =
+    ImageView per image -> (B, 3, H, W) fp32 CUDA batch, zero-padded (H, W = per-batch maxima rounded up to the divisor
+    unless given), one kernel launch."""
+    B = len(srcs)
+    assert B == len(views) and B >= 1
+    srcs = [s.contiguous() for s in srcs]
+    for s, v in zip(srcs, views):
+        if s.dtype != torch.uint8 or s.dim() != 3 or s.shape[2] != 3 or not s.is_cuda:
+            raise ValueError("dsl_b200.geometry.view_images: sources must be uint8 HWC 3-channel CUDA tensors")
+        if (int(s.shape[0]), int(s.shape[1])) != (v.src_h, v.src_w):
+            raise ValueError("dsl_b200.geometry.view_images: view.src_h / src_w do not match the source image")
+    up = lambda n: (n + size_divisor - 1) // size_divisor * size_divisor  # noqa: E731
+    H = up(max(v.img_h for v in views)) if H is None else H
+    W = up(max(v.img_w for v in views)) if W is None else W
+    if any(v.img_h > H or v.img_w > W for v in views):
+        raise ValueError("dsl_b200.geometry.view_images: a view is larger than the output batch")
+    dev = srcs[0].device
+    ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64, device=dev)
+    varr = (ImageView * B)(*views)
+    vdev = torch.frombuffer(bytearray(bytes(varr)), dtype=torch.uint8).to(dev)
+    if out is None:
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+    assert out.shape == (B, 3, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+    m = (C.c_float * 3)(*[float(x) for x in mean])
+    sd = (C.c_float * 3)(*[float(x) for x in std])
+    L.check(L.lib.dslb_view_images(L.ptr(ptrs), L.ptr(vdev), B, C.cast(m, C.c_void_p), C.cast(sd, C.c_void_p),
+                                   int(bool(to_rgb)), L.ptr(out), H, W, L.cur_stream()), "view_images")
+    return out
 
 
 def pad_batch(imgs, H=None, W=None, size_divisor=32):

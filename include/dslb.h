@@ -402,6 +402,25 @@ int dslb_view_boxes(const float* boxes, const int64_t* labels, const int32_t* of
 int dslb_pad_batch(const float* const* imgs_dev, const int32_t* hw_dev, float* out, int B, int C, int H, int W,
                    void* stream);
 
+/* Pixel side of the same pipelines (mmdet/datasets/pipelines/transforms.py:218-247 _resize_img -> mmcv.imrescale ->
+ * cv2.resize INTER_LINEAR on uint8; :2180-2199 PatchShuffle; :374-383 RandomFlip -> mmcv.imflip; :668-683 Normalize ->
+ * mmcv.imnormalize; :729-741 Pad -> mmcv.impad_to_multiple; formatting.py DefaultFormatBundle HWC -> CHW; collate):
+ * B uint8 HWC 3-channel device images (srcs_dev[b], src_h x src_w, channel order as cv2.imread gives it) -> out
+ * [B][3][H][W] fp32, zero outside img_h x img_w (the kernel writes every element of out; rows / columns beyond H, W
+ * are cropped). Bit-exact with the CPU pipeline: OpenCV's 11-bit fixed-point bilinear taps, float32 mean subtraction,
+ * multiplication by the double reciprocal of the float32 std rounded once. mean / std: 3 host floats, indexed by
+ * OUTPUT channel (after the BGR -> RGB swap when to_rgb). img_h / img_w come from mmcv.rescale_size on the host. */
+typedef struct dslb_image_view {
+  int32_t src_h, src_w;    /* source image                                                                        */
+  int32_t img_h, img_w;    /* size after Resize (img_shape)                                                       */
+  int32_t ps_mode;         /* PatchShuffle: 0 off, 1 'flip' (columns), 2 'flop' (rows), as dslb_view_t            */
+  int32_t ps_crop;         /* min(int(round(extent * PS_place)), extent); 0 or extent = no-op                     */
+  int32_t flip;            /* RandomFlip, direction 'horizontal'                                                  */
+  int32_t reserved;        /* 0                                                                                   */
+} dslb_image_view_t;
+int dslb_view_images(const uint8_t* const* srcs_dev, const dslb_image_view_t* views_dev, int B, const float* mean,
+                     const float* std, int to_rgb, float* out, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Standalone LOSSES-registry kernels (the training step uses the fused dslb_fcos_loss; these answer configs that build
  * the loss modules by themselves). One pass each: loss_elem (nullable) = weighted element-wise loss, *loss_sum

@@ -59,3 +59,62 @@ def test_view_image_vs_live_reference_other_seeds():
     from oracle.gen_golden import view_image_cases
     for seed in range(410, 414):
         _check_cases(view_image_cases(seed, 12))
+
+
+# ---- the kernel's per-pixel arithmetic (dsl_b200/csrc/view_image.cuh) compiled for the host ----------------------------
+
+@pytest.fixture(scope="module")
+def host_math(tmp_path_factory):
+    import ctypes
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    so = str(tmp_path_factory.mktemp("vi") / "view_image_host.so")
+    src = os.path.join(os.path.dirname(__file__), "view_image_host.cpp")
+    subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    lib.view_image_host.restype = None
+    return lib
+
+
+def _host_view_image(lib, src, scale, ps_mode, ps_place, flip, mean=(123.675, 116.28, 103.53),
+                     std=(58.395, 57.12, 57.375), to_rgb=True):
+    import ctypes
+    h, w = src.shape[:2]
+    nw, nh = IO.rescale_size(w, h, scale)
+    ext = nw if ps_mode == 1 else nh
+    crop = min(int(round(ext * ps_place)), ext) if ps_mode else 0
+    H, W = -(-nh // 32) * 32, -(-nw // 32) * 32
+    view = np.array([h, w, nh, nw, ps_mode, crop, int(flip), 0], dtype=np.int32)
+    m, s = np.asarray(mean, np.float32), np.asarray(std, np.float32)
+    out = np.full((3, H, W), np.nan, dtype=np.float32)
+    src = np.ascontiguousarray(src)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    lib.view_image_host(p(src), p(view), p(m), p(s), int(to_rgb), p(out), H, W)
+    return out
+
+
+def test_kernel_pixel_math_on_host_matches_reference_golden(host_math):
+    g = np.load(os.path.join(G, "view_image.npz"))
+    for k in range(int(g["meta"][0])):
+        sl, ss, mode, place, flip = g["views"][k]
+        out = _host_view_image(host_math, g[f"c{k}_src"], (int(sl), int(ss)), int(mode), float(place), bool(flip))
+        assert np.array_equal(out, g[f"c{k}_out"].transpose(2, 0, 1)), k
+
+
+def test_kernel_pixel_math_on_host_matches_oracle_random_views(host_math):
+    rng = np.random.RandomState(7)
+    for k in range(40):
+        h, w = int(rng.randint(8, 200)), int(rng.randint(8, 200))
+        src = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        scale = (int(rng.randint(40, 400)), int(rng.randint(20, 300)))
+        mode = int(rng.randint(0, 3))
+        place = float(rng.choice([0.0, 1.0, rng.uniform()]))
+        flip = bool(rng.randint(0, 2))
+        to_rgb = bool(k % 3)
+        mean, std = rng.uniform(90, 130, 3), rng.uniform(40, 70, 3)
+        ref, _ = IO.view_image(src, scale, mode, place, flip, mean=mean, std=std, to_rgb=to_rgb)
+        out = _host_view_image(host_math, src, scale, mode, place, flip, mean=mean, std=std, to_rgb=to_rgb)
+        assert np.array_equal(out, ref), (k, h, w, scale, mode, place, flip)

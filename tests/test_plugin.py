@@ -418,14 +418,14 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     import shutil
     import subprocess
     from dsl_b200 import _lib as L
-    from dsl_b200.geometry import View
+    from dsl_b200.geometry import ImageView, View
     cc = shutil.which("gcc") or shutil.which("cc")
     if cc is None:
         pytest.skip("no C compiler")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = {"dslb_conv_seg_t": L.ConvSeg, "dslb_wgrad_seg_t": L.WgradSeg, "dslb_gn_seg_t": L.GnSeg,
              "dslb_pack_desc_t": L.PackDesc, "dslb_unpack_desc_t": L.UnpackDesc, "dslb_fcos_level_t": L.FcosLevel,
-             "dslb_view_t": View, "dslb_bn_grad_desc_t": L.BnGradDesc}
+             "dslb_view_t": View, "dslb_bn_grad_desc_t": L.BnGradDesc, "dslb_image_view_t": ImageView}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dslb.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

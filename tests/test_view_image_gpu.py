@@ -1,0 +1,121 @@
+"""dslb_view_images (the pixel side of the view pipelines) through the C ABI: bit-exact against
+oracle/image_oracle.py and the reference golden (its own Resize / PatchShuffle / RandomFlip / Normalize / Pad classes).
+The per-pixel arithmetic of the kernel is also pinned on CPU (tests/test_image_oracle.py compiles the same header for the
+host); the host-side view construction is checked here without a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import image_oracle as IO
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+MEAN, STD = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)          # shipped config :66-67
+
+
+def test_image_view_host_side_matches_oracle_meta():
+    from dsl_b200 import geometry as GEO
+    rng = np.random.RandomState(3)
+    for k in range(50):
+        h, w = int(rng.randint(8, 700)), int(rng.randint(8, 700))
+        scale = [(1333, 800), (1333, 640), (int(rng.randint(40, 400)), int(rng.randint(20, 300)))][k % 3]
+        mode, place, flip = int(rng.randint(0, 3)), float(rng.uniform()), bool(k % 2)
+        v, meta = GEO.image_view((h, w), scale, ps_mode=mode, ps_place=place, flip=flip)
+        nw, nh = IO.rescale_size(w, h, scale)
+        assert (v.src_h, v.src_w, v.img_h, v.img_w) == (h, w, nh, nw) and meta["img_shape"] == (nh, nw, 3)
+        ext = nw if mode == 1 else nh
+        assert v.ps_crop == (min(int(round(ext * place)), ext) if mode else 0) and v.flip == int(flip)
+        assert np.array_equal(meta["scale_factor"], np.array([nw / w, nh / h, nw / w, nh / h], dtype=np.float32))
+        bv = GEO.view_from_meta(meta)                      # the box side reads the same meta
+        assert (bv.img_w, bv.img_h, bv.ps_mode, bv.ps_crop, bv.flip) == (nw, nh, v.ps_mode, v.ps_crop, v.flip)
+    assert GEO.image_view((480, 640), (1333, 800), "flop", 0.5)[0].ps_mode == 2
+
+
+def _run(srcs, draws, to_rgb=True, mean=MEAN, std=STD, **kw):
+    from dsl_b200 import geometry as GEO
+    views = [GEO.image_view(s.shape[:2], sc, ps_mode=m, ps_place=p, flip=f)[0] for s, (sc, m, p, f) in zip(srcs, draws)]
+    out = GEO.view_images([torch.from_numpy(np.ascontiguousarray(s)).cuda() for s in srcs], views, mean, std,
+                          to_rgb=to_rgb, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _oracle_batch(srcs, draws, H, W, to_rgb=True, mean=MEAN, std=STD):
+    ref = np.zeros((len(srcs), 3, H, W), dtype=np.float32)
+    for b, (s, (sc, m, p, f)) in enumerate(zip(srcs, draws)):
+        o, _ = IO.view_image(s, sc, m, p, f, mean=mean, std=std, to_rgb=to_rgb)
+        ref[b, :, :o.shape[1], :o.shape[2]] = o
+    return ref
+
+
+@pytest.mark.gpu
+def test_view_images_match_reference_golden():
+    g = np.load(os.path.join(G, "view_image.npz"))
+    n = int(g["meta"][0])
+    srcs = [g[f"c{k}_src"] for k in range(n)]
+    draws = [((int(v[0]), int(v[1])), int(v[2]), float(v[3]), bool(v[4])) for v in g["views"][:n]]
+    for k in range(n):                                    # one image per launch: the reference's own padded shape
+        out = _run(srcs[k:k + 1], draws[k:k + 1])
+        assert np.array_equal(out[0], g[f"c{k}_out"].transpose(2, 0, 1)), k
+    out = _run(srcs, draws)                               # the whole set as one ragged batch
+    H, W = out.shape[2:]
+    assert H % 32 == 0 and W % 32 == 0
+    for k in range(n):
+        r = g[f"c{k}_out"].transpose(2, 0, 1)
+        assert np.array_equal(out[k, :, :r.shape[1], :r.shape[2]], r), k
+        assert not out[k, :, r.shape[1]:].any() and not out[k, :, :, r.shape[2]:].any()
+
+
+@pytest.mark.gpu
+def test_view_images_random_views_vs_oracle():
+    rng = np.random.RandomState(11)
+    for it in range(6):
+        B = int(rng.randint(1, 6))
+        srcs = [rng.randint(0, 256, size=(int(rng.randint(8, 260)), int(rng.randint(8, 260)), 3)).astype(np.uint8)
+                for _ in range(B)]
+        draws = [((int(rng.randint(40, 400)), int(rng.randint(20, 300))), int(rng.randint(0, 3)),
+                  float(rng.choice([0.0, 1.0, rng.uniform()])), bool(rng.randint(0, 2))) for _ in range(B)]
+        to_rgb = bool(it % 2)
+        mean, std = rng.uniform(90, 130, 3), rng.uniform(40, 70, 3)
+        out = _run(srcs, draws, to_rgb=to_rgb, mean=mean, std=std)
+        assert np.array_equal(out, _oracle_batch(srcs, draws, out.shape[2], out.shape[3], to_rgb, mean, std)), it
+
+
+@pytest.mark.gpu
+def test_view_images_coco_sized_batch_and_properties():
+    """BASELINE batch shape: four COCO-sized sources -> (4, 3, 800, 1344); bit-exact vs the oracle, plus the size-
+    independent properties: flip of a flip-free view == the view mirrored inside img_w, PatchShuffle == a cyclic roll."""
+    rng = np.random.RandomState(5)
+    shapes = [(480, 640), (427, 640), (640, 480), (375, 500)]
+    srcs = [rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in shapes]
+    draws = [((1333, 800), 0, 0.0, False), ((1333, 800), 1, 0.37, True), ((1333, 640), 2, 0.81, False),
+             ((1333, 800), 0, 0.0, True)]
+    out = _run(srcs, draws, H=800, W=1344)
+    assert out.shape == (4, 3, 800, 1344)
+    assert np.array_equal(out, _oracle_batch(srcs, draws, 800, 1344))
+    plain = _run(srcs, [((sc, 0, 0.0, False)) for sc, _, _, _ in draws], H=800, W=1344)
+    from dsl_b200 import geometry as GEO
+    for b, (sc, m, p, f) in enumerate(draws):
+        v = GEO.image_view(srcs[b].shape[:2], sc, m, p, f)[0]
+        want = plain[b, :, :v.img_h, :v.img_w]
+        if v.ps_mode == 1:
+            want = np.roll(want, -v.ps_crop, axis=2)
+        elif v.ps_mode == 2:
+            want = np.roll(want, -v.ps_crop, axis=1)
+        if f:
+            want = want[:, :, ::-1]
+        assert np.array_equal(out[b, :, :v.img_h, :v.img_w], want), b
+
+
+@pytest.mark.gpu
+def test_view_images_reject_bad_arguments():
+    from dsl_b200 import geometry as GEO
+    src = torch.zeros(20, 30, 3, dtype=torch.uint8, device="cuda")
+    v = GEO.image_view((20, 30), (64, 48))[0]
+    with pytest.raises(ValueError):
+        GEO.view_images([src.float()], [v], MEAN, STD)
+    with pytest.raises(ValueError):
+        GEO.view_images([src], [v], MEAN, STD, H=8, W=8)
+    with pytest.raises(Exception):
+        GEO.view_images([src], [v], MEAN, (1.0, 0.0, 1.0))
