@@ -294,12 +294,14 @@ class DSLEngine:
 
     # ---------------------------------------------------------------------------------------- public
     def set_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
-        """Copy one batch into the engine's static input buffers (host tensors should be pinned for async H2D)."""
+        """Copy one batch into the engine's static input buffers (host tensors should be pinned for async H2D).
+        student_img None: the images are already there (set_images_from_sources)."""
         if self.scale_invariant:
             # reference: SemiEpochBasedRunner.train builds the extra image on the host (:186-204); here the batch of B
             # lands in the first B slots and the half-resolution copy of the last one is written by a kernel
             B = self.B
-            self.student.img[:B].copy_(student_img, non_blocking=True)
+            if student_img is not None:
+                self.student.img[:B].copy_(student_img, non_blocking=True)
             L.check(L.lib.dslb_si_half_image(L.ptr(self.student.img[B - 1]), L.ptr(self.student.img[B]), 3, self.H,
                                              self.W, L.cur_stream()), "si_half_image")
             gt_bboxes = list(gt_bboxes) + [gt_bboxes[-1] / 2]
@@ -314,7 +316,7 @@ class DSLEngine:
                     self.graphs = None      # the weight is a launch constant of the captured loss kernel
                 if self.soft_warm_up >= self.cur_iter:
                     self.cur_iter += 1
-        else:
+        elif student_img is not None:
             self.student.img.copy_(student_img, non_blocking=True)
         self.student.set_targets(gt_bboxes, gt_labels, gt_bboxes_ignore)
         if teacher_img is not None:
@@ -362,6 +364,21 @@ class DSLEngine:
         st.gt_off[BL + 1:].copy_(self._geo_off[1:] + nL)
         self._geo.run(self.pl_ig_boxes, None, self.pl_ig_off, out_boxes=st.ig_boxes[nI:], out_off=self._geo_off)
         st.ig_off[BL + 1:].copy_(self._geo_off[1:] + nI)
+
+    def set_images_from_sources(self, student_srcs, student_views, teacher_srcs=None, teacher_views=None,
+                                mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375), to_rgb=True):
+        """Render the step's images straight into the plans' static input buffers from uint8 HWC source images on the
+        device (cv2.imread order) and the draws of the reference's pipelines (geometry.image_view: Resize scale,
+        PatchShuffle cut, flip): Resize -> PatchShuffle -> RandomFlip -> Normalize -> Pad -> collate
+        (configs/fcos_semi/*.py:66-92, 108-121) as ONE launch per network, bit-exact with the cv2 / mmcv CPU pipeline.
+        The host sends ~1 byte per source pixel instead of 12 bytes per padded pixel. Boxes follow through set_inputs /
+        set_inputs_with_pseudo_labels (the scale-invariant extra image is built by set_inputs from slot B - 1)."""
+        from .geometry import view_images
+        assert len(student_srcs) == self.B
+        view_images(student_srcs, student_views, mean, std, to_rgb=to_rgb, H=self.H, W=self.W, out=self.student.img[:self.B])
+        if teacher_srcs is not None:
+            assert len(teacher_srcs) == self.teacher.B
+            view_images(teacher_srcs, teacher_views, mean, std, to_rgb=to_rgb, H=self.H, W=self.W, out=self.teacher.img)
 
     def prefetch_inputs(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore=None, teacher_img=None):
         """Asynchronous set_inputs(): the pinned host batch is copied H2D on a separate copy stream into staging

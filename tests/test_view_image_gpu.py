@@ -119,3 +119,31 @@ def test_view_images_reject_bad_arguments():
         GEO.view_images([src], [v], MEAN, STD, H=8, W=8)
     with pytest.raises(Exception):
         GEO.view_images([src], [v], MEAN, (1.0, 0.0, 1.0))
+
+
+@pytest.mark.gpu
+def test_engine_inputs_rendered_from_uint8_sources():
+    """DSLEngine.set_images_from_sources writes both networks' static input buffers (incl. the scale-invariant layout,
+    where the batch occupies the first B slots) with the pipeline's exact pixels, and the step runs on them."""
+    from dsl_b200 import geometry as GEO
+    from dsl_b200.trainer import DSLEngine
+    from tests.golden import inputs as GI
+    B, H, W = 2, 128, 160
+    eng = DSLEngine(B, H, W, depth=50, seed=0, use_graphs=False, scale_invariant=True, soft_weight=1.0, soft_warm_up=5000,
+                    teacher_B=1)           # the reference's literal mix, as bench.py --mix literal builds it
+    rng = np.random.RandomState(2)
+    srcs = [rng.randint(0, 256, size=(int(rng.randint(60, 140)), int(rng.randint(60, 140)), 3)).astype(np.uint8)
+            for _ in range(B + 1)]
+    draws = [((128, 128), 0, 0.0, False), ((120, 100), 1, 0.4, True), ((128, 96), 2, 0.7, False)]
+    views = [GEO.image_view(s.shape[:2], sc, m, p, f)[0] for s, (sc, m, p, f) in zip(srcs, draws)]
+    dsrcs = [torch.from_numpy(s).cuda() for s in srcs]
+    eng.set_images_from_sources(dsrcs[:B], views[:B], dsrcs[B:], views[B:])
+    gts, labels, ignores = GI.make_gt(1, B, H, W, with_ignore=True)
+    eng.set_inputs(None, gts, labels, ignores)
+    torch.cuda.synchronize()
+    ref = _oracle_batch(srcs, draws, H, W)
+    assert np.array_equal(eng.student.img[:B].cpu().numpy(), ref[:B])
+    assert np.array_equal(eng.teacher.img.cpu().numpy(), ref[B:])
+    losses = eng.step()
+    torch.cuda.synchronize()
+    assert all(np.isfinite(float(v)) for v in losses.values())
