@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Micro-benchmark of dslb_view_images (pixel side of the view pipelines) at the BASELINE batch shape: B COCO-sized uint8
+sources -> (B, 3, 800, 1344) fp32. CUDA events on the launching stream, an L2 flush between launches, achieved GB/s of
+the ALGORITHMIC bytes (12 B written per padded output pixel + the source bytes once) against MEASURED_PEAKS.json's HBM
+copy bandwidth. Also prints the pinned-host -> device cost of the two input formats (uint8 sources vs the fp32 batch).
+  python tools/view_image_micro.py [--batch 4] [--iters 50]
+  ncu --set full --clock-control none -k regex:view_images -c 1 -o gpurun_out/view_images python tools/view_image_micro.py --iters 1
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--iters", type=int, default=50)
+    args = ap.parse_args()
+    from dsl_b200 import geometry as GEO
+    H, W = 800, 1344
+    rng = np.random.RandomState(0)
+    shapes = [(480, 640), (427, 640), (640, 480), (375, 500)]
+    srcs = [rng.randint(0, 256, size=shapes[b % 4] + (3,)).astype(np.uint8) for b in range(args.batch)]
+    draws = [((1333, 800), b % 3, 0.37, bool(b % 2)) for b in range(args.batch)]
+    views = [GEO.image_view(s.shape[:2], sc, m, p, f)[0] for s, (sc, m, p, f) in zip(srcs, draws)]
+    hsrc = [torch.from_numpy(s).pin_memory() for s in srcs]
+    dsrc = [h.cuda() for h in hsrc]
+    out = torch.empty(args.batch, 3, H, W, dtype=torch.float32, device="cuda")
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    run = lambda: GEO.view_images(dsrc, views, mean, std, H=H, W=W, out=out)  # noqa: E731
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(args.iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    bytes_alg = out.numel() * 4 + sum(s.size for s in srcs)
+    peak = None
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk)).get("hbm_gbs")
+    # host -> device cost of the two input formats
+    hf = torch.empty(args.batch, 3, H, W, dtype=torch.float32).pin_memory()
+
+    def h2d(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+    t_u8 = h2d(lambda: [d.copy_(h, non_blocking=True) for d, h in zip(dsrc, hsrc)])
+    t_f32 = h2d(lambda: out.copy_(hf, non_blocking=True))
+    print(json.dumps(dict(kernel="view_images_kernel", batch=args.batch, out_shape=[args.batch, 3, H, W],
+                          us_median=round(t * 1e6, 2), us_min=round(min(ms) * 1e3, 2), algorithmic_bytes=bytes_alg,
+                          achieved_gbps=round(bytes_alg / t / 1e9, 1), peak_gbps=peak,
+                          frac=None if not peak else round(bytes_alg / t / 1e9 / peak, 4),
+                          note="median includes the C-ABI call's host work (pointer / view upload)",
+                          h2d_ms=dict(uint8_sources=round(t_u8, 3), fp32_batch=round(t_f32, 3)))))
+
+
+if __name__ == "__main__":
+    main()
