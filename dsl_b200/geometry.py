@@ -111,6 +111,8 @@ def view_images(srcs, views, mean, std, to_rgb=True, H=None, W=None, size_diviso
             raise ValueError("dsl_b200.geometry.view_images: sources must be uint8 HWC 3-channel CUDA tensors")
         if (int(s.shape[0]), int(s.shape[1])) != (v.src_h, v.src_w):
             raise ValueError("dsl_b200.geometry.view_images: view.src_h / src_w do not match the source image")
+        if min(v.src_h, v.src_w, v.img_h, v.img_w) < 1:
+            raise ValueError("dsl_b200.geometry.view_images: empty source image or view")
     up = lambda n: (n + size_divisor - 1) // size_divisor * size_divisor  # noqa: E731
     H = up(max(v.img_h for v in views)) if H is None else H
     W = up(max(v.img_w for v in views)) if W is None else W
