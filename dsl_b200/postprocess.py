@@ -127,6 +127,21 @@ class TeacherPost:
         self.adathres_reset()
         return self.thr_class, self.class_weight
 
+    def adathres_state(self):
+        """Host copy of the epoch's thresholds: (thr per class, class weight per class — 0 = class not counted, i.e.
+        absent from the reference's adathres.json). formats.adathres_to_json turns it into the reference's file."""
+        return self.thr_class.cpu().tolist(), self.class_weight.cpu().tolist()
+
+    def load_adathres(self, thr, counted):
+        """Resume from the reference's adathres.json (formats.adathres_from_json): installs the per-class thresholds and
+        makes them the history the next epoch's counting gate reads (absent classes: every box counts, as in
+        unlabel_pred_hook.py:328-337). Engines that captured a graph without a history must capture again."""
+        t = torch.as_tensor(thr, dtype=torch.float64)
+        self.thr_class.copy_(t, non_blocking=False)
+        prev = torch.where(torch.as_tensor(counted, dtype=torch.bool), t, torch.full_like(t, float("-inf")))
+        self.stat_prev.copy_(prev, non_blocking=False)
+        self.have_prev = True
+
     def results(self):
         """Host copy: [(dets (n,5) fp32, labels (n,) int64)] per image — what FCOSHead.get_bboxes returns."""
         cnt = self.det_count.cpu().tolist()

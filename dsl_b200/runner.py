@@ -219,6 +219,26 @@ class SemiEpochBasedRunner:
         from .plugin import ema_update_
         ema_update_(self.ema_model, self.model, self.ema_keep if keep_rate is None else keep_rate)
 
+    def save_adathres(self, path, cat_names):
+        """Write the epoch's per-class thresholds / class weights as the reference's adathres.json
+        (unlabel_pred_hook.py:344-367), e.g. for its SemiCOCODataset(thres=path) or to continue the run there."""
+        from . import formats
+        assert self.engine is not None, "no step has run yet"
+        torch.cuda.synchronize()
+        formats.save_adathres(path, *self.engine.post.adathres_state(), cat_names)
+
+    def load_adathres(self, path, cat_names, absent_thr=0.3):
+        """Resume from an adathres.json the reference (or save_adathres) wrote: thresholds + next epoch's counting
+        gate. The state is shared by every shape's engine; graphs captured without a history are dropped."""
+        from . import formats
+        assert self.engine is not None, "build an engine first (run one iteration or call _engine_for)"
+        thr, counted = formats.adathres_from_json(path, cat_names, absent_thr)
+        self.engine.post.load_adathres(thr, counted)
+        for eng in self._engines.values():
+            if eng.post is not self.engine.post:
+                eng.post.have_prev = True
+            eng.graphs = None
+
     def current_lr(self):
         return [self.engine.lr] if self.engine is not None else []
 

@@ -147,3 +147,44 @@ def test_engine_inputs_rendered_from_uint8_sources():
     losses = eng.step()
     torch.cuda.synchronize()
     assert all(np.isfinite(float(v)) for v in losses.values())
+
+
+@pytest.mark.gpu
+def test_adathres_state_round_trips_through_the_reference_file_format(tmp_path):
+    """(kept in this file so that it runs at the end of the GPU suite) Device statistics -> dslb_adathres_finalize ->
+    TeacherPost.adathres_state -> formats.save_adathres == the JSON the reference's adathres() writes for the same
+    scores (oracle restatement, pinned on the reference's own file in tests/test_formats.py); load_adathres installs
+    thresholds + history, with -inf for the classes the file does not list."""
+    import json
+    from dsl_b200 import formats as FM
+    from dsl_b200.postprocess import TeacherPost
+    from oracle import fcos_oracle as O
+    C = 6
+    cats = [f"cat{i}" for i in range(C)]
+    post = TeacherPost(1, [(4, 4)], (8,), C, "cuda")
+    rng = np.random.RandomState(9)
+    by_class = {c: [float(s) for s in np.round(rng.rand(int(rng.randint(1, 40))) * 0.6 + 0.3, 6)] for c in (0, 1, 3, 4)}
+    cnt, cum = np.zeros(C, np.int64), np.zeros(C, np.float64)
+    for c, ss in by_class.items():
+        cnt[c] = len(ss)
+        for s in ss:                                       # the reference's left-to-right fp64 accumulation
+            cum[c] += s
+    post.stat_cnt.copy_(torch.from_numpy(cnt))
+    post.stat_cum.copy_(torch.from_numpy(cum))
+    post.adathres_update()
+    torch.cuda.synchronize()
+    thr, wgt = post.adathres_state()
+    thres, weights = O.adathres(by_class)
+    p = str(tmp_path / "adathres.json")
+    FM.save_adathres(p, thr, wgt, cats)
+    d = json.load(open(p))
+    assert set(d["thres"]) == {cats[c] for c in by_class}
+    for c in by_class:
+        assert abs(d["thres"][cats[c]] - thres[c]) <= 1e-12 and abs(d["id"][str(c)] - weights[c]) <= 1e-12 * weights[c]
+    post2 = TeacherPost(1, [(4, 4)], (8,), C, "cuda")
+    post2.load_adathres(*FM.adathres_from_json(p, cats, absent_thr=0.3))
+    torch.cuda.synchronize()
+    assert post2.have_prev
+    prev = post2.stat_prev.cpu().numpy()
+    assert np.isneginf(prev[[2, 5]]).all() and np.array_equal(prev[[0, 1, 3, 4]], np.array(thr)[[0, 1, 3, 4]])
+    assert np.array_equal(post2.thr_class.cpu().numpy(), np.where(np.isin(np.arange(C), [2, 5]), 0.3, np.array(thr)))
