@@ -175,6 +175,7 @@ lib.dslb_nms_workspace_bytes.argtypes = [I, I]
 _proto("dslb_multiclass_nms", I, VP, VP, VP, VP, VP, I, I, I, F, I, VP, C.c_size_t, VP, VP, VP, VP)
 _proto("dslb_pseudo_labels", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP)
 _proto("dslb_pseudo_labels_stats", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP, VP, VP, VP)
+_proto("dslb_pseudo_labels_saved", I, VP, VP, VP, VP, VP, I, I, I, D, F, D, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP)
 _proto("dslb_sigmoid_focal_loss", I, VP, VP, VP, LL, I, F, F, VP, VP, VP, VP)
 _proto("dslb_giou_loss", I, VP, VP, VP, LL, F, VP, VP, VP, VP)
 _proto("dslb_bce_with_logits", I, VP, VP, VP, LL, VP, VP, VP, VP)

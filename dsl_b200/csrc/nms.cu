@@ -174,6 +174,11 @@ struct PseudoParams {
   long long* stat_cnt;      // [C] or null
   double* stat_cum;         // [C]
   const double* stat_prev;  // [C] last epoch's thresholds (-inf = class absent from the history) or null = first pass
+  // optional export of what the hook writes to the image's JSON file (alive after its NMS, before the dataset rule)
+  float* sv_boxes;          // [B][max_det][4] or null
+  float* sv_scores;         // [B][max_det]
+  int* sv_labels;           // [B][max_det]
+  int* sv_count;            // [B]
 };
 
 __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant__ PseudoParams P) {
@@ -245,11 +250,18 @@ __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant
     // -- dataset rule (semicoco.py:220-269), in output order; thread 0 walks the (<= 128) survivors
     if (t == 0) {
       const float W = P.img_wh[n_img * 2], H = P.img_wh[n_img * 2 + 1];
-      int g = gt_base, q = ig_base;
+      int g = gt_base, q = ig_base, sv = 0;
       for (int r = 0; r < m; ++r) {
         const int i = rank_of[r];
         if (!alive[i]) continue;
         const float4 bb = sbox[i];
+        if (P.sv_boxes) {
+          const long long at = (long long)n_img * P.max_det + sv;
+          reinterpret_cast<float4*>(P.sv_boxes)[at] = bb;
+          P.sv_scores[at] = (float)sscore[i];
+          P.sv_labels[at] = slabel[i];
+          ++sv;
+        }
         if (P.stat_cnt) {
           // adathres() reads the hook's JSON, i.e. every box alive here (before the dataset's geometry filter): counted
           // when score >= 0.3 (no history file yet) or >= last epoch's threshold of its class
@@ -281,6 +293,7 @@ __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant
       ig_base = min(q, P.max_boxes);
       P.gt_off[n_img + 1] = gt_base;
       P.ig_off[n_img + 1] = ig_base;
+      if (P.sv_boxes) P.sv_count[n_img] = sv;
     }
     __syncthreads();
   }
@@ -357,12 +370,12 @@ extern "C" int dslb_multiclass_nms(const float* boxes, const float* scores, cons
   return DSLB_OK;
 }
 
-extern "C" int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_labels, const int32_t* det_count,
-                                        const double* thr_class, const float* img_wh, int B, int max_det,
-                                        int num_classes, double infer_score_thr, float nms_iou, double ignore_lo,
-                                        int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
-                                        float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt, double* stat_cum,
-                                        const double* stat_prev, void* stream) {
+static int pseudo_labels_launch(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                                const double* thr_class, const float* img_wh, int B, int max_det, int num_classes,
+                                double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
+                                int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt,
+                                double* stat_cum, const double* stat_prev, float* sv_boxes, float* sv_scores,
+                                int32_t* sv_labels, int32_t* sv_count, void* stream) {
   DSLB_CHECK_ARG(dets && det_labels && det_count && thr_class && img_wh && gt_boxes && gt_labels && gt_off && ig_boxes &&
                      ig_off,
                  "dslb_pseudo_labels: null argument");
@@ -374,9 +387,33 @@ extern "C" int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_la
   P.B = B; P.max_det = max_det; P.C = num_classes; P.max_boxes = max_boxes;
   P.infer_score_thr = infer_score_thr; P.nms_iou = nms_iou; P.ignore_lo = ignore_lo;
   P.stat_cnt = (long long*)stat_cnt; P.stat_cum = stat_cum; P.stat_prev = stat_prev;
+  P.sv_boxes = sv_boxes; P.sv_scores = sv_scores; P.sv_labels = sv_labels; P.sv_count = sv_count;
   pseudo_label_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(P);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
+}
+
+extern "C" int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                                        const double* thr_class, const float* img_wh, int B, int max_det,
+                                        int num_classes, double infer_score_thr, float nms_iou, double ignore_lo,
+                                        int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
+                                        float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt, double* stat_cum,
+                                        const double* stat_prev, void* stream) {
+  return pseudo_labels_launch(dets, det_labels, det_count, thr_class, img_wh, B, max_det, num_classes, infer_score_thr,
+                              nms_iou, ignore_lo, max_boxes, gt_boxes, gt_labels, gt_off, ig_boxes, ig_off, stat_cnt,
+                              stat_cum, stat_prev, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int dslb_pseudo_labels_saved(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                                        const double* thr_class, const float* img_wh, int B, int max_det,
+                                        int num_classes, double infer_score_thr, float nms_iou, double ignore_lo,
+                                        int max_boxes, float* gt_boxes, int64_t* gt_labels, int32_t* gt_off,
+                                        float* ig_boxes, int32_t* ig_off, float* saved_boxes, float* saved_scores,
+                                        int32_t* saved_labels, int32_t* saved_count, void* stream) {
+  DSLB_CHECK_ARG(saved_boxes && saved_scores && saved_labels && saved_count, "dslb_pseudo_labels_saved: null argument");
+  return pseudo_labels_launch(dets, det_labels, det_count, thr_class, img_wh, B, max_det, num_classes, infer_score_thr,
+                              nms_iou, ignore_lo, max_boxes, gt_boxes, gt_labels, gt_off, ig_boxes, ig_off, nullptr,
+                              nullptr, nullptr, saved_boxes, saved_scores, saved_labels, saved_count, stream);
 }
 
 extern "C" int dslb_pseudo_labels(const float* dets, const int32_t* det_labels, const int32_t* det_count,

@@ -105,6 +105,31 @@ class TeacherPost:
             L.ptr(self.stat_cnt) if accumulate_stats else None, L.ptr(self.stat_cum) if accumulate_stats else None,
             L.ptr(self.stat_prev) if (accumulate_stats and self.have_prev) else None, L.cur_stream()), "pseudo_labels")
 
+    def saved_records(self, image_names, cat_names, infer_score_thr=0.1, hook_iou=0.6, ignore_lo=0.1):
+        """What UnlabelPredHook.save_results2file would write for the current detections, one dict per image in the
+        reference's per-image JSON layout (formats.pseudo_label_record; unlabel_pred_hook.py:142-175) — for handing the
+        teacher's pseudo labels to the reference's SemiCOCODataset. Runs the rule chain once more with the saved-list
+        export on (scratch GT / ignore outputs, no statistics) and copies the lists to the host (synchronises)."""
+        from . import formats
+        assert len(image_names) == self.B
+        if getattr(self, "_sv", None) is None:
+            z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=self.dev)  # noqa: E731
+            self._sv = dict(boxes=z(self.B, self.max_per_img, 4), scores=z(self.B, self.max_per_img),
+                            labels=z(self.B, self.max_per_img, dtype=torch.int32), count=z(self.B, dtype=torch.int32),
+                            gt=z(self.max_boxes, 4), gl=z(self.max_boxes, dtype=torch.int64),
+                            go=z(self.B + 1, dtype=torch.int32), ig=z(self.max_boxes, 4),
+                            io=z(self.B + 1, dtype=torch.int32))
+        v = self._sv
+        L.check(L.lib.dslb_pseudo_labels_saved(
+            L.ptr(self.dets), L.ptr(self.det_labels), L.ptr(self.det_count), L.ptr(self.thr_class), L.ptr(self.img_wh),
+            self.B, self.max_per_img, self.C, float(infer_score_thr), float(hook_iou), float(ignore_lo), self.max_boxes,
+            L.ptr(v["gt"]), L.ptr(v["gl"]), L.ptr(v["go"]), L.ptr(v["ig"]), L.ptr(v["io"]), L.ptr(v["boxes"]),
+            L.ptr(v["scores"]), L.ptr(v["labels"]), L.ptr(v["count"]), L.cur_stream()), "pseudo_labels_saved")
+        cnt = v["count"].cpu().tolist()
+        boxes, scores, labels = v["boxes"].cpu(), v["scores"].cpu(), v["labels"].cpu()
+        return [formats.pseudo_label_record(image_names[b], boxes[b, :cnt[b]].tolist(), scores[b, :cnt[b]].tolist(),
+                                            labels[b, :cnt[b]].tolist(), cat_names) for b in range(self.B)]
+
     def adathres_reset(self, forget_history=False):
         self.stat_cnt.zero_()
         self.stat_cum.zero_()

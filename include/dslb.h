@@ -371,6 +371,16 @@ int dslb_pseudo_labels_stats(const float* dets, const int32_t* det_labels, const
                              double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
                              int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, int64_t* stat_cnt,
                              double* stat_cum, const double* stat_prev, void* stream);
+/* dslb_pseudo_labels, plus the list the hook writes to the image's JSON file (save_results2file,
+ * unlabel_pred_hook.py:142-175: alive after the per-class NMS, BEFORE the dataset's geometry filter and threshold rule),
+ * in file order (class ascending, score descending): saved_boxes [B][max_det][4] (integer-valued), saved_scores
+ * [B][max_det] (the fp32 value the JSON carries), saved_labels [B][max_det], saved_count [B]. For hand-over to the
+ * reference's SemiCOCODataset through dsl_b200/formats.py. No statistics are accumulated by this call. */
+int dslb_pseudo_labels_saved(const float* dets, const int32_t* det_labels, const int32_t* det_count,
+                             const double* thr_class, const float* img_wh, int B, int max_det, int num_classes,
+                             double infer_score_thr, float nms_iou, double ignore_lo, int max_boxes, float* gt_boxes,
+                             int64_t* gt_labels, int32_t* gt_off, float* ig_boxes, int32_t* ig_off, float* saved_boxes,
+                             float* saved_scores, int32_t* saved_labels, int32_t* saved_count, void* stream);
 /* adathres() tail (unlabel_pred_hook.py:344-361) in fp64: mean = sum(cnt) / #{c: cnt_c > 0};
  * thr_out[c] = clip((cum_c / mean)^gamma1 * base, lo, hi); weight_out[c] = (mean / cum_c)^gamma2 (the reference writes
  * the weights but never reads them). Classes never counted: thr_out = absent_thr (SemiCOCODataset's default),

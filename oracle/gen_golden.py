@@ -10,6 +10,7 @@ Files written (all small; inputs are regenerated from seeds, only reference OUTP
   rla_detector.npz  build_detector(shipped RLA model dict).forward_train: losses + sampled parameter gradients
   decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
   view_image.npz  pixel side of the view pipelines (Resize / PatchShuffle / RandomFlip / Normalize / Pad) on small images
+  saved_files.npz  the per-image JSON files save_results2file wrote for the hook_chain.npz detections, verbatim
   misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
 """
 import json
@@ -331,7 +332,7 @@ def gen_hook_chain(R):
     np.savez_compressed(os.path.join(OUT, "hook_chain.npz"), **hook_chain_cases(R, 77, 6))
 
 
-def hook_chain_cases(R, seed, ncase):
+def hook_chain_cases(R, seed, ncase, keep_json=False):
     """Detections (multiclass_nms output order) -> bbox2result -> UnlabelPredHook.save_results2file (JSON on disk) ->
     SemiCOCODataset._parse_ann_info: the reference's whole pseudo-label rule chain, executed from its own source.
     Returns the dict the golden file stores (seed 77, 6 cases); the tests also run other seeds live."""
@@ -377,6 +378,9 @@ def hook_chain_cases(R, seed, ncase):
             slf = types.SimpleNamespace(ann_path=os.path.join(save, "sub"), thres=thr_file, default_thres=[0.1, 0.3],
                                         thres_list_by_class={}, labelmapper=dict(cat2id=cat2id))
             ann = parse_ann(slf, dict(filename="a.jpg", width=Wi, height=Hi), None)
+            if keep_json:   # the per-image file exactly as the reference's hook wrote it
+                out[f"c{k}_saved_json"] = np.frombuffer(open(os.path.join(save, "sub", "a.jpg.json"), "rb").read(),
+                                                        dtype=np.uint8)
         out[f"c{k}_dets"] = dets.numpy()
         out[f"c{k}_labels"] = labels
         out[f"c{k}_gt"] = ann["bboxes"]
@@ -385,6 +389,15 @@ def hook_chain_cases(R, seed, ncase):
     out["thr"] = np.array([0.33, 0.31, 0.35, 0.3, 0.3, 0.3], dtype=np.float64)  # missing classes -> default 0.3
     out["meta"] = np.array([ncase, C, Wi, Hi], dtype=np.int64)
     return out
+
+
+def gen_saved_files(R):
+    """The per-image JSON files UnlabelPredHook.save_results2file wrote for the hook_chain.npz detections (same seed),
+    kept verbatim: pins dsl_b200/formats.py's writer and the device-side export of the saved list."""
+    full = hook_chain_cases(R, 77, 6, keep_json=True)
+    keep = {k: v for k, v in full.items()
+            if (k.endswith(("_saved_json", "_dets", "_labels")) and not k.endswith("_gt_labels")) or k == "meta"}
+    np.savez_compressed(os.path.join(OUT, "saved_files.npz"), **keep)
 
 
 def gen_adathres_chain(R):
@@ -707,6 +720,7 @@ def main():
     gen_loss_modules(R)
     gen_view_geometry(R)
     gen_view_image(R)
+    gen_saved_files(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -130,3 +130,22 @@ def test_reference_consumes_the_files_written_here(tmp_path):
         assert np.array_equal(ann["bboxes"], np.asarray(gt, np.float32).reshape(-1, 4)), k
         assert np.array_equal(ann["labels"], np.asarray(lab, np.int64)), k
         assert np.array_equal(ann["bboxes_ignore"], np.asarray(ig, np.float32).reshape(-1, 4)), k
+
+
+def test_pseudo_label_files_match_the_files_the_reference_hook_wrote():
+    """Golden saved_files.npz = the per-image JSON files UnlabelPredHook.save_results2file wrote (verbatim) for the
+    hook_chain.npz detections: the oracle's hook_saved_boxes + formats.pseudo_label_record reproduce them exactly
+    (same boxes, same float scores, same order, same keys), and the reader inverts the file."""
+    g = np.load(os.path.join(G, "saved_files.npz"))
+    ncase, C = int(g["meta"][0]), int(g["meta"][1])
+    total = 0
+    for k in range(ncase):
+        ref = json.loads(bytes(g[f"c{k}_saved_json"]).decode())
+        rects, scores, cls = O.hook_saved_boxes(g[f"c{k}_dets"], g[f"c{k}_labels"], C)
+        rec = FM.pseudo_label_record("sub/a.jpg", rects, scores, cls, CATS)
+        assert json.loads(json.dumps(rec)) == ref, k
+        assert list(rec) == list(ref)                               # key order of the file
+        r2, s2, c2 = FM.read_pseudo_label_record(ref, CATS)
+        assert (r2, s2, c2) == ([[float(v) for v in b] for b in rects], [float(s) for s in scores], list(cls)), k
+        total += ref["targetNum"]
+    assert total > 50

@@ -188,3 +188,33 @@ def test_adathres_state_round_trips_through_the_reference_file_format(tmp_path):
     prev = post2.stat_prev.cpu().numpy()
     assert np.isneginf(prev[[2, 5]]).all() and np.array_equal(prev[[0, 1, 3, 4]], np.array(thr)[[0, 1, 3, 4]])
     assert np.array_equal(post2.thr_class.cpu().numpy(), np.where(np.isin(np.arange(C), [2, 5]), 0.3, np.array(thr)))
+
+
+@pytest.mark.gpu
+def test_saved_records_match_the_files_the_reference_hook_wrote():
+    """dslb_pseudo_labels_saved -> TeacherPost.saved_records: the per-image JSON dicts are exactly the files the
+    reference's UnlabelPredHook.save_results2file wrote for the same detections (golden saved_files.npz, verbatim), and
+    the GT / ignore lists of the same launch still equal hook_chain.npz (the export does not disturb the rule chain)."""
+    import json
+    from dsl_b200.postprocess import TeacherPost
+    g = np.load(os.path.join(G, "saved_files.npz"))
+    h = np.load(os.path.join(G, "hook_chain.npz"))
+    ncase, C, Wi, Hi = (int(v) for v in g["meta"])
+    cats = [f"cat{i}" for i in range(C)]
+    post = TeacherPost(ncase, [(8, 8)], (8,), C, "cuda", max_per_img=100)
+    post.set_meta([(Hi, Wi, 3)] * ncase, None)
+    post.set_class_thresholds(h["thr"])
+    for k in range(ncase):
+        d = torch.from_numpy(g[f"c{k}_dets"]).float()
+        post.dets[k, :len(d)] = d.cuda()
+        post.det_labels[k, :len(d)] = torch.from_numpy(g[f"c{k}_labels"]).int().cuda()
+        post.det_count[k] = len(d)
+    recs = post.saved_records(["sub/a.jpg"] * ncase, cats)
+    for k in range(ncase):
+        assert json.loads(json.dumps(recs[k])) == json.loads(bytes(g[f"c{k}_saved_json"]).decode()), k
+    v = post._sv
+    go, io = v["go"].cpu().tolist(), v["io"].cpu().tolist()
+    for k in range(ncase):
+        assert np.array_equal(v["gt"][go[k]:go[k + 1]].cpu().numpy(), h[f"c{k}_gt"].reshape(-1, 4)), k
+        assert np.array_equal(v["gl"][go[k]:go[k + 1]].cpu().numpy(), h[f"c{k}_gt_labels"]), k
+        assert np.array_equal(v["ig"][io[k]:io[k + 1]].cpu().numpy(), h[f"c{k}_ignore"].reshape(-1, 4)), k
