@@ -266,7 +266,7 @@ def main():
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (conv igemm)
     pk = peaks()
-    prof = eng.profile_kernels(steps=3)
+    prof = eng.profile_kernels(steps=3, ridge=pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9))
     launches = prof["launches_per_step"]
     if rank == 0 and os.environ.get("DSLB_PLAN_TABLE"):
         with open(os.environ["DSLB_PLAN_TABLE"], "w") as f:
@@ -288,6 +288,23 @@ def main():
                                share_of_step=round(prof["conv_wgrad"]["ms"] / prof["step_ms"], 4)),
                     head_tower=prof.get("head_tower"),
                     whole_step_tflops=round(eng.flops_per_step() / (ms_per_step * 1e-3) / 1e12, 1))
+
+    try:
+        # the same launches split by what can bound them: arithmetic intensity below the ridge (tensor peak / HBM peak)
+        # => HBM roofline (algorithmic bytes / time), else tensor roofline
+        bb = prof["by_bound"]
+        t_, h_ = bb["tensor"], bb["hbm"]
+        roofline["by_bound"] = dict(
+            ridge_flop_per_byte=round(pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9), 1),
+            tensor=dict(achieved=round(t_["flops"] / max(t_["ms"], 1e-9) / 1e9, 1), peak=pk["tf_sust"], unit="TFLOP/s",
+                        frac=round(t_["flops"] / max(t_["ms"], 1e-9) / 1e9 / pk["tf_sust"], 4), launches_per_step=t_["n"],
+                        share_of_step=round(t_["ms"] / prof["step_ms"], 4)),
+            hbm=dict(achieved=round(h_["bytes"] / max(h_["ms"], 1e-9) / 1e6, 1), peak=pk["hbm"], unit="GB/s",
+                     frac=round(h_["bytes"] / max(h_["ms"], 1e-9) / 1e6 / pk["hbm"], 4), launches_per_step=h_["n"],
+                     share_of_step=round(h_["ms"] / prof["step_ms"], 4),
+                     tflops=round(h_["flops"] / max(h_["ms"], 1e-9) / 1e9, 1)))
+    except Exception as e:  # bookkeeping only: never lose the bench line over it
+        roofline["by_bound"] = dict(error=repr(e))
 
     if rank != 0:
         if world > 1:

@@ -34,6 +34,21 @@ def conv_out(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
+def seg_bytes(s):
+    """Algorithmic HBM bytes of one conv segment (dict of dslb_conv_seg_t fields): every operand and the output touched
+    exactly once — input pixels the taps reach, packed weights, output, residual and mask reads (DESIGN section 3:
+    2 * npix * (Cin + Cout * (1 + residual + mask)) for the bf16 1x1 convs)."""
+    N, H, W, Cin, Cout = (int(s[k]) for k in ("N", "H", "W", "Cin", "Cout"))
+    R, S = int(s.get("R") or 1), int(s.get("S") or 1)
+    stride, pad = int(s.get("stride") or 1), int(s.get("pad") or 0)
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    npo = N * Ho * Wo
+    npi = npo if (R == 1 and S == 1) else N * H * W          # a strided 1x1 conv reads only the pixels it keeps
+    out_elem = 4 if s.get("out_fp32") else 2
+    extra = (1 if s.get("residual") is not None else 0) + (1 if s.get("relu_mask") is not None else 0)
+    return 2 * npi * Cin + 2 * R * S * Cout * Cin + npo * Cout * (out_elem + 2 * extra)
+
+
 class ConvPlan:
     """dslb_conv_plan_* wrapper; `segs` is a list of dicts of dslb_conv_seg_t fields (tensors for pointers)."""
 
@@ -52,6 +67,10 @@ class ConvPlan:
         self._lib = L.lib   # the library that owns the plan handle
         L.check(L.lib.dslb_conv_plan_create(arr, len(segs), C.byref(self.plan)), what)
         self.flops = L.lib.dslb_conv_plan_flops(self.plan)
+        try:   # algorithmic HBM traffic of one run: roofline bookkeeping only, never a reason to fail a plan
+            self.bytes = sum(seg_bytes(s) for s in segs)
+        except (KeyError, TypeError, ValueError):
+            self.bytes = 0
 
     def run(self):
         L.check(L.lib.dslb_conv_plan_run(self.plan, L.cur_stream()), self.what)

@@ -476,10 +476,26 @@ class DSLEngine:
                 self.graphs[2].replay()
         return self.student.losses()
 
-    def profile_kernels(self, steps=3):
+    @staticmethod
+    def split_by_bound(rows, ridge):
+        """rows: (ms, flops, bytes) per implicit-GEMM launch. A launch whose arithmetic intensity (algorithmic FLOP per
+        algorithmic HBM byte) is below `ridge` (= tensor peak / HBM peak) cannot reach the tensor roofline however good
+        the kernel is: it is accounted against the HBM roofline instead. Returns per class the summed ms / flops /
+        bytes / launch count."""
+        out = dict(tensor=dict(ms=0.0, flops=0.0, bytes=0.0, n=0), hbm=dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        for ms, flops, nbytes in rows:
+            c = out["hbm" if (nbytes > 0 and flops / nbytes < ridge) else "tensor"]
+            c["ms"] += ms
+            c["flops"] += flops
+            c["bytes"] += nbytes
+            c["n"] += 1
+        return out
+
+    def profile_kernels(self, steps=3, ridge=210.0):
         """Instrumented EAGER pass over the same workload: CUDA events (on the launching stream) around every
         implicit-GEMM conv / wgrad launch. Returns summed device ms and algorithmic FLOPs per step for the two
-        tensor-core kernel families, the FCOSHead tower share, the eager step time and the C-ABI launch count."""
+        tensor-core kernel families, the FCOSHead tower share, the eager step time and the C-ABI launch count, and the
+        implicit-GEMM launches split into tensor-bound and HBM-bound ones (`by_bound`, see split_by_bound)."""
         from .engine import ConvPlan, WgradPlan
         nets = (self.teacher, self.student)
         recs = []
@@ -522,9 +538,12 @@ class DSLEngine:
         fam = dict(conv_igemm=dict(ms=0.0, flops=0.0, n=0), conv_wgrad=dict(ms=0.0, flops=0.0, n=0))
         tower = dict(ms=0.0, flops=0.0)
         per_plan = {}
+        rows = []
         for idx, (plan, e0, e1) in enumerate(recs):
             k = "conv_wgrad" if isinstance(plan, WgradPlan) else "conv_igemm"
             ms = e0.elapsed_time(e1)
+            if k == "conv_igemm":
+                rows.append((ms / steps, plan.flops / steps, float(getattr(plan, "bytes", 0)) / steps))
             key = (idx % (len(recs) // steps), plan.what, k)
             a = per_plan.setdefault(key, [0.0, plan.flops])
             a[0] += ms / steps
@@ -539,6 +558,12 @@ class DSLEngine:
         for k in fam:
             fam[k]["n"] = int(round(fam[k]["n"]))
         out.update(fam)
+        try:
+            out["by_bound"] = self.split_by_bound(rows, ridge)
+            for c in out["by_bound"].values():
+                c["n"] = int(round(c["n"] / steps))
+        except Exception:   # bookkeeping only
+            out["by_bound"] = None
         if tower["ms"] > 0:
             out["head_tower"] = dict(tflops=round(tower["flops"] / (tower["ms"] * 1e-3) / 1e12, 1),
                                      ms_per_step=round(tower["ms"], 3), flops_per_step=tower["flops"],
