@@ -98,6 +98,39 @@ def image_view(src_hw, scale, ps_mode=None, ps_place=0.0, flip=False):
     return ImageView(h, w, nh, nw, mode, crop, int(bool(flip)), 0), meta
 
 
+def draw_view(src_hw, img_scales, multiscale_mode="value", ps_ratio=None, ps_ranges=(0.2, 0.8), ps_modes=("flip", "flop"),
+              flip_ratio=None):
+    """The random draws of one pass through Resize -> PatchShuffle -> RandomFlip, consuming NumPy's and Python's global
+    generators in the reference's order and amounts (transforms.py:127-129 random_select / :145-152 random_sample,
+    :2169-2180 PatchShuffle, :443-462 RandomFlip), so that under the same seeds the device-side views are the views the
+    reference's pipeline would have produced. ps_ratio / flip_ratio None: that step is not in the pipeline (no draw).
+    Returns image_view(...)'s (ImageView, img_meta)."""
+    import random
+    import numpy as np
+    img_scales = list(img_scales)
+    if len(img_scales) == 1:
+        scale = img_scales[0]
+    elif multiscale_mode == "value":
+        scale = img_scales[np.random.randint(len(img_scales))]
+    elif multiscale_mode == "range":
+        assert len(img_scales) == 2
+        longs, shorts = [max(s) for s in img_scales], [min(s) for s in img_scales]
+        long_edge = np.random.randint(min(longs), max(longs) + 1)
+        short_edge = np.random.randint(min(shorts), max(shorts) + 1)
+        scale = (long_edge, short_edge)
+    else:
+        raise NotImplementedError(f"dsl_b200.geometry.draw_view: multiscale_mode {multiscale_mode!r}")
+    mode, place = None, 0.0
+    if ps_ratio is not None and not (np.random.rand(1) > ps_ratio):
+        seed = np.random.rand(1)[0]
+        place = seed * abs(ps_ranges[1] - ps_ranges[0]) + ps_ranges[0]
+        mode = random.choice(list(ps_modes))
+    flip = False
+    if flip_ratio is not None:
+        flip = np.random.choice(["horizontal", None], p=[flip_ratio, 1 - flip_ratio]) is not None
+    return image_view(src_hw, scale, ps_mode=mode, ps_place=float(place), flip=flip)
+
+
 def view_images(srcs, views, mean, std, to_rgb=True, H=None, W=None, size_divisor=32, out=None):
     """Resize -> PatchShuffle -> RandomFlip -> Normalize -> Pad -> collate of the reference's train pipelines
     (configs/fcos_semi/*.py:70-92) for a batch: `srcs` = uint8 HWC 3-channel CUDA tensors (cv2.imread order), `views` =

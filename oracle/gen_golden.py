@@ -10,6 +10,7 @@ Files written (all small; inputs are regenerated from seeds, only reference OUTP
   rla_detector.npz  build_detector(shipped RLA model dict).forward_train: losses + sampled parameter gradients
   decode.npz     FCOSHead.get_bboxes (teacher decode + score gate + NMS) on random head outputs
   view_image.npz  pixel side of the view pipelines (Resize / PatchShuffle / RandomFlip / Normalize / Pad) on small images
+  view_draws.npz  the random draws of the reference's Resize / PatchShuffle / RandomFlip under fixed seeds
   saved_files.npz  the per-image JSON files save_results2file wrote for the hook_chain.npz detections, verbatim
   misc.npz       parse_det_results / adathres / _parse_ann_info filter rule / EMA body
 """
@@ -642,6 +643,32 @@ def gen_view_image(R):
     np.savez_compressed(os.path.join(OUT, "view_image.npz"), **view_image_cases(404, 6))
 
 
+def view_draw_cases(seed, n):
+    """The random draws of the reference's own Resize(multi-scale, 'value') -> PatchShuffle(0.5, [0, 1]) ->
+    RandomFlip(0.5) (shipped config :70-77) over n passes with NumPy's and Python's global generators seeded once: rows of
+    (src_h, src_w, img_h, img_w, PS, PS_mode [0 none / 1 flip / 2 flop], PS_place, flip), for geometry.draw_view."""
+    import random
+    P = _load_image_pipeline()
+    rs = P["Resize"](img_scale=[(1333, 640), (1333, 800)], multiscale_mode="value", keep_ratio=True)
+    ps = P["PatchShuffle"](ratio=0.5, ranges=[0.0, 1.0], mode=["flip", "flop"])
+    fl = P["RandomFlip"](flip_ratio=0.5)
+    shapes = np.random.RandomState(seed).randint(40, 90, size=(n, 2))
+    np.random.seed(seed)
+    random.seed(seed)
+    rows = []
+    for h, w in shapes:
+        res = dict(img=np.zeros((int(h), int(w), 3), np.uint8), img_fields=["img"], bbox_fields=[])
+        res = fl(ps(rs(res)))
+        rows.append([h, w, res["img_shape"][0], res["img_shape"][1], float(res["PS"]),
+                     {None: 0, "flip": 1, "flop": 2}[res["PS_mode"]], -1.0 if res["PS_place"] is None else res["PS_place"],
+                     float(res["flip"])])
+    return np.array(rows, dtype=np.float64)
+
+
+def gen_view_draws(R):
+    np.savez_compressed(os.path.join(OUT, "view_draws.npz"), rows=view_draw_cases(505, 40), seed=np.array([505]))
+
+
 def gen_view_geometry(R):
     np.savez_compressed(os.path.join(OUT, "view_geometry.npz"), **view_cases(202, 14))
 
@@ -721,6 +748,7 @@ def main():
     gen_view_geometry(R)
     gen_view_image(R)
     gen_saved_files(R)
+    gen_view_draws(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
