@@ -125,7 +125,7 @@ __global__ void pad_batch_kernel(const float* const* __restrict__ imgs, const in
 // Pixel side of the same pipelines (view_image.cuh): one launch turns B uint8 HWC source images into the zero-padded
 // fp32 NCHW batch the network reads. HBM-bound: 12 B written per output pixel, <= 12 source bytes gathered (adjacent
 // threads read adjacent source pixels, so the taps come from L1 / L2). A 32 x 8 thread block covers a 32 x 32 output
-// tile: a thread keeps its column tap (two double divisions) and walks four rows; a warp writes 128 contiguous bytes
+// tile: a thread keeps its column tap and the row scale (the double divisions happen once per thread) and walks four rows; a warp writes 128 contiguous bytes
 // of one channel plane.
 struct ViewImageParams {
   float mean[3];
@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(VI_TX * VI_TY) view_images_kernel(
   if (in_x) {
     int ry, rx;
     vi_source_pos(v, 0, x, ry, rx);
-    tx = vi_linear_tap(rx, v.img_w, v.src_w, false);
+    tx = vi_linear_tap(rx, vi_axis_scale(v.img_w, v.src_w), v.src_w, false);
   }
+  const double scale_y = vi_axis_scale(v.img_h, v.src_h);
 #pragma unroll
   for (int j = 0; j < VI_ROWS; ++j) {
     const int y = blockIdx.y * (VI_TY * VI_ROWS) + j * VI_TY + threadIdx.y;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(VI_TX * VI_TY) view_images_kernel(
     if (in_x && y < v.img_h) {
       int ry, rx;
       vi_source_pos(v, y, x, ry, rx);
-      const LinTap ty = vi_linear_tap(ry, v.img_h, v.src_h, true);
+      const LinTap ty = vi_linear_tap(ry, scale_y, v.src_h, true);
       vi_pixel_taps(src, v.src_w, tx, ty, prm.mean, prm.inv_std, prm.to_rgb, o);
     }
     const size_t at = (size_t)y * W + x;

@@ -62,8 +62,10 @@ struct LinTap {
   int a0, a1;   // weights, a0 + a1 == 2048 up to the two roundings
 };
 
-DSLB_HD LinTap vi_linear_tap(int d, int dn, int sn, bool vertical) {
-  const double scale = 1.0 / ((double)dn / (double)sn);
+// scale of one axis as cv::resize computes it: inv_scale = (double)dsize / ssize, scale = 1. / inv_scale
+DSLB_HD double vi_axis_scale(int dn, int sn) { return 1.0 / ((double)dn / (double)sn); }
+
+DSLB_HD LinTap vi_linear_tap(int d, double scale, int sn, bool vertical) {
   float f = (float)vi_dadd(vi_dmul((double)d + 0.5, scale), -0.5);
   int i = (int)floorf(f);
   f = vi_fsub(f, (float)i);
@@ -126,8 +128,8 @@ DSLB_HD void vi_pixel(const uint8_t* src, const ImageViewDev& v, int y, int x, c
                       int to_rgb, float* out3) {
   int ry, rx;
   vi_source_pos(v, y, x, ry, rx);
-  const LinTap tx = vi_linear_tap(rx, v.img_w, v.src_w, false);
-  const LinTap ty = vi_linear_tap(ry, v.img_h, v.src_h, true);
+  const LinTap tx = vi_linear_tap(rx, vi_axis_scale(v.img_w, v.src_w), v.src_w, false);
+  const LinTap ty = vi_linear_tap(ry, vi_axis_scale(v.img_h, v.src_h), v.src_h, true);
   vi_pixel_taps(src, v.src_w, tx, ty, mean, inv_std, to_rgb, out3);
 }
 
