@@ -16,7 +16,8 @@ def test_bilinear_u8_resize_is_bit_exact_with_opencv():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.RandomState(0)
     sizes = [(rng.randint(20, 300), rng.randint(20, 300), rng.randint(20, 400), rng.randint(20, 400)) for _ in range(40)]
-    sizes += [(480, 640, 800, 1067), (427, 640, 800, 1199), (64, 64, 64, 64), (33, 57, 1, 1), (2, 2, 31, 17)]
+    sizes += [(480, 640, 800, 1067), (427, 640, 800, 1199), (64, 64, 64, 64), (33, 57, 1, 1), (2, 2, 31, 17),
+              (1, 1, 5, 5), (1, 7, 3, 40), (3, 2, 31, 17), (480, 640, 240, 320), (100, 100, 50, 200)]
     for sh, sw, dh, dw in sizes:
         img = rng.randint(0, 256, size=(sh, sw, 3)).astype(np.uint8)
         ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
@@ -118,3 +119,9 @@ def test_kernel_pixel_math_on_host_matches_oracle_random_views(host_math):
         ref, _ = IO.view_image(src, scale, mode, place, flip, mean=mean, std=std, to_rgb=to_rgb)
         out = _host_view_image(host_math, src, scale, mode, place, flip, mean=mean, std=std, to_rgb=to_rgb)
         assert np.array_equal(out, ref), (k, h, w, scale, mode, place, flip)
+    for h, w, scale in [(1, 1, (9, 5)), (1, 7, (40, 3)), (2, 3, (31, 17)), (3, 2, (17, 31)), (64, 48, (64, 48)),
+                        (480, 640, (1333, 800)), (640, 427, (1333, 640))]:     # degenerate, identity and COCO-sized
+        src = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        for mode, flip in ((0, False), (1, True), (2, True)):
+            ref, _ = IO.view_image(src, scale, mode, 0.3, flip)
+            assert np.array_equal(_host_view_image(host_math, src, scale, mode, 0.3, flip), ref), (h, w, scale, mode)
