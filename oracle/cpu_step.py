@@ -3,6 +3,7 @@
 decode gate, student forward + FCOSHead.loss + backward, clip-grad-norm 35 + momentum SGD (bias lr x2 / wd 0) and
 the EMA body of SemiEpochBasedRunner.EMA. Used by bench.py for `cpu_baseline` and `--impl reference` (kind "port":
 the reference's own Python cannot travel to the GPU box — no mmcv there — see DESIGN.md)."""
+import contextlib
 import time
 
 import numpy as np
@@ -19,7 +20,10 @@ def _split(sd):
 
 
 class CpuStep:
-    def __init__(self, B, H, W, depth=50, seed=0, threads=None, backbone="resnet"):
+    def __init__(self, B, H, W, depth=50, seed=0, threads=None, backbone="resnet", device="cpu"):
+        """device "cpu": the reference's CPU arithmetic (cpu_baseline / --impl reference). device "cuda": the SAME
+        restatement run by stock torch eager + cuDNN on the GPU (tools/eager_gpu_comparator.py; SURVEY section 8(d)'s
+        honest GPU comparator) — still only a baseline, never part of the product."""
         from dsl_b200.params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
         if threads:
             torch.set_num_threads(threads)
@@ -39,26 +43,46 @@ class CpuStep:
         self.img_t = torch.from_numpy((rng.randn(B, 3, H, W) * 50).astype(np.float32))
         from tests.golden import inputs as GI
         self.gts, self.labels, self.ignores = GI.make_gt(seed + 1, B, H, W, with_ignore=True)
+        self.device = torch.device(device)
+        self.autocast = None         # e.g. torch.bfloat16: network forwards under torch.autocast, losses / decode in fp32
+        if self.device.type != "cpu":
+            mv = lambda t: t.to(self.device)  # noqa: E731
+            self.student = {k: mv(v) for k, v in self.student.items()}
+            self.teacher = {k: mv(v) for k, v in self.teacher.items()}
+            self.mom = {k: mv(v) for k, v in self.mom.items()}
+            self.img_s, self.img_t = mv(self.img_s), mv(self.img_t)
+            self.gts, self.labels = [mv(t) for t in self.gts], [mv(t) for t in self.labels]
+            self.ignores = [mv(t) for t in self.ignores]
 
     def _backbone(self, bb, img):
         if self.backbone == "rla":
             return O.rla_resnet_forward(bb, img, self.layers)
         return O.resnet_forward(bb, img, self.depth)
 
+    def _amp(self):
+        if self.autocast is None:
+            return contextlib.nullcontext()
+        return torch.autocast(self.device.type, dtype=self.autocast)
+
     def step(self, lr=0.01):
         B = self.B
+        f32 = lambda xs: [x.float() for x in xs]  # noqa: E731  (no-op without autocast)
         with torch.no_grad():
             bb, neck, head = _split(self.teacher)
-            ps = O.fpn_forward(neck, self._backbone(bb, self.img_t))
-            cls, box, ctr = O.fcos_head_forward(head, ps, training=False)
+            with self._amp():
+                ps = O.fpn_forward(neck, self._backbone(bb, self.img_t))
+                cls, box, ctr = O.fcos_head_forward(head, ps, training=False)
+            cls, box, ctr = f32(cls), f32(box), f32(ctr)
             O.decode_candidates(cls, box, ctr, [(self.H, self.W, 3)] * B, [[1.0] * 4] * B, nms_pre=1000,
                                 score_thr=0.05, rescale=True)
         params = {n: self.student[n].detach().requires_grad_(True) for n in self.train_names}
         sd = dict(self.student)
         sd.update(params)
         bb, neck, head = _split(sd)
-        ps = O.fpn_forward(neck, self._backbone(bb, self.img_s))
-        cls, box, ctr = O.fcos_head_forward(head, ps, training=True)
+        with self._amp():
+            ps = O.fpn_forward(neck, self._backbone(bb, self.img_s))
+            cls, box, ctr = O.fcos_head_forward(head, ps, training=True)
+        cls, box, ctr = f32(cls), f32(box), f32(ctr)
         losses = O.fcos_loss(cls, box, ctr, self.gts, self.labels, self.ignores, loss_weight=3.0)
         sum(losses.values()).backward()
         with torch.no_grad():

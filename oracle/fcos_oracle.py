@@ -146,11 +146,12 @@ def fcos_head_forward(sd, feats, strides=(8, 16, 32, 64, 128), training=True, pr
 
 # ------------------------------------------------------------------------------------------------ targets
 
-def get_points(featmap_sizes, strides, dtype=torch.float32):
+def get_points(featmap_sizes, strides, dtype=torch.float32, device=None):
     """anchor_free_head.py:287-321 + fcos_head.py:550-560: (x, y) = idx * stride + stride // 2, row-major."""
     pts = []
     for (h, w), s in zip(featmap_sizes, strides):
-        ys, xs = torch.meshgrid(torch.arange(h).to(dtype), torch.arange(w).to(dtype), indexing="ij")
+        ys, xs = torch.meshgrid(torch.arange(h, device=device).to(dtype), torch.arange(w, device=device).to(dtype),
+                                indexing="ij")
         pts.append(torch.stack((xs.reshape(-1) * s, ys.reshape(-1) * s), dim=-1) + s // 2)
     return pts
 
@@ -193,7 +194,7 @@ def get_target_single(gt_bboxes, gt_labels, points, regress_ranges, strides_per_
     min_area, min_inds = areas.min(dim=1)  # first index wins on ties (fcos_head.py:699)
     labels = gt_labels[min_inds]
     labels[min_area == INF] = num_classes
-    bbox_targets = bbox_targets[torch.arange(P), min_inds]
+    bbox_targets = bbox_targets[torch.arange(P, device=min_inds.device), min_inds]
     return labels, bbox_targets
 
 
@@ -272,13 +273,13 @@ def sigmoid_focal_loss_elem(pred, labels, num_classes, gamma=2.0, alpha=0.25):
     return F.binary_cross_entropy_with_logits(pred, target, reduction="none") * fw
 
 
-def unlabeled_weights(num_per_level_img, batch, loss_weight):
+def unlabeled_weights(num_per_level_img, batch, loss_weight, device=None):
     """fcos_head.py:217-235: per level, the first half of the (image-major) points is 'labeled' (x1), the rest
     'unlabeled' (x loss_weight); with an odd batch (scale-invariant extra image) the labeled part is the first
     (B-1)/2 images."""
     out = []
     for n in num_per_level_img:  # n = B * points_of_level
-        w = torch.ones(n, dtype=torch.float32)
+        w = torch.ones(n, dtype=torch.float32, device=device)
         if batch % 2 == 0:
             w[int(n / 2):] *= loss_weight
         else:
@@ -297,17 +298,18 @@ def fcos_loss(cls_scores, bbox_preds, centernesses, gt_bboxes, gt_labels, gt_bbo
     reduce_mean values (:266,274) for multi-rank checks; default = this rank's own values (world size 1)."""
     B = cls_scores[0].size(0)
     sizes = [c.shape[-2:] for c in cls_scores]
-    points = get_points(sizes, strides)
+    dev = cls_scores[0].device
+    points = get_points(sizes, strides, device=dev)
     labels, bbox_targets = get_targets(points, gt_bboxes, gt_labels, strides, regress_ranges, num_classes,
                                        center_sampling, radius, norm_on_bbox)
     ig_labels = None
     if gt_bboxes_ignore is not None:
-        ig_lab = [torch.zeros(b.size(0), dtype=torch.int64) + num_classes - 1 for b in gt_bboxes_ignore]
+        ig_lab = [torch.zeros(b.size(0), dtype=torch.int64, device=b.device) + num_classes - 1 for b in gt_bboxes_ignore]
         ig_labels, _ = get_targets(points, gt_bboxes_ignore, ig_lab, strides, regress_ranges, num_classes,
                                    center_sampling, radius, norm_on_bbox)
     As = None
     if loss_weight != 1.0:
-        As = unlabeled_weights([l.numel() for l in ig_labels], B, loss_weight)
+        As = unlabeled_weights([l.numel() for l in ig_labels], B, loss_weight, device=dev)
 
     f_cls = torch.cat([c.permute(0, 2, 3, 1).reshape(-1, num_classes) for c in cls_scores])
     f_box = torch.cat([b.permute(0, 2, 3, 1).reshape(-1, 4) for b in bbox_preds])
@@ -401,7 +403,7 @@ def decode_candidates(cls_scores, bbox_preds, centernesses, img_shapes, scale_fa
     Returns per image (boxes (n,4), scores (n,), labels (n,), flat candidate index (n,))."""
     B = cls_scores[0].size(0)
     C = cls_scores[0].size(1)
-    points = get_points([c.shape[-2:] for c in cls_scores], strides)
+    points = get_points([c.shape[-2:] for c in cls_scores], strides, device=cls_scores[0].device)
     mb, ms, mc = [], [], []
     for cls, box, ctr, pts in zip(cls_scores, bbox_preds, centernesses, points):
         scores = cls.permute(0, 2, 3, 1).reshape(B, -1, C).sigmoid()
@@ -411,7 +413,7 @@ def decode_candidates(cls_scores, bbox_preds, centernesses, img_shapes, scale_fa
         if 0 < nms_pre < bp.shape[1]:
             mx, _ = (scores * cn[..., None]).max(-1)
             _, topk = mx.topk(nms_pre)
-            bi = torch.arange(B).view(-1, 1).expand_as(topk)
+            bi = torch.arange(B, device=topk.device).view(-1, 1).expand_as(topk)
             pp, bp, scores, cn = pp[bi, topk], bp[bi, topk], scores[bi, topk], cn[bi, topk]
         boxes = torch.stack([distance2bbox(pp[b], bp[b], max_shape=img_shapes[b]) for b in range(B)])
         mb.append(boxes)
