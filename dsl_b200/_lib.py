@@ -27,6 +27,11 @@ def _load():
 
 
 lib = _load()
+ABI_VERSION = 101      # what include/dslb.h declares; an older build lacks entry points this package binds
+lib.dslb_version.restype = C.c_int
+if lib.dslb_version() < ABI_VERSION:
+    raise DslbError(f"{LIB_PATH} is version {lib.dslb_version()}, include/dslb.h is {ABI_VERSION}: rebuild it "
+                    "(`python -c 'import __graft_entry__ as g; g.build()'`)")
 
 
 class ConvSeg(C.Structure):

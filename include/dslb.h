@@ -33,7 +33,7 @@ extern "C" {
 #define DSLB_GN_STAT_STRIDE 32
 
 const char* dslb_last_error(void);
-int dslb_version(void);
+int dslb_version(void);   /* 101 = this header (100 + dslb_view_images, dslb_pseudo_labels_saved) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (fprop, and dgrad expressed as fprop on dY with
