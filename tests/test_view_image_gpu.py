@@ -87,7 +87,7 @@ def test_view_images_coco_sized_batch_and_properties():
     """BASELINE batch shape: four COCO-sized sources -> (4, 3, 800, 1344); bit-exact vs the oracle, plus the size-
     independent properties: flip of a flip-free view == the view mirrored inside img_w, PatchShuffle == a cyclic roll."""
     rng = np.random.RandomState(5)
-    shapes = [(480, 640), (427, 640), (640, 480), (375, 500)]
+    shapes = [(480, 640), (427, 640), (480, 600), (375, 500)]      # landscape: every view fits 800 x 1344
     srcs = [rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in shapes]
     draws = [((1333, 800), 0, 0.0, False), ((1333, 800), 1, 0.37, True), ((1333, 640), 2, 0.81, False),
              ((1333, 800), 0, 0.0, True)]

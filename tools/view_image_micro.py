@@ -26,7 +26,7 @@ def main():
     from dsl_b200 import geometry as GEO
     H, W = 800, 1344
     rng = np.random.RandomState(0)
-    shapes = [(480, 640), (427, 640), (640, 480), (375, 500)]
+    shapes = [(480, 640), (427, 640), (480, 600), (375, 500)]      # landscape: every view fits 800 x 1344
     srcs = [rng.randint(0, 256, size=shapes[b % 4] + (3,)).astype(np.uint8) for b in range(args.batch)]
     draws = [((1333, 800), b % 3, 0.37, bool(b % 2)) for b in range(args.batch)]
     views = [GEO.image_view(s.shape[:2], sc, m, p, f)[0] for s, (sc, m, p, f) in zip(srcs, draws)]
