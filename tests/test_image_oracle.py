@@ -125,3 +125,37 @@ def test_kernel_pixel_math_on_host_matches_oracle_random_views(host_math):
         for mode, flip in ((0, False), (1, True), (2, True)):
             ref, _ = IO.view_image(src, scale, mode, 0.3, flip)
             assert np.array_equal(_host_view_image(host_math, src, scale, mode, 0.3, flip), ref), (h, w, scale, mode)
+
+
+def test_gpu_test_bodies_dry_run_with_host_math(host_math, monkeypatch):
+    """The bodies of the view_images GPU tests (view construction from the draws, ragged batching, padding, the roll /
+    mirror properties, comparison with the oracle and the golden) executed here with the host-compiled kernel arithmetic
+    standing in for the launch: what is left for the GPU run is the kernel's indexing, not the test logic."""
+    import ctypes
+    import torch
+    from dsl_b200 import geometry as GEO
+    from tests import test_view_image_gpu as T
+
+    def fake_view_images(srcs, views, mean, std, to_rgb=True, H=None, W=None, size_divisor=32, out=None):
+        up = lambda n: (n + size_divisor - 1) // size_divisor * size_divisor  # noqa: E731
+        H = up(max(v.img_h for v in views)) if H is None else H
+        W = up(max(v.img_w for v in views)) if W is None else W
+        assert all(v.img_h <= H and v.img_w <= W for v in views)
+        m, sd = np.asarray(mean, np.float32), np.asarray(std, np.float32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        res = np.zeros((len(srcs), 3, H, W), np.float32)
+        for b, (s, v) in enumerate(zip(srcs, views)):
+            a = np.ascontiguousarray(s.numpy())
+            assert a.dtype == np.uint8 and a.shape == (v.src_h, v.src_w, 3)
+            vv = np.array([v.src_h, v.src_w, v.img_h, v.img_w, v.ps_mode, v.ps_crop, v.flip, 0], np.int32)
+            ob = np.empty((3, H, W), np.float32)
+            host_math.view_image_host(p(a), p(vv), p(m), p(sd), int(to_rgb), p(ob), H, W)
+            res[b] = ob
+        return torch.from_numpy(res)
+
+    monkeypatch.setattr(GEO, "view_images", fake_view_images)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    T.test_view_images_match_reference_golden()
+    T.test_view_images_random_views_vs_oracle()
+    T.test_view_images_coco_sized_batch_and_properties()
