@@ -125,50 +125,12 @@ __global__ void pad_batch_kernel(const float* const* __restrict__ imgs, const in
 // Pixel side of the same pipelines (view_image.cuh): one launch turns B uint8 HWC source images into the zero-padded
 // fp32 NCHW batch the network reads. HBM-bound: 12 B written per output pixel, <= 12 source bytes gathered (adjacent
 // threads read adjacent source pixels, so the taps come from L1 / L2). A 32 x 8 thread block covers a 32 x 32 output
-// tile: a thread keeps its column tap and the row scale (the double divisions happen once per thread) and walks four rows; a warp writes 128 contiguous bytes
-// of one channel plane.
-struct ViewImageParams {
-  float mean[3];
-  double inv_std[3];
-  int to_rgb;
-};
-
-constexpr int VI_TX = 32, VI_TY = 8, VI_ROWS = 4;
-
+// tile; a warp writes 128 contiguous bytes of one channel plane. The per-thread body (vi_thread) lives in the header so
+// that the host test harness can walk the same grid.
 __global__ void __launch_bounds__(VI_TX * VI_TY) view_images_kernel(
-    const uint8_t* const* __restrict__ srcs, const ImageViewDev* __restrict__ views, ViewImageParams prm,
+    const uint8_t* const* __restrict__ srcs, const ImageViewDev* __restrict__ views, const ViewImageParams prm,
     float* __restrict__ out, int H, int W) {
-  const int b = blockIdx.z;
-  const ImageViewDev v = views[b];
-  const uint8_t* __restrict__ src = srcs[b];
-  const int x = blockIdx.x * VI_TX + threadIdx.x;
-  if (x >= W) return;
-  const size_t plane = (size_t)H * W;
-  float* ob = out + (size_t)b * 3 * plane;
-  const bool in_x = x < v.img_w;
-  LinTap tx = {0, 0, 0, 0};
-  if (in_x) {
-    int ry, rx;
-    vi_source_pos(v, 0, x, ry, rx);
-    tx = vi_linear_tap(rx, vi_axis_scale(v.img_w, v.src_w), v.src_w, false);
-  }
-  const double scale_y = vi_axis_scale(v.img_h, v.src_h);
-#pragma unroll
-  for (int j = 0; j < VI_ROWS; ++j) {
-    const int y = blockIdx.y * (VI_TY * VI_ROWS) + j * VI_TY + threadIdx.y;
-    if (y >= H) break;
-    float o[3] = {0.f, 0.f, 0.f};
-    if (in_x && y < v.img_h) {
-      int ry, rx;
-      vi_source_pos(v, y, x, ry, rx);
-      const LinTap ty = vi_linear_tap(ry, scale_y, v.src_h, true);
-      vi_pixel_taps(src, v.src_w, tx, ty, prm.mean, prm.inv_std, prm.to_rgb, o);
-    }
-    const size_t at = (size_t)y * W + x;
-    ob[at] = o[0];
-    ob[plane + at] = o[1];
-    ob[2 * plane + at] = o[2];
-  }
+  vi_thread(srcs, views, prm, out, H, W, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y);
 }
 
 }  // namespace dslb

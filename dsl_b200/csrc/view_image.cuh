@@ -133,4 +133,53 @@ DSLB_HD void vi_pixel(const uint8_t* src, const ImageViewDev& v, int y, int x, c
   vi_pixel_taps(src, v.src_w, tx, ty, mean, inv_std, to_rgb, out3);
 }
 
+// ---- one thread of view_images_kernel ------------------------------------------------------------------------------
+struct ViewImageParams {
+  float mean[3];
+  double inv_std[3];
+  int to_rgb;
+};
+
+constexpr int VI_TX = 32, VI_TY = 8, VI_ROWS = 4;   // 32 x 8 threads per 32 x 32 output tile, four rows per thread
+
+// Thread (tx, ty) of block (bx, by, bz): column x = bx * 32 + tx of image bz, rows by * 32 + j * 8 + ty. Keeps the column
+// tap and the row scale (the double divisions happen once), walks its four rows and writes the three channel planes of
+// out [B][3][H][W]; everything outside img_h x img_w is written as zero. The __global__ wrapper in geometry.cu passes
+// its blockIdx / threadIdx; tests/view_image_host.cpp walks the same grid on the host.
+DSLB_HD void vi_thread(const uint8_t* const* srcs, const ImageViewDev* views, const ViewImageParams& prm, float* out, int H,
+                       int W, int bx, int by, int bz, int tx_, int ty_) {
+  const ImageViewDev v = views[bz];
+  const uint8_t* src = srcs[bz];
+  const int x = bx * VI_TX + tx_;
+  if (x >= W) return;
+  const size_t plane = (size_t)H * W;
+  float* ob = out + (size_t)bz * 3 * plane;
+  const bool in_x = x < v.img_w;
+  LinTap tx = {0, 0, 0, 0};
+  if (in_x) {
+    int ry, rx;
+    vi_source_pos(v, 0, x, ry, rx);
+    tx = vi_linear_tap(rx, vi_axis_scale(v.img_w, v.src_w), v.src_w, false);
+  }
+  const double scale_y = vi_axis_scale(v.img_h, v.src_h);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < VI_ROWS; ++j) {
+    const int y = by * (VI_TY * VI_ROWS) + j * VI_TY + ty_;
+    if (y >= H) break;
+    float o[3] = {0.f, 0.f, 0.f};
+    if (in_x && y < v.img_h) {
+      int ry, rx;
+      vi_source_pos(v, y, x, ry, rx);
+      const LinTap ty = vi_linear_tap(ry, scale_y, v.src_h, true);
+      vi_pixel_taps(src, v.src_w, tx, ty, prm.mean, prm.inv_std, prm.to_rgb, o);
+    }
+    const size_t at = (size_t)y * W + x;
+    ob[at] = o[0];
+    ob[plane + at] = o[1];
+    ob[2 * plane + at] = o[2];
+  }
+}
+
 }  // namespace dslb

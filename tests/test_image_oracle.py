@@ -77,6 +77,7 @@ def host_math(tmp_path_factory):
     subprocess.run([cxx, "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so], check=True)
     lib = ctypes.CDLL(so)
     lib.view_image_host.restype = None
+    lib.view_images_grid_host.restype = None
     return lib
 
 
@@ -130,7 +131,8 @@ def test_kernel_pixel_math_on_host_matches_oracle_random_views(host_math):
 def test_gpu_test_bodies_dry_run_with_host_math(host_math, monkeypatch):
     """The bodies of the view_images GPU tests (view construction from the draws, ragged batching, padding, the roll /
     mirror properties, comparison with the oracle and the golden) executed here with the host-compiled kernel arithmetic
-    standing in for the launch: what is left for the GPU run is the kernel's indexing, not the test logic."""
+    standing in for the launch — the host harness walks the SAME grid through the SAME per-thread function (vi_thread)
+    the __global__ kernel calls, so block / thread indexing, tile edges and the zero padding are covered too."""
     import ctypes
     import torch
     from dsl_b200 import geometry as GEO
@@ -143,14 +145,15 @@ def test_gpu_test_bodies_dry_run_with_host_math(host_math, monkeypatch):
         assert all(v.img_h <= H and v.img_w <= W for v in views)
         m, sd = np.asarray(mean, np.float32), np.asarray(std, np.float32)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-        res = np.zeros((len(srcs), 3, H, W), np.float32)
-        for b, (s, v) in enumerate(zip(srcs, views)):
-            a = np.ascontiguousarray(s.numpy())
+        arrs = [np.ascontiguousarray(s.numpy()) for s in srcs]
+        for a, v in zip(arrs, views):
             assert a.dtype == np.uint8 and a.shape == (v.src_h, v.src_w, 3)
-            vv = np.array([v.src_h, v.src_w, v.img_h, v.img_w, v.ps_mode, v.ps_crop, v.flip, 0], np.int32)
-            ob = np.empty((3, H, W), np.float32)
-            host_math.view_image_host(p(a), p(vv), p(m), p(sd), int(to_rgb), p(ob), H, W)
-            res[b] = ob
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        vv = np.array([[v.src_h, v.src_w, v.img_h, v.img_w, v.ps_mode, v.ps_crop, v.flip, 0] for v in views], np.int32)
+        res = np.full((len(srcs), 3, H, W), np.nan, np.float32)          # NaN: every element must be written
+        # the launch exactly as dslb_view_images issues it: same grid, same per-thread function as the __global__ kernel
+        host_math.view_images_grid_host(ptrs, p(vv), len(arrs), p(m), p(sd), int(to_rgb), p(res), H, W)
+        assert not np.isnan(res).any()
         return torch.from_numpy(res)
 
     monkeypatch.setattr(GEO, "view_images", fake_view_images)
@@ -159,3 +162,15 @@ def test_gpu_test_bodies_dry_run_with_host_math(host_math, monkeypatch):
     T.test_view_images_match_reference_golden()
     T.test_view_images_random_views_vs_oracle()
     T.test_view_images_coco_sized_batch_and_properties()
+    # output sizes that are not multiples of the 32 x 32 tile: the edge guards of the grid walk
+    rng = np.random.RandomState(3)
+    srcs = [rng.randint(0, 256, size=(30, 45, 3)).astype(np.uint8), rng.randint(0, 256, size=(21, 19, 3)).astype(np.uint8)]
+    draws = [((60, 40), 1, 0.3, True), ((33, 33), 2, 0.6, False)]
+    views = [GEO.image_view(s.shape[:2], sc, m, p, f)[0] for s, (sc, m, p, f) in zip(srcs, draws)]
+    out = fake_view_images([torch.from_numpy(s) for s in srcs], views, T.MEAN, T.STD, H=50, W=70).numpy()
+    ref = np.zeros((2, 3, 50, 70), np.float32)
+    for b, (s_, (sc, m, p, f)) in enumerate(zip(srcs, draws)):
+        o, meta = IO.view_image(s_, sc, m, p, f)
+        nh, nw = meta["img_shape"][:2]
+        ref[b, :, :nh, :nw] = o[:, :nh, :nw]
+    assert np.array_equal(out, ref)
