@@ -339,7 +339,8 @@ class DSLEngine:
             self._geo = ViewGeometry(tB, max_boxes=st.max_boxes, device=self.dev)
             self._geo_off = torch.zeros(tB + 1, dtype=torch.int32, device=self.dev)
         self._geo.set_views(views)
-        st.img.copy_(student_img, non_blocking=True)
+        if student_img is not None:      # None: already rendered in place by set_images_from_sources
+            st.img.copy_(student_img, non_blocking=True)
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
         # labeled part from the host lists
