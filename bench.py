@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"],
+                    help="reference: the reference arithmetic on the host cores; eager-gpu: the same arithmetic under stock "
+                         "torch eager + cuDNN on this GPU (SURVEY 8(d)'s GPU comparator; a baseline, not the product)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU (default: the benchmark config)")
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--backbone", default="resnet", choices=["resnet", "rla"],
@@ -170,10 +172,46 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_eager_gpu(args):
+    """SURVEY section 8(d)'s honest GPU comparator: the reference's arithmetic for one teacher+student step (the oracle
+    restatement of oracle/cpu_step.py — functional torch + autograd, NCHW) executed by STOCK torch eager + cuDNN on this
+    GPU at the benchmark shape; one JSON line per precision (fp32 with cuDNN's TF32 convs, bf16 autocast). Like the
+    cpu_baseline leg this is a baseline: nothing of the product runs here. Rank 0 only."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.cpu_step import CpuStep
+    assert torch.cuda.is_available(), "--impl eager-gpu needs a CUDA device"
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    for name, amp in (("fp32 (cuDNN, TF32 convs allowed)", None), ("bf16 autocast", torch.bfloat16)):
+        cs = CpuStep(args.batch, H, W, depth=args.depth, backbone=args.backbone, device="cuda")
+        cs.autocast = amp
+        for _ in range(warm):
+            losses = cs.step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = cs.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print(json.dumps(dict(metric=METRIC, value=round(args.batch / (ms * 1e-3), 2), unit=UNIT, n_gpus=1, steps=steps,
+                              warmup=warm, ms_per_step=round(ms, 2), higher_is_better=True, impl="eager-gpu",
+                              dtype=name, data="synthetic",
+                              config=dict(workload=WORKLOAD, note="reference arithmetic (oracle restatement) under stock "
+                                          "torch eager + cuDNN; includes the host syncs of the reference's loss"),
+                              losses={k: round(v, 4) for k, v in losses.items()})), flush=True)
+        del cs
+        torch.cuda.empty_cache()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager-gpu":
+        return run_eager_gpu(args)
 
     import numpy as np
     import torch

@@ -22,7 +22,7 @@ def _split(sd):
 class CpuStep:
     def __init__(self, B, H, W, depth=50, seed=0, threads=None, backbone="resnet", device="cpu"):
         """device "cpu": the reference's CPU arithmetic (cpu_baseline / --impl reference). device "cuda": the SAME
-        restatement run by stock torch eager + cuDNN on the GPU (tools/eager_gpu_comparator.py; SURVEY section 8(d)'s
+        restatement run by stock torch eager + cuDNN on the GPU (bench.py --impl eager-gpu; SURVEY section 8(d)'s
         honest GPU comparator) — still only a baseline, never part of the product."""
         from dsl_b200.params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
         if threads:

@@ -16,7 +16,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1
 echo "gpu suite rc=$?"
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_first.json 2> gpurun_out/bench_first.err
 echo "bench rc=$?"
-python tools/eager_gpu_comparator.py > gpurun_out/eager_gpu_comparator.jsonl 2> gpurun_out/eager_gpu_comparator.err
+python bench.py --impl eager-gpu --steps 5 --warmup 2 > gpurun_out/eager_gpu_comparator.jsonl 2> gpurun_out/eager_gpu_comparator.err
 echo "eager comparator rc=$?"
 cat gpurun_out/eager_gpu_comparator.jsonl
 tail -n 3 gpurun_out/t_new.log gpurun_out/t_all.log
