@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Debug aid: per-parameter and per-FPN-level gradient errors of the CUDA backward vs torch autograd on the oracle."""
+"""TEST INFRASTRUCTURE (run by hand on a GPU box): per-parameter and per-FPN-level gradient errors of the CUDA backward vs
+torch autograd on the oracle."""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 
