@@ -52,6 +52,7 @@ def parse():
                          "SI copy of the last one (semi_epoch_based_runner.py:186-204) + 1 teacher image "
                          "(unlabel_pred_hook.py:517,543), SI-soft loss on; secondary measurement, not the BASELINE config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-view-bench", action="store_true", help="skip the side measurement of dslb_view_images")
     ap.add_argument("--cpu-sample-hw", default="800x1344", help="HxW of the bounded CPU sample")
     return ap.parse_args()
 
@@ -152,6 +153,21 @@ def cpu_baseline(sample_hw, depth, steps=1, warmup=0, batch=1, backbone="resnet"
     return dict(value=round(r["images_per_sec"], 4), unit=UNIT, cores=r["cores"], kind="port",
                 sample=f"{steps} teacher+student step(s) of B={batch} at {h}x{w}, {'RLA_' if backbone == 'rla' else ''}R{depth}, fp32 torch CPU "
                        f"({r['seconds_per_step']:.2f} s/step), warmup {warmup}")
+
+
+def view_images_side_bench(timeout=240):
+    """Side measurement reported under "view_images" (not part of the step, value or e2e): the device-side view pipeline
+    kernel dslb_view_images at the benchmark batch shape — CUDA events around the bare launch, algorithmic GB/s against the
+    measured HBM peak, the cv2 CPU pipeline timed beside it (tools/view_image_micro.py). Runs in a process of its own
+    after the step has been measured, so nothing it does can cost the bench line."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "view_image_micro.py"), "--iters", "30"],
+                           capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        if r.returncode != 0:
+            return dict(error=(r.stderr or r.stdout)[-300:])
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return dict(error=repr(e))
 
 
 def run_reference(args):
@@ -354,6 +370,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=3, warmup=1, batch=2, backbone=args.backbone)
 
+    views = None
+    if world == 1 and not args.no_view_bench:
+        views = view_images_side_bench()
+
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
@@ -368,7 +388,8 @@ def main():
                             cuda_graph=True),
                 e2e=e2e, gpu_launches=int(launches * args.steps), gpu_launches_per_step=int(launches),
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
-                losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]))
+                losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]),
+                view_images=views)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -25,7 +25,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/bench_first.json").read().strip().splitlines()[-1])
-    print({k: d[k] for k in ("value", "ms_per_step")}, d["e2e"], d["roofline"].get("by_bound"))
+    print({k: d[k] for k in ("value", "ms_per_step")}, d["e2e"], d["roofline"].get("by_bound"), d.get("view_images"))
 except Exception as e:
     print("bench line unreadable:", e)
 PY
