@@ -170,6 +170,27 @@ def view_images_side_bench(timeout=240):
         return dict(error=repr(e))
 
 
+def eager_gpu_side_bench(args, timeout=300):
+    """SURVEY 8(d)'s GPU comparator beside the headline: `bench.py --impl eager-gpu` (the reference arithmetic under stock
+    torch eager + cuDNN on this GPU, fp32 and bf16 autocast) in a process of its own after the step has been measured.
+    Reported under "gpu_eager_baseline"; a failure there only yields an `error` entry."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "eager-gpu", "--steps", "5", "--warmup",
+                            "2", "--batch", str(args.batch), "--depth", str(args.depth), "--backbone", args.backbone],
+                           capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        rows = []
+        for ln in r.stdout.strip().splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                rows.append({k: d[k] for k in ("dtype", "value", "unit", "ms_per_step", "steps", "losses") if k in d})
+        if r.returncode != 0 or not rows:
+            return dict(error=(r.stderr or r.stdout)[-300:], rows=rows)
+        return dict(impl="torch eager + cuDNN, reference arithmetic (oracle restatement), same GPU", rows=rows)
+    except Exception as e:
+        return dict(error=repr(e))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -370,9 +391,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=3, warmup=1, batch=2, backbone=args.backbone)
 
-    views = None
+    views = eager = None
     if world == 1 and not args.no_view_bench:
         views = view_images_side_bench()
+    if world == 1 and not args.no_cpu_baseline and not literal:
+        eager = eager_gpu_side_bench(args)
 
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
@@ -389,7 +412,7 @@ def main():
                 e2e=e2e, gpu_launches=int(launches * args.steps), gpu_launches_per_step=int(launches),
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
                 losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]),
-                view_images=views)
+                view_images=views, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
