@@ -86,7 +86,13 @@ def image_view(src_hw, scale, ps_mode=None, ps_place=0.0, flip=False):
     import numpy as np
     h, w = int(src_hw[0]), int(src_hw[1])
     nw, nh = rescale_size(w, h, scale)
-    mode = ps_mode if isinstance(ps_mode, int) and not isinstance(ps_mode, bool) else PS_MODES[ps_mode]
+    import numbers
+    if isinstance(ps_mode, numbers.Integral) and not isinstance(ps_mode, bool):
+        mode = int(ps_mode)
+        if mode not in (0, 1, 2):
+            raise ValueError(f"dsl_b200.geometry.image_view: ps_mode {mode} (0 off, 1 'flip', 2 'flop')")
+    else:
+        mode = PS_MODES[ps_mode]
     crop = 0
     if mode:
         ext = nw if mode == 1 else nh
