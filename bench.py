@@ -155,7 +155,7 @@ def cpu_baseline(sample_hw, depth, steps=1, warmup=0, batch=1, backbone="resnet"
                        f"({r['seconds_per_step']:.2f} s/step), warmup {warmup}")
 
 
-def view_images_side_bench(timeout=240):
+def view_images_side_bench(timeout=120):
     """Side measurement reported under "view_images" (not part of the step, value or e2e): the device-side view pipeline
     kernel dslb_view_images at the benchmark batch shape — CUDA events around the bare launch, algorithmic GB/s against the
     measured HBM peak, the cv2 CPU pipeline timed beside it (tools/view_image_micro.py). Runs in a process of its own
@@ -170,7 +170,7 @@ def view_images_side_bench(timeout=240):
         return dict(error=repr(e))
 
 
-def eager_gpu_side_bench(args, timeout=300):
+def eager_gpu_side_bench(args, timeout=180):
     """SURVEY 8(d)'s GPU comparator beside the headline: `bench.py --impl eager-gpu` (the reference arithmetic under stock
     torch eager + cuDNN on this GPU, fp32 and bf16 autocast) in a process of its own after the step has been measured.
     Reported under "gpu_eager_baseline"; a failure there only yields an `error` entry."""
