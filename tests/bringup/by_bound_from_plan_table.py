@@ -35,3 +35,16 @@ t, h = out["tensor"], out["hbm"]
 print(json.dumps(dict(ridge=round(ridge,1),
   tensor=dict(n=t["n"], ms=round(t["ms"],3), tflops=round(t["flops"]/t["ms"]/1e9,1), frac=round(t["flops"]/t["ms"]/1e9/1378.7,3)),
   hbm=dict(n=h["n"], ms=round(h["ms"],3), gbps=round(h["bytes"]/h["ms"]/1e6,1), frac=round(h["bytes"]/h["ms"]/1e6/6550.7,3), tflops=round(h["flops"]/h["ms"]/1e9,1)))))
+names = {"tensor": {}, "hbm": {}}
+for ln in open(os.path.join(ROOT, 'profiles', 'r01d_plans.txt')):
+    m = re.match(r"\s*\d+\s+(\S+)\s+(conv_igemm|conv_wgrad)\s+([\d.]+) us\s+([\d.]+) GF", ln)
+    if not m or m.group(2) != "conv_igemm":
+        continue
+    name, us, gf = m.group(1), float(m.group(3)), float(m.group(4))
+    c = "hbm" if gf * 1e9 / by_name[name] < ridge else "tensor"
+    key = re.sub(r"\.\d+\.", ".*.", name)
+    a = names[c].setdefault(key, [0, 0.0])
+    a[0] += 1
+    a[1] += us
+for c in names:
+    print(c + ":", ", ".join(f"{k} x{n} {us:.0f}us" for k, (n, us) in sorted(names[c].items(), key=lambda kv: -kv[1][1])))
