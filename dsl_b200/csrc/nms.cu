@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(128) pseudo_label_kernel(const __grid_constant
       ok = !((double)sc < P.infer_score_thr);
       b = make_float4(truncf(d[0]), truncf(d[1]), truncf(d[2]), truncf(d[3]));
       s6 = rint((double)sc * 1e6) / 1e6;
-      // per-class NMS loop of save_results2file runs over range(0, len(id2cat) - 1): the LAST class never survives
-      ok = ok && lab < P.C - 1;
+      // per-class NMS loop of save_results2file runs over range(0, len(id2cat) - 1) (unlabel_pred_hook.py:156); the
+      // reference's category file carries a trailing background entry (tools/coco_convert2_semicoco_json.py:47-48,
+      // voc_convert2_semivoc_json.py:63), so len(id2cat) - 1 == num_classes: every real class survives
+      ok = ok && lab >= 0 && lab < P.C;
       // mmcv nms(score_threshold=0.1): scores > 0.1 in fp32
       ok = ok && ((float)s6 > 0.1f);  // hard-coded score_threshold=0.1 of the hook's nms call (:163)
     }

@@ -478,8 +478,9 @@ def filter_pseudo_labels(rects, scores, cls_ids, img_w, img_h, thres_by_class=No
 def hook_saved_boxes(dets, labels, num_classes, infer_score_thr=0.1, iou=0.6):
     """What UnlabelPredHook.save_results2file writes to the image's JSON file, as (rects, scores, class ids):
     runner/hooks/unlabel_pred_hook.py:20-38 (gate score >= thr, int() truncation, round(score, 6)), :55 (stable sort by
-    score, descending), :142-165 (per class in range(0, num_classes - 1) — the last class is dropped —
-    nms(iou, score_threshold=0.1) on the truncated fp32 boxes). These are also the boxes adathres() counts (:315-343)."""
+    score, descending), :142-165 (per class in range(0, len(id2cat) - 1): the reference's category file carries a
+    trailing background entry, tools/coco_convert2_semicoco_json.py:47-48, so that is every one of the num_classes
+    real classes — nms(iou, score_threshold=0.1) on the truncated fp32 boxes). These are also the boxes adathres() counts (:315-343)."""
     dets = np.asarray(dets, dtype=np.float32).reshape(-1, 5)
     labels = np.asarray(labels).reshape(-1)
     items = []
@@ -494,7 +495,7 @@ def hook_saved_boxes(dets, labels, num_classes, infer_score_thr=0.1, iou=0.6):
         b = np.array([t[0] for t in items], dtype=np.float32)
         s = np.array([t[1] for t in items], dtype=np.float32)
         c = np.array([t[2] for t in items], dtype=np.float32)
-        for i in range(0, num_classes - 1):
+        for i in range(0, num_classes):
             sel = c == i
             if not sel.any():
                 continue

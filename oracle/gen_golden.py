@@ -265,6 +265,7 @@ def gen_misc(R):
         cats = [f"cat{i}" for i in range(6)]
         cat2id = {c: i for i, c in enumerate(cats)}
         id2cat = {str(i): c for i, c in enumerate(cats)}
+        id2cat[str(len(cats))] = "背景"   # the converter appends a background entry (tools/coco_convert2_semicoco_json.py:47-48)
         files = []
         allsc = {c: [] for c in cats}
         for i in range(12):
@@ -343,6 +344,7 @@ def hook_chain_cases(R, seed, ncase, keep_json=False):
     cats = [f"cat{i}" for i in range(C)]
     cat2id = {c: i for i, c in enumerate(cats)}
     id2cat = {str(i): c for i, c in enumerate(cats)}
+    id2cat[str(len(cats))] = "背景"   # the converter appends a background entry (tools/coco_convert2_semicoco_json.py:47-48)
     glb = {"os": os, "json": json, "np": np}
     parse_ann = _extract_method(os.path.join(ref_loader.REF_ROOT, "mmdet/datasets/semicoco.py"),
                                 "SemiCOCODataset", "_parse_ann_info", glb)
@@ -412,6 +414,7 @@ def gen_adathres_chain(R):
     cats = [f"cat{i}" for i in range(C)]
     cat2id = {c: i for i, c in enumerate(cats)}
     id2cat = {str(i): c for i, c in enumerate(cats)}
+    id2cat[str(len(cats))] = "背景"   # the converter appends a background entry (tools/coco_convert2_semicoco_json.py:47-48)
     out = {}
     rng = np.random.RandomState(91)
     Wi, Hi = 640, 480
