@@ -27,7 +27,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 101      # what include/dslb.h declares; an older build lacks entry points this package binds
+ABI_VERSION = 102      # what include/dslb.h declares; an older build lacks entry points this package binds
 lib.dslb_version.restype = C.c_int
 if lib.dslb_version() < ABI_VERSION:
     raise DslbError(f"{LIB_PATH} is version {lib.dslb_version()}, include/dslb.h is {ABI_VERSION}: rebuild it "
@@ -136,7 +136,6 @@ _proto("dslb_wgrad_plan_flops", C.c_double, C.c_void_p)
 VP, I, LL, F, D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _proto("dslb_nchw_to_nhwc_bf16", I, VP, VP, I, I, I, I, I, VP)
 _proto("dslb_nhwc_to_nchw_f32", I, VP, VP, I, I, I, I, I, I, VP)
-_proto("dslb_stem_im2col", I, VP, VP, I, I, I, VP)
 _proto("dslb_stem_conv", I, VP, VP, VP, VP, VP, VP, F, VP, VP, I, I, I, VP)
 _proto("dslb_maxpool3x3s2", I, VP, VP, I, I, I, I, VP)
 _proto("dslb_si_half_image", I, VP, VP, I, I, I, VP)
@@ -164,7 +163,6 @@ _proto("dslb_bn_grad_plan_destroy", None, VP)
 _proto("dslb_fcos_regctr_affine", I, VP, I, VP, VP, VP, VP, VP, VP, I, VP)
 _proto("dslb_zero_upsample2", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_colsum", I, VP, VP, LL, I, I, VP)
-_proto("dslb_conv_dgrad_naive", I, VP, VP, VP, I, I, I, I, I, I, I, I, I, I, I, VP)
 _proto("dslb_fcos_targets", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, I, I, F, I, VP, VP, VP, VP, VP, VP)
 _proto("dslb_fcos_norm", I, VP, F, VP, VP)
 _proto("dslb_fcos_loss", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, F, F, F, I, F, VP, VP, VP, VP)
@@ -173,7 +171,8 @@ _proto("dslb_sq_norm", I, VP, LL, VP, VP)
 _proto("dslb_clip_coef", I, VP, F, VP, VP)
 _proto("dslb_sgd_step", I, VP, VP, VP, LL, VP, VP, F, F, F, I, VP)
 _proto("dslb_fcos_point_scores", I, VP, VP, VP, LL, I, I, VP)
-_proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I, VP, VP, VP, VP, VP, I, VP)
+_proto("dslb_fcos_topk_points", I, VP, VP, VP, VP, I, I, VP)
+_proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I, VP, VP, VP, VP, VP, I, VP, VP)
 
 lib.dslb_nms_workspace_bytes.restype = C.c_size_t
 lib.dslb_nms_workspace_bytes.argtypes = [I, I]

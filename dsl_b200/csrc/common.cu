@@ -111,4 +111,4 @@ int encode_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, i
 }  // namespace dslb
 
 extern "C" const char* dslb_last_error(void) { return dslb::g_err; }
-extern "C" int dslb_version(void) { return 101; }  // 101: + dslb_view_images, dslb_pseudo_labels_saved
+extern "C" int dslb_version(void) { return 102; }  // 102: + dslb_fcos_topk_points

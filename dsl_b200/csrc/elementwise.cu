@@ -82,54 +82,6 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ stem
-// im2col of the 7x7/2 pad-3 stem conv straight from the NCHW fp32 image: out[pix][k], k = (r*7+s)*3 + c for
-// k < 147, zero up to 192 (3 x 64-channel chunks for the tensor-core 1x1 conv that follows).
-// Block = one output row segment of STEM_QS pixels of one image: the 7 input rows x 3 channels x (2*QS+5) columns it
-// reads are staged in shared memory with coalesced fp32 loads, then each thread assembles 16-byte chunks of the
-// K-major rows (the whole block writes one contiguous QS*384-byte span).
-constexpr int STEM_QS = 64;
-constexpr int STEM_SW = 2 * STEM_QS + 5;
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
-                                                          int N, int H, int W, int Ho, int Wo) {
-  __shared__ float patch[21 * STEM_SW];  // [(r*3 + c)][column]
-  __shared__ short koff[192];            // k -> offset inside `patch` of tap (r, s), channel c; -1 for the zero padding
-  const int qsegs = (Wo + STEM_QS - 1) / STEM_QS;
-  if (threadIdx.x < 192) {
-    const int k = threadIdx.x;
-    const int tap = k / 3, c = k - tap * 3, r = tap / 7, sx = tap - r * 7;
-    koff[k] = k < 147 ? (short)((r * 3 + c) * STEM_SW + sx) : (short)-1;
-  }
-  const long long nblk = (long long)N * Ho * qsegs;
-  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-    const int qs = b % qsegs;
-    const int p = (b / qsegs) % Ho;
-    const int n = b / ((long long)qsegs * Ho);
-    const int q0 = qs * STEM_QS;
-    const int w0 = q0 * 2 - 3, h0 = p * 2 - 3;
-    __syncthreads();  // previous iteration's readers are done (and koff is visible on the first one)
-    for (int i = threadIdx.x; i < 21 * STEM_SW; i += 256) {
-      const int rc = i / STEM_SW, col = i - rc * STEM_SW;
-      const int r = rc / 3, c = rc - r * 3;
-      const int h = h0 + r, w = w0 + col;
-      patch[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(img + (((long long)n * 3 + c) * H + h) * W + w) : 0.f;
-    }
-    __syncthreads();
-    const int npx = min(STEM_QS, Wo - q0);
-    uint4* dst = reinterpret_cast<uint4*>(out + (((long long)n * Ho + p) * Wo + q0) * 192);
-    for (int i = threadIdx.x; i < npx * 24; i += 256) {
-      const int ql = i / 24, j = i - ql * 24;
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int o = koff[j * 8 + e];
-        f[e] = o >= 0 ? patch[o + 2 * ql] : 0.f;
-      }
-      dst[i] = pack8(f);
-    }
-  }
-}
-
 // 3x3 stride-2 pad-1 max-pool, NHWC bf16, 8 channels per thread
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                     int W, int C, int Ho, int Wo) {
@@ -613,39 +565,6 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __
   }
 }
 
-// Direct (CUDA-core) data gradient for the two tiny stride-2 3x3 FPN convs (P6, P7: <= 13x21 outputs), where a
-// tensor-core formulation would need a strided scatter: dx[n,h,w,ci] (+)= sum_{r,s,co} dy[n,p,q,co] * Wp[r*S+s][co][ci]
-// with h = p*stride - pad + r. Wp is the packed fprop weight (ci contiguous => coalesced across the warp).
-__global__ void conv_dgrad_naive_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ wp,
-                                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int Ci, int Co, int co_pad,
-                                        int R, int S, int stride, int pad, int Ho, int Wo, int accumulate) {
-  const long long total = (long long)N * H * W * Ci;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int ci = t % Ci;
-    const long long pix = t / Ci;
-    const int w = pix % W;
-    const int h = (pix / W) % H;
-    const int n = pix / ((long long)W * H);
-    float acc = accumulate ? __bfloat162float(dx[t]) : 0.f;
-    for (int r = 0; r < R; ++r) {
-      const int hp = h + pad - r;
-      if (hp < 0 || hp % stride != 0) continue;
-      const int p = hp / stride;
-      if (p >= Ho) continue;
-      for (int s = 0; s < S; ++s) {
-        const int wq = w + pad - s;
-        if (wq < 0 || wq % stride != 0) continue;
-        const int q = wq / stride;
-        if (q >= Wo) continue;
-        const __nv_bfloat16* dyp = dy + (((long long)n * Ho + p) * Wo + q) * Co;
-        const __nv_bfloat16* wpp = wp + ((long long)(r * S + s) * co_pad) * Ci + ci;
-        for (int co = 0; co < Co; ++co) acc += __bfloat162float(dyp[co]) * __bfloat162float(wpp[(long long)co * Ci]);
-      }
-    }
-    dx[t] = __float2bfloat16_rn(acc);
-  }
-}
-
 }  // namespace dslb
 
 using namespace dslb;
@@ -672,14 +591,6 @@ extern "C" int dslb_nhwc_to_nchw_f32(const void* x, float* y, int N, int C, int 
   else
     nhwc_to_nchw_kernel<__nv_bfloat16>
         <<<grid_for(tiles, 1, 16), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, N, C, H * W, ld);
-  LAUNCH_CHECK();
-}
-
-extern "C" int dslb_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream) {
-  DSLB_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "dslb_stem_im2col: bad arguments");
-  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const long long nblk = (long long)N * Ho * ((Wo + STEM_QS - 1) / STEM_QS);
-  stem_im2col_kernel<<<grid_for(nblk, 1, 16), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, N, H, W, Ho, Wo);
   LAUNCH_CHECK();
 }
 
@@ -901,13 +812,3 @@ extern "C" int dslb_colsum(const void* x, float* out, long long npix, int ld, in
   LAUNCH_CHECK();
 }
 
-extern "C" int dslb_conv_dgrad_naive(const void* dy, const void* wp, void* dx, int N, int H, int W, int Ci, int Co,
-                                     int co_pad, int R, int S, int stride, int pad, int accumulate, void* stream) {
-  DSLB_CHECK_ARG(dy && wp && dx && stride >= 1, "dslb_conv_dgrad_naive: bad arguments");
-  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
-  const long long total = (long long)N * H * W * Ci;
-  conv_dgrad_naive_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)wp, (__nv_bfloat16*)dx, N, H, W, Ci, Co, co_pad, R, S, stride, pad,
-      Ho, Wo, accumulate);
-  LAUNCH_CHECK();
-}

@@ -18,6 +18,7 @@ import math
 import torch
 
 from . import _lib as L
+from .arena import Arena
 from .params import RESNET_BLOCKS, ParamStore, fpn_spec, head_spec, resnet_spec, rla_resnet_spec
 
 BF16 = torch.bfloat16
@@ -155,7 +156,7 @@ class ConvW:
         self.stride, self.pad = stride, pad
         self.cout_pad = ceil_to(self.O, 16)
         dev = st.device
-        self.wp = torch.zeros(self.R * self.S, self.cout_pad, self.I, dtype=BF16, device=dev)
+        self.wp = net.mem.zeros(self.R * self.S, self.cout_pad, self.I, dtype=BF16)
         self.bn = bn
         self.scale = None
         if bn is not None:
@@ -168,7 +169,7 @@ class ConvW:
         self.trainable = trainable
         self.dy_ld = dy_ld or ceil_to(self.O, 64)  # channel stride of the gradient buffer feeding dgrad/wgrad
         if need_dgrad:
-            self.wpT = torch.zeros(self.R * self.S, ceil_to(self.I, 16), self.dy_ld, dtype=BF16, device=dev)
+            self.wpT = net.mem.zeros(self.R * self.S, ceil_to(self.I, 16), self.dy_ld, dtype=BF16)
         self.dw = None  # fp32 packed wgrad [taps][O][I]: a view into the net's zero arena (FCOSNet._alloc_arena)
         if trainable:
             net.want_arena(self, "dw", self.R * self.S * self.O * self.I, (self.R * self.S, self.O, self.I))
@@ -265,6 +266,7 @@ class FCOSNet:
                     "all": lambda: bb_spec(depth) + fpn_spec() + head_spec(num_classes)}[parts]()
             store = ParamStore(spec, device).init_reference(seed)
         self.store = store
+        self.mem = Arena(self.dev)   # every static buffer of this plan: a few memsets instead of one per buffer
         self._arena_wants = []
         self.fwd_ops, self.bwd_ops, self.repack_ops = [], [], []
         self.bwd_meta = []
@@ -273,7 +275,7 @@ class FCOSNet:
         self.flops_fwd = 0.0
         self.flops_bwd = 0.0
         if train:
-            self.grad = torch.zeros(store.n_train, dtype=torch.float32, device=self.dev)
+            self.grad = self.mem.zeros(store.n_train, dtype=torch.float32)
         if parts in ("all", "backbone"):
             self._build_backbone()
         if parts == "neck":
@@ -321,7 +323,7 @@ class FCOSNet:
 
     # ------------------------------------------------------------------------------------------ helpers
     def buf(self, *shape, dtype=BF16):
-        return torch.zeros(*shape, dtype=dtype, device=self.dev)
+        return self.mem.zeros(*shape, dtype=dtype)
 
     def want_arena(self, obj, attr, n, shape, dtype=torch.float32):
         """Reserve `n` elements of the zero arena (one memset at the start of every backward clears all of it);
@@ -335,7 +337,7 @@ class FCOSNet:
             nf = n * (2 if dtype == torch.float64 else 1)
             plan.append((obj, attr, off, nf, shape, dtype))
             off += ceil_to(nf, 64)
-        self.arena = torch.zeros(max(off, 64), dtype=torch.float32, device=self.dev)
+        self.arena = self.mem.zeros(max(off, 64), dtype=torch.float32)
         for obj, attr, o, nf, shape, dtype in plan:
             v = self.arena[o:o + nf]
             if dtype == torch.float64:
@@ -506,8 +508,8 @@ class FCOSNet:
                                                 bias=f"bbox_head.{br}_convs.{i}.conv.bias", pad=1, need_dgrad=tr,
                                                 trainable=tr))
         # GroupNorm statistics of all (branch, layer, level) maps in one buffer -> one memset per pass
-        self.gn_stats = torch.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=self.dev)
-        self.gn_mr = torch.zeros(2, 4, nl, B, 32, 4, dtype=torch.float32, device=self.dev)
+        self.gn_stats = self.mem.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64)
+        self.gn_mr = self.mem.zeros(2, 4, nl, B, 32, 4, dtype=torch.float32)
         self.add_fwd(self.gn_stats.zero_)
         self.y = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
         self.z = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
@@ -528,10 +530,10 @@ class FCOSNet:
         # rows of 8) on the reg tower with bbox = relu(scale_l * (conv + b)) (x stride in eval mode)
         self.cls_w = self.conv("bbox_head.conv_cls.weight", bias="bbox_head.conv_cls.bias", pad=1, need_dgrad=tr,
                                trainable=tr, dy_ld=128)
-        self.rc_wp = torch.zeros(9, 16, 256, dtype=BF16, device=self.dev)   # rows 0-3 conv_reg, 4 conv_centerness
-        self.rc_wpT = torch.zeros(9, 256, 64, dtype=BF16, device=self.dev)
+        self.rc_wp = self.mem.zeros(9, 16, 256, dtype=BF16)   # rows 0-3 conv_reg, 4 conv_centerness
+        self.rc_wpT = self.mem.zeros(9, 256, 64, dtype=BF16)
         self.rc_scale = torch.ones(nl, 8, dtype=torch.float32, device=self.dev)
-        self.rc_shift = torch.zeros(nl, 8, dtype=torch.float32, device=self.dev)
+        self.rc_shift = self.mem.zeros(nl, 8, dtype=torch.float32)
         self.scale_vals = torch.ones(nl, dtype=torch.float32, device=self.dev)
         self.level_mult = torch.tensor([float(s) if not self.train else 1.0 for s in self.strides[:nl]],
                                        dtype=torch.float32, device=self.dev)
@@ -618,21 +620,21 @@ class FCOSNet:
             self.dcls_f32 = [self.buf(B, h, w, C, dtype=torch.float32) for (h, w) in self.psize]
             self.drc_f32 = [self.buf(B, h, w, 8, dtype=torch.float32) for (h, w) in self.psize]
         P = self.npoints
-        self.labels = torch.zeros(P, dtype=torch.int64, device=self.dev)
-        self.bbox_targets = torch.zeros(P, 4, dtype=torch.float32, device=self.dev)
-        self.weights = torch.zeros(P, dtype=torch.float32, device=self.dev)
-        self.ctr_targets = torch.zeros(P, dtype=torch.float32, device=self.dev)
-        self.counts = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.labels = self.mem.zeros(P, dtype=torch.int64)
+        self.bbox_targets = self.mem.zeros(P, 4, dtype=torch.float32)
+        self.weights = self.mem.zeros(P, dtype=torch.float32)
+        self.ctr_targets = self.mem.zeros(P, dtype=torch.float32)
+        self.counts = self.mem.zeros(2, dtype=torch.float64)
         self.norm = torch.ones(2, dtype=torch.float32, device=self.dev)
-        self.loss_acc = torch.zeros(16, dtype=torch.float32, device=self.dev)  # one memset for both accumulators
+        self.loss_acc = self.mem.zeros(16, dtype=torch.float32)  # one memset for both accumulators
         self.loss_sums = self.loss_acc[:8].view(torch.float64)
         self.dscale = self.loss_acc[8:16]
         self.max_boxes = 1024
-        self.gt_boxes = torch.zeros(self.max_boxes, 4, dtype=torch.float32, device=self.dev)
-        self.gt_labels = torch.zeros(self.max_boxes, dtype=torch.int64, device=self.dev)
-        self.gt_off = torch.zeros(B + 1, dtype=torch.int32, device=self.dev)
-        self.ig_boxes = torch.zeros(self.max_boxes, 4, dtype=torch.float32, device=self.dev)
-        self.ig_off = torch.zeros(B + 1, dtype=torch.int32, device=self.dev)
+        self.gt_boxes = self.mem.zeros(self.max_boxes, 4, dtype=torch.float32)
+        self.gt_labels = self.mem.zeros(self.max_boxes, dtype=torch.int64)
+        self.gt_off = self.mem.zeros(B + 1, dtype=torch.int32)
+        self.ig_boxes = self.mem.zeros(self.max_boxes, 4, dtype=torch.float32)
+        self.ig_off = self.mem.zeros(B + 1, dtype=torch.int32)
         self.use_ignore = True
         self.levels_arr = self._fill_levels(True)
         self.world_size = 1.0

@@ -52,7 +52,7 @@ class SliceConvW(ConvW):
         dev = st.device
         RS = self.R * self.S
         self.w_slice = self.w.view(self.O, -1)[:, i0 * RS:]          # data_ptr = first element of the slice
-        self.wp = torch.zeros(RS, self.cout_pad, self.Ip, dtype=BF16, device=dev)
+        self.wp = net.mem.zeros(RS, self.cout_pad, self.Ip, dtype=BF16)
         self.bn = bn
         self.scale = None
         self.shift = None
@@ -65,7 +65,7 @@ class SliceConvW(ConvW):
         self.trainable = trainable
         self.dy_ld = ceil_to(self.O, 64)
         if need_dgrad:
-            self.wpT = torch.zeros(RS, self.Ip, self.dy_ld, dtype=BF16, device=dev)
+            self.wpT = net.mem.zeros(RS, self.Ip, self.dy_ld, dtype=BF16)
         self.dw = None
         if trainable:
             net.want_arena(self, "dw", RS * self.O * self.Ip, (RS, self.O, self.Ip))

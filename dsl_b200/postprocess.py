@@ -21,17 +21,22 @@ class TeacherPost:
         assert max_per_img <= 128
         self.cand_cap = cand_cap
         f32, i32 = torch.float32, torch.int32
-        z = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype, device=self.dev)  # noqa: E731
+        from .arena import Arena
+        self.mem = Arena(self.dev, first_chunk=8 << 20)
+        z = lambda *s, dtype=f32: self.mem.zeros(*s, dtype=dtype)  # noqa: E731
         self.pt_scores = [z(B, h * w) for (h, w) in self.psize]
         self.cand_boxes = z(B, cand_cap, 4)
         self.cand_scores = z(B, cand_cap)
         self.cand_labels = z(B, cand_cap, dtype=i32)
         self.cand_points = z(B, cand_cap, dtype=i32)
         self.cand_counts = z(B, dtype=i32)
+        self.cand_overflow = z(1, dtype=i32)   # sticky: some decode since the last check exceeded cand_cap
+        self._tk = None
+        self.sel = {}
         self.img_hw = z(B, 2)          # img_shape (H, W): clip range of the decoded boxes
         self.scale_factor = torch.ones(B, 4, dtype=f32, device=self.dev)
         self.ws_bytes = L.lib.dslb_nms_workspace_bytes(B, cand_cap)
-        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.ws = z(self.ws_bytes, dtype=torch.uint8)
         self.dets = z(B, max_per_img, 5)
         self.det_labels = z(B, max_per_img, dtype=i32)
         self.det_count = z(B, dtype=i32)
@@ -64,26 +69,53 @@ class TeacherPost:
         """Per-class ignore thresholds (adathres.json "thres" of the reference), python floats / fp64."""
         self.thr_class.copy_(torch.as_tensor(thr, dtype=torch.float64), non_blocking=True)
 
+    def _topk_plan(self):
+        """Levels with more points than nms_pre: their selections come from ONE dslb_fcos_topk_points launch."""
+        import ctypes as C
+        lv = [l for l, (h, w) in enumerate(self.psize) if 0 < self.nms_pre < h * w]
+        self.sel = {l: torch.zeros(self.B, self.nms_pre, dtype=torch.int64, device=self.dev) for l in lv}
+        n = len(lv)
+        self._tk = (lv, (C.c_void_p * max(n, 1))(*[self.pt_scores[l].data_ptr() for l in lv]),
+                    (C.c_void_p * max(n, 1))(*[self.sel[l].data_ptr() for l in lv]),
+                    (C.c_int32 * max(n, 1))(*[self.psize[l][0] * self.psize[l][1] for l in lv]),
+                    (C.c_int32 * max(n, 1))(*[self.nms_pre for _ in lv]))
+
     def decode(self, cls_out, rc_out):
         """Per level: top-nms_pre points by max_c(score * centerness), decode + clip + rescale, score gate."""
         s = L.cur_stream
+        if getattr(self, "_tk", None) is None:
+            self._topk_plan()
         self.cand_counts.zero_()
+        for l, (h, w) in enumerate(self.psize):
+            L.check(L.lib.dslb_fcos_point_scores(L.ptr(cls_out[l]), L.ptr(rc_out[l]), L.ptr(self.pt_scores[l]),
+                                                 self.B * h * w, self.C, self.C, s()), "point_scores")
+        lv, sc_p, sel_p, n_p, k_p = self._tk
+        if lv:   # `max_scores.topk(nms_pre)` (fcos_head.py:452-460) for every level that needs it, one launch
+            L.check(L.lib.dslb_fcos_topk_points(sc_p, sel_p, n_p, k_p, len(lv), self.B, s()), "topk_points")
         off = 0
         for l, (h, w) in enumerate(self.psize):
             n = h * w
-            L.check(L.lib.dslb_fcos_point_scores(L.ptr(cls_out[l]), L.ptr(rc_out[l]), L.ptr(self.pt_scores[l]),
-                                                 self.B * n, self.C, self.C, s()), "point_scores")
-            if 0 < self.nms_pre < n:
-                sel = self.pt_scores[l].topk(self.nms_pre, dim=1).indices
-                K, selp = self.nms_pre, L.ptr(sel)
+            if l in self.sel:
+                K, selp = self.nms_pre, L.ptr(self.sel[l])
             else:
-                sel, K, selp = None, n, None
+                K, selp = n, None
             L.check(L.lib.dslb_fcos_decode_gate(
                 L.ptr(cls_out[l]), L.ptr(rc_out[l]), selp, self.B, K, self.C, h, w, self.strides[l], self.C,
                 L.ptr(self.img_hw), L.ptr(self.scale_factor) if self.rescale else None, float(self.score_thr), off,
                 L.ptr(self.cand_boxes), L.ptr(self.cand_scores), L.ptr(self.cand_labels), L.ptr(self.cand_points),
-                L.ptr(self.cand_counts), self.cand_cap, s()), "decode_gate")
+                L.ptr(self.cand_counts), self.cand_cap, L.ptr(self.cand_overflow), s()), "decode_gate")
             off += n
+
+    def overflowed(self, clear=True):
+        """True if some image produced more gated candidates than `cand_cap` in any decode since the last check (host
+        sync; the flag is sticky on the device). The reference has no cap (up to levels x nms_pre x classes scores can
+        pass the gate); beyond it the slots are claimed in arrival order, so WHICH candidates are dropped is not
+        deterministic. 8192 is several times what a trained FCOS yields at score_thr 0.05; DSLEngine.end_epoch checks
+        the flag and raises."""
+        hit = bool(self.cand_overflow.item())
+        if hit and clear:
+            self.cand_overflow.zero_()
+        return hit
 
     def nms(self):
         """multiclass_nms: survivors in self.dets / det_labels / det_count (score-descending, <= max_per_img)."""

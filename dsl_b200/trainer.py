@@ -110,6 +110,10 @@ class DSLEngine:
         """Per-epoch adaptive thresholds (UnlabelPredHook.before_train_epoch -> adathres, unlabel_pred_hook.py:447-449):
         turn the statistics the teacher branch accumulated on the device into next epoch's per-class thresholds."""
         had = self.post.have_prev
+        if self.post.overflowed():
+            raise RuntimeError(f"teacher decode: an image produced more than cand_cap={self.post.cand_cap} gated candidates "
+                               "during this epoch; the surplus was dropped in arrival order (the reference has no cap). "
+                               "Raise TeacherPost(cand_cap=...) or score_thr.")
         out = self.post.adathres_update(**adathres_kw)
         if self.post.have_prev != had:
             # the captured pseudo-label launch carries the "no history yet" gate (a NULL pointer for last epoch's

@@ -33,7 +33,7 @@ extern "C" {
 #define DSLB_GN_STAT_STRIDE 32
 
 const char* dslb_last_error(void);
-int dslb_version(void);   /* 101 = this header (100 + dslb_view_images, dslb_pseudo_labels_saved) */
+int dslb_version(void);   /* 102 = this header (101 + dslb_fcos_topk_points; pseudo-label rule keeps class C-1) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (fprop, and dgrad expressed as fprop on dY with
@@ -103,9 +103,6 @@ double dslb_wgrad_plan_flops(const dslb_wgrad_plan_t* plan);
 int dslb_nchw_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int Cpad, void* stream);
 /* pixel-major rows of `ld` elements (bf16, or fp32 if x_is_fp32) -> NCHW fp32, first C channels. */
 int dslb_nhwc_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, int ld, int x_is_fp32, void* stream);
-/* im2col of the 7x7/2 pad-3 stem conv (resnet.py:597-610) from the NCHW fp32 image: out bf16 [N*Ho*Wo][192],
- * k = (r*7+s)*3 + c, zero for k >= 147; the stem then runs as a 1x1 tensor-core conv with Cin = 192. */
-int dslb_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream);
 /* The whole stem in one kernel: 7x7/2 pad-3 conv (3 -> 64) + frozen BatchNorm + ReLU (resnet.py:597-610,630-637) from
  * the NCHW fp32 image to NHWC bf16 [N][Ho][Wo][64]. The im2col tile is assembled in shared memory and fed to
  * tcgen05.mma; w is the fp32 OIHW master weight [64][3][7][7], bn_* the frozen BatchNorm tensors [64]. */
@@ -251,10 +248,6 @@ void dslb_bn_grad_plan_destroy(dslb_bn_grad_plan_t* plan);
 /* y[n][2p][2q][:] = x[n][p][q][:], every other pixel of the [N][H][W][C] bf16 map zero: turns the data gradient of a
  * stride-2 conv into a stride-1 tensor-core dgrad over the zero-upsampled dY (FPN P6/P7 convs, necks/fpn.py:192-201). */
 int dslb_zero_upsample2(const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream);
-/* CUDA-core data gradient of a strided conv for tiny maps (FPN P6/P7 3x3 stride-2 convs, necks/fpn.py:192-201):
- * dx[n,h,w,ci] (+)= sum dy[n,p,q,co] * wp[r*S+s][co][ci]; wp = packed fprop weight; accumulate=1 adds into dx. */
-int dslb_conv_dgrad_naive(const void* dy, const void* wp, void* dx, int N, int H, int W, int Ci, int Co, int co_pad,
-                          int R, int S, int stride, int pad, int accumulate, void* stream);
 /* out[c] += sum_p x[p][c] over a pixel-major bf16 matrix (conv bias gradient). */
 int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream);
 
@@ -326,15 +319,23 @@ int dslb_sgd_step(float* p, const float* g, float* buf, long long n, const float
 /* out[pt] = max_c sigmoid(cls[pt][c]) * sigmoid(centerness[pt])  — the key of the per-level top-nms_pre. */
 int dslb_fcos_point_scores(const float* cls, const float* regctr, float* out, long long npts, int C, int ld_cls,
                            void* stream);
+/* Per-level top-K of the point scores (`max_scores.topk(nms_pre)`, fcos_head.py:452-460), all levels that need it in
+ * ONE launch: for level i, sel[i] [B][K[i]] int64 receives the indices (inside the level) of the K[i] largest of
+ * scores[i] [B][n[i]] per image. The set equals torch.topk's whenever the K-th score is unique; ties at the cut go to
+ * the lower point index; the order inside sel is unspecified. scores / sel / n / K are HOST arrays of nlevels (<= 8)
+ * entries holding device pointers / sizes. */
+int dslb_fcos_topk_points(const float* const* scores, int64_t* const* sel, const int32_t* n, const int32_t* K,
+                          int nlevels, int B, void* stream);
 /* For the K selected points of each image (sel [B][K] int64 point indices inside the level, NULL = the first K):
  * decode + clip to img_hw[n] = (H, W) + divide by scale_factor[n][4] (NULL = no rescale); every class with raw
  * sigmoid score > score_thr appends (box, score*centerness, label, point_offset+point) at an atomically claimed slot
- * of image n (counts[n], pre-zeroed; slots >= cap are dropped but still counted). Order within an image is
- * unspecified. */
+ * of image n (counts[n], pre-zeroed; slots >= cap are dropped but still counted, and *overflow — a sticky device flag,
+ * may be NULL — is set to 1: the reference has no cap, so a caller must treat a set flag as an error). Order within an
+ * image is unspecified. */
 int dslb_fcos_decode_gate(const float* cls, const float* regctr, const int64_t* sel, int B, int K, int C, int h, int w,
                           int stride, int ld_cls, const float* img_hw, const float* scale_factor, float score_thr,
                           int point_offset, float* out_boxes, float* out_scores, int32_t* out_labels,
-                          int32_t* out_points, int32_t* counts, int cap, void* stream);
+                          int32_t* out_points, int32_t* counts, int cap, int32_t* overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Teacher post-processing on the device (the reference does this on the host: D2H, numpy, JSON files).
@@ -351,8 +352,8 @@ int dslb_multiclass_nms(const float* boxes, const float* scores, const int32_t* 
                         void* stream);
 /* Detections -> pseudo ground truth for the student, i.e. the rule chain the reference spreads over
  * UnlabelPredHook (mmdet/runner/hooks/unlabel_pred_hook.py:20-38 parse_det_results: score >= infer_score_thr, int()
- * truncation, round(score, 6); :142-165 per-class nms(iou, score_threshold=0.1) over classes 0..C-2 — the last class is
- * skipped by the reference's range(0, len(id2cat)-1)) and SemiCOCODataset._parse_ann_info (mmdet/datasets/
+ * truncation, round(score, 6); :142-165 per-class nms(iou, score_threshold=0.1) over range(0, len(id2cat)-1) = all C
+ * classes: the reference's category file ends with a background entry) and SemiCOCODataset._parse_ann_info (mmdet/datasets/
  * semicoco.py:220-269: boxes without overlap with the image or thinner than 1 px dropped; ignore_lo <= score <
  * thr_class[c] -> ignore region, every other box -> GT). Output order = the reference's (class ascending, score
  * descending). Writes the packed box lists + offsets that dslb_fcos_targets consumes. max_det <= 128. */
