@@ -186,6 +186,7 @@ _proto("dslb_bce_with_logits", I, VP, VP, VP, LL, VP, VP, VP, VP)
 lib.dslb_view_boxes_workspace_bytes.restype = C.c_size_t
 lib.dslb_view_boxes_workspace_bytes.argtypes = [I]
 _proto("dslb_view_boxes", I, VP, VP, VP, VP, I, I, I, VP, C.c_size_t, VP, VP, VP, VP)
+_proto("dslb_append_scaled_boxes", I, VP, VP, VP, I, F, I, VP)
 _proto("dslb_pad_batch", I, VP, VP, VP, I, I, I, I, VP)
 _proto("dslb_view_images", I, VP, VP, I, VP, VP, I, VP, I, I, VP)
 _proto("dslb_adathres_finalize", I, VP, VP, I, D, D, D, D, D, D, VP, VP, VP, VP)

@@ -156,6 +156,31 @@ extern "C" int dslb_view_boxes(const float* boxes, const int64_t* labels, const 
   return DSLB_OK;
 }
 
+namespace dslb {
+// Scale-invariant extra sample (semi_epoch_based_runner.py:186-204): the half-resolution copy of the LAST image of the
+// batch takes that image's boxes divided by two. Packed lists: image B-1 = [off[B-1], off[B]) is appended as image B.
+__global__ void append_scaled_boxes_kernel(float4* __restrict__ boxes, long long* __restrict__ labels,
+                                           int* __restrict__ off, int B, float scale, int max_boxes) {
+  const int a = off[B - 1], b = off[B];
+  const int n = min(b - a, max_boxes - b);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 v = boxes[a + i];
+    boxes[b + i] = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
+    if (labels) labels[b + i] = labels[a + i];
+  }
+  if (threadIdx.x == 0) off[B + 1] = b + max(n, 0);
+}
+}  // namespace dslb
+
+extern "C" int dslb_append_scaled_boxes(float* boxes, int64_t* labels, int32_t* off, int B, float scale, int max_boxes,
+                                        void* stream) {
+  DSLB_CHECK_ARG(boxes && off && B >= 1 && max_boxes >= 0, "dslb_append_scaled_boxes: bad arguments");
+  dslb::append_scaled_boxes_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((float4*)boxes, (long long*)labels, off, B, scale,
+                                                                        max_boxes);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
 extern "C" int dslb_pad_batch(const float* const* imgs_dev, const int32_t* hw_dev, float* out, int B, int C, int H, int W,
                               void* stream) {
   DSLB_CHECK_ARG(imgs_dev && hw_dev && out && B >= 1 && C >= 1 && H >= 1 && W >= 1, "dslb_pad_batch: bad arguments");

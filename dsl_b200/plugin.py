@@ -558,7 +558,7 @@ class FCOSHead(_StoreModule):
         nc = dict(c.pop("norm_cfg", dict(type="GN", num_groups=32, requires_grad=True)))
         _check(nc.get("type") == "GN" and nc.get("num_groups") == 32, "norm_cfg must be GN(32)")
         _check(len(out["strides"]) == len(out["regress_ranges"]) == 5, "five levels")
-        _check(out["num_classes"] % 16 == 0, "num_classes must be a multiple of 16")
+        _check(out["num_classes"] % 4 == 0, "num_classes must be a multiple of 4 (COCO 80, VOC 20: float4 rows of logits)")
         out["train_cfg"], out["test_cfg"] = c.pop("train_cfg", None), dict(c.pop("test_cfg", None) or {})
         c.pop("init_cfg", None)
         c.pop("conv_cfg", None)
@@ -614,6 +614,11 @@ class FCOSHead(_StoreModule):
         from . import _lib as L
         assert len(feats) == 5
         _need_cuda(feats[0], "FCOSHead.forward")
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            # a detector that composes this head with its own trainable backbone would get grad-less outputs: the
+            # gradient of the fused head comes out of the loss kernel (FCOS.forward_train), not of these tensors
+            raise NotImplementedError("dsl_b200 FCOSHead.forward does not record autograd history: train through "
+                                      "dsl_b200.plugin.FCOS (fused loss + backward) or call it under torch.no_grad()")
         B = feats[0].shape[0]
         sizes = [tuple(f.shape[-2:]) for f in feats]
         net = self._net(B, sizes, self.training)
@@ -737,56 +742,7 @@ def ema_update_(teacher, student, keep_rate):
         teacher._dirty()
 
 
-def _unwrap(m):
-    return m.module if hasattr(m, "module") else m
-
-
-class EMAOWNHook:
-    """EMAOWNHook (mmdet/runner/hooks/ema.py:4-42) with the EMA arithmetic of runner.EMA done by dslb_ema_update when
-    both models are dsl_b200 modules (otherwise it defers to runner.EMA). Same ctor kwargs and trigger rules; no
-    barriers are needed because nothing touches the file system."""
-
-    def __init__(self, interval=-1, mode="epoch", ratio=0.99, start_point=-1, step_decay=None, decay_ratio=0.1,
-                 **kwargs):
-        self.interval, self.mode, self.start_point, self.ratio = interval, mode, start_point, ratio
-        self.args, self.step_decay, self.decay_ratio = kwargs, step_decay, decay_ratio
-
-    # mmcv.runner.Hook helpers (restated so the class also works where mmcv is absent)
-    @staticmethod
-    def every_n_epochs(runner, n):
-        return (runner.epoch + 1) % n == 0 if n > 0 else False
-
-    @staticmethod
-    def every_n_iters(runner, n):
-        return (runner.iter + 1) % n == 0 if n > 0 else False
-
-    def _ema(self, runner):
-        s, t = _unwrap(runner.model), _unwrap(runner.ema_model)
-        if isinstance(s, _StoreModule) and isinstance(t, _StoreModule):
-            ema_update_(t, s, self.ratio)
-            runner.ema_flag = True
-        else:
-            runner.EMA(keep_rate=self.ratio, mode=self.mode, start_point=self.start_point, **self.args)
-
-    def after_train_epoch(self, runner):
-        if self.step_decay is not None and runner.epoch + 1 in self.step_decay:
-            self.ratio = max(1.0 - (1.0 - self.ratio) / self.decay_ratio, 0.01)
-        if self.mode != "epoch" or self.interval == -1 or self.start_point > runner.epoch + 1:
-            return
-        if self.every_n_epochs(runner, self.interval):
-            self._ema(runner)
-
-    def after_train_iter(self, runner):
-        if self.mode != "iteration" or self.interval == -1 or self.start_point > runner.iter + 1:
-            return
-        if self.every_n_iters(runner, self.interval):
-            self._ema(runner)
-
-    # the remaining Hook stages are no-ops
-    def __getattr__(self, name):
-        if name.startswith(("before_", "after_")):
-            return lambda runner: None
-        raise AttributeError(name)
+from .hooks import EMAOWNHook, _unwrap  # noqa: E402,F401  (the reference's hook; an mmcv Hook when mmcv is importable)
 
 
 def scale_invariant_input(img, gt_bboxes, gt_labels, gt_bboxes_ignore, img_metas):
@@ -861,9 +817,14 @@ class RLA_ResNet(ResNet):
             ResNet.init_weights(self)
 
 
-def register(force=True):
+def register(force=True, runner=False):
     """Register under the reference's registry keys. Returns the list of keys registered ([] when mmdet / mmcv are not
-    importable, e.g. on a bare GPU box: the classes are then used directly)."""
+    importable, e.g. on a bare GPU box: the classes are then used directly).
+
+    Importing dsl_b200.plugin swaps the MODEL-side classes (detector / backbone / neck / head / losses) and the
+    reference's own EMAOWNHook; the fused RUNNERS['SemiEpochBasedRunner'] changes how a whole iteration executes, so it
+    is registered only on request: `custom_imports=dict(imports=['dsl_b200.plugin', 'dsl_b200.plugin_runner'])` or
+    register(runner=True)."""
     done = []
     try:
         from mmdet.models.builder import DETECTORS, HEADS
@@ -886,11 +847,14 @@ def register(force=True):
         done.append("HOOKS.EMAOWNHook")
     except Exception:
         pass
-    try:   # LOSSES.{FocalLoss, GIoULoss, CrossEntropyLoss} and RUNNERS.SemiEpochBasedRunner (need libdslb.so)
-        from . import losses, runner
-        done += losses.register(force) + runner.register(force)
+    try:   # LOSSES.{FocalLoss, GIoULoss, CrossEntropyLoss} (need libdslb.so)
+        from . import losses
+        done += losses.register(force)
     except Exception:
         pass
+    if runner:
+        from . import runner as _runner
+        done += _runner.register(force)
     return done
 
 

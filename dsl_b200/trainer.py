@@ -55,6 +55,7 @@ class DSLEngine:
         self.bias_lr_mult, self.bias_decay_mult = bias_lr_mult, bias_decay_mult
         self.max_grad_norm = max_grad_norm
         self.ema_keep = ema_keep
+        self.ema_in_step = True   # False: the EMA is applied by an explicit DSLEngine.ema() call (EMAOWNHook epoch mode)
         self.sqnorm = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.coef = torch.ones(2, dtype=torch.float32, device=self.dev)
         self.lr_scale = torch.ones(1, dtype=torch.float32, device=self.dev)
@@ -194,7 +195,9 @@ class DSLEngine:
         g = self.student.grad
         self.sqnorm.zero_()
         L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
-        L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm), L.ptr(self.coef), s), "clip_coef")
+        # max_grad_norm None = no clipping (optimizer_config.grad_clip=None): a bound no fp32 norm reaches gives coef 1
+        L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm if self.max_grad_norm is not None
+                                                                 else 3.0e38), L.ptr(self.coef), s), "clip_coef")
         a0, a1 = st.region_range["A"]
         b0, b1 = st.region_range["B"]
         L.check(L.lib.dslb_sgd_step(L.ptr(st.flat[a0:a1]), L.ptr(g[a0:a1]), L.ptr(self.mom[a0:a1]), a1 - a0,
@@ -208,6 +211,8 @@ class DSLEngine:
         c_t = float(torch.tensor(k, dtype=torch.float32))
 
         def teacher_side():
+            if not self.ema_in_step:
+                return
             L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, L.cur_stream()), "ema")
             self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
 
@@ -226,6 +231,17 @@ class DSLEngine:
             teacher_side()
             self.student.repack(everything=False)
 
+    def ema(self, keep_rate=None):
+        """runner.EMA() as an explicit call (semi_epoch_based_runner.py:368-409): T <- (1 - k) S + k T over every
+        state_dict entry + refresh of the teacher's derived operands. The captured step does this itself while
+        `ema_in_step` is set."""
+        k = float(self.ema_keep if keep_rate is None else keep_rate)
+        c_s = float(torch.tensor(1 - k, dtype=torch.float32))
+        c_t = float(torch.tensor(k, dtype=torch.float32))
+        st, tt = self.student.store, self.teacher.store
+        L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, L.cur_stream()), "ema")
+        self.teacher.repack(everything=True)
+
     def _allreduce_counts(self):
         dist_ops.allreduce_sum_(self.student.counts)   # packed (num_pos, sum ctr-targets): one collective
 
@@ -238,25 +254,33 @@ class DSLEngine:
         _, _, lo, hi = self._bucket_ranges()[k]
         return dist_ops.allreduce_mean_async_(self.student.grad[lo:hi])
 
-    def _run_eager(self):
+    def _run_eager(self, collectives=True):
+        """One step without graphs. collectives=False: the same launches without any all-reduce — the warm-up pass of
+        a graph capture. A rank captures whenever IT first meets a padded shape (multi-scale batches differ between
+        ranks), so a warm-up that talked to its peers would pair its collectives with whatever the other ranks happen to
+        be sending (a gradient bucket against a 2-double normaliser: hang or corrupted gradients). The captured graphs
+        exclude the collectives anyway and the warm-up's state changes are rolled back."""
         if self.world > 1 and self.bucketed:
             self._phase_t()
-            wc = dist_ops.allreduce_sum_async_(self.student.counts)
+            wc = dist_ops.allreduce_sum_async_(self.student.counts) if collectives else None
             self._phase_a_fwd()
             if wc is not None:
                 wc.wait()
             works = []
             for k in range(len(self.student.bwd_buckets)):
                 self._phase_b_part(k)
-                works.append(self._allreduce_bucket_async(k))
+                if collectives:
+                    works.append(self._allreduce_bucket_async(k))
             for w in works:
                 if w is not None:
                     w.wait()
         else:
             self._phase_a()
-            self._allreduce_counts()
+            if collectives:
+                self._allreduce_counts()
             self._phase_b()
-            self._allreduce_grads()
+            if collectives:
+                self._allreduce_grads()
         self._phase_c()
 
     def _capture(self):
@@ -269,7 +293,7 @@ class DSLEngine:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream, as torch's graph capture requires
-            self._run_eager()
+            self._run_eager(collectives=False)   # no peer traffic: capture is a rank-local event (see _run_eager)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         for t, v in zip(state, saved):
@@ -312,29 +336,34 @@ class DSLEngine:
             gt_labels = list(gt_labels) + [gt_labels[-1]]
             if gt_bboxes_ignore is not None:
                 gt_bboxes_ignore = list(gt_bboxes_ignore) + [gt_bboxes_ignore[-1] / 2]
-            # soft-loss warm-up (fcos_head.py:325-327): weight / 1000 while soft_warm_up >= cur_iter
-            if self.soft_weight != 0.0:
-                sw = self.soft_weight / 1000.0 if self.soft_warm_up >= self.cur_iter else self.soft_weight
-                if sw != self.student.si_weight:
-                    self.student.si_weight = sw
-                    self.graphs = None      # the weight is a launch constant of the captured loss kernel
-                if self.soft_warm_up >= self.cur_iter:
-                    self.cur_iter += 1
+            self._si_weight_tick()
         elif student_img is not None:
             self.student.img.copy_(student_img, non_blocking=True)
         self.student.set_targets(gt_bboxes, gt_labels, gt_bboxes_ignore)
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
 
-    def set_inputs_with_pseudo_labels(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore, views, teacher_img=None):
+    def _si_weight_tick(self):
+        """Soft-loss warm-up (fcos_head.py:325-327): weight / 1000 while soft_warm_up >= cur_iter."""
+        if self.soft_weight != 0.0:
+            sw = self.soft_weight / 1000.0 if self.soft_warm_up >= self.cur_iter else self.soft_weight
+            if sw != self.student.si_weight:
+                self.student.si_weight = sw
+                self.graphs = None      # the weight is a launch constant of the captured loss kernel
+            if self.soft_warm_up >= self.cur_iter:
+                self.cur_iter += 1
+
+    def set_inputs_with_pseudo_labels(self, student_img, gt_bboxes, gt_labels, gt_bboxes_ignore, views, teacher_img=None,
+                                      pl=None):
         """set_inputs() for the reference's labeled + unlabeled batch mix, with the unlabeled part labelled ON THE
         DEVICE: `gt_*` cover only the first B - tB (labeled) images; the last tB images are the strong views of the
-        images the EMA teacher labelled in its previous pass (self.pl_* = pseudo GT / ignore boxes in original-image
-        coordinates), carried into each strong view by `views` (geometry.View per unlabeled image: Resize scale,
-        PatchShuffle cut, flip). Replaces the reference's JSON round trip (UnlabelPredHook.save_results2file ->
-        SemiCOCODataset -> pipelines) for the transforms geometry.py covers. No host sync."""
+        images the EMA teacher labelled in an earlier pass (`pl` = (gt_boxes, gt_labels, gt_off, ig_boxes, ig_off) in
+        original-image coordinates, default: this engine's own self.pl_* of the previous step), carried into each
+        strong view by `views` (geometry.View per unlabeled image: Resize scale, PatchShuffle cut, flip). Replaces the
+        reference's JSON round trip (UnlabelPredHook.save_results2file -> SemiCOCODataset -> pipelines) for the
+        transforms geometry.py covers. With scale_invariant the extra half-resolution copy of the last image and its
+        halved box lists (semi_epoch_based_runner.py:186-204) are built on the device as well. No host sync."""
         from .geometry import ViewGeometry
-        assert not self.scale_invariant, "the device-side pseudo-label feed does not build the SI extra image yet"
         st, tB = self.student, self.teacher.B
         BL = self.B - tB
         assert BL >= 0 and len(gt_bboxes) == BL and len(gt_labels) == BL and len(views) == tB
@@ -343,10 +372,13 @@ class DSLEngine:
             self._geo = ViewGeometry(tB, max_boxes=st.max_boxes, device=self.dev)
             self._geo_off = torch.zeros(tB + 1, dtype=torch.int32, device=self.dev)
         self._geo.set_views(views)
+        B = self.B
         if student_img is not None:      # None: already rendered in place by set_images_from_sources
-            st.img.copy_(student_img, non_blocking=True)
+            st.img[:B].copy_(student_img, non_blocking=True)
         if teacher_img is not None:
             self.teacher.img.copy_(teacher_img, non_blocking=True)
+        pl_gt_boxes, pl_gt_labels, pl_gt_off, pl_ig_boxes, pl_ig_off = pl if pl is not None else (
+            self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, self.pl_ig_boxes, self.pl_ig_off)
         # labeled part from the host lists
         offs, ioffs = [0], [0]
         for b in gt_bboxes:
@@ -364,11 +396,19 @@ class DSLEngine:
         st.ig_off[:BL + 1].copy_(torch.tensor(ioffs, dtype=torch.int32), non_blocking=True)
         st.use_ignore = True
         # unlabeled part: teacher's pseudo GT / ignore lists -> strong views, appended behind the labeled boxes
-        self._geo.run(self.pl_gt_boxes, self.pl_gt_labels, self.pl_gt_off, out_boxes=st.gt_boxes[nL:],
+        self._geo.run(pl_gt_boxes, pl_gt_labels, pl_gt_off, out_boxes=st.gt_boxes[nL:],
                       out_labels=st.gt_labels[nL:], out_off=self._geo_off)
-        st.gt_off[BL + 1:].copy_(self._geo_off[1:] + nL)
-        self._geo.run(self.pl_ig_boxes, None, self.pl_ig_off, out_boxes=st.ig_boxes[nI:], out_off=self._geo_off)
-        st.ig_off[BL + 1:].copy_(self._geo_off[1:] + nI)
+        st.gt_off[BL + 1:B + 1].copy_(self._geo_off[1:] + nL)
+        self._geo.run(pl_ig_boxes, None, pl_ig_off, out_boxes=st.ig_boxes[nI:], out_off=self._geo_off)
+        st.ig_off[BL + 1:B + 1].copy_(self._geo_off[1:] + nI)
+        if self.scale_invariant:
+            s = L.cur_stream()
+            L.check(L.lib.dslb_si_half_image(L.ptr(st.img[B - 1]), L.ptr(st.img[B]), 3, self.H, self.W, s), "si_half_image")
+            L.check(L.lib.dslb_append_scaled_boxes(L.ptr(st.gt_boxes), L.ptr(st.gt_labels), L.ptr(st.gt_off), B, 0.5,
+                                                   st.max_boxes, s), "si boxes")
+            L.check(L.lib.dslb_append_scaled_boxes(L.ptr(st.ig_boxes), None, L.ptr(st.ig_off), B, 0.5, st.max_boxes, s),
+                    "si ignore boxes")
+            self._si_weight_tick()
 
     def set_images_from_sources(self, student_srcs, student_views, teacher_srcs=None, teacher_views=None,
                                 mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375), to_rgb=True):

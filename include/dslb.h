@@ -45,7 +45,8 @@ int dslb_version(void);   /* 102 = this header (101 + dslb_fcos_topk_points; pse
  * Epilogue, per output element (n,p,q,c), in this order:
  *     v = acc * scale[c] + shift[c];  v += residual;  if (c < relu_nch) v = max(v,0);
  *     if (relu_mask) v = relu_mask > 0 ? v : 0;
- *     gn_stats[n][c / gn_cpg][0..1] += (v, v*v)   (fp64 atomics on the bf16-rounded output: GroupNorm statistics)
+ *     gn_stats[n][c / gn_cpg][0..1] += (v, v*v)   (GroupNorm statistics: per-tile fp32 partial sums of the fp32 v, i.e.
+ *                                                  before the bf16 rounding of the store, added with fp64 atomics)
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct dslb_conv_seg {
   const void* x;         /* bf16 NHWC [N][H][W][Cin], Cin % 64 == 0                                   */
@@ -410,6 +411,10 @@ size_t dslb_view_boxes_workspace_bytes(int max_in);
 int dslb_view_boxes(const float* boxes, const int64_t* labels, const int32_t* off, const dslb_view_t* views_dev, int B,
                     int max_in, int max_out, void* workspace, size_t ws_bytes, float* out_boxes, int64_t* out_labels,
                     int32_t* out_off, void* stream);
+/* Scale-invariant extra sample (mmdet/runner/hooks/semi_epoch_based_runner.py:186-204: gt_bboxes.append(gt_bboxes[-1] / 2),
+ * same labels): in a packed list with offsets off[0..B], image B-1's boxes x scale are appended as image B and off[B+1]
+ * is written (truncated at max_boxes). labels may be NULL (ignore lists). off must have room for B + 2 entries. */
+int dslb_append_scaled_boxes(float* boxes, int64_t* labels, int32_t* off, int B, float scale, int max_boxes, void* stream);
 int dslb_pad_batch(const float* const* imgs_dev, const int32_t* hw_dev, float* out, int B, int C, int H, int W,
                    void* stream);
 

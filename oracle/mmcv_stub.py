@@ -10,6 +10,8 @@ What each piece stands in for (mmcv 1.3.x public behaviour):
   build_conv_layer / build_norm_layer -- nn.Conv2d / (name, nn.BatchNorm2d|nn.GroupNorm); requires_grad flag
   force_fp32 / auto_fp16 / jit -- identity decorators (fp16_enabled is False on this path)
   ops.nms / ops.batched_nms  -- torchvision NMS (IoU > thr suppressed, offset 0), class-offset trick
+  runner.Hook / HOOKS / RUNNERS / build_runner / build_optimizer / OptimizerHook / EpochBasedRunner,
+  parallel.MMDataParallel    -- shells so that mmdet/apis/train.py::train_detector executes in place (no training logic)
   ops.sigmoid_focal_loss     -- deliberately NOT provided: on CPU the reference takes its own
                                 py_sigmoid_focal_loss branch (mmdet/models/losses/focal_loss.py:162-168)
 """
@@ -220,23 +222,113 @@ def install():
         return m
 
     mmcv = mod("mmcv", __dslb_stub__=True, __version__="1.3.10", jit=_identity_decorator,
-               is_tuple_of=lambda seq, t: isinstance(seq, tuple) and all(isinstance(s, t) for s in seq))
+               is_tuple_of=lambda seq, t: isinstance(seq, tuple) and all(isinstance(s, t) for s in seq),
+               is_list_of=lambda seq, t: isinstance(seq, list) and all(isinstance(s, t) for s in seq),
+               is_str=lambda x: isinstance(x, str), build_from_cfg=build_from_cfg)
     MODELS = Registry("model")
     mmcv.cnn = mod("mmcv.cnn", MODELS=MODELS, ConvModule=ConvModule, Scale=Scale,
                    build_conv_layer=build_conv_layer, build_norm_layer=build_norm_layer,
                    build_plugin_layer=build_plugin_layer)
     mmcv.utils = mod("mmcv.utils", Registry=Registry, build_from_cfg=build_from_cfg)
 
-    class OptimizerHook:  # placeholder: mmdet/core/utils/dist_utils.py subclasses it at import time
-        def __init__(self, *a, **k):
-            pass
-
     def _no_checkpoint(*a, **k):   # resnet_rla.py imports these; the oracle never loads a checkpoint file
         raise RuntimeError("checkpoint loading is not part of the oracle")
 
+    # ---- runner-side shells (mmcv/runner/*): just enough for mmdet/apis/train.py::train_detector to execute in place
+    # against a runner class registered under RUNNERS (tests/test_train_detector.py). No training logic lives here.
+    class Hook:   # mmcv/runner/hooks/hook.py: every stage a no-op, *_train_* / *_val_* fall through to the generic ones
+        def before_run(self, runner): pass
+        def after_run(self, runner): pass
+        def before_epoch(self, runner): pass
+        def after_epoch(self, runner): pass
+        def before_iter(self, runner): pass
+        def after_iter(self, runner): pass
+        def before_train_epoch(self, runner): self.before_epoch(runner)
+        def before_val_epoch(self, runner): self.before_epoch(runner)
+        def after_train_epoch(self, runner): self.after_epoch(runner)
+        def after_val_epoch(self, runner): self.after_epoch(runner)
+        def before_train_iter(self, runner): self.before_iter(runner)
+        def before_val_iter(self, runner): self.before_iter(runner)
+        def after_train_iter(self, runner): self.after_iter(runner)
+        def after_val_iter(self, runner): self.after_iter(runner)
+        def every_n_epochs(self, runner, n): return (runner.epoch + 1) % n == 0 if n > 0 else False
+        def every_n_inner_iters(self, runner, n): return (runner.inner_iter + 1) % n == 0 if n > 0 else False
+        def every_n_iters(self, runner, n): return (runner.iter + 1) % n == 0 if n > 0 else False
+        def end_of_epoch(self, runner): return runner.inner_iter + 1 == len(runner.data_loader)
+        def is_last_epoch(self, runner): return runner.epoch + 1 == runner._max_epochs
+        def is_last_iter(self, runner): return runner.iter + 1 == runner._max_iters
+
+    class OptimizerHook(Hook):   # also subclassed by mmdet/core/utils/dist_utils.py at import time
+        def __init__(self, grad_clip=None, *a, **k):
+            self.grad_clip = grad_clip
+
+    class Fp16OptimizerHook(OptimizerHook):
+        pass
+
+    class DistSamplerSeedHook(Hook):
+        def before_epoch(self, runner):
+            s = getattr(runner.data_loader, "sampler", None)
+            if hasattr(s, "set_epoch"):
+                s.set_epoch(runner.epoch)
+
+    class EpochBasedRunner:   # isinstance() target of train_detector (:167)
+        pass
+
+    HOOKS = Registry("hook")
+    RUNNERS = Registry("runner")
+
+    def build_runner(cfg, default_args=None):   # mmcv/runner/builder.py
+        return build_from_cfg(cfg, RUNNERS, default_args=default_args)
+
+    def build_optimizer(model, cfg):
+        """mmcv DefaultOptimizerConstructor for what the fcos_semi configs use (configs/fcos_semi/*.py:179-182):
+        torch.optim.<type> with one param group per parameter when paramwise_cfg is given; bias_lr_mult /
+        bias_decay_mult apply to `.bias` of non-norm layers; parameters with requires_grad=False keep the defaults."""
+        cfg = dict(cfg)
+        paramwise = cfg.pop("paramwise_cfg", None)
+        cfg.pop("constructor", None)
+        cls = getattr(torch.optim, cfg.pop("type"))
+        if hasattr(model, "module"):
+            model = model.module
+        if not paramwise:
+            return cls(model.parameters(), **cfg)
+        groups = []
+        for name, p in model.named_parameters():
+            g = {"params": [p]}
+            is_norm = any(t in name for t in (".gn.", ".bn", "downsample.1.", "stage_bns."))
+            if p.requires_grad and name.endswith(".bias") and not is_norm:
+                g["lr"] = cfg["lr"] * paramwise.get("bias_lr_mult", 1.0)
+                if cfg.get("weight_decay") is not None:
+                    g["weight_decay"] = cfg["weight_decay"] * paramwise.get("bias_decay_mult", 1.0)
+            groups.append(g)
+        return cls(groups, **cfg)
+
     mmcv.runner = mod("mmcv.runner", BaseModule=BaseModule, Sequential=Sequential, ModuleList=ModuleList,
                       force_fp32=_identity_decorator, auto_fp16=_identity_decorator, OptimizerHook=OptimizerHook,
-                      load_checkpoint=_no_checkpoint, load_state_dict=_no_checkpoint)
+                      load_checkpoint=_no_checkpoint, load_state_dict=_no_checkpoint, Hook=Hook, HOOKS=HOOKS,
+                      RUNNERS=RUNNERS, build_runner=build_runner, build_optimizer=build_optimizer,
+                      EpochBasedRunner=EpochBasedRunner, Fp16OptimizerHook=Fp16OptimizerHook,
+                      DistSamplerSeedHook=DistSamplerSeedHook)
+    sys.modules["mmcv.runner.builder"] = mod("mmcv.runner.builder", RUNNERS=RUNNERS, build_runner=build_runner)
+
+    class _Wrap(nn.Module):   # mmcv/parallel: MMDataParallel / MMDistributedDataParallel keep the model in .module
+        def __init__(self, module, device_ids=None, **kw):
+            super().__init__()
+            self.module = module
+            self.device_ids = device_ids
+
+        def train_step(self, *a, **k):
+            return self.module.train_step(*a, **k)
+
+        def forward(self, *a, **k):
+            return self.module(*a, **k)
+
+    class DataContainer:
+        def __init__(self, data, stack=False, padding_value=0, cpu_only=False, pad_dims=2):
+            self.data, self.stack, self.cpu_only = data, stack, cpu_only
+
+    mmcv.parallel = mod("mmcv.parallel", MMDataParallel=_Wrap, MMDistributedDataParallel=_Wrap,
+                        DataContainer=DataContainer, is_module_wrapper=lambda m: isinstance(m, _Wrap))
 
     def _no_cuda_focal(*a, **k):
         raise RuntimeError("mmcv.ops.sigmoid_focal_loss is CUDA-only; the CPU oracle uses py_sigmoid_focal_loss")

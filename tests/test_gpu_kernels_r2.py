@@ -224,8 +224,9 @@ def test_predictor_fp32_output_identical_inputs():
 
 
 def test_gn_stats_epilogue_identical_inputs():
-    """GroupNorm statistics accumulated by the conv epilogue (fp64 atomics on the bf16-rounded output), several
-    segments in one launch incl. a map smaller than one tile and a tile that straddles two images."""
+    """GroupNorm statistics accumulated by the conv epilogue (fp64 atomics over per-tile fp32 partial sums of the fp32
+    conv + bias values, i.e. BEFORE the bf16 rounding of the stored map), several segments in one launch incl. a map
+    smaller than one tile and a tile that straddles two images."""
     from dsl_b200 import _lib as L
     from dsl_b200.engine import ConvPlan
     g = torch.Generator().manual_seed(12)
@@ -247,9 +248,11 @@ def test_gn_stats_epilogue_identical_inputs():
         ref = F.conv2d(x.to(DEV), w.to(DEV), padding=1) + bias.view(1, -1, 1, 1)
         assert _rel(y.permute(0, 3, 1, 2).float(), ref) < 4e-3
         N = x.shape[0]
-        yg = y.double().view(N, -1, 32, 8)
+        yg = ref.permute(0, 2, 3, 1).double().reshape(N, -1, 32, 8)
         s1, s2 = yg.sum(dim=(1, 3)), (yg * yg).sum(dim=(1, 3))
-        assert _rel(stats[:, :, 0], s1) < 1e-5 and _rel(stats[:, :, 1], s2) < 1e-5
+        e1, e2 = _rel(stats[:, :, 0], s1), _rel(stats[:, :, 1], s2)
+        print(f"gn stats {tuple(x.shape)}: sum rel {e1:.2e} sumsq rel {e2:.2e}")
+        assert e1 < 2e-5 and e2 < 2e-5
 
 
 def test_stem_identical_inputs():
@@ -289,13 +292,14 @@ def test_bn_grad_plan_identical_inputs():
     from dsl_b200.engine_rla import BnGradPlan
     g = torch.Generator().manual_seed(14)
     N, H, W, Ci, Co = 2, 13, 21, 128, 64
-    x = torch.randn(N, Ci, H, W, generator=g).to(DEV)
-    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(DEV)
+    # bf16-representable operands: cuDNN's TF32 products of the fp32 reference are then exact
+    x = _bf(torch.randn(N, Ci, H, W, generator=g)).to(DEV)
+    w = _bf(torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(DEV)
     gamma = (torch.rand(Co, generator=g) + 0.5).to(DEV).requires_grad_(True)
     beta = torch.zeros(Co, device=DEV, requires_grad=True)
     mean = (torch.randn(Co, generator=g) * 0.2).to(DEV)
     var = (torch.rand(Co, generator=g) + 0.5).to(DEV)
-    dy = torch.randn(N, Co, H, W, generator=g).to(DEV)
+    dy = _bf(torch.randn(N, Co, H, W, generator=g)).to(DEV)
     y = F.batch_norm(F.conv2d(x, w, padding=1), mean, var, gamma, beta, False, 0.0, 1e-5)
     y.backward(dy)
     # the folded conv's weight gradient dW' = d loss / d (W * gamma / sigma), packed [tap][O][I]

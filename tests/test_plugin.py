@@ -541,9 +541,14 @@ def test_runner_keeps_one_engine_per_batch_shape_with_shared_optimizer_state(mon
             self.B, self.H, self.W, self.kw = B, H, W, kw
             self.mom, self.lr_scale = torch.zeros(4), torch.ones(1)
             self.cur_iter, self.graphs, self.lr, self.ema_keep = 0, "captured", kw["lr"], kw["ema_keep"]
+            self.ema_in_step, self.max_grad_norm = True, kw["max_grad_norm"]
+            self.teacher = SimpleNamespace(B=kw.get("teacher_B") or B)
             z = lambda dt: torch.zeros(80, dtype=dt)  # noqa: E731
             self.post = SimpleNamespace(stat_cnt=z(torch.int64), stat_cum=z(torch.float64), stat_prev=z(torch.float64),
-                                        thr_class=z(torch.float64), class_weight=z(torch.float64), have_prev=False)
+                                        thr_class=z(torch.float64), class_weight=z(torch.float64), have_prev=False,
+                                        cand_overflow=torch.zeros(1, dtype=torch.int32))
+            for n in ("pl_gt_boxes", "pl_gt_labels", "pl_gt_off", "pl_ig_boxes", "pl_ig_off"):
+                setattr(self, n, torch.zeros(4))
             FakeEngine.made.append(self)
 
         def set_inputs(self, *a, **k):
@@ -561,7 +566,9 @@ def test_runner_keeps_one_engine_per_batch_shape_with_shared_optimizer_state(mon
     monkeypatch.setattr(R, "DSLEngine", FakeEngine)
     m = _build()
     m.store.device = torch.device("cuda")          # the stub never dereferences it
-    run = R.SemiEpochBasedRunner(m, logger=logging.getLogger("t"), max_epochs=1)
+    t = _build()
+    t.store.device = torch.device("cuda")
+    run = R.SemiEpochBasedRunner(m, logger=logging.getLogger("t"), max_epochs=1, ema_model=t)
     run.register_hook(plugin.EMAOWNHook(interval=1, mode="iteration", ratio=0.999, start_point=0))
     shapes = [(2, 128, 160), (2, 160, 128), (2, 128, 160), (2, 192, 160)]
     loader = [dict(img=torch.zeros(B, 3, H, W), img_metas=[dict(filename=f"{i}_{b}.jpg") for b in range(B)],
