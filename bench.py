@@ -33,6 +33,47 @@ METRIC = "images/sec (teacher+student step) FCOS-R50 1333x800"
 UNIT = "img/s"
 B_PER_GPU, H, W = 4, 800, 1344
 WORKLOAD = "configs[1]: FCOS-R50-FPN DSL teacher-student, synthetic COCO 1333x800 (padded 800x1344), bs=4/GPU, bf16"
+# the other BASELINE.json configs that name a throughput case (secondary lines, committed under profiles/)
+WORKLOADS = {
+    "configs1": dict(depth=50, batch=4, text=WORKLOAD),
+    "configs3": dict(depth=101, batch=2, text="configs[3]: FCOS-R101-FPN DSL teacher-student, synthetic 1333x800 (padded "
+                                              "800x1344), bs=2/GPU, bf16"),
+    "configs4": dict(depth=50, batch=4, text="configs[4]: FCOS-R50 multi-scale 800-1333 short-edge {640,800}, PatchShuffle "
+                                             "p=.5 + flip p=.5 views rendered on the device, variable padded shapes, "
+                                             "bs=4/GPU, bf16"),
+}
+
+
+def make_gt(seed, B, h, w, max_gt=20, max_ignore=5):
+    """Synthetic COCO-shaped boxes, SURVEY 8(d)'s `_demo_mm_inputs` recipe (cx, cy, bw, bh ~ U(0,1), clipped to the image;
+    labels U{0..79}; a few ignore boxes). Returns per-image lists of fp32 (n,4) / int64 (n,) / fp32 (m,4) tensors."""
+    import numpy as np
+    import torch
+    rng = np.random.RandomState(seed)
+    gts, labels, ignores = [], [], []
+    for _ in range(B):
+        def boxes(n):
+            cx, cy, bw, bh = rng.rand(4, n)
+            x1 = np.clip((cx * w - w * bw / 2), 0, w)
+            y1 = np.clip((cy * h - h * bh / 2), 0, h)
+            x2 = np.clip((cx * w + w * bw / 2), 0, w)
+            y2 = np.clip((cy * h + h * bh / 2), 0, h)
+            return torch.from_numpy(np.stack([x1, y1, x2, y2], 1).astype(np.float32))
+        n = int(rng.randint(1, max_gt + 1))
+        gts.append(boxes(n))
+        labels.append(torch.from_numpy(rng.randint(0, 80, size=n).astype(np.int64)))
+        ignores.append(boxes(int(rng.randint(0, max_ignore + 1))))
+    return gts, labels, ignores
+
+
+def confident_heads(eng, bias0=-3.0):
+    """Random-init FCOS has conv_cls bias -log(99): every score is 0.01 < score_thr 0.05 and the teacher's decode / NMS /
+    pseudo-label kernels would be timed on ZERO candidates. One class gets a trained-like bias so that every step runs
+    them on a few thousand gated candidates per image (reported as `cand_counts`)."""
+    for net in (eng.student, eng.teacher):
+        net.store["bbox_head.conv_cls.bias"][0] = bias0
+    eng.student.repack(everything=True)
+    eng.teacher.repack(everything=True)
 
 
 def parse():
@@ -43,8 +84,11 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"],
                     help="reference: the reference arithmetic on the host cores; eager-gpu: the same arithmetic under stock "
                          "torch eager + cuDNN on this GPU (SURVEY 8(d)'s GPU comparator; a baseline, not the product)")
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU (default: the benchmark config)")
-    ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS),
+                    help="configs1 (default) = the BASELINE.json headline config; configs3 = R101 bs 2; configs4 = multi-scale "
+                         "+ PatchShuffle, variable padded shapes through the runner's per-shape engine cache")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the workload's)")
+    ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--backbone", default="resnet", choices=["resnet", "rla"],
                     help="rla: RLA_ResNet, the backbone of the shipped DSL configs (not the BASELINE.json config)")
     ap.add_argument("--mix", default="bench", choices=["bench", "literal"],
@@ -54,7 +98,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-view-bench", action="store_true", help="skip the side measurement of dslb_view_images")
     ap.add_argument("--cpu-sample-hw", default="800x1344", help="HxW of the bounded CPU sample")
-    return ap.parse_args()
+    ap.add_argument("--no-ncu-traffic", action="store_true", help="skip the live ncu DRAM-traffic capture of the conv family")
+    a = ap.parse_args()
+    wl = WORKLOADS[a.workload]
+    a.batch = wl["batch"] if a.batch is None else a.batch
+    a.depth = wl["depth"] if a.depth is None else a.depth
+    a.workload_text = wl["text"] if (a.batch, a.depth) == (wl["batch"], wl["depth"]) else \
+        wl["text"] + f" [overridden: depth {a.depth}, bs {a.batch}/GPU]"
+    return a
 
 
 def peaks():
@@ -123,10 +174,48 @@ class ClockSampler:
         return out
 
 
-def ncu_traffic_per_launch():
-    """DRAM bytes per launch of the conv_igemm family (both kernels) from the committed ncu launch list of
-    `tools/profile_step.py` (same workload, `--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`),
-    summarised by tools/launch_summary.py into profiles/r01d_launches_summary.txt. None when the file is absent."""
+def ncu_traffic_per_launch(args, timeout=420):
+    """DRAM read + write bytes per launch of the conv_igemm family, measured LIVE on the benched libdslb.so: one eager
+    step of the same workload (tools/profile_step.py) under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum
+    --clock-control none`, in a process of its own after the step has been timed (bytes, not time, are taken from it).
+    Falls back to the committed launch list of an earlier build — and says so — when ncu cannot run."""
+    import csv
+    import shutil
+    out = os.path.join(tempfile.gettempdir(), f"dslb_traffic_{os.getpid()}.csv")
+    try:
+        ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+        cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum",
+               "--clock-control", "none", "-k", "regex:conv_igemm", "--csv", "--log-file", out,
+               sys.executable, os.path.join(ROOT, "tools", "profile_step.py"), "--batch", str(args.batch), "--depth",
+               str(args.depth), "--backbone", args.backbone]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        rows = [ln for ln in open(out) if ln.startswith('"')]
+        rd = csv.DictReader(rows)
+        per = {}
+        for row in rd:
+            per.setdefault(row["ID"], 0.0)
+            v = float(row["Metric Value"].replace(",", ""))
+            unit = row["Metric Unit"].lower()
+            per[row["ID"]] += v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        if not per:
+            raise RuntimeError((r.stderr or r.stdout)[-200:])
+        return dict(bytes=round(sum(per.values()) / len(per)), launches=len(per),
+                    source="live: ncu dram__bytes_read.sum + dram__bytes_write.sum over one eager step of this build "
+                           "(tools/profile_step.py), per conv_igemm launch")
+    except Exception as e:   # noqa: BLE001
+        fb = _committed_traffic()
+        if fb is not None:
+            fb["source"] += f" [live ncu capture failed: {e!r:.120}]"
+        return fb
+    finally:
+        try:
+            os.unlink(out)
+        except OSError:
+            pass
+
+
+def _committed_traffic():
     path = os.path.join(ROOT, "profiles", "r01d_launches_summary.txt")
     try:
         n_tot, b_tot = 0, 0.0
@@ -136,7 +225,7 @@ def ncu_traffic_per_launch():
                 n, mb = int(f[1]), float(f[3])
                 n_tot += n
                 b_tot += n * mb * 1e6
-        return dict(bytes=round(b_tot / n_tot), source="profiles/r01d_launches_summary.txt (ncu dram__bytes_read+write)") \
+        return dict(bytes=round(b_tot / n_tot), source="STALE: profiles/r01d_launches_summary.txt (round-1 build)") \
             if n_tot else None
     except OSError:
         return None
@@ -202,7 +291,7 @@ def run_reference(args):
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=round(1000.0 * args.batch / cb["value"], 1), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="fp32", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, note="CPU port of the reference arithmetic, same per-GPU batch, bounded "
+                config=dict(workload=args.workload_text, note="CPU port of the reference arithmetic, same per-GPU batch, bounded "
                                                     "number of steps; host cores only, no GPU"),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, wall_s=round(time.time() - t0, 1))
@@ -243,6 +332,177 @@ def run_eager_gpu(args):
         torch.cuda.empty_cache()
 
 
+def run_multiscale(args, world, rank, local):
+    """BASELINE configs[4]: multi-scale (short edge 640 / 800, long edge <= 1333) + PatchShuffle p=.5 + flip p=.5, so the
+    padded batch shape changes from step to step (SURVEY 8(d) recipe: source aspect drawn per batch from COCO-like
+    {4:3, 3:2, 16:9, 3:4} — GroupSampler keeps a batch to one orientation — scale drawn per image). Every step renders
+    the strong and weak views from uint8 sources ON THE DEVICE (dslb_view_images), picks the engine of the padded shape
+    from the runner's per-shape cache (`SemiEpochBasedRunner._engine_for`: plan + CUDA graph per (B, H, W), shared
+    weights / momentum / LR / adathres state) and runs the fused step. `value` times K steps right after W warm-up steps:
+    building + capturing the plan of a shape met for the first time is INSIDE the timed region (`captures_in_timed_region`);
+    `steady` repeats the same K-step sequence once every shape is cached. `e2e` adds the H2D of the uint8 sources from
+    pinned host memory every step and the D2H of the losses."""
+    import logging
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dsl_b200 import _lib as L
+    from dsl_b200 import plugin
+    from dsl_b200.geometry import image_view
+    from dsl_b200.runner import SemiEpochBasedRunner
+
+    B = args.batch
+    model_cfg = dict(
+        backbone=dict(type="ResNet", depth=args.depth, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                      norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="caffe"),
+        neck=dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1,
+                  add_extra_convs="on_output", num_outs=5, relu_before_extra_convs=True),
+        bbox_head=dict(type="FCOSHead", num_classes=80, in_channels=256, stacked_convs=4, feat_channels=256,
+                       strides=[8, 16, 32, 64, 128], norm_on_bbox=True, centerness_on_reg=True, dcn_on_last_conv=False,
+                       center_sampling=True, conv_bias=True, loss_weight=3.0,
+                       loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                       loss_bbox=dict(type="GIoULoss", loss_weight=1.0),
+                       loss_centerness=dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0)),
+        test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.6),
+                      max_per_img=100))
+    model, ema = plugin.FCOS(**model_cfg).cuda(), plugin.FCOS(**model_cfg).cuda()
+    with torch.no_grad():
+        model.store["bbox_head.conv_cls.bias"][0] = -3.0      # see confident_heads()
+    model._dirty()
+    ema.load_state_dict(model.state_dict())
+    runner = SemiEpochBasedRunner(model, logger=logging.getLogger("bench"), max_epochs=1, ema_model=ema)
+    runner.max_cached_shapes = 8
+    # uint8 sources of the four aspects (cv2.imread layout), pinned on the host and resident on the device
+    rng = np.random.RandomState(300 + rank)
+    src_shapes = [(480, 640), (427, 640), (360, 640), (640, 480)]
+    h_srcs = {hw: [torch.from_numpy(rng.randint(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)).pin_memory()
+                   for _ in range(B)] for hw in src_shapes}
+    d_srcs = {hw: [t.cuda() for t in v] for hw, v in h_srcs.items()}
+    scales = [(1333, 640), (1333, 800)]
+    import random
+    mean, std = (103.53, 116.28, 123.675), (1.0, 1.0, 1.0)
+
+    def draw_step(i):
+        """the draws of step i, reproducible: (source aspect, strong views, weak views, padded H, W, boxes)"""
+        np.random.seed(1000 * (rank + 1) + i)
+        random.seed(1000 * (rank + 1) + i)
+        hw = src_shapes[np.random.randint(len(src_shapes))]
+        sv, wv = [], []
+        for _ in range(B):      # Resize(multiscale 'value') -> PatchShuffle(p=.5, place U(.2,.8)) -> RandomFlip(p=.5)
+            sc = scales[np.random.randint(len(scales))]
+            ps = np.random.rand() < 0.5
+            place = 0.2 + 0.6 * np.random.rand()
+            mode = random.choice(["flip", "flop"]) if ps else None
+            flip = np.random.rand() < 0.5
+            sv.append(image_view(hw, sc, ps_mode=mode, ps_place=place, flip=flip)[0])
+            wv.append(image_view(hw, sc)[0])    # weak view of the teacher: same scale, test pipeline (no PS / flip)
+        up = lambda n: (n + 31) // 32 * 32  # noqa: E731
+        Hh, Ww = up(max(v.img_h for v in sv)), up(max(v.img_w for v in sv))
+        gts, labels, ignores = make_gt(5000 + i, B, min(v.img_h for v in sv), min(v.img_w for v in sv))
+        return hw, sv, wv, Hh, Ww, gts, labels, ignores
+
+    host_out = torch.zeros(4, dtype=torch.float32).pin_memory()
+    stats = dict(captures=0)
+
+    def step(i, from_host):
+        hw, sv, wv, Hh, Ww, gts, labels, ignores = draw_step(i)
+        n_eng = len(runner._engines)
+        eng = runner._engine_for(B, Hh, Ww)
+        fresh = len(runner._engines) != n_eng or eng.graphs is None
+        stats["captures"] += int(fresh)
+        if from_host:
+            srcs = [t.cuda(non_blocking=True) for t in h_srcs[hw]]     # ~0.9 MB per image instead of 12.9 MB fp32
+        else:
+            srcs = d_srcs[hw]
+        eng.set_images_from_sources(srcs, sv, teacher_srcs=srcs, teacher_views=wv, mean=mean, std=std, to_rgb=False)
+        eng.set_inputs(None, gts, labels, ignores)
+        losses = eng.step()
+        if from_host:
+            host_out[:3].copy_(torch.stack([losses["loss_cls"], losses["loss_bbox"], losses["loss_centerness"]]),
+                               non_blocking=False)
+        return eng
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(i0, n, from_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(i0, i0 + n):
+            eng = step(i, from_host)
+        e1.record()
+        barrier()
+        wall = time.time() - t0
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1]), eng
+
+    W_, K = max(args.warmup, 3), args.steps
+    for i in range(W_):
+        step(i, False)
+    L.reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stats["captures"] = 0
+    ms, wall_ms, eng = timed(W_, K, False)
+    cap_timed = stats["captures"]
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = L.launch_count / K
+    ms_steady, _, eng = timed(W_, K, False)           # same sequence again: every shape is cached now
+    ms_e2e, _, eng = timed(W_, K, True)
+    shapes = sorted(runner._engines)
+    torch.cuda.synchronize()
+    loss_vals = [float(v) for v in host_out[:3]]
+    assert all(np.isfinite(loss_vals)), f"non-finite losses {loss_vals}"
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    # the device clock around the K steps includes the host-side plan builds (the GPU idles meanwhile); wall agrees
+    h2d = sum(int(np.prod(hw)) * 3 for hw in src_shapes) / len(src_shapes) * B
+    flops = eng.flops_per_step()
+    line = dict(metric=METRIC, value=round(B * world * K / (ms * 1e-3), 2), unit=UNIT, n_gpus=world, steps=K, warmup=W_,
+                ms_per_step=round(ms / K, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload=args.workload_text, global_batch=B * world, per_gpu_batch=B, teacher_batch=B,
+                            parallelism=f"dp{world}", l2="working set (activations) >> 126 MB L2; no flush needed",
+                            step="views rendered on the device (dslb_view_images), teacher fwd+decode+NMS+pseudo labels, "
+                                 "student fwd+loss+bwd, grad allreduce, clip+SGD, EMA, repack; engine per padded shape",
+                            shapes=[list(k) for k in shapes], cuda_graph=True,
+                            captures_in_timed_region=cap_timed, wall_ms_per_step=round(wall_ms / K, 3)),
+                steady=dict(value=round(B * world * K / (ms_steady * 1e-3), 2), unit=UNIT,
+                            ms_per_step=round(ms_steady / K, 3), note="same K-step sequence, every shape's plan cached"),
+                e2e=dict(value=round(B * world * K / (ms_e2e * 1e-3), 2), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                         d2h_bytes_per_step=12, ms_per_step=round(ms_e2e / K, 3),
+                         note="uint8 sources H2D from pinned memory every step, plans cached"),
+                gpu_launches=int(launches * K), gpu_launches_per_step=int(launches),
+                roofline=dict(bound="tensor", kernel="whole step of the last shape's engine (conv_igemm family dominates; "
+                                                     "per-family split: the configs[1] line)",
+                              achieved=round(flops / (ms_steady / K * 1e-3) / 1e12, 1), peak=pk["tf_burst"],
+                              unit="TFLOP/s", frac=round(flops / (ms_steady / K * 1e-3) / 1e12 / pk["tf_burst"], 4),
+                              traffic=None, peak_source=pk["src"] + " burst",
+                              note="upper bound on the mix: FLOPs of the LAST step's shape over the mean steady step time"),
+                cpu_baseline=None, clocks=clocks,
+                losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]),
+                cand_counts=eng.cand_counts.tolist())
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline("640x960", args.depth, steps=2, warmup=1, batch=B, backbone=args.backbone)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -266,8 +526,9 @@ def main():
 
     from dsl_b200 import _lib as L
     from dsl_b200.trainer import DSLEngine
-    from tests.golden import inputs as GI
 
+    if args.workload == "configs4":
+        return run_multiscale(args, world, rank, local)
     literal = args.mix == "literal"
     B = 2 if literal else args.batch
     tB = 1 if literal else B
@@ -277,7 +538,8 @@ def main():
     # synthetic COCO-shaped batch in PINNED host memory (mean-subtracted pixels, caffe normalisation: std 1)
     img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
     img_t = torch.from_numpy((rng.rand(tB, 3, H, W) * 255 - 115).astype(np.float32)).pin_memory()
-    gts, labels, ignores = GI.make_gt(200 + rank, B, H, W, max_gt=20, max_ignore=5, with_ignore=True)
+    gts, labels, ignores = make_gt(200 + rank, B, H, W, max_gt=20, max_ignore=5)
+    confident_heads(eng)
     gts = [g.pin_memory() for g in gts]
     labels = [l.pin_memory() for l in labels]
     ignores = [i.pin_memory() for i in ignores]
@@ -349,15 +611,28 @@ def main():
                 f.write(json.dumps(r) + "\n")
     ck = prof["conv_igemm"]
     achieved = ck["flops"] / (ck["ms"] * 1e-3) / 1e12 if ck["ms"] > 0 else 0.0
-    traffic = ncu_traffic_per_launch()
+    traffic = None
+    if rank == 0 and world == 1 and not args.no_ncu_traffic:
+        traffic = ncu_traffic_per_launch(args)
+    # which measured peak: the timed region of this run in seconds decides (B200_PROFILING.md: the burst figure for
+    # short regions at boost clocks, the sustained one inside a long, power-capped run)
+    long_run = ms * 1e-3 >= 5.0
+    tf_peak = pk["tf_sust"] if long_run else pk["tf_burst"]
     roofline = dict(bound="tensor", kernel="conv_igemm_kernel + conv_igemm_fast4_kernel (fprop + dgrad implicit GEMM, "
                                            "tcgen05)",
-                    achieved=round(achieved, 1), peak=pk["tf_sust"], unit="TFLOP/s",
-                    frac=round(achieved / pk["tf_sust"], 4), traffic=traffic["bytes"] if traffic else None,
+                    achieved=round(achieved, 1), peak=tf_peak, unit="TFLOP/s",
+                    frac=round(achieved / tf_peak, 4), frac_of_sustained_peak=round(achieved / pk["tf_sust"], 4),
+                    frac_of_burst_peak=round(achieved / pk["tf_burst"], 4),
+                    traffic=traffic["bytes"] if traffic else None,
                     traffic_unit="bytes/launch (DRAM read+write)", traffic_source=traffic["source"] if traffic else None,
-                    peak_source=pk["src"] + " sustained",
+                    algorithmic_bytes_per_launch=round(sum(r[2] for r in prof.get("rows", [])) / max(ck["n"], 1))
+                    if prof.get("rows") else None,
+                    peak_source=pk["src"] + (" sustained (timed region >= 5 s)" if long_run else
+                                             " burst (timed region %.2f s at boost clocks)" % (ms * 1e-3)),
                     launches_per_step=ck["n"], avg_launch_us=round(1e3 * ck["ms"] / max(ck["n"], 1), 2),
                     flops_per_step=ck["flops"], share_of_step=round(ck["ms"] / prof["step_ms"], 4),
+                    share_of="the instrumented EAGER step (%.2f ms: events around every conv launch, teacher branch "
+                             "serialised), not the %.2f ms graph step" % (prof["step_ms"], ms_per_step),
                     wgrad=dict(achieved=round(prof["conv_wgrad"]["flops"] / max(prof["conv_wgrad"]["ms"], 1e-9) / 1e9,
                                               1), unit="TFLOP/s", launches_per_step=prof["conv_wgrad"]["n"],
                                share_of_step=round(prof["conv_wgrad"]["ms"] / prof["step_ms"], 4)),
@@ -389,7 +664,7 @@ def main():
 
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=3, warmup=1, batch=2, backbone=args.backbone)
+        cb = cpu_baseline(args.cpu_sample_hw, args.depth, steps=2, warmup=1, batch=args.batch, backbone=args.backbone)
 
     views = eager = None
     if world == 1 and not args.no_view_bench:
@@ -400,7 +675,7 @@ def main():
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=(WORKLOAD if args.backbone == "resnet" else WORKLOAD.replace(
+                config=dict(workload=(args.workload_text if args.backbone == "resnet" else WORKLOAD.replace(
                     "configs[1]: FCOS-R50-FPN", "variant of configs[1] with the shipped configs' RLA_ResNet backbone: FCOS-RLA_R50-FPN"))
                     if not literal else WORKLOAD.replace("configs[1]:", "reference-literal mix (SURVEY 8d) of configs[1]:").replace(
                         "bs=4/GPU", "2 student images + half-res SI copy + 1 teacher image per GPU, SI-soft loss on")
@@ -412,6 +687,7 @@ def main():
                 e2e=e2e, gpu_launches=int(launches * args.steps), gpu_launches_per_step=int(launches),
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
                 losses=dict(loss_cls=loss_vals[0], loss_bbox=loss_vals[1], loss_centerness=loss_vals[2]),
+                cand_counts=eng.cand_counts.tolist(), det_counts=eng.post.det_count.tolist(),
                 view_images=views, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
     if world > 1:

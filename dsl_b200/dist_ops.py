@@ -12,12 +12,24 @@ def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _native_avg():
+    """NCCL reduces with ncclAvg in the collective itself; gloo has no AVG op (pre-scale there)."""
+    try:
+        return dist.get_backend() == "nccl"
+    except Exception:   # noqa: BLE001
+        return False
+
+
 def allreduce_mean_(t):
-    """In place: t <- mean over ranks (what DDP leaves in .grad)."""
+    """In place: t <- mean over ranks (what DDP leaves in .grad). On NCCL the 1/world factor rides inside the
+    collective (ReduceOp.AVG): no separate pass over the 128 MB gradient."""
     w = world_size()
     if w > 1:
-        t.div_(w)
-        dist.all_reduce(t)
+        if _native_avg():
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            t.div_(w)
+            dist.all_reduce(t)
     return t
 
 
@@ -25,6 +37,8 @@ def allreduce_mean_async_(t):
     """Same as allreduce_mean_ but returns the in-flight work handle (None with one rank): call .wait() before using t."""
     w = world_size()
     if w > 1:
+        if _native_avg():
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True)
         t.div_(w)
         return dist.all_reduce(t, async_op=True)
     return None

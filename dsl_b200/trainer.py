@@ -22,6 +22,9 @@ from .engine import FCOSNet, STRIDES
 from .postprocess import TeacherPost
 
 
+_COMM_WARM = False   # the process group's NCCL communicator exists (its creation cannot be captured into a graph)
+
+
 class DSLEngine:
     def __init__(self, B, H, W, depth=50, num_classes=80, device="cuda", seed=0, lr=0.01, momentum=0.9,
                  weight_decay=1e-4, bias_lr_mult=2.0, bias_decay_mult=0.0, max_grad_norm=35.0, ema_keep=0.99,
@@ -67,6 +70,20 @@ class DSLEngine:
         self.adathres_stats = True   # accumulate the adaptive-threshold statistics in every teacher pass
         # world > 1: all-reduce the gradient in buckets as the backward produces them (DSLB_NO_BUCKETS=1: one all-reduce)
         self.bucketed = os.environ.get("DSLB_NO_BUCKETS") is None
+        # world > 1: capture the collectives INSIDE one CUDA graph (NCCL is capturable): the step is then ONE graph
+        # launch instead of six graphs with eager ncclAllReduce launches between them; the bucket all-reduces run on a
+        # communication stream forked off the backward, so they still overlap the later buckets. DSLB_GRAPH_NCCL=0: off.
+        self.graph_nccl = os.environ.get("DSLB_GRAPH_NCCL", "1") != "0"
+        self.s_comm = torch.cuda.Stream()
+        self._comm_evs = None
+        global _COMM_WARM
+        if self.world > 1 and not _COMM_WARM:
+            # first engine of the process = a point every rank reaches together: force the (lazy) communicator creation
+            # here, eagerly, on the stream the captured collectives will use
+            with torch.cuda.stream(self.s_comm):
+                dist.all_reduce(torch.zeros(1, device=self.dev))
+            torch.cuda.synchronize()
+            _COMM_WARM = True
         self._build_teacher_post()
         self.launches_per_step = None
         self.two_streams = two_streams
@@ -283,6 +300,38 @@ class DSLEngine:
                 self._allreduce_grads()
         self._phase_c()
 
+    def _step_with_collectives(self):
+        """The whole multi-rank step as one stream-ordered sequence (capturable): target assignment, the packed
+        normaliser all-reduce on the communication stream under the forward passes, backward bucket by bucket with each
+        bucket's mean all-reduce forked onto the communication stream as soon as the bucket is final, join, optimizer."""
+        main = torch.cuda.current_stream()
+        nb = len(self.student.bwd_buckets)
+        if self._comm_evs is None:
+            self._comm_evs = [torch.cuda.Event() for _ in range(2 * (nb + 1))]
+        ev = self._comm_evs
+        self._phase_t()
+        ev[0].record(main)
+        self.s_comm.wait_event(ev[0])
+        with torch.cuda.stream(self.s_comm):
+            dist_ops.allreduce_sum_(self.student.counts)
+            ev[1].record(self.s_comm)
+        self._fork_teacher()       # joined before the optimizer / EMA (the teacher branch overlaps the whole backward)
+        with torch.no_grad():
+            self.student.forward()
+        main.wait_event(ev[1])
+        for k in range(nb):
+            self._phase_b_part(k)
+            _, _, lo, hi = self._bucket_ranges()[k]
+            ev[2 + 2 * k].record(main)
+            self.s_comm.wait_event(ev[2 + 2 * k])
+            with torch.cuda.stream(self.s_comm):
+                dist_ops.allreduce_mean_(self.student.grad[lo:hi])
+                ev[3 + 2 * k].record(self.s_comm)
+        for k in range(nb):
+            main.wait_event(ev[3 + 2 * k])
+        self._join_teacher()
+        self._phase_c()
+
     def _capture(self):
         torch.cuda.synchronize()
         # The warm-up pass torch's graph capture requires must not count as a training step: every piece of state a step
@@ -303,6 +352,8 @@ class DSLEngine:
         torch.cuda.synchronize()
         if self.world == 1:
             phases = [[self._phase_a, self._phase_b, self._phase_c]]
+        elif self.bucketed and self.graph_nccl:
+            phases = [[self._step_with_collectives]]
         elif self.bucketed:
             nb = len(self.student.bwd_buckets)
             phases = [[self._phase_t], [self._phase_a_fwd]] + [[(lambda k=k: self._phase_b_part(k))] for k in range(nb)] + \
@@ -497,7 +548,7 @@ class DSLEngine:
         else:
             if self.graphs is None:
                 self._capture()
-            if self.world == 1:
+            if self.world == 1 or (self.bucketed and self.graph_nccl):
                 self.graphs[0].replay()
             elif self.bucketed:
                 self.graphs[0].replay()
@@ -603,6 +654,7 @@ class DSLEngine:
         for k in fam:
             fam[k]["n"] = int(round(fam[k]["n"]))
         out.update(fam)
+        out["rows"] = rows
         try:
             out["by_bound"] = self.split_by_bound(rows, ridge)
             for c in out["by_bound"].values():

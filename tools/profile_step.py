@@ -22,10 +22,11 @@ ap.add_argument("--hw", default="800x1344")
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--backbone", default="resnet", choices=["resnet", "rla"])
+ap.add_argument("--depth", type=int, default=50)
 a = ap.parse_args()
 H, W = (int(v) for v in a.hw.split("x"))
 B = a.batch
-eng = DSLEngine(B, H, W, depth=50, seed=0, use_graphs=False, backbone=a.backbone)
+eng = DSLEngine(B, H, W, depth=a.depth, seed=0, use_graphs=False, backbone=a.backbone)
 rng = np.random.RandomState(100)
 img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
 img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
