@@ -66,7 +66,7 @@ def make_gt(seed, B, h, w, max_gt=20, max_ignore=5):
     return gts, labels, ignores
 
 
-def confident_heads(eng, bias0=-3.0):
+def confident_heads(eng, bias0=-2.0):
     """Random-init FCOS has conv_cls bias -log(99): every score is 0.01 < score_thr 0.05 and the teacher's decode / NMS /
     pseudo-label kernels would be timed on ZERO candidates. One class gets a trained-like bias so that every step runs
     them on a few thousand gated candidates per image (reported as `cand_counts`)."""
@@ -369,7 +369,7 @@ def run_multiscale(args, world, rank, local):
                       max_per_img=100))
     model, ema = plugin.FCOS(**model_cfg).cuda(), plugin.FCOS(**model_cfg).cuda()
     with torch.no_grad():
-        model.store["bbox_head.conv_cls.bias"][0] = -3.0      # see confident_heads()
+        model.store["bbox_head.conv_cls.bias"][0] = -2.0      # see confident_heads()
     model._dirty()
     ema.load_state_dict(model.state_dict())
     runner = SemiEpochBasedRunner(model, logger=logging.getLogger("bench"), max_epochs=1, ema_model=ema)

@@ -64,6 +64,13 @@ FPROP_CASES = [
     ("3x3 stride 2 256->256 (P6)", 2, 25, 42, 256, 256, 3, 2, 1, False, False, False),
     ("3x3 256->256 mask (dgrad-shaped)", 1, 13, 21, 256, 256, 3, 1, 1, False, False, True),
     ("3x3 512->512 relu, tiny map (layer4 conv2)", 2, 7, 11, 512, 512, 3, 1, 1, False, True, False),
+    # halo-tile kernel (conv_halo.cu): several patches per CTA (ring wrap-around), resident and streamed weights,
+    # patches hanging over the right / bottom edge, every Cin x Cout combination it accepts
+    ("3x3 64->64 relu, 1100 patches (halo, resident weights)", 4, 100, 168, 64, 64, 3, 1, 1, False, True, False),
+    ("3x3 128->128 relu, 600 patches (halo, streamed weights)", 4, 100, 170, 128, 128, 3, 1, 1, False, True, False),
+    ("3x3 64->128 no relu (halo)", 3, 40, 60, 64, 128, 3, 1, 1, False, False, False),
+    ("3x3 128->64 mask (halo)", 3, 33, 41, 128, 64, 3, 1, 1, False, False, True),
+    ("3x3 64->64 no shift path, W = 8 (halo)", 5, 70, 8, 64, 64, 3, 1, 1, False, False, False),
 ]
 
 
@@ -111,6 +118,7 @@ DGRAD_CASES = [
     ("3x3 s1 128<-128 mask", 2, 25, 42, 128, 128, 3, 1, 1, False, True),
     ("3x3 s2 256<-256 zero-upsample", 2, 25, 42, 256, 256, 3, 2, 1, False, False),
     ("3x3 s2 256<-256 zero-upsample, odd map + residual", 2, 13, 21, 256, 256, 3, 2, 1, True, False),
+    ("3x3 s1 128<-128 mask, 600 patches (halo)", 4, 100, 168, 128, 128, 3, 1, 1, False, True),
 ]
 
 

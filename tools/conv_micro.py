@@ -24,6 +24,9 @@ CASES = {
     "l3_conv3_256_1024_res": (4, 50, 84, 256, 1024, 1, 1, 0, True, False, True, True),
     "l2_conv1dgrad_128_512_res_mask": (4, 100, 168, 128, 512, 1, 1, 0, True, True, False, False),
     "tower_3x3_256": (4, 100, 168, 256, 256, 3, 1, 1, False, False, False, False),
+    "l2_conv2_3x3_128": (4, 100, 168, 128, 128, 3, 1, 1, False, False, True, True),
+    "l2_conv2dgrad_3x3_128_mask": (4, 100, 168, 128, 128, 3, 1, 1, False, True, False, False),
+    "pred_cls_3x3_256_80_fp32": (4, 100, 168, 256, 80, 3, 1, 1, False, False, True, False),
     # RLA_ResNet state path at C2 / C3 (engine_rla.py): conv_out 4*planes -> 64-channel state rows, the h half of conv1,
     # recurrent_conv 3x3 on the state rows, conv1's x half with the h half as the residual operand
     "rla_c2_conv_out_256_64": (4, 200, 336, 256, 64, 1, 1, 0, False, False, False, False),
@@ -45,9 +48,10 @@ def run(name, N, H, W, Ci, Co, R, stride, pad, res, mask, affine, relu, iters=20
     plans = []
     for _ in range(nset):
         x = torch.randn(N, H, W, Ci, device=dev).to(BF)
-        y = torch.zeros(N, Ho, Wo, Co, dtype=BF, device=dev)
+        fp32 = name.endswith("fp32")
+        y = torch.zeros(N, Ho, Wo, Co, dtype=torch.float32 if fp32 else BF, device=dev)
         seg = dict(x=x, w=w, y=y, N=N, H=H, W=W, Cin=Ci, Cout=Co, cout_pad=Co, R=R, S=R, stride=stride, pad=pad, ldc=Co,
-                   relu_nch=Co if relu else 0)
+                   relu_nch=Co if relu else 0, out_fp32=int(fp32))
         if affine:
             seg.update(shift=shift)  # BN scale is folded into the packed weights, as in the engine
         if res:
