@@ -404,7 +404,7 @@ def test_runner_closes_the_teacher_student_loop_on_the_device():
     cfg["bbox_head"] = dict(cfg["bbox_head"], loss_weight=3.0, soft_weight=1.0, soft_warm_up=1)
     model, ema = plugin.FCOS(**cfg).cuda(), plugin.FCOS(**cfg).cuda()
     with torch.no_grad():
-        model.store["bbox_head.conv_cls.bias"][:3] = -1.2        # three confident classes: thousands of candidates
+        model.store["bbox_head.conv_cls.bias"][:3] = 1.5         # three confident classes: scores ~0.8 x centerness
     model._dirty()
     ema.load_state_dict(model.state_dict())
     runner = SemiEpochBasedRunner(model, logger=logging.getLogger("t"), max_epochs=1, ema_model=ema, scale_invariant=True)
@@ -458,8 +458,8 @@ def test_runner_closes_the_teacher_student_loop_on_the_device():
         # scale-invariant extra sample: the unlabeled image's lists, halved
         assert go[3] - go[2] == go[2] - go[1] and np.array_equal(r["gt"][go[2]:go[3]], wb / 2)
         assert np.array_equal(r["gl"][go[2]:go[3]], wl) and np.array_equal(r["ig"][io[2]:io[3]], wi / 2)
-        n_pl += len(wb)
-    assert n_pl > 0, "pseudo labels must have reached the student"
+        n_pl += len(wb) + len(wi)
+    assert n_pl > 0, "pseudo GT / ignore boxes must have reached the student"
     # burn-in: iteration 0 used the dataloader's boxes for both images
     go0 = rec[0]["go"].tolist()
     assert go0[2] - go0[1] == len(loader[0]["gt_bboxes"][1])
