@@ -59,6 +59,11 @@ static void resolve_driver() {
 
 int encode_tiled_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box) {
+  return encode_tiled_bf16_swz(tm, base, rank, dims, strides, box, 128);
+}
+
+int encode_tiled_bf16_swz(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                          const uint32_t* box, int swizzle_bytes) {
   std::call_once(g_once, resolve_driver);
   if (!g_tiled) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -67,7 +72,8 @@ int encode_tiled_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                        (const cuuint64_t*)dims, (const cuuint64_t*)strides, (const cuuint32_t*)box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,

@@ -38,6 +38,9 @@ int num_sms();
 // bf16 tiled tensor map (rank 2..4), 128B swizzle. dims/strides innermost first; strides in bytes for dims 1..
 int encode_tiled_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box);
+// same with the shared-memory swizzle chosen by the caller: 0 = none (dense box rows), 128 = 128B swizzle
+int encode_tiled_bf16_swz(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                          const uint32_t* box, int swizzle_bytes);
 // bf16 im2col tensor map on an NHWC tensor [N][H][W][C]: 64 channels x `pixels` output pixels per load.
 int encode_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int R, int S, int stride,
                        int pad, int pixels);

@@ -13,6 +13,9 @@
 //              bytes patch[r][2q .. 2q+8): an A row is 28 aligned sixteen-byte chunks copied verbatim; the pad tap /
 //              pad channel read real (finite) data and meet zero weights.
 //   B operand  built in shared memory by the kernel itself from the fp32 OIHW master weight x BN scale.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -234,6 +237,213 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ direct-patch stem
+// Same arithmetic, no A-tile assembly: with 8-byte pixels and stride 2, the K segment of (output pixel q, filter row r)
+// is the 64 contiguous bytes patch[r][16 q .. 16 q + 64) — consecutive pixels start 16 bytes apart and OVERLAP. That is
+// exactly the un-swizzled K-major canonical layout of tcgen05 (a core matrix = 8 rows x 16 bytes with rows 16 bytes
+// apart) read with LBO = 16 (next 8-element K chunk) and SBO = 128 (next 8 rows): the MMA reads the patch row in
+// place. Per tile: one elected thread TMA-loads the 7 x 264-pixel patch (two boxes of 8 x 132 x 7, out-of-bounds rows /
+// pixel pairs zero-filled = the conv padding), another issues 14 UMMAs (7 filter rows x K 32), 8 epilogue warps turn
+// the TMEM accumulator into the NHWC bf16 row segment (shift + ReLU -> swizzled slab -> TMA store, clipped at Wo).
+// No CTA-wide barrier inside the tile loop (the old kernel spent 45 % of its stall samples at its two).
+constexpr int S2_STAGES = 4;
+constexpr int S2_PATCH = 7 * ST_ROWB;                                  // 14 784 bytes
+constexpr int S2_PATCH_STRIDE = (S2_PATCH + 1023) / 1024 * 1024;       // 15 360
+constexpr int S2_SMEM = 1024 + S2_STAGES * S2_PATCH_STRIDE + ST_B_BYTES + 2 * 16384 + 64 * 4 + 256;
+
+struct alignas(64) Stem2Params {
+  CUtensorMap tmX;   // NHWC4 image as [N][H][W/2][8 bf16]: box 8 x 132 x 7 x 1, no swizzle
+  CUtensorMap tmY;   // output [N*Ho][Wo][64]: box 64 x 128 x 1, 128B swizzle
+  const float* w;
+  const float* bn_gamma;
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  float eps;
+  int Ho, qsegs, ntiles;
+};
+
+__device__ __forceinline__ uint64_t make_sdesc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void tma_load_4d_tile(const void* desc, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1) stem2_conv_kernel(const __grid_constant__ Stem2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* const sPatch = smem;
+  uint8_t* const sB = sPatch + S2_STAGES * S2_PATCH_STRIDE;
+  uint8_t* const sOut = sB + ST_B_BYTES;              // 2 slabs (double-buffered TMA stores)
+  float* const sShift = reinterpret_cast<float*>(sOut + 2 * 16384);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(sShift + 64);
+  uint64_t* const full = bars;            // [S2_STAGES]
+  uint64_t* const empty = bars + 4;       // [S2_STAGES]
+  uint64_t* const tfull = bars + 8;       // [2]
+  uint64_t* const tempty = bars + 10;     // [2]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = P.ntiles;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S2_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  // B operand [4 K-chunks][64 out][64 k] bf16, K-major, 128B swizzle, BN scale folded in; k' = r*32 + s'*4 + c
+  for (int e = tid; e < 64 * 64 * ST_KC; e += blockDim.x) {
+    const int o = e / (64 * ST_KC), k = e - o * (64 * ST_KC);
+    const int r = k >> 5, s = ((k & 31) >> 2) - 1, c = k & 3;   // tap slot 0 is the pad tap
+    float v = 0.f;
+    if (r < 7 && s >= 0 && c < 3) {
+      const float sc = P.bn_gamma[o] / sqrtf(P.bn_var[o] + P.eps);
+      v = P.w[((o * 3 + c) * 7 + r) * 7 + s] * sc;
+    }
+    const int kc = k >> 6, c16 = (k & 63) >> 3;
+    *reinterpret_cast<__nv_bfloat16*>(sB + kc * 8192 + o * 128 + ((c16 ^ (o & 7)) << 4) + (k & 7) * 2) =
+        __float2bfloat16_rn(v);
+  }
+  if (tid < 64) {
+    const float sc = P.bn_gamma[tid] / sqrtf(P.bn_var[tid] + P.eps);
+    sShift[tid] = P.bn_beta[tid] - P.bn_mean[tid] * sc;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int qs = t % P.qsegs;
+        const int np = t / P.qsegs;          // n * Ho + p
+        const int p = np % P.Ho, n = np / P.Ho;
+        const int h0 = 2 * p - 3, pair0 = qs * 128 - 2;   // first pixel 2*q0 - 4 = pair index q0 - 2
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], S2_PATCH);
+        // the box is [7 rows][132 pairs][16 B]: one load (132 <= 256 box limit)
+        tma_load_4d_tile(&P.tmX, &full[st], sPatch + st * S2_PATCH_STRIDE, 0, pair0, h0, n);
+        if (++st == S2_STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t b_base = smem_u32(sB);
+      int st = 0, it = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sPatch + st * S2_PATCH_STRIDE);
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {      // k = 2 r + kk: filter row r, K elements [16 kk, 16 kk + 16) of its 32
+          const int r = k >> 1, kk = k & 1;
+          const uint64_t ad = make_sdesc_noswz(a_base + r * ST_ROWB + kk * 32, 16, 128);
+          const uint64_t bd = make_sdesc(b_base + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem_base + acc * 64, ad, bd, idesc, k != 0);
+        }
+        umma_commit(&empty[st]);
+        umma_commit(&tfull[acc]);
+        if (++st == S2_STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // 8 epilogue warps: quadrant ew owns pixels [32 ew, 32 ew + 32); half eh owns channels [32 eh, 32 eh + 32)
+    const int ew = warp & 3, eh = (warp - 4) >> 2;
+    const int et = ew * 32 + lane;
+    const bool leader = (warp == 4 && lane == 0);
+    int it = 0;
+    bool pending = false;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      uint8_t* const slab = sOut + (it & 1) * 16384;
+      const uint32_t row = smem_u32(slab) + et * 128;
+      // the store issued two tiles ago read this slab: drained before anyone overwrites it
+      if (leader && pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 64 + eh * 32;
+      uint32_t ra[16], rb[16];
+      tmem_ld16(taddr, ra);
+      tmem_ld16(taddr + 16, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {        // four 16-byte slots of 8 channels
+        const uint32_t* src = g < 2 ? ra + 8 * g : rb + 8 * (g - 2);
+        const float* sh = sShift + eh * 32 + 8 * g;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = __uint_as_float(src[2 * j]) + sh[2 * j], v1 = __uint_as_float(src[2 * j + 1]) + sh[2 * j + 1];
+          asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(v1), "f"(v0));
+        }
+        const uint32_t slot = (uint32_t)(eh * 4 + g);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((slot ^ (uint32_t)(et & 7)) << 4)), "r"(o[0]),
+                     "r"(o[1]), "r"(o[2]), "r"(o[3])
+                     : "memory");
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (leader) {
+        const int qs = t % P.qsegs;
+        tma_store_3d(&P.tmY, slab, 0, qs * 128, t / P.qsegs);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        pending = true;
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 }  // namespace dslb
 
 using namespace dslb;
@@ -260,6 +470,39 @@ extern "C" int dslb_stem_conv(const float* img, const float* w, const float* bn_
   const long long ntiles = (long long)N * Ho * ((Wo + 127) / 128);
   DSLB_CHECK_ARG(ntiles < (1ll << 30) && (long long)H * W < (1ll << 31), "dslb_stem_conv: image too large");
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+  static const bool old_stem = getenv("DSLB_OLD_STEM") != nullptr;
+  if (!old_stem && W % 2 == 0 && ((uintptr_t)out % 16) == 0) {
+    // direct-patch kernel: the image as [N][H][W/2][2 px x 4 ch] (16-byte innermost rows, no swizzle)
+    Stem2Params P;
+    memset(&P, 0, sizeof(P));
+    const uint64_t xd[4] = {8, (uint64_t)(W / 2), (uint64_t)H, (uint64_t)N};
+    const uint64_t xs[3] = {16, (uint64_t)W * 8, (uint64_t)H * W * 8};
+    const uint32_t xb[4] = {8, ST_PW / 2, 7, 1};
+    int rc = encode_tiled_bf16_swz(&P.tmX, workspace, 4, xd, xs, xb, 0);
+    if (rc != DSLB_OK) return rc;
+    const uint64_t yd[3] = {64, (uint64_t)Wo, (uint64_t)N * Ho};
+    const uint64_t ys[2] = {128, (uint64_t)Wo * 128};
+    const uint32_t yb[3] = {64, 128, 1};
+    rc = encode_tiled_bf16(&P.tmY, out, 3, yd, ys, yb);
+    if (rc != DSLB_OK) return rc;
+    P.w = w;
+    P.bn_gamma = bn_gamma;
+    P.bn_beta = bn_beta;
+    P.bn_mean = bn_mean;
+    P.bn_var = bn_var;
+    P.eps = eps;
+    P.Ho = Ho;
+    P.qsegs = (Wo + 127) / 128;
+    P.ntiles = (int)ntiles;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      DSLB_CHECK_CUDA(cudaFuncSetAttribute(stem2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+      attr2_set = true;
+    }
+    stem2_conv_kernel<<<grid, 384, S2_SMEM, (cudaStream_t)stream>>>(P);
+    DSLB_CHECK_CUDA(cudaGetLastError());
+    return DSLB_OK;
+  }
   stem_conv_kernel<<<grid, ST_NT, ST_SMEM, (cudaStream_t)stream>>>((const uint2*)workspace, w, bn_gamma, bn_beta, bn_mean,
                                                                   bn_var, eps, (__nv_bfloat16*)out, N, H, W, Ho, Wo);
   DSLB_CHECK_CUDA(cudaGetLastError());
