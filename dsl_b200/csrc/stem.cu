@@ -243,17 +243,21 @@ stem_conv_kernel(const uint2* __restrict__ x4, const float* __restrict__ w, cons
 // is the 64 contiguous bytes patch[r][16 q .. 16 q + 64) — consecutive pixels start 16 bytes apart and OVERLAP. That is
 // exactly the un-swizzled K-major canonical layout of tcgen05 (a core matrix = 8 rows x 16 bytes with rows 16 bytes
 // apart) read with LBO = 16 (next 8-element K chunk) and SBO = 128 (next 8 rows): the MMA reads the patch row in
-// place. Per tile: one elected thread TMA-loads the 7 x 264-pixel patch (two boxes of 8 x 132 x 7, out-of-bounds rows /
-// pixel pairs zero-filled = the conv padding), another issues 14 UMMAs (7 filter rows x K 32), 8 epilogue warps turn
+// place. Per tile: one elected thread TMA-loads the 7-row patch (one box of 7 rows x 18 blocks of 16 pixels, out-of-bounds
+// rows / blocks zero-filled = the conv padding), another issues 14 UMMAs (7 filter rows x K 32), 8 epilogue warps turn
 // the TMEM accumulator into the NHWC bf16 row segment (shift + ReLU -> swizzled slab -> TMA store, clipped at Wo).
 // No CTA-wide barrier inside the tile loop (the old kernel spent 45 % of its stall samples at its two).
 constexpr int S2_STAGES = 4;
-constexpr int S2_PATCH = 7 * ST_ROWB;                                  // 14 784 bytes
-constexpr int S2_PATCH_STRIDE = (S2_PATCH + 1023) / 1024 * 1024;       // 15 360
+// patch rows are loaded as 18 boxes of 16 pixels (128-byte TMA rows: the TMA unit's cost is per row, and 16-byte rows —
+// one pixel pair — made the load the bottleneck), starting at the 16-pixel boundary 12 pixels before the patch
+constexpr int S2_ROWB = 18 * 128;                                      // 2 304 bytes per patch row
+constexpr int S2_LEAD = 12 * 8;                                        // bytes in front of the first patch pixel
+constexpr int S2_PATCH = 7 * S2_ROWB;                                  // 16 128 bytes
+constexpr int S2_PATCH_STRIDE = (S2_PATCH + 1023) / 1024 * 1024;       // 16 384
 constexpr int S2_SMEM = 1024 + S2_STAGES * S2_PATCH_STRIDE + ST_B_BYTES + 2 * 16384 + 64 * 4 + 256;
 
 struct alignas(64) Stem2Params {
-  CUtensorMap tmX;   // NHWC4 image as [N][H][W/2][8 bf16]: box 8 x 132 x 7 x 1, no swizzle
+  CUtensorMap tmX;   // NHWC4 image as [N][H][W/16][64 bf16 = 16 px]: box 64 x 18 x 7 x 1, no swizzle
   CUtensorMap tmY;   // output [N*Ho][Wo][64]: box 64 x 128 x 1, 128B swizzle
   const float* w;
   const float* bn_gamma;
@@ -348,11 +352,10 @@ __global__ void __launch_bounds__(384, 1) stem2_conv_kernel(const __grid_constan
         const int qs = t % P.qsegs;
         const int np = t / P.qsegs;          // n * Ho + p
         const int p = np % P.Ho, n = np / P.Ho;
-        const int h0 = 2 * p - 3, pair0 = qs * 128 - 2;   // first pixel 2*q0 - 4 = pair index q0 - 2
+        const int h0 = 2 * p - 3, blk0 = qs * 16 - 1;   // first pixel 2*q0 - 4 lies 12 pixels into block 16*qs - 1
         mbar_wait(&empty[st], ph ^ 1);
         mbar_expect_tx(&full[st], S2_PATCH);
-        // the box is [7 rows][132 pairs][16 B]: one load (132 <= 256 box limit)
-        tma_load_4d_tile(&P.tmX, &full[st], sPatch + st * S2_PATCH_STRIDE, 0, pair0, h0, n);
+        tma_load_4d_tile(&P.tmX, &full[st], sPatch + st * S2_PATCH_STRIDE, 0, blk0, h0, n);
         if (++st == S2_STAGES) {
           st = 0;
           ph ^= 1;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(384, 1) stem2_conv_kernel(const __grid_constan
 #pragma unroll
         for (int k = 0; k < 14; ++k) {      // k = 2 r + kk: filter row r, K elements [16 kk, 16 kk + 16) of its 32
           const int r = k >> 1, kk = k & 1;
-          const uint64_t ad = make_sdesc_noswz(a_base + r * ST_ROWB + kk * 32, 16, 128);
+          const uint64_t ad = make_sdesc_noswz(a_base + r * S2_ROWB + S2_LEAD + kk * 32, 16, 128);
           const uint64_t bd = make_sdesc(b_base + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
           umma_bf16(tmem_base + acc * 64, ad, bd, idesc, k != 0);
         }
@@ -471,13 +474,13 @@ extern "C" int dslb_stem_conv(const float* img, const float* w, const float* bn_
   DSLB_CHECK_ARG(ntiles < (1ll << 30) && (long long)H * W < (1ll << 31), "dslb_stem_conv: image too large");
   const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
   static const bool old_stem = getenv("DSLB_OLD_STEM") != nullptr;
-  if (!old_stem && W % 2 == 0 && ((uintptr_t)out % 16) == 0) {
-    // direct-patch kernel: the image as [N][H][W/2][2 px x 4 ch] (16-byte innermost rows, no swizzle)
+  if (!old_stem && W % 16 == 0 && ((uintptr_t)out % 16) == 0) {
+    // direct-patch kernel: the image as [N][H][W/16][16 px x 4 ch] (128-byte innermost rows, no swizzle)
     Stem2Params P;
     memset(&P, 0, sizeof(P));
-    const uint64_t xd[4] = {8, (uint64_t)(W / 2), (uint64_t)H, (uint64_t)N};
-    const uint64_t xs[3] = {16, (uint64_t)W * 8, (uint64_t)H * W * 8};
-    const uint32_t xb[4] = {8, ST_PW / 2, 7, 1};
+    const uint64_t xd[4] = {64, (uint64_t)(W / 16), (uint64_t)H, (uint64_t)N};
+    const uint64_t xs[3] = {128, (uint64_t)W * 8, (uint64_t)H * W * 8};
+    const uint32_t xb[4] = {64, 18, 7, 1};
     int rc = encode_tiled_bf16_swz(&P.tmX, workspace, 4, xd, xs, xb, 0);
     if (rc != DSLB_OK) return rc;
     const uint64_t yd[3] = {64, (uint64_t)Wo, (uint64_t)N * Ho};
