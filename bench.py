@@ -349,7 +349,7 @@ def run_multiscale(args, world, rank, local):
     import torch.distributed as dist
 
     from dsl_b200 import _lib as L
-    from dsl_b200 import plugin
+    from dsl_b200 import dist_ops, plugin
     from dsl_b200.geometry import image_view
     from dsl_b200.runner import SemiEpochBasedRunner
 
@@ -463,9 +463,7 @@ def run_multiscale(args, world, rank, local):
     loss_vals = [float(v) for v in host_out[:3]]
     assert all(np.isfinite(loss_vals)), f"non-finite losses {loss_vals}"
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        dist_ops.shutdown(*runner._engines.values())
         return
     pk = peaks()
     # the device clock around the K steps includes the host-side plan builds (the GPU idles meanwhile); wall agrees
@@ -498,13 +496,14 @@ def run_multiscale(args, world, rank, local):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline("640x960", args.depth, steps=2, warmup=1, batch=B, backbone=args.backbone)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    dist_ops.shutdown(*runner._engines.values())
 
 
 def main():
     args = parse()
+    if os.environ.get("DSLB_HANG_DUMP"):      # debugging aid: dump every thread's stack if the run is still going then
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["DSLB_HANG_DUMP"]), exit=True)
     if args.impl == "reference":
         return run_reference(args)
     if args.impl == "eager-gpu":
@@ -525,6 +524,7 @@ def main():
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     from dsl_b200 import _lib as L
+    from dsl_b200 import dist_ops
     from dsl_b200.trainer import DSLEngine
 
     if args.workload == "configs4":
@@ -660,9 +660,7 @@ def main():
         roofline["by_bound"] = dict(error=repr(e))
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        dist_ops.shutdown(eng)
         return
 
     cb = None
@@ -696,9 +694,7 @@ def main():
                 det_counts=dict(first_step=det0, last_step=eng.post.det_count.tolist()),
                 view_images=views, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    dist_ops.shutdown(eng)
 
 
 if __name__ == "__main__":

@@ -71,3 +71,35 @@ def reduce_log_vars(log_vars):
         vals = vals.clone()
         dist.all_reduce(vals.div_(w))
     return type(log_vars)(zip(keys, vals.tolist()))
+
+
+def shutdown(*engines, timeout=20.0):
+    """End of a multi-rank run. CUDA graphs that captured NCCL work (DSLEngine's one-graph step) must be released BEFORE
+    the communicator: ProcessGroupNCCL's destructor otherwise waits forever on work it can no longer see complete
+    (measured: both ranks stuck in destroy_process_group). Destroys the graphs, synchronises, barriers, and tears the
+    process group down under a watchdog — if NCCL still refuses to die the process exits cleanly instead of hanging."""
+    import gc
+    import os
+    import sys
+    import threading
+    for e in engines:
+        if e is not None:
+            e.graphs = None
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    try:
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    except Exception:   # noqa: BLE001
+        pass
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)

@@ -80,4 +80,5 @@ engA.step() if rank == 0 else engB.step()
 torch.cuda.synchronize()
 if rank == 0:
     print("rank-local capture OK")
-dist.destroy_process_group()
+from dsl_b200 import dist_ops as _D  # noqa: E402
+_D.shutdown(engA, engB if rank == 1 else None)

@@ -108,6 +108,5 @@ print(f"rank {rank}: {len(evs)} GPU activities over {n} step(s); span {end / n:.
 print("busy us/step per stream:", {str(k): round(v / n, 1) for k, v in sorted(by_stream.items(), key=lambda kv: -kv[1])})
 for k, (us, c) in sorted(by_name.items(), key=lambda kv: -kv[1][0])[:22]:
     print(f"  {us / n:9.1f} us/step  x{c / n:6.1f}  {k}")
-if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+from dsl_b200 import dist_ops as _D  # noqa: E402
+_D.shutdown(eng)
