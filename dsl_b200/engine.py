@@ -860,6 +860,10 @@ class FCOSNet:
             name = f"layer{li + 1}.{bi}"
             if idx == stage_last[li] and li == 2:
                 self._emit_bucket((self.bb_prefix + "layer4.",))   # 60 MB of gradients are final once layer4 is done
+            if idx == stage_last[li] and li == 1 and self.parts == "all":
+                # layer3 (28 MB) is final before layer2's backward starts: only layer2's 5 MB travel after the backward's
+                # end (N=8 timeline, profiles/r02_timeline_n8.txt: the last bucket's all-reduce is the exposed one)
+                self._emit_bucket((self.bb_prefix + "layer3.",))
             if idx == stage_last[li]:
                 if li == 3:
                     blk["M"] = self.gc[2]  # already masked by the lateral dgrad epilogue

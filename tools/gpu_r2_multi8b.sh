@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+set -u
+O=gpurun_out/r2m8b
+mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519"
+run() { S=$(date +%s); "${@:2}" > $O/$1.json 2> $O/$1.err; echo "$1 rc=$? $(( $(date +%s) - S ))s"; }
+run bench_c1_n1 timeout 120 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-view-bench --no-ncu-traffic
+run bench_c1_n8 timeout 150 $TR bench.py --gpus 8 --steps 30 --warmup 5
+run bench_c1_n8_simple timeout 150 env NCCL_PROTO=Simple $TR bench.py --gpus 8 --steps 30 --warmup 5
+run bench_c1_n8_ll128 timeout 150 env NCCL_PROTO=LL128 $TR bench.py --gpus 8 --steps 30 --warmup 5
+run bench_c1_n8_nvls timeout 150 env NCCL_ALGO=NVLS $TR bench.py --gpus 8 --steps 30 --warmup 5
+for f in bench_c1_n1 bench_c1_n8 bench_c1_n8_simple bench_c1_n8_ll128 bench_c1_n8_nvls; do python - "$O/$f.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], d["value"], d["ms_per_step"], d["e2e"]["value"], d["clocks"])
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e); print(open(sys.argv[1].replace(".json", ".err")).read()[-600:])
+PY
+done
