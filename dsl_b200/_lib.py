@@ -144,6 +144,8 @@ _proto("dslb_upsample_add_bwd", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_relu_family", I, VP, VP, VP, LL, I, VP)
 _proto("dslb_gn_apply_relu", I, C.POINTER(GnSeg), I, I, I, F, VP)
 _proto("dslb_gn_apply_relu_tab", I, C.POINTER(GnSeg), I, I, I, F, VP, I, VP)
+_proto("dslb_gn_apply_relu_split", I, C.POINTER(GnSeg), I, I, I, F, VP)
+_proto("dslb_bf16_to_split", I, VP, VP, LL, I, VP)
 _proto("dslb_gn_bwd_blocks", I, C.POINTER(GnSeg), I)
 _proto("dslb_gn_bwd_plan", I, C.POINTER(GnSeg), I, VP)
 _proto("dslb_gn_bwd", I, C.POINTER(GnSeg), I, I, I, F, VP, I, VP)

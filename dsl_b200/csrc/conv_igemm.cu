@@ -979,8 +979,8 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
       }
       any_aux = true;
     }
-    if (s.gn_stats && !d.staged) {
-      set_error("conv seg %d: gn_stats needs a bf16, non-scattered output", i);
+    if (s.gn_stats && s.scatter2) {   // (fp32 direct-store outputs accumulate the statistics in the same chunk loop)
+      set_error("conv seg %d: gn_stats needs a non-scattered output", i);
       delete h;
       return DSLB_EINVAL;
     }

@@ -712,6 +712,84 @@ extern "C" int dslb_gn_apply_relu_tab(const dslb_gn_seg_t* segs, int nseg, int C
   LAUNCH_CHECK();
 }
 
+namespace dslb {
+// Split-bf16 ("bf16x3") operands of the accurate FCOSHead mode: a value v travels as hi = bf16(v), lo = bf16(v - hi) and a
+// conv over the 3C-channel row [hi | lo | hi] against the weights [w_hi | w_hi | w_lo] accumulates
+// hi*w_hi + lo*w_hi + hi*w_lo in fp32 on the tensor core: operand precision ~2^-17 instead of bf16's 2^-9.
+__device__ __forceinline__ void split_store8(const float (&v)[8], __nv_bfloat16* row, int C, int c0) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+    lo[e] = v[e] - hi[e];
+  }
+  const uint4 h = pack8(hi), l = pack8(lo);
+  *reinterpret_cast<uint4*>(row + c0) = h;
+  *reinterpret_cast<uint4*>(row + C + c0) = l;
+  *reinterpret_cast<uint4*>(row + 2 * C + c0) = h;
+}
+
+// y[3C] = split(relu((x - mean) * rstd * gamma + beta)) with x in FP32 (the accurate mode keeps the tower maps in fp32)
+__global__ void gn_apply_relu_split_kernel(const __grid_constant__ GnParams P) {
+  const int cv = P.C / 8;
+  const int G = P.C / P.cpg;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P.total; t += (long long)gridDim.x * blockDim.x) {
+    const GnSeg& s = P.seg[gn_find(P, t)];
+    const long long tl = t - s.work_begin;
+    const int c8 = (int)(tl % cv);
+    const long long pix = tl / cv;
+    const int n = (int)(pix / s.HW);
+    const float4 mr = __ldg(s.mr + n * G + (c8 * 8) / P.cpg);
+    const float* xp = reinterpret_cast<const float*>(s.x) + pix * P.C + c8 * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xp)), b = __ldg(reinterpret_cast<const float4*>(xp) + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float ga = __ldg(s.gamma + c8 * 8 + e) * mr.y;
+      v[e] = fmaxf(fmaf(x[e], ga, __ldg(s.beta + c8 * 8 + e) - mr.x * ga), 0.f);
+    }
+    split_store8(v, s.y + pix * 3 * P.C, P.C, c8 * 8);
+  }
+}
+
+// bf16 map [npix][C] -> [npix][3C] = [x | 0 | x]   (a bf16 value is its own hi part)
+__global__ void bf16_to_split_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long npix,
+                                     int C) {
+  const int cv = C / 8;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < npix * cv; t += (long long)gridDim.x * blockDim.x) {
+    const long long pix = t / cv;
+    const int c0 = (int)(t - pix * cv) * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * C + c0));
+    __nv_bfloat16* row = y + pix * 3 * C;
+    *reinterpret_cast<uint4*>(row + c0) = v;
+    *reinterpret_cast<uint4*>(row + C + c0) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row + 2 * C + c0) = v;
+  }
+}
+}  // namespace dslb
+
+extern "C" int dslb_gn_apply_relu_split(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream) {
+  GnParams P;
+  int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
+  if (rc != DSLB_OK) return rc;
+  int maxN = 1;
+  for (int i = 0; i < nseg; ++i) maxN = segs[i].N > maxN ? segs[i].N : maxN;
+  const int nfin = nseg * maxN * groups;
+  gn_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  gn_apply_relu_split_kernel<<<grid_for(P.total, 256), 256, 0, (cudaStream_t)stream>>>(P);
+  LAUNCH_CHECK();
+}
+
+extern "C" int dslb_bf16_to_split(const void* x, void* y, long long npix, int C, void* stream) {
+  DSLB_CHECK_ARG(x && y && npix >= 0 && C % 8 == 0, "dslb_bf16_to_split: bad arguments");
+  if (npix == 0) return DSLB_OK;
+  bf16_to_split_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
+                                                                                      (__nv_bfloat16*)y, npix, C);
+  LAUNCH_CHECK();
+}
+
 extern "C" int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream) {
   GnParams P;
   int rc = fill_gn_params(P, segs, nseg, C, groups, eps);

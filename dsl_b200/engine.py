@@ -234,7 +234,7 @@ class FCOSNet:
     def __init__(self, B, H, W, depth=50, num_classes=80, train=True, store=None, device="cuda", seed=0,
                  loss_weight=1.0, soft_weight=0.0, center_sampling=True, radius=1.5, norm_on_bbox=True,
                  max_boxes=1024, parity_outputs=False, parts="all", level_sizes=None, strides=STRIDES,
-                 regress_ranges=REGRESS_RANGES, backbone="resnet"):
+                 regress_ranges=REGRESS_RANGES, backbone="resnet", head_precision="bf16"):
         """parts="all": backbone + FPN + head on a (B, 3, H, W) image. parts="head": FCOSHead only, on caller-filled
         FPN maps self.p[l] of `level_sizes` (the standalone HEADS-registry module); backward then ends at self.dp.
         parts="backbone": ResNet only (BACKBONES module): stage outputs in self.stage_out, backward seeded by the caller
@@ -246,6 +246,10 @@ class FCOSNet:
         # layers = RESNET_BLOCKS[depth]; see engine_rla.py
         assert backbone in ("resnet", "rla")
         self.backbone = backbone
+        # "bf16x3": the accurate inference mode of the FCOSHead (split-bf16 operands, fp32 tower maps; _build_head_split)
+        assert head_precision in ("bf16", "bf16x3")
+        assert head_precision == "bf16" or not train, "the bf16x3 head is an inference mode (teacher / simple_test)"
+        self.head_precision = head_precision
         assert parts in ("head", "neck") or (H % 32 == 0 and W % 32 == 0), \
             "inputs are padded to a multiple of 32 (Pad size_divisor=32)"
         self.parts = parts
@@ -496,7 +500,115 @@ class FCOSNet:
         self.plan_fwd([self.fpnc[4].fseg(self.r6, self.p[4], B, h6, w6)], "fpn.p7")
 
     # ------------------------------------------------------------------------------------------ head
+    def _build_head_split(self):
+        """FCOSHead forward with split-bf16 operands (north_star: FCOSHead outputs within 1e-3 of the fp32 reference,
+        fcos_head.py:118-168; plain bf16 measures 1.4e-3 on identical inputs). Every activation travels as [hi | lo | hi]
+        (3 x 256 bf16 channels), every weight as [w_hi | w_hi | w_lo]: the SAME tcgen05 implicit-GEMM launches with
+        K = 3 x 2304 accumulate hi*w_hi + lo*w_hi + hi*w_lo in fp32; the tower maps are stored in fp32 (conv epilogue:
+        fp32 direct store + GroupNorm statistics) and dslb_gn_apply_relu_split turns them into the next split operand.
+        3x the tower FLOPs, inference only."""
+        B, C = self.B, self.C
+        st = self.store
+        nl = len(self.psize)
+        f32 = torch.float32
+        self.tower = {"cls": [], "reg": []}
+        split_w = []      # (packed split operand, [(fp32 master weight, first row)], rows_pad)
+
+        def split_operand(parts, rows_pad):
+            wp = self.mem.zeros(9, rows_pad, 768, dtype=BF16)
+            split_w.append((wp, parts, rows_pad))
+            return wp
+
+        for br in ("cls", "reg"):
+            for i in range(4):
+                self.tower[br].append(split_operand([(st[f"bbox_head.{br}_convs.{i}.conv.weight"], 0)], 256))
+        self.gn_stats = self.mem.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64)
+        self.gn_mr = self.mem.zeros(2, 4, nl, B, 32, 4, dtype=f32)
+        self.add_fwd(self.gn_stats.zero_)
+        self.ps = [self.buf(B, h, w, 768) for (h, w) in self.psize]
+        self.y = {br: [[self.buf(B, h, w, 256, dtype=f32) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
+        self.z = {br: [[self.buf(B, h, w, 768) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
+        for l, (h, w) in enumerate(self.psize):
+            self.add_fwd(self.ew("dslb_bf16_to_split", self.p[l], self.ps[l], B * h * w, 256))
+        for i in range(4):
+            segs, gsegs = [], []
+            for bi_, br in enumerate(("cls", "reg")):
+                for l, (h, w) in enumerate(self.psize):
+                    x = self.ps[l] if i == 0 else self.z[br][i - 1][l]
+                    segs.append(dict(x=x, w=self.tower[br][i], y=self.y[br][i][l], N=B, H=h, W=w, Cin=768, Cout=256,
+                                     cout_pad=256, R=3, S=3, stride=1, pad=1, ldc=256, out_fp32=1,
+                                     shift=st[f"bbox_head.{br}_convs.{i}.conv.bias"], gn_stats=self.gn_stats[bi_, i, l],
+                                     gn_cpg=8))
+                    gsegs.append(dict(x=self.y[br][i][l], y=self.z[br][i][l], stats=self.gn_stats[bi_, i, l],
+                                      gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
+                                      beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], mr=self.gn_mr[bi_, i, l], N=B,
+                                      HW=h * w))
+            p = ConvPlan(segs, f"head.tower{i}.bf16x3")
+            self.flops_fwd += p.flops / 3.0      # algorithmic FLOPs: the reference's conv, not the three partial products
+            self.add_fwd(p.run)
+            arr = (L.GnSeg * len(gsegs))()
+            keep = []
+            for a, g in zip(arr, gsegs):
+                for k, v in g.items():
+                    if isinstance(v, torch.Tensor):
+                        keep.append(v)
+                        setattr(a, k, v.data_ptr())
+                    else:
+                        setattr(a, k, v)
+
+            def gn_run(_arr=arr, _n=len(gsegs), _k=keep):
+                L.check(L.lib.dslb_gn_apply_relu_split(_arr, _n, 256, 32, 1e-5, L.cur_stream()), "gn_apply_split")
+
+            self.add_fwd(gn_run)
+        cls_wp = split_operand([(st["bbox_head.conv_cls.weight"], 0)], ceil_to(C, 16))
+        rc_wp = split_operand([(st["bbox_head.conv_reg.weight"], 0), (st["bbox_head.conv_centerness.weight"], 4)], 16)
+        self.rc_scale = torch.ones(nl, 8, dtype=f32, device=self.dev)
+        self.rc_shift = self.mem.zeros(nl, 8, dtype=f32)
+        self.scale_vals = torch.ones(nl, dtype=f32, device=self.dev)
+        self.level_mult = torch.tensor([float(s) for s in self.strides[:nl]], dtype=f32, device=self.dev)   # eval: x stride
+        offs = [st.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
+        self.scale_stride = offs[1] - offs[0]
+
+        def repack_split():
+            # [w_hi | w_hi | w_lo]: w_hi is the bf16 rounding the pack kernel applies to the first two thirds, w_lo the
+            # rounding of the remainder (torch ops: this optional path is refreshed only after a weight update)
+            for wp, parts, rows_pad in split_w:
+                rows = []
+                for wt, r0 in parts:
+                    wf = wt.detach().float()
+                    wl = wf - wf.to(BF16).float()
+                    rows.append((r0, torch.cat([wf, wf, wl], dim=1)))
+                O = max(r0 + c.shape[0] for r0, c in rows)
+                cat = torch.zeros(O, 768, 3, 3, dtype=f32, device=self.dev)
+                for r0, c in rows:
+                    cat[r0:r0 + c.shape[0]] = c
+                L.check(L.lib.dslb_pack_weight(L.ptr(cat), L.ptr(wp), O, 768, 3, 3, rows_pad, 768, None, 0, L.cur_stream()),
+                        "pack split")
+                self._split_keep = cat   # stays alive until the (stream-ordered) next allocation re-uses it
+            L.check(L.lib.dslb_fcos_regctr_affine(
+                L.ptr(st["bbox_head.scales.0.scale"]), self.scale_stride, L.ptr(st["bbox_head.conv_reg.bias"]),
+                L.ptr(st["bbox_head.conv_centerness.bias"]), L.ptr(self.level_mult), L.ptr(self.rc_scale),
+                L.ptr(self.rc_shift), L.ptr(self.scale_vals), nl, L.cur_stream()), "regctr_affine")
+
+        self.repack_ops.append(repack_split)
+        self.cls_out = [self.buf(B, h, w, C, dtype=f32) for (h, w) in self.psize]
+        self.rc_out = [self.buf(B, h, w, 8, dtype=f32) for (h, w) in self.psize]
+        segs = []
+        for l, (h, w) in enumerate(self.psize):
+            segs.append(dict(x=self.z["cls"][3][l], w=cls_wp, y=self.cls_out[l], N=B, H=h, W=w, Cin=768, Cout=C,
+                             cout_pad=ceil_to(C, 16), R=3, S=3, stride=1, pad=1, ldc=C, out_fp32=1,
+                             shift=st["bbox_head.conv_cls.bias"]))
+        for l, (h, w) in enumerate(self.psize):
+            segs.append(dict(x=self.z["reg"][3][l], w=rc_wp, y=self.rc_out[l], N=B, H=h, W=w, Cin=768, Cout=5,
+                             cout_pad=16, R=3, S=3, stride=1, pad=1, ldc=8, out_fp32=1, relu_nch=4,
+                             scale=self.rc_scale[l], shift=self.rc_shift[l]))
+        p = ConvPlan(segs, "head.predictors.bf16x3")
+        self.flops_fwd += p.flops / 3.0
+        self.add_fwd(p.run)
+
     def _build_head(self):
+        if self.head_precision == "bf16x3":
+            return self._build_head_split()
         B, C = self.B, self.C
         tr = self.train
         st = self.store
@@ -968,13 +1080,14 @@ class FCOSNet:
             all_d.append(d)
             if tr:
                 train_d.append(d)
-        self.pack_all = TablePlan(all_d, "pack", "pack_all")
+        self.pack_all = TablePlan(all_d, "pack", "pack_all") if all_d else None
         self.pack_train = TablePlan(train_d, "pack", "pack_train") if train_d else None
 
     def repack(self, everything=True):
         """Refresh the derived bf16 operands from the fp32 master parameters (after an optimizer / EMA step)."""
         if everything or self.pack_train is None:
-            self.pack_all.run()
+            if self.pack_all is not None:
+                self.pack_all.run()
         else:
             self.pack_train.run()
         for f in self.repack_ops:

@@ -246,10 +246,21 @@ class FCOS(_StoreModule):
                                       soft_weight=hc["soft_weight"], center_sampling=hc["center_sampling"],
                                       radius=hc["center_sample_radius"], norm_on_bbox=hc["norm_on_bbox"],
                                       strides=hc["strides"], regress_ranges=hc["regress_ranges"],
-                                      backbone=self.backbone_kind)
+                                      backbone=self.backbone_kind,
+                                      head_precision="bf16" if train else self.eval_head_precision)
         else:
             self._nets.move_to_end(key)
         return self._nets[key]
+
+    # inference precision of the FCOSHead: "bf16" (default) or "bf16x3" = split-bf16 operands with fp32 tower maps, which
+    # holds the reference's fp32 outputs (fcos_head.py:118-168) to 1e-3 at 3x the tower FLOPs (engine._build_head_split).
+    # Also settable for a whole process with DSLB_HEAD_PRECISION=bf16x3.
+    eval_head_precision = __import__("os").environ.get("DSLB_HEAD_PRECISION", "bf16")
+
+    def set_eval_head_precision(self, precision):
+        assert precision in ("bf16", "bf16x3")
+        self.eval_head_precision = precision
+        self._nets.clear()
 
     def extract_feat(self, img):
         """FPN outputs as the reference returns them: 5 x (B, 256, h, w) fp32 NCHW (single_stage.py:136-141)."""

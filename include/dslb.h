@@ -56,7 +56,7 @@ typedef struct dslb_conv_seg {
   const void* relu_mask; /* bf16, same indexing as y, or NULL                                         */
   const float* scale;    /* [Cout] or NULL (=1)                                                       */
   const float* shift;    /* [Cout] or NULL (=0)                                                       */
-  double* gn_stats;      /* [N][Cout/gn_cpg][DSLB_GN_STAT_STRIDE] ([0]=sum,[1]=sumsq), pre-zeroed, or NULL */
+  double* gn_stats;      /* [N][Cout/gn_cpg][DSLB_GN_STAT_STRIDE] ([0]=sum,[1]=sumsq), pre-zeroed, or NULL (bf16 or fp32 y) */
   int32_t N, H, W, Cin;
   int32_t Cout;          /* real output channels                                                      */
   int32_t cout_pad;      /* rows per tap in w; multiple of 16; tiles of <=256                         */
@@ -140,6 +140,15 @@ int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, f
 /* same result, faster: driven by the block table of dslb_gn_bwd_plan (C must be 256) */
 int dslb_gn_apply_relu_tab(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, const int* blk_tab_dev,
                            int nblocks, void* stream);
+/* Accurate ("bf16x3", split-bf16) FCOSHead mode, inference only: north_star asks for FCOSHead outputs within 1e-3 of the
+ * fp32 reference (fcos_head.py:118-168 runs in fp32). A value v travels as hi = bf16(v), lo = bf16(v - hi); a conv over
+ * the 3C-channel rows [hi | lo | hi] against packed weights [w_hi | w_hi | w_lo] accumulates hi*w_hi + lo*w_hi + hi*w_lo
+ * in fp32 on the tensor core (operand precision ~2^-17). The tower maps stay fp32 (conv segments with out_fp32 = 1 AND
+ * gn_stats), and this apply turns them into the next layer's split operand:
+ *     y[pix][3C] = split(relu(GroupNorm(x)))   with x fp32 [N*HW][C] (seg.x), y bf16 (seg.y). */
+int dslb_gn_apply_relu_split(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream);
+/* bf16 map [npix][C] -> split operand [npix][3C] = [x | 0 | x] (the FPN outputs entering the accurate head). */
+int dslb_bf16_to_split(const void* x, void* y, long long npix, int C, void* stream);
 /* backward: dslb_gn_bwd_blocks -> size of the block table; dslb_gn_bwd_plan fills a HOST table of 2*blocks ints the
  * caller copies to the device once; dslb_gn_bwd runs the reduce + apply passes (C must be 256). */
 int dslb_gn_bwd_blocks(const dslb_gn_seg_t* segs, int nseg);

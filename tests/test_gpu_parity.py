@@ -112,6 +112,42 @@ def test_head_forward_identical_inputs(small_net):
             assert max(per_level) < 2e-2, (k, per_level)
 
 
+def test_head_forward_bf16x3_within_1e3(small_net):
+    """The accurate inference mode of the FCOSHead (split-bf16 operands, fp32 tower maps, engine._build_head_split):
+    north_star bar 1e-3 against the fp32 reference on identical inputs — cls logits, bbox and centerness, pooled AND per
+    level — with the plain bf16 head of the same weights measured beside it."""
+    from dsl_b200.engine import FCOSNet
+    from oracle import fcos_oracle as O
+    rng = np.random.RandomState(9)
+    nets = dict(bf16=FCOSNet(2, 256, 320, depth=50, train=False, store=small_net.store),
+                bf16x3=FCOSNet(2, 256, 320, depth=50, train=False, store=small_net.store, head_precision="bf16x3"))
+    feats = []
+    for l, (h, w) in enumerate(nets["bf16"].psize):
+        feats.append(GI.make_tensor(rng, 2, 256, h, w).to(torch.bfloat16))
+    _, _, head = _oracle_state(small_net)
+    with torch.no_grad():
+        cls, box, ctr = O.fcos_head_forward(head, [f.float() for f in feats], training=False)
+    ref = dict(cls=cls, bbox=box, ctr=ctr)
+    worst = {}
+    for name, net in nets.items():
+        for l, f in enumerate(feats):
+            net.p[l].copy_(f.permute(0, 2, 3, 1))
+        net.forward_head()
+        torch.cuda.synchronize()
+        got = dict(cls=[_nchw(net.cls_out[l], 80) for l in range(5)], bbox=[_nchw(net.rc_out[l], 4) for l in range(5)],
+                   ctr=[_nchw(net.rc_out[l][..., 4:5], 1) for l in range(5)])
+        for k in ("cls", "bbox", "ctr"):
+            diffs = [(got[k][l] - ref[k][l]).abs().max().item() for l in range(5)]
+            refs = [ref[k][l].abs().max().item() for l in range(5)]
+            pooled = max(diffs) / max(refs)
+            per_level = max(d / (r + 1e-12) for d, r in zip(diffs, refs))
+            worst[(name, k)] = (pooled, per_level)
+            print(f"{name} {k}: pooled rel {pooled:.3e}, worst level {per_level:.3e}")
+    for k in ("cls", "bbox", "ctr"):
+        assert worst[("bf16x3", k)][0] < 1e-3 and worst[("bf16x3", k)][1] < 1e-3, (k, worst[("bf16x3", k)])
+        assert worst[("bf16x3", k)][0] < 0.25 * worst[("bf16", k)][0], "the split operands must buy real accuracy"
+
+
 def _run_loss(net, gts, labels, ignores):
     net.set_targets([g.cuda() for g in gts], [l.cuda() for l in labels],
                     None if ignores is None else [i.cuda() for i in ignores])

@@ -614,3 +614,25 @@ def test_runner_multi_shape_training_on_the_gpu():
     assert e0.mom is e1.mom and float(e0.mom.abs().sum()) > 0
     assert all(not torch.equal(a, b) for a, b in zip(flats, flats[1:]))      # every iteration stepped the same weights
     assert e0.post.have_prev and e1.post.have_prev and e0.graphs is None and e1.graphs is None
+
+
+@pytest.mark.gpu
+def test_plugin_simple_test_with_the_accurate_head_mode():
+    """FCOS.set_eval_head_precision('bf16x3'): the registry module's inference path (simple_test -> bbox2result lists) on
+    the split-bf16 head; detections stay those of the bf16 head up to score / box noise well inside the NMS rules."""
+    m = _build().cuda()
+    with torch.no_grad():
+        m.store["bbox_head.conv_cls.bias"][:2] = 1.0        # two confident classes
+    m._dirty()
+    m.eval()
+    data = _data(2, 256, 320, 17)
+    base = m.simple_test(data["img"], data["img_metas"], rescale=False)
+    m.set_eval_head_precision("bf16x3")
+    acc = m.simple_test(data["img"], data["img_metas"], rescale=False)
+    assert len(acc) == 2 and len(acc[0]) == 80
+    for b in range(2):
+        nb, na = sum(len(r) for r in base[b]), sum(len(r) for r in acc[b])
+        assert na == 100 and nb == 100                       # max_per_img survivors in both modes
+        top_b = max((r[:, 4].max() for r in base[b] if len(r)), default=0.0)
+        top_a = max((r[:, 4].max() for r in acc[b] if len(r)), default=0.0)
+        assert abs(float(top_a) - float(top_b)) < 2e-2 * float(top_b)
