@@ -56,6 +56,7 @@ class ConvPlan:
     def __init__(self, segs, what="conv"):
         self.what = what
         self.keep = []
+        self.segs = [dict(s) for s in segs]     # kept so that plans of two networks can be merged (DSLEngine joint forward)
         arr = (L.ConvSeg * len(segs))()
         for a, s in zip(arr, segs):
             for k, v in s.items():

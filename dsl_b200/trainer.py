@@ -85,6 +85,11 @@ class DSLEngine:
             torch.cuda.synchronize()
             _COMM_WARM = True
         self._build_teacher_post()
+        # Tried and kept as an opt-in (DSLB_JOINT_FWD=1): teacher + student forward as JOINT launches — layer k of the two
+        # networks as ONE persistent conv launch with the segments of both. Measured slower (9.52-9.59 ms vs 9.37 ms, B=4 at
+        # 800x1344; R101 bs 2: 7.86 vs 7.80 ms): two independent passes on two streams let one kernel's tail wave overlap the
+        # other's prologue and let the small elementwise kernels co-run, which a merged launch serialises again.
+        self.joint_fwd = self._build_joint_forward() if os.environ.get("DSLB_JOINT_FWD", "0") == "1" else None
         self.launches_per_step = None
         self.two_streams = two_streams
         self.s2 = torch.cuda.Stream()   # teacher branch
@@ -114,6 +119,48 @@ class DSLEngine:
         self.pl_gt_off = torch.zeros(t.B + 1, dtype=torch.int32, device=self.dev)
         self.pl_ig_boxes = torch.zeros(mb, 4, dtype=torch.float32, device=self.dev)
         self.pl_ig_off = torch.zeros(t.B + 1, dtype=torch.int32, device=self.dev)
+
+    def _build_joint_forward(self):
+        from .engine import ConvPlan
+        s_ops, t_ops = self.student.fwd_ops, self.teacher.fwd_ops
+        if len(s_ops) != len(t_ops):
+            return None
+        joint, merged = [], 0
+        self._joint_plans = []
+        for a, b in zip(s_ops, t_ops):
+            pa, pb = getattr(a, "__self__", None), getattr(b, "__self__", None)
+            ok = isinstance(pa, ConvPlan) and isinstance(pb, ConvPlan) and len(pa.segs) + len(pb.segs) <= L.MAX_SEGS
+            if ok and len(pa.segs) == 1:
+                g = pa.segs[0]      # single narrow 3x3 stride-1 convs run on the halo-tile kernel, which takes one segment
+                if g.get("R") == 3 and g.get("stride", 1) == 1 and g.get("Cin") in (64, 128) and g.get("Cout") in (64, 128):
+                    ok = False
+            if ok:
+                plan = ConvPlan(pa.segs + pb.segs, pa.what + "+teacher")
+                self._joint_plans.append(plan)
+                joint.append(plan.run)
+                merged += 1
+            else:
+                joint.append(a)
+                joint.append(b)
+        return joint if merged else None
+
+    def _forward_both(self):
+        """Teacher (no_grad, eval) and student forward, then the teacher's post-processing forked onto the second stream
+        (nothing in this step's student pass consumes it)."""
+        with torch.no_grad():
+            for op in self.joint_fwd:
+                op()
+        if not self.two_streams:
+            with torch.no_grad():
+                self.teacher_decode()
+            return
+        main = torch.cuda.current_stream()
+        self._fork_ev.record(main)
+        self.s2.wait_event(self._fork_ev)
+        with torch.cuda.stream(self.s2):
+            with torch.no_grad():
+                self.teacher_decode()
+            self._join_ev.record(self.s2)
 
     def teacher_decode(self):
         """Teacher head outputs -> gated candidates -> NMS -> pseudo GT / ignore boxes, all on the device
@@ -165,9 +212,13 @@ class DSLEngine:
             torch.cuda.current_stream().wait_event(self._join_ev)
 
     def _phase_a(self):
-        self._fork_teacher()
+        if self.joint_fwd is not None:
+            self._forward_both()
+        else:
+            self._fork_teacher()
+            with torch.no_grad():
+                self.student.forward()
         with torch.no_grad():
-            self.student.forward()
             self.student.run_targets()
         if self.world > 1:
             self._join_teacher()   # each captured graph must re-join its forked stream
@@ -179,9 +230,12 @@ class DSLEngine:
             self.student.run_targets()
 
     def _phase_a_fwd(self):
-        self._fork_teacher()
-        with torch.no_grad():
-            self.student.forward()
+        if self.joint_fwd is not None:
+            self._forward_both()
+        else:
+            self._fork_teacher()
+            with torch.no_grad():
+                self.student.forward()
         self._join_teacher()
 
     def _phase_b(self):
@@ -315,9 +369,12 @@ class DSLEngine:
         with torch.cuda.stream(self.s_comm):
             dist_ops.allreduce_sum_(self.student.counts)
             ev[1].record(self.s_comm)
-        self._fork_teacher()       # joined before the optimizer / EMA (the teacher branch overlaps the whole backward)
-        with torch.no_grad():
-            self.student.forward()
+        if self.joint_fwd is not None:
+            self._forward_both()
+        else:
+            self._fork_teacher()   # joined before the optimizer / EMA (the teacher branch overlaps the whole backward)
+            with torch.no_grad():
+                self.student.forward()
         main.wait_event(ev[1])
         for k in range(nb):
             self._phase_b_part(k)
@@ -612,6 +669,7 @@ class DSLEngine:
 
         saved = [(n, n.fwd_ops, n.bwd_ops) for n in nets]
         two, self.two_streams = self.two_streams, False   # serialise the teacher branch: per-kernel times must not overlap
+        joint, self.joint_fwd = self.joint_fwd, None      # per-plan accounting: the two networks' launches one by one
         for n in nets:
             n.fwd_ops = [wrap(o) for o in n.fwd_ops]
             n.bwd_ops = [wrap(o) for o in n.bwd_ops]
@@ -630,6 +688,7 @@ class DSLEngine:
             for n, f, b in saved:
                 n.fwd_ops, n.bwd_ops = f, b
             self.two_streams = two
+            self.joint_fwd = joint
         out = dict(step_ms=t0.elapsed_time(t1) / steps, launches_per_step=L.launch_count / steps)
         fam = dict(conv_igemm=dict(ms=0.0, flops=0.0, n=0), conv_wgrad=dict(ms=0.0, flops=0.0, n=0))
         tower = dict(ms=0.0, flops=0.0)
