@@ -165,6 +165,9 @@ _proto("dslb_bn_grad_plan_destroy", None, VP)
 _proto("dslb_fcos_regctr_affine", I, VP, I, VP, VP, VP, VP, VP, VP, I, VP)
 _proto("dslb_zero_upsample2", I, VP, VP, I, I, I, I, I, I, VP)
 _proto("dslb_colsum", I, VP, VP, LL, I, I, VP)
+_proto("dslb_zero", I, VP, C.c_size_t, VP)
+_proto("dslb_scatter_f32", I, VP, VP, VP, I, VP)
+_proto("dslb_f64_to_f32", I, VP, VP, I, VP)
 _proto("dslb_fcos_targets", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, I, I, F, I, VP, VP, VP, VP, VP, VP)
 _proto("dslb_fcos_norm", I, VP, F, VP, VP)
 _proto("dslb_fcos_loss", I, C.POINTER(FcosLevel), I, I, I, VP, VP, VP, VP, VP, F, F, F, I, F, VP, VP, VP, VP)
@@ -215,6 +218,11 @@ def check(rc, what=""):
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def zero(t):
+    """t.zero_() without a framework kernel: cudaMemsetAsync on the current stream (a memset node under graph capture)."""
+    check(lib.dslb_zero(ptr(t), t.numel() * t.element_size(), cur_stream()), "zero")
 
 
 def cur_stream():

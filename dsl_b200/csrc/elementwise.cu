@@ -782,6 +782,38 @@ extern "C" int dslb_gn_apply_relu_split(const dslb_gn_seg_t* segs, int nseg, int
   LAUNCH_CHECK();
 }
 
+namespace dslb {
+__global__ void scatter_f32_kernel(float* __restrict__ dst, const long long* __restrict__ idx, const float* __restrict__ src,
+                                   int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[i];
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+}  // namespace dslb
+
+extern "C" int dslb_zero(void* p, size_t bytes, void* stream) {
+  DSLB_CHECK_ARG(p || bytes == 0, "dslb_zero: null pointer");
+  if (bytes) DSLB_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return DSLB_OK;
+}
+
+extern "C" int dslb_scatter_f32(float* dst, const int64_t* idx, const float* src, int n, void* stream) {
+  DSLB_CHECK_ARG(dst && idx && src && n >= 0, "dslb_scatter_f32: bad arguments");
+  if (n == 0) return DSLB_OK;
+  scatter_f32_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dst, (const long long*)idx, src, n);
+  LAUNCH_CHECK();
+}
+
+extern "C" int dslb_f64_to_f32(const double* src, float* dst, int n, void* stream) {
+  DSLB_CHECK_ARG(src && dst && n >= 0, "dslb_f64_to_f32: bad arguments");
+  if (n == 0) return DSLB_OK;
+  f64_to_f32_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, dst, n);
+  LAUNCH_CHECK();
+}
+
 extern "C" int dslb_bf16_to_split(const void* x, void* y, long long npix, int C, void* stream) {
   DSLB_CHECK_ARG(x && y && npix >= 0 && C % 8 == 0, "dslb_bf16_to_split: bad arguments");
   if (npix == 0) return DSLB_OK;

@@ -305,8 +305,8 @@ class FCOSNet:
                 self._alloc_arena()
 
                 def zero_state():
-                    self.grad.zero_()
-                    self.arena.zero_()
+                    L.zero(self.grad)
+                    L.zero(self.arena)
 
                 self.add_bwd(zero_state)
             if parts == "neck":
@@ -525,7 +525,7 @@ class FCOSNet:
                 self.tower[br].append(split_operand([(st[f"bbox_head.{br}_convs.{i}.conv.weight"], 0)], 256))
         self.gn_stats = self.mem.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64)
         self.gn_mr = self.mem.zeros(2, 4, nl, B, 32, 4, dtype=f32)
-        self.add_fwd(self.gn_stats.zero_)
+        self.add_fwd(lambda: L.zero(self.gn_stats))
         self.ps = [self.buf(B, h, w, 768) for (h, w) in self.psize]
         self.y = {br: [[self.buf(B, h, w, 256, dtype=f32) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
         self.z = {br: [[self.buf(B, h, w, 768) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
@@ -623,7 +623,7 @@ class FCOSNet:
         # GroupNorm statistics of all (branch, layer, level) maps in one buffer -> one memset per pass
         self.gn_stats = self.mem.zeros(2, 4, nl, B, 32, L.GN_STAT_STRIDE, dtype=torch.float64)
         self.gn_mr = self.mem.zeros(2, 4, nl, B, 32, 4, dtype=torch.float32)
-        self.add_fwd(self.gn_stats.zero_)
+        self.add_fwd(lambda: L.zero(self.gn_stats))
         self.y = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
         self.z = {br: [[self.buf(B, h, w, 256) for (h, w) in self.psize] for _ in range(4)] for br in ("cls", "reg")}
         for i in range(4):
@@ -742,6 +742,7 @@ class FCOSNet:
         self.loss_acc = self.mem.zeros(16, dtype=torch.float32)  # one memset for both accumulators
         self.loss_sums = self.loss_acc[:8].view(torch.float64)
         self.dscale = self.loss_acc[8:16]
+        self.loss_f32 = self.mem.zeros(4, dtype=torch.float32)   # the four loss scalars as the detector returns them
         self.max_boxes = 1024
         self.gt_boxes = self.mem.zeros(self.max_boxes, 4, dtype=torch.float32)
         self.gt_labels = self.mem.zeros(self.max_boxes, dtype=torch.int64)
@@ -787,7 +788,7 @@ class FCOSNet:
 
     def run_targets(self):
         """kernel 1 of the loss: labels / bbox_targets / weights / centerness targets + local normaliser sums."""
-        self.counts.zero_()
+        L.zero(self.counts)
         lw = self.loss_weight
         L.check(L.lib.dslb_fcos_targets(
             self.levels_arr, len(self.psize), self.B, self.C, L.ptr(self.gt_boxes), L.ptr(self.gt_labels),
@@ -800,12 +801,13 @@ class FCOSNet:
         """kernel 2 (after `counts` has been all-reduced over ranks): losses + gradients of the head outputs."""
         s = L.cur_stream()
         L.check(L.lib.dslb_fcos_norm(L.ptr(self.counts), float(self.world_size), L.ptr(self.norm), s), "fcos_norm")
-        self.loss_acc.zero_()
+        L.zero(self.loss_acc)
         nl = len(self.psize)
         L.check(L.lib.dslb_fcos_loss(
             self.levels_arr, nl, self.B, self.C, L.ptr(self.labels), L.ptr(self.bbox_targets), L.ptr(self.weights),
             L.ptr(self.ctr_targets), L.ptr(self.norm), 0.25, 2.0, self.loss_weight, self.n_labeled,
             float(self.si_weight), L.ptr(self.scale_vals), L.ptr(self.loss_sums), L.ptr(self.dscale), s), "fcos_loss")
+        L.check(L.lib.dslb_f64_to_f32(L.ptr(self.loss_sums), L.ptr(self.loss_f32), 4, s), "loss scalars")
 
     # ------------------------------------------------------------------------------------------ head backward
     def _build_head_bwd(self):
@@ -820,8 +822,8 @@ class FCOSNet:
         self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]  # gradient w.r.t. the FPN outputs
 
         def zero_state():
-            self.grad.zero_()
-            self.arena.zero_()  # every packed wgrad accumulator, the GroupNorm backward sums, rc_dw / rc_db
+            L.zero(self.grad)
+            L.zero(self.arena)  # every packed wgrad accumulator, the GroupNorm backward sums, rc_dw / rc_db
 
         self.add_bwd(zero_state)
         # --- predictors: wgrad (10 segs), bias grads, dgrad into the last tower outputs
@@ -1037,10 +1039,17 @@ class FCOSNet:
         # stalls at a bucket boundary; backward() joins the two streams at the end of every op range
         self.add_bwd(plan.run, side=True, tag="unpack")
         if head:
+            o_reg = self.store.offsets["bbox_head.conv_reg.bias"][0]
+            o_ctr = self.store.offsets["bbox_head.conv_centerness.bias"][0]
+            self.head_bias_idx = torch.tensor([o_reg, o_reg + 1, o_reg + 2, o_reg + 3, o_ctr], dtype=torch.long,
+                                              device=self.dev)
+
             def finish_head_grads():
-                self.grad_view("bbox_head.conv_reg.bias").copy_(self.rc_db[:4])
-                self.grad_view("bbox_head.conv_centerness.bias").copy_(self.rc_db[4:5])
-                self.grad.index_copy_(0, self.scale_idx, self.dscale[:len(self.psize)])
+                s = L.cur_stream()
+                L.check(L.lib.dslb_scatter_f32(L.ptr(self.grad), L.ptr(self.head_bias_idx), L.ptr(self.rc_db), 5, s),
+                        "head bias grads")
+                L.check(L.lib.dslb_scatter_f32(L.ptr(self.grad), L.ptr(self.scale_idx), L.ptr(self.dscale),
+                                               len(self.psize), s), "scale grads")
 
             self.add_bwd(finish_head_grads, side=True, tag="finish_head")
         offs = [self.store.offsets[n] for n in names]
@@ -1141,7 +1150,7 @@ class FCOSNet:
 
     def losses(self):
         """dict of the reference's loss names -> 0-dim fp32 tensors (device)."""
-        s = self.loss_sums.to(torch.float32)
+        s = self.loss_f32
         out = dict(loss_cls=s[0], loss_bbox=s[1], loss_centerness=s[2])
         if self.si_weight != 0.0:
             out["loss_sisoft"] = s[3]

@@ -85,7 +85,7 @@ class TeacherPost:
         s = L.cur_stream
         if getattr(self, "_tk", None) is None:
             self._topk_plan()
-        self.cand_counts.zero_()
+        L.zero(self.cand_counts)
         for l, (h, w) in enumerate(self.psize):
             L.check(L.lib.dslb_fcos_point_scores(L.ptr(cls_out[l]), L.ptr(rc_out[l]), L.ptr(self.pt_scores[l]),
                                                  self.B * h * w, self.C, self.C, s()), "point_scores")

@@ -264,7 +264,7 @@ class DSLEngine:
         s = L.cur_stream()
         st, tt = self.student.store, self.teacher.store
         g = self.student.grad
-        self.sqnorm.zero_()
+        L.zero(self.sqnorm)
         L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
         # max_grad_norm None = no clipping (optimizer_config.grad_clip=None): a bound no fp32 norm reaches gives coef 1
         L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm if self.max_grad_norm is not None

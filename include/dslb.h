@@ -258,6 +258,12 @@ void dslb_bn_grad_plan_destroy(dslb_bn_grad_plan_t* plan);
 /* y[n][2p][2q][:] = x[n][p][q][:], every other pixel of the [N][H][W][C] bf16 map zero: turns the data gradient of a
  * stride-2 conv into a stride-1 tensor-core dgrad over the zero-upsampled dY (FPN P6/P7 convs, necks/fpn.py:192-201). */
 int dslb_zero_upsample2(const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream);
+/* Small glue so that no framework kernel sits inside the captured step: buffer clears (a memset node in the CUDA graph),
+ * dst[idx[i]] = src[i] (the reg / centerness bias and Scale gradients into the flat gradient buffer), fp64 loss sums ->
+ * the fp32 scalars the detector returns (detectors/base.py:201-206 logs them). */
+int dslb_zero(void* p, size_t bytes, void* stream);
+int dslb_scatter_f32(float* dst, const int64_t* idx, const float* src, int n, void* stream);
+int dslb_f64_to_f32(const double* src, float* dst, int n, void* stream);
 /* out[c] += sum_p x[p][c] over a pixel-major bf16 matrix (conv bias gradient). */
 int dslb_colsum(const void* x, float* out, long long npix, int ld, int C, void* stream);
 

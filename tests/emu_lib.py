@@ -238,6 +238,22 @@ class EmuLib:
         view(y, n, BF16).copy_(r.to(BF16))
         return 0
 
+    def dslb_zero(self, p, nbytes, stream):
+        if nbytes:
+            view(p, int(nbytes), torch.uint8).zero_()
+        return 0
+
+    def dslb_scatter_f32(self, dst, idx, src, n, stream):
+        i = view(idx, n, torch.int64)
+        s_ = view(src, n, torch.float32)
+        for k in range(n):
+            view(_addr(dst) + 4 * int(i[k]), 1, torch.float32)[0] = s_[k]
+        return 0
+
+    def dslb_f64_to_f32(self, src, dst, n, stream):
+        view(dst, n, torch.float32).copy_(view(src, n, torch.float64).to(torch.float32))
+        return 0
+
     def dslb_colsum(self, x, out, npix, ld, Cc, stream):
         view(out, Cc, torch.float32).add_(_rows(x, npix, ld, BF16)[:, :Cc].float().sum(0))
         return 0

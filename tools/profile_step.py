@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from dsl_b200.trainer import DSLEngine
-from tests.golden import inputs as GI
+from bench import confident_heads, make_gt
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
@@ -30,7 +30,8 @@ eng = DSLEngine(B, H, W, depth=a.depth, seed=0, use_graphs=False, backbone=a.bac
 rng = np.random.RandomState(100)
 img_s = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
 img_t = torch.from_numpy((rng.rand(B, 3, H, W) * 255 - 115).astype(np.float32))
-gts, labels, ignores = GI.make_gt(200, B, H, W, max_gt=20, max_ignore=5, with_ignore=True)
+gts, labels, ignores = make_gt(200, B, H, W, max_gt=20, max_ignore=5)
+confident_heads(eng)
 eng.set_inputs(img_s, gts, labels, ignores, teacher_img=img_t)
 for _ in range(a.warm):
     eng.step()
