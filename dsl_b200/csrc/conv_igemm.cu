@@ -78,6 +78,9 @@ struct alignas(128) ConvParamsDev {
   int has_ident;  // some segment uses res_mma: 8 KiB identity tile after the staging slabs (3-stage layout only)
   int any_aux;  // some segment brings its residual / mask tiles in by TMA (nbuf == 2); with nbuf == 2 and no aux the
                 // second slab double-buffers the TMA stores instead
+  int cta2;     // 1: launched as CTA PAIRS (cluster of 2, conv_igemm_cta2_kernel): two consecutive 128-pixel tiles of one
+                // segment form ONE tcgen05.mma.cta_group::2 of M = 256; each CTA keeps its own A tile and HALF of the
+                // 256-row weight tile (b_stride = 16 KiB), so a k-iteration feeds 32 KiB per SM instead of 48 KiB
 };
 
 __device__ __forceinline__ int find_seg(const ConvParamsDev* P, int tile) {
@@ -209,6 +212,7 @@ __device__ __forceinline__ ConvSmem conv_carve(const ConvParamsDev* P, uint8_t* 
 }
 
 // barrier init, TMEM allocation, identity tile; returns the TMEM base address. Ends with a CTA-wide barrier.
+template <bool CTA2 = false>
 __device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const ConvSmem& S, int epi_warps) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,13 +224,22 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParamsDev* P, const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&S.tfull[i], 1);
-      mbar_init(&S.tempty[i], epi_warps);
+      mbar_init(&S.tempty[i], CTA2 ? 2 * epi_warps : epi_warps);   // pair: the peer's epilogue warps arrive here too
     }
     for (int i = 0; i < 4; ++i) mbar_init(&S.auxfull[i], 1);
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc(S.tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc2(S.tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(S.tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
+  }
+  if (CTA2) {   // the peer's barriers are initialised before anything can arrive on them remotely
+    __syncwarp();
+    cluster_sync_all();
   }
   if (P->has_ident) {
     // row n holds 1.0 at k == n: 16-byte slot (n >> 3) ^ (n & 7) of the 128-byte row, element n & 7 inside it
@@ -370,11 +383,80 @@ __device__ __forceinline__ void conv_mma(const ConvParamsDev* P, const ConvSmem&
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variants (cta_group::2)
+// Both CTAs of the pair run the producer for THEIR tile (tile = blockIdx.x + k * gridDim.x; blockIdx.x = 2 * pair + rank, the
+// pair's two tiles are consecutive 128-pixel tiles of one segment): own im2col A tile + rows [128 rank, 128 rank + 128) of
+// the weight tile into their own shared memory, every byte accounted on the LEADER's full barrier.
+__device__ __forceinline__ void conv_producer_cta2(const ConvParamsDev* P, const ConvSmem& S, uint32_t rank) {
+  const int total = P->total_tiles, nst = S.nst;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+    const int mt = tile - sg.tile_begin;      // n_tiles == 1
+    const int pix0 = mt * BM;
+    const int n_img = pix0 / sg.HoWo;
+    const int rem = pix0 - n_img * sg.HoWo;
+    const int p = rem / sg.Wo;
+    const int q = rem - p * sg.Wo;
+    const int cw = q * sg.stride - sg.pad, ch = p * sg.stride - sg.pad;
+    const int half = sg.bn / 2;
+    for (int tap = 0; tap < sg.taps; ++tap) {
+      const int r = tap / sg.S;
+      const int s = tap - r * sg.S;
+      for (int kc = 0; kc < sg.cin_chunks; ++kc) {
+        mbar_wait(&S.empty[stage], phase ^ 1);     // local: the leader's commit multicasts to both CTAs
+        if (rank == 0) mbar_expect_tx(&S.full[stage], 2 * (A_BYTES + half * (BK * 2)));
+        const uint32_t bar = mapa_rank(smem_u32(&S.full[stage]), 0);
+        tma_load_im2col_4d_cta2(&sg.tmA, bar, S.sA + stage * S.a_stride, kc * BK, cw, ch, n_img, (uint16_t)s, (uint16_t)r);
+        tma_load_3d_cta2(&sg.tmB, bar, S.sB + stage * S.b_stride, kc * BK, (int)rank * half, tap);
+        if (++stage == nst) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  }
+}
+
+// Leader only: one tcgen05.mma.cta_group::2 of M = 256 x N = bn per 16-channel K step; commits multicast to both CTAs.
+__device__ __forceinline__ void conv_mma_cta2(const ConvParamsDev* P, const ConvSmem& S, uint32_t tmem_base) {
+  const int total = P->total_tiles, nst = S.nst;
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    const ConvSegDev& sg = P->seg[find_seg(P, tile)];
+    const int kiters = sg.taps * sg.cin_chunks;
+    const int acc = it & 1;
+    mbar_wait(&S.tempty[acc], ((it >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * 256;
+    const uint32_t idesc = make_idesc_bf16(2 * BM, sg.bn, 0, 0);
+    for (int ki = 0; ki < kiters; ++ki) {
+      mbar_wait(&S.full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(S.sA + stage * S.a_stride);
+      const uint32_t b_base = smem_u32(S.sB + stage * S.b_stride);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k)
+        umma_bf16_cta2(d_tmem, make_sdesc(a_base + k * 32, 16, 1024), make_sdesc(b_base + k * 32, 16, 1024), idesc,
+                       (ki | k) != 0);
+      umma_commit_cta2(&S.empty[stage]);
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit_cta2(&S.tfull[acc]);
+  }
+}
+
 // The whole parameter block (tile table + TMA descriptors, <= 10 KiB) travels as a __grid_constant__ kernel parameter:
 // it lives in the constant bank, so the per-tile / per-chunk reads of segment fields are constant-cache hits instead
 // of dependent global loads that every "memory"-clobbering barrier asm would force again.
-__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvParamsDev PP) {
-  const ConvParamsDev* P = &PP;
+template <bool CTA2>
+__device__ __forceinline__ void conv_igemm_body(const ConvParamsDev* P) {
   extern __shared__ uint8_t smem_raw[];
   const ConvSmem S = conv_carve(P, smem_raw);
   const int nbuf = P->nbuf;
@@ -385,13 +467,21 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   float* const sStat = S.sStat;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = conv_prologue(P, S, 8);
+  const uint32_t tmem_base = conv_prologue<CTA2>(P, S, 8);
   const int total = P->total_tiles;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
-    if (elect_one()) conv_producer(P, S);
+    if (elect_one()) {
+      if (CTA2) conv_producer_cta2(P, S, cta_rank);
+      else conv_producer(P, S);
+    }
   } else if (warp == 1) {
-    if (elect_one()) conv_mma(P, S, tmem_base);
+    if (CTA2) {
+      if (cta_rank == 0 && elect_one()) conv_mma_cta2(P, S, tmem_base);
+    } else if (elect_one()) {
+      conv_mma(P, S, tmem_base);
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (2 warpgroups x 4 warps)
     const int ew = warp & 3;          // TMEM lane quadrant this warp may read
@@ -639,7 +729,10 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         if (rend == bn) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if (CTA2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));   // the pair's MMA warp lives in rank 0
+            else mbar_arrive(&tempty[acc]);
+          }
         }
         if (shared) {
           fence_proxy_async();
@@ -680,10 +773,24 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) {   // the peer may still be reading this CTA's operands / signalling its barriers
+    __syncwarp();
+    cluster_sync_all();
+  }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTA2) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+__global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvParamsDev PP) {
+  conv_igemm_body<false>(&PP);
+}
+
+// Same kernel launched as clusters of two CTAs (cudaLaunchAttributeClusterDimension = 2): see ConvParamsDev::cta2.
+__global__ void __launch_bounds__(384, 1) conv_igemm_cta2_kernel(const __grid_constant__ ConvParamsDev PP) {
+  conv_igemm_body<true>(&PP);
 }
 
 // Fast kernel for plans whose every tile takes the lean epilogue (bf16 staged output, full chunks, no scale / GroupNorm
@@ -789,6 +896,7 @@ struct dslb_conv_plan {
   double flops = 0.0;
   int fast4 = 0;  // launch conv_igemm_fast4_kernel (16 epilogue warps)
   dslb_halo_plan* halo = nullptr;  // narrow 3x3 stride-1 conv: halo-tile kernel of conv_halo.cu instead
+  int cta2 = 0;   // launch conv_igemm_cta2_kernel as clusters of two CTAs
 };
 
 static int pick_bn(int cout_pad) {
@@ -1042,6 +1150,36 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     tiles = t;
     h->total_tiles = tiles;
   }
+  // CTA pairs (cta_group::2): compute-heavy plans whose every segment is one 256-wide n-tile with a staged bf16 output and
+  // no residual (the FCOSHead tower layers + their dgrads, the FPN output convs): M = 256 per MMA halves the weight bytes
+  // each SM pulls per k-iteration. DSLB_CTA2=0 switches it off.
+  bool cta2 = !fast4 && !pair && !any_ident && getenv("DSLB_CTA2") != nullptr && getenv("DSLB_CTA2")[0] == '1';
+  for (int i = 0; i < nseg && cta2; ++i) {
+    const ConvSegDev& d = h->seg[i];
+    if (!d.staged || d.bn != 256 || d.n_tiles != 1 || d.scatter2 || d.residual || d.taps * d.cin_chunks < 18) cta2 = false;
+  }
+  if (cta2) {   // every segment gets an even number of 128-pixel row tiles: a pair never straddles two segments
+    int t = 0;
+    for (int i = 0; i < nseg; ++i) {
+      ConvSegDev& d = h->seg[i];
+      const dslb_conv_seg_t& sg = segs[i];
+      d.m_tiles = (d.m_tiles + 1) & ~1;
+      d.tile_begin = t;
+      t += d.m_tiles * d.n_tiles;
+      // each CTA of the pair loads its own half of the weight tile: box of bn / 2 rows
+      const uint64_t wd[3] = {(uint64_t)sg.Cin, (uint64_t)sg.cout_pad, (uint64_t)(sg.R * sg.S)};
+      const uint64_t ws[2] = {(uint64_t)sg.Cin * 2, (uint64_t)sg.cout_pad * sg.Cin * 2};
+      const uint32_t wb[3] = {64, (uint32_t)d.bn / 2, 1};
+      const int rc2 = encode_tiled_bf16(&d.tmB, sg.w, 3, wd, ws, wb);
+      if (rc2 != DSLB_OK) {
+        delete h;
+        return rc2;
+      }
+    }
+    tiles = t;
+    h->total_tiles = tiles;
+  }
+  h->cta2 = cta2 ? 1 : 0;
   h->pair = pair ? 1 : 0;
   h->any_aux = any_aux ? 1 : 0;
   h->has_ident = any_ident ? 1 : 0;
@@ -1049,6 +1187,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   {
     int bn_max = 16;
     for (int i = 0; i < nseg; ++i) bn_max = h->seg[i].bn > bn_max ? h->seg[i].bn : bn_max;
+    if (cta2) bn_max /= 2;   // each CTA of a pair stages half of the weight tile
     h->b_stride = ((bn_max * BK * 2 + 1023) / 1024) * 1024;  // tiles stay 1024-byte aligned (128B swizzle atoms)
     const int budget = CONV_SMEM - 1024 - h->nbuf * OUT_BYTES - (any_ident ? IDENT_BYTES : 0) - BAR_BYTES - STAT_BYTES;
     int nst = budget / ((pair ? 2 : 1) * A_BYTES + h->b_stride);
@@ -1067,8 +1206,11 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
   plan->total_tiles = tiles;
   plan->flops = flops;
   plan->fast4 = fast4 ? 1 : 0;
+  plan->cta2 = cta2 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
+    DSLB_CHECK_CUDA(
+        cudaFuncSetAttribute(conv_igemm_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     DSLB_CHECK_CUDA(
         cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     DSLB_CHECK_CUDA(
@@ -1084,6 +1226,26 @@ extern "C" int dslb_conv_plan_run(const dslb_conv_plan_t* plan, void* stream) {
   if (plan->halo) return halo_plan_run(plan->halo, stream);
   const int work = plan->dev->pair ? plan->total_tiles / 2 : plan->total_tiles;
   const int grid = work < num_sms() ? work : num_sms();
+  if (plan->cta2) {
+    // clusters of two CTAs (same TPC): even grid, total_tiles is even by construction
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grid & ~1));
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = CONV_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    DSLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_cta2_kernel, *plan->dev));
+    DSLB_CHECK_CUDA(cudaGetLastError());
+    return DSLB_OK;
+  }
   if (plan->fast4)
     DSLB_CHECK_CUDA(launch_pdl(conv_igemm_fast4_kernel, dim3(grid), dim3(640), CONV_SMEM, (cudaStream_t)stream, *plan->dev));
   else
