@@ -393,7 +393,9 @@ __device__ __forceinline__ void conv_producer_cta2(const ConvParamsDev* P, const
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const ConvSegDev& sg = P->seg[find_seg(P, tile)];
-    const int mt = tile - sg.tile_begin;      // n_tiles == 1
+    const int tl = tile - sg.tile_begin;
+    const int nt = tl / sg.m_tiles;           // m_tiles is even: a pair shares its n-tile
+    const int mt = tl - nt * sg.m_tiles;
     const int pix0 = mt * BM;
     const int n_img = pix0 / sg.HoWo;
     const int rem = pix0 - n_img * sg.HoWo;
@@ -409,7 +411,7 @@ __device__ __forceinline__ void conv_producer_cta2(const ConvParamsDev* P, const
         if (rank == 0) mbar_expect_tx(&S.full[stage], 2 * (A_BYTES + half * (BK * 2)));
         const uint32_t bar = mapa_rank(smem_u32(&S.full[stage]), 0);
         tma_load_im2col_4d_cta2(&sg.tmA, bar, S.sA + stage * S.a_stride, kc * BK, cw, ch, n_img, (uint16_t)s, (uint16_t)r);
-        tma_load_3d_cta2(&sg.tmB, bar, S.sB + stage * S.b_stride, kc * BK, (int)rank * half, tap);
+        tma_load_3d_cta2(&sg.tmB, bar, S.sB + stage * S.b_stride, kc * BK, nt * sg.bn + (int)rank * half, tap);
         if (++stage == nst) {
           stage = 0;
           phase ^= 1;
@@ -1151,12 +1153,16 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     h->total_tiles = tiles;
   }
   // CTA pairs (cta_group::2): compute-heavy plans whose every segment is one 256-wide n-tile with a staged bf16 output and
-  // no residual (the FCOSHead tower layers + their dgrads, the FPN output convs): M = 256 per MMA halves the weight bytes
-  // each SM pulls per k-iteration. DSLB_CTA2=0 switches it off.
-  bool cta2 = !fast4 && !pair && !any_ident && getenv("DSLB_CTA2") != nullptr && getenv("DSLB_CTA2")[0] == '1';
-  for (int i = 0; i < nseg && cta2; ++i) {
-    const ConvSegDev& d = h->seg[i];
-    if (!d.staged || d.bn != 256 || d.n_tiles != 1 || d.scatter2 || d.residual || d.taps * d.cin_chunks < 18) cta2 = false;
+  // no residual (the FCOSHead tower layers + their dgrads, the FPN output / lateral convs, the 256- and 512-wide backbone
+  // convs): M = 256 per MMA halves the weight bytes each SM pulls per k-iteration. DSLB_CTA2=0 switches it off.
+  bool cta2 = !fast4 && !pair && !any_ident && !(getenv("DSLB_CTA2") != nullptr && getenv("DSLB_CTA2")[0] == '0');
+  {
+    int kmin = 8;   // k-iterations per tile from which the pair pays (DSLB_CTA2_KMIN overrides, for experiments)
+    if (const char* e = getenv("DSLB_CTA2_KMIN")) kmin = atoi(e);
+    for (int i = 0; i < nseg && cta2; ++i) {
+      const ConvSegDev& d = h->seg[i];
+      if (!d.staged || d.bn != 256 || d.scatter2 || d.residual || d.taps * d.cin_chunks < kmin) cta2 = false;
+    }
   }
   if (cta2) {   // every segment gets an even number of 128-pixel row tiles: a pair never straddles two segments
     int t = 0;

@@ -48,6 +48,47 @@ def test_cta2_conv_matches_fp32_reference(cta2_env, shape):
     assert e < 4e-3
 
 
+# (name, N, H, W, Cin, Cout, k, stride, pad, relu, mask)
+CASES = [
+    ("3x3 512->512, two n-tiles (layer4 conv2)", 2, 25, 42, 512, 512, 3, 1, 1, True, False),
+    ("1x1 1024->256 K=16 (layer3 conv1)", 2, 50, 84, 1024, 256, 1, 1, 0, True, False),
+    ("1x1 2048->256 (lateral)", 2, 25, 42, 2048, 256, 1, 1, 0, False, False),
+    ("1x1 stride 2 1024->512 (layer4 conv1, caffe style)", 2, 50, 84, 1024, 512, 1, 2, 0, True, False),
+    ("3x3 256->256 mask (layer3 conv2 dgrad)", 3, 50, 84, 256, 256, 3, 1, 1, False, True),
+    ("3x3 128->256 (predictor dgrad shape, K=18)", 2, 25, 43, 128, 256, 3, 1, 1, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_cta2_other_shapes(cta2_env, case):
+    from tests.test_gpu_kernels_r2 import _bf, _nhwc, _pack
+    from dsl_b200.engine import ConvPlan
+    _, N, H, W, Ci, Co, k, stride, pad, relu, use_mask = case
+    g = torch.Generator().manual_seed(Ci + Co + H)
+    x = _bf(torch.randn(N, Ci, H, W, generator=g))
+    w = _bf(torch.randn(Co, Ci, k, k, generator=g) * (1.0 / (Ci * k * k) ** 0.5))
+    shift = torch.randn(Co, generator=g) * 0.1
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    mask = _bf(torch.randn(N, Co, Ho, Wo, generator=g)) if use_mask else None
+    ref = F.conv2d(x.to(DEV), w.to(DEV), stride=stride, padding=pad) + shift.to(DEV).view(1, -1, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    if use_mask:
+        ref = ref * (mask.to(DEV) > 0)
+    y = torch.full((N, Ho, Wo, Co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    seg = dict(x=_nhwc(x), w=_pack(w, False), y=y, N=N, H=H, W=W, Cin=Ci, Cout=Co, cout_pad=Co, R=k, S=k, stride=stride,
+               pad=pad, ldc=Co, shift=shift.to(DEV), relu_nch=Co if relu else 0)
+    if use_mask:
+        seg["relu_mask"] = _nhwc(mask)
+    ConvPlan([seg], "cta2").run()
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    e = _rel(got, ref)
+    print(f"cta2 {case[0]}: rel {e:.2e}")
+    assert e < 4e-3
+
+
 def test_cta2_tower_layer_matches_single_cta_kernel(cta2_env):
     """The ten-segment FCOSHead tower layer (GroupNorm statistics in the epilogue) under both kernels: same bf16 maps,
     same statistics (summation order inside a tile is identical; across tiles it is fp64 atomics)."""
