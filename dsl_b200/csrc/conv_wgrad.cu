@@ -9,6 +9,7 @@
 //   B operand     X tile [64 pixels (+) tap][bn ci] loaded by bn/64 im2col-TMA boxes, MN-major likewise.
 //   Everything else (warp roles, mbarrier ring, TMEM double buffering) mirrors conv_igemm.cu.
 #include <new>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -20,7 +21,10 @@ constexpr int WG_STAGES = 4;
 constexpr int WG_BOX = 64 * 64 * 2;           // one [64 px][64 ch] box = 8 KiB
 constexpr int WG_A_BYTES = 2 * WG_BOX;        // 128 co
 constexpr int WG_B_BYTES_MAX = 4 * WG_BOX;    // up to 256 ci
+constexpr int WG_STAGES2 = 6;                 // CTA pairs stage half of the X tile: 32 KiB stages
+constexpr int WG_MAXST = 8;
 constexpr int WG_SMEM = 1024 + WG_STAGES * (WG_A_BYTES + WG_B_BYTES_MAX) + 256;
+static_assert(WG_STAGES2 * (WG_A_BYTES + WG_B_BYTES_MAX / 2) <= WG_STAGES * (WG_A_BYTES + WG_B_BYTES_MAX), "pair stages fit");
 constexpr int WG_TMEM_COLS = 512;
 
 struct alignas(128) WgSegDev {
@@ -39,6 +43,8 @@ struct alignas(128) WgParamsDev {
   WgSegDev seg[DSLB_MAX_SEGS];
   int nseg;
   int total_jobs;
+  int cta2;   // 1: CTA pairs (cta_group::2): jobs 2j / 2j+1 are the two 128-channel Cout tiles of one (tap, Cin tile, K split);
+              // they form one M = 256 MMA, each CTA staging its own dY tile and HALF of the X tile
 };
 
 struct WgJob {
@@ -53,12 +59,25 @@ __device__ __forceinline__ WgJob wg_decode(const WgParamsDev* P, int job) {
   int j = job - sg.job_begin;
   WgJob o;
   o.si = si;
-  const int ks = j % sg.ksplits;
-  j /= sg.ksplits;
-  o.nt = j % sg.n_tiles;
-  j /= sg.n_tiles;
-  o.mt = j % sg.m_tiles;
-  o.tap = j / sg.m_tiles;
+  int ks;
+  if (P->cta2) {   // (tap, m pair, nt, ks, m parity): the parity is the CTA's rank in its pair
+    const int lo = j & 1;
+    j >>= 1;
+    ks = j % sg.ksplits;
+    j /= sg.ksplits;
+    o.nt = j % sg.n_tiles;
+    j /= sg.n_tiles;
+    const int mp = j % (sg.m_tiles >> 1);
+    o.tap = j / (sg.m_tiles >> 1);
+    o.mt = 2 * mp + lo;
+  } else {
+    ks = j % sg.ksplits;
+    j /= sg.ksplits;
+    o.nt = j % sg.n_tiles;
+    j /= sg.n_tiles;
+    o.mt = j % sg.m_tiles;
+    o.tap = j / sg.m_tiles;
+  }
   o.c_begin = ks * sg.chunks_per_split;
   o.c_end = min(o.c_begin + sg.chunks_per_split, sg.chunks);
   return o;
@@ -70,15 +89,17 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // parameter block by value in the constant bank (see conv_igemm.cu)
-__global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgParamsDev PP) {
-  const WgParamsDev* P = &PP;
+template <bool CTA2>
+__device__ __forceinline__ void conv_wgrad_body(const WgParamsDev* P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NST = CTA2 ? WG_STAGES2 : WG_STAGES;
+  constexpr int B_STAGE = CTA2 ? WG_B_BYTES_MAX / 2 : WG_B_BYTES_MAX;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + WG_STAGES * WG_A_BYTES;
+  uint8_t* sB = smem + NST * WG_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * (WG_A_BYTES + WG_B_BYTES_MAX));
-  uint64_t* empty = full + WG_STAGES;
-  uint64_t* tfull = empty + WG_STAGES;
+  uint64_t* empty = full + WG_MAXST;
+  uint64_t* tfull = empty + WG_MAXST;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -87,19 +108,29 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
   pdl_launch_dependents();
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], CTA2 ? 8 : 4);
     }
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, WG_TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc2(tmem_slot, WG_TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, WG_TMEM_COLS);
+      tmem_relinquish();
+    }
   }
+  if (CTA2) {
+    __syncwarp();
+    cluster_sync_all();
+  }
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   pdl_wait();
   tc_fence_before();
   __syncthreads();
@@ -118,8 +149,9 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
         const int s = jb.tap - r * sg.S;
         const int co0 = jb.mt * 128;
         const int a_boxes = (co0 + 64 < sg.ldy) ? 2 : 1;  // second 64-channel block may not exist
-        const int b_boxes = sg.bn / 64;
-        const uint32_t tx = (a_boxes + b_boxes) * WG_BOX;
+        const int b_boxes = CTA2 ? sg.bn / 128 : sg.bn / 64;   // a pair's CTA stages half of the Cin tile
+        const uint32_t tx = (CTA2 ? 2 : 1) * (a_boxes + b_boxes) * WG_BOX;
+        const int ci0 = jb.nt * sg.bn + (CTA2 ? (int)cta_rank * (sg.bn / 2) : 0);
         for (int kc = jb.c_begin; kc < jb.c_end; ++kc) {
           const int pix0 = kc * WG_BK;
           const int n_img = pix0 / sg.HoWo;
@@ -127,14 +159,23 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
           const int p = rem / sg.Wo;
           const int q = rem - p * sg.Wo;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx);
           uint8_t* a = sA + stage * WG_A_BYTES;
-          uint8_t* b = sB + stage * WG_B_BYTES_MAX;
-          for (int i = 0; i < a_boxes; ++i) tma_load_2d(&sg.tmDY, &full[stage], a + i * WG_BOX, co0 + 64 * i, pix0);
-          for (int i = 0; i < b_boxes; ++i)
-            tma_load_im2col_4d(&sg.tmX, &full[stage], b + i * WG_BOX, jb.nt * sg.bn + 64 * i,
-                               q * sg.stride - sg.pad, p * sg.stride - sg.pad, n_img, (uint16_t)s, (uint16_t)r);
-          if (++stage == WG_STAGES) {
+          uint8_t* b = sB + stage * B_STAGE;
+          if (CTA2) {
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], tx);
+            const uint32_t bar = mapa_rank(smem_u32(&full[stage]), 0);
+            for (int i = 0; i < a_boxes; ++i) tma_load_2d_cta2(&sg.tmDY, bar, a + i * WG_BOX, co0 + 64 * i, pix0);
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_im2col_4d_cta2(&sg.tmX, bar, b + i * WG_BOX, ci0 + 64 * i, q * sg.stride - sg.pad,
+                                      p * sg.stride - sg.pad, n_img, (uint16_t)s, (uint16_t)r);
+          } else {
+            mbar_expect_tx(&full[stage], tx);
+            for (int i = 0; i < a_boxes; ++i) tma_load_2d(&sg.tmDY, &full[stage], a + i * WG_BOX, co0 + 64 * i, pix0);
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_im2col_4d(&sg.tmX, &full[stage], b + i * WG_BOX, ci0 + 64 * i, q * sg.stride - sg.pad,
+                                 p * sg.stride - sg.pad, n_img, (uint16_t)s, (uint16_t)r);
+          }
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
@@ -142,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if ((!CTA2 || cta_rank == 0) && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -153,25 +194,28 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        const uint32_t idesc = make_idesc_bf16(128, sg.bn, 1, 1);
+        const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : 128, sg.bn, 1, 1);
         for (int kc = jb.c_begin; kc < jb.c_end; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * WG_A_BYTES);
-          const uint32_t b_base = smem_u32(sB + stage * WG_B_BYTES_MAX);
+          const uint32_t b_base = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
           for (int k = 0; k < WG_BK / 16; ++k) {
             const uint64_t ad = make_sdesc(a_base + k * 2048, WG_BOX, 1024);
             const uint64_t bd = make_sdesc(b_base + k * 2048, WG_BOX, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kc > jb.c_begin) || (k != 0));
+            if (CTA2) umma_bf16_cta2(d_tmem, ad, bd, idesc, (kc > jb.c_begin) || (k != 0));
+            else umma_bf16(d_tmem, ad, bd, idesc, (kc > jb.c_begin) || (k != 0));
           }
-          umma_commit(&empty[stage]);
-          if (++stage == WG_STAGES) {
+          if (CTA2) umma_commit_cta2(&empty[stage]);
+          else umma_commit(&empty[stage]);
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (CTA2) umma_commit_cta2(&tfull[acc]);
+        else umma_commit(&tfull[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -201,16 +245,31 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));
+        else mbar_arrive(&tempty[acc]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) {
+    __syncwarp();
+    cluster_sync_all();
+  }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, WG_TMEM_COLS);
+    if (CTA2) tmem_dealloc2(tmem_base, WG_TMEM_COLS);
+    else tmem_dealloc(tmem_base, WG_TMEM_COLS);
   }
+}
+
+__global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgParamsDev PP) {
+  conv_wgrad_body<false>(&PP);
+}
+__global__ void __launch_bounds__(256, 1) conv_wgrad_cta2_kernel(const __grid_constant__ WgParamsDev PP) {
+  conv_wgrad_body<true>(&PP);
 }
 
 }  // namespace dslb
@@ -221,6 +280,7 @@ struct dslb_wgrad_plan {
   WgParamsDev* dev = nullptr;  // HOST copy, passed by value at launch
   int total_jobs = 0;
   double flops = 0.0;
+  int cta2 = 0;
 };
 
 extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, dslb_wgrad_plan_t** out) {
@@ -310,6 +370,14 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
   (void)base_jobs;
   h->nseg = nseg;
   h->total_jobs = jobs;
+  // CTA pairs: every segment's Cout is a multiple of 256 (two 128-channel tiles = one M = 256 MMA) and its Cin tile splits
+  // into two halves of whole 64-channel boxes. DSLB_CTA2=0 switches it off.
+  bool cta2 = !(getenv("DSLB_CTA2") != nullptr && getenv("DSLB_CTA2")[0] == '0');
+  for (int i = 0; i < nseg && cta2; ++i) {
+    const WgSegDev& d = h->seg[i];
+    if (d.cout % 256 != 0 || d.bn % 128 != 0 || d.ldy < d.cout) cta2 = false;
+  }
+  h->cta2 = cta2 ? 1 : 0;
 
   dslb_wgrad_plan* plan = new (std::nothrow) dslb_wgrad_plan();
   if (!plan) {
@@ -320,8 +388,10 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
   plan->dev = h;
   plan->total_jobs = jobs;
   plan->flops = flops;
+  plan->cta2 = cta2 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
+    DSLB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     DSLB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     attr_set = true;
   }
@@ -332,6 +402,25 @@ extern "C" int dslb_wgrad_plan_create(const dslb_wgrad_seg_t* segs, int nseg, ds
 extern "C" int dslb_wgrad_plan_run(const dslb_wgrad_plan_t* plan, void* stream) {
   DSLB_CHECK_ARG(plan && plan->dev, "dslb_wgrad_plan_run: null plan");
   const int grid = plan->total_jobs < num_sms() ? plan->total_jobs : num_sms();
+  if (plan->cta2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grid & ~1));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = WG_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    DSLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_cta2_kernel, *plan->dev));
+    DSLB_CHECK_CUDA(cudaGetLastError());
+    return DSLB_OK;
+  }
   DSLB_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, dim3(grid), dim3(256), WG_SMEM, (cudaStream_t)stream, *plan->dev));
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;

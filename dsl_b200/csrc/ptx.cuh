@@ -223,6 +223,13 @@ __device__ __forceinline__ void tma_load_im2col_4d_cta2(const void* desc, uint32
       "h"(off_h)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_cta2(const void* desc, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_cta2(const void* desc, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
                                                  int c2) {
   asm volatile(

@@ -176,6 +176,11 @@ WGRAD_CASES = [
     ("3x3 stride 2 256->256", 2, 25, 43, 256, 256, 3, 2, 1),
     ("3x3 256->80 (conv_cls, ldy 128)", 2, 13, 21, 256, 80, 3, 1, 1),
     ("3x3 512->512 tiny map", 2, 7, 11, 512, 512, 3, 1, 1),
+    # CTA-pair wgrad (Cout % 256 == 0): tower shape, several Cin tiles, several Cout pairs, Cin = 128 (one box per CTA)
+    ("3x3 256->256 tower level (CTA pairs)", 4, 50, 84, 256, 256, 3, 1, 1),
+    ("1x1 1024->256, four Cin tiles (CTA pairs)", 2, 50, 84, 1024, 256, 1, 1, 0),
+    ("1x1 256->1024, four Cout pairs... two pairs (CTA pairs)", 2, 25, 43, 256, 1024, 1, 1, 0),
+    ("3x3 128->256 (CTA pairs, one X box per CTA)", 2, 25, 42, 128, 256, 3, 1, 1),
 ]
 
 
