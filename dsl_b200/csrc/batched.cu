@@ -25,6 +25,8 @@ struct PackDescDev {
   int mode;
   float eps;
   int ldw;               // input channels per output-channel row of w in memory (>= I; > I for a slice of a wider tensor)
+  int it;                // tiled kernel: input channels per tile
+  __nv_bfloat16* out2;   // tiled kernel: the dgrad operand of a merged (mode 0 + mode 1) descriptor, else null
   long long work_begin;  // prefix sum of rows * cols8
 };
 
@@ -120,13 +122,23 @@ __global__ void pack_batched_kernel(const PackDescDev* __restrict__ D, int n, lo
 }
 
 // Tiled variant for the regular convs (O, I multiples of 32, no padding / offsets, <= 9 taps): one block = 32 output
-// channels x 32 input channels x all taps. The OIHW rows are read fully coalesced into shared memory (scaled by the
-// folded BatchNorm), then written tap plane by tap plane as 64-byte runs: [tap][o][i] (mode 0) or, transposed and
-// rotated by 180 degrees, [RS-1-tap][i][o] (mode 1). `work_begin` counts tiles here.
+// channels x `it` input channels x all taps, `it` = 32 * f with f the largest power of two such that f * R*S <= 9 and
+// it | I (256 input channels for a 1x1 conv, 32 for a 3x3), so a tile is up to 32 x 288 floats whatever the filter.
+// The OIHW rows are read fully coalesced into shared memory (scaled by the folded BatchNorm) ONCE and leave as the
+// fprop operand [tap][o][i] and/or, transposed and rotated by 180 degrees, the dgrad operand [RS-1-tap][i][o]: a
+// descriptor whose `out2` is set is the merge of a mode-0 and a mode-1 descriptor over the same weight (the plan
+// pairs them at creation). `work_begin` counts tiles here.
 constexpr int PT = 32;
 constexpr int PT_MAX_TAPS = 9;
-__global__ void __launch_bounds__(256) pack_tiled_kernel(const PackDescDev* __restrict__ D, int n, int total_tiles) {
-  __shared__ float st[PT][PT * PT_MAX_TAPS + 1];
+constexpr int PT_PITCH = PT * PT_MAX_TAPS + 1;
+
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256, 5) pack_tiled_kernel(const PackDescDev* __restrict__ D, int n, int total_tiles) {
+  __shared__ float st[PT][PT_PITCH];
   __shared__ float ssc[PT];
   const int tid = threadIdx.x;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -137,17 +149,18 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const PackDescDev* __re
     }
     const PackDescDev& d = D[lo];
     const int tl = tile - (int)d.work_begin;
-    const int itiles = d.I / PT;
+    const int IT = d.it;
+    const int itiles = d.I / IT;
     const int ot = tl / itiles, it = tl - ot * itiles;
-    const int o0 = ot * PT, i0 = it * PT;
+    const int o0 = ot * PT, i0 = it * IT;
     const int RS = d.R * d.S;
-    const int rowlen = PT * RS;
+    const int pieces = (IT >> 5) * RS;   // 128-byte pieces per tile row, <= 9
     if (tid < PT) {
       float sc = 1.f;
       if (d.bn_gamma) {
         const int o = o0 + tid;
         sc = d.bn_gamma[o] / sqrtf(d.bn_var[o] + d.eps);
-        if (d.mode == 0 && it == 0) {
+        if (d.scale_out && it == 0) {
           d.scale_out[o] = sc;
           d.shift_out[o] = d.bn_beta[o] - d.bn_mean[o] * sc;
         }
@@ -166,41 +179,57 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const PackDescDev* __re
         float v[PT_MAX_TAPS];
 #pragma unroll
         for (int j = 0; j < PT_MAX_TAPS; ++j)
-          if (j < RS) v[j] = __ldg(src + 32 * j);
+          if (j < pieces) v[j] = __ldg(src + 32 * j);
         const float sc = ssc[oo];
 #pragma unroll
         for (int j = 0; j < PT_MAX_TAPS; ++j)
-          if (j < RS) st[oo][lane + 32 * j] = v[j] * sc;
+          if (j < pieces) st[oo][lane + 32 * j] = v[j] * sc;
       }
     }
-    (void)rowlen;
     __syncthreads();
-    // 16-byte stores: one thread = 8 consecutive packed columns of one (tap, row)
-    const int octs = RS * PT * (PT / 8);
-    if (d.mode == 0) {
-      for (int idx = tid; idx < octs; idx += 256) {
-        const int i8 = idx & 3, oo = (idx >> 2) & 31, tap = idx >> 7;
-        const float* sp = &st[oo][(8 * i8) * RS + tap];
-        uint4 o;
-        __nv_bfloat162 h;
-        h = __floats2bfloat162_rn(sp[0], sp[RS]); o.x = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[2 * RS], sp[3 * RS]); o.y = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[4 * RS], sp[5 * RS]); o.z = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[6 * RS], sp[7 * RS]); o.w = *reinterpret_cast<uint32_t*>(&h);
-        *reinterpret_cast<uint4*>(d.out + ((long long)tap * d.rows_pad + o0 + oo) * d.cols_pad + i0 + 8 * i8) = o;
+    __nv_bfloat16* const out_f = d.mode == 0 ? d.out : nullptr;
+    __nv_bfloat16* const out_t = d.mode == 1 ? d.out : d.out2;
+    if (out_f) {
+      if (RS == 1) {
+        // 1x1: a tile row is `IT` consecutive packed columns; one lane = 2 of them (conflict-free shared reads,
+        // 128-byte warp stores)
+        const int half = IT >> 1;
+        for (int idx = tid; idx < PT * half; idx += 256) {
+          const int oo = idx / half, pr = idx - oo * half;
+          const float* sp = &st[oo][2 * pr];
+          *reinterpret_cast<uint32_t*>(out_f + (long long)(o0 + oo) * d.cols_pad + i0 + 2 * pr) = pack_bf162(sp[0], sp[1]);
+        }
+      } else {
+        // 16-byte stores: one thread = 8 consecutive packed columns of one (tap, row)
+        const int i8n = IT >> 3;
+        const int octs = RS * PT * i8n;
+        for (int idx = tid; idx < octs; idx += 256) {
+          const int i8 = idx % i8n, r2 = idx / i8n;
+          const int oo = r2 & (PT - 1), tap = r2 >> 5;
+          const float* sp = &st[oo][(8 * i8) * RS + tap];
+          uint4 o;
+          o.x = pack_bf162(sp[0], sp[RS]);
+          o.y = pack_bf162(sp[2 * RS], sp[3 * RS]);
+          o.z = pack_bf162(sp[4 * RS], sp[5 * RS]);
+          o.w = pack_bf162(sp[6 * RS], sp[7 * RS]);
+          *reinterpret_cast<uint4*>(out_f + ((long long)tap * d.rows_pad + o0 + oo) * d.cols_pad + i0 + 8 * i8) = o;
+        }
       }
-    } else {
-      constexpr int PITCH = PT * PT_MAX_TAPS + 1;
+    }
+    if (out_t) {
+      // transposed operand: rows are input channels, 32 output channels = one 64-byte run per (tap, input channel)
+      const int rows_t = d.mode == 1 ? d.rows_pad : d.I, cols_t = d.mode == 1 ? d.cols_pad : d.O;
+      const int octs = RS * IT * (PT / 8);
       for (int idx = tid; idx < octs; idx += 256) {
-        const int o8 = idx & 3, ii = (idx >> 2) & 31, tap = idx >> 7;
+        const int o8 = idx & 3, r2 = idx >> 2;
+        const int ii = r2 % IT, tap = r2 / IT;
         const float* sp = &st[8 * o8][ii * RS + tap];
         uint4 o;
-        __nv_bfloat162 h;
-        h = __floats2bfloat162_rn(sp[0], sp[PITCH]); o.x = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[2 * PITCH], sp[3 * PITCH]); o.y = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[4 * PITCH], sp[5 * PITCH]); o.z = *reinterpret_cast<uint32_t*>(&h);
-        h = __floats2bfloat162_rn(sp[6 * PITCH], sp[7 * PITCH]); o.w = *reinterpret_cast<uint32_t*>(&h);
-        *reinterpret_cast<uint4*>(d.out + ((long long)(RS - 1 - tap) * d.rows_pad + i0 + ii) * d.cols_pad + o0 + 8 * o8) = o;
+        o.x = pack_bf162(sp[0], sp[PT_PITCH]);
+        o.y = pack_bf162(sp[2 * PT_PITCH], sp[3 * PT_PITCH]);
+        o.z = pack_bf162(sp[4 * PT_PITCH], sp[5 * PT_PITCH]);
+        o.w = pack_bf162(sp[6 * PT_PITCH], sp[7 * PT_PITCH]);
+        *reinterpret_cast<uint4*>(out_t + ((long long)(RS - 1 - tap) * rows_t + i0 + ii) * cols_t + o0 + 8 * o8) = o;
       }
     }
     __syncthreads();
@@ -377,6 +406,8 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
     d.mode = s.mode;
     d.eps = s.bn_eps;
     d.ldw = s.w_ld > 0 ? s.w_ld : s.I;
+    d.it = PT;
+    d.out2 = nullptr;
     if (d.ldw < s.I) {
       delete[] h;
       delete[] ht;
@@ -401,14 +432,38 @@ extern "C" int dslb_pack_plan_create(const dslb_pack_desc_t* descs, int n, dslb_
                        s.col_off == 0 && s.rows_pad == real_rows && s.cols_pad == real_cols && s.cols_pad % 8 == 0 &&
                        ((uintptr_t)s.out % 16) == 0;
     if (tiled) {
-      d.work_begin = tiles;
-      tiles += (long long)(s.O / PT) * (s.I / PT);
+      int f = 1;
+      while (2 * f * s.R * s.S <= PT_MAX_TAPS && (s.I / PT) % (2 * f) == 0) f *= 2;
+      d.it = PT * f;
       ht[ntiled++] = d;
     } else {
       d.work_begin = w;
       w += (long long)d.rows * d.cols8;
       h[nslow++] = d;
     }
+  }
+  // a conv's fprop and dgrad operands come from the same weight: merge the two descriptors so the tile is read once
+  for (int a = 0; a < ntiled; ++a) {
+    if (ht[a].mode != 0) continue;
+    for (int b = 0; b < ntiled; ++b) {
+      const PackDescDev& t = ht[b];
+      if (t.mode == 1 && t.w == ht[a].w && t.O == ht[a].O && t.I == ht[a].I && t.R == ht[a].R && t.S == ht[a].S &&
+          t.ldw == ht[a].ldw && t.bn_gamma == ht[a].bn_gamma && t.bn_var == ht[a].bn_var && t.eps == ht[a].eps) {
+        ht[a].out2 = t.out;
+        ht[b].mode = -1;   // absorbed
+        break;
+      }
+    }
+  }
+  {
+    int m = 0;
+    for (int k = 0; k < ntiled; ++k)
+      if (ht[k].mode >= 0) ht[m++] = ht[k];
+    ntiled = m;
+  }
+  for (int k = 0; k < ntiled; ++k) {
+    ht[k].work_begin = tiles;
+    tiles += (long long)(ht[k].O / PT) * (ht[k].I / ht[k].it);
   }
   dslb_table_plan* p = new (std::nothrow) dslb_table_plan();
   cudaError_t e = p ? cudaSuccess : cudaErrorMemoryAllocation;
@@ -514,7 +569,7 @@ extern "C" int dslb_table_plan_run(const dslb_table_plan_t* p, void* stream) {
   if (blocks > cap) blocks = cap;
   if (p->kind == 0) {
     if (p->n_tiled) {
-      const int tb = p->tiles < num_sms() * 6 ? p->tiles : num_sms() * 6;
+      const int tb = p->tiles < num_sms() * 5 ? p->tiles : num_sms() * 5;
       pack_tiled_kernel<<<tb, 256, 0, (cudaStream_t)stream>>>((const PackDescDev*)p->dev_tiled, p->n_tiled, p->tiles);
     }
     if (p->n)

@@ -407,3 +407,58 @@ def test_candidate_cap_overflow_is_reported():
     torch.cuda.synchronize()
     assert int(post.cand_counts[0]) > 1024
     assert post.overflowed() and not post.overflowed(), "flag is sticky until read, then cleared"
+
+
+# ---- multi-tensor operand refresh: one table launch == per-tensor torch restatement, bit for bit ----------------------
+@pytest.mark.gpu
+def test_pack_table_tiled_tiles_and_merged_operands_bit_exact():
+    """dslb_pack_plan_*: the tiled kernel picks its tile width from the filter (256 input channels for a 1x1 down to 32
+    for a 3x3) and writes the fprop AND the dgrad operand of a conv from one read when both descriptors are in the
+    table. Every operand must equal the bf16 rounding of w * bn_scale in its layout exactly."""
+    from dsl_b200.engine import TablePlan
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dev = "cuda"
+    shapes = [(64, 64, 1, True, True), (256, 64, 1, True, False), (128, 512, 1, True, True), (512, 2048, 1, False, True),
+              (64, 96, 1, True, True), (128, 128, 3, True, True), (256, 256, 3, False, True), (64, 64, 3, True, False),
+              (32, 160, 1, False, True), (96, 32, 3, False, True)]
+    descs, checks = [], []
+    for O, I, k, bn, dgrad in shapes:
+        w = torch.randn(O, I, k, k, generator=g).to(dev)
+        d = dict(w=w, O=O, I=I, R=k, S=k, fill_padding=1)
+        sc = torch.ones(O, device=dev)
+        extra = {}
+        if bn:
+            gam, bet = torch.rand(O, generator=g).to(dev) + 0.5, torch.randn(O, generator=g).to(dev)
+            mu, var = torch.randn(O, generator=g).to(dev), torch.rand(O, generator=g).to(dev) + 0.1
+            sc = gam / torch.sqrt(var + 1e-5)
+            extra = dict(bn_gamma=gam, bn_beta=bet, bn_mean=mu, bn_var=var, bn_eps=1e-5,
+                         scale_out=torch.zeros(O, device=dev), shift_out=torch.zeros(O, device=dev))
+            checks.append(("scale", extra["scale_out"], sc))
+            checks.append(("shift", extra["shift_out"], bet - mu * sc))
+        ws = (w * sc.view(-1, 1, 1, 1))
+        wp = torch.full((k * k, O, I), 7.0, dtype=torch.bfloat16, device=dev)
+        descs.append(dict(d, out=wp, rows_pad=O, cols_pad=I, mode=0, **extra))
+        checks.append((f"fprop {O}x{I}x{k}", wp, ws.permute(2, 3, 0, 1).reshape(k * k, O, I).to(torch.bfloat16)))
+        if dgrad:
+            wpT = torch.full((k * k, I, O), 7.0, dtype=torch.bfloat16, device=dev)
+            dd = dict(d, out=wpT, rows_pad=I, cols_pad=O, mode=1, **extra)
+            # the dgrad descriptor of every other conv sits far from its fprop one in the table
+            (descs.append if len(descs) % 4 else (lambda x: descs.insert(0, x)))(dd)
+            checks.append((f"dgrad {O}x{I}x{k}", wpT,
+                           ws.flip(2, 3).permute(2, 3, 1, 0).reshape(k * k, I, O).to(torch.bfloat16)))
+    plan = TablePlan(descs, "pack", "test table")
+    plan.run()
+    torch.cuda.synchronize()
+    for name, got, want in checks:
+        if got.dtype == torch.bfloat16:
+            assert torch.equal(got.view(torch.int16), want.contiguous().view(torch.int16)), name
+        else:
+            assert torch.allclose(got, want, rtol=1e-6, atol=1e-7), name
+    # dgrad-only descriptor (no fprop partner in the table)
+    w = torch.randn(128, 256, 3, 3, generator=g).to(dev)
+    wpT = torch.zeros(9, 256, 128, dtype=torch.bfloat16, device=dev)
+    TablePlan([dict(w=w, out=wpT, O=128, I=256, R=3, S=3, rows_pad=256, cols_pad=128, mode=1, fill_padding=1)], "pack",
+              "dgrad only").run()
+    torch.cuda.synchronize()
+    assert torch.equal(wpT.view(torch.int16),
+                       w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 256, 128).to(torch.bfloat16).contiguous().view(torch.int16))
