@@ -27,7 +27,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 102      # what include/dslb.h declares; an older build lacks entry points this package binds
+ABI_VERSION = 103      # what include/dslb.h declares; an older build lacks entry points this package binds
 lib.dslb_version.restype = C.c_int
 if lib.dslb_version() < ABI_VERSION:
     raise DslbError(f"{LIB_PATH} is version {lib.dslb_version()}, include/dslb.h is {ABI_VERSION}: rebuild it "
@@ -44,6 +44,8 @@ class ConvSeg(C.Structure):
         ("R", C.c_int32), ("S", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("ldc", C.c_int32), ("out_fp32", C.c_int32), ("relu_nch", C.c_int32), ("gn_cpg", C.c_int32),
         ("scatter2", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
+        ("gnb_x", C.c_void_p), ("gnb_mr", C.c_void_p), ("gnb_gamma", C.c_void_p), ("gnb_beta", C.c_void_p),
+        ("gnb_sums", C.c_void_p),
     ]
 
 
@@ -64,6 +66,7 @@ class GnSeg(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("red", C.c_void_p), ("dbias", C.c_void_p),
         ("mr", C.c_void_p),
         ("N", C.c_int32), ("HW", C.c_int32),
+        ("gsums", C.c_void_p),
     ]
 
 

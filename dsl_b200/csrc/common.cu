@@ -117,4 +117,4 @@ int encode_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, i
 }  // namespace dslb
 
 extern "C" const char* dslb_last_error(void) { return dslb::g_err; }
-extern "C" int dslb_version(void) { return 102; }  // 102: + dslb_fcos_topk_points
+extern "C" int dslb_version(void) { return 103; }  // 103: + dslb_conv_seg_t::gnb_*, dslb_gn_seg_t::gsums

@@ -292,7 +292,7 @@ bool dslb::halo_eligible(const dslb_conv_seg_t& s) {
   if (getenv("DSLB_NO_HALO")) return false;
   if (s.R != 3 || s.S != 3 || s.stride != 1 || s.pad != 1) return false;
   if (!(s.Cin == 64 || s.Cin == 128) || !(s.Cout == 64 || s.Cout == 128) || s.cout_pad != s.Cout) return false;
-  if (s.out_fp32 || s.scatter2 || s.gn_stats || s.scale || s.residual) return false;
+  if (s.out_fp32 || s.scatter2 || s.gn_stats || s.gnb_x || s.scale || s.residual) return false;
   if (!(s.relu_nch == 0 || s.relu_nch >= s.Cout) || s.ldc % 8 != 0) return false;
   if (s.W < HP_COLS || s.H < 1) return false;
   return true;

@@ -51,7 +51,11 @@ struct alignas(128) ConvSegDev {
   const void* relu_mask;
   const float* scale;
   const float* shift;
-  double* stats;
+  double* stats;             // GroupNorm sums of this output (forward), or of the GroupNorm backward below (gnb_x set)
+  const void* gnb_x;         // GroupNorm BACKWARD sums: pre-norm map [npix][cout] bf16 of the norm this output flows into
+  const float4* gnb_mr;      // [N][groups] (mean, rstd, -, -) of that norm
+  const float* gnb_gamma;    // [cout]
+  const float* gnb_beta;     // [cout]
   int npix, HoWo, Wo;
   int m_tiles, n_tiles, tile_begin;
   int cin_chunks, taps, S, stride, pad;
@@ -59,7 +63,7 @@ struct alignas(128) ConvSegDev {
   int out_fp32, relu_nch, cpg, groups;
   int scatter2, Hs, Ws;
   int staged;  // 1: bf16 output goes through the smem staging tile + TMA store
-  int aux_kind;  // 0: none; 1: residual, 2: ReLU mask arrive by TMA in the staging slab and are consumed in place
+  int aux_kind;  // 0: none; 1: residual, 2: ReLU mask, 3: gnb_x tile arrive by TMA in the staging slab, consumed in place
   int res_mma;   // 1: the residual is added on the tensor core: after the K loop its [128 px][64 ch] tiles travel
                  // through the operand ring as A tiles and are multiplied by a shared-memory 64x64 identity into
                  // the matching 64 accumulator columns, so the epilogue never sees it (`residual` is null then)
@@ -602,7 +606,7 @@ __device__ __forceinline__ void conv_igemm_body(const ConvParamsDev* P) {
         // the bf16x2 conversion and the mask is applied to the packed result, so a chunk costs ~50-80 instructions.
         const int relu_nch = sg.relu_nch;
         const int tile_c0 = nt * bn;
-        const bool fast = staged && !do_stats && sg.scale == nullptr && tile_c0 + bn <= sg.cout &&
+        const bool fast = staged && !do_stats && aux_here != 3 && sg.scale == nullptr && tile_c0 + bn <= sg.cout &&
                           (relu_nch >= tile_c0 + bn || relu_nch <= tile_c0) &&
                           (sg.residual == nullptr || aux_here == 1) && (sg.relu_mask == nullptr || aux_here == 2);
         if (fast) {
@@ -625,12 +629,50 @@ __device__ __forceinline__ void conv_igemm_body(const ConvParamsDev* P) {
           const int cb = nt * bn + c0;  // first global output channel of this chunk
           const bool fullchunk = (cb + 16 <= sg.cout);
           float v[16];
-          epilogue_math(sg, rr, v, cb, fullchunk, valid, row, aux_here, a0, a1);
+          epilogue_math(sg, rr, v, cb, fullchunk, valid, row, aux_here == 3 ? 0 : aux_here, a0, a1);
           if (do_stats) {
             // GroupNorm partial sums of the two 8-channel halves of this chunk, reduced over the warp's 32 pixels
             // with a 6-shuffle butterfly; lanes 0/8/16/24 end up with (s1,h0) (s2,h0) (s1,h1) (s2,h1).
             float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
-            if (valid) {
+            if (valid && sg.gnb_x) {
+              // backward of conv-bias -> GroupNorm -> ReLU in front of this output: v is dz (the gradient w.r.t. the
+              // post-ReLU map), rounded to the bf16 the apply pass will read back. Per 8-channel half:
+              //   (a | b) = sum gamma * dy,  (c | d) = sum gamma * dy * xhat,  dy = dz * [xhat * gamma + beta > 0]
+              // (x tile: brought into the staging slab by TMA like a residual tile, aux_kind 3; else read from memory)
+              uint4 x0 = a0, x1 = a1;
+              if (aux_here != 3) {
+                const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(sg.gnb_x) +
+                                                                 (long long)pix * sg.cout + cb);
+                x0 = __ldg(xp);
+                x1 = __ldg(xp + 1);
+              }
+              const float4 m0 = __ldg(sg.gnb_mr + n_img * sg.groups + cb / sg.cpg);
+              const float4 m1 = __ldg(sg.gnb_mr + n_img * sg.groups + (cb + 8) / sg.cpg);
+              const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(sg.gnb_gamma + cb) + q);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(sg.gnb_beta + cb) + q);
+                const float gq[4] = {g4.x, g4.y, g4.z, g4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
+                const float mean = q < 2 ? m0.x : m1.x, rstd = q < 2 ? m0.y : m1.y;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * q + e;
+                  const uint32_t w2 = xw[j >> 1];
+                  const float xv = __uint_as_float((j & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
+                  const float xh = (xv - mean) * rstd;
+                  const float dzr = __bfloat162float(__float2bfloat16_rn(v[j]));
+                  const float gd = fmaf(xh, gq[e], bq[e]) > 0.f ? gq[e] * dzr : 0.f;
+                  if (q < 2) {
+                    a += gd;
+                    c = fmaf(gd, xh, c);
+                  } else {
+                    b += gd;
+                    d = fmaf(gd, xh, d);
+                  }
+                }
+              }
+            } else if (valid) {
               if (fullchunk) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -958,7 +1000,7 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
         if (bn > cap && s.cout_pad % cap == 0) bn = cap;
         // residual / mask tiles by TMA need > 64 channels; GroupNorm statistics were tuned for full-width tiles
         if (cap < 128 && (s.residual || s.relu_mask)) bn = pick_bn(s.cout_pad) > 128 && s.cout_pad % 128 == 0 ? 128 : pick_bn(s.cout_pad);
-        if (s.gn_stats) bn = pick_bn(s.cout_pad);
+        if (s.gn_stats || s.gnb_x) bn = pick_bn(s.cout_pad);
         const long long t = (long long)cdiv(s.N * Ho * Wo, BM) * (s.cout_pad / bn);
         const double kit = (double)s.R * s.S * (s.Cin / 64);
         ntile += t;
@@ -1002,6 +1044,16 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
       SEG_CHECK(s.gn_cpg == 8 || s.gn_cpg == 16, "conv seg %d: gn_cpg=%d must be 8 or 16", i, s.gn_cpg);
       SEG_CHECK(s.Cout % s.gn_cpg == 0, "conv seg %d: Cout %% gn_cpg != 0", i);
     }
+    if (s.gnb_x) {
+      SEG_CHECK(!s.gn_stats && s.gnb_mr && s.gnb_gamma && s.gnb_beta && s.gnb_sums,
+                "conv seg %d: gnb_x needs gnb_mr / gnb_gamma / gnb_beta / gnb_sums and excludes gn_stats", i);
+      SEG_CHECK((s.gn_cpg == 8 || s.gn_cpg == 16) && s.Cout % 16 == 0 && s.cout_pad == s.Cout && s.Cout % s.gn_cpg == 0 &&
+                    !s.scatter2 && !s.out_fp32,
+                "conv seg %d: gnb_x needs gn_cpg 8 or 16, Cout %% 16 == 0, a bf16 non-scattered output", i);
+      SEG_CHECK(((uintptr_t)s.gnb_x % 16) == 0 && ((uintptr_t)s.gnb_mr % 16) == 0 && ((uintptr_t)s.gnb_gamma % 16) == 0 &&
+                    ((uintptr_t)s.gnb_beta % 16) == 0,
+                "conv seg %d: gnb pointers must be 16-byte aligned", i);
+    }
     if (s.scatter2) SEG_CHECK(s.Hs >= 2 * Ho - 1 && s.Ws >= 2 * Wo - 1, "conv seg %d: scatter map too small", i);
 #undef SEG_CHECK
     d.y = s.y;
@@ -1009,12 +1061,16 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     d.relu_mask = s.relu_mask;
     d.scale = s.scale;
     d.shift = s.shift;
-    d.stats = s.gn_stats;
+    d.stats = s.gnb_x ? s.gnb_sums : s.gn_stats;
+    d.gnb_x = s.gnb_x;
+    d.gnb_mr = reinterpret_cast<const float4*>(s.gnb_mr);
+    d.gnb_gamma = s.gnb_gamma;
+    d.gnb_beta = s.gnb_beta;
     d.npix = s.N * Ho * Wo;
     d.HoWo = Ho * Wo;
     d.Wo = Wo;
     d.bn = pick_bn(s.cout_pad);
-    if (!s.gn_stats) {
+    if (!s.gn_stats && !s.gnb_x) {
       if (d.bn > bn_cap && s.cout_pad % bn_cap == 0) d.bn = bn_cap;
       if (bn_cap < 128 && (s.residual || s.relu_mask))
         d.bn = pick_bn(s.cout_pad) > 128 && s.cout_pad % 128 == 0 ? 128 : pick_bn(s.cout_pad);
@@ -1032,8 +1088,8 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
     d.ldc = s.ldc;
     d.out_fp32 = s.out_fp32;
     d.relu_nch = s.relu_nch;
-    d.cpg = s.gn_stats ? s.gn_cpg : 16;
-    d.groups = s.gn_stats ? s.Cout / s.gn_cpg : 1;
+    d.cpg = (s.gn_stats || s.gnb_x) ? s.gn_cpg : 16;
+    d.groups = (s.gn_stats || s.gnb_x) ? s.Cout / s.gn_cpg : 1;
     d.scatter2 = s.scatter2;
     d.Hs = s.Hs;
     d.Ws = s.Ws;
@@ -1083,6 +1139,20 @@ extern "C" int dslb_conv_plan_create(const dslb_conv_seg_t* segs, int nseg, dslb
       const uint64_t as[1] = {(uint64_t)s.ldc * 2};
       const uint32_t ab[2] = {64, (uint32_t)BM};
       rc = encode_tiled_bf16(&d.tmAux, aux, 2, ad, as, ab);
+      if (rc != DSLB_OK) {
+        delete h;
+        return rc;
+      }
+      any_aux = true;
+    }
+    if (d.aux_kind == 0 && s.gnb_x && d.staged && s.Cout % 64 == 0 && d.bn > 64 && getenv("DSLB_GNB_NO_TMA") == nullptr) {
+      // the pre-norm tile of the GroupNorm backward sums travels like a residual tile: [128 px][64 ch] by TMA into the
+      // staging slab, read in place by the thread that then overwrites the same bytes with its output
+      d.aux_kind = 3;
+      const uint64_t ad[2] = {(uint64_t)s.Cout, (uint64_t)d.npix};
+      const uint64_t as[1] = {(uint64_t)s.Cout * 2};
+      const uint32_t ab[2] = {64, (uint32_t)BM};
+      rc = encode_tiled_bf16(&d.tmAux, s.gnb_x, 2, ad, as, ab);
       if (rc != DSLB_OK) {
         delete h;
         return rc;

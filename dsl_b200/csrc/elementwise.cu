@@ -196,6 +196,7 @@ struct GnSeg {
   double* red;              // bwd: [N][C][2] (sum dy, sum dy*xhat), fp64
   float* dbias;             // bwd: [C] += sum dx
   float4* mr;               // [N][G] (mean, rstd, k1, k2) in fp32: .xy written by the forward apply, .zw by the backward
+  const double* gsums;      // bwd: [N][G][DSLB_GN_STAT_STRIDE] group sums from the producing conv's epilogue, or null
   int HW, npix;             // pixels per image, N*HW
   long long work_begin;     // prefix of (npix * C/8) work items
 };
@@ -259,9 +260,19 @@ __global__ void gn_apply_relu_kernel(const __grid_constant__ GnParams P) {
   }
 }
 
+// (sum, sumsq) of one (image, group) in fp64 -> (mean, rstd) in fp32, the arithmetic of gn_finalize_kernel
+__device__ __forceinline__ float2 gn_mean_rstd(const double* __restrict__ st, double m, float eps) {
+  const double mean = st[0] / m;
+  double var = st[1] / m - mean * mean;
+  if (var < 0) var = 0;
+  return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 // Same, driven by the block table of the backward (block = GN_PIXB pixels of ONE image of ONE map; thread = one
-// 8-channel group x one of 8 pixel lanes): per-thread constants (mean, rstd, gamma, beta) are loaded once and the loop
-// body is two 16-byte accesses and 16 FMAs — no per-element search or integer division.
+// 8-channel group x one of 8 pixel lanes): per-thread constants (mean, rstd, gamma, beta) are computed once and the loop
+// body is two 16-byte accesses and 16 FMAs — no per-element search or integer division. The (mean, rstd) of the
+// thread's group come straight from the fp64 sums of the conv epilogue (no separate finalize launch); the first block of
+// every image leaves them in `mr` for the backward.
 __global__ void __launch_bounds__(256) gn_apply_relu_tab_kernel(const __grid_constant__ GnParams P,
                                                                 const int* __restrict__ blk_seg,
                                                                 const int* __restrict__ blk_pix0) {
@@ -271,7 +282,13 @@ __global__ void __launch_bounds__(256) gn_apply_relu_tab_kernel(const __grid_con
   const int pend = min(pix0 + 256, (n + 1) * s.HW);
   const int c8 = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int G = P.C / P.cpg;
-  const float4 mr = __ldg(s.mr + n * G + (c8 * 8) / P.cpg);
+  const int g = (c8 * 8) / P.cpg;
+  const float2 mr = gn_mean_rstd(s.stats + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE, (double)P.cpg * s.HW, P.eps);
+  if (pix0 == n * s.HW && pl == 0 && (c8 * 8) % P.cpg == 0) {
+    float4* o = s.mr + n * G + g;
+    o->x = mr.x;
+    o->y = mr.y;
+  }
   float a_[8], b_[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -321,7 +338,7 @@ __global__ void gn_bwd_reduce_kernel(const __grid_constant__ GnParams P, const i
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - fmean) * rstd;
-      const float dy = (xh * ga[e] + be[e] > 0.f) ? d[e] : 0.f;
+      const float dy = (fmaf(xh, ga[e], be[e]) > 0.f) ? d[e] : 0.f;
       A[e] += dy;
       B[e] += dy * xh;
     }
@@ -367,9 +384,14 @@ __global__ void gn_bwd_finalize_kernel(const __grid_constant__ GnParams P, int m
 
 // Backward pass 2: dx = rstd * (gamma*dy - S1/m - xhat*S2/m), S1 = sum_{c in g} gamma_c A_c, S2 likewise with B;
 // also accumulates dbias[c] += sum dx (the conv bias in front of the GroupNorm).
-__global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const int* __restrict__ blk_seg,
-                                    const int* __restrict__ blk_pix0) {
-  __shared__ float sm[8][256];
+// FUSED: the producing conv's epilogue already left S1, S2 per (image, group) in `gsums` (dslb_conv_seg_t::gnb_sums), so
+// there was no reduce pass: the two constants are formed here, and the per-(image, channel) sums A, B that dgamma /
+// dbeta need (`red`) are accumulated in this pass too.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __grid_constant__ GnParams P,
+                                                           const int* __restrict__ blk_seg,
+                                                           const int* __restrict__ blk_pix0) {
+  __shared__ float sm[FUSED ? 3 : 1][8][256];
   const GnSeg& s = P.seg[blk_seg[blockIdx.x]];
   const int pix0 = blk_pix0[blockIdx.x];
   const int n = pix0 / s.HW;
@@ -378,13 +400,22 @@ __global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const in
   const int G = P.C / P.cpg;
   const int g = (c8 * 8) / P.cpg;
   const float4 mr = __ldg(s.mr + n * G + g);
-  const float rstd = mr.y, fmean = mr.x, k1 = mr.z, k2 = mr.w;
-  float ga[8], be[8], D[8];
+  const float rstd = mr.y, fmean = mr.x;
+  float k1 = mr.z, k2 = mr.w;
+  if (FUSED) {
+    const double* gs = s.gsums + ((long long)n * G + g) * DSLB_GN_STAT_STRIDE;
+    const double m = (double)P.cpg * s.HW;
+    k1 = (float)(gs[0] / m);
+    k2 = (float)(gs[1] / m);
+  }
+  float ga[8], be[8], D[8], A[8], B[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     ga[e] = __ldg(s.gamma + c8 * 8 + e);
     be[e] = __ldg(s.beta + c8 * 8 + e);
     D[e] = 0.f;
+    A[e] = 0.f;
+    B[e] = 0.f;
   }
 #pragma unroll 4
   for (int p = pix0 + pl; p < pend; p += 8) {   // unrolled: 8 independent 16-byte loads in flight per thread
@@ -394,21 +425,42 @@ __global__ void gn_bwd_apply_kernel(const __grid_constant__ GnParams P, const in
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float xh = (x[e] - fmean) * rstd;
-      const float dy = (xh * ga[e] + be[e] > 0.f) ? d[e] : 0.f;
+      const float dy = (fmaf(xh, ga[e], be[e]) > 0.f) ? d[e] : 0.f;
       const float dx = rstd * (ga[e] * dy - k1 - xh * k2);
+      if (FUSED) {
+        A[e] += dy;
+        B[e] = fmaf(dy, xh, B[e]);
+      }
       d[e] = dx;
       D[e] += dx;
     }
     *reinterpret_cast<uint4*>(s.y + (long long)p * P.C + c8 * 8) = pack8(d);
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) sm[pl][c8 * 8 + e] = D[e];
+  for (int e = 0; e < 8; ++e) {
+    sm[0][pl][c8 * 8 + e] = D[e];
+    if (FUSED) {
+      sm[1][pl][c8 * 8 + e] = A[e];
+      sm[2][pl][c8 * 8 + e] = B[e];
+    }
+  }
   __syncthreads();
   const int c = threadIdx.x;
-  float a = 0.f;
+  float a = 0.f, sa = 0.f, sb = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a += sm[k][c];
+  for (int k = 0; k < 8; ++k) {
+    a += sm[0][k][c];
+    if (FUSED) {
+      sa += sm[1][k][c];
+      sb += sm[2][k][c];
+    }
+  }
   atomicAdd(s.dbias + c, a);
+  if (FUSED) {
+    double* dst = s.red + ((long long)n * P.C + c) * 2;
+    atomicAdd(dst, (double)sa);
+    atomicAdd(dst + 1, (double)sb);
+  }
 }
 
 // dgamma[c] += sum_n B[n][c], dbeta[c] += sum_n A[n][c]
@@ -687,6 +739,7 @@ static int fill_gn_params(GnParams& P, const dslb_gn_seg_t* segs, int nseg, int 
     d.red = segs[i].red;
     d.dbias = segs[i].dbias;
     d.mr = reinterpret_cast<float4*>(segs[i].mr);
+    d.gsums = segs[i].gsums;
     DSLB_CHECK_ARG(d.x && d.y && d.stats && d.gamma && d.beta && d.mr, "gn: seg %d has a null pointer", i);
     d.HW = segs[i].HW;
     d.npix = segs[i].N * segs[i].HW;
@@ -703,11 +756,6 @@ extern "C" int dslb_gn_apply_relu_tab(const dslb_gn_seg_t* segs, int nseg, int C
   GnParams P;
   int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
   if (rc != DSLB_OK) return rc;
-  int maxN = 1;
-  for (int i = 0; i < nseg; ++i) maxN = segs[i].N > maxN ? segs[i].N : maxN;
-  const int nfin = nseg * maxN * groups;
-  gn_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
-  DSLB_CHECK_CUDA(cudaGetLastError());
   gn_apply_relu_tab_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
   LAUNCH_CHECK();
 }
@@ -863,6 +911,16 @@ extern "C" int dslb_gn_bwd(const dslb_gn_seg_t* segs, int nseg, int C, int group
   GnParams P;
   int rc = fill_gn_params(P, segs, nseg, C, groups, eps);
   if (rc != DSLB_OK) return rc;
+  int with_sums = 0;
+  for (int i = 0; i < nseg; ++i) {
+    DSLB_CHECK_ARG(segs[i].dz && segs[i].red && segs[i].dbias, "dslb_gn_bwd: seg %d has a null dz / red / dbias", i);
+    with_sums += segs[i].gsums != nullptr;
+  }
+  DSLB_CHECK_ARG(with_sums == 0 || with_sums == nseg, "dslb_gn_bwd: gsums must be given for every segment or for none");
+  if (with_sums) {   // the group sums came out of the producing convs' epilogues: one pass
+    gn_bwd_apply_kernel<true><<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
+    LAUNCH_CHECK();
+  }
   gn_bwd_reduce_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
   DSLB_CHECK_CUDA(cudaGetLastError());
   int maxN = 1;
@@ -870,7 +928,7 @@ extern "C" int dslb_gn_bwd(const dslb_gn_seg_t* segs, int nseg, int C, int group
   const int nfin = nseg * maxN * groups;
   gn_bwd_finalize_kernel<<<(nfin + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, maxN);
   DSLB_CHECK_CUDA(cudaGetLastError());
-  gn_bwd_apply_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
+  gn_bwd_apply_kernel<false><<<nblocks, 256, 0, (cudaStream_t)stream>>>(P, blk_tab_dev, blk_tab_dev + nblocks);
   LAUNCH_CHECK();
 }
 

@@ -14,6 +14,7 @@ Reference functions replaced (paths relative to the reference root):
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -756,6 +757,9 @@ class FCOSNet:
         self.n_labeled = B // 2 if B % 2 == 0 else (B - 1) // 2
         self.si_weight = 0.0
         self.want_arena(self, "gn_red", 2 * 4 * nl * B * 256 * 2, (2, 4, nl, B, 256, 2), torch.float64)
+        # GroupNorm-backward group sums (sum gamma*dy, sum gamma*dy*xhat) left by the epilogue of the dgrad that produces dz
+        self.want_arena(self, "gn_bsum", 2 * 4 * nl * B * 32 * L.GN_STAT_STRIDE, (2, 4, nl, B, 32, L.GN_STAT_STRIDE),
+                        torch.float64)
         self.want_arena(self, "rc_dw", 9 * 5 * 256, (9, 5, 256))
         self.want_arena(self, "rc_db", 8, (8,))
         scale_idx = [self.store.offsets[f"bbox_head.scales.{l}.scale"][0] for l in range(nl)]
@@ -838,12 +842,26 @@ class FCOSNet:
         for l, (h, w) in enumerate(self.psize):
             self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C), side=True, tag="colsum")
             self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5), side=True, tag="colsum")
+        # DSLB_GN_BWD_FUSED=1: the dgrad that produces dz of tower layer i also accumulates that layer's GroupNorm-backward
+        # group sums in its epilogue (dslb_conv_seg_t::gnb_*), so dslb_gn_bwd is ONE pass over (x, dz) instead of reduce +
+        # apply. Opt-in: measured on B200 the 8 epilogue warps become the bound of the dgrad (126 -> 168 us per tower
+        # layer) and eat what the dropped reduce pass (58 us alone) gives back: 8.998 vs 8.980 ms per step over three
+        # interleaved runs (profiles/r02g_gn_bwd_fused_ab.txt).
+        fuse_gnb = os.environ.get("DSLB_GN_BWD_FUSED", "0") == "1"
+
+        def gnb(bi_, br, i, l):
+            if not fuse_gnb:
+                return {}
+            return dict(gnb_x=self.y[br][i][l], gnb_mr=self.gn_mr[bi_, i, l],
+                        gnb_gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
+                        gnb_beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], gnb_sums=self.gn_bsum[bi_, i, l], gn_cpg=8)
+
         dsegs = []
         for l, (h, w) in enumerate(self.psize):
-            dsegs.append(self.cls_w.dseg(self.dcls[l], self.dz["cls"][l], B, h, w, h, w))
+            dsegs.append(self.cls_w.dseg(self.dcls[l], self.dz["cls"][l], B, h, w, h, w, **gnb(0, "cls", 3, l)))
         for l, (h, w) in enumerate(self.psize):
             dsegs.append(dict(x=self.drc[l], w=self.rc_wpT, y=self.dz["reg"][l], N=B, H=h, W=w, Cin=64, Cout=256,
-                              cout_pad=256, R=3, S=3, stride=1, pad=1, ldc=256))
+                              cout_pad=256, R=3, S=3, stride=1, pad=1, ldc=256, **gnb(1, "reg", 3, l)))
         self.plan_bwd(dsegs, "head.predictors.dgrad")
         # --- towers, last layer first
         for i in (3, 2, 1, 0):
@@ -856,7 +874,8 @@ class FCOSNet:
                                       gamma=st[f"bbox_head.{br}_convs.{i}.gn.weight"],
                                       beta=st[f"bbox_head.{br}_convs.{i}.gn.bias"], red=self.gn_red[bi_, i, l],
                                       mr=self.gn_mr[bi_, i, l],
-                                      dbias=self.grad_view(f"bbox_head.{br}_convs.{i}.conv.bias"), N=B, HW=h * w))
+                                      dbias=self.grad_view(f"bbox_head.{br}_convs.{i}.conv.bias"), N=B, HW=h * w,
+                                      **({"gsums": self.gn_bsum[bi_, i, l]} if fuse_gnb else {})))
             self.add_bwd(self._gn_bwd(gsegs), wait=f"head.tower{i + 2}.wgrad" if i + 2 <= 3 else None)
             for bi_, br in enumerate(br_names):
                 # dgamma / dbeta: sum over levels and images of the per-(n,c) sums
@@ -872,9 +891,10 @@ class FCOSNet:
             self.plan_wgrad(wsegs, f"head.tower{i}.wgrad")
             if i > 0:
                 dsegs = []
-                for br in br_names:
+                for bi_, br in enumerate(br_names):
                     for l, (h, w) in enumerate(self.psize):
-                        dsegs.append(self.tower[br][i].dseg(self.dy[br][l], self.dz[br][l], B, h, w, h, w))
+                        dsegs.append(self.tower[br][i].dseg(self.dy[br][l], self.dz[br][l], B, h, w, h, w,
+                                                            **gnb(bi_, br, i - 1, l)))
                 self.plan_bwd(dsegs, f"head.tower{i}.dgrad")
             else:
                 # both towers read the FPN output: cls-tower dgrad writes dP, reg-tower dgrad accumulates into it

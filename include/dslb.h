@@ -33,7 +33,7 @@ extern "C" {
 #define DSLB_GN_STAT_STRIDE 32
 
 const char* dslb_last_error(void);
-int dslb_version(void);   /* 102 = this header (101 + dslb_fcos_topk_points; pseudo-label rule keeps class C-1) */
+int dslb_version(void);   /* 103 = this header (102 + GroupNorm backward sums in the conv epilogue: gnb_* / gsums) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (fprop, and dgrad expressed as fprop on dY with
@@ -67,6 +67,17 @@ typedef struct dslb_conv_seg {
   int32_t gn_cpg;        /* channels per GroupNorm group, 8 or 16 (only with gn_stats)                */
   int32_t scatter2;      /* 1: write output pixel (p,q) at (2p,2q) of an [N][Hs][Ws] map (dgrad of a  */
   int32_t Hs, Ws;        /*    stride-2 1x1 conv); y must then be pre-zeroed or accumulated           */
+  /* GroupNorm BACKWARD sums in the epilogue (gnb_x != NULL; excludes gn_stats): this conv is the dgrad whose output dz
+   * is the gradient w.r.t. relu(GroupNorm(x)) of the layer below (mmcv ConvModule conv -> GN -> ReLU,
+   * anchor_free_head.py:95-139). Per image n and group g, with xhat = (x - mean) * rstd and
+   * dy = bf16(dz) * [xhat * gamma + beta > 0], the epilogue adds
+   *     gnb_sums[n][g][0] += sum gamma * dy,     gnb_sums[n][g][1] += sum gamma * dy * xhat
+   * (fp64 atomics), which dslb_gn_bwd then uses instead of running its own reduction pass over x and dz. */
+  const void* gnb_x;       /* bf16 pre-norm map [N*Ho*Wo][Cout] (dense), Cout % 16 == 0, cout_pad == Cout        */
+  const float* gnb_mr;     /* [N][Cout/gn_cpg][4]: (mean, rstd, -, -) as the forward apply left them              */
+  const float* gnb_gamma;  /* [Cout]                                                                             */
+  const float* gnb_beta;   /* [Cout]                                                                             */
+  double* gnb_sums;        /* [N][Cout/gn_cpg][DSLB_GN_STAT_STRIDE], pre-zeroed                                   */
 } dslb_conv_seg_t;
 
 typedef struct dslb_conv_plan dslb_conv_plan_t;
@@ -135,6 +146,9 @@ typedef struct dslb_gn_seg {
   float* mr;           /* [N][groups][4] fp32 scratch: (mean, rstd) written by the forward apply and re-used by
                           the backward, which adds its two per-group reduction constants                       */
   int32_t N, HW;
+  double* gsums;       /* bwd only, or NULL: [N][groups][DSLB_GN_STAT_STRIDE] group sums a conv epilogue accumulated
+                          (dslb_conv_seg_t::gnb_sums). When EVERY segment has them dslb_gn_bwd skips its reduction pass:
+                          one apply launch computes the two group constants from gsums and also produces `red`.   */
 } dslb_gn_seg_t;
 int dslb_gn_apply_relu(const dslb_gn_seg_t* segs, int nseg, int C, int groups, float eps, void* stream);
 /* same result, faster: driven by the block table of dslb_gn_bwd_plan (C must be 256) */

@@ -128,6 +128,21 @@ class EmuLib:
             vg = vq.double().view(N, Ho * Wo, G, cpg)
             st[:, :, 0] += vg.sum(dim=(1, 3))
             st[:, :, 1] += (vg * vg).sum(dim=(1, 3))
+        if s["gnb_x"]:   # group sums of the GroupNorm backward this output (dz) flows into, see include/dslb.h
+            assert not s["gn_stats"] and not s["out_fp32"] and s["cout_pad"] == Cout
+            cpg = s["gn_cpg"]
+            G = Cout // cpg
+            HW = Ho * Wo
+            xg = view(s["gnb_x"], npix * Cout, BF16).view(N, HW, G, cpg).float()
+            mr = view(s["gnb_mr"], N * G * 4, torch.float32).view(N, G, 4)
+            gam = view(s["gnb_gamma"], Cout, torch.float32).view(1, 1, G, cpg)
+            bet = view(s["gnb_beta"], Cout, torch.float32).view(1, 1, G, cpg)
+            xh = (xg - mr[:, :, 0].view(N, 1, G, 1)) * mr[:, :, 1].view(N, 1, G, 1)
+            dz = vq.float().view(N, HW, G, cpg)
+            gdy = torch.where(xh * gam + bet > 0, dz, torch.zeros_like(dz)) * gam
+            sums = view(s["gnb_sums"], N * G * GN_STAT_STRIDE, torch.float64).view(N, G, GN_STAT_STRIDE)
+            sums[:, :, 0] += gdy.double().sum(dim=(1, 3))
+            sums[:, :, 1] += (gdy * xh).double().sum(dim=(1, 3))
         _rows(s["y"], npix, ldc, ydt)[:, :Cout] = vq
 
     # ------------------------------------------------------------------------------------------ wgrad plans
@@ -332,8 +347,13 @@ class EmuLib:
             red[:, :, 0] += dy.sum(dim=1).reshape(N, Cc).double()
             red[:, :, 1] += (dy * xhat).sum(dim=1).reshape(N, Cc).double()
             gdy = gamma * dy
-            m1 = gdy.mean(dim=(1, 3), keepdim=True)
-            m2 = (gdy * xhat).mean(dim=(1, 3), keepdim=True)
+            if d["gsums"]:   # the producing conv's epilogue left the group sums: no reduction here
+                gs = view(d["gsums"], N * groups * GN_STAT_STRIDE, torch.float64).view(N, groups, GN_STAT_STRIDE)
+                m1 = (gs[:, :, 0] / float(HW * cpg)).float().view(N, 1, groups, 1)
+                m2 = (gs[:, :, 1] / float(HW * cpg)).float().view(N, 1, groups, 1)
+            else:
+                m1 = gdy.mean(dim=(1, 3), keepdim=True)
+                m2 = (gdy * xhat).mean(dim=(1, 3), keepdim=True)
             dx = (rstd * (gdy - m1 - xhat * m2)).to(BF16)
             view(d["y"], dx.numel(), BF16).copy_(dx.reshape(-1))
             if d["dbias"]:

@@ -462,3 +462,117 @@ def test_pack_table_tiled_tiles_and_merged_operands_bit_exact():
     torch.cuda.synchronize()
     assert torch.equal(wpT.view(torch.int16),
                        w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 256, 128).to(torch.bfloat16).contiguous().view(torch.int16))
+
+
+# ---- GroupNorm backward with the group sums taken in the producing dgrad's epilogue ------------------------------------
+def _gn_bwd_case(g, N, H, W, C=256):
+    """Synthetic tower layer: pre-norm map x (bf16), its GroupNorm(32) statistics / (mean, rstd), gamma, beta."""
+    from dsl_b200 import _lib as L
+    x = _bf(torch.randn(N, H, W, C, generator=g) * 1.5 + 0.3).to(DEV)
+    xg = x.double().view(N, H * W, 32, 8)
+    stats = torch.zeros(N, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=DEV)
+    stats[:, :, 0] = xg.sum(dim=(1, 3))
+    stats[:, :, 1] = (xg * xg).sum(dim=(1, 3))
+    m = float(H * W * 8)
+    mean = stats[:, :, 0] / m
+    rstd = 1.0 / torch.sqrt((stats[:, :, 1] / m - mean * mean).clamp_min(0) + 1e-5)
+    mr = torch.zeros(N, 32, 4, dtype=torch.float32, device=DEV)
+    mr[:, :, 0], mr[:, :, 1] = mean.float(), rstd.float()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    return x.to(torch.bfloat16), stats, mr, gamma, beta
+
+
+@pytest.mark.parametrize("pairs", ["1", "0"], ids=["cta-pairs", "single-cta"])
+def test_gn_bwd_group_sums_in_dgrad_epilogue(pairs, monkeypatch):
+    """dslb_conv_seg_t::gnb_*: the dgrad whose output is dz leaves sum(gamma*dy) and sum(gamma*dy*xhat) per (image, group)
+    in gnb_sums, dy = bf16(dz) * [xhat*gamma + beta > 0]. Against a torch restatement on the stored (bf16) dz; maps that are
+    smaller than a tile, tiles that straddle two images, three segments in one launch, both kernel flavours."""
+    from dsl_b200 import _lib as L
+    from dsl_b200.engine import ConvPlan
+    monkeypatch.setenv("DSLB_CTA2", pairs)
+    g = torch.Generator().manual_seed(21)
+    C = 256
+    w = _bf(torch.randn(C, C, 3, 3, generator=g) * 0.02)
+    wpT = _pack(w, True)
+    segs, keep = [], []
+    for (N, H, W) in ((2, 25, 42), (2, 7, 11), (3, 13, 21)):
+        dy_in = _bf(torch.randn(N, C, H, W, generator=g))
+        x, stats, mr, gamma, beta = _gn_bwd_case(g, N, H, W)
+        dz = torch.zeros(N, H, W, C, dtype=torch.bfloat16, device=DEV)
+        sums = torch.zeros(N, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=DEV)
+        segs.append(dict(x=_nhwc(dy_in), w=wpT, y=dz, N=N, H=H, W=W, Cin=C, Cout=C, cout_pad=C, R=3, S=3, stride=1, pad=1,
+                         ldc=C, gnb_x=x, gnb_mr=mr, gnb_gamma=gamma, gnb_beta=beta, gnb_sums=sums, gn_cpg=8))
+        keep.append((dy_in, x, mr, gamma, beta, dz, sums))
+    ConvPlan(segs, "tower dgrad").run()
+    torch.cuda.synchronize()
+    for dy_in, x, mr, gamma, beta, dz, sums in keep:
+        N = x.shape[0]
+        ref = F.conv_transpose2d(dy_in.to(DEV), w.to(DEV), padding=1)   # == the dgrad the packed transposed operand computes
+        assert _rel(dz.permute(0, 3, 1, 2).float(), ref) < 4e-3
+        xg = x.float().view(N, -1, 32, 8)
+        xh = (xg - mr[:, :, 0].view(N, 1, 32, 1)) * mr[:, :, 1].view(N, 1, 32, 1)
+        ga, be = gamma.view(1, 1, 32, 8), beta.view(1, 1, 32, 8)
+        dzg = dz.float().view(N, -1, 32, 8)
+        gdy = torch.where(torch.addcmul(be, xh, ga) > 0, dzg, torch.zeros_like(dzg)) * ga
+        s1, s2 = gdy.double().sum(dim=(1, 3)), (gdy.double() * xh.double()).sum(dim=(1, 3))
+        # the sums cancel heavily (zero-mean dz): measure against the sum of magnitudes
+        e1 = ((sums[:, :, 0] - s1).abs().max() / gdy.double().abs().sum(dim=(1, 3)).max()).item()
+        e2 = ((sums[:, :, 1] - s2).abs().max() / (gdy.double() * xh.double()).abs().sum(dim=(1, 3)).max()).item()
+        print(f"gnb sums {tuple(x.shape)}: S1 {e1:.2e} S2 {e2:.2e}")
+        # 2e-4 of the magnitude sum = about one element of the smallest map: leaves room for a ReLU gate that flips on a
+        # pre-activation within one fp32 ulp of zero, nothing systematic passes
+        assert e1 < 2e-4 and e2 < 2e-4
+        assert float(sums[:, :, 2:].abs().max()) == 0.0
+
+
+def test_gn_bwd_one_pass_equals_reduce_plus_apply():
+    """dslb_gn_bwd with gsums (one apply launch) against the same call without them (reduce + finalize + apply): same dx
+    up to the rounding of the group constants, same per-channel sums for dgamma / dbeta and the same conv-bias gradient."""
+    from dsl_b200 import _lib as L
+    g = torch.Generator().manual_seed(22)
+    C = 256
+    cases = []
+    for (N, H, W) in ((2, 25, 42), (1, 7, 11), (3, 13, 21)):
+        x, stats, mr, gamma, beta = _gn_bwd_case(g, N, H, W)
+        dz = _bf(torch.randn(N, H * W, C, generator=g)).to(DEV).to(torch.bfloat16)
+        xg = x.float().view(N, -1, 32, 8)
+        xh = (xg - mr[:, :, 0].view(N, 1, 32, 1)) * mr[:, :, 1].view(N, 1, 32, 1)
+        ga, be = gamma.view(1, 1, 32, 8), beta.view(1, 1, 32, 8)
+        dzg = dz.float().view(N, -1, 32, 8)
+        gdy = torch.where(torch.addcmul(be, xh, ga) > 0, dzg, torch.zeros_like(dzg)) * ga
+        gs = torch.zeros(N, 32, L.GN_STAT_STRIDE, dtype=torch.float64, device=DEV)
+        gs[:, :, 0] = gdy.double().sum(dim=(1, 3))
+        gs[:, :, 1] = (gdy.double() * xh.double()).sum(dim=(1, 3))
+        cases.append((N, H * W, x, stats, mr, gamma, beta, dz, gs))
+
+    def run(fused):
+        arr = (L.GnSeg * len(cases))()
+        outs = []
+        for a, (N, HW, x, stats, mr, gamma, beta, dz, gs) in zip(arr, cases):
+            dx = torch.zeros(N, HW, C, dtype=torch.bfloat16, device=DEV)
+            red = torch.zeros(N, C, 2, dtype=torch.float64, device=DEV)
+            dbias = torch.zeros(C, device=DEV)
+            mr2 = mr.clone()
+            for k, v in dict(x=x, y=dx, dz=dz, stats=stats, gamma=gamma, beta=beta, red=red, dbias=dbias, mr=mr2).items():
+                setattr(a, k, v.data_ptr())
+            a.N, a.HW = N, HW
+            if fused:
+                a.gsums = gs.data_ptr()
+            outs.append((dx, red, dbias, mr2))
+        nb = L.lib.dslb_gn_bwd_blocks(arr, len(cases))
+        host = (C_int * (2 * nb))()
+        L.check(L.lib.dslb_gn_bwd_plan(arr, len(cases), host), "plan")
+        tab = torch.tensor(list(host), dtype=torch.int32, device=DEV)
+        L.check(L.lib.dslb_gn_bwd(arr, len(cases), C, 32, 1e-5, L.ptr(tab), nb, L.cur_stream()), "gn_bwd")
+        torch.cuda.synchronize()
+        return outs
+
+    import ctypes
+    C_int = ctypes.c_int
+    for (dx0, red0, db0, _), (dx1, red1, db1, _) in zip(run(False), run(True)):
+        assert _rel(dx1.float(), dx0.float()) < 1e-2          # one bf16 ulp of the largest entry
+        assert (dx1.float() - dx0.float()).abs().mean().item() < 1e-4 * dx0.float().abs().mean().item() + 1e-7
+        scale = red0.abs().max().item()
+        assert (red1 - red0).abs().max().item() < 2e-5 * scale + 1e-9
+        assert (db1 - db0).abs().max().item() < 2e-3 * db0.abs().max().item() + 1e-4
