@@ -82,40 +82,48 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   }
 }
 
-// 3x3 stride-2 pad-1 max-pool, NHWC bf16, 8 channels per thread
+// 3x3 stride-2 pad-1 max-pool, NHWC bf16. One thread = 8 channels of TWO horizontally adjacent output pixels: their
+// windows share a column, so 15 loads (3 rows x 5 columns) make two outputs instead of 18, and the row-wise maxima of the
+// five columns are formed once. Padding taps read -inf; max is exact in bf16, so it runs on packed bf16x2 values.
+__device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b) {
+  uint4 m = a;
+  __nv_bfloat162* x = reinterpret_cast<__nv_bfloat162*>(&m);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) x[e] = __hmax2(x[e], y[e]);
+  return m;
+}
+
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                     int W, int C, int Ho, int Wo) {
   const int cv = C / 8;
-  const long long total = (long long)N * Ho * Wo * cv;
+  const int Wp = (Wo + 1) >> 1;
+  const long long total = (long long)N * Ho * Wp * cv;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int c8 = t % cv;
-    const long long pix = t / cv;
-    const int q = pix % Wo;
-    const int p = (pix / Wo) % Ho;
-    const int n = pix / ((long long)Wo * Ho);
-    // all nine taps are loaded first (independent requests in flight), padding taps read -inf; max is exact in bf16,
-    // so the reduction runs on packed bf16x2 values
-    uint4 u[9];
+    const long long pp = t / cv;
+    const int qp = pp % Wp;
+    const int p = (pp / Wp) % Ho;
+    const int n = pp / ((long long)Wp * Ho);
+    const int q = qp * 2;
+    const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+    uint4 u[15];   // all taps are loaded first: independent requests in flight
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = p * 2 - 1 + r;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
+      for (int s = 0; s < 5; ++s) {
         const int w = q * 2 - 1 + s;
         const bool ok = h >= 0 && h < H && w >= 0 && w < W;
-        u[r * 3 + s] = ok ? __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + c8 * 8))
-                          : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+        u[r * 5 + s] = ok ? __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + c8 * 8)) : ninf;
       }
     }
-    uint4 m = u[0];
+    uint4 cm[5];
 #pragma unroll
-    for (int k = 1; k < 9; ++k) {
-      __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&m);
-      const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = __hmax2(a[e], b[e]);
-    }
-    *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = m;
+    for (int s = 0; s < 5; ++s) cm[s] = max8(max8(u[s], u[5 + s]), u[10 + s]);
+    __nv_bfloat16* dst = y + (((long long)n * Ho + p) * Wo + q) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(dst) = max8(max8(cm[0], cm[1]), cm[2]);
+    if (q + 1 < Wo) *reinterpret_cast<uint4*>(dst + C) = max8(max8(cm[2], cm[3]), cm[4]);
   }
 }
 
@@ -689,7 +697,7 @@ extern "C" int dslb_si_half_image(const float* img, float* out, int C, int H, in
 extern "C" int dslb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   DSLB_CHECK_ARG(x && y && C % 8 == 0, "dslb_maxpool3x3s2: C must be a multiple of 8");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = (long long)N * Ho * Wo * (C / 8);
+  const long long total = (long long)N * Ho * ((Wo + 1) / 2) * (C / 8);
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
                                                                                 N, H, W, C, Ho, Wo);
   LAUNCH_CHECK();

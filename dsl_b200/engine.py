@@ -1072,12 +1072,21 @@ class FCOSNet:
                                                len(self.psize), s), "scale grads")
 
             self.add_bwd(finish_head_grads, side=True, tag="finish_head")
+        # last side op of the bucket: everything in its gradient range is final here -> `bucket_hook(k, lo, hi)` (a
+        # single-GPU trainer takes the bucket's share of the gradient norm off the critical path)
+        self.add_bwd(lambda k=len(self.bwd_buckets): self._bucket_done(k), side=True, tag="bucket_done")
         offs = [self.store.offsets[n] for n in names]
         lo = min(o for o, _ in offs)
         hi = max(o + n for o, n in offs)
         if head:
             hi = self.store.n_train          # head / neck biases (region B) and the Scale parameters travel with it
         self.bwd_buckets.append((len(self.bwd_ops), lo, hi))
+
+    def _bucket_done(self, k):
+        hook = getattr(self, "bucket_hook", None)
+        if hook is not None:
+            _, lo, hi = self.bwd_buckets[k]
+            hook(k, lo, hi)
 
     def _build_finish_bwd(self):
         # the remaining packed wgrads -> their OIHW gradient views (standalone head: everything, in one launch)
@@ -1132,11 +1141,14 @@ class FCOSNet:
         for op in self.fwd_ops[self.head_op_start:]:
             op()
 
-    def backward(self, side_stream=None, start=0, end=None):
+    def backward(self, side_stream=None, start=0, end=None, join=True):
         """Run backward ops [start, end) (default: all). With `side_stream` the weight-gradient launches (off the dgrad
         critical path) go to that stream, ordered by events, so they fill the SMs the small deep-layer dgrad grids
         leave idle. A partial range ends with the main stream joined to the side stream (bucket boundaries of
-        `bwd_buckets`: everything in the bucket's gradient range is final when the call returns)."""
+        `bwd_buckets`: everything in the bucket's gradient range is final when the call returns). join=False (ranges
+        of ONE stream-ordered sequence / ONE captured graph only): no join — the call returns the side stream's last
+        event, the bucket is final once that event AND the main stream's position have been reached, and the dgrad chain
+        runs on exactly as it does in an un-bucketed backward; the last range of the step must join."""
         end = len(self.bwd_ops) if end is None else end
         if side_stream is None:
             for op in self.bwd_ops[start:end]:
@@ -1147,7 +1159,9 @@ class FCOSNet:
             self._bwd_events = [(torch.cuda.Event(), torch.cuda.Event()) if m[0] else None for m in self.bwd_meta]
         # every earlier range ended joined to the side stream, so no event of it needs (or, under graph capture, may) be
         # waited on again
-        self._bwd_done, self._bwd_last = {}, None
+        if start == 0 or not getattr(self, "_bwd_open", False):
+            self._bwd_done, self._bwd_last = {}, None
+        self._bwd_open = not join   # an un-joined range leaves its side events live for the next range of the step
         done = self._bwd_done
         for i in range(start, end):
             op, (side, tag, wait), evs = self.bwd_ops[i], self.bwd_meta[i], self._bwd_events[i]
@@ -1165,8 +1179,11 @@ class FCOSNet:
                 done[tag] = self._bwd_last = ev_side
             else:
                 op()
+        if not join:
+            return self._bwd_last
         if self._bwd_last is not None:
             main.wait_event(self._bwd_last)   # join: the range's gradients are final (and a captured graph re-joins its fork)
+        return None
 
     def losses(self):
         """dict of the reference's loss names -> 0-dim fp32 tensors (device)."""

@@ -76,6 +76,15 @@ class DSLEngine:
         self.graph_nccl = os.environ.get("DSLB_GRAPH_NCCL", "1") != "0"
         self.s_comm = torch.cuda.Stream()
         self._comm_evs = None
+        # |g|^2 bucket by bucket as the gradients become final (one GPU: on the weight-gradient side stream behind each
+        # bucket's unpack; several: on the communication stream behind each bucket's all-reduce) instead of one pass over
+        # all 128 MB between the backward and clip -> SGD. DSLB_BUCKET_SQNORM=0: off.
+        self.bucket_sqnorm = os.environ.get("DSLB_BUCKET_SQNORM", "1") != "0"
+        self._sq_partial = False
+        # several GPUs, one-graph step: the dgrad stream does not join the weight-gradient stream at bucket boundaries —
+        # only the communication stream waits for a bucket to be final. DSLB_BUCKET_JOIN=1: join as before.
+        self.lazy_bucket_join = os.environ.get("DSLB_BUCKET_JOIN", "0") != "1"
+        self.student.bucket_hook = self._bucket_sqnorm if (self.world == 1 and self.bucket_sqnorm) else None
         global _COMM_WARM
         if self.world > 1 and not _COMM_WARM:
             # first engine of the process = a point every rank reaches together: force the (lazy) communicator creation
@@ -240,7 +249,16 @@ class DSLEngine:
 
     def _phase_b(self):
         self.student.run_loss()
+        if self.student.bucket_hook is not None:
+            L.zero(self.sqnorm)    # the buckets add their shares as they become final (_bucket_sqnorm)
+            self._sq_partial = True
         self.student.backward(self.s3 if self.two_streams else None)
+
+    def _bucket_sqnorm(self, k, lo, hi):
+        """bucket_hook of a single-GPU step: the bucket's share of |g|^2, on the side stream behind its unpack, so only
+        the last (smallest) bucket's share sits between the backward and clip -> SGD."""
+        g = self.student.grad
+        L.check(L.lib.dslb_sq_norm(L.ptr(g[lo:hi]), hi - lo, L.ptr(self.sqnorm), L.cur_stream()), "sq_norm bucket")
 
     def _bucket_ranges(self):
         """Backward op ranges ending at the gradient-bucket boundaries: [(op_start, op_end, grad_lo, grad_hi)]."""
@@ -251,12 +269,13 @@ class DSLEngine:
         out[-1] = (out[-1][0], len(self.student.bwd_ops), out[-1][2], out[-1][3])
         return out
 
-    def _phase_b_part(self, k):
-        """Bucket k of the backward (k = 0 also evaluates the loss): when it returns, grad[lo:hi] of that bucket is final."""
+    def _phase_b_part(self, k, join=True):
+        """Bucket k of the backward (k = 0 also evaluates the loss): when it returns, grad[lo:hi] of that bucket is final
+        (join=False: final once the returned side-stream event has been reached, see FCOSNet.backward)."""
         start, end, _, _ = self._bucket_ranges()[k]
         if k == 0:
             self.student.run_loss()
-        self.student.backward(self.s3 if self.two_streams else None, start=start, end=end)
+        return self.student.backward(self.s3 if self.two_streams else None, start=start, end=end, join=join)
 
     def _phase_c(self):
         if self.world == 1:
@@ -264,8 +283,10 @@ class DSLEngine:
         s = L.cur_stream()
         st, tt = self.student.store, self.teacher.store
         g = self.student.grad
-        L.zero(self.sqnorm)
-        L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
+        if not self._sq_partial:
+            L.zero(self.sqnorm)
+            L.check(L.lib.dslb_sq_norm(L.ptr(g), g.numel(), L.ptr(self.sqnorm), s), "sq_norm")
+        self._sq_partial = False
         # max_grad_norm None = no clipping (optimizer_config.grad_clip=None): a bound no fp32 norm reaches gives coef 1
         L.check(L.lib.dslb_clip_coef(L.ptr(self.sqnorm), float(self.max_grad_norm if self.max_grad_norm is not None
                                                                  else 3.0e38), L.ptr(self.coef), s), "clip_coef")
@@ -376,13 +397,23 @@ class DSLEngine:
             with torch.no_grad():
                 self.student.forward()
         main.wait_event(ev[1])
+        lazy = self.lazy_bucket_join and self.two_streams
+        if self.bucket_sqnorm:
+            L.zero(self.sqnorm)
+            self._sq_partial = True
         for k in range(nb):
-            self._phase_b_part(k)
+            # lazy: the main (dgrad) stream does not wait for the bucket's weight gradients — only the communication
+            # stream does, so the dgrad chain of the next bucket starts at once, as in the single-GPU step
+            side_ev = self._phase_b_part(k, join=not lazy or k == nb - 1)
             _, _, lo, hi = self._bucket_ranges()[k]
             ev[2 + 2 * k].record(main)
             self.s_comm.wait_event(ev[2 + 2 * k])
+            if side_ev is not None:
+                self.s_comm.wait_event(side_ev)
             with torch.cuda.stream(self.s_comm):
                 dist_ops.allreduce_mean_(self.student.grad[lo:hi])
+                if self.bucket_sqnorm:   # the bucket's share of |mean gradient|^2, behind its all-reduce
+                    self._bucket_sqnorm(k, lo, hi)
                 ev[3 + 2 * k].record(self.s_comm)
         for k in range(nb):
             main.wait_event(ev[3 + 2 * k])
