@@ -825,11 +825,10 @@ class FCOSNet:
         self.dy2 = [{br: [self.buf(B, h, w, 256) for (h, w) in self.psize] for br in br_names} for _ in range(2)]
         self.dp = [self.buf(B, h, w, 256) for (h, w) in self.psize]  # gradient w.r.t. the FPN outputs
 
-        def zero_state():
-            L.zero(self.grad)
-            L.zero(self.arena)  # every packed wgrad accumulator, the GroupNorm backward sums, rc_dw / rc_db
-
-        self.add_bwd(zero_state)
+        # gradient buffers cleared at the head of the backward — unless a trainer does it earlier, off the critical path
+        # (zero_in_bwd = False + its own zero_state() call under the forward pass)
+        self.zero_in_bwd = True
+        self.add_bwd(lambda: self.zero_state() if self.zero_in_bwd else None)
         # --- predictors: wgrad (10 segs), bias grads, dgrad into the last tower outputs
         wsegs = []
         for l, (h, w) in enumerate(self.psize):
@@ -903,6 +902,12 @@ class FCOSNet:
                 self.plan_bwd([self.tower["reg"][0].dseg(self.dy["reg"][l], self.dp[l], B, h, w, h, w,
                                                          residual=self.dp[l])
                                for l, (h, w) in enumerate(self.psize)], "head.tower0.dgrad.reg")
+
+    def zero_state(self):
+        """Clear what the backward accumulates into: the flat gradient and the zero arena (every packed wgrad accumulator,
+        the GroupNorm backward sums, rc_dw / rc_db)."""
+        L.zero(self.grad)
+        L.zero(self.arena)
 
     def _gn_bwd(self, gsegs):
         n = len(gsegs)
