@@ -178,6 +178,7 @@ _proto("dslb_ema_update", I, VP, VP, LL, F, F, VP)
 _proto("dslb_sq_norm", I, VP, LL, VP, VP)
 _proto("dslb_clip_coef", I, VP, F, VP, VP)
 _proto("dslb_sgd_step", I, VP, VP, VP, LL, VP, VP, F, F, F, I, VP)
+_proto("dslb_sgd_ema_step", I, VP, VP, VP, LL, VP, VP, F, F, F, I, VP, F, F, VP)
 _proto("dslb_fcos_point_scores", I, VP, VP, VP, LL, I, I, VP)
 _proto("dslb_fcos_topk_points", I, VP, VP, VP, VP, I, I, VP)
 _proto("dslb_fcos_decode_gate", I, VP, VP, VP, I, I, I, I, I, I, I, VP, VP, F, I, VP, VP, VP, VP, VP, I, VP, VP)

@@ -64,9 +64,12 @@ __global__ void clip_coef_kernel(const double* __restrict__ sqnorm, float max_no
 
 // torch.optim.SGD (momentum, dampening 0, no nesterov) with the clip coefficient applied to the gradient first:
 //   d = g*coef + wd*p;  buf = first ? d : mom*buf + d;  p -= lr*buf
+// EMA: the teacher copy of the same parameters follows in the same pass, T <- P_new * c_s + T * c_t with the rounding of
+// ema_kernel (one read of the student weights less than SGD followed by the flat EMA).
+template <bool EMA>
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n4,
                            long long n, const float* __restrict__ coef, const float* __restrict__ lr_scale, float lr,
-                           float mom, float wd, int first) {
+                           float mom, float wd, int first, float* __restrict__ t, float c_s, float c_t) {
   const float c = coef ? coef[0] : 1.f;
   if (lr_scale) lr *= lr_scale[0];
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -81,12 +84,22 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     d = gv.w * c + wd * pv.w; bv.w = first ? d : mom * bv.w + d; pv.w -= lr * bv.w;
     reinterpret_cast<float4*>(buf)[i] = bv;
     reinterpret_cast<float4*>(p)[i] = pv;
+    if (EMA) {
+      float4 a = reinterpret_cast<float4*>(t)[i];
+      a.x = __fadd_rn(__fmul_rn(pv.x, c_s), __fmul_rn(a.x, c_t));
+      a.y = __fadd_rn(__fmul_rn(pv.y, c_s), __fmul_rn(a.y, c_t));
+      a.z = __fadd_rn(__fmul_rn(pv.z, c_s), __fmul_rn(a.z, c_t));
+      a.w = __fadd_rn(__fmul_rn(pv.w, c_s), __fmul_rn(a.w, c_t));
+      reinterpret_cast<float4*>(t)[i] = a;
+    }
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float d = g[i] * c + wd * p[i];
     const float b = first ? d : mom * buf[i] + d;
     buf[i] = b;
-    p[i] -= lr * b;
+    const float pn = p[i] - lr * b;
+    p[i] = pn;
+    if (EMA) t[i] = __fadd_rn(__fmul_rn(pn, c_s), __fmul_rn(t[i], c_t));
   }
 }
 
@@ -134,8 +147,23 @@ extern "C" int dslb_sgd_step(float* p, const float* g, float* buf, long long n, 
   DSLB_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)buf % 16) == 0,
                  "dslb_sgd_step: 16-byte alignment");
   if (n == 0) return DSLB_OK;
-  sgd_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n / 4, n, coef, lr_scale, lr, momentum,
-                                                                  weight_decay, first_step);
+  sgd_kernel<false><<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n / 4, n, coef, lr_scale, lr, momentum,
+                                                                         weight_decay, first_step, nullptr, 0.f, 0.f);
+  DSLB_CHECK_CUDA(cudaGetLastError());
+  return DSLB_OK;
+}
+
+extern "C" int dslb_sgd_ema_step(float* p, const float* g, float* buf, long long n, const float* coef,
+                                 const float* lr_scale, float lr, float momentum, float weight_decay, int first_step,
+                                 float* teacher, float c_student, float c_teacher, void* stream) {
+  DSLB_CHECK_ARG(p && g && buf && teacher, "dslb_sgd_ema_step: null argument");
+  DSLB_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)buf % 16) == 0 &&
+                     ((uintptr_t)teacher % 16) == 0,
+                 "dslb_sgd_ema_step: 16-byte alignment");
+  if (n == 0) return DSLB_OK;
+  sgd_kernel<true><<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n / 4, n, coef, lr_scale, lr, momentum,
+                                                                        weight_decay, first_step, teacher, c_student,
+                                                                        c_teacher);
   DSLB_CHECK_CUDA(cudaGetLastError());
   return DSLB_OK;
 }

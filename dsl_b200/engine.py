@@ -1137,8 +1137,8 @@ class FCOSNet:
         for f in self.repack_ops:
             f()
 
-    def forward(self):
-        for op in self.fwd_ops:
+    def forward(self, start=0, end=None):
+        for op in self.fwd_ops[start:end]:
             op()
 
     def forward_head(self):

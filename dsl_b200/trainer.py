@@ -87,9 +87,13 @@ class DSLEngine:
         # DSLB_PREP_UNDER_FWD=1: gradient-buffer memsets + target assignment on the weight-gradient stream under the
         # forward pass instead of at the head of the backward. Opt-in: measured slower on B200 (8.78 vs 8.70 ms over three
         # interleaved runs) — the 256 MB of memset writes compete with the HBM-bound layer1 convs they overlap.
-        self.prep_under_forward = os.environ.get("DSLB_PREP_UNDER_FWD", "0") == "1"
+        # DSLB_PREP_UNDER_FWD=towers: the same, forked where the FCOSHead towers start (tensor-bound launches, HBM idle).
+        _m = os.environ.get("DSLB_PREP_UNDER_FWD", "0")
+        self.prep_mode = {"1": "start", "start": "start", "towers": "towers"}.get(_m, "off")
+        self.prep_under_forward = self.prep_mode != "off"
         self.student.zero_in_bwd = not self.prep_under_forward
         self._prep_ev0, self._prep_ev1 = torch.cuda.Event(), torch.cuda.Event()
+        self.fuse_ema = os.environ.get("DSLB_FUSE_EMA", "1") != "0"   # EMA of the trainable regions inside the SGD kernel
         self.student.bucket_hook = self._bucket_sqnorm if (self.world == 1 and self.bucket_sqnorm) else None
         global _COMM_WARM
         if self.world > 1 and not _COMM_WARM:
@@ -256,14 +260,25 @@ class DSLEngine:
         if self.two_streams:
             torch.cuda.current_stream().wait_event(self._prep_ev1)
 
+    def _student_forward(self, targets):
+        """Student forward pass; prep_mode "towers" forks the backward's preparation (_fork_prep) where the head starts."""
+        with torch.no_grad():
+            if self.prep_mode == "towers":
+                k = self.student.head_op_start
+                self.student.forward(end=k)
+                self._fork_prep(targets)
+                self.student.forward(start=k)
+            else:
+                self.student.forward()
+
     def _phase_a(self):
-        self._fork_prep(targets=True)
+        if self.prep_mode == "start" or self.joint_fwd is not None:
+            self._fork_prep(targets=True)
         if self.joint_fwd is not None:
             self._forward_both()
         else:
             self._fork_teacher()
-            with torch.no_grad():
-                self.student.forward()
+            self._student_forward(targets=True)
         self._join_prep(targets=True)
         if self.world > 1:
             self._join_teacher()   # each captured graph must re-join its forked stream
@@ -275,13 +290,13 @@ class DSLEngine:
             self.student.run_targets()
 
     def _phase_a_fwd(self):
-        self._fork_prep(targets=False)
+        if self.prep_mode == "start" or self.joint_fwd is not None:
+            self._fork_prep(targets=False)
         if self.joint_fwd is not None:
             self._forward_both()
         else:
             self._fork_teacher()
-            with torch.no_grad():
-                self.student.forward()
+            self._student_forward(targets=False)
         self._join_prep(targets=False)
         self._join_teacher()
 
@@ -330,20 +345,28 @@ class DSLEngine:
                                                                  else 3.0e38), L.ptr(self.coef), s), "clip_coef")
         a0, a1 = st.region_range["A"]
         b0, b1 = st.region_range["B"]
-        L.check(L.lib.dslb_sgd_step(L.ptr(st.flat[a0:a1]), L.ptr(g[a0:a1]), L.ptr(self.mom[a0:a1]), a1 - a0,
-                                    L.ptr(self.coef), L.ptr(self.lr_scale), self.lr, self.momentum, self.wd, 0, s),
-                "sgd A")
-        L.check(L.lib.dslb_sgd_step(L.ptr(st.flat[b0:b1]), L.ptr(g[b0:b1]), L.ptr(self.mom[b0:b1]), b1 - b0,
-                                    L.ptr(self.coef), L.ptr(self.lr_scale), self.lr * self.bias_lr_mult,
-                                    self.momentum, self.wd * self.bias_decay_mult, 0, s), "sgd B")
         k = float(self.ema_keep)
         c_s = float(torch.tensor(1 - k, dtype=torch.float32))  # fp32(1 - keep_rate), as torch's scalar promotion does
         c_t = float(torch.tensor(k, dtype=torch.float32))
+        # per-iteration EMA: the teacher copies of the trainable regions are updated by the SGD kernel itself (same
+        # arithmetic on the new weights, one read of them less); the flat EMA then only covers what SGD never touches
+        fused = self.ema_in_step and self.fuse_ema
+        for (r0, r1, lr, wd, what) in ((a0, a1, self.lr, self.wd, "sgd A"),
+                                       (b0, b1, self.lr * self.bias_lr_mult, self.wd * self.bias_decay_mult, "sgd B")):
+            args = (L.ptr(st.flat[r0:r1]), L.ptr(g[r0:r1]), L.ptr(self.mom[r0:r1]), r1 - r0, L.ptr(self.coef),
+                    L.ptr(self.lr_scale), lr, self.momentum, wd, 0)
+            if fused:
+                L.check(L.lib.dslb_sgd_ema_step(*args, L.ptr(tt.flat[r0:r1]), c_s, c_t, s), what)
+            else:
+                L.check(L.lib.dslb_sgd_step(*args, s), what)
+        assert a0 == 0 and b0 == a1 and b1 == st.n_train
 
         def teacher_side():
             if not self.ema_in_step:
                 return
-            L.check(L.lib.dslb_ema_update(L.ptr(tt.flat), L.ptr(st.flat), st.numel, c_s, c_t, L.cur_stream()), "ema")
+            lo = st.n_train if fused else 0    # (frozen weights, BatchNorm buffers: everything behind the trainable range)
+            L.check(L.lib.dslb_ema_update(L.ptr(tt.flat[lo:]), L.ptr(st.flat[lo:]), st.numel - lo, c_s, c_t,
+                                          L.cur_stream()), "ema")
             self.teacher.repack(everything=True)    # the reference's EMA touches every state_dict entry
 
         if self.two_streams:
@@ -428,13 +451,13 @@ class DSLEngine:
         with torch.cuda.stream(self.s_comm):
             dist_ops.allreduce_sum_(self.student.counts)
             ev[1].record(self.s_comm)
-        self._fork_prep(targets=False)
+        if self.prep_mode == "start" or self.joint_fwd is not None:
+            self._fork_prep(targets=False)
         if self.joint_fwd is not None:
             self._forward_both()
         else:
             self._fork_teacher()   # joined before the optimizer / EMA (the teacher branch overlaps the whole backward)
-            with torch.no_grad():
-                self.student.forward()
+            self._student_forward(targets=False)
         self._join_prep(targets=False)
         main.wait_event(ev[1])
         lazy = self.lazy_bucket_join and self.two_streams

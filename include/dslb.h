@@ -33,7 +33,7 @@ extern "C" {
 #define DSLB_GN_STAT_STRIDE 32
 
 const char* dslb_last_error(void);
-int dslb_version(void);   /* 103 = this header (102 + GroupNorm backward sums in the conv epilogue: gnb_* / gsums) */
+int dslb_version(void);   /* 103 = this header (102 + GroupNorm backward sums in the conv epilogue: gnb_* / gsums; dslb_sgd_ema_step) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (fprop, and dgrad expressed as fprop on dY with
@@ -341,6 +341,12 @@ int dslb_clip_coef(const double* sqnorm, float max_norm, float* coef, void* stre
  * cfg optimizer: lr .01, momentum .9, wd 1e-4, paramwise bias_lr_mult 2 / bias_decay_mult 0 (one call per region). */
 int dslb_sgd_step(float* p, const float* g, float* buf, long long n, const float* coef, const float* lr_scale, float lr,
                   float momentum, float weight_decay, int first_step, void* stream);
+/* the same step with the EMA teacher of these parameters updated in the same pass (the arithmetic of dslb_ema_update on
+ * the NEW p: teacher = p*c_student + teacher*c_teacher, products and sum rounded separately; EMAOWNHook per-iteration
+ * mode, runner/hooks/semi_epoch_based_runner.py:398-404): one read of the student weights less per step. */
+int dslb_sgd_ema_step(float* p, const float* g, float* buf, long long n, const float* coef, const float* lr_scale,
+                      float lr, float momentum, float weight_decay, int first_step, float* teacher, float c_student,
+                      float c_teacher, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Teacher decode + score gate (FCOSHead._get_bboxes, fcos_head.py:406-527; multiclass_nms gate,

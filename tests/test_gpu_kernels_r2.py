@@ -576,3 +576,41 @@ def test_gn_bwd_one_pass_equals_reduce_plus_apply():
         scale = red0.abs().max().item()
         assert (red1 - red0).abs().max().item() < 2e-5 * scale + 1e-9
         assert (db1 - db0).abs().max().item() < 2e-3 * db0.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 50, 84), (1, 64, 37, 53), (3, 128, 8, 6), (1, 64, 5, 1), (2, 64, 400, 672)])
+def test_maxpool_bit_exact(shape):
+    """dslb_maxpool3x3s2 (two output pixels per thread, odd widths end with a single one) == nn.MaxPool2d(3, 2, 1) on the
+    same bf16 values, bit for bit (max is exact)."""
+    from dsl_b200 import _lib as L
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = _bf(torch.randn(N, C, H, W, generator=g))
+    xd = _nhwc(x)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.full((N, Ho, Wo, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib.dslb_maxpool3x3s2(L.ptr(xd), L.ptr(y), N, H, W, C, L.cur_stream()), "maxpool")
+    ref = F.max_pool2d(x.to(DEV), 3, 2, 1)
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), ref)
+
+
+def test_sgd_with_ema_equals_sgd_then_ema():
+    """dslb_sgd_ema_step == dslb_sgd_step followed by dslb_ema_update on the same range, bit for bit (weights, momentum
+    buffer and teacher), including a length that is not a multiple of four."""
+    from dsl_b200 import _lib as L
+    n = 1_000_003
+    g = torch.Generator().manual_seed(3)
+    p, gr, buf, t = (torch.randn(n, generator=g).to(DEV) for _ in range(4))
+    coef = torch.tensor([0.37, 0.0], device=DEV)
+    lrs = torch.tensor([0.5], device=DEV)
+    k = 0.9996
+    c_s, c_t = float(torch.tensor(1 - k, dtype=torch.float32)), float(torch.tensor(k, dtype=torch.float32))
+    p1, b1, t1 = p.clone(), buf.clone(), t.clone()
+    L.check(L.lib.dslb_sgd_step(L.ptr(p1), L.ptr(gr), L.ptr(b1), n, L.ptr(coef), L.ptr(lrs), 0.01, 0.9, 1e-4, 0,
+                                L.cur_stream()), "sgd")
+    L.check(L.lib.dslb_ema_update(L.ptr(t1), L.ptr(p1), n, c_s, c_t, L.cur_stream()), "ema")
+    p2, b2, t2 = p.clone(), buf.clone(), t.clone()
+    L.check(L.lib.dslb_sgd_ema_step(L.ptr(p2), L.ptr(gr), L.ptr(b2), n, L.ptr(coef), L.ptr(lrs), 0.01, 0.9, 1e-4, 0,
+                                    L.ptr(t2), c_s, c_t, L.cur_stream()), "sgd+ema")
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and torch.equal(b1, b2) and torch.equal(t1, t2)
