@@ -836,11 +836,21 @@ class FCOSNet:
         for l, (h, w) in enumerate(self.psize):
             wsegs.append(dict(x=self.z["reg"][3][l], dy=self.drc[l], dw=self.rc_dw, N=B, H=h, W=w, Cin=256, Cout=5,
                               ldy=64, dw_rows=5, R=3, S=3, stride=1, pad=1))
-        self.plan_wgrad(wsegs, "head.predictors.wgrad")
-        g_cls_b = self.grad_view("bbox_head.conv_cls.bias")
-        for l, (h, w) in enumerate(self.psize):
-            self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C), side=True, tag="colsum")
-            self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5), side=True, tag="colsum")
+        # order of a layer's weight-gradient launch (side stream) and its dgrad (main stream), DSLB_WGRAD_AFTER_DGRAD:
+        # 0 = wgrad issued first (both start together and time-slice the SMs), 1 = tower wgrads issued behind their dgrad
+        # (they then run under the next layer's GroupNorm backward, which otherwise leaves the tensor pipe idle), 2 = the
+        # predictors' too
+        wg_mode = int(os.environ.get("DSLB_WGRAD_AFTER_DGRAD", "1"))
+
+        def pred_wgrads(wsegs=wsegs):
+            self.plan_wgrad(wsegs, "head.predictors.wgrad")
+            g_cls_b = self.grad_view("bbox_head.conv_cls.bias")
+            for l, (h, w) in enumerate(self.psize):
+                self.add_bwd(self.ew("dslb_colsum", self.dcls[l], g_cls_b, B * h * w, 128, self.C), side=True, tag="colsum")
+                self.add_bwd(self.ew("dslb_colsum", self.drc[l], self.rc_db, B * h * w, 64, 5), side=True, tag="colsum")
+
+        if wg_mode < 2:
+            pred_wgrads()
         # DSLB_GN_BWD_FUSED=1: the dgrad that produces dz of tower layer i also accumulates that layer's GroupNorm-backward
         # group sums in its epilogue (dslb_conv_seg_t::gnb_*), so dslb_gn_bwd is ONE pass over (x, dz) instead of reduce +
         # apply. Opt-in: measured on B200 the 8 epilogue warps become the bound of the dgrad (126 -> 168 us per tower
@@ -862,6 +872,8 @@ class FCOSNet:
             dsegs.append(dict(x=self.drc[l], w=self.rc_wpT, y=self.dz["reg"][l], N=B, H=h, W=w, Cin=64, Cout=256,
                               cout_pad=256, R=3, S=3, stride=1, pad=1, ldc=256, **gnb(1, "reg", 3, l)))
         self.plan_bwd(dsegs, "head.predictors.dgrad")
+        if wg_mode >= 2:
+            pred_wgrads()
         # --- towers, last layer first
         for i in (3, 2, 1, 0):
             self.dy = self.dy2[i & 1]
@@ -887,7 +899,12 @@ class FCOSNet:
                 for l, (h, w) in enumerate(self.psize):
                     x = self.p[l] if i == 0 else self.z[br][i - 1][l]
                     wsegs.append(self.tower[br][i].wseg(x, self.dy[br][l], B, h, w))
-            self.plan_wgrad(wsegs, f"head.tower{i}.wgrad")
+            # wg_mode >= 1: issue the layer's dgrad first, so the side-stream wgrad (ordered behind the main stream's
+            # position at its issue) starts when the dgrad has finished and runs under the NEXT layer's GroupNorm backward
+            # instead of time-slicing the SMs with its own dgrad (8.907 vs 8.971 ms per step, three interleaved pairs)
+            wgrad_late = wg_mode >= 1 and i > 0
+            if not wgrad_late:
+                self.plan_wgrad(wsegs, f"head.tower{i}.wgrad")
             if i > 0:
                 dsegs = []
                 for bi_, br in enumerate(br_names):
@@ -895,6 +912,8 @@ class FCOSNet:
                         dsegs.append(self.tower[br][i].dseg(self.dy[br][l], self.dz[br][l], B, h, w, h, w,
                                                             **gnb(bi_, br, i - 1, l)))
                 self.plan_bwd(dsegs, f"head.tower{i}.dgrad")
+                if wgrad_late:
+                    self.plan_wgrad(wsegs, f"head.tower{i}.wgrad")
             else:
                 # both towers read the FPN output: cls-tower dgrad writes dP, reg-tower dgrad accumulates into it
                 self.plan_bwd([self.tower["cls"][0].dseg(self.dy["cls"][l], self.dp[l], B, h, w, h, w)
