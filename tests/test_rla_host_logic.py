@@ -152,7 +152,15 @@ def test_full_detector_plan_on_the_emulator(backbone):
         net.set_targets(gts, labels, ignores)
         net.run_targets()
         net.run_loss()
+        # bucket_hook contract (the trainer takes |g|^2 bucket by bucket, a data-parallel step all-reduces the range):
+        # when the hook of bucket k runs, everything in [lo, hi) of the flat gradient is final
+        seen = []
+        net.bucket_hook = lambda k, lo, hi: seen.append((k, lo, hi, net.grad[lo:hi].double().pow(2).sum().item()))
         net.backward()
+        final_sq = [net.grad[lo:hi].double().pow(2).sum().item() for _, lo, hi, _ in seen]
+        assert [k for k, *_ in seen] == list(range(len(net.bwd_buckets)))
+        assert [(lo, hi) for _, lo, hi, _ in seen] == [(lo, hi) for _, lo, hi in net.bwd_buckets]
+        assert all(a == b and a > 0 for (_, _, _, a), b in zip(seen, final_sq)), (seen, final_sq)
         got_losses = {k: float(v) for k, v in net.losses().items()}
         ps = [p.float().permute(0, 3, 1, 2).clone() for p in net.p]
         cls = [c.permute(0, 3, 1, 2).clone() for c in net.cls_out]
