@@ -88,10 +88,12 @@ class DSLEngine:
         # forward pass instead of at the head of the backward. Opt-in: measured slower on B200 (8.78 vs 8.70 ms over three
         # interleaved runs) — the 256 MB of memset writes compete with the HBM-bound layer1 convs they overlap.
         # DSLB_PREP_UNDER_FWD=towers: the same, forked where the FCOSHead towers start (tensor-bound launches, HBM idle).
+        # DSLB_PREP_UNDER_FWD=loss: only the two memsets, on the weight-gradient stream BESIDE the loss kernel (which reads
+        # and writes 63 MB and none of those buffers) instead of in front of the backward.
         _m = os.environ.get("DSLB_PREP_UNDER_FWD", "0")
-        self.prep_mode = {"1": "start", "start": "start", "towers": "towers"}.get(_m, "off")
-        self.prep_under_forward = self.prep_mode != "off"
-        self.student.zero_in_bwd = not self.prep_under_forward
+        self.prep_mode = {"1": "start", "start": "start", "towers": "towers", "loss": "loss"}.get(_m, "off")
+        self.prep_under_forward = self.prep_mode in ("start", "towers")
+        self.student.zero_in_bwd = not (self.prep_under_forward or (self.prep_mode == "loss" and two_streams))
         self._prep_ev0, self._prep_ev1 = torch.cuda.Event(), torch.cuda.Event()
         self.fuse_ema = os.environ.get("DSLB_FUSE_EMA", "1") != "0"   # EMA of the trainable regions inside the SGD kernel
         self.student.bucket_hook = self._bucket_sqnorm if (self.world == 1 and self.bucket_sqnorm) else None
@@ -300,8 +302,25 @@ class DSLEngine:
         self._join_prep(targets=False)
         self._join_teacher()
 
+    def _run_loss(self):
+        """Loss + head-output gradients; prep_mode "loss": the gradient-buffer memsets run beside it on the side stream."""
+        if self.prep_mode == "loss" and not self.student.zero_in_bwd and not self.two_streams:
+            self.student.zero_state()      # (instrumented passes serialise the streams)
+            self.student.run_loss()
+        elif self.prep_mode == "loss" and not self.student.zero_in_bwd:
+            main = torch.cuda.current_stream()
+            self._prep_ev0.record(main)
+            self.s3.wait_event(self._prep_ev0)
+            with torch.cuda.stream(self.s3):
+                self.student.zero_state()
+                self._prep_ev1.record(self.s3)
+            self.student.run_loss()
+            main.wait_event(self._prep_ev1)
+        else:
+            self.student.run_loss()
+
     def _phase_b(self):
-        self.student.run_loss()
+        self._run_loss()
         if self.student.bucket_hook is not None:
             L.zero(self.sqnorm)    # the buckets add their shares as they become final (_bucket_sqnorm)
             self._sq_partial = True
@@ -327,7 +346,7 @@ class DSLEngine:
         (join=False: final once the returned side-stream event has been reached, see FCOSNet.backward)."""
         start, end, _, _ = self._bucket_ranges()[k]
         if k == 0:
-            self.student.run_loss()
+            self._run_loss()
         return self.student.backward(self.s3 if self.two_streams else None, start=start, end=end, join=join)
 
     def _phase_c(self):
